@@ -1,0 +1,240 @@
+"""c_oracle.py — ctypes binding of the dependency-free C oracle (oracle/liborb_oracle.so).
+
+ORACLE = test infrastructure.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs import this module; the product never does.
+"""
+import ctypes as ct
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+MAX_LEVELS = 16
+
+
+class Keypoint(ct.Structure):
+    _fields_ = [("x", ct.c_float), ("y", ct.c_float), ("size", ct.c_float), ("angle", ct.c_float),
+                ("response", ct.c_float), ("octave", ct.c_int32), ("class_id", ct.c_int32)]
+
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+DM_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
+CAND_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("score", "<i4")])
+BOX_DTYPE = np.dtype([("cx", "<f8"), ("cy", "<f8"), ("w", "<f8"), ("h", "<f8"), ("class_id", "<i4"), ("pad", "<i4")])
+assert KP_DTYPE.itemsize == 28 and DM_DTYPE.itemsize == 16 and BOX_DTYPE.itemsize == 40
+
+
+class Extractor(ct.Structure):
+    _fields_ = [("nfeatures", ct.c_int), ("nlevels", ct.c_int), ("iniThFAST", ct.c_int), ("minThFAST", ct.c_int),
+                ("scaleFactor", ct.c_double),
+                ("scale", ct.c_float * MAX_LEVELS), ("inv_scale", ct.c_float * MAX_LEVELS),
+                ("sigma2", ct.c_float * MAX_LEVELS), ("inv_sigma2", ct.c_float * MAX_LEVELS),
+                ("nfeat_level", ct.c_int * MAX_LEVELS), ("umax", ct.c_int * 16)]
+
+
+class Trace(ct.Structure):
+    _fields_ = [("pyramid", ct.c_void_p), ("blurred", ct.c_void_p), ("cands", ct.c_void_p),
+                ("cand_cap", ct.c_int32), ("ncands", ct.c_int32 * MAX_LEVELS), ("nkeys", ct.c_int32 * MAX_LEVELS),
+                ("lw", ct.c_int32 * MAX_LEVELS), ("lh", ct.c_int32 * MAX_LEVELS)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liborb_oracle.so")
+    src = [os.path.join(_HERE, f) for f in ("orb_oracle.c", "orb_oracle.h", "stdsort_shim.cpp")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ct.CDLL(build())
+        _lib.orc_fast_atan2.restype = ct.c_float
+        _lib.orc_fast_atan2.argtypes = [ct.c_float, ct.c_float]
+        _lib.orc_ic_angle.restype = ct.c_float
+        _lib.orc_cosf.restype = ct.c_float
+        _lib.orc_sinf.restype = ct.c_float
+        _lib.orc_cosf.argtypes = [ct.c_float]
+        _lib.orc_sinf.argtypes = [ct.c_float]
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ct.c_void_p)
+
+
+class COracle:
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7):
+        self.ex = Extractor()
+        rc = lib().orc_extractor_init(ct.byref(self.ex), nfeatures, ct.c_float(scaleFactor), nlevels, iniThFAST, minThFAST)
+        if rc != 0:
+            raise ValueError("bad extractor parameters")
+        self.nlevels = nlevels
+
+    @property
+    def nfeat(self):
+        return list(self.ex.nfeat_level[:self.nlevels])
+
+    @property
+    def scale(self):
+        return np.array(self.ex.scale[:self.nlevels], dtype=np.float32)
+
+    @property
+    def umax(self):
+        return list(self.ex.umax)
+
+    def level_size(self, w, h, level):
+        lw, lh = ct.c_int(), ct.c_int()
+        lib().orc_level_size(ct.byref(self.ex), w, h, level, ct.byref(lw), ct.byref(lh))
+        return lw.value, lh.value
+
+    def extract(self, gray, cap=20000, trace=False):
+        gray = np.ascontiguousarray(gray, dtype=np.uint8)
+        h, w = gray.shape
+        kps = np.zeros(cap, dtype=KP_DTYPE)
+        desc = np.zeros((cap, 32), dtype=np.uint8)
+        tr = None
+        bufs = None
+        if trace:
+            sizes = [self.level_size(w, h, l) for l in range(self.nlevels)]
+            total = sum(a * b for a, b in sizes)
+            cand_cap = 1 << 17
+            bufs = dict(pyr=np.zeros(total, np.uint8), blur=np.zeros(total, np.uint8),
+                        cands=np.zeros((self.nlevels, cand_cap), CAND_DTYPE))
+            tr = Trace()
+            tr.pyramid, tr.blurred, tr.cands, tr.cand_cap = _p(bufs["pyr"]), _p(bufs["blur"]), _p(bufs["cands"]), cand_cap
+        n = lib().orc_extract(ct.byref(self.ex), _p(gray), w, h, ct.c_size_t(gray.strides[0]), _p(kps), _p(desc), cap,
+                              ct.byref(tr) if tr is not None else None)
+        if n < 0:
+            raise RuntimeError("orc_extract failed: %d" % n)
+        out = dict(kps=kps[:n].copy(), desc=desc[:n].copy())
+        if trace:
+            off = 0
+            pyr, blur, cands = [], [], []
+            for l, (lw, lh) in enumerate(sizes):
+                pyr.append(bufs["pyr"][off:off + lw * lh].reshape(lh, lw).copy())
+                blur.append(bufs["blur"][off:off + lw * lh].reshape(lh, lw).copy())
+                cands.append(bufs["cands"][l, :tr.ncands[l]].copy())
+                off += lw * lh
+            out.update(pyramid=pyr, blurred=blur, cands=cands, nkeys=list(tr.nkeys[:self.nlevels]))
+        return out
+
+    def extract_batch(self, frames, cap=4096, nthreads=0):
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        nf, h, w = frames.shape
+        kps = np.zeros((nf, cap), dtype=KP_DTYPE)
+        desc = np.zeros((nf, cap, 32), dtype=np.uint8)
+        counts = np.zeros(nf, dtype=np.int32)
+        rc = lib().orc_extract_batch(ct.byref(self.ex), _p(frames), nf, w, h, _p(kps), _p(desc), cap, _p(counts), nthreads)
+        if rc != 0:
+            raise RuntimeError("orc_extract_batch failed")
+        return kps, desc, counts
+
+
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().orc_resize_linear(_p(src), src.shape[1], src.shape[0], ct.c_size_t(src.strides[0]), _p(dst), dw, dh, ct.c_size_t(dw))
+    return dst
+
+
+def fast_roi(img, threshold, cap=1 << 16):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    out = np.zeros(cap, CAND_DTYPE)
+    n = lib().orc_fast_roi(_p(img), ct.c_size_t(img.strides[0]), img.shape[1], img.shape[0], threshold, _p(out), cap)
+    return out[:n].copy()
+
+
+def fast_cells(orc, img, cap=1 << 17):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    out = np.zeros(cap, CAND_DTYPE)
+    n = lib().orc_fast_cells(ct.byref(orc.ex), _p(img), ct.c_size_t(img.strides[0]), img.shape[1], img.shape[0], _p(out), cap)
+    return out[:n].copy()
+
+
+def distribute_octtree(cands, minX, maxX, minY, maxY, N):
+    cands = np.ascontiguousarray(cands, dtype=CAND_DTYPE)
+    out = np.zeros(max(len(cands), 1) + 8, CAND_DTYPE)
+    n = lib().orc_distribute_octtree(_p(cands), len(cands), minX, maxX, minY, maxY, N, _p(out), len(out))
+    if n < 0:
+        raise RuntimeError("orc_distribute_octtree failed: %d" % n)
+    return out[:n].copy()
+
+
+def gaussian_blur7(img):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    out = np.zeros_like(img)
+    lib().orc_gaussian_blur7(_p(img), img.shape[1], img.shape[0], ct.c_size_t(img.strides[0]), _p(out), ct.c_size_t(out.strides[0]))
+    return out
+
+
+def fast_atan2(y, x):
+    return float(lib().orc_fast_atan2(ct.c_float(y), ct.c_float(x)))
+
+
+def filter_depth(kps, desc, depth, min_depth=0.3, max_depth=3.0):
+    kps = np.ascontiguousarray(kps, dtype=KP_DTYPE)
+    desc = np.ascontiguousarray(desc, dtype=np.uint8)
+    depth = np.ascontiguousarray(depth, dtype=np.uint16)
+    n = len(kps)
+    okps = np.zeros(max(n, 1), KP_DTYPE)
+    odesc = np.zeros((max(n, 1), 32), np.uint8)
+    oidx = np.zeros(max(n, 1), np.int32)
+    m = lib().orc_filter_depth(_p(kps), _p(desc), n, _p(depth), depth.shape[1], depth.shape[0],
+                               ct.c_size_t(depth.strides[0] // 2), ct.c_float(min_depth), ct.c_float(max_depth),
+                               _p(okps), _p(odesc), _p(oidx))
+    return okps[:m].copy(), odesc[:m].copy(), oidx[:m].copy()
+
+
+def categorize(px, py, boxes):
+    boxes = np.ascontiguousarray(boxes, dtype=BOX_DTYPE)
+    return lib().orc_categorize(ct.c_float(px), ct.c_float(py), _p(boxes), len(boxes))
+
+
+def match(q, t, nthreads=0):
+    q = np.ascontiguousarray(q, dtype=np.uint8)
+    t = np.ascontiguousarray(t, dtype=np.uint8)
+    out = np.zeros(len(q), DM_DTYPE)
+    n = lib().orc_match(_p(q), len(q), _p(t), len(t), _p(out), nthreads)
+    return out[:n].copy()
+
+
+def knn2(q, t, nthreads=0):
+    q = np.ascontiguousarray(q, dtype=np.uint8)
+    t = np.ascontiguousarray(t, dtype=np.uint8)
+    out = np.zeros((len(q), 2), DM_DTYPE)
+    lib().orc_knn2(_p(q), len(q), _p(t), len(t), _p(out), nthreads)
+    return out
+
+
+def synth_gray(seed, frame, w, h):
+    out = np.zeros((h, w), np.uint8)
+    lib().orc_synth_gray(ct.c_uint32(seed), frame, w, h, _p(out), ct.c_size_t(w))
+    return out
+
+
+def synth_depth(seed, frame, w, h):
+    out = np.zeros((h, w), np.uint16)
+    lib().orc_synth_depth(ct.c_uint32(seed), frame, w, h, _p(out), ct.c_size_t(w))
+    return out
+
+
+def synth_descriptors(seed, first_row, nrows):
+    out = np.zeros((nrows, 32), np.uint8)
+    lib().orc_synth_descriptors(ct.c_uint32(seed), ct.c_uint64(first_row), nrows, _p(out))
+    return out
+
+
+def introsort_pairs(cnt, ulx):
+    n = len(cnt)
+    c = np.array(cnt, np.int32)
+    u = np.array(ulx, np.int32)
+    p = np.arange(n, dtype=np.int32)
+    lib().orc_introsort_pairs(_p(c), _p(u), _p(p), n)
+    return list(p)

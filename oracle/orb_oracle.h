@@ -1,0 +1,109 @@
+/* orb_oracle.h — CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * Dependency-free C restatement of the reference's ORB hot path:
+ *   ORB_SLAM3::ORBextractor            reference dynamic_visual_slam/src/ORBextractor.cpp
+ *   cv::BFMatcher(NORM_HAMMING).match  reference frontend.cpp:1123, :614 ; backend.cpp:1072
+ *   Frontend::filterDepth              reference frontend.cpp:457-527
+ *   Backend::categorizeObservation     reference backend.cpp:1011-1029
+ * plus the OpenCV 4.x primitives those call (resize INTER_LINEAR, FAST-9/16, GaussianBlur 7x7,
+ * fastAtan2, cvRound), restated from their published arithmetic and pinned
+ * bit-for-bit against python cv2 4.13.0 in tests/test_oracle_vs_cv2.py and tests/golden/.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * link or call this library.  The product (liborbx.so) never does.
+ */
+#ifndef ORB_ORACLE_H
+#define ORB_ORACLE_H
+#include <stdint.h>
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_MAX_LEVELS 16
+
+/* 28-byte cv::KeyPoint layout */
+typedef struct { float x, y, size, angle, response; int32_t octave, class_id; } orc_keypoint;
+/* 16-byte cv::DMatch layout */
+typedef struct { int32_t queryIdx, trainIdx, imgIdx; float distance; } orc_dmatch;
+/* yolo_msgs bbox: centre + size, fp64 (reference backend.cpp:1017-1020) */
+typedef struct { double cx, cy, w, h; int32_t class_id; int32_t pad; } orc_box;
+
+/* candidate corner inside one level, coordinates relative to the border box (minBorderX,minBorderY) */
+typedef struct { int32_t x, y; int32_t score; } orc_cand;
+
+typedef struct {
+    int nfeatures, nlevels, iniThFAST, minThFAST;
+    double scaleFactor;                       /* double member initialised from a float argument */
+    float scale[ORC_MAX_LEVELS], inv_scale[ORC_MAX_LEVELS];
+    float sigma2[ORC_MAX_LEVELS], inv_sigma2[ORC_MAX_LEVELS];
+    int   nfeat_level[ORC_MAX_LEVELS];
+    int   umax[16];
+} orc_extractor;
+
+/* optional stage trace for stage-wise parity tests; every pointer may be NULL */
+typedef struct {
+    uint8_t  *pyramid;        /* levels concatenated, each tightly packed w*h */
+    uint8_t  *blurred;        /* same layout */
+    orc_cand *cands;          /* per level, capacity cand_cap each: cands + level*cand_cap */
+    int32_t   cand_cap;
+    int32_t   ncands[ORC_MAX_LEVELS];
+    int32_t   nkeys[ORC_MAX_LEVELS];   /* keypoints retained per level */
+    int32_t   lw[ORC_MAX_LEVELS], lh[ORC_MAX_LEVELS];
+} orc_trace;
+
+int  orc_extractor_init(orc_extractor *ex, int nfeatures, float scaleFactor, int nlevels,
+                        int iniThFAST, int minThFAST);
+void orc_level_size(const orc_extractor *ex, int w, int h, int level, int *lw, int *lh);
+
+void orc_resize_linear(const uint8_t *src, int sw, int sh, size_t sstep,
+                       uint8_t *dst, int dw, int dh, size_t dstep);
+/* tables used by the resize (exported so the CUDA host code can be checked against them) */
+void orc_resize_tables(int ssize, int dsize, int32_t *ofs, int16_t *coef /*2 per i*/, int horizontal);
+
+int  orc_fast_roi(const uint8_t *img, size_t step, int w, int h, int threshold,
+                  orc_cand *out, int cap);
+int  orc_fast_cells(const orc_extractor *ex, const uint8_t *img, size_t step, int w, int h,
+                    orc_cand *out, int cap);
+int  orc_distribute_octtree(const orc_cand *cands, int n, int minX, int maxX, int minY, int maxY,
+                            int N, orc_cand *out, int cap);
+float orc_fast_atan2(float y, float x);
+float orc_ic_angle(const uint8_t *img, size_t step, int cx, int cy, const int *umax);
+void orc_gaussian_blur7(const uint8_t *src, int w, int h, size_t sstep, uint8_t *dst, size_t dstep);
+void orc_descriptor(const uint8_t *blur, size_t step, int cx, int cy, float angle_deg, uint8_t *desc32);
+
+/* ORBextractor::operator() ; returns keypoint count, -1 on empty image, -2 capacity */
+int  orc_extract(const orc_extractor *ex, const uint8_t *gray, int w, int h, size_t step,
+                 orc_keypoint *kps, uint8_t *desc, int cap, orc_trace *trace);
+/* frame-parallel (OpenMP) batch, used by the CPU baseline: frames tightly packed */
+int  orc_extract_batch(const orc_extractor *ex, const uint8_t *gray, int nframes, int w, int h,
+                       orc_keypoint *kps, uint8_t *desc, int cap_per_frame, int32_t *counts, int nthreads);
+
+int  orc_filter_depth(const orc_keypoint *kps, const uint8_t *desc, int n,
+                      const uint16_t *depth, int dw, int dh, size_t dstep_elems,
+                      float min_depth, float max_depth,
+                      orc_keypoint *okps, uint8_t *odesc, int32_t *orig_idx);
+/* first box containing the pixel → class id, -1 = "unlabeled" */
+int  orc_categorize(float px, float py, const orc_box *boxes, int nboxes);
+
+int  orc_hamming(const uint8_t *a, const uint8_t *b);
+/* BFMatcher.match: one DMatch per query (k=1), lowest trainIdx on ties */
+int  orc_match(const uint8_t *q, int nq, const uint8_t *t, int nt, orc_dmatch *out, int nthreads);
+/* knnMatch k=2: out[2*i], out[2*i+1]; trainIdx=-1 when fewer than k train rows */
+int  orc_knn2(const uint8_t *q, int nq, const uint8_t *t, int nt, orc_dmatch *out, int nthreads);
+
+/* seeded integer-only synthetic inputs (identical bytes on host and device) */
+void orc_synth_gray(uint32_t seed, int frame, int w, int h, uint8_t *out, size_t step);
+void orc_synth_depth(uint32_t seed, int frame, int w, int h, uint16_t *out, size_t step_elems);
+void orc_synth_descriptors(uint32_t seed, uint64_t first_row, int nrows, uint8_t *out);
+
+/* libstdc++ std::sort emulation on (count, ULx) keys, exported for its own test */
+void orc_introsort_pairs(int32_t *cnt, int32_t *ulx, int32_t *payload, int n);
+
+float orc_cosf(float x);
+float orc_sinf(float x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
