@@ -1,0 +1,235 @@
+// k_describe.cu — intensity-centroid orientation + rBRIEF-256 + keypoint assembly, one warp per keypoint.
+// Replaces IC_Angle / computeOrientation (reference ORBextractor.cpp:76-103, 471-478), computeOrbDescriptor /
+// computeDescriptors (:106-146, 1077-1084), the tail of ComputeKeyPointsOctTree (:874-890) and the
+// per-level assembly loop of operator() (:1123-1164).
+//
+// Floating point on this stage must round exactly like the reference's x86-64 build:
+//   * cv::fastAtan2: fp32 polynomial, every operation rounded on its own (no FMA)   — SURVEY App. A.4
+//   * cosf/sinf: glibc's algorithm (double-precision range reduction + polynomial, rounded once to
+//     fp32) restated below; pinned against glibc over every float32 angle in [0,360] degrees
+//   * x*b + y*a: fp32 multiply, fp32 add, cvRound = round-half-even                  — SURVEY App. A.5
+#include "orbx_internal.h"
+
+__device__ __constant__ signed char c_pattern[1024] = {
+#include "../../include/orbx_pattern.inc"
+};
+__device__ __constant__ int c_umax[16];
+
+void upload_umax(const int *umax) { cudaMemcpyToSymbol(c_umax, umax, sizeof(int) * 16); }
+
+// ---- glibc sinf/cosf (sysdeps/ieee754/flt-32/s_sincosf.h algorithm, |x| < 120) ----
+__device__ __forceinline__ float glibc_sincos_poly(double x, double x2, int neg, int n)
+{
+    // neg selects the table entry that computes -cos for free
+    if ((n & 1) == 0) {
+        const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
+        const double x3 = __dmul_rn(x, x2);
+        const double s1 = __dadd_rn(S2, __dmul_rn(x2, S3));
+        const double x7 = __dmul_rn(x3, x2);
+        const double s = __dadd_rn(x, __dmul_rn(x3, S1));
+        return __double2float_rn(__dadd_rn(s, __dmul_rn(x7, s1)));
+    } else {
+        const double sg = neg ? -1.0 : 1.0;
+        const double C0 = sg * 0x1p0, C1 = sg * -0x1.ffffffd0c621cp-2, C2 = sg * 0x1.55553e1068f19p-5;
+        const double C3 = sg * -0x1.6c087e89a359dp-10, C4 = sg * 0x1.99343027bf8c3p-16;
+        const double x4 = __dmul_rn(x2, x2);
+        const double c2 = __dadd_rn(C3, __dmul_rn(x2, C4));
+        const double c1 = __dadd_rn(C0, __dmul_rn(x2, C1));
+        const double x6 = __dmul_rn(x4, x2);
+        const double c = __dadd_rn(c1, __dmul_rn(x4, C2));
+        return __double2float_rn(__dadd_rn(c, __dmul_rn(x6, c2)));
+    }
+}
+__device__ __forceinline__ unsigned abstop12(float f) { return (__float_as_uint(f) >> 20) & 0x7ff; }
+
+__device__ float glibc_cosf(float y)
+{
+    double x = (double)y;
+    if (abstop12(y) < 0x3f4u) {                       // |y| < ~pi/4 (top-12-bit compare, as glibc)
+        if (abstop12(y) < abstop12(0x1p-12f)) return 1.0f;
+        return glibc_sincos_poly(x, __dmul_rn(x, x), 0, 1);
+    }
+    const double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);
+    const int n = (__double2int_rz(r) + 0x800000) >> 24;
+    x = __dadd_rn(x, -__dmul_rn((double)n, 0x1.921FB54442D18p0));
+    const double s = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+    return glibc_sincos_poly(__dmul_rn(x, s), __dmul_rn(x, x), (n & 2) ? 1 : 0, n ^ 1);
+}
+__device__ float glibc_sinf(float y)
+{
+    double x = (double)y;
+    if (abstop12(y) < 0x3f4u) {
+        if (abstop12(y) < abstop12(0x1p-12f)) return y;
+        return glibc_sincos_poly(x, __dmul_rn(x, x), 0, 0);
+    }
+    const double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);
+    const int n = (__double2int_rz(r) + 0x800000) >> 24;
+    x = __dadd_rn(x, -__dmul_rn((double)n, 0x1.921FB54442D18p0));
+    const double s = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+    return glibc_sincos_poly(__dmul_rn(x, s), __dmul_rn(x, x), (n & 2) ? 1 : 0, n);
+}
+
+// ---- cv::fastAtan2, scalar path ----
+__device__ float cv_fast_atan2(float y, float x)
+{
+    const float scale = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = __fmul_rn(0.9997878412794807f, scale), p3 = __fmul_rn(-0.3258083974640975f, scale);
+    const float p5 = __fmul_rn(0.1555786518463281f, scale), p7 = __fmul_rn(-0.04432655554792128f, scale);
+    const float eps = (float)2.2204460492503131e-16;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+struct DescParams {
+    const uint8_t *l0; size_t l0_step, l0_fstride;
+    const uint8_t *pyr; size_t pyr_slab;
+    const uint8_t *blur; size_t blur_slab;
+    const uint32_t *sel; int sel_slab;
+    const int32_t *nsel;
+    orbx_keypoint *kps; uint8_t *desc; int cap;     // per-frame capacity
+    int32_t *counts;
+    int32_t *status;
+};
+
+#define DESC_WARPS 4
+
+__global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescParams P, const FrameGeom *__restrict__ G)
+{
+    const int f = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int nl = G->nlevels;
+    int gidx = blockIdx.x * DESC_WARPS + (threadIdx.x >> 5);
+    // locate (level, index in level): levels are concatenated in order (ORBextractor.cpp:1123)
+    int level = -1, k = gidx, total = 0;
+    for (int l = 0; l < nl; l++) {
+        const int c = P.nsel[f * nl + l];
+        if (level < 0) { if (k < c) level = l; else k -= c; }
+        total += c;
+    }
+    if (gidx == 0 && lane == 0) {
+        P.counts[f] = total <= P.cap ? total : 0;
+        if (total > P.cap) atomicOr(P.status, ORBX_DS_KP_OVERFLOW);
+    }
+    if (level < 0 || total > P.cap) return;
+    const LevelGeom &g = G->lv[level];
+    const uint32_t c = P.sel[(size_t)f * P.sel_slab + g.sel_off + k];
+    // pt += (minBorderX, minBorderY) — ORBextractor.cpp:886-887; integer-valued, cvRound is the identity
+    const int cx = orbx_px(c) + ORBX_BORDER, cy = orbx_py(c) + ORBX_BORDER;
+    const uint8_t *img; size_t step;
+    if (level == 0) { img = P.l0 + (size_t)f * P.l0_fstride; step = P.l0_step; }
+    else { img = P.pyr + (size_t)f * P.pyr_slab + g.off; step = (size_t)g.pitch; }
+
+    // ---- IC_Angle: lane = column u+15, loop rows v ----
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int u = lane - ORBX_HALF_PATCH;
+        const int au = u < 0 ? -u : u;
+        const uint8_t *ctr = img + (size_t)cy * step + cx + u;
+        for (int v = -ORBX_HALF_PATCH; v <= ORBX_HALF_PATCH; v++) {
+            const int av = v < 0 ? -v : v;
+            if (au <= c_umax[av]) {
+                const int val = __ldg(ctr + (ptrdiff_t)v * (ptrdiff_t)step);
+                m10 += u * val; m01 += v * val;
+            }
+        }
+    }
+    m10 = __reduce_add_sync(0xffffffffu, m10);
+    m01 = __reduce_add_sync(0xffffffffu, m01);
+    const float angle = cv_fast_atan2((float)m01, (float)m10);
+
+    // ---- rBRIEF: lane i computes descriptor byte i ----
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    const float ang = __fmul_rn(angle, factorPI);
+    const float a = glibc_cosf(ang), b = glibc_sinf(ang);
+    const uint8_t *bctr = P.blur + (size_t)f * P.blur_slab + g.boff + (size_t)cy * g.bpitch + cx;
+    const int bstep = g.bpitch;
+    const signed char *pat = c_pattern + lane * 32;
+    int val = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float x0 = (float)pat[4 * j], y0 = (float)pat[4 * j + 1], x1 = (float)pat[4 * j + 2], y1 = (float)pat[4 * j + 3];
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int t0 = __ldg(bctr + r0 * bstep + c0), t1 = __ldg(bctr + r1 * bstep + c1);
+        val |= (t0 < t1) << j;
+    }
+    uint8_t *drow = P.desc + ((size_t)f * P.cap + gidx) * ORBX_DESC_BYTES;
+    drow[lane] = (uint8_t)val;
+    if (lane == 0) {
+        orbx_keypoint kp;
+        kp.x = (float)cx; kp.y = (float)cy;
+        if (level != 0) { kp.x = __fmul_rn(kp.x, g.scale); kp.y = __fmul_rn(kp.y, g.scale); }   // :1147-1149
+        kp.size = g.size; kp.angle = angle; kp.response = (float)orbx_ps(c);
+        kp.octave = level; kp.class_id = -1;
+        P.kps[(size_t)f * P.cap + gidx] = kp;
+    }
+}
+
+void launch_describe_to(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride,
+                        orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts)
+{
+    DescParams P;
+    P.l0 = l0; P.l0_step = l0_step; P.l0_fstride = l0_fstride;
+    P.pyr = h->d_pyr; P.pyr_slab = h->pyr_slab;
+    P.blur = h->d_blur; P.blur_slab = h->blur_slab;
+    P.sel = h->d_sel; P.sel_slab = h->geo.sel_entries; P.nsel = h->d_nsel;
+    P.kps = d_kps; P.desc = d_desc; P.cap = cap; P.counts = d_counts; P.status = h->d_status;
+    const int maxk = h->geo.sel_entries < cap ? h->geo.sel_entries : cap;
+    dim3 grid((maxk + DESC_WARPS - 1) / DESC_WARPS, nframes);
+    k_describe<<<grid, DESC_WARPS * 32, 0, h->stream>>>(P, h->d_geo);
+    h->launches++;
+}
+
+// ---- device self-tests of the floating-point restatements ----
+__global__ void k_test_trig(const float *in, int n, float *oc, float *os)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { oc[i] = glibc_cosf(in[i]); os[i] = glibc_sinf(in[i]); }
+}
+__global__ void k_test_atan2(const float *y, const float *x, int n, float *o)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = cv_fast_atan2(y[i], x[i]);
+}
+// sum of the result bit patterns over angle_deg bit patterns [first, last]
+__global__ void k_trig_checksum(uint32_t first, uint32_t last, unsigned long long *sums)
+{
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    unsigned long long sc = 0, ss = 0;
+    const unsigned long long total = (unsigned long long)last - first + 1ull;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float deg = __uint_as_float(first + (uint32_t)i);
+        const float rad = __fmul_rn(deg, factorPI);
+        sc += __float_as_uint(glibc_cosf(rad));
+        ss += __float_as_uint(glibc_sinf(rad));
+    }
+    for (int o = 16; o > 0; o >>= 1) { sc += __shfl_xor_sync(0xffffffffu, sc, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&sums[0], sc); atomicAdd(&sums[1], ss); }
+}
+void launch_test_trig(orbx_handle *h, const float *d_in, int n, float *d_c, float *d_s)
+{
+    k_test_trig<<<(n + 255) / 256, 256, 0, h->stream>>>(d_in, n, d_c, d_s); h->launches++;
+}
+void launch_test_atan2(orbx_handle *h, const float *d_y, const float *d_x, int n, float *d_o)
+{
+    k_test_atan2<<<(n + 255) / 256, 256, 0, h->stream>>>(d_y, d_x, n, d_o); h->launches++;
+}
+void launch_trig_checksum(orbx_handle *h, uint32_t first, uint32_t last, unsigned long long *d_sums)
+{
+    k_trig_checksum<<<h->sm_count * 8, 256, 0, h->stream>>>(first, last, d_sums); h->launches++;
+}

@@ -1,0 +1,323 @@
+// k_match.cu — brute-force Hamming matching of 256-bit descriptors (k = 1 / 2, threshold and ratio epilogues).
+// Replaces cv::BFMatcher(NORM_HAMMING).match at reference frontend.cpp:1123 and :614 (+ the
+// `distance < 50` loops :1126-1132, :617-623) and the per-pair match() loop of
+// Backend::associateObservation (backend.cpp:1068-1077).  Semantics: SURVEY App. A.8 — integer popcount
+// distance, ties to the lowest trainIdx, one DMatch per query in query order.
+//
+// This is integer-issue-bound work (8 LOP3 + 8 POPC per pair), not a dense FP contraction: no
+// tensor cores.  Layout: one thread owns one query descriptor in registers (8 x u32); train rows
+// are staged in shared memory in 128-bit pieces and broadcast to the warp; per pair the thread does
+// 8 XOR + 8 POPC + 7 IADD and a 3-instruction top-2 update on the packed key
+// (distance << 22 | row), whose unsigned order IS the (distance, index) lexicographic order, so the
+// lowest-index tie-break needs no extra compare.  The train set is split over gridDim.y; partial
+// top-2 keys are merged (lexicographic min, 64-bit keys with global row numbers) by the epilogue
+// kernel, which also applies the threshold / ratio test and compacts in query order.
+#include "orbx_internal.h"
+#include <float.h>
+
+#define MT_THREADS 128
+#define MT_TILE 256                 // train rows staged per shared-memory tile (8 KB)
+#define MT_KEY_SHIFT 22
+#define MT_INF 0xFFFFFFFFu
+
+struct MatchParams {
+    const uint8_t *q; const int32_t *nq_arr; int nq_imm; size_t q_stride;     // stride between problems' query sets (bytes)
+    const uint8_t *t; const int32_t *nt_arr; int nt_imm; size_t t_stride;
+    const int32_t *qsel, *tsel;     // problem -> set index (nullable: identity)
+    unsigned long long *part;        // [problem][split][nq_max][2] 64-bit keys (dist<<32 | global row)
+    int nq_max, nsplit, rows_per_split;
+    uint32_t row_base;               // global index of train row 0 (database shards)
+};
+
+__device__ __forceinline__ int hamming256(const uint32_t q[8], const uint4 a, const uint4 b)
+{
+    return __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w) +
+           __popc(q[4] ^ b.x) + __popc(q[5] ^ b.y) + __popc(q[6] ^ b.z) + __popc(q[7] ^ b.w);
+}
+
+__global__ void __launch_bounds__(MT_THREADS) k_match_partial(MatchParams P)
+{
+    __shared__ uint4 s_t[MT_TILE * 2];
+    const int prob = blockIdx.z;
+    const int qs = P.qsel ? P.qsel[prob] : prob, ts = P.tsel ? P.tsel[prob] : prob;
+    const int nq = P.nq_arr ? P.nq_arr[qs] : P.nq_imm;
+    const int nt = P.nt_arr ? P.nt_arr[ts] : P.nt_imm;
+    const int qi = blockIdx.x * MT_THREADS + threadIdx.x;
+    if (blockIdx.x * MT_THREADS >= nq) return;
+    const int r0 = blockIdx.y * P.rows_per_split;
+    const int r1 = min(nt, r0 + P.rows_per_split);
+    const uint8_t *qbase = P.q + (size_t)qs * P.q_stride;
+    const uint4 *tbase = reinterpret_cast<const uint4 *>(P.t + (size_t)ts * P.t_stride);
+    uint32_t q[8];
+    {
+        const uint4 *qp = reinterpret_cast<const uint4 *>(qbase + (size_t)(qi < nq ? qi : 0) * ORBX_DESC_BYTES);
+        const uint4 a = __ldg(qp), b = __ldg(qp + 1);
+        q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
+    }
+    uint32_t m0 = MT_INF, m1 = MT_INF;
+    for (int base = r0; base < r1; base += MT_TILE) {
+        const int cnt = min(MT_TILE, r1 - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt * 2; i += MT_THREADS) s_t[i] = __ldg(tbase + (size_t)base * 2 + i);
+        __syncthreads();
+        uint32_t key = (uint32_t)(base - r0);
+#pragma unroll 4
+        for (int j = 0; j < cnt; j++, key++) {
+            const int d = hamming256(q, s_t[2 * j], s_t[2 * j + 1]);
+            const uint32_t kk = ((uint32_t)d << MT_KEY_SHIFT) + key;
+            m1 = min(m1, max(m0, kk));
+            m0 = min(m0, kk);
+        }
+    }
+    if (qi < nq) {
+        unsigned long long *o = P.part + (((size_t)prob * P.nsplit + blockIdx.y) * P.nq_max + qi) * 2;
+        const unsigned long long gb = (unsigned long long)P.row_base + (unsigned long long)r0;
+        o[0] = m0 == MT_INF ? ~0ull : (((unsigned long long)(m0 >> MT_KEY_SHIFT) << 32) | (gb + (m0 & ((1u << MT_KEY_SHIFT) - 1))));
+        o[1] = m1 == MT_INF ? ~0ull : (((unsigned long long)(m1 >> MT_KEY_SHIFT) << 32) | (gb + (m1 & ((1u << MT_KEY_SHIFT) - 1))));
+    }
+}
+
+struct MatchEpiParams {
+    const unsigned long long *part; int nq_max, nsplit;
+    const int32_t *nq_arr; int nq_imm; const int32_t *nt_arr; int nt_imm;
+    const int32_t *qsel, *tsel;
+    int k; float max_dist; int ratio_num;       // ratio = ratio_num / 1024, 0 = off
+    orbx_dmatch *out; size_t out_stride;         // entries per problem
+    int32_t *n_out;
+    orbx_top2 *top2;                             // nullable: raw per-query top-2 instead of DMatch
+};
+
+__device__ __forceinline__ void top2_insert(unsigned long long &a, unsigned long long &b, unsigned long long v)
+{
+    // keep the two smallest of {a, b, v}, a <= b
+    const unsigned long long hi = a > v ? a : v;
+    a = a < v ? a : v;
+    b = b < hi ? b : hi;
+}
+
+__global__ void __launch_bounds__(256) k_match_epilogue(MatchEpiParams P)
+{
+    __shared__ int s_warp[9];
+    __shared__ int s_base;
+    const int prob = blockIdx.x;
+    const int qs = P.qsel ? P.qsel[prob] : prob, ts = P.tsel ? P.tsel[prob] : prob;
+    const int nq = P.nq_arr ? P.nq_arr[qs] : P.nq_imm;
+    const int nt = P.nt_arr ? P.nt_arr[ts] : P.nt_imm;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    orbx_dmatch *out = P.out ? P.out + (size_t)prob * P.out_stride : nullptr;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int base = 0; base < nq; base += 256) {
+        const int qi = base + threadIdx.x;
+        unsigned long long a = ~0ull, b = ~0ull;
+        if (qi < nq && nt > 0) {
+            for (int s = 0; s < P.nsplit; s++) {
+                const unsigned long long *p = P.part + (((size_t)prob * P.nsplit + s) * P.nq_max + qi) * 2;
+                top2_insert(a, b, p[0]);
+                top2_insert(a, b, p[1]);
+            }
+        }
+        if (P.top2) {
+            if (qi < nq) {
+                orbx_top2 r;
+                r.dist0 = a == ~0ull ? 0xFFFFFFFFu : (uint32_t)(a >> 32); r.idx0 = (uint32_t)a;
+                r.dist1 = b == ~0ull ? 0xFFFFFFFFu : (uint32_t)(b >> 32); r.idx1 = (uint32_t)b;
+                P.top2[(size_t)prob * P.nq_max + qi] = r;
+            }
+            continue;
+        }
+        const int d0 = (int)(a >> 32), d1 = (int)(b >> 32);
+        const bool has0 = a != ~0ull, has1 = b != ~0ull;
+        if (P.k == 2 && P.ratio_num <= 0) {                 // knnMatch(k=2): two entries per query
+            if (qi < nq) {
+                orbx_dmatch m;
+                m.queryIdx = qi; m.imgIdx = 0;
+                m.trainIdx = has0 ? (int)(uint32_t)a : -1; m.distance = has0 ? (float)d0 : 0.f; out[2 * qi] = m;
+                m.trainIdx = has1 ? (int)(uint32_t)b : -1; m.distance = has1 ? (float)d1 : 0.f; out[2 * qi + 1] = m;
+            }
+            continue;
+        }
+        bool keep = qi < nq && has0;
+        if (keep && P.max_dist > 0.f) keep = (float)d0 < P.max_dist;
+        if (keep && P.k == 2) keep = has1 && (d0 * 1024 < P.ratio_num * d1);
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        if (threadIdx.x == 0) { int run = 0; for (int w = 0; w < 8; w++) { const int c = s_warp[w]; s_warp[w] = run; run += c; } s_warp[8] = run; }
+        __syncthreads();
+        if (keep) {
+            const int o = s_base + s_warp[wid] + __popc(bal & ((1u << lane) - 1u));
+            orbx_dmatch m;
+            m.queryIdx = qi; m.trainIdx = (int)(uint32_t)a; m.imgIdx = 0; m.distance = (float)d0;
+            out[o] = m;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += s_warp[8];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && P.n_out) {
+        if (P.top2) P.n_out[prob] = nq;
+        else if (P.k == 2 && P.ratio_num <= 0) P.n_out[prob] = 2 * nq;
+        else P.n_out[prob] = s_base;
+    }
+}
+
+// choose the train split so the grid covers the machine a few times over
+static int pick_split(orbx_handle *h, int nq_max, int nt_max, int nproblems, int *rows_per_split)
+{
+    const int qtiles = (nq_max + MT_THREADS - 1) / MT_THREADS;
+    const long ctas_wanted = (long)h->sm_count * 8;
+    long split = (ctas_wanted + (long)qtiles * nproblems - 1) / ((long)qtiles * nproblems);
+    const long max_split = (nt_max + MT_TILE - 1) / MT_TILE;
+    if (split > max_split) split = max_split;
+    if (split < 1) split = 1;
+    long rps = (nt_max + split - 1) / split;
+    rps = (rps + MT_TILE - 1) / MT_TILE * MT_TILE;
+    if (rps > (1 << MT_KEY_SHIFT)) rps = 1 << MT_KEY_SHIFT;
+    split = (nt_max + rps - 1) / rps;
+    if (split < 1) split = 1;
+    *rows_per_split = (int)rps;
+    return (int)split;
+}
+
+static int ensure_part(orbx_handle *h, size_t entries)
+{
+    if (entries <= h->mpart_cap) return 0;
+    if (h->d_mpart) cudaFree(h->d_mpart);
+    h->d_mpart = nullptr; h->mpart_cap = 0;
+    if (cudaMalloc(&h->d_mpart, entries * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    h->mpart_cap = entries;
+    return 0;
+}
+
+int launch_match_core(orbx_handle *h, const uint8_t *d_q, const int32_t *d_nq, int nq_max, size_t q_stride,
+                      const uint8_t *d_t, const int32_t *d_nt, int nt_max, size_t t_stride,
+                      const int32_t *d_qsel, const int32_t *d_tsel, int nproblems, uint32_t row_base,
+                      int k, float max_dist, int ratio_num, orbx_dmatch *d_out, size_t out_stride, int32_t *d_n_out,
+                      orbx_top2 *d_top2)
+{
+    if (nproblems <= 0 || nq_max <= 0) return 0;
+    int rps = MT_TILE;
+    const int nsplit = nt_max > 0 ? pick_split(h, nq_max, nt_max, nproblems, &rps) : 1;
+    if (ensure_part(h, (size_t)nproblems * nsplit * nq_max * 2) != 0) return -1;
+    if (nt_max > 0) {
+        MatchParams P;
+        P.q = d_q; P.nq_arr = d_nq; P.nq_imm = nq_max; P.q_stride = q_stride;
+        P.t = d_t; P.nt_arr = d_nt; P.nt_imm = nt_max; P.t_stride = t_stride;
+        P.qsel = d_qsel; P.tsel = d_tsel;
+        P.part = (unsigned long long *)h->d_mpart; P.nq_max = nq_max; P.nsplit = nsplit; P.rows_per_split = rps;
+        P.row_base = row_base;
+        dim3 grid((nq_max + MT_THREADS - 1) / MT_THREADS, nsplit, nproblems);
+        // every slot the epilogue reads (qi < nq, all splits) is written by the partial kernel; splits that
+        // start beyond a problem's own nt write the "empty" key
+        k_match_partial<<<grid, MT_THREADS, 0, h->stream>>>(P);
+        h->launches++;
+    }
+    MatchEpiParams E;
+    E.part = (const unsigned long long *)h->d_mpart; E.nq_max = nq_max; E.nsplit = nsplit;
+    E.nq_arr = d_nq; E.nq_imm = nq_max; E.nt_arr = d_nt; E.nt_imm = nt_max;
+    E.qsel = d_qsel; E.tsel = d_tsel;
+    E.k = k; E.max_dist = max_dist; E.ratio_num = ratio_num;
+    E.out = d_out; E.out_stride = out_stride; E.n_out = d_n_out; E.top2 = d_top2;
+    k_match_epilogue<<<nproblems, 256, 0, h->stream>>>(E);
+    h->launches++;
+    return 0;
+}
+
+// ---- merge of per-shard top-2 after the all-gather ----
+__global__ void k_merge_top2(const orbx_top2 *parts, int nshards, int nq, orbx_top2 *out)
+{
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    unsigned long long a = ~0ull, b = ~0ull;
+    for (int s = 0; s < nshards; s++) {
+        const orbx_top2 p = parts[(size_t)s * nq + qi];
+        if (p.dist0 != 0xFFFFFFFFu) top2_insert(a, b, ((unsigned long long)p.dist0 << 32) | p.idx0);
+        if (p.dist1 != 0xFFFFFFFFu) top2_insert(a, b, ((unsigned long long)p.dist1 << 32) | p.idx1);
+    }
+    orbx_top2 r;
+    r.dist0 = a == ~0ull ? 0xFFFFFFFFu : (uint32_t)(a >> 32); r.idx0 = (uint32_t)a;
+    r.dist1 = b == ~0ull ? 0xFFFFFFFFu : (uint32_t)(b >> 32); r.idx1 = (uint32_t)b;
+    out[qi] = r;
+}
+void launch_merge_top2(orbx_handle *h, const orbx_top2 *d_parts, int nshards, int nq, orbx_top2 *d_out)
+{
+    if (nq <= 0) return;
+    k_merge_top2<<<(nq + 127) / 128, 128, 0, h->stream>>>(d_parts, nshards, nq, d_out);
+    h->launches++;
+}
+
+// ---- radius query: every (query, row) with distance < max_dist (backend.cpp:1074-1076) ----
+// one thread per query over a row split; hits are appended through a global counter and sorted by
+// (queryIdx, trainIdx) on the host side of the ABI (the hit list is tiny: candidates within 50 bits).
+struct RadiusParams { const uint8_t *q; int nq; const uint8_t *t; int nt; int rows_per_split; uint32_t row_base;
+                      float max_dist; orbx_dmatch *out; int cap; int32_t *n_out; };
+__global__ void __launch_bounds__(MT_THREADS) k_match_radius(RadiusParams P)
+{
+    __shared__ uint4 s_t[MT_TILE * 2];
+    const int qi = blockIdx.x * MT_THREADS + threadIdx.x;
+    const int r0 = blockIdx.y * P.rows_per_split, r1 = min(P.nt, r0 + P.rows_per_split);
+    uint32_t q[8];
+    {
+        const uint4 *qp = reinterpret_cast<const uint4 *>(P.q + (size_t)(qi < P.nq ? qi : 0) * ORBX_DESC_BYTES);
+        const uint4 a = __ldg(qp), b = __ldg(qp + 1);
+        q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
+    }
+    const uint4 *tbase = reinterpret_cast<const uint4 *>(P.t);
+    for (int base = r0; base < r1; base += MT_TILE) {
+        const int cnt = min(MT_TILE, r1 - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt * 2; i += MT_THREADS) s_t[i] = __ldg(tbase + (size_t)base * 2 + i);
+        __syncthreads();
+        if (qi >= P.nq) continue;
+        for (int j = 0; j < cnt; j++) {
+            const int d = hamming256(q, s_t[2 * j], s_t[2 * j + 1]);
+            if ((float)d < P.max_dist) {
+                const int o = atomicAdd(P.n_out, 1);
+                if (o < P.cap) { orbx_dmatch m; m.queryIdx = qi; m.trainIdx = (int)(P.row_base + (uint32_t)(base + j)); m.imgIdx = 0; m.distance = (float)d; P.out[o] = m; }
+            }
+        }
+    }
+}
+void launch_match_radius(orbx_handle *h, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, uint32_t row_base,
+                         float max_dist, orbx_dmatch *d_out, int cap, int32_t *d_n_out)
+{
+    if (nq <= 0 || nt <= 0) return;
+    int rps;
+    const int nsplit = pick_split(h, nq, nt, 1, &rps);
+    RadiusParams P = { d_q, nq, d_t, nt, rps, row_base, max_dist, d_out, cap, d_n_out };
+    dim3 grid((nq + MT_THREADS - 1) / MT_THREADS, nsplit);
+    k_match_radius<<<grid, MT_THREADS, 0, h->stream>>>(P);
+    h->launches++;
+}
+
+// ---- POPC issue-rate microbenchmark: the denominator of the matching roofline ----
+__global__ void k_popc_bench(uint32_t *out, int iters)
+{
+    uint32_t a = threadIdx.x * 2654435761u + blockIdx.x, b = a ^ 0x9E3779B9u, c = a + 0x7F4A7C15u, d = ~a;
+    uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            s0 += __popc(a ^ s1); s1 += __popc(b ^ s2); s2 += __popc(c ^ s3); s3 += __popc(d ^ s0);
+        }
+    }
+    if ((s0 ^ s1 ^ s2 ^ s3) == 0x12345678u) out[0] = s0;
+}
+double run_popc_bench(orbx_handle *h)
+{
+    uint32_t *d = nullptr;
+    if (cudaMalloc(&d, 4) != cudaSuccess) return 0.0;
+    const int iters = 4096, blocks = h->sm_count * 8, threads = 256;
+    k_popc_bench<<<blocks, threads, 0, h->stream>>>(d, 64);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, h->stream);
+    k_popc_bench<<<blocks, threads, 0, h->stream>>>(d, iters);
+    cudaEventRecord(e1, h->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    h->launches += 2;
+    const double popc = (double)blocks * threads * (double)iters * 32.0;
+    return ms > 0 ? popc / (ms * 1e-3) : 0.0;
+}

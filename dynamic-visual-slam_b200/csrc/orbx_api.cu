@@ -1,0 +1,766 @@
+// orbx_api.cu — the C ABI (include/orbx.h): handle, geometry, arenas, pipeline orchestration.
+// Host-side restatements cited inline: ORBextractor ctor (reference ORBextractor.cpp:409-469),
+// ComputePyramid sizes (:1173-1174), the cell grid (:789-803), quadtree roots (:559-560) and the
+// coefficient tables cv::resize builds for INTER_LINEAR.
+#include "orbx_internal.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+static std::string g_create_err;
+static inline int cv_round_f(float v) { return (int)lrintf(v); }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" const char *orbx_version(void) { return "orbx 0.1 (sm_100a)"; }
+
+extern "C" void orbx_default_params(orbx_params *p)
+{
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->nfeatures = 1000; p->scale_factor = 1.2f; p->nlevels = 8; p->ini_th_fast = 20; p->min_th_fast = 7;   // frontend.cpp:205-211
+    p->depth_min = 0.3f; p->depth_max = 3.0f;                                                             // frontend.cpp:241-242
+    p->max_width = 1280; p->max_height = 720; p->max_batch = 1; p->max_keypoints = 0; p->cand_divisor = 0; p->device = 0;
+}
+
+extern "C" const char *orbx_last_error(const orbx_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+// ---- ORBextractor ctor tables — ORBextractor.cpp:409-469 ----
+static void build_tables(orbx_handle *h)
+{
+    const orbx_params &p = h->prm;
+    const double scaleFactor = (double)p.scale_factor;
+    h->scale[0] = 1.0f; h->sigma2[0] = 1.0f;
+    for (int i = 1; i < p.nlevels; i++) {
+        h->scale[i] = (float)((double)h->scale[i - 1] * scaleFactor);
+        h->sigma2[i] = h->scale[i] * h->scale[i];
+    }
+    for (int i = 0; i < p.nlevels; i++) { h->inv_scale[i] = 1.0f / h->scale[i]; h->inv_sigma2[i] = 1.0f / h->sigma2[i]; }
+    const float factor = (float)(1.0f / scaleFactor);
+    float nDesired = p.nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)p.nlevels));
+    int sum = 0;
+    for (int l = 0; l < p.nlevels - 1; l++) { h->nfeat[l] = cv_round_f(nDesired); sum += h->nfeat[l]; nDesired *= factor; }
+    h->nfeat[p.nlevels - 1] = std::max(p.nfeatures - sum, 0);
+    int v, v0;
+    const int vmax = (int)floorf(ORBX_HALF_PATCH * sqrtf(2.f) / 2 + 1), vmin = (int)ceilf(ORBX_HALF_PATCH * sqrtf(2.f) / 2);
+    const double hp2 = ORBX_HALF_PATCH * ORBX_HALF_PATCH;
+    for (v = 0; v <= vmax; ++v) h->umax[v] = (int)lrint(sqrt(hp2 - v * v));
+    for (v = ORBX_HALF_PATCH, v0 = 0; v >= vmin; --v) {
+        while (h->umax[v0] == h->umax[v0 + 1]) ++v0;
+        h->umax[v] = v0; ++v0;
+    }
+}
+
+// cv::resize INTER_LINEAR coefficient tables
+static void resize_table(int ssize, int dsize, bool horizontal, ResizeTab *out)
+{
+    const double inv_scale = (double)dsize / ssize, scale = 1. / inv_scale;
+    for (int d = 0; d < dsize; d++) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= s;
+        if (horizontal) {
+            if (s < 0) { f = 0; s = 0; }
+            if (s >= ssize - 1) { f = 0; s = ssize - 1; }
+        }
+        const int a0 = cv_round_f((1.f - f) * 2048.f), a1 = cv_round_f(f * 2048.f);
+        out[d].ofs = s;
+        out[d].a0 = (int16_t)std::min(32767, std::max(-32768, a0));
+        out[d].a1 = (int16_t)std::min(32767, std::max(-32768, a1));
+    }
+}
+
+// geometry for one input size; returns false when the reference itself is undefined for it
+static bool build_geometry(const orbx_handle *h, int w, int hgt, FrameGeom &G, std::vector<ResizeTab> *xt, std::vector<ResizeTab> *yt)
+{
+    memset(&G, 0, sizeof(G));
+    const orbx_params &p = h->prm;
+    G.nlevels = p.nlevels; G.width = w; G.height = hgt;
+    const int cdiv = p.cand_divisor > 0 ? p.cand_divisor : 16;
+    size_t off = 0, boff = 0, coff = 0; int soff = 0, cells = 0, tiles = 0, ncmax = 8;
+    for (int l = 0; l < p.nlevels; l++) {
+        LevelGeom &g = G.lv[l];
+        g.w = cv_round_f((float)w * h->inv_scale[l]);                     // ORBextractor.cpp:1174
+        g.h = cv_round_f((float)hgt * h->inv_scale[l]);
+        if (g.w < 1 || g.h < 1) return false;
+        g.pitch = (int)align_up((size_t)g.w, 128);
+        if (l > 0) { g.off = off; off += align_up((size_t)g.pitch * g.h, 256); }
+        g.bpitch = g.pitch; g.boff = boff; boff += align_up((size_t)g.bpitch * g.h, 256);
+        const int W = g.w - 2 * ORBX_BORDER, H = g.h - 2 * ORBX_BORDER;    // maxBorder - minBorder, :786-795
+        g.scale = h->scale[l];
+        g.size = (float)(int)(ORBX_PATCH * h->scale[l]);                  // :880
+        g.N = h->nfeat[l];
+        if (W >= ORBX_CELL_W && H >= ORBX_CELL_W) {
+            const float width = (float)W, height = (float)H;
+            g.ncols = (int)(width / (float)ORBX_CELL_W); g.nrows = (int)(height / (float)ORBX_CELL_W);   // :799-800
+            g.wcell = (int)ceilf(width / g.ncols); g.hcell = (int)ceilf(height / g.nrows);               // :801-802
+            g.nini = (int)roundf((float)W / H);                                                           // :559
+            if (g.nini < 1 || g.nini > 64) return false;          // reference divides by zero for nini == 0
+            g.hx = (float)W / g.nini;                                                                     // :560
+        } else { g.ncols = g.nrows = 0; g.wcell = g.hcell = 1; g.nini = 0; g.hx = 1.f; }
+        g.cell_first = cells; cells += g.ncols * g.nrows;
+        g.blur_tx = (g.w + 127) / 128; g.blur_ty = (g.h + 31) / 32;
+        g.blur_first = tiles; tiles += g.blur_tx * g.blur_ty;
+        g.cand_cap = (int)align_up((size_t)std::max(4096, g.w * g.h / cdiv), 64);
+        g.cand_off = coff; coff += (size_t)g.cand_cap;
+        g.sel_cap = (int)align_up((size_t)std::max(g.N + 4, 4 * g.nini + 4), 8);
+        g.sel_off = soff; soff += g.sel_cap;
+        ncmax = std::max(ncmax, g.sel_cap);
+        if (l > 0 && xt && yt) {
+            g.xtab_off = (int)xt->size(); xt->resize(xt->size() + g.w);
+            resize_table(G.lv[l - 1].w, g.w, true, xt->data() + g.xtab_off);
+            g.ytab_off = (int)yt->size(); yt->resize(yt->size() + g.h);
+            resize_table(G.lv[l - 1].h, g.h, false, yt->data() + g.ytab_off);
+        }
+    }
+    G.total_cells = cells; G.total_blur_tiles = tiles;
+    G.pyr_bytes = std::max<size_t>(off, 256); G.blur_bytes = boff; G.cand_entries = coff; G.sel_entries = soff; G.node_cap_max = ncmax;
+    return true;
+}
+
+static orbx_status set_geometry(orbx_handle *h, int w, int hgt)
+{
+    if (h->geo.width == w && h->geo.height == hgt) return ORBX_OK;
+    if (w > h->prm.max_width || hgt > h->prm.max_height) { h->err = "frame larger than max_width x max_height"; return ORBX_E_INVALID; }
+    if (w > 4096 + 2 * ORBX_BORDER || hgt > 4096 + 2 * ORBX_BORDER) { h->err = "frame larger than 4128 px"; return ORBX_E_UNSUPPORTED; }
+    FrameGeom G; std::vector<ResizeTab> xt, yt;
+    if (!build_geometry(h, w, hgt, G, &xt, &yt)) { h->err = "unsupported frame geometry (aspect ratio gives 0 or > 64 quadtree roots, or a level vanishes)"; return ORBX_E_UNSUPPORTED; }
+    const size_t B = (size_t)h->prm.max_batch;
+    if (G.pyr_bytes * B > h->pyr_cap || G.blur_bytes * B > h->blur_cap || G.cand_entries * B > h->cand_cap ||
+        (size_t)G.sel_entries * B > h->sel_cap || (int)xt.size() > h->tab_cap || (int)yt.size() > h->tab_cap ||
+        G.sel_entries > h->max_kp) { h->err = "frame geometry does not fit the arenas sized at create"; return ORBX_E_INVALID; }
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    ORBX_CUDA(h, cudaMemcpy(h->d_geo, &G, sizeof(G), cudaMemcpyHostToDevice));
+    if (!xt.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_xtab, xt.data(), xt.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
+    if (!yt.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_ytab, yt.data(), yt.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
+    h->geo = G; h->pyr_slab = G.pyr_bytes; h->blur_slab = G.blur_bytes;
+    return ORBX_OK;
+}
+
+extern "C" void orbx_destroy(orbx_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void *dev[] = { h->d_geo, h->d_xtab, h->d_ytab, h->d_pyr, h->d_blur, h->d_in, h->d_depth_in, h->d_cand, h->d_cand2, h->d_qtmp,
+                    h->d_owner, h->d_owner2, h->d_ncand, h->d_sel, h->d_nsel, h->d_kps_all, h->d_desc_all, h->d_count_all,
+                    h->d_kps_out, h->d_desc_out, h->d_count_out, h->d_boxes, h->d_status, h->d_mpart, h->d_mq, h->d_mt, h->d_mout, h->d_mcount };
+    for (void *p : dev) if (p) cudaFree(p);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_status) cudaFreeHost(h->h_status);
+    if (h->ev_a) cudaEventDestroy(h->ev_a);
+    if (h->ev_b) cudaEventDestroy(h->ev_b);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    delete h;
+}
+
+#define CREATE_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    g_create_err = std::string(#call) + ": " + cudaGetErrorString(e_); orbx_destroy(h); return ORBX_E_CUDA; } } while (0)
+
+extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
+{
+    if (!pp || !out) { g_create_err = "null argument"; return ORBX_E_INVALID; }
+    *out = nullptr;
+    orbx_params p = *pp;
+    if (p.nlevels < 1 || p.nlevels > ORBX_MAX_LEVELS || p.nfeatures < 1 || !(p.scale_factor > 1.0f) ||
+        p.max_width < 1 || p.max_height < 1 || p.max_batch < 1 || p.ini_th_fast < 0 || p.min_th_fast < 0 ||
+        p.ini_th_fast > 255 || p.min_th_fast > 255) { g_create_err = "invalid orbx_params"; return ORBX_E_INVALID; }
+    if (p.scale_factor == 2.0f) { g_create_err = "scale_factor 2.0 takes cv::resize's INTER_AREA fast path, not implemented"; return ORBX_E_UNSUPPORTED; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { g_create_err = "no CUDA device: this path has no CPU fallback"; return ORBX_E_CUDA; }
+    if (p.device < 0 || p.device >= ndev) { g_create_err = "device ordinal out of range"; return ORBX_E_INVALID; }
+    orbx_handle *h = new orbx_handle();
+    h->prm = p; h->device = p.device; h->launches = 0; h->geo.width = -1; h->geo.height = -1;
+    CREATE_CUDA(cudaSetDevice(p.device));
+    cudaDeviceProp prop;
+    CREATE_CUDA(cudaGetDeviceProperties(&prop, p.device));
+    h->sm_count = prop.multiProcessorCount;
+    CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
+    build_tables(h);
+    upload_umax(h->umax);
+    FrameGeom G;
+    if (!build_geometry(h, p.max_width, p.max_height, G, nullptr, nullptr)) {
+        g_create_err = "unsupported max_width x max_height geometry"; orbx_destroy(h); return ORBX_E_UNSUPPORTED;
+    }
+    const size_t B = (size_t)p.max_batch;
+    // arenas are sized for the max geometry with 12% headroom so that smaller frames with unlucky padding still fit
+    h->pyr_cap = (G.pyr_bytes + G.pyr_bytes / 8 + 4096) * B; h->blur_cap = (G.blur_bytes + G.blur_bytes / 8 + 4096) * B;
+    h->cand_cap = (G.cand_entries + G.cand_entries / 8 + 4096 * p.nlevels) * B;
+    h->sel_cap = (size_t)(G.sel_entries + 64 * p.nlevels) * B;
+    h->max_kp = std::max(p.max_keypoints, G.sel_entries + 64 * p.nlevels);
+    h->tab_cap = 2 * (p.max_width + p.max_height) * 6 + 1024;
+    h->in_cap = align_up((size_t)p.max_width, 128) * p.max_height * B;
+    h->depth_cap = align_up((size_t)p.max_width * 2, 128) * p.max_height * B;
+    CREATE_CUDA(cudaMalloc(&h->d_geo, sizeof(FrameGeom)));
+    CREATE_CUDA(cudaMalloc(&h->d_xtab, sizeof(ResizeTab) * h->tab_cap));
+    CREATE_CUDA(cudaMalloc(&h->d_ytab, sizeof(ResizeTab) * h->tab_cap));
+    CREATE_CUDA(cudaMalloc(&h->d_pyr, h->pyr_cap));
+    CREATE_CUDA(cudaMalloc(&h->d_blur, h->blur_cap));
+    CREATE_CUDA(cudaMalloc(&h->d_in, h->in_cap));
+    CREATE_CUDA(cudaMalloc(&h->d_depth_in, h->depth_cap));
+    CREATE_CUDA(cudaMalloc(&h->d_cand, h->cand_cap * sizeof(uint32_t)));
+    CREATE_CUDA(cudaMalloc(&h->d_cand2, h->cand_cap * sizeof(uint32_t)));
+    CREATE_CUDA(cudaMalloc(&h->d_qtmp, h->cand_cap * sizeof(uint32_t)));
+    CREATE_CUDA(cudaMalloc(&h->d_owner, h->cand_cap * sizeof(uint16_t)));
+    CREATE_CUDA(cudaMalloc(&h->d_owner2, h->cand_cap * sizeof(uint16_t)));
+    CREATE_CUDA(cudaMalloc(&h->d_ncand, B * ORBX_MAX_LEVELS * sizeof(int32_t)));
+    CREATE_CUDA(cudaMalloc(&h->d_nsel, B * ORBX_MAX_LEVELS * sizeof(int32_t)));
+    CREATE_CUDA(cudaMalloc(&h->d_sel, h->sel_cap * sizeof(uint32_t)));
+    CREATE_CUDA(cudaMalloc(&h->d_kps_all, B * h->max_kp * sizeof(orbx_keypoint)));
+    CREATE_CUDA(cudaMalloc(&h->d_desc_all, B * h->max_kp * ORBX_DESC_BYTES));
+    CREATE_CUDA(cudaMalloc(&h->d_count_all, B * sizeof(int32_t)));
+    CREATE_CUDA(cudaMalloc(&h->d_kps_out, B * h->max_kp * sizeof(orbx_keypoint)));
+    CREATE_CUDA(cudaMalloc(&h->d_desc_out, B * h->max_kp * ORBX_DESC_BYTES));
+    CREATE_CUDA(cudaMalloc(&h->d_count_out, B * sizeof(int32_t)));
+    h->boxes_cap = 256;
+    CREATE_CUDA(cudaMalloc(&h->d_boxes, h->boxes_cap * sizeof(orbx_box)));
+    CREATE_CUDA(cudaMalloc(&h->d_status, sizeof(int32_t)));
+    CREATE_CUDA(cudaMalloc(&h->d_mcount, sizeof(int32_t) * 4));
+    CREATE_CUDA(cudaMemset(h->d_status, 0, sizeof(int32_t)));
+    CREATE_CUDA(cudaMemset(h->d_nsel, 0, B * ORBX_MAX_LEVELS * sizeof(int32_t)));
+    h->h_out_bytes = B * ((size_t)h->max_kp * (sizeof(orbx_keypoint) + ORBX_DESC_BYTES) + 64);
+    CREATE_CUDA(cudaMallocHost(&h->h_out, h->h_out_bytes));
+    CREATE_CUDA(cudaMallocHost(&h->h_status, 64));
+    orbx_status st = set_geometry(h, p.max_width, p.max_height);
+    if (st != ORBX_OK) { g_create_err = h->err; orbx_destroy(h); return st; }
+    *out = h;
+    return ORBX_OK;
+}
+
+// surfaces device-side error flags (capacity overflows) after a synchronisation point
+static orbx_status check_device_status(orbx_handle *h)
+{
+    ORBX_CUDA(h, cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    const int s = h->h_status[0];
+    if (s == 0) return ORBX_OK;
+    ORBX_CUDA(h, cudaMemsetAsync(h->d_status, 0, sizeof(int32_t), h->stream));
+    h->err = std::string("device capacity exceeded:") + ((s & ORBX_DS_CAND_OVERFLOW) ? " candidate list (lower cand_divisor)" : "") +
+             ((s & ORBX_DS_NODE_OVERFLOW) ? " quadtree nodes" : "") + ((s & ORBX_DS_KP_OVERFLOW) ? " keypoint output (raise cap / max_keypoints)" : "");
+    return ORBX_E_CAPACITY;
+}
+
+extern "C" orbx_status orbx_sync(orbx_handle *h)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    return check_device_status(h);
+}
+extern "C" void *orbx_stream(orbx_handle *h) { return h ? (void *)h->stream : nullptr; }
+extern "C" int64_t orbx_launch_count(const orbx_handle *h) { return h ? h->launches : 0; }
+
+extern "C" int32_t orbx_get_levels(const orbx_handle *h) { return h ? h->prm.nlevels : 0; }
+extern "C" float orbx_get_scale_factor(const orbx_handle *h) { return h ? (float)(double)h->prm.scale_factor : 0.f; }
+extern "C" void orbx_get_scale_factors(const orbx_handle *h, float *o) { if (h && o) memcpy(o, h->scale, sizeof(float) * h->prm.nlevels); }
+extern "C" void orbx_get_inverse_scale_factors(const orbx_handle *h, float *o) { if (h && o) memcpy(o, h->inv_scale, sizeof(float) * h->prm.nlevels); }
+extern "C" void orbx_get_scale_sigma_squares(const orbx_handle *h, float *o) { if (h && o) memcpy(o, h->sigma2, sizeof(float) * h->prm.nlevels); }
+extern "C" void orbx_get_inverse_scale_sigma_squares(const orbx_handle *h, float *o) { if (h && o) memcpy(o, h->inv_sigma2, sizeof(float) * h->prm.nlevels); }
+extern "C" void orbx_get_features_per_level(const orbx_handle *h, int32_t *o) { if (h && o) for (int l = 0; l < h->prm.nlevels; l++) o[l] = h->nfeat[l]; }
+extern "C" orbx_status orbx_level_size(const orbx_handle *h, int32_t w, int32_t hgt, int32_t level, int32_t *lw, int32_t *lh)
+{
+    if (!h || level < 0 || level >= h->prm.nlevels || !lw || !lh) return ORBX_E_INVALID;
+    *lw = cv_round_f((float)w * h->inv_scale[level]); *lh = cv_round_f((float)hgt * h->inv_scale[level]);
+    return ORBX_OK;
+}
+
+// ---- the extraction pipeline: ORBextractor::operator() (ORBextractor.cpp:1086-1167) on nframes frames ----
+static orbx_status run_pipeline(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride,
+                                const uint16_t *d_depth, size_t dstep, size_t dfstride,
+                                const orbx_box *d_boxes, int nboxes, uint64_t drop_mask,
+                                orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts)
+{
+    const int nl = h->geo.nlevels;
+    ORBX_CUDA(h, cudaMemsetAsync(h->d_ncand, 0, (size_t)nframes * nl * sizeof(int32_t), h->stream));
+    for (int l = 1; l < nl; l++) launch_resize_level(h, l, nframes, l0, l0_step, l0_fstride);   // ComputePyramid
+    launch_fast(h, nframes, l0, l0_step, l0_fstride);                                            // cell FAST
+    launch_quadtree(h, nframes);                                                                 // DistributeOctTree
+    launch_blur(h, nframes, l0, l0_step, l0_fstride);                                            // GaussianBlur per level
+    const bool filtered = d_depth != nullptr || nboxes > 0;
+    if (!filtered) launch_describe_to(h, nframes, l0, l0_step, l0_fstride, d_kps, d_desc, cap, d_counts);
+    else {
+        launch_describe_to(h, nframes, l0, l0_step, l0_fstride, h->d_kps_all, h->d_desc_all, h->max_kp, h->d_count_all);
+        launch_filter(h, nframes, d_depth, dstep, dfstride, d_boxes, nboxes, drop_mask, d_kps, d_desc, cap, d_counts);
+    }
+    h->last_batch = nframes; h->last_l0 = l0; h->last_l0_step = l0_step; h->last_l0_fstride = l0_fstride;
+    ORBX_CUDA(h, cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" orbx_status orbx_extract_batch_device(orbx_handle *h, const uint8_t *d_gray, int32_t nframes,
+                                                 int32_t width, int32_t height, size_t step, size_t frame_stride,
+                                                 const uint16_t *d_depth, size_t dstep, size_t dframe_stride,
+                                                 orbx_keypoint *d_kps, uint8_t *d_desc, int32_t cap, int32_t *d_counts)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    if (!d_gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }
+    if (nframes < 1 || nframes > h->prm.max_batch || !d_kps || !d_desc || !d_counts || cap < 1) { h->err = "bad batch arguments"; return ORBX_E_INVALID; }
+    if (step < (size_t)width || (step & 15) || ((uintptr_t)d_gray & 15) || (frame_stride & 15)) { h->err = "device frames need 16-byte aligned base, step and frame stride"; return ORBX_E_INVALID; }
+    if (d_depth && ((dstep & 1) || dstep < (size_t)width * 2)) { h->err = "bad depth step"; return ORBX_E_INVALID; }
+    orbx_status st = set_geometry(h, width, height);
+    if (st != ORBX_OK) return st;
+    return run_pipeline(h, nframes, d_gray, step, frame_stride, d_depth, dstep, dframe_stride, nullptr, 0, 0, d_kps, d_desc, cap, d_counts);
+}
+
+extern "C" orbx_status orbx_extract_filtered(orbx_handle *h, const uint8_t *gray, int32_t width, int32_t height, size_t step,
+                                             const uint16_t *depth, size_t dstep, const orbx_box *boxes, int32_t nboxes, uint64_t drop_mask,
+                                             orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *n_out)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    if (n_out) *n_out = 0;
+    if (!gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }        // ORBextractor.cpp:1090-1091
+    if (!kps || !desc || !n_out || cap < 0 || step < (size_t)width || nboxes < 0 || (nboxes > 0 && !boxes)) { h->err = "bad arguments"; return ORBX_E_INVALID; }
+    orbx_status st = set_geometry(h, width, height);
+    if (st != ORBX_OK) return st;
+    const size_t pitch = align_up((size_t)width, 128), dpitch = align_up((size_t)width * 2, 128);
+    ORBX_CUDA(h, cudaMemcpy2DAsync(h->d_in, pitch, gray, step, (size_t)width, (size_t)height, cudaMemcpyHostToDevice, h->stream));
+    if (depth) ORBX_CUDA(h, cudaMemcpy2DAsync(h->d_depth_in, dpitch, depth, dstep, (size_t)width * 2, (size_t)height, cudaMemcpyHostToDevice, h->stream));
+    if (nboxes > 0) {
+        if (nboxes > h->boxes_cap) {
+            cudaStreamSynchronize(h->stream);
+            cudaFree(h->d_boxes); h->d_boxes = nullptr; h->boxes_cap = 0;
+            ORBX_CUDA(h, cudaMalloc(&h->d_boxes, (size_t)nboxes * sizeof(orbx_box)));
+            h->boxes_cap = nboxes;
+        }
+        ORBX_CUDA(h, cudaMemcpyAsync(h->d_boxes, boxes, (size_t)nboxes * sizeof(orbx_box), cudaMemcpyHostToDevice, h->stream));
+    }
+    st = run_pipeline(h, 1, h->d_in, pitch, 0, depth ? h->d_depth_in : nullptr, dpitch, 0, h->d_boxes, nboxes, drop_mask,
+                      h->d_kps_out, h->d_desc_out, h->max_kp, h->d_count_out);
+    if (st != ORBX_OK) return st;
+    // one packed D2H: [count | keypoints | descriptors] for min(cap, max_kp) entries
+    const int ncopy = std::min(cap, h->max_kp);
+    uint8_t *hb = h->h_out;
+    ORBX_CUDA(h, cudaMemcpyAsync(hb, h->d_count_out, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (ncopy > 0) {
+        ORBX_CUDA(h, cudaMemcpyAsync(hb + 64, h->d_kps_out, (size_t)ncopy * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, h->stream));
+        ORBX_CUDA(h, cudaMemcpyAsync(hb + 64 + (size_t)h->max_kp * sizeof(orbx_keypoint), h->d_desc_out, (size_t)ncopy * ORBX_DESC_BYTES, cudaMemcpyDeviceToHost, h->stream));
+    }
+    st = check_device_status(h);
+    if (st != ORBX_OK) return st;
+    const int n = *(int32_t *)hb;
+    if (n > cap) { h->err = "output capacity too small"; *n_out = n; return ORBX_E_CAPACITY; }
+    memcpy(kps, hb + 64, (size_t)n * sizeof(orbx_keypoint));
+    memcpy(desc, hb + 64 + (size_t)h->max_kp * sizeof(orbx_keypoint), (size_t)n * ORBX_DESC_BYTES);
+    *n_out = n;
+    return ORBX_OK;
+}
+
+extern "C" orbx_status orbx_extract(orbx_handle *h, const uint8_t *gray, int32_t width, int32_t height, size_t step,
+                                    orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *n_out)
+{
+    return orbx_extract_filtered(h, gray, width, height, step, nullptr, 0, nullptr, 0, 0, kps, desc, cap, n_out);
+}
+
+extern "C" orbx_status orbx_extract_batch(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
+                                          size_t step, const uint16_t *depth, size_t dstep,
+                                          orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *counts)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    if (!gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }
+    if (nframes < 0 || !kps || !desc || !counts || cap < 1 || step < (size_t)width) { h->err = "bad arguments"; return ORBX_E_INVALID; }
+    orbx_status st = set_geometry(h, width, height);
+    if (st != ORBX_OK) return st;
+    const size_t pitch = align_up((size_t)width, 128), dpitch = align_up((size_t)width * 2, 128);
+    const size_t fstride = pitch * height, dfstride = dpitch * height;
+    const int B = h->prm.max_batch;
+    const int kcap = std::min(cap, h->max_kp);
+    for (int f0 = 0; f0 < nframes; f0 += B) {
+        const int nb = std::min(B, nframes - f0);
+        for (int f = 0; f < nb; f++) {
+            ORBX_CUDA(h, cudaMemcpy2DAsync(h->d_in + (size_t)f * fstride, pitch, gray + (size_t)(f0 + f) * height * step, step,
+                                           (size_t)width, (size_t)height, cudaMemcpyHostToDevice, h->stream));
+            if (depth) ORBX_CUDA(h, cudaMemcpy2DAsync((uint8_t *)h->d_depth_in + (size_t)f * dfstride, dpitch,
+                                                      (const uint8_t *)depth + (size_t)(f0 + f) * height * dstep, dstep,
+                                                      (size_t)width * 2, (size_t)height, cudaMemcpyHostToDevice, h->stream));
+        }
+        st = run_pipeline(h, nb, h->d_in, pitch, fstride, depth ? h->d_depth_in : nullptr, dpitch, dfstride, nullptr, 0, 0,
+                          h->d_kps_out, h->d_desc_out, h->max_kp, h->d_count_out);
+        if (st != ORBX_OK) return st;
+        ORBX_CUDA(h, cudaMemcpyAsync(counts + f0, h->d_count_out, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        ORBX_CUDA(h, cudaMemcpy2DAsync(kps + (size_t)f0 * cap, (size_t)cap * sizeof(orbx_keypoint), h->d_kps_out, (size_t)h->max_kp * sizeof(orbx_keypoint),
+                                       (size_t)kcap * sizeof(orbx_keypoint), (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
+        ORBX_CUDA(h, cudaMemcpy2DAsync(desc + (size_t)f0 * cap * ORBX_DESC_BYTES, (size_t)cap * ORBX_DESC_BYTES, h->d_desc_out, (size_t)h->max_kp * ORBX_DESC_BYTES,
+                                       (size_t)kcap * ORBX_DESC_BYTES, (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
+        st = check_device_status(h);
+        if (st != ORBX_OK) return st;
+        for (int f = 0; f < nb; f++) if (counts[f0 + f] > cap) { h->err = "output capacity too small"; return ORBX_E_CAPACITY; }
+    }
+    return ORBX_OK;
+}
+
+// ---- stage access (mvImagePyramid is public in the reference, ORBextractor.hpp:84) ----
+extern "C" orbx_status orbx_get_pyramid_level(orbx_handle *h, int32_t frame, int32_t level, uint8_t *out, size_t out_step)
+{
+    if (!h || !out || level < 0 || level >= h->geo.nlevels || frame < 0 || frame >= h->last_batch) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    const LevelGeom &g = h->geo.lv[level];
+    const uint8_t *src; size_t step;
+    if (level == 0) { src = h->last_l0 + (size_t)frame * h->last_l0_fstride; step = h->last_l0_step; }
+    else { src = h->d_pyr + (size_t)frame * h->pyr_slab + g.off; step = g.pitch; }
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    ORBX_CUDA(h, cudaMemcpy2D(out, out_step, src, step, (size_t)g.w, (size_t)g.h, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+extern "C" orbx_status orbx_get_blurred_level(orbx_handle *h, int32_t frame, int32_t level, uint8_t *out, size_t out_step)
+{
+    if (!h || !out || level < 0 || level >= h->geo.nlevels || frame < 0 || frame >= h->last_batch) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    const LevelGeom &g = h->geo.lv[level];
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    ORBX_CUDA(h, cudaMemcpy2D(out, out_step, h->d_blur + (size_t)frame * h->blur_slab + g.boff, g.bpitch, (size_t)g.w, (size_t)g.h, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+extern "C" orbx_status orbx_get_candidates(orbx_handle *h, int32_t frame, int32_t level, int32_t *out_xys, int32_t cap, int32_t *n_out)
+{
+    if (!h || !out_xys || !n_out || level < 0 || level >= h->geo.nlevels || frame < 0 || frame >= h->last_batch) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    const LevelGeom &g = h->geo.lv[level];
+    int32_t n = 0;
+    ORBX_CUDA(h, cudaMemcpy(&n, h->d_ncand + frame * h->geo.nlevels + level, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    *n_out = n;
+    if (n > g.cand_cap) { h->err = "candidate list overflowed"; return ORBX_E_CAPACITY; }
+    if (n > cap) return ORBX_E_CAPACITY;
+    // the quadtree ping-pongs between d_cand and d_cand2 but only permutes inside the list: either buffer holds the full set
+    std::vector<uint32_t> tmp((size_t)std::max(n, 1));
+    ORBX_CUDA(h, cudaMemcpy(tmp.data(), h->d_cand + (size_t)frame * h->geo.cand_entries + g.cand_off, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) { out_xys[3 * i] = orbx_px(tmp[i]); out_xys[3 * i + 1] = orbx_py(tmp[i]); out_xys[3 * i + 2] = orbx_ps(tmp[i]); }
+    return ORBX_OK;
+}
+extern "C" orbx_status orbx_get_level_counts(orbx_handle *h, int32_t frame, int32_t *out)
+{
+    if (!h || !out || frame < 0 || frame >= h->last_batch) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    ORBX_CUDA(h, cudaMemcpy(out, h->d_nsel + frame * h->geo.nlevels, sizeof(int32_t) * h->geo.nlevels, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+// ---- matching ----
+static int ratio_to_num(float ratio) { return ratio > 0.f ? (int)lrintf(ratio * 1024.f) : 0; }
+
+extern "C" orbx_status orbx_match_device(orbx_handle *h, const uint8_t *d_q, int32_t nq, const uint8_t *d_t, int32_t nt,
+                                         int32_t k, float max_dist, float ratio, orbx_dmatch *d_out, int32_t *d_n_out)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    if (nq < 0 || nt < 0 || (k != 1 && k != 2) || !d_out || (nq > 0 && !d_q) || (nt > 0 && !d_t)) { h->err = "bad match arguments"; return ORBX_E_INVALID; }
+    if (nq == 0) { if (d_n_out) ORBX_CUDA(h, cudaMemsetAsync(d_n_out, 0, sizeof(int32_t), h->stream)); return ORBX_OK; }
+    if (launch_match_core(h, d_q, nullptr, nq, 0, d_t, nullptr, nt, 0, nullptr, nullptr, 1, 0, k, max_dist, ratio_to_num(ratio),
+                          d_out, (size_t)nq * k, d_n_out, nullptr) != 0) { h->err = "out of device memory (match scratch)"; return ORBX_E_NOMEM; }
+    ORBX_CUDA(h, cudaGetLastError());
+    return ORBX_OK;
+}
+
+static orbx_status grow(orbx_handle *h, uint8_t **p, size_t *cap, size_t need)
+{
+    if (need <= *cap) return ORBX_OK;
+    if (*p) { cudaStreamSynchronize(h->stream); cudaFree(*p); *p = nullptr; *cap = 0; }
+    ORBX_CUDA(h, cudaMalloc(p, need));
+    *cap = need;
+    return ORBX_OK;
+}
+
+extern "C" orbx_status orbx_match(orbx_handle *h, const uint8_t *q, int32_t nq, const uint8_t *t, int32_t nt,
+                                  int32_t k, float max_dist, float ratio, orbx_dmatch *out, int32_t *n_out)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    if (n_out) *n_out = 0;
+    if (nq < 0 || nt < 0 || (k != 1 && k != 2) || !out || !n_out || (nq > 0 && !q) || (nt > 0 && !t)) { h->err = "bad match arguments"; return ORBX_E_INVALID; }
+    if (nq == 0) return ORBX_OK;
+    orbx_status st;
+    if ((st = grow(h, &h->d_mq, &h->mq_cap, (size_t)nq * ORBX_DESC_BYTES)) != ORBX_OK) return st;
+    if ((st = grow(h, &h->d_mt, &h->mt_cap, (size_t)std::max(nt, 1) * ORBX_DESC_BYTES)) != ORBX_OK) return st;
+    if ((st = grow(h, (uint8_t **)&h->d_mout, &h->mout_cap, (size_t)nq * k * sizeof(orbx_dmatch))) != ORBX_OK) return st;
+    ORBX_CUDA(h, cudaMemcpyAsync(h->d_mq, q, (size_t)nq * ORBX_DESC_BYTES, cudaMemcpyHostToDevice, h->stream));
+    if (nt > 0) ORBX_CUDA(h, cudaMemcpyAsync(h->d_mt, t, (size_t)nt * ORBX_DESC_BYTES, cudaMemcpyHostToDevice, h->stream));
+    st = orbx_match_device(h, h->d_mq, nq, h->d_mt, nt, k, max_dist, ratio, h->d_mout, h->d_mcount);
+    if (st != ORBX_OK) return st;
+    int32_t n = 0;
+    ORBX_CUDA(h, cudaMemcpyAsync(&n, h->d_mcount, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (n > 0) ORBX_CUDA(h, cudaMemcpy(out, h->d_mout, (size_t)n * sizeof(orbx_dmatch), cudaMemcpyDeviceToHost));
+    *n_out = n;
+    return ORBX_OK;
+}
+
+extern "C" orbx_status orbx_match_pairs_device(orbx_handle *h, const uint8_t *d_desc, const int32_t *d_counts, int32_t cap,
+                                               const int32_t *q_frame, const int32_t *t_frame, int32_t npairs,
+                                               int32_t k, float max_dist, float ratio, orbx_dmatch *d_out, int32_t *d_n_out)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    if (!d_desc || !d_counts || cap < 1 || npairs < 0 || (k != 1 && k != 2) || !d_out || !d_n_out || (npairs > 0 && (!q_frame || !t_frame))) { h->err = "bad match arguments"; return ORBX_E_INVALID; }
+    if (npairs == 0) return ORBX_OK;
+    orbx_status st;
+    size_t need = (size_t)npairs * 2 * sizeof(int32_t);
+    if ((st = grow(h, &h->d_mq, &h->mq_cap, need)) != ORBX_OK) return st;     // reuse the query scratch for the pair lists
+    int32_t *d_qsel = (int32_t *)h->d_mq, *d_tsel = d_qsel + npairs;
+    ORBX_CUDA(h, cudaMemcpyAsync(d_qsel, q_frame, (size_t)npairs * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(h, cudaMemcpyAsync(d_tsel, t_frame, (size_t)npairs * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    if (launch_match_core(h, d_desc, d_counts, cap, (size_t)cap * ORBX_DESC_BYTES, d_desc, d_counts, cap, (size_t)cap * ORBX_DESC_BYTES,
+                          d_qsel, d_tsel, npairs, 0, k, max_dist, ratio_to_num(ratio), d_out, (size_t)cap * k, d_n_out, nullptr) != 0) {
+        h->err = "out of device memory (match scratch)"; return ORBX_E_NOMEM;
+    }
+    ORBX_CUDA(h, cudaGetLastError());
+    return ORBX_OK;
+}
+
+// ---- landmark database (Backend::associateObservation, descriptor stage) ----
+extern "C" orbx_status orbx_db_create(orbx_handle *h, int64_t capacity_rows, uint32_t first_index, orbx_db **out)
+{
+    if (!h || !out || capacity_rows < 1) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    orbx_db *db = new orbx_db();
+    memset(db, 0, sizeof(*db));
+    db->h = h; db->cap = capacity_rows; db->rows = 0; db->first_index = first_index;
+    if (cudaMalloc(&db->d_rows, (size_t)capacity_rows * ORBX_DESC_BYTES) != cudaSuccess) { delete db; h->err = "out of device memory (db)"; return ORBX_E_NOMEM; }
+    *out = db;
+    return ORBX_OK;
+}
+extern "C" void orbx_db_destroy(orbx_db *db)
+{
+    if (!db) return;
+    cudaSetDevice(db->h->device);
+    cudaStreamSynchronize(db->h->stream);
+    if (db->d_rows) cudaFree(db->d_rows);
+    if (db->d_q) cudaFree(db->d_q);
+    if (db->d_out) cudaFree(db->d_out);
+    delete db;
+}
+extern "C" int64_t orbx_db_rows(const orbx_db *db) { return db ? db->rows : 0; }
+extern "C" orbx_status orbx_db_append(orbx_db *db, const uint8_t *rows, int64_t n)
+{
+    if (!db || n < 0 || (n > 0 && !rows)) return ORBX_E_INVALID;
+    orbx_handle *h = db->h; cudaSetDevice(h->device);
+    if (db->rows + n > db->cap) { h->err = "database capacity exceeded"; return ORBX_E_CAPACITY; }
+    ORBX_CUDA(h, cudaMemcpyAsync(db->d_rows + (size_t)db->rows * ORBX_DESC_BYTES, rows, (size_t)n * ORBX_DESC_BYTES, cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    db->rows += n;
+    return ORBX_OK;
+}
+extern "C" orbx_status orbx_db_append_device(orbx_db *db, const uint8_t *d_rows, int64_t n)
+{
+    if (!db || n < 0 || (n > 0 && !d_rows)) return ORBX_E_INVALID;
+    orbx_handle *h = db->h; cudaSetDevice(h->device);
+    if (db->rows + n > db->cap) { h->err = "database capacity exceeded"; return ORBX_E_CAPACITY; }
+    ORBX_CUDA(h, cudaMemcpyAsync(db->d_rows + (size_t)db->rows * ORBX_DESC_BYTES, d_rows, (size_t)n * ORBX_DESC_BYTES, cudaMemcpyDeviceToDevice, h->stream));
+    db->rows += n;
+    return ORBX_OK;
+}
+extern "C" orbx_status orbx_db_query_top2_device(orbx_db *db, const uint8_t *d_q, int32_t nq, orbx_top2 *d_out)
+{
+    if (!db || nq < 0 || !d_out || (nq > 0 && !d_q)) return ORBX_E_INVALID;
+    orbx_handle *h = db->h; cudaSetDevice(h->device);
+    if (nq == 0) return ORBX_OK;
+    if (db->rows > 0x7FFFFFFF) { h->err = "shard too large"; return ORBX_E_UNSUPPORTED; }
+    if (launch_match_core(h, d_q, nullptr, nq, 0, db->d_rows, nullptr, (int)db->rows, 0, nullptr, nullptr, 1, db->first_index,
+                          2, 0.f, 0, nullptr, 0, nullptr, d_out) != 0) { h->err = "out of device memory (match scratch)"; return ORBX_E_NOMEM; }
+    ORBX_CUDA(h, cudaGetLastError());
+    return ORBX_OK;
+}
+static orbx_status db_stage_queries(orbx_db *db, const uint8_t *q, int32_t nq, size_t out_bytes)
+{
+    orbx_handle *h = db->h;
+    if ((size_t)nq * ORBX_DESC_BYTES > db->q_cap) {
+        if (db->d_q) { cudaStreamSynchronize(h->stream); cudaFree(db->d_q); db->d_q = nullptr; db->q_cap = 0; }
+        ORBX_CUDA(h, cudaMalloc(&db->d_q, (size_t)nq * ORBX_DESC_BYTES)); db->q_cap = (size_t)nq * ORBX_DESC_BYTES;
+    }
+    if (out_bytes > db->out_cap) {
+        if (db->d_out) { cudaStreamSynchronize(h->stream); cudaFree(db->d_out); db->d_out = nullptr; db->out_cap = 0; }
+        ORBX_CUDA(h, cudaMalloc(&db->d_out, out_bytes)); db->out_cap = out_bytes;
+    }
+    ORBX_CUDA(h, cudaMemcpyAsync(db->d_q, q, (size_t)nq * ORBX_DESC_BYTES, cudaMemcpyHostToDevice, h->stream));
+    return ORBX_OK;
+}
+extern "C" orbx_status orbx_db_query_top2(orbx_db *db, const uint8_t *q, int32_t nq, orbx_top2 *out)
+{
+    if (!db || nq < 0 || !out || (nq > 0 && !q)) return ORBX_E_INVALID;
+    orbx_handle *h = db->h; cudaSetDevice(h->device);
+    if (nq == 0) return ORBX_OK;
+    orbx_status st = db_stage_queries(db, q, nq, (size_t)nq * sizeof(orbx_top2));
+    if (st != ORBX_OK) return st;
+    if ((st = orbx_db_query_top2_device(db, db->d_q, nq, db->d_out)) != ORBX_OK) return st;
+    ORBX_CUDA(h, cudaMemcpyAsync(out, db->d_out, (size_t)nq * sizeof(orbx_top2), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+extern "C" orbx_status orbx_merge_top2_device(orbx_handle *h, const orbx_top2 *d_parts, int32_t nshards, int32_t nq, orbx_top2 *d_out)
+{
+    if (!h || !d_parts || !d_out || nshards < 1 || nq < 0) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    launch_merge_top2(h, d_parts, nshards, nq, d_out);
+    ORBX_CUDA(h, cudaGetLastError());
+    return ORBX_OK;
+}
+extern "C" orbx_status orbx_db_query_radius(orbx_db *db, const uint8_t *q, int32_t nq, float max_dist,
+                                            orbx_dmatch *out, int32_t cap, int32_t *n_out)
+{
+    if (!db || nq < 0 || !out || !n_out || cap < 0 || (nq > 0 && !q)) return ORBX_E_INVALID;
+    orbx_handle *h = db->h; cudaSetDevice(h->device);
+    *n_out = 0;
+    if (nq == 0 || db->rows == 0) return ORBX_OK;
+    orbx_status st = db_stage_queries(db, q, nq, (size_t)std::max(cap, 1) * sizeof(orbx_dmatch));
+    if (st != ORBX_OK) return st;
+    ORBX_CUDA(h, cudaMemsetAsync(h->d_mcount, 0, sizeof(int32_t), h->stream));
+    launch_match_radius(h, db->d_q, nq, db->d_rows, (int)db->rows, db->first_index, max_dist, (orbx_dmatch *)db->d_out, cap, h->d_mcount);
+    int32_t n = 0;
+    ORBX_CUDA(h, cudaMemcpyAsync(&n, h->d_mcount, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    *n_out = n;
+    if (n > cap) { h->err = "radius output capacity too small"; return ORBX_E_CAPACITY; }
+    if (n > 0) ORBX_CUDA(h, cudaMemcpy(out, db->d_out, (size_t)n * sizeof(orbx_dmatch), cudaMemcpyDeviceToHost));
+    std::sort(out, out + n, [](const orbx_dmatch &a, const orbx_dmatch &b) { return a.queryIdx != b.queryIdx ? a.queryIdx < b.queryIdx : a.trainIdx < b.trainIdx; });
+    return ORBX_OK;
+}
+
+// ---- synthetic inputs ----
+extern "C" orbx_status orbx_synth_gray_device(orbx_handle *h, uint32_t seed, int32_t first, int32_t n, int32_t w, int32_t hgt, uint8_t *d, size_t step, size_t fstride)
+{
+    if (!h || !d || n < 1 || w < 1 || hgt < 1 || step < (size_t)w) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    launch_synth_gray(h, seed, first, n, w, hgt, d, step, fstride);
+    ORBX_CUDA(h, cudaGetLastError());
+    return ORBX_OK;
+}
+extern "C" orbx_status orbx_synth_depth_device(orbx_handle *h, uint32_t seed, int32_t first, int32_t n, int32_t w, int32_t hgt, uint16_t *d, size_t step, size_t fstride)
+{
+    if (!h || !d || n < 1 || w < 1 || hgt < 1 || step < (size_t)w * 2) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    launch_synth_depth(h, seed, first, n, w, hgt, d, step, fstride);
+    ORBX_CUDA(h, cudaGetLastError());
+    return ORBX_OK;
+}
+extern "C" orbx_status orbx_synth_descriptors_device(orbx_handle *h, uint32_t seed, uint64_t first_row, int64_t nrows, uint8_t *d)
+{
+    if (!h || !d || nrows < 1) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    launch_synth_desc(h, seed, first_row, nrows, d);
+    ORBX_CUDA(h, cudaGetLastError());
+    return ORBX_OK;
+}
+
+// ---- utilities ----
+extern "C" void *orbx_alloc_pinned(size_t bytes) { void *p = nullptr; return cudaMallocHost(&p, bytes) == cudaSuccess ? p : nullptr; }
+extern "C" void orbx_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+extern "C" void *orbx_alloc_device(orbx_handle *h, size_t bytes) { if (!h) return nullptr; cudaSetDevice(h->device); void *p = nullptr; return cudaMalloc(&p, bytes) == cudaSuccess ? p : nullptr; }
+extern "C" void orbx_free_device(orbx_handle *h, void *p) { if (h && p) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); cudaFree(p); } }
+extern "C" orbx_status orbx_copy_to_device(orbx_handle *h, void *d, const void *s, size_t bytes)
+{
+    if (!h || !d || !s) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    ORBX_CUDA(h, cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+extern "C" orbx_status orbx_copy_to_host(orbx_handle *h, void *d, const void *s, size_t bytes)
+{
+    if (!h || !d || !s) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    ORBX_CUDA(h, cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+extern "C" orbx_status orbx_test_trig(orbx_handle *h, const float *in, int32_t n, float *oc, float *os)
+{
+    if (!h || !in || !oc || !os || n < 1) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    float *d = nullptr;
+    ORBX_CUDA(h, cudaMalloc(&d, sizeof(float) * 3 * (size_t)n));
+    cudaMemcpyAsync(d, in, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream);
+    launch_test_trig(h, d, n, d + n, d + 2 * (size_t)n);
+    cudaMemcpyAsync(oc, d + n, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(os, d + 2 * (size_t)n, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    ORBX_CUDA(h, e);
+    return ORBX_OK;
+}
+extern "C" orbx_status orbx_test_atan2(orbx_handle *h, const float *y, const float *x, int32_t n, float *out)
+{
+    if (!h || !y || !x || !out || n < 1) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    float *d = nullptr;
+    ORBX_CUDA(h, cudaMalloc(&d, sizeof(float) * 3 * (size_t)n));
+    cudaMemcpyAsync(d, y, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(d + n, x, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream);
+    launch_test_atan2(h, d, d + n, n, d + 2 * (size_t)n);
+    cudaMemcpyAsync(out, d + 2 * (size_t)n, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    ORBX_CUDA(h, e);
+    return ORBX_OK;
+}
+extern "C" orbx_status orbx_test_trig_checksum(orbx_handle *h, uint32_t first, uint32_t last, uint64_t *sc, uint64_t *ss)
+{
+    if (!h || !sc || !ss || last < first) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    unsigned long long *d = nullptr, hs[2] = { 0, 0 };
+    ORBX_CUDA(h, cudaMalloc(&d, 16));
+    cudaMemsetAsync(d, 0, 16, h->stream);
+    launch_trig_checksum(h, first, last, d);
+    cudaMemcpyAsync(hs, d, 16, cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    ORBX_CUDA(h, e);
+    *sc = hs[0]; *ss = hs[1];
+    return ORBX_OK;
+}
+
+// the distribution stage alone, on a caller-supplied candidate list (order-independent by construction)
+extern "C" orbx_status orbx_test_quadtree(orbx_handle *h, const int32_t *xys, int32_t n, int32_t box_w, int32_t box_h,
+                                          int32_t wcell, int32_t hcell, int32_t ncols, int32_t N, int32_t *out_xys, int32_t cap, int32_t *n_out)
+{
+    if (!h || !xys || !out_xys || !n_out || n < 0 || box_w < 1 || box_h < 1 || wcell < 1 || hcell < 1 || ncols < 1 || N < 0) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    FrameGeom G; memset(&G, 0, sizeof(G));
+    G.nlevels = 1;
+    LevelGeom &g = G.lv[0];
+    g.w = box_w + 2 * ORBX_BORDER; g.h = box_h + 2 * ORBX_BORDER;
+    g.wcell = wcell; g.hcell = hcell; g.ncols = ncols; g.N = N;
+    g.nini = (int)roundf((float)box_w / box_h);
+    if (g.nini < 1 || g.nini > 64) { h->err = "unsupported aspect"; return ORBX_E_UNSUPPORTED; }
+    g.hx = (float)box_w / g.nini;
+    g.cand_cap = (int)std::min<size_t>(h->cand_cap, 1u << 30); g.cand_off = 0;
+    g.sel_cap = (int)align_up((size_t)std::max(N + 4, 4 * g.nini + 4), 8); g.sel_off = 0;
+    if (n > g.cand_cap || (size_t)g.sel_cap > h->sel_cap || n > 65535 * 64) { h->err = "test input too large"; return ORBX_E_CAPACITY; }
+    std::vector<uint32_t> packed((size_t)std::max(n, 1));
+    for (int i = 0; i < n; i++) packed[i] = orbx_pack(xys[3 * i], xys[3 * i + 1], xys[3 * i + 2]);
+    FrameGeom *d_g = nullptr;
+    ORBX_CUDA(h, cudaMalloc(&d_g, sizeof(FrameGeom)));
+    cudaMemcpyAsync(d_g, &G, sizeof(G), cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(h->d_cand, packed.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(h->d_ncand, &n, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream);
+    launch_quadtree_geo(h, d_g, 1, 1, g.sel_cap, h->cand_cap, (int)h->sel_cap);
+    int32_t m = 0;
+    cudaMemcpyAsync(&m, h->d_nsel, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_g);
+    ORBX_CUDA(h, e);
+    orbx_status st = check_device_status(h);
+    if (st != ORBX_OK) return st;
+    *n_out = m;
+    if (m > cap) return ORBX_E_CAPACITY;
+    std::vector<uint32_t> sel((size_t)std::max(m, 1));
+    ORBX_CUDA(h, cudaMemcpy(sel.data(), h->d_sel, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < m; i++) { out_xys[3 * i] = orbx_px(sel[i]); out_xys[3 * i + 1] = orbx_py(sel[i]); out_xys[3 * i + 2] = orbx_ps(sel[i]); }
+    return ORBX_OK;
+}
+
+extern "C" orbx_status orbx_bench_popc(orbx_handle *h, double *popc_per_sec)
+{
+    if (!h || !popc_per_sec) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    *popc_per_sec = run_popc_bench(h);
+    ORBX_CUDA(h, cudaGetLastError());
+    return ORBX_OK;
+}

@@ -1,0 +1,144 @@
+// orbx_internal.h — shared declarations of the sm_100a ORB path (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/orbx.h"
+
+#define ORBX_EDGE 19                 // EDGE_THRESHOLD, reference ORBextractor.cpp:73
+#define ORBX_BORDER 16               // EDGE_THRESHOLD - 3  (minBorderX, ORBextractor.cpp:787)
+#define ORBX_CELL_W 35               // W, ORBextractor.cpp:783
+#define ORBX_HALF_PATCH 15
+#define ORBX_PATCH 31
+
+// candidate / selected-keypoint packing: x:12 | y:12 | score:8, coordinates relative to the border box
+__host__ __device__ inline uint32_t orbx_pack(int x, int y, int s) { return (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24); }
+__host__ __device__ inline int orbx_px(uint32_t c) { return (int)(c & 0xFFFu); }
+__host__ __device__ inline int orbx_py(uint32_t c) { return (int)((c >> 12) & 0xFFFu); }
+__host__ __device__ inline int orbx_ps(uint32_t c) { return (int)(c >> 24); }
+
+// Geometry of one pyramid level for the current (width, height); lives in __constant__-like param structs.
+struct LevelGeom {
+    int w, h;                // level image size (ORBextractor.cpp:1173-1174)
+    int pitch;               // bytes per row in the pyramid slab (multiple of 128); level 0 aliases the input frame
+    size_t off;              // byte offset of the level inside a frame's pyramid slab (levels >= 1)
+    int bpitch;              // bytes per row in the blurred slab (all levels)
+    size_t boff;             // byte offset inside a frame's blurred slab
+    int ncols, nrows;        // cell grid (ORBextractor.cpp:799-802)
+    int wcell, hcell;
+    int cell_first;          // index of this level's first cell in the flattened all-level cell list
+    int blur_first, blur_tx, blur_ty;   // blur tiles
+    int N;                   // mnFeaturesPerLevel
+    int nini;                // quadtree roots (ORBextractor.cpp:559)
+    float hx;                // root width
+    int cand_cap;            // capacity of the candidate list
+    size_t cand_off;         // offset (in entries) of this level's candidate list inside a frame's candidate slab
+    int sel_cap;             // capacity of the selected list = node cap
+    int sel_off;             // offset (entries) inside a frame's selected slab
+    float scale;             // mvScaleFactor[level]
+    float size;              // (float)(int)(31*scale)
+    // resize tables (level l from l-1): offsets into the table buffers
+    int xtab_off, ytab_off;
+};
+
+struct FrameGeom {
+    int nlevels;
+    int width, height;
+    int total_cells, total_blur_tiles;
+    size_t pyr_bytes;        // per-frame pyramid slab size (levels 1..)
+    size_t blur_bytes;       // per-frame blurred slab size (levels 0..)
+    size_t cand_entries;     // per-frame candidate slab entries
+    int sel_entries;         // per-frame selected slab entries
+    int node_cap_max;
+    LevelGeom lv[ORBX_MAX_LEVELS];
+};
+
+struct ResizeTab { int32_t ofs; int16_t a0, a1; };   // 8 bytes
+
+struct orbx_handle {
+    orbx_params prm;
+    int device;
+    cudaStream_t stream, copy_stream;
+    cudaEvent_t ev_a, ev_b;
+    std::string err;
+    int64_t launches;
+    // extractor tables (ORBextractor.cpp:409-469)
+    float scale[ORBX_MAX_LEVELS], inv_scale[ORBX_MAX_LEVELS], sigma2[ORBX_MAX_LEVELS], inv_sigma2[ORBX_MAX_LEVELS];
+    int nfeat[ORBX_MAX_LEVELS];
+    int umax[16];
+    int max_kp;
+    // geometry of the current frame size (rebuilt when width/height change)
+    FrameGeom geo;
+    FrameGeom *d_geo;
+    ResizeTab *d_xtab, *d_ytab; int tab_cap;
+    // arenas, sized for max_width x max_height x max_batch
+    uint8_t *d_pyr, *d_blur;     size_t pyr_slab, blur_slab;          // current per-frame strides
+    size_t pyr_cap, blur_cap;                                          // arena bytes
+    uint8_t *d_in; size_t in_cap;          // staging for host-API inputs (gray)
+    uint16_t *d_depth_in; size_t depth_cap;
+    uint32_t *d_cand, *d_cand2;  size_t cand_cap;        // candidate values (entries), ping-pong for the quadtree
+    uint32_t *d_qtmp; uint16_t *d_owner, *d_owner2;
+    int32_t *d_ncand;            // [batch][levels]
+    uint32_t *d_sel; size_t sel_cap;        // selected per (frame, level), entries
+    int32_t *d_nsel;             // [batch][levels]
+    orbx_keypoint *d_kps_all; uint8_t *d_desc_all;   // unfiltered per-frame outputs [batch][max_kp]
+    int32_t *d_count_all;        // [batch]
+    orbx_keypoint *d_kps_out; uint8_t *d_desc_out; int32_t *d_count_out;   // host-API outputs [batch][max_kp]
+    orbx_box *d_boxes; int boxes_cap;
+    int32_t *d_status;           // device-side error flags
+    // pinned staging for the host API
+    uint8_t *h_out; size_t h_out_bytes;
+    int32_t *h_status;
+    // matcher scratch
+    uint32_t *d_mpart; size_t mpart_cap;    // partial top-2 keys
+    uint8_t *d_mq, *d_mt; size_t mq_cap, mt_cap;
+    orbx_dmatch *d_mout; size_t mout_cap; int32_t *d_mcount;
+    int last_batch;
+    const uint8_t *last_l0; size_t last_l0_step, last_l0_fstride;   // level 0 of the last batch (may alias caller memory)
+    int sm_count;
+};
+
+struct orbx_db {
+    orbx_handle *h;
+    uint8_t *d_rows; int64_t cap, rows; uint32_t first_index;
+    uint32_t *d_part; size_t part_cap;
+    uint8_t *d_q; size_t q_cap; orbx_top2 *d_out; size_t out_cap;
+};
+
+#define ORBX_CUDA(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return ORBX_E_CUDA; } } while (0)
+
+// device status bits
+#define ORBX_DS_CAND_OVERFLOW 1
+#define ORBX_DS_NODE_OVERFLOW 2
+#define ORBX_DS_KP_OVERFLOW   4
+
+// ---- kernel launchers (one per .cu) ----
+void launch_resize_level(orbx_handle *h, int level, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
+void launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
+void launch_quadtree(orbx_handle *h, int nframes);
+void launch_quadtree_geo(orbx_handle *h, const FrameGeom *d_geo, int nlevels, int nframes, int node_cap, size_t cand_slab, int sel_slab);
+void launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
+void launch_describe_to(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride,
+                        orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts);
+void upload_umax(const int *umax);
+void launch_filter(orbx_handle *h, int nframes, const uint16_t *d_depth, size_t dstep, size_t dfstride,
+                   const orbx_box *d_boxes, int nboxes, uint64_t drop_mask,
+                   orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts);
+int  launch_match_core(orbx_handle *h, const uint8_t *d_q, const int32_t *d_nq, int nq_max, size_t q_stride,
+                       const uint8_t *d_t, const int32_t *d_nt, int nt_max, size_t t_stride,
+                       const int32_t *d_qsel, const int32_t *d_tsel, int nproblems, uint32_t row_base,
+                       int k, float max_dist, int ratio_num, orbx_dmatch *d_out, size_t out_stride, int32_t *d_n_out,
+                       orbx_top2 *d_top2);
+void launch_match_radius(orbx_handle *h, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, uint32_t row_base,
+                         float max_dist, orbx_dmatch *d_out, int cap, int32_t *d_n_out);
+void launch_merge_top2(orbx_handle *h, const orbx_top2 *d_parts, int nshards, int nq, orbx_top2 *d_out);
+void launch_synth_gray(orbx_handle *h, uint32_t seed, int first, int n, int w, int hh, uint8_t *d, size_t step, size_t fstride);
+void launch_synth_depth(orbx_handle *h, uint32_t seed, int first, int n, int w, int hh, uint16_t *d, size_t step, size_t fstride);
+void launch_synth_desc(orbx_handle *h, uint32_t seed, uint64_t first_row, int64_t nrows, uint8_t *d);
+void launch_test_trig(orbx_handle *h, const float *d_in, int n, float *d_c, float *d_s);
+void launch_test_atan2(orbx_handle *h, const float *d_y, const float *d_x, int n, float *d_o);
+void launch_trig_checksum(orbx_handle *h, uint32_t first, uint32_t last, unsigned long long *d_sums);
+double run_popc_bench(orbx_handle *h);

@@ -1,0 +1,394 @@
+"""orbx — thin ctypes binding of the C ABI in include/orbx.h (tests and bench harness only).
+
+The product is liborbx.so (hand-written sm_100a kernels behind a C ABI); this module only marshals
+numpy arrays / raw device pointers into it.  There is NO CPU fallback: if the shared library is
+missing or no CUDA device is present, construction fails loudly.
+
+Mirrors of the reference call shapes (paths relative to the reference's dynamic_visual_slam/):
+  ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)   include/.../ORBextractor.hpp:50-51
+  ORBextractor.__call__(image)  -> (keypoints, descriptors)             ORBextractor.hpp:58-60
+  BFMatcher.match(query, train) -> DMatch[]                             frontend.cpp:1123
+"""
+import ctypes as ct
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "liborbx.so"))
+
+OK, E_INVALID, E_CUDA, E_CAPACITY, E_EMPTY, E_NOMEM, E_UNSUPPORTED = range(7)
+MAX_LEVELS = 16
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+DM_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
+BOX_DTYPE = np.dtype([("cx", "<f8"), ("cy", "<f8"), ("w", "<f8"), ("h", "<f8"), ("class_id", "<i4"), ("pad", "<i4")])
+TOP2_DTYPE = np.dtype([("dist0", "<u4"), ("idx0", "<u4"), ("dist1", "<u4"), ("idx1", "<u4")])
+assert KP_DTYPE.itemsize == 28 and DM_DTYPE.itemsize == 16 and BOX_DTYPE.itemsize == 40 and TOP2_DTYPE.itemsize == 16
+
+
+class Params(ct.Structure):
+    _fields_ = [("nfeatures", ct.c_int32), ("scale_factor", ct.c_float), ("nlevels", ct.c_int32),
+                ("ini_th_fast", ct.c_int32), ("min_th_fast", ct.c_int32),
+                ("depth_min", ct.c_float), ("depth_max", ct.c_float),
+                ("max_width", ct.c_int32), ("max_height", ct.c_int32), ("max_batch", ct.c_int32),
+                ("max_keypoints", ct.c_int32), ("cand_divisor", ct.c_int32), ("device", ct.c_int32),
+                ("reserved_", ct.c_int32 * 3)]
+
+
+class OrbxError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("orbx status %d: %s" % (status, msg))
+        self.status = status
+
+
+_lib = None
+
+
+def load():
+    """Load liborbx.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("liborbx.so not built at %s — run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+    L = ct.CDLL(LIB_PATH)
+    vp, i32, i64, u32, u64, f32, sz = ct.c_void_p, ct.c_int32, ct.c_int64, ct.c_uint32, ct.c_uint64, ct.c_float, ct.c_size_t
+    sig = {
+        "orbx_default_params": (None, [vp]),
+        "orbx_create": (i32, [vp, vp]),
+        "orbx_destroy": (None, [vp]),
+        "orbx_last_error": (ct.c_char_p, [vp]),
+        "orbx_version": (ct.c_char_p, []),
+        "orbx_sync": (i32, [vp]),
+        "orbx_stream": (vp, [vp]),
+        "orbx_get_levels": (i32, [vp]),
+        "orbx_get_scale_factor": (f32, [vp]),
+        "orbx_get_scale_factors": (None, [vp, vp]),
+        "orbx_get_inverse_scale_factors": (None, [vp, vp]),
+        "orbx_get_scale_sigma_squares": (None, [vp, vp]),
+        "orbx_get_inverse_scale_sigma_squares": (None, [vp, vp]),
+        "orbx_get_features_per_level": (None, [vp, vp]),
+        "orbx_level_size": (i32, [vp, i32, i32, i32, vp, vp]),
+        "orbx_extract": (i32, [vp, vp, i32, i32, sz, vp, vp, i32, vp]),
+        "orbx_extract_filtered": (i32, [vp, vp, i32, i32, sz, vp, sz, vp, i32, u64, vp, vp, i32, vp]),
+        "orbx_extract_batch": (i32, [vp, vp, i32, i32, i32, sz, vp, sz, vp, vp, i32, vp]),
+        "orbx_extract_batch_device": (i32, [vp, vp, i32, i32, i32, sz, sz, vp, sz, sz, vp, vp, i32, vp]),
+        "orbx_match": (i32, [vp, vp, i32, vp, i32, i32, f32, f32, vp, vp]),
+        "orbx_match_device": (i32, [vp, vp, i32, vp, i32, i32, f32, f32, vp, vp]),
+        "orbx_match_pairs_device": (i32, [vp, vp, vp, i32, vp, vp, i32, i32, f32, f32, vp, vp]),
+        "orbx_db_create": (i32, [vp, i64, u32, vp]),
+        "orbx_db_destroy": (None, [vp]),
+        "orbx_db_append": (i32, [vp, vp, i64]),
+        "orbx_db_append_device": (i32, [vp, vp, i64]),
+        "orbx_db_rows": (i64, [vp]),
+        "orbx_db_query_top2_device": (i32, [vp, vp, i32, vp]),
+        "orbx_db_query_top2": (i32, [vp, vp, i32, vp]),
+        "orbx_merge_top2_device": (i32, [vp, vp, i32, i32, vp]),
+        "orbx_db_query_radius": (i32, [vp, vp, i32, f32, vp, i32, vp]),
+        "orbx_get_pyramid_level": (i32, [vp, i32, i32, vp, sz]),
+        "orbx_get_blurred_level": (i32, [vp, i32, i32, vp, sz]),
+        "orbx_get_candidates": (i32, [vp, i32, i32, vp, i32, vp]),
+        "orbx_get_level_counts": (i32, [vp, i32, vp]),
+        "orbx_synth_gray_device": (i32, [vp, u32, i32, i32, i32, i32, vp, sz, sz]),
+        "orbx_synth_depth_device": (i32, [vp, u32, i32, i32, i32, i32, vp, sz, sz]),
+        "orbx_synth_descriptors_device": (i32, [vp, u32, u64, i64, vp]),
+        "orbx_alloc_pinned": (vp, [sz]),
+        "orbx_free_pinned": (None, [vp]),
+        "orbx_alloc_device": (vp, [vp, sz]),
+        "orbx_free_device": (None, [vp, vp]),
+        "orbx_copy_to_device": (i32, [vp, vp, vp, sz]),
+        "orbx_copy_to_host": (i32, [vp, vp, vp, sz]),
+        "orbx_test_trig": (i32, [vp, vp, i32, vp, vp]),
+        "orbx_test_atan2": (i32, [vp, vp, vp, i32, vp]),
+        "orbx_test_trig_checksum": (i32, [vp, u32, u32, vp, vp]),
+        "orbx_test_quadtree": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
+        "orbx_bench_popc": (i32, [vp, vp]),
+        "orbx_launch_count": (i64, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+ABI_SYMBOLS = None  # filled by tests from include/orbx.h
+
+
+def _p(a):
+    return a.ctypes.data_as(ct.c_void_p) if a is not None else None
+
+
+class ORBextractor:
+    """ORB_SLAM3::ORBextractor over the C ABI (reference ORBextractor.hpp:44-111)."""
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7,
+                 max_width=1280, max_height=720, max_batch=1, device=0, depth_min=0.3, depth_max=3.0,
+                 max_keypoints=0, cand_divisor=0):
+        L = load()
+        p = Params()
+        L.orbx_default_params(ct.byref(p))
+        p.nfeatures, p.scale_factor, p.nlevels = nfeatures, scaleFactor, nlevels
+        p.ini_th_fast, p.min_th_fast = iniThFAST, minThFAST
+        p.max_width, p.max_height, p.max_batch, p.device = max_width, max_height, max_batch, device
+        p.depth_min, p.depth_max, p.max_keypoints, p.cand_divisor = depth_min, depth_max, max_keypoints, cand_divisor
+        self._h = ct.c_void_p()
+        st = L.orbx_create(ct.byref(p), ct.byref(self._h))
+        if st != OK:
+            raise OrbxError(st, (L.orbx_last_error(None) or b"").decode())
+        self.L = L
+        self.params = p
+        self.nlevels = nlevels
+        self.max_batch = max_batch
+
+    # -- lifetime --
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.L.orbx_destroy(self._h)
+            self._h = ct.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != OK:
+            raise OrbxError(st, (self.L.orbx_last_error(self._h) or b"").decode())
+
+    @property
+    def handle(self):
+        return self._h
+
+    def sync(self):
+        self._check(self.L.orbx_sync(self._h))
+
+    @property
+    def stream(self):
+        return self.L.orbx_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return int(self.L.orbx_launch_count(self._h))
+
+    # -- getters (ORBextractor.hpp:62-82) --
+    def GetLevels(self):
+        return int(self.L.orbx_get_levels(self._h))
+
+    def GetScaleFactor(self):
+        return float(self.L.orbx_get_scale_factor(self._h))
+
+    def _vec(self, fn, dtype=np.float32):
+        out = np.zeros(self.nlevels, dtype)
+        fn(self._h, _p(out))
+        return out
+
+    def GetScaleFactors(self):
+        return self._vec(self.L.orbx_get_scale_factors)
+
+    def GetInverseScaleFactors(self):
+        return self._vec(self.L.orbx_get_inverse_scale_factors)
+
+    def GetScaleSigmaSquares(self):
+        return self._vec(self.L.orbx_get_scale_sigma_squares)
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._vec(self.L.orbx_get_inverse_scale_sigma_squares)
+
+    def features_per_level(self):
+        return self._vec(self.L.orbx_get_features_per_level, np.int32)
+
+    def level_size(self, w, h, level):
+        lw, lh = ct.c_int32(), ct.c_int32()
+        self._check(self.L.orbx_level_size(self._h, w, h, level, ct.byref(lw), ct.byref(lh)))
+        return lw.value, lh.value
+
+    # -- operator() --
+    def __call__(self, image, depth=None, boxes=None, drop_class_mask=0, cap=4096):
+        """Returns (keypoints[KP_DTYPE], descriptors[N,32] uint8).  Returns -1 for an empty image,
+        as the reference's operator() does (ORBextractor.cpp:1090-1091)."""
+        if image is None or image.size == 0:
+            return -1
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise TypeError("image must be CV_8UC1")          # reference: assert(image.type() == CV_8UC1)
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        h, w = image.shape
+        self._last_w, self._last_h = w, h
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = ct.c_int32()
+        if depth is None and boxes is None:
+            st = self.L.orbx_extract(self._h, _p(image), w, h, image.strides[0], _p(kps), _p(desc), cap, ct.byref(n))
+        else:
+            dptr, dstep = None, 0
+            if depth is not None:
+                if depth.dtype != np.uint16 or depth.shape != image.shape:
+                    raise TypeError("depth must be CV_16UC1 of the image size")
+                if depth.strides[1] != 2:
+                    depth = np.ascontiguousarray(depth)
+                dptr, dstep = _p(depth), depth.strides[0]
+            bptr, nb = None, 0
+            if boxes is not None and len(boxes):
+                boxes = np.ascontiguousarray(boxes, dtype=BOX_DTYPE)
+                bptr, nb = _p(boxes), len(boxes)
+            st = self.L.orbx_extract_filtered(self._h, _p(image), w, h, image.strides[0], dptr, dstep, bptr, nb,
+                                              ct.c_uint64(drop_class_mask), _p(kps), _p(desc), cap, ct.byref(n))
+        self._check(st)
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, frames, depth=None, cap=2048):
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        nf, h, w = frames.shape
+        self._last_w, self._last_h = w, h
+        kps = np.zeros((nf, cap), KP_DTYPE)
+        desc = np.zeros((nf, cap, 32), np.uint8)
+        counts = np.zeros(nf, np.int32)
+        dptr, dstep = None, 0
+        if depth is not None:
+            depth = np.ascontiguousarray(depth, dtype=np.uint16)
+            dptr, dstep = _p(depth), depth.strides[1]
+        self._check(self.L.orbx_extract_batch(self._h, _p(frames), nf, w, h, frames.strides[1], dptr, dstep,
+                                              _p(kps), _p(desc), cap, _p(counts)))
+        return kps, desc, counts
+
+    def extract_batch_device(self, d_gray, nframes, w, h, step, frame_stride, d_kps, d_desc, cap, d_counts,
+                             d_depth=None, dstep=0, dframe_stride=0):
+        """Raw device-pointer variant (ints), asynchronous on the handle's stream."""
+        self._check(self.L.orbx_extract_batch_device(self._h, d_gray, nframes, w, h, step, frame_stride,
+                                                     d_depth, dstep, dframe_stride, d_kps, d_desc, cap, d_counts))
+
+    # -- stage access --
+    def pyramid_level(self, level, frame=0):
+        w, h = self.level_size(self._last_w, self._last_h, level)
+        out = np.zeros((h, w), np.uint8)
+        self._check(self.L.orbx_get_pyramid_level(self._h, frame, level, _p(out), out.strides[0]))
+        return out
+
+    def blurred_level(self, level, frame=0):
+        w, h = self.level_size(self._last_w, self._last_h, level)
+        out = np.zeros((h, w), np.uint8)
+        self._check(self.L.orbx_get_blurred_level(self._h, frame, level, _p(out), out.strides[0]))
+        return out
+
+    def candidates(self, level, frame=0, cap=1 << 18):
+        out = np.zeros((cap, 3), np.int32)
+        n = ct.c_int32()
+        self._check(self.L.orbx_get_candidates(self._h, frame, level, _p(out), cap, ct.byref(n)))
+        return out[:n.value].copy()
+
+    def level_counts(self, frame=0):
+        out = np.zeros(self.nlevels, np.int32)
+        self._check(self.L.orbx_get_level_counts(self._h, frame, _p(out)))
+        return out
+
+    def set_size(self, w, h):
+        self._last_w, self._last_h = w, h
+
+    # -- self tests --
+    def test_trig(self, x):
+        x = np.ascontiguousarray(x, np.float32)
+        c, s = np.zeros_like(x), np.zeros_like(x)
+        self._check(self.L.orbx_test_trig(self._h, _p(x), len(x), _p(c), _p(s)))
+        return c, s
+
+    def test_atan2(self, y, x):
+        y = np.ascontiguousarray(y, np.float32)
+        x = np.ascontiguousarray(x, np.float32)
+        o = np.zeros_like(x)
+        self._check(self.L.orbx_test_atan2(self._h, _p(y), _p(x), len(x), _p(o)))
+        return o
+
+    def test_trig_checksum(self, first_bits, last_bits):
+        a, b = ct.c_uint64(), ct.c_uint64()
+        self._check(self.L.orbx_test_trig_checksum(self._h, first_bits, last_bits, ct.byref(a), ct.byref(b)))
+        return a.value, b.value
+
+    def test_quadtree(self, xys, box_w, box_h, wcell, hcell, ncols, N):
+        xys = np.ascontiguousarray(xys, np.int32).reshape(-1, 3)
+        out = np.zeros((len(xys) + 16, 3), np.int32)
+        n = ct.c_int32()
+        self._check(self.L.orbx_test_quadtree(self._h, _p(xys), len(xys), box_w, box_h, wcell, hcell, ncols, N,
+                                              _p(out), len(out), ct.byref(n)))
+        return out[:n.value].copy()
+
+    def bench_popc(self):
+        v = ct.c_double()
+        self._check(self.L.orbx_bench_popc(self._h, ct.byref(v)))
+        return v.value
+
+    # -- matching (cv::BFMatcher(NORM_HAMMING)) --
+    def match(self, query, train, k=1, max_dist=0.0, ratio=0.0):
+        query = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+        train = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+        out = np.zeros(max(len(query) * k, 1), DM_DTYPE)
+        n = ct.c_int32()
+        self._check(self.L.orbx_match(self._h, _p(query), len(query), _p(train), len(train), k,
+                                      ct.c_float(max_dist), ct.c_float(ratio), _p(out), ct.byref(n)))
+        return out[:n.value].copy()
+
+
+class BFMatcher:
+    """cv::BFMatcher(NORM_HAMMING) call shape over an extractor handle (reference frontend.cpp:220, 294)."""
+
+    def __init__(self, extractor):
+        self.ex = extractor
+
+    def match(self, query, train):
+        return self.ex.match(query, train, k=1)
+
+    def knnMatch(self, query, train, k=2):
+        assert k == 2
+        return self.ex.match(query, train, k=2).reshape(-1, 2)
+
+
+class LandmarkDB:
+    """Row-sharded landmark descriptor database (Backend::associateObservation, backend.cpp:1064-1083)."""
+
+    def __init__(self, extractor, capacity_rows, first_index=0):
+        self.ex = extractor
+        self.L = extractor.L
+        self._db = ct.c_void_p()
+        extractor._check(self.L.orbx_db_create(extractor.handle, capacity_rows, first_index, ct.byref(self._db)))
+
+    def close(self):
+        if self._db.value:
+            self.L.orbx_db_destroy(self._db)
+            self._db = ct.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def rows(self):
+        return int(self.L.orbx_db_rows(self._db))
+
+    def append(self, rows):
+        rows = np.ascontiguousarray(rows, np.uint8).reshape(-1, 32)
+        self.ex._check(self.L.orbx_db_append(self._db, _p(rows), len(rows)))
+
+    def append_device(self, d_rows, nrows):
+        self.ex._check(self.L.orbx_db_append_device(self._db, d_rows, nrows))
+
+    def query_top2(self, query):
+        query = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+        out = np.zeros(len(query), TOP2_DTYPE)
+        self.ex._check(self.L.orbx_db_query_top2(self._db, _p(query), len(query), _p(out)))
+        return out
+
+    def query_top2_device(self, d_query, nq, d_out):
+        self.ex._check(self.L.orbx_db_query_top2_device(self._db, d_query, nq, d_out))
+
+    def query_radius(self, query, max_dist=50.0, cap=1 << 20):
+        query = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+        out = np.zeros(cap, DM_DTYPE)
+        n = ct.c_int32()
+        self.ex._check(self.L.orbx_db_query_radius(self._db, _p(query), len(query), ct.c_float(max_dist), _p(out), cap, ct.byref(n)))
+        return out[:n.value].copy()

@@ -1,0 +1,213 @@
+/* orbx.h — C ABI of the B200-native ORB extract + Hamming match path.
+ *
+ * Drop-in boundary for the ONE data-parallel hot path of andrewkwolek/dynamic-visual-slam
+ * (paths below are relative to the reference's dynamic_visual_slam/ directory):
+ *
+ *   seam 1  ORB_SLAM3::ORBextractor                    include/dynamic_visual_slam/ORBextractor.hpp:44-111
+ *           ctor (nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)            ORBextractor.hpp:50-51
+ *           int operator()(image, mask, keypoints, descriptors, vLappingArea)       ORBextractor.hpp:58-60
+ *           getters + public mvImagePyramid                                         ORBextractor.hpp:62-84
+ *           callers: frontend.cpp:1094, :1285
+ *   seam 2  cv::BFMatcher(NORM_HAMMING).match(query, train, matches) + `distance < 50`
+ *           callers: frontend.cpp:1123-1132, :614-623 ; backend.cpp:1072-1076
+ *   post-filters fused behind the same call: Frontend::filterDepth (frontend.cpp:457-527) and
+ *           Backend::categorizeObservation + filtered_objects_ (backend.cpp:1011-1029, 746-751)
+ *   backend association, descriptor stage: Backend::associateObservation  backend.cpp:1064-1083
+ *
+ * The reference has no FFI layer; this header IS the binding surface a maintainer would call from
+ * the two nodes (see INTEGRATION.md and dynamic-visual-slam_b200/host/ORBextractor.hpp for the
+ * C++ adapter that reproduces the two call shapes over it).  Plain pointers and sizes only; no
+ * torch / OpenCV / CUDA types.  Status codes, never exceptions or aborts.  One handle = one CUDA
+ * device + one stream, single caller at a time (the reference's extractor is not re-entrant either).
+ *
+ * Memory-space convention: functions ending in `_device` take DEVICE pointers and are asynchronous
+ * on the handle's stream (call orbx_sync); all others take HOST pointers and are synchronous.
+ */
+#ifndef ORBX_H
+#define ORBX_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBX_MAX_LEVELS 16
+#define ORBX_DESC_BYTES 32
+
+typedef enum {
+    ORBX_OK = 0,
+    ORBX_E_INVALID = 1,      /* bad argument */
+    ORBX_E_CUDA = 2,         /* CUDA runtime error, see orbx_last_error */
+    ORBX_E_CAPACITY = 3,     /* an output or an internal candidate list was too small; nothing truncated silently */
+    ORBX_E_EMPTY = 4,        /* empty image: the reference's operator() returns -1 here (ORBextractor.cpp:1090) */
+    ORBX_E_NOMEM = 5,
+    ORBX_E_UNSUPPORTED = 6   /* e.g. aspect ratio for which the reference itself divides by zero */
+} orbx_status;
+
+/* 28-byte cv::KeyPoint layout (pt.x, pt.y, size, angle, response, octave, class_id) */
+typedef struct { float x, y, size, angle, response; int32_t octave, class_id; } orbx_keypoint;
+/* 16-byte cv::DMatch layout (queryIdx, trainIdx, imgIdx, distance) */
+typedef struct { int32_t queryIdx, trainIdx, imgIdx; float distance; } orbx_dmatch;
+/* one YOLO detection box, yolo_msgs bbox convention: centre + size in pixels (backend.cpp:1017-1020) */
+typedef struct { double cx, cy, w, h; int32_t class_id; int32_t pad_; } orbx_box;
+/* per-shard top-2 of a landmark-database query (association, backend.cpp:1064-1083) */
+typedef struct { uint32_t dist0, idx0, dist1, idx1; } orbx_top2;
+
+typedef struct {
+    /* ORBextractor ctor arguments — defaults are the reference's literals, frontend.cpp:205-211 */
+    int32_t nfeatures;        /* 1000 */
+    float   scale_factor;     /* 1.2f */
+    int32_t nlevels;          /* 8    */
+    int32_t ini_th_fast;      /* 20   */
+    int32_t min_th_fast;      /* 7    */
+    /* Frontend depth validity range in metres — frontend.cpp:241-242 */
+    float   depth_min;        /* 0.3f */
+    float   depth_max;        /* 3.0f */
+    /* arena sizing */
+    int32_t max_width;        /* 1280 */
+    int32_t max_height;       /* 720  */
+    int32_t max_batch;        /* frames resident per batch call (1) */
+    int32_t max_keypoints;    /* per-frame output capacity; 0 = nfeatures + 4*nlevels + 64 */
+    int32_t cand_divisor;     /* candidate-list capacity per level = max(4096, pixels/cand_divisor); 0 = 16 */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t reserved_[3];
+} orbx_params;
+
+typedef struct orbx_handle orbx_handle;
+typedef struct orbx_db orbx_db;
+
+void        orbx_default_params(orbx_params *p);
+orbx_status orbx_create(const orbx_params *p, orbx_handle **out);
+void        orbx_destroy(orbx_handle *h);
+const char *orbx_last_error(const orbx_handle *h);   /* h may be NULL: last error of a failed create */
+const char *orbx_version(void);
+orbx_status orbx_sync(orbx_handle *h);
+void       *orbx_stream(orbx_handle *h);              /* the handle's cudaStream_t */
+
+/* ---- ORBextractor getters (ORBextractor.hpp:62-82) ---- */
+int32_t orbx_get_levels(const orbx_handle *h);
+float   orbx_get_scale_factor(const orbx_handle *h);
+void    orbx_get_scale_factors(const orbx_handle *h, float *out /*nlevels*/);
+void    orbx_get_inverse_scale_factors(const orbx_handle *h, float *out);
+void    orbx_get_scale_sigma_squares(const orbx_handle *h, float *out);
+void    orbx_get_inverse_scale_sigma_squares(const orbx_handle *h, float *out);
+void    orbx_get_features_per_level(const orbx_handle *h, int32_t *out);
+/* level geometry for a given input size (ComputePyramid, ORBextractor.cpp:1173-1174) */
+orbx_status orbx_level_size(const orbx_handle *h, int32_t width, int32_t height, int32_t level,
+                            int32_t *lw, int32_t *lh);
+
+/* ---- extraction: ORBextractor::operator() (ORBextractor.cpp:1086-1167) ----
+ * gray: CV_8UC1 rows of `step` bytes.  depth (nullable): CV_16UC1 millimetres, rows of `dstep` BYTES;
+ * when given, keypoints without valid depth are dropped after selection (Frontend::filterDepth).
+ * boxes (nullable) + drop_class_mask: keypoints whose first containing box has a class_id c with
+ * bit c set in the mask are dropped after selection (categorizeObservation + filtered_objects_).
+ * Outputs are caller-allocated with capacity `cap`; *n_out receives the count
+ * (ORBX_E_CAPACITY if it would exceed cap).  Featureless frames give *n_out = 0 and ORBX_OK.     */
+orbx_status orbx_extract(orbx_handle *h, const uint8_t *gray, int32_t width, int32_t height, size_t step,
+                         orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *n_out);
+orbx_status orbx_extract_filtered(orbx_handle *h, const uint8_t *gray, int32_t width, int32_t height, size_t step,
+                                  const uint16_t *depth, size_t dstep,
+                                  const orbx_box *boxes, int32_t nboxes, uint64_t drop_class_mask,
+                                  orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *n_out);
+
+/* frame-parallel batch, HOST buffers: frames tightly packed (frame f at gray + f*height*step).
+ * depth nullable.  kps/desc have room for cap_per_frame entries per frame; counts[nframes].
+ * Internally chunks by max_batch and overlaps H2D / compute / D2H.                              */
+orbx_status orbx_extract_batch(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
+                               size_t step, const uint16_t *depth, size_t dstep,
+                               orbx_keypoint *kps, uint8_t *desc, int32_t cap_per_frame, int32_t *counts);
+
+/* frame-parallel batch, DEVICE buffers, asynchronous.  nframes <= max_batch.  Frame f starts at
+ * d_gray + f*frame_stride (bytes); rows are `step` bytes, step % 16 == 0 and 16-byte aligned base.
+ * d_depth nullable (frame stride dframe_stride BYTES, row step dstep BYTES).  Per-frame boxes are
+ * not supported in the batch call (use the single-frame call).  d_kps / d_desc hold cap_per_frame
+ * entries per frame; d_counts[nframes].  Errors detected on the device (capacity) are reported by
+ * the next orbx_sync.                                                                            */
+orbx_status orbx_extract_batch_device(orbx_handle *h, const uint8_t *d_gray, int32_t nframes,
+                                      int32_t width, int32_t height, size_t step, size_t frame_stride,
+                                      const uint16_t *d_depth, size_t dstep, size_t dframe_stride,
+                                      orbx_keypoint *d_kps, uint8_t *d_desc, int32_t cap_per_frame,
+                                      int32_t *d_counts);
+
+/* ---- matching: cv::BFMatcher(NORM_HAMMING) ----
+ * k = 1: BFMatcher::match.   max_dist <= 0: one DMatch per query, query order (exactly match()).
+ *                            max_dist  > 0: only matches with distance < max_dist, query order
+ *                                           (the frontend's `distance < 50` loop, frontend.cpp:1126-1132).
+ * k = 2: BFMatcher::knnMatch(k=2).  ratio <= 0: two DMatch per query (out[2q], out[2q+1]).
+ *                            ratio  > 0: Lowe test, keeps the best match iff d0 < ratio*d1 evaluated
+ *                                        exactly in integers as d0*den < num*d1 with ratio = num/den
+ *                                        rounded to 1/1024; 0.75 is exact.  max_dist also applies if > 0.
+ * Ties resolve to the lowest trainIdx, as BFMatcher does.  out capacity must be nq*k.            */
+orbx_status orbx_match(orbx_handle *h, const uint8_t *query, int32_t nq, const uint8_t *train, int32_t nt,
+                       int32_t k, float max_dist, float ratio, orbx_dmatch *out, int32_t *n_out);
+orbx_status orbx_match_device(orbx_handle *h, const uint8_t *d_query, int32_t nq, const uint8_t *d_train, int32_t nt,
+                              int32_t k, float max_dist, float ratio, orbx_dmatch *d_out, int32_t *d_n_out);
+/* stream matching over a batch: for every pair p in [0,npairs): query = frame q_frame[p], train = frame
+ * t_frame[p] of the (d_desc, d_counts, cap_per_frame) arrays produced by orbx_extract_batch_device.
+ * Outputs: d_out[p*cap_per_frame*k ...], d_n_out[p].  Host index arrays.                          */
+orbx_status orbx_match_pairs_device(orbx_handle *h, const uint8_t *d_desc, const int32_t *d_counts,
+                                    int32_t cap_per_frame, const int32_t *q_frame, const int32_t *t_frame,
+                                    int32_t npairs, int32_t k, float max_dist, float ratio,
+                                    orbx_dmatch *d_out, int32_t *d_n_out);
+
+/* ---- landmark database for Backend::associateObservation (descriptor stage) ----
+ * A shard holds `rows` 32-byte descriptors whose GLOBAL landmark indices are first_index ..
+ * first_index+rows-1.  Query returns, per query, the two nearest rows of THIS shard as
+ * (distance, global index), ties to the lowest index.  Shards on different GPUs are merged with
+ * orbx_merge_top2 after an all-gather of the per-shard results.                   */
+orbx_status orbx_db_create(orbx_handle *h, int64_t capacity_rows, uint32_t first_index, orbx_db **out);
+void        orbx_db_destroy(orbx_db *db);
+orbx_status orbx_db_append(orbx_db *db, const uint8_t *rows_host, int64_t nrows);
+orbx_status orbx_db_append_device(orbx_db *db, const uint8_t *d_rows, int64_t nrows);
+int64_t     orbx_db_rows(const orbx_db *db);
+orbx_status orbx_db_query_top2_device(orbx_db *db, const uint8_t *d_query, int32_t nq, orbx_top2 *d_out);
+orbx_status orbx_db_query_top2(orbx_db *db, const uint8_t *query, int32_t nq, orbx_top2 *out);
+/* merge nshards per-shard results laid out [shard][nq] into out[nq] (lexicographic (dist, idx) min) */
+orbx_status orbx_merge_top2_device(orbx_handle *h, const orbx_top2 *d_parts, int32_t nshards, int32_t nq,
+                                   orbx_top2 *d_out);
+/* reference semantics of the descriptor stage: every row with distance < max_dist is a candidate
+ * (backend.cpp:1074-1076).  Writes up to cap (query, global idx, distance) triples as orbx_dmatch
+ * (queryIdx, trainIdx = global idx, imgIdx = 0, distance), sorted by (queryIdx, trainIdx).        */
+orbx_status orbx_db_query_radius(orbx_db *db, const uint8_t *query, int32_t nq, float max_dist,
+                                 orbx_dmatch *out, int32_t cap, int32_t *n_out);
+
+/* ---- stage access for parity tests (the reference exposes mvImagePyramid publicly, ORBextractor.hpp:84) ----
+ * Valid after an extract call, for frame slot `frame` of the last batch.  Host outputs.          */
+orbx_status orbx_get_pyramid_level(orbx_handle *h, int32_t frame, int32_t level, uint8_t *out, size_t out_step);
+orbx_status orbx_get_blurred_level(orbx_handle *h, int32_t frame, int32_t level, uint8_t *out, size_t out_step);
+/* FAST candidates of a level before distribution: packed (x, y, score) relative to the border box,
+ * unordered.  out_xys: int32 triples.                                                             */
+orbx_status orbx_get_candidates(orbx_handle *h, int32_t frame, int32_t level, int32_t *out_xys, int32_t cap, int32_t *n_out);
+/* keypoints per level retained by the quadtree, in the reference's list order */
+orbx_status orbx_get_level_counts(orbx_handle *h, int32_t frame, int32_t *out /*nlevels*/);
+
+/* ---- seeded synthetic inputs, generated on the device (bench / tests; identical bytes to the oracle's generator) ---- */
+orbx_status orbx_synth_gray_device(orbx_handle *h, uint32_t seed, int32_t first_frame, int32_t nframes,
+                                   int32_t width, int32_t height, uint8_t *d_out, size_t step, size_t frame_stride);
+orbx_status orbx_synth_depth_device(orbx_handle *h, uint32_t seed, int32_t first_frame, int32_t nframes,
+                                    int32_t width, int32_t height, uint16_t *d_out, size_t step_bytes, size_t frame_stride_bytes);
+orbx_status orbx_synth_descriptors_device(orbx_handle *h, uint32_t seed, uint64_t first_row, int64_t nrows, uint8_t *d_out);
+
+/* ---- utilities ---- */
+void *orbx_alloc_pinned(size_t bytes);
+void  orbx_free_pinned(void *p);
+void *orbx_alloc_device(orbx_handle *h, size_t bytes);
+void  orbx_free_device(orbx_handle *h, void *p);
+orbx_status orbx_copy_to_device(orbx_handle *h, void *d_dst, const void *src, size_t bytes);
+orbx_status orbx_copy_to_host(orbx_handle *h, void *dst, const void *d_src, size_t bytes);
+/* device self-tests used by the parity suite: evaluate the device cosf/sinf/fastAtan2 restatements */
+orbx_status orbx_test_trig(orbx_handle *h, const float *in, int32_t n, float *out_cos, float *out_sin);
+orbx_status orbx_test_atan2(orbx_handle *h, const float *y, const float *x, int32_t n, float *out);
+/* checksum of device cosf/sinf over every float32 angle in [0,360] degrees (exhaustive pin vs glibc) */
+orbx_status orbx_test_trig_checksum(orbx_handle *h, uint32_t first_bits, uint32_t last_bits, uint64_t *sum_cos, uint64_t *sum_sin);
+orbx_status orbx_test_quadtree(orbx_handle *h, const int32_t *xys, int32_t n, int32_t box_w, int32_t box_h,
+                               int32_t wcell, int32_t hcell, int32_t ncols, int32_t N, int32_t *out_xys, int32_t cap, int32_t *n_out);
+/* POPC issue-rate microbenchmark (matching roofline denominator): returns popc/s over the whole GPU */
+orbx_status orbx_bench_popc(orbx_handle *h, double *popc_per_sec);
+/* number of kernels this library has launched on the handle since creation */
+int64_t orbx_launch_count(const orbx_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBX_H */

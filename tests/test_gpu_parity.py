@@ -1,0 +1,87 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle, stage by stage.
+
+Bars (BASELINE.json north_star): pyramid levels, FAST corners, smoothed images, descriptors and Hamming
+matches bit-exact; retained keypoint sets identical (we also require identical ORDER, i.e. the
+reference's list order, which DMatch indices depend on).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(1280, 720, 7), (640, 480, 3), (741, 417, 11)]
+
+
+@pytest.fixture(scope="module")
+def ex(built):
+    import orbx
+    e = orbx.ORBextractor(max_width=1280, max_height=720, max_batch=4)
+    yield e
+    e.close()
+
+
+def _kp_table(k):
+    return np.stack([k["x"], k["y"], k["size"], k["angle"], k["response"], k["octave"].astype(np.float32),
+                     k["class_id"].astype(np.float32)], 1)
+
+
+@pytest.mark.parametrize("w,h,seed", SIZES)
+def test_stages_bit_exact(ex, oracle, w, h, seed):
+    g = oracle.synth_gray(seed, 0, w, h)
+    orc = oracle.COracle()
+    ref = orc.extract(g, trace=True)
+    kps, desc = ex(g)
+    # a1: ctor tables
+    assert list(ex.features_per_level()) == orc.nfeat
+    assert np.array_equal(ex.GetScaleFactors(), orc.scale)
+    for l in range(8):
+        # a2: pyramid levels bit-exact
+        assert np.array_equal(ex.pyramid_level(l), ref["pyramid"][l]), "pyramid level %d" % l
+        # a7: smoothed levels bit-exact
+        assert np.array_equal(ex.blurred_level(l), ref["blurred"][l]), "blurred level %d" % l
+        # a3: FAST corners (set equality; the device list is unordered by design)
+        c = ex.candidates(l)
+        r = ref["cands"][l]
+        rc = np.stack([r["x"], r["y"], r["score"]], 1)
+        assert len(c) == len(rc), ("candidate count level %d" % l, len(c), len(rc))
+        cs = c[np.lexsort((c[:, 0], c[:, 1]))]
+        rs = rc[np.lexsort((rc[:, 0], rc[:, 1]))]
+        assert np.array_equal(cs, rs), "FAST candidates level %d" % l
+    # a4: retained per level
+    assert list(ex.level_counts()) == ref["nkeys"]
+    # a5/a6/a8/a9: keypoints (order, coordinates, size, angle, response, octave) and descriptors bit-exact
+    assert len(kps) == len(ref["kps"])
+    assert np.array_equal(kps.view(np.uint8), ref["kps"].view(np.uint8)), "keypoints"
+    assert np.array_equal(desc, ref["desc"]), "descriptors"
+
+
+def test_match_bit_exact(ex, oracle):
+    w, h = 1280, 720
+    g0, g1 = oracle.synth_gray(7, 0, w, h), oracle.synth_gray(7, 1, w, h)
+    _, d0 = ex(g0)
+    _, d1 = ex(g1)
+    m = ex.match(d1, d0, k=1)
+    mo = oracle.match(d1, d0)
+    assert np.array_equal(m.view(np.uint8), mo.view(np.uint8))
+    # frontend's distance < 50 loop (frontend.cpp:1126-1132)
+    mf = ex.match(d1, d0, k=1, max_dist=50.0)
+    assert np.array_equal(mf.view(np.uint8), mo[mo["distance"] < 50.0].view(np.uint8))
+    # knnMatch k=2 and ratio 0.75
+    k2 = ex.match(d1, d0, k=2).reshape(-1, 2)
+    ko = oracle.knn2(d1, d0)
+    assert np.array_equal(k2.view(np.uint8), ko.view(np.uint8))
+    good = ex.match(d1, d0, k=2, ratio=0.75)
+    keep = ko[:, 0]["distance"] < np.float32(0.75) * ko[:, 1]["distance"]
+    assert np.array_equal(good.view(np.uint8), ko[keep, 0].view(np.uint8))
+
+
+def test_depth_filter(ex, oracle):
+    w, h = 1280, 720
+    g = oracle.synth_gray(9, 2, w, h)
+    d = oracle.synth_depth(9, 2, w, h)
+    kps, desc = ex(g)
+    fk, fd = ex(g, depth=d)
+    ok, od, _ = oracle.filter_depth(kps, desc, d)
+    assert 0 < len(ok) < len(kps)
+    assert np.array_equal(fk.view(np.uint8), ok.view(np.uint8))
+    assert np.array_equal(fd, od)
