@@ -31,32 +31,32 @@ struct FastParams {
 
 // ring offsets in a pitch-80 tile, order of SURVEY App. A.2
 #define RO(dx, dy) ((dy) * FT_PITCH + (dx))
-__device__ __constant__ int c_ring[16] = {
-    RO(0, 3), RO(1, 3), RO(2, 2), RO(3, 1), RO(3, 0), RO(3, -1), RO(2, -2), RO(1, -3),
-    RO(0, -3), RO(-1, -3), RO(-2, -2), RO(-3, -1), RO(-3, 0), RO(-3, 1), RO(-2, 2), RO(-1, 3) };
-
 __device__ __forceinline__ int fast_score(const uint8_t *p)
 {
-    // d[k] = I(p) - I(ring_k); S = max_k max( min_{j<9} d[k+j], min_{j<9} -d[k+j] )
+    // S = max( I(p) - min_k max9_k(ring),  max_k min9_k(ring) - I(p) ) over the 16 arcs of 9 contiguous ring
+    // pixels: "all darker by more than t" <=> I(p) - max9 > t ; "all brighter" <=> min9 - I(p) > t.
+    // Formulated on the raw ring values (no negated operands) with a log-step sliding window.
     const int v = p[0];
-    int d[16];
-    d[0] = v - p[RO(0, 3)];   d[1] = v - p[RO(1, 3)];    d[2] = v - p[RO(2, 2)];    d[3] = v - p[RO(3, 1)];
-    d[4] = v - p[RO(3, 0)];   d[5] = v - p[RO(3, -1)];   d[6] = v - p[RO(2, -2)];   d[7] = v - p[RO(1, -3)];
-    d[8] = v - p[RO(0, -3)];  d[9] = v - p[RO(-1, -3)];  d[10] = v - p[RO(-2, -2)]; d[11] = v - p[RO(-3, -1)];
-    d[12] = v - p[RO(-3, 0)]; d[13] = v - p[RO(-3, 1)];  d[14] = v - p[RO(-2, 2)];  d[15] = v - p[RO(-1, 3)];
+    int r[16];
+    r[0] = p[RO(0, 3)];   r[1] = p[RO(1, 3)];    r[2] = p[RO(2, 2)];    r[3] = p[RO(3, 1)];
+    r[4] = p[RO(3, 0)];   r[5] = p[RO(3, -1)];   r[6] = p[RO(2, -2)];   r[7] = p[RO(1, -3)];
+    r[8] = p[RO(0, -3)];  r[9] = p[RO(-1, -3)];  r[10] = p[RO(-2, -2)]; r[11] = p[RO(-3, -1)];
+    r[12] = p[RO(-3, 0)]; r[13] = p[RO(-3, 1)];  r[14] = p[RO(-2, 2)];  r[15] = p[RO(-1, 3)];
     int mn2[16], mx2[16], mn4[16], mx4[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) { mn2[k] = min(d[k], d[(k + 1) & 15]); mx2[k] = max(d[k], d[(k + 1) & 15]); }
+    for (int k = 0; k < 16; k++) { mn2[k] = min(r[k], r[(k + 1) & 15]); mx2[k] = max(r[k], r[(k + 1) & 15]); }
 #pragma unroll
     for (int k = 0; k < 16; k++) { mn4[k] = min(mn2[k], mn2[(k + 2) & 15]); mx4[k] = max(mx2[k], mx2[(k + 2) & 15]); }
-    int best = -256;
+    int hi_of_min = 0, lo_of_max = 255;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
-        const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
-        best = max(best, max(mn9, -mx9));
+        const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), r[(k + 8) & 15]);
+        const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), r[(k + 8) & 15]);
+        hi_of_min = max(hi_of_min, mn9);
+        lo_of_max = min(lo_of_max, mx9);
     }
-    return best;
+    const int s_dark = v - lo_of_max, s_bright = hi_of_min - v;
+    return s_dark > s_bright ? s_dark : s_bright;
 }
 
 __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(FastParams P, const FrameGeom *__restrict__ G)
