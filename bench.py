@@ -1,0 +1,386 @@
+#!/usr/bin/env python3
+"""bench.py — ORB extract + Hamming match throughput at 1280x720 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+
+A "step" is one pass of the hot path over one batch of B synthetic 1280x720 RGB-D frames:
+8-level pyramid -> per-cell FAST -> quadtree -> orientation -> blur -> rBRIEF-256 -> depth filter ->
+brute-force Hamming match of every frame against its predecessor with `distance < 50`
+(BASELINE.json configs[1]; reference frontend.cpp:1094-1132).
+  value : frames/s with the batch resident in HBM (orbx_track_batch_device), whole job over all ranks
+  e2e   : frames/s through the host-buffer C-ABI call (orbx_track_batch): pinned host frames in,
+          keypoints/descriptors/matches out, H2D and D2H inside the timed region
+PyTorch is plumbing only here (device buffers, stream wrapper for CUDA events, torch.distributed).
+"""
+import argparse
+import ctypes as ct
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "dynamic-visual-slam_b200", "python"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+W, H = 1280, 720
+SEED = 20261018
+METRIC = "frames/s ORB extract+Hamming match, 1280x720"
+# algorithmic bytes per 1280x720 frame, staged model; pixels summed over the 8 levels
+LEVEL_PX = [1280 * 720, 1067 * 600, 889 * 500, 741 * 417, 617 * 347, 514 * 289, 429 * 241, 357 * 201]
+ALG_BYTES = {
+    "k_resize_linear": sum(LEVEL_PX[:7]) + sum(LEVEL_PX[1:]),      # read L0..L6 once, write L1..L7 once (7 launches)
+    "k_fast_cells": sum(LEVEL_PX),                                  # read every level once
+    "k_blur7": 2 * sum(LEVEL_PX),                                   # read + write every level once
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_path(frames, depths, nthreads):
+    """The reference's CPU path (oracle port): extract -> filterDepth -> match vs previous, `distance < 50`."""
+    import c_oracle as co
+    orc = cpu_path.orc
+    t0 = time.perf_counter()
+    kps, desc, counts = orc.extract_batch(frames, cap=2048, nthreads=nthreads)
+    prev = None
+    nmatch = 0
+    for f in range(len(frames)):
+        k, d, _ = co.filter_depth(kps[f, :counts[f]], desc[f, :counts[f]], depths[f])
+        if prev is not None and len(d) and len(prev):
+            m = co.match(d, prev, nthreads=nthreads)
+            nmatch += int((m["distance"] < 50.0).sum())
+        prev = d
+    return time.perf_counter() - t0, nmatch
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path (the oracle's C port — the
+    reference's C++ needs OpenCV/ROS headers and cannot be compiled here) with all host threads."""
+    if rank != 0:
+        return
+    import c_oracle as co
+    co.build()
+    cores = os.cpu_count() or 1
+    S = max(8, min(32, cores))                      # bounded sample of the 1280x720 stream per step
+    frames = np.stack([co.synth_gray(SEED, f, W, H) for f in range(S)])
+    depths = np.stack([co.synth_depth(SEED, f, W, H) for f in range(S)])
+    cpu_path.orc = co.COracle()
+    for _ in range(args.warmup):
+        cpu_path(frames, depths, cores)
+    t = 0.0
+    for _ in range(args.steps):
+        dt, _ = cpu_path(frames, depths, cores)
+        t += dt
+    fps = S * args.steps / t
+    sample = "%d frames/step of the synthetic 1280x720 RGB-D stream, extract+filterDepth+match" % S
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "configs[1]: 1280x720 RGB-D stream, depth-filtered extraction + frame-to-frame matching",
+                   "frames_per_step": S, "nfeatures": 1000, "nlevels": 8},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="orbx", choices=["orbx", "reference"])
+    ap.add_argument("--batch", type=int, default=128, help="frames resident per step and per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-assoc", action="store_true", help="skip the landmark-association leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import orbx
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the ORB path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    B, K, CAP = args.batch, args.steps, 1280
+    ex = orbx.ORBextractor(max_width=W, max_height=H, max_batch=B, device=local_rank, max_keypoints=CAP)
+    L, hnd = ex.L, ex.handle
+    stream = torch.cuda.ExternalStream(ex.stream, device=dev)
+
+    # ---- synthetic inputs generated in HBM; rank r owns frames [r*B, (r+1)*B) of the stream ----
+    gray = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+    depth = torch.empty((B, H, W), dtype=torch.int16, device=dev)
+    ex._check(L.orbx_synth_gray_device(hnd, SEED, rank * B, B, W, H, gray.data_ptr(), W, W * H))
+    ex._check(L.orbx_synth_depth_device(hnd, SEED, rank * B, B, W, H, depth.data_ptr(), 2 * W, 2 * W * H))
+    kps = torch.empty((B, CAP, 28), dtype=torch.uint8, device=dev)
+    desc = torch.empty((B, CAP, 32), dtype=torch.uint8, device=dev)
+    counts = torch.zeros(B, dtype=torch.int32, device=dev)
+    matches = torch.empty((B, CAP, 16), dtype=torch.uint8, device=dev)
+    mcounts = torch.zeros(B, dtype=torch.int32, device=dev)
+
+    def step():
+        ex._check(L.orbx_track_batch_device(hnd, gray.data_ptr(), B, W, H, W, W * H, depth.data_ptr(), 2 * W, 2 * W * H,
+                                            kps.data_ptr(), desc.data_ptr(), CAP, counts.data_ptr(),
+                                            matches.data_ptr(), mcounts.data_ptr(), ct.c_float(50.0)))
+
+    def barrier():
+        ex.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ex.profile_enable(True)
+    launches0 = ex.launch_count
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        step()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    gpu_launches = ex.launch_count - launches0
+    prof = ex.profile_read()
+    ex.profile_enable(False)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * K / (ms * 1e-3)
+    nkp = counts.cpu().numpy()
+    nm = mcounts.cpu().numpy()
+
+    # ---- per-kernel device time and roofline of the dense stages ----
+    hbm, peak_src = peaks()
+    total_k = sum(v[0] for v in prof.values()) or 1.0
+    kernels = {}
+    for name, (kms, cnt) in prof.items():
+        if cnt == 0:
+            continue
+        kernels[name] = {"ms_per_step": kms / K, "launches_per_step": cnt / K, "share": kms / total_k}
+        if name in ALG_BYTES:
+            gbs = ALG_BYTES[name] * B * K / (kms * 1e-3) / 1e9
+            kernels[name].update({"achieved_gbs": gbs, "frac_of_hbm": gbs / hbm})
+    dense = [n for n in ALG_BYTES if n in kernels]
+    dom = max(dense, key=lambda n: kernels[n]["ms_per_step"]) if dense else None
+    roofline = None
+    if dom:
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
+                    "frac": kernels[dom]["frac_of_hbm"], "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": ALG_BYTES[dom] * B / max(1.0, kernels[dom]["launches_per_step"]),
+                    "dominant_overall": max(kernels, key=lambda n: kernels[n]["ms_per_step"])}
+
+    # ---- e2e: the host-buffer C-ABI call, pinned host memory, H2D + D2H inside the timed region ----
+    e2e = None
+    Be = B
+    nbytes_g, nbytes_d = Be * W * H, Be * W * H * 2
+    hp = {}
+    sizes = {"gray": nbytes_g, "depth": nbytes_d, "kps": Be * CAP * 28, "desc": Be * CAP * 32, "cnt": Be * 4,
+             "m": Be * CAP * 16, "mc": Be * 4}
+    for k, n in sizes.items():
+        hp[k] = L.orbx_alloc_pinned(n)
+        if not hp[k]:
+            raise SystemExit("pinned allocation failed")
+    ex._check(L.orbx_copy_to_host(hnd, hp["gray"], gray.data_ptr(), nbytes_g))
+    ex._check(L.orbx_copy_to_host(hnd, hp["depth"], depth.data_ptr(), nbytes_d))
+
+    def step_e2e(nf=Be):
+        ex._check(L.orbx_track_batch(hnd, hp["gray"], nf, W, H, W, hp["depth"], 2 * W, hp["kps"], hp["desc"], CAP, hp["cnt"],
+                                     hp["m"], hp["mc"], ct.c_float(50.0)))
+
+    for _ in range(args.warmup):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(K):
+        step_e2e()
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    ms_e = max(e0.elapsed_time(e1), 0.0)
+    ms_e = max(ms_e, wall * 1e3) if ms_e == 0 else ms_e
+    if dist is not None:
+        t = torch.tensor([ms_e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e = float(t.item())
+    e2e = {"value": world * Be * K / (ms_e * 1e-3), "unit": "frames/s",
+           "h2d_bytes_per_step": nbytes_g + nbytes_d,
+           "d2h_bytes_per_step": Be * (CAP * (28 + 32 + 16) + 8),
+           "api": "orbx_track_batch (host pinned buffers)", "ms_per_step": ms_e / K, "host_wall_ms_per_step": wall * 1e3 / K}
+
+    # ---- per-frame latency, batch = 1 through the same host call (configs[1] p50) ----
+    lat = []
+    ex.track_reset()
+    for i in range(220):
+        t0 = time.perf_counter()
+        step_e2e(1)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    lat = np.array(lat[20:])
+    latency = {"p50_ms": float(np.percentile(lat, 50)), "p95_ms": float(np.percentile(lat, 95)), "frames": len(lat),
+               "api": "orbx_track_batch, nframes=1, host buffers"}
+
+    # ---- landmark association (configs[3]): 2048 queries vs a 1M-row database sharded over the ranks ----
+    assoc = None
+    if not args.no_assoc:
+        NQ, ROWS = 2048, 1 << 20
+        rows_r = ROWS // world
+        db = orbx.LandmarkDB(ex, rows_r, first_index=rank * rows_r)
+        drows = torch.empty((rows_r, 32), dtype=torch.uint8, device=dev)
+        ex._check(L.orbx_synth_descriptors_device(hnd, 1234, rank * rows_r, rows_r, drows.data_ptr()))
+        db.append_device(drows.data_ptr(), rows_r)
+        q = torch.empty((NQ, 32), dtype=torch.uint8, device=dev)
+        ex._check(L.orbx_synth_descriptors_device(hnd, 1234, 0, NQ, q.data_ptr()))       # queries = rows 0..NQ-1 (exact hits on shard 0)
+        part = torch.empty((NQ, 4), dtype=torch.int32, device=dev)
+        gathered = torch.empty((world, NQ, 4), dtype=torch.int32, device=dev)
+        merged = torch.empty((NQ, 4), dtype=torch.int32, device=dev)
+
+        def assoc_step():
+            db.query_top2_device(q.data_ptr(), NQ, part.data_ptr())
+            if dist is not None:
+                ex.sync()                                   # hand-over from the handle's stream to torch's NCCL stream
+                dist.all_gather_into_tensor(gathered, part)
+                torch.cuda.synchronize()
+                ex._check(L.orbx_merge_top2_device(hnd, gathered.data_ptr(), world, NQ, merged.data_ptr()))
+
+        for _ in range(3):
+            assoc_step()
+        barrier()
+        ex.profile_enable(True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(K):
+            assoc_step()
+        e1.record(stream)
+        barrier()
+        wall_a = (time.perf_counter() - t0) * 1e3 / K
+        profa = ex.profile_read()
+        ex.profile_enable(False)
+        ms_a = (e0.elapsed_time(e1) / K) if dist is None else wall_a
+        if dist is not None:
+            t = torch.tensor([ms_a], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_a = float(t.item())
+        res = (merged if dist is not None else part).cpu().numpy().view(np.uint32)
+        popc = ex.bench_popc()
+        kms = profa["k_match_partial"][0] / max(1, profa["k_match_partial"][1])
+        pairs = NQ * rows_r
+        assoc = {"queries": NQ, "db_rows": ROWS, "rows_per_gpu": rows_r, "ms_per_query_batch": ms_a,
+                 "gpairs_per_s": NQ * ROWS / (ms_a * 1e-3) / 1e9, "exact_hits": int((res[:, 0] == 0).sum()),
+                 "kernel_ms": kms, "popc_per_s_measured_peak": popc,
+                 "popc_frac": (8.0 * pairs / (kms * 1e-3)) / popc if popc > 0 and kms > 0 else None,
+                 "collective": "nccl all_gather_into_tensor of 32 KB/rank + merge kernel" if dist is not None else "none (1 GPU)"}
+        db.close()
+
+    # ---- reference CPU path timed beside it (rank 0, N = 1 only) ----
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import c_oracle as co
+        co.build()
+        cores = os.cpu_count() or 1
+        S = max(16, min(64, 2 * cores))
+        fr = np.stack([co.synth_gray(SEED, f, W, H) for f in range(S)])
+        dp = np.stack([co.synth_depth(SEED, f, W, H) for f in range(S)])
+        cpu_path.orc = co.COracle()
+        cpu_path(fr[:4], dp[:4], cores)
+        dt, _ = cpu_path(fr, dp, cores)
+        cpu_baseline = {"value": S / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+                        "sample": "%d frames of the same synthetic stream, extract+filterDepth+match, OpenMP over %d threads" % (S, cores)}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "configs[1]: 1280x720 RGB-D stream, 8-level pyramid scale 1.2, depth-filtered extraction + "
+                                   "frame-to-frame matching (k=1, distance<50)", "frames_per_step_per_gpu": B, "width": W, "height": H,
+                       "nfeatures": 1000, "nlevels": 8, "l2_policy": "inputs larger than L2 (%.0f MB per step per GPU)" % (B * W * H * 3 / 1e6),
+                       "sharding": "frame-parallel, no data-path collective"},
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "e2e": e2e, "latency": latency,
+            "association": assoc, "gpu_launches": int(gpu_launches), "clocks": clocks,
+            "keypoints_per_frame": float(nkp.mean()), "matches_per_frame": float(nm.mean()),
+        }
+        print(json.dumps(out))
+    for p in hp.values():
+        L.orbx_free_pinned(p)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

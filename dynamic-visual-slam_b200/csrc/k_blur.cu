@@ -90,6 +90,6 @@ void launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step,
     P.pyr = h->d_pyr; P.pyr_slab = h->pyr_slab;
     P.blur = h->d_blur; P.blur_slab = h->blur_slab;
     dim3 grid(h->geo.total_blur_tiles, nframes);
+    ProfScope ps(h, ORBX_K_BLUR);
     k_blur7<<<grid, 256, 0, h->stream>>>(P, h->d_geo);
-    h->launches++;
 }

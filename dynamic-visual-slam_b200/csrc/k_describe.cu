@@ -190,8 +190,8 @@ void launch_describe_to(orbx_handle *h, int nframes, const uint8_t *l0, size_t l
     P.kps = d_kps; P.desc = d_desc; P.cap = cap; P.counts = d_counts; P.status = h->d_status;
     const int maxk = h->geo.sel_entries < cap ? h->geo.sel_entries : cap;
     dim3 grid((maxk + DESC_WARPS - 1) / DESC_WARPS, nframes);
+    ProfScope ps(h, ORBX_K_DESCRIBE);
     k_describe<<<grid, DESC_WARPS * 32, 0, h->stream>>>(P, h->d_geo);
-    h->launches++;
 }
 
 // ---- device self-tests of the floating-point restatements ----

@@ -162,6 +162,6 @@ void launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step,
     P.ini_th = h->prm.ini_th_fast; P.min_th = h->prm.min_th_fast;
     P.status = h->d_status;
     dim3 grid(h->geo.total_cells, nframes);
+    ProfScope ps(h, ORBX_K_FAST);
     k_fast_cells<<<grid, FAST_THREADS, 0, h->stream>>>(P, h->d_geo);
-    h->launches++;
 }

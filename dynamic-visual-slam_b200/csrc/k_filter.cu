@@ -92,6 +92,6 @@ void launch_filter(orbx_handle *h, int nframes, const uint16_t *d_depth, size_t 
     P.dmin = h->prm.depth_min; P.dmax = h->prm.depth_max;
     P.boxes = d_boxes; P.nboxes = nboxes; P.drop_mask = drop_mask;
     P.kout = d_kps; P.dout = d_desc; P.nout = d_counts; P.cap_out = cap; P.status = h->d_status;
+    ProfScope ps(h, ORBX_K_FILTER);
     k_filter<<<nframes, 256, 0, h->stream>>>(P);
-    h->launches++;
 }

@@ -210,8 +210,8 @@ int launch_match_core(orbx_handle *h, const uint8_t *d_q, const int32_t *d_nq, i
         dim3 grid((nq_max + MT_THREADS - 1) / MT_THREADS, nsplit, nproblems);
         // every slot the epilogue reads (qi < nq, all splits) is written by the partial kernel; splits that
         // start beyond a problem's own nt write the "empty" key
+        ProfScope ps(h, ORBX_K_MATCH);
         k_match_partial<<<grid, MT_THREADS, 0, h->stream>>>(P);
-        h->launches++;
     }
     MatchEpiParams E;
     E.part = (const unsigned long long *)h->d_mpart; E.nq_max = nq_max; E.nsplit = nsplit;
@@ -219,8 +219,8 @@ int launch_match_core(orbx_handle *h, const uint8_t *d_q, const int32_t *d_nq, i
     E.qsel = d_qsel; E.tsel = d_tsel;
     E.k = k; E.max_dist = max_dist; E.ratio_num = ratio_num;
     E.out = d_out; E.out_stride = out_stride; E.n_out = d_n_out; E.top2 = d_top2;
+    ProfScope ps(h, ORBX_K_MATCH_EPI);
     k_match_epilogue<<<nproblems, 256, 0, h->stream>>>(E);
-    h->launches++;
     return 0;
 }
 

@@ -58,6 +58,6 @@ void launch_resize_level(orbx_handle *h, int level, int nframes, const uint8_t *
     P.sw = gs.w; P.sh = gs.h; P.dw = gd.w; P.dh = gd.h;
     P.xtab = h->d_xtab + gd.xtab_off; P.ytab = h->d_ytab + gd.ytab_off;
     dim3 block(32, 8), grid((gd.w + 127) / 128, (gd.h + 7) / 8, nframes);
+    ProfScope ps(h, ORBX_K_RESIZE);
     k_resize_linear<<<grid, block, 0, h->stream>>>(P);
-    h->launches++;
 }

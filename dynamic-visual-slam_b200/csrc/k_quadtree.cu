@@ -458,8 +458,8 @@ void launch_quadtree_geo(orbx_handle *h, const FrameGeom *d_geo, int nlevels, in
         configured = smem;
     }
     dim3 grid(nlevels, nframes);
+    ProfScope ps(h, ORBX_K_QUADTREE);
     k_quadtree<<<grid, QT_THREADS, smem, h->stream>>>(P, d_geo);
-    h->launches++;
 }
 
 void launch_quadtree(orbx_handle *h, int nframes)

@@ -10,6 +10,7 @@
 #include <mutex>
 
 static std::string g_create_err;
+static orbx_status grow(orbx_handle *h, uint8_t **p, size_t *cap, size_t need);
 static inline int cv_round_f(float v) { return (int)lrintf(v); }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -143,7 +144,8 @@ extern "C" void orbx_destroy(orbx_handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    void *dev[] = { h->d_geo, h->d_xtab, h->d_ytab, h->d_pyr, h->d_blur, h->d_in, h->d_depth_in, h->d_cand, h->d_cand2, h->d_qtmp,
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+    void *dev[] = { h->d_prev_desc, h->d_prev_count, h->d_geo, h->d_xtab, h->d_ytab, h->d_pyr, h->d_blur, h->d_in, h->d_depth_in, h->d_cand, h->d_cand2, h->d_qtmp,
                     h->d_owner, h->d_owner2, h->d_ncand, h->d_sel, h->d_nsel, h->d_kps_all, h->d_desc_all, h->d_count_all,
                     h->d_kps_out, h->d_desc_out, h->d_count_out, h->d_boxes, h->d_status, h->d_mpart, h->d_mq, h->d_mt, h->d_mout, h->d_mcount };
     for (void *p : dev) if (p) cudaFree(p);
@@ -173,6 +175,8 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     if (p.device < 0 || p.device >= ndev) { g_create_err = "device ordinal out of range"; return ORBX_E_INVALID; }
     orbx_handle *h = new orbx_handle();
     h->prm = p; h->device = p.device; h->launches = 0; h->geo.width = -1; h->geo.height = -1;
+    h->prof_on = 0; h->prof_n = 0; h->prev_valid = 0;
+    memset(h->prof_ms, 0, sizeof(h->prof_ms)); memset(h->prof_cnt, 0, sizeof(h->prof_cnt));
     CREATE_CUDA(cudaSetDevice(p.device));
     cudaDeviceProp prop;
     CREATE_CUDA(cudaGetDeviceProperties(&prop, p.device));
@@ -217,6 +221,9 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     CREATE_CUDA(cudaMalloc(&h->d_kps_out, B * h->max_kp * sizeof(orbx_keypoint)));
     CREATE_CUDA(cudaMalloc(&h->d_desc_out, B * h->max_kp * ORBX_DESC_BYTES));
     CREATE_CUDA(cudaMalloc(&h->d_count_out, B * sizeof(int32_t)));
+    CREATE_CUDA(cudaMalloc(&h->d_prev_desc, (size_t)h->max_kp * ORBX_DESC_BYTES));
+    CREATE_CUDA(cudaMalloc(&h->d_prev_count, sizeof(int32_t)));
+    CREATE_CUDA(cudaMemset(h->d_prev_count, 0, sizeof(int32_t)));
     h->boxes_cap = 256;
     CREATE_CUDA(cudaMalloc(&h->d_boxes, h->boxes_cap * sizeof(orbx_box)));
     CREATE_CUDA(cudaMalloc(&h->d_status, sizeof(int32_t)));
@@ -388,6 +395,107 @@ extern "C" orbx_status orbx_extract_batch(orbx_handle *h, const uint8_t *gray, i
                                        (size_t)kcap * sizeof(orbx_keypoint), (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
         ORBX_CUDA(h, cudaMemcpy2DAsync(desc + (size_t)f0 * cap * ORBX_DESC_BYTES, (size_t)cap * ORBX_DESC_BYTES, h->d_desc_out, (size_t)h->max_kp * ORBX_DESC_BYTES,
                                        (size_t)kcap * ORBX_DESC_BYTES, (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
+        st = check_device_status(h);
+        if (st != ORBX_OK) return st;
+        for (int f = 0; f < nb; f++) if (counts[f0 + f] > cap) { h->err = "output capacity too small"; return ORBX_E_CAPACITY; }
+    }
+    return ORBX_OK;
+}
+
+// ---- stream step: extraction + depth filter + match against the previous frame (frontend.cpp:1094-1132) ----
+extern "C" void orbx_track_reset(orbx_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaMemsetAsync(h->d_prev_count, 0, sizeof(int32_t), h->stream);
+    h->prev_valid = 0;
+}
+
+static orbx_status track_device(orbx_handle *h, const uint8_t *d_gray, int nframes, int width, int height, size_t step, size_t fstride,
+                                const uint16_t *d_depth, size_t dstep, size_t dfstride,
+                                orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts,
+                                orbx_dmatch *d_matches, int32_t *d_mcounts, float max_dist)
+{
+    if (cap > h->max_kp) { h->err = "cap_per_frame larger than the handle's max_keypoints"; return ORBX_E_INVALID; }
+    orbx_status st = run_pipeline(h, nframes, d_gray, step, fstride, d_depth, dstep, dfstride, nullptr, 0, 0, d_kps, d_desc, cap, d_counts);
+    if (st != ORBX_OK) return st;
+    // frame 0 against the carried state (prev count is 0 on the first frame => no matches, count 0)
+    if (launch_match_core(h, d_desc, d_counts, cap, 0, h->d_prev_desc, h->d_prev_count, h->max_kp, 0, nullptr, nullptr, 1, 0,
+                          1, max_dist, 0, d_matches, (size_t)cap, d_mcounts, nullptr) != 0) { h->err = "out of device memory (match scratch)"; return ORBX_E_NOMEM; }
+    // frames 1..n-1 against their predecessor inside the batch: problem p = frame p+1
+    if (nframes > 1 &&
+        launch_match_core(h, d_desc + (size_t)cap * ORBX_DESC_BYTES, d_counts + 1, cap, (size_t)cap * ORBX_DESC_BYTES,
+                          d_desc, d_counts, cap, (size_t)cap * ORBX_DESC_BYTES, nullptr, nullptr, nframes - 1, 0,
+                          1, max_dist, 0, d_matches + cap, (size_t)cap, d_mcounts + 1, nullptr) != 0) { h->err = "out of device memory (match scratch)"; return ORBX_E_NOMEM; }
+    // carry the last frame: prev_descriptors_ = filtered_descriptors.clone() (frontend.cpp:1258-1259)
+    ORBX_CUDA(h, cudaMemcpyAsync(h->d_prev_desc, d_desc + (size_t)(nframes - 1) * cap * ORBX_DESC_BYTES, (size_t)cap * ORBX_DESC_BYTES, cudaMemcpyDeviceToDevice, h->stream));
+    ORBX_CUDA(h, cudaMemcpyAsync(h->d_prev_count, d_counts + (nframes - 1), sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+    h->prev_valid = 1;
+    ORBX_CUDA(h, cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" orbx_status orbx_track_batch_device(orbx_handle *h, const uint8_t *d_gray, int32_t nframes,
+                                               int32_t width, int32_t height, size_t step, size_t frame_stride,
+                                               const uint16_t *d_depth, size_t dstep, size_t dframe_stride,
+                                               orbx_keypoint *d_kps, uint8_t *d_desc, int32_t cap, int32_t *d_counts,
+                                               orbx_dmatch *d_matches, int32_t *d_mcounts, float max_dist)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    if (!d_gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }
+    if (nframes < 1 || nframes > h->prm.max_batch || !d_kps || !d_desc || !d_counts || !d_matches || !d_mcounts || cap < 1) { h->err = "bad batch arguments"; return ORBX_E_INVALID; }
+    if (step < (size_t)width || (step & 15) || ((uintptr_t)d_gray & 15) || (frame_stride & 15)) { h->err = "device frames need 16-byte aligned base, step and frame stride"; return ORBX_E_INVALID; }
+    if (d_depth && ((dstep & 1) || dstep < (size_t)width * 2)) { h->err = "bad depth step"; return ORBX_E_INVALID; }
+    orbx_status st = set_geometry(h, width, height);
+    if (st != ORBX_OK) return st;
+    return track_device(h, d_gray, nframes, width, height, step, frame_stride, d_depth, dstep, dframe_stride, d_kps, d_desc, cap, d_counts, d_matches, d_mcounts, max_dist);
+}
+
+extern "C" orbx_status orbx_track_batch(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
+                                        size_t step, const uint16_t *depth, size_t dstep,
+                                        orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *counts,
+                                        orbx_dmatch *matches, int32_t *mcounts, float max_dist)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    if (!gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }
+    if (nframes < 0 || !kps || !desc || !counts || !matches || !mcounts || cap < 1 || step < (size_t)width) { h->err = "bad arguments"; return ORBX_E_INVALID; }
+    orbx_status st = set_geometry(h, width, height);
+    if (st != ORBX_OK) return st;
+    const size_t pitch = align_up((size_t)width, 128), dpitch = align_up((size_t)width * 2, 128);
+    const size_t fstride = pitch * height, dfstride = dpitch * height;
+    const int B = h->prm.max_batch;
+    const int kcap = std::min(cap, h->max_kp);
+    // device-side match output lives in the matcher scratch, sized [B][max_kp]
+    if ((st = grow(h, (uint8_t **)&h->d_mout, &h->mout_cap, (size_t)B * h->max_kp * sizeof(orbx_dmatch) + (size_t)B * sizeof(int32_t))) != ORBX_OK) return st;
+    orbx_dmatch *d_m = h->d_mout;
+    int32_t *d_mc = (int32_t *)((uint8_t *)h->d_mout + (size_t)B * h->max_kp * sizeof(orbx_dmatch));
+    const bool tight = (step == (size_t)width) && (pitch == (size_t)width);
+    for (int f0 = 0; f0 < nframes; f0 += B) {
+        const int nb = std::min(B, nframes - f0);
+        if (tight) ORBX_CUDA(h, cudaMemcpyAsync(h->d_in, gray + (size_t)f0 * height * step, (size_t)nb * fstride, cudaMemcpyHostToDevice, h->stream));
+        else for (int f = 0; f < nb; f++)
+            ORBX_CUDA(h, cudaMemcpy2DAsync(h->d_in + (size_t)f * fstride, pitch, gray + (size_t)(f0 + f) * height * step, step,
+                                           (size_t)width, (size_t)height, cudaMemcpyHostToDevice, h->stream));
+        if (depth) {
+            if (dstep == dpitch) ORBX_CUDA(h, cudaMemcpyAsync(h->d_depth_in, (const uint8_t *)depth + (size_t)f0 * height * dstep, (size_t)nb * dfstride, cudaMemcpyHostToDevice, h->stream));
+            else for (int f = 0; f < nb; f++)
+                ORBX_CUDA(h, cudaMemcpy2DAsync((uint8_t *)h->d_depth_in + (size_t)f * dfstride, dpitch,
+                                               (const uint8_t *)depth + (size_t)(f0 + f) * height * dstep, dstep,
+                                               (size_t)width * 2, (size_t)height, cudaMemcpyHostToDevice, h->stream));
+        }
+        st = track_device(h, h->d_in, nb, width, height, pitch, fstride, depth ? h->d_depth_in : nullptr, dpitch, dfstride,
+                          h->d_kps_out, h->d_desc_out, h->max_kp, h->d_count_out, d_m, d_mc, max_dist);
+        if (st != ORBX_OK) return st;
+        ORBX_CUDA(h, cudaMemcpyAsync(counts + f0, h->d_count_out, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        ORBX_CUDA(h, cudaMemcpyAsync(mcounts + f0, d_mc, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        ORBX_CUDA(h, cudaMemcpy2DAsync(kps + (size_t)f0 * cap, (size_t)cap * sizeof(orbx_keypoint), h->d_kps_out, (size_t)h->max_kp * sizeof(orbx_keypoint),
+                                       (size_t)kcap * sizeof(orbx_keypoint), (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
+        ORBX_CUDA(h, cudaMemcpy2DAsync(desc + (size_t)f0 * cap * ORBX_DESC_BYTES, (size_t)cap * ORBX_DESC_BYTES, h->d_desc_out, (size_t)h->max_kp * ORBX_DESC_BYTES,
+                                       (size_t)kcap * ORBX_DESC_BYTES, (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
+        ORBX_CUDA(h, cudaMemcpy2DAsync(matches + (size_t)f0 * cap, (size_t)cap * sizeof(orbx_dmatch), d_m, (size_t)h->max_kp * sizeof(orbx_dmatch),
+                                       (size_t)kcap * sizeof(orbx_dmatch), (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
         st = check_device_status(h);
         if (st != ORBX_OK) return st;
         for (int f = 0; f < nb; f++) if (counts[f0 + f] > cap) { h->err = "output capacity too small"; return ORBX_E_CAPACITY; }
@@ -753,6 +861,35 @@ extern "C" orbx_status orbx_test_quadtree(orbx_handle *h, const int32_t *xys, in
     std::vector<uint32_t> sel((size_t)std::max(m, 1));
     ORBX_CUDA(h, cudaMemcpy(sel.data(), h->d_sel, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     for (int i = 0; i < m; i++) { out_xys[3 * i] = orbx_px(sel[i]); out_xys[3 * i + 1] = orbx_py(sel[i]); out_xys[3 * i + 2] = orbx_ps(sel[i]); }
+    return ORBX_OK;
+}
+
+// ---- per-kernel event profiling ----
+static const char *k_prof_names[ORBX_K_COUNT] = { "k_resize_linear", "k_fast_cells", "k_quadtree", "k_blur7", "k_describe", "k_filter",
+                                                  "k_match_partial", "k_match_epilogue", "other" };
+extern "C" int32_t orbx_profile_kernels(void) { return ORBX_K_COUNT; }
+extern "C" const char *orbx_profile_name(int32_t id) { return id >= 0 && id < ORBX_K_COUNT ? k_prof_names[id] : ""; }
+extern "C" void orbx_profile_enable(orbx_handle *h, int32_t on)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (on && h->prof_ev.empty()) {
+        h->prof_ev.resize(2 * 8192); h->prof_id.resize(8192);
+        for (auto &e : h->prof_ev) cudaEventCreate(&e);
+    }
+    h->prof_on = on ? 1 : 0;
+}
+extern "C" orbx_status orbx_profile_read(orbx_handle *h, double *ms, int64_t *launches)
+{
+    if (!h || !ms || !launches) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < h->prof_n; i++) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]) == cudaSuccess) { h->prof_ms[h->prof_id[i]] += t; h->prof_cnt[h->prof_id[i]]++; }
+    }
+    h->prof_n = 0;
+    for (int k = 0; k < ORBX_K_COUNT; k++) { ms[k] = h->prof_ms[k]; launches[k] = h->prof_cnt[k]; h->prof_ms[k] = 0; h->prof_cnt[k] = 0; }
     return ORBX_OK;
 }
 

@@ -55,6 +55,9 @@ struct FrameGeom {
     LevelGeom lv[ORBX_MAX_LEVELS];
 };
 
+enum { ORBX_K_RESIZE = 0, ORBX_K_FAST, ORBX_K_QUADTREE, ORBX_K_BLUR, ORBX_K_DESCRIBE, ORBX_K_FILTER,
+       ORBX_K_MATCH, ORBX_K_MATCH_EPI, ORBX_K_OTHER, ORBX_K_COUNT };
+
 struct ResizeTab { int32_t ofs; int16_t a0, a1; };   // 8 bytes
 
 struct orbx_handle {
@@ -98,6 +101,22 @@ struct orbx_handle {
     int last_batch;
     const uint8_t *last_l0; size_t last_l0_step, last_l0_fstride;   // level 0 of the last batch (may alias caller memory)
     int sm_count;
+    // previous-frame descriptors for the stream API (the frontend's prev_descriptors_, frontend.cpp:1258-1259)
+    uint8_t *d_prev_desc; int32_t *d_prev_count; int prev_valid;
+    // per-kernel CUDA-event profiling (bench roofline): pairs of events around every launch
+    int prof_on; int prof_n;
+    std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_id;
+    double prof_ms[ORBX_K_COUNT]; long prof_cnt[ORBX_K_COUNT];
+};
+
+struct ProfScope {
+    orbx_handle *h; int idx;
+    ProfScope(orbx_handle *hh, int id) : h(hh), idx(-1) {
+        if (h->prof_on && (size_t)(2 * h->prof_n + 1) < h->prof_ev.size()) {
+            idx = h->prof_n++; h->prof_id[idx] = id; cudaEventRecord(h->prof_ev[2 * idx], h->stream);
+        }
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(h->prof_ev[2 * idx + 1], h->stream); h->launches++; }
 };
 
 struct orbx_db {

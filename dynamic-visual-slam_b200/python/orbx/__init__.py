@@ -106,6 +106,13 @@ def load():
         "orbx_test_quadtree": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
         "orbx_bench_popc": (i32, [vp, vp]),
         "orbx_launch_count": (i64, [vp]),
+        "orbx_track_batch_device": (i32, [vp, vp, i32, i32, i32, sz, sz, vp, sz, sz, vp, vp, i32, vp, vp, vp, f32]),
+        "orbx_track_batch": (i32, [vp, vp, i32, i32, i32, sz, vp, sz, vp, vp, i32, vp, vp, vp, f32]),
+        "orbx_track_reset": (None, [vp]),
+        "orbx_profile_enable": (None, [vp, i32]),
+        "orbx_profile_kernels": (i32, []),
+        "orbx_profile_name": (ct.c_char_p, [i32]),
+        "orbx_profile_read": (i32, [vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -261,6 +268,38 @@ class ORBextractor:
         """Raw device-pointer variant (ints), asynchronous on the handle's stream."""
         self._check(self.L.orbx_extract_batch_device(self._h, d_gray, nframes, w, h, step, frame_stride,
                                                      d_depth, dstep, dframe_stride, d_kps, d_desc, cap, d_counts))
+
+    # -- stream step (hot part of Frontend::syncCallback) --
+    def track_reset(self):
+        self.L.orbx_track_reset(self._h)
+
+    def track_batch(self, frames, depth=None, cap=2048, max_dist=50.0):
+        """frames [n,h,w] u8 (+ depth [n,h,w] u16): per-frame filtered keypoints/descriptors and matches vs the previous frame."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        nf, h, w = frames.shape
+        self._last_w, self._last_h = w, h
+        kps = np.zeros((nf, cap), KP_DTYPE)
+        desc = np.zeros((nf, cap, 32), np.uint8)
+        counts = np.zeros(nf, np.int32)
+        matches = np.zeros((nf, cap), DM_DTYPE)
+        mcounts = np.zeros(nf, np.int32)
+        dptr, dstep = None, 0
+        if depth is not None:
+            depth = np.ascontiguousarray(depth, dtype=np.uint16)
+            dptr, dstep = _p(depth), depth.strides[1]
+        self._check(self.L.orbx_track_batch(self._h, _p(frames), nf, w, h, frames.strides[1], dptr, dstep,
+                                            _p(kps), _p(desc), cap, _p(counts), _p(matches), _p(mcounts), ct.c_float(max_dist)))
+        return kps, desc, counts, matches, mcounts
+
+    def profile_enable(self, on=True):
+        self.L.orbx_profile_enable(self._h, 1 if on else 0)
+
+    def profile_read(self):
+        n = self.L.orbx_profile_kernels()
+        ms = np.zeros(n, np.float64)
+        cnt = np.zeros(n, np.int64)
+        self._check(self.L.orbx_profile_read(self._h, _p(ms), _p(cnt)))
+        return {self.L.orbx_profile_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
 
     # -- stage access --
     def pyramid_level(self, level, frame=0):

@@ -129,6 +129,24 @@ orbx_status orbx_extract_batch_device(orbx_handle *h, const uint8_t *d_gray, int
                                       orbx_keypoint *d_kps, uint8_t *d_desc, int32_t cap_per_frame,
                                       int32_t *d_counts);
 
+/* ---- stream step: the hot part of Frontend::syncCallback (frontend.cpp:1094-1132, first frame :1277-1317) ----
+ * For every frame of the batch: extraction, depth filter (d_depth / depth nullable), then
+ * matcher_.match(filtered_descriptors, prev_descriptors_) + `distance < max_dist` against the PREVIOUS
+ * frame's filtered descriptors.  Frame 0 of a call is matched against the handle's carried state (the
+ * last frame of the previous call; none after create / orbx_track_reset => 0 matches, as on the
+ * reference's first frame).  matches: cap_per_frame entries per frame, query order; match_counts[nframes].
+ * max_dist <= 0 keeps every match (exactly match()).                                               */
+orbx_status orbx_track_batch_device(orbx_handle *h, const uint8_t *d_gray, int32_t nframes,
+                                    int32_t width, int32_t height, size_t step, size_t frame_stride,
+                                    const uint16_t *d_depth, size_t dstep, size_t dframe_stride,
+                                    orbx_keypoint *d_kps, uint8_t *d_desc, int32_t cap_per_frame, int32_t *d_counts,
+                                    orbx_dmatch *d_matches, int32_t *d_match_counts, float max_dist);
+orbx_status orbx_track_batch(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
+                             size_t step, const uint16_t *depth, size_t dstep,
+                             orbx_keypoint *kps, uint8_t *desc, int32_t cap_per_frame, int32_t *counts,
+                             orbx_dmatch *matches, int32_t *match_counts, float max_dist);
+void        orbx_track_reset(orbx_handle *h);
+
 /* ---- matching: cv::BFMatcher(NORM_HAMMING) ----
  * k = 1: BFMatcher::match.   max_dist <= 0: one DMatch per query, query order (exactly match()).
  *                            max_dist  > 0: only matches with distance < max_dist, query order
@@ -206,6 +224,13 @@ orbx_status orbx_test_quadtree(orbx_handle *h, const int32_t *xys, int32_t n, in
 orbx_status orbx_bench_popc(orbx_handle *h, double *popc_per_sec);
 /* number of kernels this library has launched on the handle since creation */
 int64_t orbx_launch_count(const orbx_handle *h);
+/* per-kernel device time, CUDA events recorded on the handle's stream around every launch while enabled.
+ * orbx_profile_read synchronises, accumulates and returns total ms and launch count per kernel id
+ * (0 <= id < orbx_profile_kernels(); names from orbx_profile_name), then clears the accumulators.   */
+void        orbx_profile_enable(orbx_handle *h, int32_t on);
+int32_t     orbx_profile_kernels(void);
+const char *orbx_profile_name(int32_t id);
+orbx_status orbx_profile_read(orbx_handle *h, double *ms, int64_t *launches);
 
 #ifdef __cplusplus
 }
