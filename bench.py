@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--batch", type=int, default=128, help="frames resident per step and per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-assoc", action="store_true", help="skip the landmark-association leg")
+    ap.add_argument("--kernels-only", action="store_true", help="device-resident leg only (for ncu captures)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -245,6 +246,11 @@ def main():
                     "algorithmic_bytes_per_launch": ALG_BYTES[dom] * B / max(1.0, kernels[dom]["launches_per_step"]),
                     "dominant_overall": max(kernels, key=lambda n: kernels[n]["ms_per_step"])}
 
+    if args.kernels_only:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+                              "ms_per_step": ms / K, "kernels": kernels, "roofline": roofline, "gpu_launches": int(gpu_launches), "clocks": clocks}))
+        return
     # ---- e2e: the host-buffer C-ABI call, pinned host memory, H2D + D2H inside the timed region ----
     e2e = None
     Be = B

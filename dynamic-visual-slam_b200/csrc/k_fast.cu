@@ -4,21 +4,34 @@
 // nothing, `cv::FAST(roi, kps, minThFAST, true)` (:826-827, :845-846).  FAST arithmetic: SURVEY App. A.2
 //   S = max over the 16 arcs of 9 contiguous ring pixels of min(I(p)-I(ring)) resp. min(I(ring)-I(p));
 //   corner iff S > th; score = S - 1; strict 3x3 NMS INSIDE the cell's ROI (scores outside the
-//   ROI's 3-px margin read as 0).
+//   cell's detection area read as 0).
 //
-// One CTA per cell, all levels of all frames in one launch.  The cell's ROI is staged in shared
-// memory (pitch 80 so ring offsets are compile-time constants), scores go to a second shared tile,
-// survivors are appended to the (frame, level) candidate list with one global atomic per CTA.
-// Candidate order in the list is arbitrary; the quadtree kernel is order-independent (it
-// reconstructs the reference's insertion order from coordinates where ties need it).
+// Design.  One CTA owns a horizontal run of cells of one cell row (a "strip"); all levels of all
+// frames go in one launch.
+//   1. the strip's ROI is staged in shared memory with aligned 32-bit loads;
+//   2. column sweep: thread = one pixel column walking down the rows with a 7-deep register window,
+//      so the first opposite-pair test (ring 0 / ring 8 = same column, +-3 rows) costs ONE shared load
+//      per pixel; pairs (4,12), (2,10), (6,14) are loaded only for survivors.  The pair tests are an
+//      exact necessary condition for S > th (every 9-arc contains a member of each opposite pair);
+//   3. survivors are compacted into a shared queue (warp-aggregated) and scored densely: the 16-arc
+//      min/max network runs on packed u16x2 lanes (VIMNMX.U16x2): low half = ring value, high half =
+//      255 - ring value, so one instruction serves the darker and the brighter polarity;
+//   4. NMS touches queue entries only; neighbours in another cell of the strip are masked to 0;
+//   5. cells with no survivor at iniThFAST are swept again at minThFAST (the reference's retry).
+// Survivors are appended to the (frame, level) candidate list with one global atomic per CTA;
+// list order is arbitrary (the quadtree kernel is order-independent).
+//
+// Toolchain note: an earlier formulation on signed differences (d = I(p) - I(ring), score via
+// max(mn9, -mx9)) produced wrong results on sm_100a with nvcc 12.9 (the negation feeding a fused
+// 3-input VIMNMX3 was lost); the raw-value formulation below has no negated min/max operands.
 #include "orbx_internal.h"
 
-#define FT_PITCH 80            // >= max ROI width 75 (wCell <= 69 for any box >= 35 px)
-#define FT_ROWS 76
-#define FS_PITCH 72            // score tile: detection area + 1-px zero ring, <= 71 wide
-#define FS_ROWS 72
-#define FAST_THREADS 128
-#define FAST_OUT_CAP 1296      // NMS survivors are never 8-adjacent: <= ceil(69/2)^2 = 1225
+#define FS_THREADS 256
+#define FS_TP 272                // tile pitch: >= ORBX_FAST_MAX_W + 6 + 3 (alignment slack), multiple of 16
+#define FS_SP 272                // score-map pitch: >= detection width + 2, multiple of 16
+#define FS_QCAP 4096             // survivor queue entries (u16 tile offsets); beyond it survivors are scored inline
+#define FS_OUT_CAP 1024          // staged outputs; beyond it survivors are written straight to the global list
+#define FS_MAX_CELLS 8
 
 struct FastParams {
     const uint8_t *l0; size_t l0_step, l0_fstride;
@@ -27,129 +40,195 @@ struct FastParams {
     int32_t *ncand;
     int ini_th, min_th;
     int32_t *status;
+    int tile_rows;               // max (hCell + 6) over the levels
 };
 
-// ring offsets in a pitch-80 tile, order of SURVEY App. A.2
-#define RO(dx, dy) ((dy) * FT_PITCH + (dx))
-__device__ __forceinline__ int fast_score(const uint8_t *p)
+#define RO(dx, dy) ((dy) * FS_TP + (dx))
+
+// S on the raw ring values: S = max( I(p) - min_k max9_k(ring), max_k min9_k(ring) - I(p) ).
+// Packed lanes: lo16 = r, hi16 = 255 - r  =>  a lane-wise min yields (min r, 255 - max r).
+__device__ __forceinline__ int fast_score_packed(const uint8_t *p)
 {
-    // S = max( I(p) - min_k max9_k(ring),  max_k min9_k(ring) - I(p) ) over the 16 arcs of 9 contiguous ring
-    // pixels: "all darker by more than t" <=> I(p) - max9 > t ; "all brighter" <=> min9 - I(p) > t.
-    // Formulated on the raw ring values (no negated operands) with a log-step sliding window.
     const int v = p[0];
-    int r[16];
-    r[0] = p[RO(0, 3)];   r[1] = p[RO(1, 3)];    r[2] = p[RO(2, 2)];    r[3] = p[RO(3, 1)];
-    r[4] = p[RO(3, 0)];   r[5] = p[RO(3, -1)];   r[6] = p[RO(2, -2)];   r[7] = p[RO(1, -3)];
-    r[8] = p[RO(0, -3)];  r[9] = p[RO(-1, -3)];  r[10] = p[RO(-2, -2)]; r[11] = p[RO(-3, -1)];
-    r[12] = p[RO(-3, 0)]; r[13] = p[RO(-3, 1)];  r[14] = p[RO(-2, 2)];  r[15] = p[RO(-1, 3)];
-    int mn2[16], mx2[16], mn4[16], mx4[16];
+    uint32_t r[16];
+#define PK(x) ((uint32_t)(x) * 0xFFFF0001u + 0x00FF0000u)
+    r[0] = PK(p[RO(0, 3)]);   r[1] = PK(p[RO(1, 3)]);    r[2] = PK(p[RO(2, 2)]);    r[3] = PK(p[RO(3, 1)]);
+    r[4] = PK(p[RO(3, 0)]);   r[5] = PK(p[RO(3, -1)]);   r[6] = PK(p[RO(2, -2)]);   r[7] = PK(p[RO(1, -3)]);
+    r[8] = PK(p[RO(0, -3)]);  r[9] = PK(p[RO(-1, -3)]);  r[10] = PK(p[RO(-2, -2)]); r[11] = PK(p[RO(-3, -1)]);
+    r[12] = PK(p[RO(-3, 0)]); r[13] = PK(p[RO(-3, 1)]);  r[14] = PK(p[RO(-2, 2)]);  r[15] = PK(p[RO(-1, 3)]);
+#undef PK
+    uint32_t m2[16], m4[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) { mn2[k] = min(r[k], r[(k + 1) & 15]); mx2[k] = max(r[k], r[(k + 1) & 15]); }
+    for (int k = 0; k < 16; k++) m2[k] = __vminu2(r[k], r[(k + 1) & 15]);
 #pragma unroll
-    for (int k = 0; k < 16; k++) { mn4[k] = min(mn2[k], mn2[(k + 2) & 15]); mx4[k] = max(mx2[k], mx2[(k + 2) & 15]); }
-    int hi_of_min = 0, lo_of_max = 255;
+    for (int k = 0; k < 16; k++) m4[k] = __vminu2(m2[k], m2[(k + 2) & 15]);
+    uint32_t best = 0;           // per lane: max_k min9_k
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), r[(k + 8) & 15]);
-        const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), r[(k + 8) & 15]);
-        hi_of_min = max(hi_of_min, mn9);
-        lo_of_max = min(lo_of_max, mx9);
+        const uint32_t m9 = __vminu2(__vminu2(m4[k], m4[(k + 4) & 15]), r[(k + 8) & 15]);
+        best = __vmaxu2(best, m9);
     }
+    const int hi_of_min = (int)(best & 0xFFFFu);                  // max_k min9_k(r)
+    const int lo_of_max = 255 - (int)(best >> 16);                // min_k max9_k(r)
     const int s_dark = v - lo_of_max, s_bright = hi_of_min - v;
     return s_dark > s_bright ? s_dark : s_bright;
 }
 
-__global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(FastParams P, const FrameGeom *__restrict__ G)
+__global__ void __launch_bounds__(FS_THREADS) k_fast_cells(FastParams P, const FrameGeom *__restrict__ G)
 {
-    __shared__ __align__(16) uint8_t s_img[FT_ROWS * FT_PITCH];
-    __shared__ uint8_t s_sc[FS_ROWS * FS_PITCH];
-    __shared__ uint32_t s_out[FAST_OUT_CAP];
-    __shared__ int s_nout, s_base;
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    __shared__ uint16_t s_q[FS_QCAP];
+    __shared__ uint32_t s_out[FS_OUT_CAP];
+    __shared__ int s_qn, s_nout, s_base, s_redo, s_ovf;
+    __shared__ int s_ccnt[FS_MAX_CELLS];
+    __shared__ uint8_t s_col2cell[ORBX_FAST_MAX_W];
+    uint8_t *s_img = s_dyn;                                        // tile_rows x FS_TP
+    uint8_t *s_sc = s_dyn + P.tile_rows * FS_TP;                  // (tile_rows - 4) x FS_SP score map with a zero ring
 
     const int f = blockIdx.y;
     int level = 0;
     const int nl = G->nlevels;
-    for (int l = 1; l < nl; l++) if ((int)blockIdx.x >= G->lv[l].cell_first) level = l;
+    for (int l = 1; l < nl; l++) if ((int)blockIdx.x >= G->lv[l].strip_first) level = l;
     const LevelGeom &g = G->lv[level];
-    const int cell = blockIdx.x - g.cell_first;
-    const int ci = cell / g.ncols, cj = cell % g.ncols;
-    // cell ROI in image coordinates — ORBextractor.cpp:805-822
+    const int sidx = blockIdx.x - g.strip_first;
+    const int ci = sidx / g.strips_per_row, sj = sidx - ci * g.strips_per_row;
+    const int cj0 = sj * g.cells_per_strip;
+    // strip ROI in image coordinates — ORBextractor.cpp:805-822 (cells cj0 .. cj0+ncell-1 of cell row ci)
     const int maxBX = g.w - ORBX_BORDER, maxBY = g.h - ORBX_BORDER;
-    const int iniX = ORBX_BORDER + cj * g.wcell, iniY = ORBX_BORDER + ci * g.hcell;
+    const int iniX = ORBX_BORDER + cj0 * g.wcell, iniY = ORBX_BORDER + ci * g.hcell;
     if (iniY >= maxBY - 3 || iniX >= maxBX - 6) return;
-    const int maxX = min(iniX + g.wcell + 6, maxBX), maxY = min(iniY + g.hcell + 6, maxBY);
+    int ncell = min(g.cells_per_strip, g.ncols - cj0);
+    // cells whose iniX >= maxBorderX-6 are skipped by the reference (:815-816)
+    while (ncell > 0 && ORBX_BORDER + (cj0 + ncell - 1) * g.wcell >= maxBX - 6) ncell--;
+    if (ncell <= 0) return;
+    const int maxX = min(iniX + ncell * g.wcell + 6, maxBX), maxY = min(iniY + g.hcell + 6, maxBY);
     const int rw = maxX - iniX, rh = maxY - iniY;
-    const int dw = rw - 6, dh = rh - 6;            // detection area, ROI-relative origin (3,3)
+    const int dw = rw - 6, dh = rh - 6;            // detection area of the strip, ROI-relative origin (3,3)
     if (dw <= 0 || dh <= 0) return;
 
     const uint8_t *src; size_t step;
     if (level == 0) { src = P.l0 + (size_t)f * P.l0_fstride; step = P.l0_step; }
     else { src = P.pyr + (size_t)f * P.pyr_slab + g.off; step = (size_t)g.pitch; }
-    src += (size_t)iniY * step + iniX;
-
-    for (int i = threadIdx.x; i < rh * rw; i += FAST_THREADS) {
-        const int r = i / rw, c = i - r * rw;
-        s_img[r * FT_PITCH + c] = __ldg(src + (size_t)r * step + c);
+    // stage the ROI with aligned 32-bit loads; tile column `ax` is image column iniX
+    const int ax = iniX & 3;
+    const int words = (ax + rw + 3) >> 2;
+    src += (size_t)iniY * step + (iniX - ax);
+    for (int r = threadIdx.x >> 6; r < rh; r += FS_THREADS / 64) {
+        const uint32_t *srow = reinterpret_cast<const uint32_t *>(src + (size_t)r * step);
+        uint32_t *drow = reinterpret_cast<uint32_t *>(s_img + r * FS_TP);
+        for (int wi = threadIdx.x & 63; wi < words; wi += 64) drow[wi] = __ldg(srow + wi);
     }
-    // zero the score tile once; the 1-px ring around the detection area stays 0 for both passes
-    for (int i = threadIdx.x; i < (dh + 2) * FS_PITCH; i += FAST_THREADS) s_sc[i] = 0;
-    if (threadIdx.x == 0) s_nout = 0;
-    __syncthreads();
+    for (int c = threadIdx.x; c < dw; c += FS_THREADS) s_col2cell[c] = (uint8_t)min(c / g.wcell, ncell - 1);
+    if (threadIdx.x < FS_MAX_CELLS) s_ccnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { s_nout = 0; s_redo = 0; }
+    const uint8_t *tile = s_img + ax;               // tile[r * FS_TP + c] = ROI(r, c)
+    const int lane = threadIdx.x & 31;
+    uint32_t *gdst = P.cand + (size_t)f * P.cand_slab + g.cand_off;
+    int32_t *gcnt = &P.ncand[f * nl + level];
 
     for (int pass = 0; pass < 2; pass++) {
         const int th = pass == 0 ? P.ini_th : P.min_th;
-        // scores
-        for (int i = threadIdx.x; i < dw * dh; i += FAST_THREADS) {
-            const int r = i / dw, c = i - r * dw;
-            const uint8_t *p = &s_img[(r + 3) * FT_PITCH + (c + 3)];
-            const int v = p[0], hi = v + th, lo = v - th;
-            int sc = 0;
-            // exact necessary condition: each opposite ring pair must contain an arc member
-            int a = p[RO(0, 3)], b = p[RO(0, -3)];
-            bool br = (a > hi) | (b > hi), dk = (a < lo) | (b < lo);
-            if (br | dk) {
-                a = p[RO(3, 0)]; b = p[RO(-3, 0)];
-                br &= (a > hi) | (b > hi); dk &= (a < lo) | (b < lo);
-                if (br | dk) {
-                    a = p[RO(2, 2)]; b = p[RO(-2, -2)];
-                    br &= (a > hi) | (b > hi); dk &= (a < lo) | (b < lo);
-                    a = p[RO(2, -2)]; b = p[RO(-2, 2)];
+        // zero the score map (1-px ring included) and the queue
+        for (int i = threadIdx.x; i < ((dh + 2) * FS_SP) / 16; i += FS_THREADS) reinterpret_cast<uint4 *>(s_sc)[i] = make_uint4(0, 0, 0, 0);
+        if (threadIdx.x == 0) { s_qn = 0; s_ovf = 0; }
+        __syncthreads();
+        // ---- column sweep with a 7-deep register window ----
+        for (int c0 = 0; c0 < dw; c0 += FS_THREADS) {
+            const int c = c0 + threadIdx.x;
+            const int cc = c < dw ? c : dw - 1;
+            const bool col_ok = c < dw && (pass == 0 || s_ccnt[s_col2cell[cc]] == 0);
+            const uint8_t *colp = tile + cc + 3;                        // column of the centre pixel in the tile
+            int q0 = 0, q1 = colp[0], q2 = colp[FS_TP], q3 = colp[2 * FS_TP], q4 = colp[3 * FS_TP], q5 = colp[4 * FS_TP], q6 = colp[5 * FS_TP];
+            for (int r = 0; r < dh; r++) {
+                q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = q5; q5 = q6;
+                q6 = colp[(r + 6) * FS_TP];                               // ring 0 (dy = +3) of detection row r
+                const int v = q3, hi = v + th, lo = v - th;
+                bool br = (q6 > hi) | (q0 > hi), dk = (q6 < lo) | (q0 < lo);
+                bool pass_all = false;
+                if (col_ok && (br | dk)) {
+                    const uint8_t *p = colp + (r + 3) * FS_TP;
+                    int a = p[RO(3, 0)], b = p[RO(-3, 0)];
                     br &= (a > hi) | (b > hi); dk &= (a < lo) | (b < lo);
                     if (br | dk) {
-                        const int s = fast_score(p);
-                        if (s > th) sc = s - 1;
+                        a = p[RO(2, 2)]; b = p[RO(-2, -2)];
+                        br &= (a > hi) | (b > hi); dk &= (a < lo) | (b < lo);
+                        a = p[RO(2, -2)]; b = p[RO(-2, 2)];
+                        br &= (a > hi) | (b > hi); dk &= (a < lo) | (b < lo);
+                        pass_all = br | dk;
+                    }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, pass_all);
+                if (bal) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_qn, __popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (pass_all) {
+                        const int slot = base + __popc(bal & ((1u << lane) - 1u));
+                        if (slot < FS_QCAP) s_q[slot] = (uint16_t)((r + 3) * FS_TP + c + 3);
+                        else {                                            // queue full: score inline, NMS will scan the map
+                            const int s = fast_score_packed(colp + (r + 3) * FS_TP);
+                            s_sc[(r + 1) * FS_SP + (c + 1)] = (uint8_t)(s > th ? s - 1 : 0);
+                            s_ovf = 1;
+                        }
                     }
                 }
             }
-            s_sc[(r + 1) * FS_PITCH + (c + 1)] = (uint8_t)sc;
         }
         __syncthreads();
-        // strict 3x3 NMS inside the cell
-        for (int i = threadIdx.x; i < dw * dh; i += FAST_THREADS) {
-            const int r = i / dw, c = i - r * dw;
-            const uint8_t *q = &s_sc[(r + 1) * FS_PITCH + (c + 1)];
+        const int qn = min(s_qn, FS_QCAP);
+        // ---- dense scoring of the queued survivors ----
+        for (int i = threadIdx.x; i < qn; i += FS_THREADS) {
+            const int off = s_q[i];
+            const int s = fast_score_packed(tile + off);
+            const int tr = off / FS_TP, tc = off - tr * FS_TP;         // tile coords = detection coords + 3
+            s_sc[(tr - 2) * FS_SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
+        }
+        __syncthreads();
+        // ---- strict 3x3 NMS inside each cell: queue entries, or the whole map if the queue overflowed ----
+        const bool scan_all = s_ovf != 0;
+        const int nitems = scan_all ? dw * dh : qn;
+        for (int i = threadIdx.x; i < nitems; i += FS_THREADS) {
+            int r, c;
+            if (scan_all) { r = i / dw; c = i - r * dw; }
+            else { const int off = s_q[i]; const int tr = off / FS_TP; r = tr - 3; c = off - tr * FS_TP - 3; }
+            const uint8_t *q = &s_sc[(r + 1) * FS_SP + (c + 1)];
             const int s = q[0];
             if (s == 0) continue;
-            if (s > q[-1] && s > q[1] && s > q[-FS_PITCH - 1] && s > q[-FS_PITCH] && s > q[-FS_PITCH + 1] &&
-                s > q[FS_PITCH - 1] && s > q[FS_PITCH] && s > q[FS_PITCH + 1]) {
-                const int o = atomicAdd(&s_nout, 1);
+            const int cell = s_col2cell[c];
+            const int cl = c - cell * g.wcell;                          // column inside the cell's detection area
+            const bool hasL = cl > 0, hasR = (cl < g.wcell - 1) && (c < dw - 1);
+            bool ok = s > q[-FS_SP] && s > q[FS_SP];
+            if (hasL) ok = ok && s > q[-1] && s > q[-FS_SP - 1] && s > q[FS_SP - 1];
+            if (hasR) ok = ok && s > q[1] && s > q[-FS_SP + 1] && s > q[FS_SP + 1];
+            if (ok) {
+                atomicAdd(&s_ccnt[cell], 1);
                 // box-relative coordinates: kp.pt + (j*wCell, i*hCell) — ORBextractor.cpp:865-866
-                if (o < FAST_OUT_CAP) s_out[o] = orbx_pack(cj * g.wcell + c + 3, ci * g.hcell + r + 3, s);
+                const uint32_t val = orbx_pack(cj0 * g.wcell + c + 3, ci * g.hcell + r + 3, s);
+                const int o = atomicAdd(&s_nout, 1);
+                if (o < FS_OUT_CAP) s_out[o] = val;
+                else {                                                    // staging full: straight to the global list
+                    const int go = atomicAdd(gcnt, 1);
+                    if (go < g.cand_cap) gdst[go] = val; else atomicOr(P.status, ORBX_DS_CAND_OVERFLOW);
+                }
             }
         }
         __syncthreads();
-        if (s_nout > 0) break;            // uniform: fallback only when the first pass found nothing
+        // fallback pass only for cells that produced nothing (uniform decision)
+        if (pass == 0) {
+            if (threadIdx.x < ncell && s_ccnt[threadIdx.x] == 0) s_redo = 1;
+            __syncthreads();
+            if (!s_redo) break;
+        }
     }
-    const int n = min(s_nout, FAST_OUT_CAP);
+    const int n = min(s_nout, FS_OUT_CAP);
     if (n == 0) return;
-    if (threadIdx.x == 0) s_base = atomicAdd(&P.ncand[f * nl + level], n);
+    if (threadIdx.x == 0) s_base = atomicAdd(gcnt, n);
     __syncthreads();
     const int base = s_base;
-    uint32_t *dst = P.cand + (size_t)f * P.cand_slab + g.cand_off;
-    for (int i = threadIdx.x; i < n; i += FAST_THREADS) {
-        if (base + i < g.cand_cap) dst[base + i] = s_out[i];
+    for (int i = threadIdx.x; i < n; i += FS_THREADS) {
+        if (base + i < g.cand_cap) gdst[base + i] = s_out[i];
     }
-    if (threadIdx.x == 0 && (base + n > g.cand_cap || s_nout > FAST_OUT_CAP)) atomicOr(P.status, ORBX_DS_CAND_OVERFLOW);
+    if (threadIdx.x == 0 && base + n > g.cand_cap) atomicOr(P.status, ORBX_DS_CAND_OVERFLOW);
 }
 
 void launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride)
@@ -161,7 +240,14 @@ void launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step,
     P.ncand = h->d_ncand;
     P.ini_th = h->prm.ini_th_fast; P.min_th = h->prm.min_th_fast;
     P.status = h->d_status;
-    dim3 grid(h->geo.total_cells, nframes);
+    P.tile_rows = h->geo.max_hcell + 6;
+    const size_t smem = (size_t)P.tile_rows * FS_TP + (size_t)(P.tile_rows - 4) * FS_SP;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    dim3 grid(h->geo.total_strips, nframes);
     ProfScope ps(h, ORBX_K_FAST);
-    k_fast_cells<<<grid, FAST_THREADS, 0, h->stream>>>(P, h->d_geo);
+    k_fast_cells<<<grid, FS_THREADS, smem, h->stream>>>(P, h->d_geo);
 }

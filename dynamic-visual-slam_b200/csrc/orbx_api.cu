@@ -79,7 +79,7 @@ static bool build_geometry(const orbx_handle *h, int w, int hgt, FrameGeom &G, s
     const orbx_params &p = h->prm;
     G.nlevels = p.nlevels; G.width = w; G.height = hgt;
     const int cdiv = p.cand_divisor > 0 ? p.cand_divisor : 16;
-    size_t off = 0, boff = 0, coff = 0; int soff = 0, cells = 0, tiles = 0, ncmax = 8;
+    size_t off = 0, boff = 0, coff = 0; int soff = 0, cells = 0, tiles = 0, ncmax = 8, strips = 0, max_hcell = 1;
     for (int l = 0; l < p.nlevels; l++) {
         LevelGeom &g = G.lv[l];
         g.w = cv_round_f((float)w * h->inv_scale[l]);                     // ORBextractor.cpp:1174
@@ -101,6 +101,13 @@ static bool build_geometry(const orbx_handle *h, int w, int hgt, FrameGeom &G, s
             g.hx = (float)W / g.nini;                                                                     // :560
         } else { g.ncols = g.nrows = 0; g.wcell = g.hcell = 1; g.nini = 0; g.hx = 1.f; }
         g.cell_first = cells; cells += g.ncols * g.nrows;
+        if (g.ncols > 0) {
+            const int cps_max = std::max(1, std::min(8, ORBX_FAST_MAX_W / g.wcell));
+            g.strips_per_row = (g.ncols + cps_max - 1) / cps_max;
+            g.cells_per_strip = (g.ncols + g.strips_per_row - 1) / g.strips_per_row;
+            max_hcell = std::max(max_hcell, g.hcell);
+        } else { g.strips_per_row = 0; g.cells_per_strip = 1; }
+        g.strip_first = strips; strips += g.strips_per_row * g.nrows;
         g.blur_tx = (g.w + 127) / 128; g.blur_ty = (g.h + 31) / 32;
         g.blur_first = tiles; tiles += g.blur_tx * g.blur_ty;
         g.cand_cap = (int)align_up((size_t)std::max(4096, g.w * g.h / cdiv), 64);
@@ -115,7 +122,7 @@ static bool build_geometry(const orbx_handle *h, int w, int hgt, FrameGeom &G, s
             resize_table(G.lv[l - 1].h, g.h, false, yt->data() + g.ytab_off);
         }
     }
-    G.total_cells = cells; G.total_blur_tiles = tiles;
+    G.total_cells = cells; G.total_blur_tiles = tiles; G.total_strips = std::max(strips, 1); G.max_hcell = max_hcell;
     G.pyr_bytes = std::max<size_t>(off, 256); G.blur_bytes = boff; G.cand_entries = coff; G.sel_entries = soff; G.node_cap_max = ncmax;
     return true;
 }

@@ -12,6 +12,7 @@
 #define ORBX_CELL_W 35               // W, ORBextractor.cpp:783
 #define ORBX_HALF_PATCH 15
 #define ORBX_PATCH 31
+#define ORBX_FAST_MAX_W 256          // max detection width (px) of one FAST strip (k_fast.cu)
 
 // candidate / selected-keypoint packing: x:12 | y:12 | score:8, coordinates relative to the border box
 __host__ __device__ inline uint32_t orbx_pack(int x, int y, int s) { return (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24); }
@@ -29,6 +30,7 @@ struct LevelGeom {
     int ncols, nrows;        // cell grid (ORBextractor.cpp:799-802)
     int wcell, hcell;
     int cell_first;          // index of this level's first cell in the flattened all-level cell list
+    int cells_per_strip, strips_per_row, strip_first;   // FAST strips: runs of cells of one cell row
     int blur_first, blur_tx, blur_ty;   // blur tiles
     int N;                   // mnFeaturesPerLevel
     int nini;                // quadtree roots (ORBextractor.cpp:559)
@@ -46,7 +48,7 @@ struct LevelGeom {
 struct FrameGeom {
     int nlevels;
     int width, height;
-    int total_cells, total_blur_tiles;
+    int total_cells, total_blur_tiles, total_strips, max_hcell;
     size_t pyr_bytes;        // per-frame pyramid slab size (levels 1..)
     size_t blur_bytes;       // per-frame blurred slab size (levels 0..)
     size_t cand_entries;     // per-frame candidate slab entries
