@@ -10,7 +10,9 @@
 //   * x*b + y*a: fp32 multiply, fp32 add, cvRound = round-half-even                  — SURVEY App. A.5
 #include "orbx_internal.h"
 
-__device__ __constant__ signed char c_pattern[1024] = {
+// read with 128-bit __ldg per lane (lane i owns pairs 8i..8i+7): a __constant__ table would serialise the
+// 32 distinct addresses of a warp
+__device__ __align__(16) const signed char c_pattern[1024] = {
 #include "../../include/orbx_pattern.inc"
 };
 __device__ __constant__ int c_umax[16];
@@ -155,7 +157,12 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescParams P, cons
     const float a = glibc_cosf(ang), b = glibc_sinf(ang);
     const uint8_t *bctr = P.blur + (size_t)f * P.blur_slab + g.boff + (size_t)cy * g.bpitch + cx;
     const int bstep = g.bpitch;
-    const signed char *pat = c_pattern + lane * 32;
+    signed char pat[32];
+    {
+        const int4 *pp = reinterpret_cast<const int4 *>(c_pattern + lane * 32);
+        *reinterpret_cast<int4 *>(pat) = __ldg(pp);
+        *reinterpret_cast<int4 *>(pat + 16) = __ldg(pp + 1);
+    }
     int val = 0;
 #pragma unroll
     for (int j = 0; j < 8; j++) {

@@ -9,9 +9,9 @@
 // Design.  One CTA owns a horizontal run of cells of one cell row (a "strip"); all levels of all
 // frames go in one launch.
 //   1. the strip's ROI is staged in shared memory with aligned 32-bit loads;
-//   2. column sweep: thread = one pixel column walking down the rows with a 7-deep register window,
-//      so the first opposite-pair test (ring 0 / ring 8 = same column, +-3 rows) costs ONE shared load
-//      per pixel; pairs (4,12), (2,10), (6,14) are loaded only for survivors.  The pair tests are an
+//   2. column sweep: thread = one pixel column walking down the rows with a 7-deep register window
+//      (ring 0 / ring 8 / centre come from the window: one shared load per pixel); the four opposite
+//      pairs (0,8) (4,12) (2,10) (6,14) are tested branch-free with min/max.  The pair tests are an
 //      exact necessary condition for S > th (every 9-arc contains a member of each opposite pair);
 //   3. survivors are compacted into a shared queue (warp-aggregated) and scored densely: the 16-arc
 //      min/max network runs on packed u16x2 lanes (VIMNMX.U16x2): low half = ring value, high half =
@@ -132,43 +132,44 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(FastParams P, const F
         for (int i = threadIdx.x; i < ((dh + 2) * FS_SP) / 16; i += FS_THREADS) reinterpret_cast<uint4 *>(s_sc)[i] = make_uint4(0, 0, 0, 0);
         if (threadIdx.x == 0) { s_qn = 0; s_ovf = 0; }
         __syncthreads();
-        // ---- column sweep with a 7-deep register window ----
+        // ---- column sweep with a 7-deep register window (rows unrolled by 7: the window rotates statically).
+        // All four opposite-pair tests are evaluated branch-free: bright arc possible iff
+        // min over pairs of max(pair) > I+th, dark arc possible iff max over pairs of min(pair) < I-th.
         for (int c0 = 0; c0 < dw; c0 += FS_THREADS) {
             const int c = c0 + threadIdx.x;
             const int cc = c < dw ? c : dw - 1;
             const bool col_ok = c < dw && (pass == 0 || s_ccnt[s_col2cell[cc]] == 0);
             const uint8_t *colp = tile + cc + 3;                        // column of the centre pixel in the tile
-            int q0 = 0, q1 = colp[0], q2 = colp[FS_TP], q3 = colp[2 * FS_TP], q4 = colp[3 * FS_TP], q5 = colp[4 * FS_TP], q6 = colp[5 * FS_TP];
-            for (int r = 0; r < dh; r++) {
-                q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = q5; q5 = q6;
-                q6 = colp[(r + 6) * FS_TP];                               // ring 0 (dy = +3) of detection row r
-                const int v = q3, hi = v + th, lo = v - th;
-                bool br = (q6 > hi) | (q0 > hi), dk = (q6 < lo) | (q0 < lo);
-                bool pass_all = false;
-                if (col_ok && (br | dk)) {
-                    const uint8_t *p = colp + (r + 3) * FS_TP;
-                    int a = p[RO(3, 0)], b = p[RO(-3, 0)];
-                    br &= (a > hi) | (b > hi); dk &= (a < lo) | (b < lo);
-                    if (br | dk) {
-                        a = p[RO(2, 2)]; b = p[RO(-2, -2)];
-                        br &= (a > hi) | (b > hi); dk &= (a < lo) | (b < lo);
-                        a = p[RO(2, -2)]; b = p[RO(-2, 2)];
-                        br &= (a > hi) | (b > hi); dk &= (a < lo) | (b < lo);
-                        pass_all = br | dk;
-                    }
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, pass_all);
-                if (bal) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&s_qn, __popc(bal));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (pass_all) {
-                        const int slot = base + __popc(bal & ((1u << lane) - 1u));
-                        if (slot < FS_QCAP) s_q[slot] = (uint16_t)((r + 3) * FS_TP + c + 3);
-                        else {                                            // queue full: score inline, NMS will scan the map
-                            const int s = fast_score_packed(colp + (r + 3) * FS_TP);
-                            s_sc[(r + 1) * FS_SP + (c + 1)] = (uint8_t)(s > th ? s - 1 : 0);
-                            s_ovf = 1;
+            int w[7];
+#pragma unroll
+            for (int k = 0; k < 6; k++) w[k] = colp[k * FS_TP];
+            for (int r0 = 0; r0 < dh; r0 += 7) {
+#pragma unroll
+                for (int k = 0; k < 7; k++) {
+                    const int r = r0 + k;
+                    if (r < dh) {                                         // uniform
+                        w[(k + 6) % 7] = colp[(r + 6) * FS_TP];           // ring 0 (dy = +3) of detection row r
+                        const int top = w[k % 7], v = w[(k + 3) % 7], bot = w[(k + 6) % 7];
+                        const uint8_t *p = colp + (r + 3) * FS_TP;
+                        const int a4 = p[RO(3, 0)], a12 = p[RO(-3, 0)], a2 = p[RO(2, 2)], a10 = p[RO(-2, -2)];
+                        const int a6 = p[RO(2, -2)], a14 = p[RO(-2, 2)];
+                        const int M = min(min(max(top, bot), max(a4, a12)), min(max(a2, a10), max(a6, a14)));
+                        const int m = max(max(min(top, bot), min(a4, a12)), max(min(a2, a10), min(a6, a14)));
+                        const bool pass_all = col_ok && ((M > v + th) | (m < v - th));
+                        const unsigned bal = __ballot_sync(0xffffffffu, pass_all);
+                        if (bal) {
+                            int base = 0;
+                            if (lane == 0) base = atomicAdd(&s_qn, __popc(bal));
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            if (pass_all) {
+                                const int slot = base + __popc(bal & ((1u << lane) - 1u));
+                                if (slot < FS_QCAP) s_q[slot] = (uint16_t)((r + 3) * FS_TP + c + 3);
+                                else {                                    // queue full: score inline, NMS will scan the map
+                                    const int s = fast_score_packed(p);
+                                    s_sc[(r + 1) * FS_SP + (c + 1)] = (uint8_t)(s > th ? s - 1 : 0);
+                                    s_ovf = 1;
+                                }
+                            }
                         }
                     }
                 }

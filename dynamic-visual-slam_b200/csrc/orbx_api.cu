@@ -108,7 +108,7 @@ static bool build_geometry(const orbx_handle *h, int w, int hgt, FrameGeom &G, s
             max_hcell = std::max(max_hcell, g.hcell);
         } else { g.strips_per_row = 0; g.cells_per_strip = 1; }
         g.strip_first = strips; strips += g.strips_per_row * g.nrows;
-        g.blur_tx = (g.w + 127) / 128; g.blur_ty = (g.h + 31) / 32;
+        g.blur_tx = (g.w + ORBX_BLUR_TW - 1) / ORBX_BLUR_TW; g.blur_ty = (g.h + 4 * ORBX_BLUR_H - 1) / (4 * ORBX_BLUR_H);
         g.blur_first = tiles; tiles += g.blur_tx * g.blur_ty;
         g.cand_cap = (int)align_up((size_t)std::max(4096, g.w * g.h / cdiv), 64);
         g.cand_off = coff; coff += (size_t)g.cand_cap;

@@ -12,6 +12,8 @@
 #define ORBX_CELL_W 35               // W, ORBextractor.cpp:783
 #define ORBX_HALF_PATCH 15
 #define ORBX_PATCH 31
+#define ORBX_BLUR_TW 128             // blur tile: 128 px x (4 warps x ORBX_BLUR_H rows) per CTA (k_blur.cu)
+#define ORBX_BLUR_H 35
 #define ORBX_FAST_MAX_W 256          // max detection width (px) of one FAST strip (k_fast.cu)
 
 // candidate / selected-keypoint packing: x:12 | y:12 | score:8, coordinates relative to the border box
