@@ -8,12 +8,12 @@
 //
 // Design.  One CTA owns a horizontal run of cells of one cell row (a "strip"); all levels of all
 // frames go in one launch.
-//   1. the strip's ROI is staged in shared memory with aligned 32-bit loads;
+//   1. the strip's ROI is staged in shared memory with aligned 128-bit loads;
 //   2. column sweep: thread = one pixel column walking down the rows with a 7-deep register window
 //      (ring 0 / ring 8 / centre come from the window: one shared load per pixel); the four opposite
 //      pairs (0,8) (4,12) (2,10) (6,14) are tested branch-free with min/max.  The pair tests are an
 //      exact necessary condition for S > th (every 9-arc contains a member of each opposite pair);
-//   3. survivors are compacted into a shared queue (warp-aggregated) and scored densely: the 16-arc
+//   3. survivor rows are kept in a per-thread bit mask, compacted once into a shared queue and scored densely: the 16-arc
 //      min/max network runs on packed u16x2 lanes (VIMNMX.U16x2): low half = ring value, high half =
 //      255 - ring value, so one instruction serves the darker and the brighter polarity;
 //   4. NMS touches queue entries only; neighbours in another cell of the strip are masked to 0;
@@ -27,7 +27,7 @@
 #include "orbx_internal.h"
 
 #define FS_THREADS 256
-#define FS_TP 272                // tile pitch: >= ORBX_FAST_MAX_W + 6 + 3 (alignment slack), multiple of 16
+#define FS_TP 288                // tile pitch: >= ORBX_FAST_MAX_W + 6 + 15 (alignment slack), multiple of 16
 #define FS_SP 272                // score-map pitch: >= detection width + 2, multiple of 16
 #define FS_QCAP 4096             // survivor queue entries (u16 tile offsets); beyond it survivors are scored inline
 #define FS_OUT_CAP 1024          // staged outputs; beyond it survivors are written straight to the global list
@@ -80,10 +80,11 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(FastParams P, const F
     __shared__ uint16_t s_q[FS_QCAP];
     __shared__ uint32_t s_out[FS_OUT_CAP];
     __shared__ int s_qn, s_nout, s_base, s_redo, s_ovf;
+    __shared__ int s_wsum[FS_THREADS / 32];
     __shared__ int s_ccnt[FS_MAX_CELLS];
     __shared__ uint8_t s_col2cell[ORBX_FAST_MAX_W];
     uint8_t *s_img = s_dyn;                                        // tile_rows x FS_TP
-    uint8_t *s_sc = s_dyn + P.tile_rows * FS_TP;                  // (tile_rows - 4) x FS_SP score map with a zero ring
+    uint8_t *s_sc = s_dyn + (P.tile_rows + 7) * FS_TP;            // (tile_rows - 4) x FS_SP score map with a zero ring
 
     const int f = blockIdx.y;
     int level = 0;
@@ -109,14 +110,13 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(FastParams P, const F
     const uint8_t *src; size_t step;
     if (level == 0) { src = P.l0 + (size_t)f * P.l0_fstride; step = P.l0_step; }
     else { src = P.pyr + (size_t)f * P.pyr_slab + g.off; step = (size_t)g.pitch; }
-    // stage the ROI with aligned 32-bit loads; tile column `ax` is image column iniX
-    const int ax = iniX & 3;
-    const int words = (ax + rw + 3) >> 2;
+    // stage the ROI with aligned 128-bit loads; tile column `ax` is image column iniX
+    const int ax = iniX & 15;
+    const int vecs = (ax + rw + 15) >> 4;
     src += (size_t)iniY * step + (iniX - ax);
-    for (int r = threadIdx.x >> 6; r < rh; r += FS_THREADS / 64) {
-        const uint32_t *srow = reinterpret_cast<const uint32_t *>(src + (size_t)r * step);
-        uint32_t *drow = reinterpret_cast<uint32_t *>(s_img + r * FS_TP);
-        for (int wi = threadIdx.x & 63; wi < words; wi += 64) drow[wi] = __ldg(srow + wi);
+    for (int i = threadIdx.x; i < rh * 32; i += FS_THREADS) {
+        const int r = i >> 5, vi = i & 31;
+        if (vi < vecs) reinterpret_cast<uint4 *>(s_img + r * FS_TP)[vi] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * step) + vi);
     }
     for (int c = threadIdx.x; c < dw; c += FS_THREADS) s_col2cell[c] = (uint8_t)min(c / g.wcell, ncell - 1);
     if (threadIdx.x < FS_MAX_CELLS) s_ccnt[threadIdx.x] = 0;
@@ -135,19 +135,22 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(FastParams P, const F
         // ---- column sweep with a 7-deep register window (rows unrolled by 7: the window rotates statically).
         // All four opposite-pair tests are evaluated branch-free: bright arc possible iff
         // min over pairs of max(pair) > I+th, dark arc possible iff max over pairs of min(pair) < I-th.
+        // Survivor rows are collected in a per-thread 63-bit mask and compacted once per row chunk.
         for (int c0 = 0; c0 < dw; c0 += FS_THREADS) {
             const int c = c0 + threadIdx.x;
             const int cc = c < dw ? c : dw - 1;
             const bool col_ok = c < dw && (pass == 0 || s_ccnt[s_col2cell[cc]] == 0);
             const uint8_t *colp = tile + cc + 3;                        // column of the centre pixel in the tile
-            int w[7];
+            for (int rc = 0; rc < dh; rc += 63) {
+                unsigned long long mask = 0ull;
+                int w[7];
 #pragma unroll
-            for (int k = 0; k < 6; k++) w[k] = colp[k * FS_TP];
-            for (int r0 = 0; r0 < dh; r0 += 7) {
+                for (int k = 0; k < 6; k++) w[k] = colp[(rc + k) * FS_TP];
+                const int rend = min(dh, rc + 63);
+                for (int r0 = rc; r0 < rend; r0 += 7) {
 #pragma unroll
-                for (int k = 0; k < 7; k++) {
-                    const int r = r0 + k;
-                    if (r < dh) {                                         // uniform
+                    for (int k = 0; k < 7; k++) {
+                        const int r = r0 + k;                             // rows past dh read padding rows of the tile and are masked
                         w[(k + 6) % 7] = colp[(r + 6) * FS_TP];           // ring 0 (dy = +3) of detection row r
                         const int top = w[k % 7], v = w[(k + 3) % 7], bot = w[(k + 6) % 7];
                         const uint8_t *p = colp + (r + 3) * FS_TP;
@@ -155,24 +158,37 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(FastParams P, const F
                         const int a6 = p[RO(2, -2)], a14 = p[RO(-2, 2)];
                         const int M = min(min(max(top, bot), max(a4, a12)), min(max(a2, a10), max(a6, a14)));
                         const int m = max(max(min(top, bot), min(a4, a12)), max(min(a2, a10), min(a6, a14)));
-                        const bool pass_all = col_ok && ((M > v + th) | (m < v - th));
-                        const unsigned bal = __ballot_sync(0xffffffffu, pass_all);
-                        if (bal) {
-                            int base = 0;
-                            if (lane == 0) base = atomicAdd(&s_qn, __popc(bal));
-                            base = __shfl_sync(0xffffffffu, base, 0);
-                            if (pass_all) {
-                                const int slot = base + __popc(bal & ((1u << lane) - 1u));
-                                if (slot < FS_QCAP) s_q[slot] = (uint16_t)((r + 3) * FS_TP + c + 3);
-                                else {                                    // queue full: score inline, NMS will scan the map
-                                    const int s = fast_score_packed(p);
-                                    s_sc[(r + 1) * FS_SP + (c + 1)] = (uint8_t)(s > th ? s - 1 : 0);
-                                    s_ovf = 1;
-                                }
-                            }
-                        }
+                        const bool hit = ((M > v + th) | (m < v - th)) & (r < rend);
+                        mask |= (unsigned long long)hit << (r - rc);
                     }
                 }
+                if (!col_ok) mask = 0ull;
+                // block-wide compaction of the masks into the queue
+                const int cnt = __popcll(mask);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+                if (lane == 31) s_wsum[threadIdx.x >> 5] = incl;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    int run = s_qn;
+                    for (int wv = 0; wv < FS_THREADS / 32; wv++) { const int t = s_wsum[wv]; s_wsum[wv] = run; run += t; }
+                    s_qn = run;
+                }
+                __syncthreads();
+                int slot = s_wsum[threadIdx.x >> 5] + incl - cnt;
+                while (mask) {
+                    const int r = rc + __ffsll((long long)mask) - 1;
+                    mask &= mask - 1;
+                    if (slot < FS_QCAP) s_q[slot] = (uint16_t)((r + 3) * FS_TP + c + 3);
+                    else {                                                // queue full: score inline, NMS will scan the map
+                        const int s = fast_score_packed(colp + (r + 3) * FS_TP);
+                        s_sc[(r + 1) * FS_SP + (c + 1)] = (uint8_t)(s > th ? s - 1 : 0);
+                        s_ovf = 1;
+                    }
+                    slot++;
+                }
+                __syncthreads();
             }
         }
         __syncthreads();
@@ -242,7 +258,7 @@ void launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step,
     P.ini_th = h->prm.ini_th_fast; P.min_th = h->prm.min_th_fast;
     P.status = h->d_status;
     P.tile_rows = h->geo.max_hcell + 6;
-    const size_t smem = (size_t)P.tile_rows * FS_TP + (size_t)(P.tile_rows - 4) * FS_SP;
+    const size_t smem = (size_t)(P.tile_rows + 7) * FS_TP + (size_t)(P.tile_rows - 4) * FS_SP;
     static size_t configured = 0;
     if (smem > configured) {
         cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

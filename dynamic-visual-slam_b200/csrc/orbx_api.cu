@@ -122,6 +122,24 @@ static bool build_geometry(const orbx_handle *h, int w, int hgt, FrameGeom &G, s
             resize_table(G.lv[l - 1].h, g.h, false, yt->data() + g.ytab_off);
         }
     }
+    // source window of a 128 x 64 resize tile, maximised over levels and tiles (k_pyramid.cu)
+    int rzp = 16, rzr = 1;
+    if (xt && yt) for (int l = 1; l < p.nlevels; l++) {
+        const LevelGeom &g = G.lv[l];
+        const ResizeTab *tx = xt->data() + g.xtab_off, *ty = yt->data() + g.ytab_off;
+        for (int x0 = 0; x0 < g.w; x0 += 128) {
+            const int x1 = std::min(x0 + 128, g.w) - 1;
+            const int lo = tx[x0].ofs & ~15, hi = std::min(tx[x1].ofs + 1, G.lv[l - 1].w - 1);
+            rzp = std::max(rzp, ((hi - lo + 16) >> 4) * 16);
+        }
+        for (int y0 = 0; y0 < g.h; y0 += 64) {
+            const int y1 = std::min(y0 + 64, g.h) - 1;
+            const int lo = std::max(0, std::min(ty[y0].ofs, G.lv[l - 1].h - 1)), hi = std::max(0, std::min(ty[y1].ofs + 1, G.lv[l - 1].h - 1));
+            rzr = std::max(rzr, hi - lo + 1);
+        }
+    }
+    G.rz_pitch = rzp; G.rz_rows = rzr;
+    if ((size_t)rzp * rzr > 200 * 1024) return false;
     G.total_cells = cells; G.total_blur_tiles = tiles; G.total_strips = std::max(strips, 1); G.max_hcell = max_hcell;
     G.pyr_bytes = std::max<size_t>(off, 256); G.blur_bytes = boff; G.cand_entries = coff; G.sel_entries = soff; G.node_cap_max = ncmax;
     return true;

@@ -51,6 +51,7 @@ struct FrameGeom {
     int nlevels;
     int width, height;
     int total_cells, total_blur_tiles, total_strips, max_hcell;
+    int rz_pitch, rz_rows;   // shared-memory window of the resize kernel (max over levels and tiles)
     size_t pyr_bytes;        // per-frame pyramid slab size (levels 1..)
     size_t blur_bytes;       // per-frame blurred slab size (levels 0..)
     size_t cand_entries;     // per-frame candidate slab entries
