@@ -1,0 +1,234 @@
+// ORBextractor.hpp — header-only C++ adapter over the C ABI (include/orbx.h).
+//
+// Reproduces the two call shapes the reference's nodes use today, so that switching the frontend / backend
+// to the B200 path is a change of #include and namespace, not of call sites:
+//
+//   seam 1  ORB_SLAM3::ORBextractor                      reference include/dynamic_visual_slam/ORBextractor.hpp:44-111
+//           ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)                          :50-51
+//           int operator()(InputArray image, InputArray mask, vector<KeyPoint>&, OutputArray desc,
+//                          vector<int>& vLappingArea)                                                    :58-60
+//           GetLevels / GetScaleFactor / GetScaleFactors / GetInverseScaleFactors /
+//           GetScaleSigmaSquares / GetInverseScaleSigmaSquares                                           :62-82
+//           public mvImagePyramid                                                                        :84
+//   seam 2  cv::BFMatcher(cv::NORM_HAMMING).match(query, train, matches)      reference frontend.cpp:220, :614, :1123;
+//                                                                             backend.cpp:222, :1072
+//   plus    Frontend::filterDepth (frontend.cpp:503-527) and the `distance < 50` loop (:1126-1132) as optional
+//           fused post-filters (extractFiltered / matchBelow), results identical to running them on the host.
+//
+// Error behaviour mirrors the reference: operator() returns -1 for an empty image (ORBextractor.cpp:1090-1091),
+// a non-CV_8UC1 image is a programming error (the reference asserts, :1094), everything else throws
+// (cv::Exception when OpenCV is present, std::runtime_error otherwise) and is caught by the nodes' existing
+// try/catch (frontend.cpp:1319-1323).  Like the reference's extractor an instance is NOT re-entrant.
+//
+// Build modes:
+//   -DORBX_WITH_OPENCV   cv::Mat / cv::KeyPoint / cv::DMatch are used directly (what the ROS nodes compile with)
+//   (default)            layout-identical stand-ins in orbx::compat, so the adapter builds and is tested where
+//                        OpenCV headers are absent (this repository's containers).
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/orbx.h"
+
+#ifdef ORBX_WITH_OPENCV
+#include <opencv2/core.hpp>
+#include <opencv2/features2d.hpp>
+#endif
+
+namespace orbx {
+
+#ifdef ORBX_WITH_OPENCV
+using Mat = cv::Mat;
+using KeyPoint = cv::KeyPoint;
+using DMatch = cv::DMatch;
+static inline int type_8uc1() { return CV_8UC1; }
+static inline int type_16uc1() { return CV_16UC1; }
+[[noreturn]] static inline void raise(const std::string &what) { CV_Error(cv::Error::StsError, what); }
+#else
+namespace compat {
+// cv::KeyPoint is { Point2f pt; float size, angle, response; int octave, class_id; } = 28 bytes
+struct Point2f { float x, y; };
+struct KeyPoint { Point2f pt; float size, angle, response; int octave, class_id; };
+// cv::DMatch is { int queryIdx, trainIdx, imgIdx; float distance; } = 16 bytes
+struct DMatch { int queryIdx, trainIdx, imgIdx; float distance; };
+// the subset of cv::Mat the path touches: a dense 2-D array with a row step, optionally owning its bytes
+struct Mat {
+    int rows = 0, cols = 0, type_ = 0;       // type_: 0 = CV_8UC1, 2 = CV_16UC1 (OpenCV's numeric values)
+    size_t step = 0;
+    uint8_t *data = nullptr;
+    std::vector<uint8_t> own;
+    Mat() {}
+    Mat(int r, int c, int t, void *d, size_t s) : rows(r), cols(c), type_(t), step(s), data((uint8_t *)d) {}
+    void create(int r, int c, int t) {
+        rows = r; cols = c; type_ = t; step = (size_t)c * (t == 2 ? 2 : 1);
+        own.assign(step * (size_t)(r > 0 ? r : 0), 0); data = own.data();
+    }
+    bool empty() const { return rows <= 0 || cols <= 0 || !data; }
+    int type() const { return type_; }
+    template <class T> T *ptr(int r = 0) { return (T *)(data + (size_t)r * step); }
+    template <class T> const T *ptr(int r = 0) const { return (const T *)(data + (size_t)r * step); }
+};
+}  // namespace compat
+using Mat = compat::Mat;
+using KeyPoint = compat::KeyPoint;
+using DMatch = compat::DMatch;
+static inline int type_8uc1() { return 0; }
+static inline int type_16uc1() { return 2; }
+[[noreturn]] static inline void raise(const std::string &what) { throw std::runtime_error(what); }
+#endif
+
+static_assert(sizeof(KeyPoint) == sizeof(orbx_keypoint), "cv::KeyPoint layout");
+static_assert(sizeof(DMatch) == sizeof(orbx_dmatch), "cv::DMatch layout");
+
+// Drop-in for ORB_SLAM3::ORBextractor.
+class ORBextractor {
+public:
+    enum { HARRIS_SCORE = 0, FAST_SCORE = 1 };
+
+    // max_width / max_height size the device arenas once (README default stream: 1280x720); device = CUDA ordinal.
+    ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST,
+                 int max_width = 1280, int max_height = 720, int device = 0)
+    {
+        orbx_params p;
+        orbx_default_params(&p);
+        p.nfeatures = nfeatures; p.scale_factor = scaleFactor; p.nlevels = nlevels;
+        p.ini_th_fast = iniThFAST; p.min_th_fast = minThFAST;
+        p.max_width = max_width; p.max_height = max_height; p.device = device;
+        const orbx_status st = orbx_create(&p, &h_);
+        if (st != ORBX_OK) raise(std::string("orbx_create: ") + orbx_last_error(nullptr));
+        nlevels_ = nlevels;
+    }
+    ~ORBextractor() { orbx_destroy(h_); }
+    ORBextractor(const ORBextractor &) = delete;
+    ORBextractor &operator=(const ORBextractor &) = delete;
+
+    // Mask is ignored, as in the reference (ORBextractor.hpp:55-57); vLappingArea = {0,0} => mono only (:1152-1161).
+    int operator()(const Mat &image, const Mat & /*mask*/, std::vector<KeyPoint> &keypoints, Mat &descriptors,
+                   std::vector<int> & /*vLappingArea*/)
+    {
+        return extractFiltered(image, Mat(), keypoints, descriptors);
+    }
+
+    // operator() followed by Frontend::filterDepth (frontend.cpp:503-527) when `depth` (CV_16UC1, millimetres) is given.
+    int extractFiltered(const Mat &image, const Mat &depth, std::vector<KeyPoint> &keypoints, Mat &descriptors)
+    {
+        if (image.empty()) return -1;                                              // ORBextractor.cpp:1090-1091
+        if (image.type() != type_8uc1()) raise("ORBextractor: image must be CV_8UC1");   // reference: assert, :1094
+        if (!depth.empty() && (depth.type() != type_16uc1() || depth.rows != image.rows || depth.cols != image.cols))
+            raise("ORBextractor: depth must be CV_16UC1 of the image size");
+        kbuf_.resize(cap_);
+        dbuf_.resize((size_t)cap_ * ORBX_DESC_BYTES);
+        int32_t n = 0;
+        orbx_status st = orbx_extract_filtered(h_, image.data, image.cols, image.rows, (size_t)image.step,
+                                               depth.empty() ? nullptr : (const uint16_t *)depth.data, depth.empty() ? 0 : (size_t)depth.step,
+                                               nullptr, 0, 0, kbuf_.data(), dbuf_.data(), cap_, &n);
+        if (st == ORBX_E_CAPACITY && n > cap_) {                                   // grow once and retry
+            cap_ = n + 64; kbuf_.resize(cap_); dbuf_.resize((size_t)cap_ * ORBX_DESC_BYTES);
+            st = orbx_extract_filtered(h_, image.data, image.cols, image.rows, (size_t)image.step,
+                                       depth.empty() ? nullptr : (const uint16_t *)depth.data, depth.empty() ? 0 : (size_t)depth.step,
+                                       nullptr, 0, 0, kbuf_.data(), dbuf_.data(), cap_, &n);
+        }
+        if (st != ORBX_OK) raise(std::string("orbx_extract: ") + orbx_last_error(h_));
+        keypoints.resize((size_t)n);
+        if (n > 0) std::memcpy((void *)keypoints.data(), kbuf_.data(), (size_t)n * sizeof(orbx_keypoint));
+        if (n == 0) descriptors = Mat();                                           // _descriptors.release(), :1108
+        else {
+            descriptors.create(n, 32, type_8uc1());                                // :1112
+            for (int r = 0; r < n; r++) std::memcpy(descriptors.ptr<uint8_t>(r), dbuf_.data() + (size_t)r * ORBX_DESC_BYTES, ORBX_DESC_BYTES);
+        }
+        last_w_ = image.cols; last_h_ = image.rows;
+        pyramid_valid_ = false;
+        return n;                                                                  // monoIndex, :1166
+    }
+
+    int GetLevels() { return orbx_get_levels(h_); }
+    float GetScaleFactor() { return orbx_get_scale_factor(h_); }
+    std::vector<float> GetScaleFactors() { return vec(orbx_get_scale_factors); }
+    std::vector<float> GetInverseScaleFactors() { return vec(orbx_get_inverse_scale_factors); }
+    std::vector<float> GetScaleSigmaSquares() { return vec(orbx_get_scale_sigma_squares); }
+    std::vector<float> GetInverseScaleSigmaSquares() { return vec(orbx_get_inverse_scale_sigma_squares); }
+
+    // The reference exposes its pyramid as a public member (ORBextractor.hpp:84).  Here the levels live in HBM and
+    // are fetched on demand (nothing in the two nodes reads them; they exist for parity checks).
+    const std::vector<Mat> &imagePyramid()
+    {
+        if (!pyramid_valid_ && last_w_ > 0) {
+            mvImagePyramid.resize((size_t)nlevels_);
+            for (int l = 0; l < nlevels_; l++) {
+                int32_t lw = 0, lh = 0;
+                orbx_level_size(h_, last_w_, last_h_, l, &lw, &lh);
+                mvImagePyramid[l].create(lh, lw, type_8uc1());
+                if (orbx_get_pyramid_level(h_, 0, l, mvImagePyramid[l].data, (size_t)mvImagePyramid[l].step) != ORBX_OK)
+                    raise(std::string("orbx_get_pyramid_level: ") + orbx_last_error(h_));
+            }
+            pyramid_valid_ = true;
+        }
+        return mvImagePyramid;
+    }
+    std::vector<Mat> mvImagePyramid;
+
+    orbx_handle *handle() { return h_; }
+
+private:
+    std::vector<float> vec(void (*fn)(const orbx_handle *, float *))
+    {
+        std::vector<float> v((size_t)nlevels_);
+        fn(h_, v.data());
+        return v;
+    }
+    orbx_handle *h_ = nullptr;
+    int nlevels_ = 0, cap_ = 2048, last_w_ = 0, last_h_ = 0;
+    bool pyramid_valid_ = false;
+    std::vector<orbx_keypoint> kbuf_;
+    std::vector<uint8_t> dbuf_;
+};
+
+// Drop-in for the `cv::BFMatcher matcher_(cv::NORM_HAMMING)` members (frontend.cpp:294, backend.cpp:628).
+class BFMatcher {
+public:
+    explicit BFMatcher(ORBextractor &ex) : h_(ex.handle()) {}
+    explicit BFMatcher(orbx_handle *h) : h_(h) {}
+
+    // cv::DescriptorMatcher::match: one DMatch per query row, lowest trainIdx on ties
+    void match(const Mat &query, const Mat &train, std::vector<DMatch> &matches) { run(query, train, 1, 0.f, 0.f, matches); }
+    // match() followed by the nodes' `if (m.distance < max_dist) good.push_back(m)` loop (frontend.cpp:1126-1132)
+    void matchBelow(const Mat &query, const Mat &train, float max_dist, std::vector<DMatch> &good) { run(query, train, 1, max_dist, 0.f, good); }
+    // cv::DescriptorMatcher::knnMatch(k = 2)
+    void knnMatch(const Mat &query, const Mat &train, std::vector<std::vector<DMatch>> &matches, int k)
+    {
+        if (k != 2) raise("BFMatcher::knnMatch: only k = 2 is implemented");
+        std::vector<DMatch> flat;
+        run(query, train, 2, 0.f, 0.f, flat);
+        matches.assign(flat.size() / 2, std::vector<DMatch>());
+        for (size_t i = 0; i < matches.size(); i++)
+            for (int j = 0; j < 2; j++) if (flat[2 * i + j].trainIdx >= 0) matches[i].push_back(flat[2 * i + j]);
+    }
+
+private:
+    void run(const Mat &query, const Mat &train, int k, float max_dist, float ratio, std::vector<DMatch> &out)
+    {
+        out.clear();
+        if (query.empty() || train.empty()) return;                 // callers pre-guard this case (frontend.cpp:1107-1117)
+        if (query.cols != 32 || train.cols != 32 || query.type() != type_8uc1() || train.type() != type_8uc1())
+            raise("BFMatcher: descriptors must be N x 32 CV_8U");
+        std::vector<uint8_t> q = pack(query), t = pack(train);
+        std::vector<orbx_dmatch> buf((size_t)query.rows * k);
+        int32_t n = 0;
+        if (orbx_match(h_, q.data(), query.rows, t.data(), train.rows, k, max_dist, ratio, buf.data(), &n) != ORBX_OK)
+            raise(std::string("orbx_match: ") + orbx_last_error(h_));
+        out.resize((size_t)n);
+        if (n > 0) std::memcpy((void *)out.data(), buf.data(), (size_t)n * sizeof(orbx_dmatch));
+    }
+    static std::vector<uint8_t> pack(const Mat &m)
+    {
+        std::vector<uint8_t> v((size_t)m.rows * 32);
+        for (int r = 0; r < m.rows; r++) std::memcpy(v.data() + (size_t)r * 32, m.data + (size_t)r * m.step, 32);
+        return v;
+    }
+    orbx_handle *h_;
+};
+
+}  // namespace orbx
