@@ -9,13 +9,17 @@
 // Design.  One CTA owns a horizontal run of cells of one cell row (a "strip"); all levels of all
 // frames go in one launch.
 //   1. the strip's ROI is staged in shared memory with aligned 128-bit loads;
-//   2. column sweep: thread = one pixel column walking down the rows with a 7-deep register window
-//      (ring 0 / ring 8 / centre come from the window: one shared load per pixel); the four opposite
-//      pairs (0,8) (4,12) (2,10) (6,14) are tested branch-free with min/max.  The pair tests are an
-//      exact necessary condition for S > th (every 9-arc contains a member of each opposite pair);
-//   3. survivor rows are kept in a per-thread bit mask, compacted once into a shared queue and scored densely: the 16-arc
-//      min/max network runs on packed u16x2 lanes (VIMNMX.U16x2): low half = ring value, high half =
-//      255 - ring value, so one instruction serves the darker and the brighter polarity;
+//   2. packed column sweep: a thread owns one aligned 32-bit word of the tile (4 adjacent pixels) and walks
+//      down a band of rows with a 7-row register window (3 LDS.32 + 4 PRMT per row of 4 pixels).  Per row it
+//      evaluates a polarity-agnostic pre-test on the four opposite ring pairs (0,8) (4,12) (2,10) (6,14):
+//      |I(ring) - I(p)| for 4 pixels is ONE VABSDIFF4.U8; "some member of the pair differs by more than T"
+//      with T = 2^k - 1 <= th is an OR, a mask and one add per pair (SWAR, no per-byte compares).  Every
+//      9-arc contains a member of each opposite pair, so the test is an exact NECESSARY condition for
+//      S > th; it is loose by design (T <= th, sign ignored) and passes ~5 % of the pixels;
+//   3. survivor flags are kept bit-packed per thread (7 rows x 4 pixels per register), compacted once into a
+//      shared queue and scored exactly: the 16-arc min/max network runs on packed u16x2 lanes
+//      (VIMNMX3.U16x2): low half = ring value, high half = 255 - ring value, so one instruction serves
+//      the darker and the brighter polarity;
 //   4. NMS touches queue entries only; neighbours in another cell of the strip are masked to 0;
 //   5. cells with no survivor at iniThFAST are swept again at minThFAST (the reference's retry).
 // Survivors are appended to the (frame, level) candidate list with one global atomic per CTA;
@@ -27,11 +31,17 @@
 #include "orbx_internal.h"
 
 #define FS_THREADS 256
-#define FS_TP 288                // tile pitch: >= ORBX_FAST_MAX_W + 6 + 15 (alignment slack), multiple of 16
+#define FS_GROUPS 64             // 4-pixel column groups per row band (FS_THREADS = FS_GROUPS x FS_BANDS)
+#define FS_BANDS 4
+#define FS_TP 288                // tile pitch: >= 15 (alignment) + ORBX_FAST_MAX_W + 6 + 8, multiple of 16
+#define FS_TPW (FS_TP / 4)
+#define FS_PAD 16                // bytes in front of the tile: the word left of tile column 0 is addressable
+#define FS_PADROWS 16            // rows behind the tile: the unrolled sweep may overrun a band by < 16 rows
 #define FS_SP 272                // score-map pitch: >= detection width + 2, multiple of 16
-#define FS_QCAP 4096             // survivor queue entries (u16 tile offsets); beyond it survivors are scored inline
+#define FS_QCAP 6144             // survivor queue entries (u16 tile offsets); beyond it survivors are scored inline
 #define FS_OUT_CAP 1024          // staged outputs; beyond it survivors are written straight to the global list
 #define FS_MAX_CELLS 8
+#define FS_MAX_GROUPS7 3         // 7-row flag registers per thread: bands of up to 21 rows (hCell <= 69 => <= 18)
 
 struct FastParams {
     const uint8_t *l0; size_t l0_step, l0_fstride;
@@ -47,6 +57,9 @@ struct FastParams {
 
 // S on the raw ring values: S = max( I(p) - min_k max9_k(ring), max_k min9_k(ring) - I(p) ).
 // Packed lanes: lo16 = r, hi16 = 255 - r  =>  a lane-wise min yields (min r, 255 - max r).
+// min9_k = min3( min3(r_k..r_k+2), min3(r_k+3..r_k+5), min3(r_k+6..r_k+8) ): 40 three-input min/max in all.
+__device__ __forceinline__ uint32_t vmin3u2(uint32_t a, uint32_t b, uint32_t c) { return __vminu2(__vminu2(a, b), c); }
+__device__ __forceinline__ uint32_t vmax3u2(uint32_t a, uint32_t b, uint32_t c) { return __vmaxu2(__vmaxu2(a, b), c); }
 __device__ __forceinline__ int fast_score_packed(const uint8_t *p)
 {
     const int v = p[0];
@@ -57,21 +70,35 @@ __device__ __forceinline__ int fast_score_packed(const uint8_t *p)
     r[8] = PK(p[RO(0, -3)]);  r[9] = PK(p[RO(-1, -3)]);  r[10] = PK(p[RO(-2, -2)]); r[11] = PK(p[RO(-3, -1)]);
     r[12] = PK(p[RO(-3, 0)]); r[13] = PK(p[RO(-3, 1)]);  r[14] = PK(p[RO(-2, 2)]);  r[15] = PK(p[RO(-1, 3)]);
 #undef PK
-    uint32_t m2[16], m4[16];
+    uint32_t m3[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) m2[k] = __vminu2(r[k], r[(k + 1) & 15]);
+    for (int k = 0; k < 16; k++) m3[k] = vmin3u2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+    uint32_t m9[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) m4[k] = __vminu2(m2[k], m2[(k + 2) & 15]);
-    uint32_t best = 0;           // per lane: max_k min9_k
+    for (int k = 0; k < 16; k++) m9[k] = vmin3u2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+    uint32_t b4[4];
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const uint32_t m9 = __vminu2(__vminu2(m4[k], m4[(k + 4) & 15]), r[(k + 8) & 15]);
-        best = __vmaxu2(best, m9);
-    }
+    for (int k = 0; k < 4; k++) b4[k] = __vmaxu2(vmax3u2(m9[4 * k], m9[4 * k + 1], m9[4 * k + 2]), m9[4 * k + 3]);
+    const uint32_t best = __vmaxu2(__vmaxu2(b4[0], b4[1]), __vmaxu2(b4[2], b4[3]));   // per lane: max_k min9_k
     const int hi_of_min = (int)(best & 0xFFFFu);                  // max_k min9_k(r)
     const int lo_of_max = 255 - (int)(best >> 16);                // min_k max9_k(r)
     const int s_dark = v - lo_of_max, s_bright = hi_of_min - v;
     return s_dark > s_bright ? s_dark : s_bright;
+}
+
+// one tile row entering the sweep window: the thread's own word C plus the four shifted views of it
+struct FastRow { uint32_t C, P2, M2, P3, M3; };
+__device__ __forceinline__ FastRow fast_row(const uint32_t *colw, int trow)
+{
+    const uint32_t *q = colw + trow * FS_TPW;
+    const uint32_t L = q[-1], C = q[0], R = q[1];
+    FastRow w;
+    w.C = C;
+    w.P2 = __byte_perm(C, R, 0x5432);      // columns x+2 .. x+5
+    w.M2 = __byte_perm(L, C, 0x5432);      // columns x-2 .. x+1
+    w.P3 = __byte_perm(C, R, 0x6543);      // columns x+3 .. x+6
+    w.M3 = __byte_perm(L, C, 0x4321);      // columns x-3 .. x
+    return w;
 }
 
 __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(FastParams P, const FrameGeom *__restrict__ G)
@@ -83,8 +110,8 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(FastParams P, const F
     __shared__ int s_wsum[FS_THREADS / 32];
     __shared__ int s_ccnt[FS_MAX_CELLS];
     __shared__ uint8_t s_col2cell[ORBX_FAST_MAX_W];
-    uint8_t *s_img = s_dyn;                                        // tile_rows x FS_TP
-    uint8_t *s_sc = s_dyn + (P.tile_rows + 7) * FS_TP;            // (tile_rows - 4) x FS_SP score map with a zero ring
+    uint8_t *s_img = s_dyn + FS_PAD;                                               // (tile_rows + FS_PADROWS) x FS_TP
+    uint8_t *s_sc = s_dyn + FS_PAD + (P.tile_rows + FS_PADROWS) * FS_TP;           // (tile_rows - 4) x FS_SP score map with a zero ring
 
     const int f = blockIdx.y;
     int level = 0;
@@ -121,83 +148,103 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(FastParams P, const F
     for (int c = threadIdx.x; c < dw; c += FS_THREADS) s_col2cell[c] = (uint8_t)min(c / g.wcell, ncell - 1);
     if (threadIdx.x < FS_MAX_CELLS) s_ccnt[threadIdx.x] = 0;
     if (threadIdx.x == 0) { s_nout = 0; s_redo = 0; }
-    const uint8_t *tile = s_img + ax;               // tile[r * FS_TP + c] = ROI(r, c)
     const int lane = threadIdx.x & 31;
     uint32_t *gdst = P.cand + (size_t)f * P.cand_slab + g.cand_off;
     int32_t *gcnt = &P.ncand[f * nl + level];
 
+    // sweep geometry: thread = tile word wi (4 pixels) x row band
+    const int grp = threadIdx.x & (FS_GROUPS - 1), band = threadIdx.x / FS_GROUPS;
+    const int wi = ((ax + 3) >> 2) + grp;                         // first word holding a detection column + group
+    const int cbase = 4 * wi - (ax + 3);                          // detection column of byte 0 of the word (-3 .. )
+    const uint32_t *colw = reinterpret_cast<const uint32_t *>(s_img) + wi;
+    const int RB = (dh + FS_BANDS - 1) / FS_BANDS;                // rows per band (<= 18 for hCell <= 69)
+    const int r_begin = band * RB, r_end = min(dh, r_begin + RB);
+
     for (int pass = 0; pass < 2; pass++) {
         const int th = pass == 0 ? P.ini_th : P.min_th;
+        // loose pre-test threshold T = 2^sh - 1 <= th: |d| > T  <=>  (|d| & HM) != 0
+        const int sh = min(7, 31 - __clz(th + 1));
+        const uint32_t HM = ((0xFFu << sh) & 0xFFu) * 0x01010101u;
+        const uint32_t KK = (0x80u - (1u << sh)) * 0x01010101u;   // t + KK sets bit 7 of every byte with t >= 2^sh
         // zero the score map (1-px ring included) and the queue
         for (int i = threadIdx.x; i < ((dh + 2) * FS_SP) / 16; i += FS_THREADS) reinterpret_cast<uint4 *>(s_sc)[i] = make_uint4(0, 0, 0, 0);
         if (threadIdx.x == 0) { s_qn = 0; s_ovf = 0; }
         __syncthreads();
-        // ---- column sweep with a 7-deep register window (rows unrolled by 7: the window rotates statically).
-        // All four opposite-pair tests are evaluated branch-free: bright arc possible iff
-        // min over pairs of max(pair) > I+th, dark arc possible iff max over pairs of min(pair) < I-th.
-        // Survivor rows are collected in a per-thread 63-bit mask and compacted once per row chunk.
-        for (int c0 = 0; c0 < dw; c0 += FS_THREADS) {
-            const int c = c0 + threadIdx.x;
-            const int cc = c < dw ? c : dw - 1;
-            const bool col_ok = c < dw && (pass == 0 || s_ccnt[s_col2cell[cc]] == 0);
-            const uint8_t *colp = tile + cc + 3;                        // column of the centre pixel in the tile
-            for (int rc = 0; rc < dh; rc += 63) {
-                unsigned long long mask = 0ull;
-                int w[7];
+        // columns this thread may report: inside the detection area and (retry pass) in a cell that is still empty
+        uint32_t vm = 0;
 #pragma unroll
-                for (int k = 0; k < 6; k++) w[k] = colp[(rc + k) * FS_TP];
-                const int rend = min(dh, rc + 63);
-                for (int r0 = rc; r0 < rend; r0 += 7) {
+        for (int j = 0; j < 4; j++) {
+            const int c = cbase + j;
+            if (c >= 0 && c < dw && (pass == 0 || s_ccnt[s_col2cell[c]] == 0)) vm |= 0xFEu << (8 * j);
+        }
+        // ---- packed sweep: flags[gi] bit (7-k) of byte j = pixel (row r_begin + 7*gi + k, column cbase + j) survives ----
+        uint32_t flags[FS_MAX_GROUPS7] = { 0u, 0u, 0u };
+        if (vm != 0u && r_begin < r_end) {
+            FastRow w[7];
+#pragma unroll
+            for (int k = 0; k < 6; k++) w[k] = fast_row(colw, r_begin + k);
+#pragma unroll
+            for (int gi = 0; gi < FS_MAX_GROUPS7; gi++) {
+                const int r0 = r_begin + 7 * gi;
+                if (r0 < r_end) {
+                    uint32_t fl = 0u;
 #pragma unroll
                     for (int k = 0; k < 7; k++) {
-                        const int r = r0 + k;                             // rows past dh read padding rows of the tile and are masked
-                        w[(k + 6) % 7] = colp[(r + 6) * FS_TP];           // ring 0 (dy = +3) of detection row r
-                        const int top = w[k % 7], v = w[(k + 3) % 7], bot = w[(k + 6) % 7];
-                        const uint8_t *p = colp + (r + 3) * FS_TP;
-                        const int a4 = p[RO(3, 0)], a12 = p[RO(-3, 0)], a2 = p[RO(2, 2)], a10 = p[RO(-2, -2)];
-                        const int a6 = p[RO(2, -2)], a14 = p[RO(-2, 2)];
-                        const int M = min(min(max(top, bot), max(a4, a12)), min(max(a2, a10), max(a6, a14)));
-                        const int m = max(max(min(top, bot), min(a4, a12)), max(min(a2, a10), min(a6, a14)));
-                        const bool hit = ((M > v + th) | (m < v - th)) & (r < rend);
-                        mask |= (unsigned long long)hit << (r - rc);
+                        w[(k + 6) % 7] = fast_row(colw, r0 + k + 6);           // ring row dy = +3 of detection row r0 + k
+                        const uint32_t C0 = w[(k + 3) % 7].C;
+                        const uint32_t p08 = __vabsdiffu4(w[(k + 6) % 7].C, C0) | __vabsdiffu4(w[k % 7].C, C0);
+                        const uint32_t p4c = __vabsdiffu4(w[(k + 3) % 7].P3, C0) | __vabsdiffu4(w[(k + 3) % 7].M3, C0);
+                        const uint32_t p2a = __vabsdiffu4(w[(k + 5) % 7].P2, C0) | __vabsdiffu4(w[(k + 1) % 7].M2, C0);
+                        const uint32_t p6e = __vabsdiffu4(w[(k + 1) % 7].P2, C0) | __vabsdiffu4(w[(k + 5) % 7].M2, C0);
+                        const uint32_t t0 = p08 & HM, t1 = p4c & HM, t2 = p2a & HM, t3 = p6e & HM;
+                        uint32_t acc = t0 | (t0 + KK);
+                        acc &= t1 | (t1 + KK);
+                        acc &= t2 | (t2 + KK);
+                        acc &= t3 | (t3 + KK);
+                        fl |= (acc >> k) & (0x80808080u >> k);
                     }
+                    const int nv = min(7, r_end - r0);                         // rows of this group inside the band
+                    flags[gi] = fl & vm & (((0xFF00u >> nv) & 0xFFu) * 0x01010101u);
                 }
-                if (!col_ok) mask = 0ull;
-                // block-wide compaction of the masks into the queue
-                const int cnt = __popcll(mask);
-                int incl = cnt;
+            }
+        }
+        // block-wide compaction of the flags into the queue
+        const int cnt = __popc(flags[0]) + __popc(flags[1]) + __popc(flags[2]);
+        int incl = cnt;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-                if (lane == 31) s_wsum[threadIdx.x >> 5] = incl;
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    int run = s_qn;
-                    for (int wv = 0; wv < FS_THREADS / 32; wv++) { const int t = s_wsum[wv]; s_wsum[wv] = run; run += t; }
-                    s_qn = run;
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        if (lane == 31) s_wsum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int run = 0;
+            for (int wv = 0; wv < FS_THREADS / 32; wv++) { const int t = s_wsum[wv]; s_wsum[wv] = run; run += t; }
+            s_qn = run;
+        }
+        __syncthreads();
+        int slot = s_wsum[threadIdx.x >> 5] + incl - cnt;
+#pragma unroll
+        for (int gi = 0; gi < FS_MAX_GROUPS7; gi++) {
+            uint32_t m = flags[gi];
+            while (m) {
+                const int bit = __ffs((int)m) - 1;
+                m &= m - 1;
+                const int r = r_begin + 7 * gi + 7 - (bit & 7), tcol = 4 * wi + (bit >> 3);   // tile byte column
+                if (slot < FS_QCAP) s_q[slot] = (uint16_t)((r + 3) * FS_TP + tcol);
+                else {                                                // queue full: score inline, NMS will scan the map
+                    const int s = fast_score_packed(s_img + (r + 3) * FS_TP + tcol);
+                    s_sc[(r + 1) * FS_SP + (tcol - ax - 3 + 1)] = (uint8_t)(s > th ? s - 1 : 0);
+                    s_ovf = 1;
                 }
-                __syncthreads();
-                int slot = s_wsum[threadIdx.x >> 5] + incl - cnt;
-                while (mask) {
-                    const int r = rc + __ffsll((long long)mask) - 1;
-                    mask &= mask - 1;
-                    if (slot < FS_QCAP) s_q[slot] = (uint16_t)((r + 3) * FS_TP + c + 3);
-                    else {                                                // queue full: score inline, NMS will scan the map
-                        const int s = fast_score_packed(colp + (r + 3) * FS_TP);
-                        s_sc[(r + 1) * FS_SP + (c + 1)] = (uint8_t)(s > th ? s - 1 : 0);
-                        s_ovf = 1;
-                    }
-                    slot++;
-                }
-                __syncthreads();
+                slot++;
             }
         }
         __syncthreads();
         const int qn = min(s_qn, FS_QCAP);
-        // ---- dense scoring of the queued survivors ----
+        // ---- exact scoring of the queued survivors ----
         for (int i = threadIdx.x; i < qn; i += FS_THREADS) {
             const int off = s_q[i];
-            const int s = fast_score_packed(tile + off);
-            const int tr = off / FS_TP, tc = off - tr * FS_TP;         // tile coords = detection coords + 3
+            const int s = fast_score_packed(s_img + off);
+            const int tr = off / FS_TP, tc = off - tr * FS_TP - ax;    // ROI coords = detection coords + 3
             s_sc[(tr - 2) * FS_SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
         }
         __syncthreads();
@@ -207,7 +254,7 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(FastParams P, const F
         for (int i = threadIdx.x; i < nitems; i += FS_THREADS) {
             int r, c;
             if (scan_all) { r = i / dw; c = i - r * dw; }
-            else { const int off = s_q[i]; const int tr = off / FS_TP; r = tr - 3; c = off - tr * FS_TP - 3; }
+            else { const int off = s_q[i]; const int tr = off / FS_TP; r = tr - 3; c = off - tr * FS_TP - ax - 3; }
             const uint8_t *q = &s_sc[(r + 1) * FS_SP + (c + 1)];
             const int s = q[0];
             if (s == 0) continue;
@@ -258,7 +305,7 @@ void launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step,
     P.ini_th = h->prm.ini_th_fast; P.min_th = h->prm.min_th_fast;
     P.status = h->d_status;
     P.tile_rows = h->geo.max_hcell + 6;
-    const size_t smem = (size_t)(P.tile_rows + 7) * FS_TP + (size_t)(P.tile_rows - 4) * FS_SP;
+    const size_t smem = FS_PAD + (size_t)(P.tile_rows + FS_PADROWS) * FS_TP + (size_t)(P.tile_rows - 4) * FS_SP;
     static size_t configured = 0;
     if (smem > configured) {
         cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

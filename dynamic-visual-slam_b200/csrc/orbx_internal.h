@@ -14,7 +14,7 @@
 #define ORBX_PATCH 31
 #define ORBX_BLUR_TW 128             // blur tile: 128 px x (4 warps x ORBX_BLUR_H rows) per CTA (k_blur.cu)
 #define ORBX_BLUR_H 35
-#define ORBX_FAST_MAX_W 256          // max detection width (px) of one FAST strip (k_fast.cu)
+#define ORBX_FAST_MAX_W 248          // max detection width (px) of one FAST strip: <= 64 aligned 4-pixel words (k_fast.cu)
 
 // candidate / selected-keypoint packing: x:12 | y:12 | score:8, coordinates relative to the border box
 __host__ __device__ inline uint32_t orbx_pack(int x, int y, int s) { return (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24); }
