@@ -6,22 +6,25 @@
 //   corner iff S > th; score = S - 1; strict 3x3 NMS INSIDE the cell's ROI (scores outside the
 //   cell's detection area read as 0).
 //
-// Design.  One CTA owns a horizontal run of cells of one cell row (a "strip"); all levels of all
-// frames go in one launch.
+// Design.  One CTA owns a horizontal run of cells of one cell row (a "strip", described by a host-built
+// table); all levels of all frames go in one launch.  Cells are independent in the reference (NMS and the
+// threshold retry are per cell ROI), so after the shared staging each WARP owns whole cells and the only block
+// barriers are the ones around the staging and the block-wide sweep.
 //   1. the strip's ROI is staged in shared memory with aligned 128-bit loads;
-//   2. packed column sweep: a thread owns one aligned 32-bit word of the tile (4 adjacent pixels) and walks
-//      down a band of rows with a 7-row register window (3 LDS.32 + 4 PRMT per row of 4 pixels).  Per row it
+//   2. packed sweep, block-wide: a work item is one aligned 32-bit word of the tile (4 adjacent pixels) x 7
+//      rows, walked with a 7-row register window (3 LDS.32 + 4 PRMT per row of 4 pixels).  Per row it
 //      evaluates a polarity-agnostic pre-test on the four opposite ring pairs (0,8) (4,12) (2,10) (6,14):
 //      |I(ring) - I(p)| for 4 pixels is ONE VABSDIFF4.U8; "some member of the pair differs by more than T"
 //      with T = 2^k - 1 <= th is an OR, a mask and one add per pair (SWAR, no per-byte compares).  Every
 //      9-arc contains a member of each opposite pair, so the test is an exact NECESSARY condition for
-//      S > th; it is loose by design (T <= th, sign ignored) and passes ~5 % of the pixels;
-//   3. survivor flags are kept bit-packed per thread (7 rows x 4 pixels per register), compacted once into a
-//      shared queue and scored exactly: the 16-arc min/max network runs on packed u16x2 lanes
-//      (VIMNMX3.U16x2): low half = ring value, high half = 255 - ring value, so one instruction serves
-//      the darker and the brighter polarity;
-//   4. NMS touches queue entries only; neighbours in another cell of the strip are masked to 0;
-//   5. cells with no survivor at iniThFAST are swept again at minThFAST (the reference's retry).
+//      S > th; it is loose by design (T <= th, sign ignored) and passes ~5 % of the pixels.  The 28 flags of an
+//      item are one word of a shared bitmap;
+//   3. per cell (one warp): the cell's flag words are compacted into the warp's queue (shuffle prefix sums) and
+//      scored exactly: the 16-arc min/max network runs on packed u16x2 lanes (VIMNMX3.U16x2): low half = ring
+//      value, high half = 255 - ring value, so one instruction serves the darker and the brighter polarity;
+//   4. strict 3x3 NMS over the queue entries; neighbours in another cell are never read (they count as 0);
+//   5. a cell with no keypoint at iniThFAST is swept again at minThFAST by its own warp (the reference's retry)
+//      — only that cell, not the strip.
 // Survivors are appended to the (frame, level) candidate list with one global atomic per CTA;
 // list order is arbitrary (the quadtree kernel is order-independent).
 //
@@ -30,24 +33,24 @@
 // 3-input VIMNMX3 was lost); the raw-value formulation below has no negated min/max operands.
 #include "orbx_internal.h"
 
-#define FS_THREADS 256
-#define FS_GROUPS 64             // 4-pixel column groups per row band (FS_THREADS = FS_GROUPS x FS_BANDS)
-#define FS_BANDS 4
+#define FS_THREADS 192
+#define FS_WARPS (FS_THREADS / 32)
 #define FS_TP 288                // tile pitch: >= 15 (alignment) + ORBX_FAST_MAX_W + 6 + 8, multiple of 16
 #define FS_TPW (FS_TP / 4)
 #define FS_PAD 16                // bytes in front of the tile: the word left of tile column 0 is addressable
-#define FS_PADROWS 16            // rows behind the tile: the unrolled sweep may overrun a band by < 16 rows
+#define FS_PADROWS 16            // rows behind the tile: a 7-row item may start on the last detection row
 #define FS_SP 272                // score-map pitch: >= detection width + 2, multiple of 16
-#define FS_QCAP 6144             // survivor queue entries (u16 tile offsets); beyond it survivors are scored inline
+#define FS_WQ 1024               // per-warp survivor queue (u16 tile offsets) >= 32 lanes x 28 flags
 #define FS_OUT_CAP 1024          // staged outputs; beyond it survivors are written straight to the global list
-#define FS_MAX_CELLS 8
-#define FS_MAX_GROUPS7 3         // 7-row flag registers per thread: bands of up to 21 rows (hCell <= 69 => <= 18)
+#define FS_MAXSEG 10             // 7-row segments per strip: hCell <= 69
+#define FS_GROUPS 64             // aligned 4-pixel words per strip row (ORBX_FAST_MAX_W / 4 + alignment)
 
 struct FastParams {
     const uint8_t *l0; size_t l0_step, l0_fstride;
     const uint8_t *pyr; size_t pyr_slab;
     uint32_t *cand; size_t cand_slab;
     int32_t *ncand;
+    const uint32_t *strips;      // level:4 | cells:4 | cell row:12 | first cell column:12
     int ini_th, min_th;
     int32_t *status;
     int tile_rows;               // max (hCell + 6) over the levels
@@ -88,9 +91,8 @@ __device__ __forceinline__ int fast_score_packed(const uint8_t *p)
 
 // one tile row entering the sweep window: the thread's own word C plus the four shifted views of it
 struct FastRow { uint32_t C, P2, M2, P3, M3; };
-__device__ __forceinline__ FastRow fast_row(const uint32_t *colw, int trow)
+__device__ __forceinline__ FastRow fast_row(const uint32_t *q)
 {
-    const uint32_t *q = colw + trow * FS_TPW;
     const uint32_t L = q[-1], C = q[0], R = q[1];
     FastRow w;
     w.C = C;
@@ -101,35 +103,65 @@ __device__ __forceinline__ FastRow fast_row(const uint32_t *colw, int trow)
     return w;
 }
 
+// Pre-test of 7 detection rows x 4 pixels.  q = the item's word in tile row r0 (= ring row dy = -3 of the first
+// detection row).  Result: bit (7-k) of byte j set iff pixel (row r0 + k, byte j) may be a corner at threshold T.
+__device__ __noinline__ uint32_t fast_sweep7(const uint32_t *q, uint32_t HM, uint32_t KK)
+{
+    FastRow w[7];
+#pragma unroll
+    for (int k = 0; k < 6; k++) w[k] = fast_row(q + k * FS_TPW);
+    uint32_t fl = 0u;
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+        w[(k + 6) % 7] = fast_row(q + (k + 6) * FS_TPW);                       // ring row dy = +3 of detection row k
+        const uint32_t C0 = w[(k + 3) % 7].C;
+        const uint32_t p08 = __vabsdiffu4(w[(k + 6) % 7].C, C0) | __vabsdiffu4(w[k % 7].C, C0);
+        const uint32_t p4c = __vabsdiffu4(w[(k + 3) % 7].P3, C0) | __vabsdiffu4(w[(k + 3) % 7].M3, C0);
+        const uint32_t p2a = __vabsdiffu4(w[(k + 5) % 7].P2, C0) | __vabsdiffu4(w[(k + 1) % 7].M2, C0);
+        const uint32_t p6e = __vabsdiffu4(w[(k + 1) % 7].P2, C0) | __vabsdiffu4(w[(k + 5) % 7].M2, C0);
+        const uint32_t t0 = p08 & HM, t1 = p4c & HM, t2 = p2a & HM, t3 = p6e & HM;
+        uint32_t acc = t0 | (t0 + KK);
+        acc &= t1 | (t1 + KK);
+        acc &= t2 | (t2 + KK);
+        acc &= t3 | (t3 + KK);
+        fl |= (acc >> k) & (0x80808080u >> k);
+    }
+    return fl;
+}
+
+// loose pre-test threshold T = 2^sh - 1 <= th:  |d| > T  <=>  (|d| & HM) != 0;  t + KK sets bit 7 of every byte with t >= 2^sh
+__device__ __forceinline__ void fast_masks(int th, uint32_t &HM, uint32_t &KK)
+{
+    const int sh = min(7, 31 - __clz(th + 1));
+    HM = ((0xFFu << sh) & 0xFFu) * 0x01010101u;
+    KK = (0x80u - (1u << sh)) * 0x01010101u;
+}
+
 __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(FastParams P, const FrameGeom *__restrict__ G)
 {
     extern __shared__ __align__(16) uint8_t s_dyn[];
-    __shared__ uint16_t s_q[FS_QCAP];
+    __shared__ uint16_t s_wq[FS_WARPS][FS_WQ];
+    __shared__ uint32_t s_flag[FS_MAXSEG * FS_GROUPS];
     __shared__ uint32_t s_out[FS_OUT_CAP];
-    __shared__ int s_qn, s_nout, s_base, s_redo, s_ovf;
-    __shared__ int s_wsum[FS_THREADS / 32];
-    __shared__ int s_ccnt[FS_MAX_CELLS];
-    __shared__ uint8_t s_col2cell[ORBX_FAST_MAX_W];
+    __shared__ int s_nout, s_base;
     uint8_t *s_img = s_dyn + FS_PAD;                                               // (tile_rows + FS_PADROWS) x FS_TP
     uint8_t *s_sc = s_dyn + FS_PAD + (P.tile_rows + FS_PADROWS) * FS_TP;           // (tile_rows - 4) x FS_SP score map with a zero ring
 
     const int f = blockIdx.y;
-    int level = 0;
+    const uint32_t sd = __ldg(P.strips + blockIdx.x);
+    const int level = (int)(sd & 15u), ci = (int)((sd >> 8) & 0xFFFu), cj0 = (int)(sd >> 20);
+    int ncell = (int)((sd >> 4) & 15u);
     const int nl = G->nlevels;
-    for (int l = 1; l < nl; l++) if ((int)blockIdx.x >= G->lv[l].strip_first) level = l;
     const LevelGeom &g = G->lv[level];
-    const int sidx = blockIdx.x - g.strip_first;
-    const int ci = sidx / g.strips_per_row, sj = sidx - ci * g.strips_per_row;
-    const int cj0 = sj * g.cells_per_strip;
+    const int wcell = g.wcell;
     // strip ROI in image coordinates — ORBextractor.cpp:805-822 (cells cj0 .. cj0+ncell-1 of cell row ci)
     const int maxBX = g.w - ORBX_BORDER, maxBY = g.h - ORBX_BORDER;
-    const int iniX = ORBX_BORDER + cj0 * g.wcell, iniY = ORBX_BORDER + ci * g.hcell;
+    const int iniX = ORBX_BORDER + cj0 * wcell, iniY = ORBX_BORDER + ci * g.hcell;
     if (iniY >= maxBY - 3 || iniX >= maxBX - 6) return;
-    int ncell = min(g.cells_per_strip, g.ncols - cj0);
     // cells whose iniX >= maxBorderX-6 are skipped by the reference (:815-816)
-    while (ncell > 0 && ORBX_BORDER + (cj0 + ncell - 1) * g.wcell >= maxBX - 6) ncell--;
+    while (ncell > 0 && ORBX_BORDER + (cj0 + ncell - 1) * wcell >= maxBX - 6) ncell--;
     if (ncell <= 0) return;
-    const int maxX = min(iniX + ncell * g.wcell + 6, maxBX), maxY = min(iniY + g.hcell + 6, maxBY);
+    const int maxX = min(iniX + ncell * wcell + 6, maxBX), maxY = min(iniY + g.hcell + 6, maxBY);
     const int rw = maxX - iniX, rh = maxY - iniY;
     const int dw = rw - 6, dh = rh - 6;            // detection area of the strip, ROI-relative origin (3,3)
     if (dw <= 0 || dh <= 0) return;
@@ -137,153 +169,141 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(FastParams P, const F
     const uint8_t *src; size_t step;
     if (level == 0) { src = P.l0 + (size_t)f * P.l0_fstride; step = P.l0_step; }
     else { src = P.pyr + (size_t)f * P.pyr_slab + g.off; step = (size_t)g.pitch; }
-    // stage the ROI with aligned 128-bit loads; tile column `ax` is image column iniX
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // stage the ROI with aligned 128-bit loads (lane = 16-byte column, warp = row); tile column `ax` is image column iniX
     const int ax = iniX & 15;
-    const int vecs = (ax + rw + 15) >> 4;
-    src += (size_t)iniY * step + (iniX - ax);
-    for (int i = threadIdx.x; i < rh * 32; i += FS_THREADS) {
-        const int r = i >> 5, vi = i & 31;
-        if (vi < vecs) reinterpret_cast<uint4 *>(s_img + r * FS_TP)[vi] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * step) + vi);
+    const int vecs = (ax + rw + 15) >> 4;          // <= 18
+    if (lane < vecs) {
+        const uint8_t *gp = src + (size_t)(iniY + warp) * step + (iniX - ax) + lane * 16;
+        uint8_t *sp = s_img + warp * FS_TP + lane * 16;
+        for (int r = warp; r < rh; r += FS_WARPS, gp += (size_t)FS_WARPS * step, sp += FS_WARPS * FS_TP)
+            *reinterpret_cast<uint4 *>(sp) = __ldg(reinterpret_cast<const uint4 *>(gp));
     }
-    for (int c = threadIdx.x; c < dw; c += FS_THREADS) s_col2cell[c] = (uint8_t)min(c / g.wcell, ncell - 1);
-    if (threadIdx.x < FS_MAX_CELLS) s_ccnt[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { s_nout = 0; s_redo = 0; }
-    const int lane = threadIdx.x & 31;
+    // zero the score map (1-px ring included)
+    for (int i = threadIdx.x; i < ((dh + 2) * FS_SP) / 16; i += FS_THREADS) reinterpret_cast<uint4 *>(s_sc)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) s_nout = 0;
+    __syncthreads();
+
+    // ---- block-wide packed sweep at iniThFAST: one flag word per (7-row segment, tile word) ----
+    const int w0 = (ax + 3) >> 2;                                  // tile word holding detection column 0
+    const int nGs = ((ax + 3 + dw - 1) >> 2) - w0 + 1;             // words holding detection columns (<= FS_GROUPS)
+    const int nseg = (dh + 6) / 7;
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(s_img);
+    uint32_t HM, KK;
+    fast_masks(P.ini_th, HM, KK);
+    {
+        const float inv = 1.0f / (float)nGs;
+        for (int it = threadIdx.x; it < nGs * nseg; it += FS_THREADS) {
+            const int seg = __float2int_rd(((float)it + 0.5f) * inv), gidx = it - seg * nGs;
+            s_flag[seg * FS_GROUPS + gidx] = fast_sweep7(words + (7 * seg) * FS_TPW + w0 + gidx, HM, KK);
+        }
+    }
+    __syncthreads();
+
     uint32_t *gdst = P.cand + (size_t)f * P.cand_slab + g.cand_off;
     int32_t *gcnt = &P.ncand[f * nl + level];
+    uint16_t *wq = s_wq[warp];
 
-    // sweep geometry: thread = tile word wi (4 pixels) x row band
-    const int grp = threadIdx.x & (FS_GROUPS - 1), band = threadIdx.x / FS_GROUPS;
-    const int wi = ((ax + 3) >> 2) + grp;                         // first word holding a detection column + group
-    const int cbase = 4 * wi - (ax + 3);                          // detection column of byte 0 of the word (-3 .. )
-    const uint32_t *colw = reinterpret_cast<const uint32_t *>(s_img) + wi;
-    const int RB = (dh + FS_BANDS - 1) / FS_BANDS;                // rows per band (<= 18 for hCell <= 69)
-    const int r_begin = band * RB, r_end = min(dh, r_begin + RB);
-
-    for (int pass = 0; pass < 2; pass++) {
-        const int th = pass == 0 ? P.ini_th : P.min_th;
-        // loose pre-test threshold T = 2^sh - 1 <= th: |d| > T  <=>  (|d| & HM) != 0
-        const int sh = min(7, 31 - __clz(th + 1));
-        const uint32_t HM = ((0xFFu << sh) & 0xFFu) * 0x01010101u;
-        const uint32_t KK = (0x80u - (1u << sh)) * 0x01010101u;   // t + KK sets bit 7 of every byte with t >= 2^sh
-        // zero the score map (1-px ring included) and the queue
-        for (int i = threadIdx.x; i < ((dh + 2) * FS_SP) / 16; i += FS_THREADS) reinterpret_cast<uint4 *>(s_sc)[i] = make_uint4(0, 0, 0, 0);
-        if (threadIdx.x == 0) { s_qn = 0; s_ovf = 0; }
-        __syncthreads();
-        // columns this thread may report: inside the detection area and (retry pass) in a cell that is still empty
-        uint32_t vm = 0;
+    // ---- one warp per cell: compaction, exact score, NMS, retry ----
+    for (int cell = warp; cell < ncell; cell += FS_WARPS) {
+        const int c_lo = cell * wcell, c_hi = min(c_lo + wcell, dw);          // detection columns of the cell
+        const int ga = ((ax + 3 + c_lo) >> 2) - w0, nG = ((ax + 3 + c_hi - 1) >> 2) - w0 - ga + 1;
+        const int items = nG * nseg;
+        const float inv = 1.0f / (float)nG;
+        for (int pass = 0; pass < 2; pass++) {
+            const int th = pass == 0 ? P.ini_th : P.min_th;
+            int qn = 0;
+            bool ovf = false;
+            for (int it0 = 0; it0 < items; it0 += 32) {
+                const int it = it0 + lane;
+                uint32_t word = 0u;
+                int base_off = 0;
+                if (it < items) {
+                    const int seg = __float2int_rd(((float)it + 0.5f) * inv), gidx = ga + it - seg * nG;
+                    const uint32_t raw = pass == 0 ? s_flag[seg * FS_GROUPS + gidx]
+                                                   : fast_sweep7(words + (7 * seg) * FS_TPW + w0 + gidx, HM, KK);
+                    // columns of this word inside the cell, rows of this segment inside the strip
+                    const int cb = 4 * (w0 + gidx) - (ax + 3);                // detection column of byte 0
+                    uint32_t cm = 0u;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int c = cbase + j;
-            if (c >= 0 && c < dw && (pass == 0 || s_ccnt[s_col2cell[c]] == 0)) vm |= 0xFEu << (8 * j);
-        }
-        // ---- packed sweep: flags[gi] bit (7-k) of byte j = pixel (row r_begin + 7*gi + k, column cbase + j) survives ----
-        uint32_t flags[FS_MAX_GROUPS7] = { 0u, 0u, 0u };
-        if (vm != 0u && r_begin < r_end) {
-            FastRow w[7];
+                    for (int j = 0; j < 4; j++) if (cb + j >= c_lo && cb + j < c_hi) cm |= 0xFEu << (8 * j);
+                    const int nv = min(7, dh - 7 * seg);
+                    word = raw & cm & (((0xFF00u >> nv) & 0xFFu) * 0x01010101u);
+                    base_off = (7 * seg + 3) * FS_TP + 4 * (w0 + gidx);
+                }
+                const int cnt = __popc(word);
+                int incl = cnt;
 #pragma unroll
-            for (int k = 0; k < 6; k++) w[k] = fast_row(colw, r_begin + k);
-#pragma unroll
-            for (int gi = 0; gi < FS_MAX_GROUPS7; gi++) {
-                const int r0 = r_begin + 7 * gi;
-                if (r0 < r_end) {
-                    uint32_t fl = 0u;
-#pragma unroll
-                    for (int k = 0; k < 7; k++) {
-                        w[(k + 6) % 7] = fast_row(colw, r0 + k + 6);           // ring row dy = +3 of detection row r0 + k
-                        const uint32_t C0 = w[(k + 3) % 7].C;
-                        const uint32_t p08 = __vabsdiffu4(w[(k + 6) % 7].C, C0) | __vabsdiffu4(w[k % 7].C, C0);
-                        const uint32_t p4c = __vabsdiffu4(w[(k + 3) % 7].P3, C0) | __vabsdiffu4(w[(k + 3) % 7].M3, C0);
-                        const uint32_t p2a = __vabsdiffu4(w[(k + 5) % 7].P2, C0) | __vabsdiffu4(w[(k + 1) % 7].M2, C0);
-                        const uint32_t p6e = __vabsdiffu4(w[(k + 1) % 7].P2, C0) | __vabsdiffu4(w[(k + 5) % 7].M2, C0);
-                        const uint32_t t0 = p08 & HM, t1 = p4c & HM, t2 = p2a & HM, t3 = p6e & HM;
-                        uint32_t acc = t0 | (t0 + KK);
-                        acc &= t1 | (t1 + KK);
-                        acc &= t2 | (t2 + KK);
-                        acc &= t3 | (t3 + KK);
-                        fl |= (acc >> k) & (0x80808080u >> k);
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                if (qn + total > FS_WQ) {                                     // queue full: score what is queued, NMS will scan the cell
+                    __syncwarp();
+                    for (int i = lane; i < qn; i += 32) {
+                        const int off = wq[i];
+                        const int s = fast_score_packed(s_img + off);
+                        const int tr = off / FS_TP, tc = off - tr * FS_TP - ax;
+                        s_sc[(tr - 2) * FS_SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
                     }
-                    const int nv = min(7, r_end - r0);                         // rows of this group inside the band
-                    flags[gi] = fl & vm & (((0xFF00u >> nv) & 0xFFu) * 0x01010101u);
+                    __syncwarp();
+                    qn = 0; ovf = true;
+                }
+                int slot = qn + incl - cnt;
+                while (word) {
+                    const int bit = __ffs((int)word) - 1;
+                    word &= word - 1;
+                    wq[slot++] = (uint16_t)(base_off + (7 - (bit & 7)) * FS_TP + (bit >> 3));
+                }
+                qn += total;
+            }
+            __syncwarp();
+            // exact scoring of the queued survivors (ROI coords = detection coords + 3)
+            for (int i = lane; i < qn; i += 32) {
+                const int off = wq[i];
+                const int s = fast_score_packed(s_img + off);
+                const int tr = off / FS_TP, tc = off - tr * FS_TP - ax;
+                s_sc[(tr - 2) * FS_SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
+            }
+            __syncwarp();
+            // strict 3x3 NMS inside the cell: queue entries, or every pixel of the cell if the queue overflowed
+            const int cw = c_hi - c_lo;
+            const int nitems = ovf ? cw * dh : qn;
+            const float invw = 1.0f / (float)cw;
+            int found = 0;
+            for (int i0 = 0; i0 < nitems; i0 += 32) {
+                const int i = i0 + lane;
+                bool ok = false;
+                int r = 0, c = 0, s = 0;
+                if (i < nitems) {
+                    if (ovf) { r = __float2int_rd(((float)i + 0.5f) * invw); c = c_lo + i - r * cw; }
+                    else { const int off = wq[i]; const int tr = off / FS_TP; r = tr - 3; c = off - tr * FS_TP - ax - 3; }
+                    const uint8_t *q = &s_sc[(r + 1) * FS_SP + (c + 1)];
+                    s = q[0];
+                    if (s != 0) {
+                        ok = s > q[-FS_SP] && s > q[FS_SP];
+                        if (c > c_lo) ok = ok && s > q[-1] && s > q[-FS_SP - 1] && s > q[FS_SP - 1];
+                        if (c < c_hi - 1) ok = ok && s > q[1] && s > q[-FS_SP + 1] && s > q[FS_SP + 1];
+                    }
+                }
+                found += __popc(__ballot_sync(0xffffffffu, ok));
+                if (ok) {
+                    // box-relative coordinates: kp.pt + (j*wCell, i*hCell) — ORBextractor.cpp:865-866
+                    const uint32_t val = orbx_pack(cj0 * wcell + c + 3, ci * g.hcell + r + 3, s);
+                    const int o = atomicAdd(&s_nout, 1);
+                    if (o < FS_OUT_CAP) s_out[o] = val;
+                    else {                                                    // staging full: straight to the global list
+                        const int go = atomicAdd(gcnt, 1);
+                        if (go < g.cand_cap) gdst[go] = val; else atomicOr(P.status, ORBX_DS_CAND_OVERFLOW);
+                    }
                 }
             }
+            // the reference retries a cell at minThFAST only if iniThFAST produced nothing (:843-846)
+            if (found > 0 || pass == 1) break;
+            fast_masks(P.min_th, HM, KK);
+            __syncwarp();
         }
-        // block-wide compaction of the flags into the queue
-        const int cnt = __popc(flags[0]) + __popc(flags[1]) + __popc(flags[2]);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-        if (lane == 31) s_wsum[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int run = 0;
-            for (int wv = 0; wv < FS_THREADS / 32; wv++) { const int t = s_wsum[wv]; s_wsum[wv] = run; run += t; }
-            s_qn = run;
-        }
-        __syncthreads();
-        int slot = s_wsum[threadIdx.x >> 5] + incl - cnt;
-#pragma unroll
-        for (int gi = 0; gi < FS_MAX_GROUPS7; gi++) {
-            uint32_t m = flags[gi];
-            while (m) {
-                const int bit = __ffs((int)m) - 1;
-                m &= m - 1;
-                const int r = r_begin + 7 * gi + 7 - (bit & 7), tcol = 4 * wi + (bit >> 3);   // tile byte column
-                if (slot < FS_QCAP) s_q[slot] = (uint16_t)((r + 3) * FS_TP + tcol);
-                else {                                                // queue full: score inline, NMS will scan the map
-                    const int s = fast_score_packed(s_img + (r + 3) * FS_TP + tcol);
-                    s_sc[(r + 1) * FS_SP + (tcol - ax - 3 + 1)] = (uint8_t)(s > th ? s - 1 : 0);
-                    s_ovf = 1;
-                }
-                slot++;
-            }
-        }
-        __syncthreads();
-        const int qn = min(s_qn, FS_QCAP);
-        // ---- exact scoring of the queued survivors ----
-        for (int i = threadIdx.x; i < qn; i += FS_THREADS) {
-            const int off = s_q[i];
-            const int s = fast_score_packed(s_img + off);
-            const int tr = off / FS_TP, tc = off - tr * FS_TP - ax;    // ROI coords = detection coords + 3
-            s_sc[(tr - 2) * FS_SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
-        }
-        __syncthreads();
-        // ---- strict 3x3 NMS inside each cell: queue entries, or the whole map if the queue overflowed ----
-        const bool scan_all = s_ovf != 0;
-        const int nitems = scan_all ? dw * dh : qn;
-        for (int i = threadIdx.x; i < nitems; i += FS_THREADS) {
-            int r, c;
-            if (scan_all) { r = i / dw; c = i - r * dw; }
-            else { const int off = s_q[i]; const int tr = off / FS_TP; r = tr - 3; c = off - tr * FS_TP - ax - 3; }
-            const uint8_t *q = &s_sc[(r + 1) * FS_SP + (c + 1)];
-            const int s = q[0];
-            if (s == 0) continue;
-            const int cell = s_col2cell[c];
-            const int cl = c - cell * g.wcell;                          // column inside the cell's detection area
-            const bool hasL = cl > 0, hasR = (cl < g.wcell - 1) && (c < dw - 1);
-            bool ok = s > q[-FS_SP] && s > q[FS_SP];
-            if (hasL) ok = ok && s > q[-1] && s > q[-FS_SP - 1] && s > q[FS_SP - 1];
-            if (hasR) ok = ok && s > q[1] && s > q[-FS_SP + 1] && s > q[FS_SP + 1];
-            if (ok) {
-                atomicAdd(&s_ccnt[cell], 1);
-                // box-relative coordinates: kp.pt + (j*wCell, i*hCell) — ORBextractor.cpp:865-866
-                const uint32_t val = orbx_pack(cj0 * g.wcell + c + 3, ci * g.hcell + r + 3, s);
-                const int o = atomicAdd(&s_nout, 1);
-                if (o < FS_OUT_CAP) s_out[o] = val;
-                else {                                                    // staging full: straight to the global list
-                    const int go = atomicAdd(gcnt, 1);
-                    if (go < g.cand_cap) gdst[go] = val; else atomicOr(P.status, ORBX_DS_CAND_OVERFLOW);
-                }
-            }
-        }
-        __syncthreads();
-        // fallback pass only for cells that produced nothing (uniform decision)
-        if (pass == 0) {
-            if (threadIdx.x < ncell && s_ccnt[threadIdx.x] == 0) s_redo = 1;
-            __syncthreads();
-            if (!s_redo) break;
-        }
+        fast_masks(P.ini_th, HM, KK);
     }
+    __syncthreads();
     const int n = min(s_nout, FS_OUT_CAP);
     if (n == 0) return;
     if (threadIdx.x == 0) s_base = atomicAdd(gcnt, n);
@@ -302,6 +322,7 @@ void launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step,
     P.pyr = h->d_pyr; P.pyr_slab = h->pyr_slab;
     P.cand = h->d_cand; P.cand_slab = h->geo.cand_entries;
     P.ncand = h->d_ncand;
+    P.strips = h->d_strips;
     P.ini_th = h->prm.ini_th_fast; P.min_th = h->prm.min_th_fast;
     P.status = h->d_status;
     P.tile_rows = h->geo.max_hcell + 6;

@@ -73,7 +73,8 @@ static void resize_table(int ssize, int dsize, bool horizontal, ResizeTab *out)
 }
 
 // geometry for one input size; returns false when the reference itself is undefined for it
-static bool build_geometry(const orbx_handle *h, int w, int hgt, FrameGeom &G, std::vector<ResizeTab> *xt, std::vector<ResizeTab> *yt)
+static bool build_geometry(const orbx_handle *h, int w, int hgt, FrameGeom &G, std::vector<ResizeTab> *xt, std::vector<ResizeTab> *yt,
+                           std::vector<uint32_t> *strip_tab = nullptr)
 {
     memset(&G, 0, sizeof(G));
     const orbx_params &p = h->prm;
@@ -108,6 +109,11 @@ static bool build_geometry(const orbx_handle *h, int w, int hgt, FrameGeom &G, s
             max_hcell = std::max(max_hcell, g.hcell);
         } else { g.strips_per_row = 0; g.cells_per_strip = 1; }
         g.strip_first = strips; strips += g.strips_per_row * g.nrows;
+        // strip descriptors for k_fast_cells: level:4 | cells:4 | cell row:12 | first cell column:12
+        if (strip_tab) for (int ci = 0; ci < g.nrows; ci++) for (int sj = 0; sj < g.strips_per_row; sj++) {
+            const int cj0 = sj * g.cells_per_strip, nc = std::min(g.cells_per_strip, g.ncols - cj0);
+            strip_tab->push_back((uint32_t)l | ((uint32_t)std::max(nc, 0) << 4) | ((uint32_t)ci << 8) | ((uint32_t)cj0 << 20));
+        }
         g.blur_tx = (g.w + ORBX_BLUR_TW - 1) / ORBX_BLUR_TW; g.blur_ty = (g.h + 4 * ORBX_BLUR_H - 1) / (4 * ORBX_BLUR_H);
         g.blur_first = tiles; tiles += g.blur_tx * g.blur_ty;
         g.cand_cap = (int)align_up((size_t)std::max(4096, g.w * g.h / cdiv), 64);
@@ -150,16 +156,17 @@ static orbx_status set_geometry(orbx_handle *h, int w, int hgt)
     if (h->geo.width == w && h->geo.height == hgt) return ORBX_OK;
     if (w > h->prm.max_width || hgt > h->prm.max_height) { h->err = "frame larger than max_width x max_height"; return ORBX_E_INVALID; }
     if (w > 4096 + 2 * ORBX_BORDER || hgt > 4096 + 2 * ORBX_BORDER) { h->err = "frame larger than 4128 px"; return ORBX_E_UNSUPPORTED; }
-    FrameGeom G; std::vector<ResizeTab> xt, yt;
-    if (!build_geometry(h, w, hgt, G, &xt, &yt)) { h->err = "unsupported frame geometry (aspect ratio gives 0 or > 64 quadtree roots, or a level vanishes)"; return ORBX_E_UNSUPPORTED; }
+    FrameGeom G; std::vector<ResizeTab> xt, yt; std::vector<uint32_t> strips;
+    if (!build_geometry(h, w, hgt, G, &xt, &yt, &strips)) { h->err = "unsupported frame geometry (aspect ratio gives 0 or > 64 quadtree roots, or a level vanishes)"; return ORBX_E_UNSUPPORTED; }
     const size_t B = (size_t)h->prm.max_batch;
     if (G.pyr_bytes * B > h->pyr_cap || G.blur_bytes * B > h->blur_cap || G.cand_entries * B > h->cand_cap ||
         (size_t)G.sel_entries * B > h->sel_cap || (int)xt.size() > h->tab_cap || (int)yt.size() > h->tab_cap ||
-        G.sel_entries > h->max_kp) { h->err = "frame geometry does not fit the arenas sized at create"; return ORBX_E_INVALID; }
+        G.sel_entries > h->max_kp || (int)strips.size() > h->strip_cap) { h->err = "frame geometry does not fit the arenas sized at create"; return ORBX_E_INVALID; }
     ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
     ORBX_CUDA(h, cudaMemcpy(h->d_geo, &G, sizeof(G), cudaMemcpyHostToDevice));
     if (!xt.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_xtab, xt.data(), xt.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
     if (!yt.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_ytab, yt.data(), yt.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
+    if (!strips.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_strips, strips.data(), strips.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     h->geo = G; h->pyr_slab = G.pyr_bytes; h->blur_slab = G.blur_bytes;
     return ORBX_OK;
 }
@@ -170,7 +177,7 @@ extern "C" void orbx_destroy(orbx_handle *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
-    void *dev[] = { h->d_prev_desc, h->d_prev_count, h->d_geo, h->d_xtab, h->d_ytab, h->d_pyr, h->d_blur, h->d_in, h->d_depth_in, h->d_cand, h->d_cand2, h->d_qtmp,
+    void *dev[] = { h->d_strips, h->d_prev_desc, h->d_prev_count, h->d_geo, h->d_xtab, h->d_ytab, h->d_pyr, h->d_blur, h->d_in, h->d_depth_in, h->d_cand, h->d_cand2, h->d_qtmp,
                     h->d_owner, h->d_owner2, h->d_ncand, h->d_sel, h->d_nsel, h->d_kps_all, h->d_desc_all, h->d_count_all,
                     h->d_kps_out, h->d_desc_out, h->d_count_out, h->d_boxes, h->d_status, h->d_mpart, h->d_mq, h->d_mt, h->d_mout, h->d_mcount };
     for (void *p : dev) if (p) cudaFree(p);
@@ -226,6 +233,8 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     h->in_cap = align_up((size_t)p.max_width, 128) * p.max_height * B;
     h->depth_cap = align_up((size_t)p.max_width * 2, 128) * p.max_height * B;
     CREATE_CUDA(cudaMalloc(&h->d_geo, sizeof(FrameGeom)));
+    h->strip_cap = G.total_cells + 64 * p.nlevels;
+    CREATE_CUDA(cudaMalloc(&h->d_strips, sizeof(uint32_t) * h->strip_cap));
     CREATE_CUDA(cudaMalloc(&h->d_xtab, sizeof(ResizeTab) * h->tab_cap));
     CREATE_CUDA(cudaMalloc(&h->d_ytab, sizeof(ResizeTab) * h->tab_cap));
     CREATE_CUDA(cudaMalloc(&h->d_pyr, h->pyr_cap));

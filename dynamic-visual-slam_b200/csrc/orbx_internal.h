@@ -81,6 +81,7 @@ struct orbx_handle {
     FrameGeom geo;
     FrameGeom *d_geo;
     ResizeTab *d_xtab, *d_ytab; int tab_cap;
+    uint32_t *d_strips; int strip_cap;   // FAST strip descriptors (k_fast.cu)
     // arenas, sized for max_width x max_height x max_batch
     uint8_t *d_pyr, *d_blur;     size_t pyr_slab, blur_slab;          // current per-frame strides
     size_t pyr_cap, blur_cap;                                          // arena bytes
