@@ -6,51 +6,54 @@
 //   corner iff S > th; score = S - 1; strict 3x3 NMS INSIDE the cell's ROI (scores outside the
 //   cell's detection area read as 0).
 //
-// Design.  One CTA owns a horizontal run of cells of one cell row (a "strip", described by a host-built
-// table); all levels of all frames go in one launch.  Cells are independent in the reference (NMS and the
-// threshold retry are per cell ROI), so after the shared staging each WARP owns whole cells and the only block
-// barriers are the ones around the staging and the block-wide sweep.
-//   1. the strip's ROI is staged in shared memory with aligned 128-bit loads;
-//   2. packed sweep, block-wide: a work item is one aligned 32-bit word of the tile (4 adjacent pixels) x 7
+// Design.  A work item is a horizontal run of cells of one cell row of one level of one frame (a "strip",
+// described by a host-built table).  The kernel is PERSISTENT: one CTA per resident slot loops over the items of
+// the whole batch, and the strip's ROI arrives in shared memory by TMA (cp.async.bulk.tensor, one descriptor per
+// pyramid level, frames as the third tensor dimension) into a double buffer: the tile of item i+1 is in flight
+// while item i is processed, so no thread ever issues a staging load or waits for one.
+//   1. packed sweep, block-wide: a sweep unit is one aligned 32-bit word of the tile (4 adjacent pixels) x 7
 //      rows, walked with a 7-row register window (3 LDS.32 + 4 PRMT per row of 4 pixels).  Per row it
 //      evaluates a polarity-agnostic pre-test on the four opposite ring pairs (0,8) (4,12) (2,10) (6,14):
 //      |I(ring) - I(p)| for 4 pixels is ONE VABSDIFF4.U8; "some member of the pair differs by more than T"
 //      with T = 2^k - 1 <= th is an OR, a mask and one add per pair (SWAR, no per-byte compares).  Every
 //      9-arc contains a member of each opposite pair, so the test is an exact NECESSARY condition for
-//      S > th; it is loose by design (T <= th, sign ignored) and passes ~5 % of the pixels.  The 28 flags of an
-//      item are one word of a shared bitmap;
-//   3. per cell (one warp): the cell's flag words are compacted into the warp's queue (shuffle prefix sums) and
-//      scored exactly: the 16-arc min/max network runs on packed u16x2 lanes (VIMNMX3.U16x2): low half = ring
-//      value, high half = 255 - ring value, so one instruction serves the darker and the brighter polarity;
-//   4. strict 3x3 NMS over the queue entries; neighbours in another cell are never read (they count as 0);
-//   5. a cell with no keypoint at iniThFAST is swept again at minThFAST by its own warp (the reference's retry)
-//      — only that cell, not the strip.
-// Survivors are appended to the (frame, level) candidate list with one global atomic per CTA;
+//      S > th; it is loose by design (T <= th, sign ignored) and passes ~5 % of the pixels.  Survivors go
+//      straight into one shared queue (warp-aggregated slot allocation);
+//   2. exact score of the queued survivors, dense over the block: the 16-arc min/max network runs on packed
+//      u16x2 lanes (VIMNMX3.U16x2): low half = ring value, high half = 255 - ring value, so one instruction
+//      serves the darker and the brighter polarity;
+//   3. strict 3x3 NMS over the queue entries; neighbours in another cell are never read (the reference runs
+//      FAST per cell ROI, so they count as 0);
+//   4. a cell with no keypoint at iniThFAST is swept again at minThFAST (the reference's retry) by ONE warp —
+//      only that cell, not the strip.
+// Survivors are appended to the (frame, level) candidate list with one global atomic per item;
 // list order is arbitrary (the quadtree kernel is order-independent).
 //
 // Toolchain note: an earlier formulation on signed differences (d = I(p) - I(ring), score via
 // max(mn9, -mx9)) produced wrong results on sm_100a with nvcc 12.9 (the negation feeding a fused
 // 3-input VIMNMX3 was lost); the raw-value formulation below has no negated min/max operands.
 #include "orbx_internal.h"
+#include <algorithm>
+#include <cstring>
 
 #define FS_THREADS 192
 #define FS_WARPS (FS_THREADS / 32)
-#define FS_TP 288                // tile pitch: >= 15 (alignment) + ORBX_FAST_MAX_W + 6 + 8, multiple of 16
+#define FS_TP 288                // tile pitch = TMA box width: 72 u32 elements >= 16 + 15 + ORBX_FAST_MAX_W + 6 + 4
 #define FS_TPW (FS_TP / 4)
-#define FS_PAD 16                // bytes in front of the tile: the word left of tile column 0 is addressable
-#define FS_PADROWS 16            // rows behind the tile: a 7-row item may start on the last detection row
+#define FS_PADROWS 6             // rows behind the tile: a 7-row sweep unit may start on the last detection row
 #define FS_SP 272                // score-map pitch: >= detection width + 2, multiple of 16
-#define FS_WQ 1024               // per-warp survivor queue (u16 tile offsets) >= 32 lanes x 28 flags
+#define FS_QCAP 6144             // survivor queue (u16 tile offsets); FS_WARPS x FS_WQ in the retry phase
+#define FS_WQ (FS_QCAP / FS_WARPS)   // per-warp queue of the retry phase, >= 32 lanes x 28 flags
 #define FS_OUT_CAP 1024          // staged outputs; beyond it survivors are written straight to the global list
-#define FS_MAXSEG 10             // 7-row segments per strip: hCell <= 69
-#define FS_GROUPS 64             // aligned 4-pixel words per strip row (ORBX_FAST_MAX_W / 4 + alignment)
+#define FS_MAX_CELLS 8
+
+struct FastMaps { CUtensorMap m[ORBX_MAX_LEVELS]; };
 
 struct FastParams {
-    const uint8_t *l0; size_t l0_step, l0_fstride;
-    const uint8_t *pyr; size_t pyr_slab;
     uint32_t *cand; size_t cand_slab;
     int32_t *ncand;
     const uint32_t *strips;      // level:4 | cells:4 | cell row:12 | first cell column:12
+    int nstrips, nitems;         // items = nstrips x frames
     int ini_th, min_th;
     int32_t *status;
     int tile_rows;               // max (hCell + 6) over the levels
@@ -137,96 +140,117 @@ __device__ __forceinline__ void fast_masks(int th, uint32_t &HM, uint32_t &KK)
     KK = (0x80u - (1u << sh)) * 0x01010101u;
 }
 
-__global__ void __launch_bounds__(FS_THREADS) k_fast_cells(FastParams P, const FrameGeom *__restrict__ G)
+// ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG, SYNCS) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
 {
-    extern __shared__ __align__(16) uint8_t s_dyn[];
-    __shared__ uint16_t s_wq[FS_WARPS][FS_WQ];
-    __shared__ uint32_t s_flag[FS_MAXSEG * FS_GROUPS];
-    __shared__ uint32_t s_out[FS_OUT_CAP];
-    __shared__ int s_nout, s_base;
-    uint8_t *s_img = s_dyn + FS_PAD;                                               // (tile_rows + FS_PADROWS) x FS_TP
-    uint8_t *s_sc = s_dyn + FS_PAD + (P.tile_rows + FS_PADROWS) * FS_TP;           // (tile_rows - 4) x FS_SP score map with a zero ring
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
 
-    const int f = blockIdx.y;
-    const uint32_t sd = __ldg(P.strips + blockIdx.x);
-    const int level = (int)(sd & 15u), ci = (int)((sd >> 8) & 0xFFFu), cj0 = (int)(sd >> 20);
-    int ncell = (int)((sd >> 4) & 15u);
-    const int nl = G->nlevels;
-    const LevelGeom &g = G->lv[level];
-    const int wcell = g.wcell;
+// geometry of one work item, derived from its strip descriptor
+struct FastItem { int f, level, ci, cj0, ncell, wcell, hcell, iniX, iniY, ax, rw, rh, dw, dh; };
+__device__ __forceinline__ FastItem fast_item(const FastParams &P, const FrameGeom *__restrict__ G, int item)
+{
+    FastItem t;
+    t.f = item / P.nstrips;
+    const uint32_t sd = __ldg(P.strips + (item - t.f * P.nstrips));
+    t.level = (int)(sd & 15u); t.ncell = (int)((sd >> 4) & 15u); t.ci = (int)((sd >> 8) & 0xFFFu); t.cj0 = (int)(sd >> 20);
+    const LevelGeom &g = G->lv[t.level];
+    t.wcell = g.wcell; t.hcell = g.hcell;
     // strip ROI in image coordinates — ORBextractor.cpp:805-822 (cells cj0 .. cj0+ncell-1 of cell row ci)
-    const int maxBX = g.w - ORBX_BORDER, maxBY = g.h - ORBX_BORDER;
-    const int iniX = ORBX_BORDER + cj0 * wcell, iniY = ORBX_BORDER + ci * g.hcell;
-    if (iniY >= maxBY - 3 || iniX >= maxBX - 6) return;
-    // cells whose iniX >= maxBorderX-6 are skipped by the reference (:815-816)
-    while (ncell > 0 && ORBX_BORDER + (cj0 + ncell - 1) * wcell >= maxBX - 6) ncell--;
-    if (ncell <= 0) return;
-    const int maxX = min(iniX + ncell * wcell + 6, maxBX), maxY = min(iniY + g.hcell + 6, maxBY);
-    const int rw = maxX - iniX, rh = maxY - iniY;
-    const int dw = rw - 6, dh = rh - 6;            // detection area of the strip, ROI-relative origin (3,3)
-    if (dw <= 0 || dh <= 0) return;
+    t.iniX = ORBX_BORDER + t.cj0 * t.wcell; t.iniY = ORBX_BORDER + t.ci * t.hcell;
+    const int maxX = min(t.iniX + t.ncell * t.wcell + 6, g.w - ORBX_BORDER), maxY = min(t.iniY + t.hcell + 6, g.h - ORBX_BORDER);
+    t.rw = maxX - t.iniX; t.rh = maxY - t.iniY;
+    t.dw = t.rw - 6; t.dh = t.rh - 6;          // detection area of the strip, ROI-relative origin (3,3)
+    t.ax = 16 + (t.iniX & 15);                 // tile byte of ROI column 0: TMA boxes start on 16-byte columns; one 16-byte unit of left margin
+    return t;
+}
 
-    const uint8_t *src; size_t step;
-    if (level == 0) { src = P.l0 + (size_t)f * P.l0_fstride; step = P.l0_step; }
-    else { src = P.pyr + (size_t)f * P.pyr_slab + g.off; step = (size_t)g.pitch; }
+__global__ void __launch_bounds__(FS_THREADS) k_fast_cells(const __grid_constant__ FastMaps M, FastParams P, const FrameGeom *__restrict__ G)
+{
+    extern __shared__ __align__(128) uint8_t s_dyn_raw[];
+    uint8_t *s_dyn = s_dyn_raw + ((128u - (smem_u32(s_dyn_raw) & 127u)) & 127u);      // TMA destinations are 128-byte aligned
+    __shared__ uint16_t s_q[FS_QCAP];
+    __shared__ uint32_t s_out[FS_OUT_CAP];
+    __shared__ __align__(8) uint64_t s_full[2];
+    __shared__ int s_qn, s_nout, s_base, s_ovf, s_next;
+    __shared__ int s_ccnt[FS_MAX_CELLS], s_redo[FS_MAX_CELLS];
+    const int tile_bytes = ((P.tile_rows + FS_PADROWS) * FS_TP + 127) & ~127;
+    uint8_t *s_sc = s_dyn + 2 * tile_bytes;                          // (tile_rows - 4) x FS_SP score map with a zero ring
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // stage the ROI with aligned 128-bit loads (lane = 16-byte column, warp = row); tile column `ax` is image column iniX
-    const int ax = iniX & 15;
-    const int vecs = (ax + rw + 15) >> 4;          // <= 18
-    if (lane < vecs) {
-        const uint8_t *gp = src + (size_t)(iniY + warp) * step + (iniX - ax) + lane * 16;
-        uint8_t *sp = s_img + warp * FS_TP + lane * 16;
-        for (int r = warp; r < rh; r += FS_WARPS, gp += (size_t)FS_WARPS * step, sp += FS_WARPS * FS_TP)
-            *reinterpret_cast<uint4 *>(sp) = __ldg(reinterpret_cast<const uint4 *>(gp));
-    }
-    // zero the score map (1-px ring included)
-    for (int i = threadIdx.x; i < ((dh + 2) * FS_SP) / 16; i += FS_THREADS) reinterpret_cast<uint4 *>(s_sc)[i] = make_uint4(0, 0, 0, 0);
-    if (threadIdx.x == 0) s_nout = 0;
-    __syncthreads();
+    const int nl = G->nlevels;
 
-    // ---- block-wide packed sweep at iniThFAST: one flag word per (7-row segment, tile word) ----
-    const int w0 = (ax + 3) >> 2;                                  // tile word holding detection column 0
-    const int nGs = ((ax + 3 + dw - 1) >> 2) - w0 + 1;             // words holding detection columns (<= FS_GROUPS)
-    const int nseg = (dh + 6) / 7;
-    const uint32_t *words = reinterpret_cast<const uint32_t *>(s_img);
-    uint32_t HM, KK;
-    fast_masks(P.ini_th, HM, KK);
-    {
-        const float inv = 1.0f / (float)nGs;
-        for (int it = threadIdx.x; it < nGs * nseg; it += FS_THREADS) {
-            const int seg = __float2int_rd(((float)it + 0.5f) * inv), gidx = it - seg * nGs;
-            s_flag[seg * FS_GROUPS + gidx] = fast_sweep7(words + (7 * seg) * FS_TPW + w0 + gidx, HM, KK);
+    if (threadIdx.x == 0) {
+        mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    // prologue: the first item's tile
+    if (threadIdx.x == 0 && (int)blockIdx.x < P.nitems) {
+        const FastItem t = fast_item(P, G, blockIdx.x);
+        mbar_expect_tx(&s_full[0], (uint32_t)((t.hcell + 6) * FS_TP));
+        tma_load_3d(s_dyn, &M.m[t.level], ((t.iniX & ~15) >> 2) - 4, t.iniY, t.f, &s_full[0]);
+    }
+
+    int it_n = 0;
+    for (int item = blockIdx.x; item < P.nitems; item += gridDim.x, it_n++) {
+        const int buf = it_n & 1;
+        // next item's tile into the other buffer (its previous readers passed the barrier that ended the last iteration)
+        if (threadIdx.x == 0 && item + (int)gridDim.x < P.nitems) {
+            const FastItem t = fast_item(P, G, item + gridDim.x);
+            mbar_expect_tx(&s_full[buf ^ 1], (uint32_t)((t.hcell + 6) * FS_TP));
+            tma_load_3d(s_dyn + (buf ^ 1) * tile_bytes, &M.m[t.level], ((t.iniX & ~15) >> 2) - 4, t.iniY, t.f, &s_full[buf ^ 1]);
         }
-    }
-    __syncthreads();
+        const FastItem T = fast_item(P, G, item);
+        const LevelGeom &g = G->lv[T.level];
+        const int ax = T.ax, dw = T.dw, dh = T.dh, wcell = T.wcell;
+        const uint8_t *s_img = s_dyn + buf * tile_bytes;
+        // zero the score map (1-px ring included) while the tile lands
+        for (int i = threadIdx.x; i < ((dh + 2) * FS_SP) / 16; i += FS_THREADS) reinterpret_cast<uint4 *>(s_sc)[i] = make_uint4(0, 0, 0, 0);
+        if (threadIdx.x == 0) { s_nout = 0; s_qn = 0; s_ovf = 0; s_next = 0; }
+        if (threadIdx.x < FS_MAX_CELLS) s_ccnt[threadIdx.x] = 0;
+        mbar_wait(&s_full[buf], (uint32_t)((it_n >> 1) & 1));
+        __syncthreads();
 
-    uint32_t *gdst = P.cand + (size_t)f * P.cand_slab + g.cand_off;
-    int32_t *gcnt = &P.ncand[f * nl + level];
-    uint16_t *wq = s_wq[warp];
-
-    // ---- one warp per cell: compaction, exact score, NMS, retry ----
-    for (int cell = warp; cell < ncell; cell += FS_WARPS) {
-        const int c_lo = cell * wcell, c_hi = min(c_lo + wcell, dw);          // detection columns of the cell
-        const int ga = ((ax + 3 + c_lo) >> 2) - w0, nG = ((ax + 3 + c_hi - 1) >> 2) - w0 - ga + 1;
-        const int items = nG * nseg;
-        const float inv = 1.0f / (float)nG;
-        for (int pass = 0; pass < 2; pass++) {
-            const int th = pass == 0 ? P.ini_th : P.min_th;
-            int qn = 0;
-            bool ovf = false;
-            for (int it0 = 0; it0 < items; it0 += 32) {
-                const int it = it0 + lane;
+        // ---- block-wide packed sweep at iniThFAST ----
+        const int w0 = (ax + 3) >> 2;                                  // tile word holding detection column 0
+        const int nGs = ((ax + 3 + dw - 1) >> 2) - w0 + 1;             // words holding detection columns (<= 64)
+        const int nseg = (dh + 6) / 7;
+        const uint32_t *words = reinterpret_cast<const uint32_t *>(s_img);
+        uint32_t HM, KK;
+        fast_masks(P.ini_th, HM, KK);
+        {
+            const float inv = 1.0f / (float)nGs;
+            const int units = nGs * nseg;
+            for (int u0 = 0; u0 < units; u0 += FS_THREADS) {
+                const int u = u0 + threadIdx.x;
                 uint32_t word = 0u;
                 int base_off = 0;
-                if (it < items) {
-                    const int seg = __float2int_rd(((float)it + 0.5f) * inv), gidx = ga + it - seg * nG;
-                    const uint32_t raw = pass == 0 ? s_flag[seg * FS_GROUPS + gidx]
-                                                   : fast_sweep7(words + (7 * seg) * FS_TPW + w0 + gidx, HM, KK);
-                    // columns of this word inside the cell, rows of this segment inside the strip
+                if (u < units) {
+                    const int seg = __float2int_rd(((float)u + 0.5f) * inv), gidx = u - seg * nGs;
+                    const uint32_t raw = fast_sweep7(words + (7 * seg) * FS_TPW + w0 + gidx, HM, KK);
                     const int cb = 4 * (w0 + gidx) - (ax + 3);                // detection column of byte 0
                     uint32_t cm = 0u;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) if (cb + j >= c_lo && cb + j < c_hi) cm |= 0xFEu << (8 * j);
+                    for (int j = 0; j < 4; j++) if (cb + j >= 0 && cb + j < dw) cm |= 0xFEu << (8 * j);
                     const int nv = min(7, dh - 7 * seg);
                     word = raw & cm & (((0xFF00u >> nv) & 0xFFu) * 0x01010101u);
                     base_off = (7 * seg + 3) * FS_TP + 4 * (w0 + gidx);
@@ -235,59 +259,60 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(FastParams P, const F
                 int incl = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                if (qn + total > FS_WQ) {                                     // queue full: score what is queued, NMS will scan the cell
-                    __syncwarp();
-                    for (int i = lane; i < qn; i += 32) {
-                        const int off = wq[i];
-                        const int s = fast_score_packed(s_img + off);
-                        const int tr = off / FS_TP, tc = off - tr * FS_TP - ax;
-                        s_sc[(tr - 2) * FS_SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
-                    }
-                    __syncwarp();
-                    qn = 0; ovf = true;
-                }
-                int slot = qn + incl - cnt;
+                int wbase = 0;
+                if (lane == 31 && incl > 0) wbase = atomicAdd(&s_qn, incl);
+                wbase = __shfl_sync(0xffffffffu, wbase, 31);
+                int slot = wbase + incl - cnt;
                 while (word) {
                     const int bit = __ffs((int)word) - 1;
                     word &= word - 1;
-                    wq[slot++] = (uint16_t)(base_off + (7 - (bit & 7)) * FS_TP + (bit >> 3));
+                    if (slot < FS_QCAP) s_q[slot] = (uint16_t)(base_off + (7 - (bit & 7)) * FS_TP + (bit >> 3));
+                    slot++;
                 }
-                qn += total;
             }
-            __syncwarp();
-            // exact scoring of the queued survivors (ROI coords = detection coords + 3)
-            for (int i = lane; i < qn; i += 32) {
-                const int off = wq[i];
+        }
+        __syncthreads();
+        const bool ovf = s_qn > FS_QCAP;                                // uniform
+        const int qn = ovf ? 0 : s_qn;
+        const int th0 = P.ini_th;
+        // ---- exact score (ROI coords = detection coords + 3): queue entries, or every pixel if the queue overflowed ----
+        if (!ovf) {
+            for (int i = threadIdx.x; i < qn; i += FS_THREADS) {
+                const int off = s_q[i];
                 const int s = fast_score_packed(s_img + off);
                 const int tr = off / FS_TP, tc = off - tr * FS_TP - ax;
-                s_sc[(tr - 2) * FS_SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
+                s_sc[(tr - 2) * FS_SP + (tc - 2)] = (uint8_t)(s > th0 ? s - 1 : 0);
             }
-            __syncwarp();
-            // strict 3x3 NMS inside the cell: queue entries, or every pixel of the cell if the queue overflowed
-            const int cw = c_hi - c_lo;
-            const int nitems = ovf ? cw * dh : qn;
-            const float invw = 1.0f / (float)cw;
-            int found = 0;
-            for (int i0 = 0; i0 < nitems; i0 += 32) {
-                const int i = i0 + lane;
-                bool ok = false;
-                int r = 0, c = 0, s = 0;
-                if (i < nitems) {
-                    if (ovf) { r = __float2int_rd(((float)i + 0.5f) * invw); c = c_lo + i - r * cw; }
-                    else { const int off = wq[i]; const int tr = off / FS_TP; r = tr - 3; c = off - tr * FS_TP - ax - 3; }
-                    const uint8_t *q = &s_sc[(r + 1) * FS_SP + (c + 1)];
-                    s = q[0];
-                    if (s != 0) {
-                        ok = s > q[-FS_SP] && s > q[FS_SP];
-                        if (c > c_lo) ok = ok && s > q[-1] && s > q[-FS_SP - 1] && s > q[FS_SP - 1];
-                        if (c < c_hi - 1) ok = ok && s > q[1] && s > q[-FS_SP + 1] && s > q[FS_SP + 1];
-                    }
-                }
-                found += __popc(__ballot_sync(0xffffffffu, ok));
+        } else {
+            for (int i = threadIdx.x; i < dw * dh; i += FS_THREADS) {
+                const int r = i / dw, c = i - r * dw;
+                const int s = fast_score_packed(s_img + (r + 3) * FS_TP + ax + c + 3);
+                s_sc[(r + 1) * FS_SP + (c + 1)] = (uint8_t)(s > th0 ? s - 1 : 0);
+            }
+        }
+        __syncthreads();
+        uint32_t *gdst = P.cand + (size_t)T.f * P.cand_slab + g.cand_off;
+        int32_t *gcnt = &P.ncand[T.f * nl + T.level];
+        // ---- strict 3x3 NMS inside each cell ----
+        {
+            const int nitems = ovf ? dw * dh : qn;
+            const float invc = 1.0f / (float)wcell;
+            for (int i = threadIdx.x; i < nitems; i += FS_THREADS) {
+                int r, c;
+                if (ovf) { r = i / dw; c = i - r * dw; }
+                else { const int off = s_q[i]; const int tr = off / FS_TP; r = tr - 3; c = off - tr * FS_TP - ax - 3; }
+                const uint8_t *q = &s_sc[(r + 1) * FS_SP + (c + 1)];
+                const int s = q[0];
+                if (s == 0) continue;
+                const int cell = min(__float2int_rd(((float)c + 0.5f) * invc), T.ncell - 1);
+                const int c_lo = cell * wcell, c_hi = min(c_lo + wcell, dw);
+                bool ok = s > q[-FS_SP] && s > q[FS_SP];
+                if (c > c_lo) ok = ok && s > q[-1] && s > q[-FS_SP - 1] && s > q[FS_SP - 1];
+                if (c < c_hi - 1) ok = ok && s > q[1] && s > q[-FS_SP + 1] && s > q[FS_SP + 1];
                 if (ok) {
+                    atomicAdd(&s_ccnt[cell], 1);
                     // box-relative coordinates: kp.pt + (j*wCell, i*hCell) — ORBextractor.cpp:865-866
-                    const uint32_t val = orbx_pack(cj0 * wcell + c + 3, ci * g.hcell + r + 3, s);
+                    const uint32_t val = orbx_pack(T.cj0 * wcell + c + 3, T.ci * T.hcell + r + 3, s);
                     const int o = atomicAdd(&s_nout, 1);
                     if (o < FS_OUT_CAP) s_out[o] = val;
                     else {                                                    // staging full: straight to the global list
@@ -296,43 +321,180 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(FastParams P, const F
                     }
                 }
             }
-            // the reference retries a cell at minThFAST only if iniThFAST produced nothing (:843-846)
-            if (found > 0 || pass == 1) break;
-            fast_masks(P.min_th, HM, KK);
-            __syncwarp();
         }
-        fast_masks(P.ini_th, HM, KK);
+        __syncthreads();
+        // ---- the reference retries a cell at minThFAST iff iniThFAST produced nothing (:843-846): one warp per such cell ----
+        if (threadIdx.x == 0) {
+            int n = 0;
+            for (int c = 0; c < T.ncell; c++) if (s_ccnt[c] == 0) s_redo[n++] = c;
+            s_next = n;
+        }
+        __syncthreads();
+        const int nredo = s_next;
+        if (nredo > 0) {
+            fast_masks(P.min_th, HM, KK);
+            const int th = P.min_th;
+            uint16_t *wq = s_q + warp * FS_WQ;
+            for (int ri = warp; ri < nredo; ri += FS_WARPS) {
+                const int cell = s_redo[ri];
+                const int c_lo = cell * wcell, c_hi = min(c_lo + wcell, dw);          // detection columns of the cell
+                const int ga = ((ax + 3 + c_lo) >> 2) - w0, nG = ((ax + 3 + c_hi - 1) >> 2) - w0 - ga + 1;
+                const int units = nG * nseg;
+                const float inv = 1.0f / (float)nG;
+                int wn = 0;
+                bool wovf = false;
+                for (int u0 = 0; u0 < units; u0 += 32) {
+                    const int u = u0 + lane;
+                    uint32_t word = 0u;
+                    int base_off = 0;
+                    if (u < units) {
+                        const int seg = __float2int_rd(((float)u + 0.5f) * inv), gidx = ga + u - seg * nG;
+                        const uint32_t raw = fast_sweep7(words + (7 * seg) * FS_TPW + w0 + gidx, HM, KK);
+                        const int cb = 4 * (w0 + gidx) - (ax + 3);
+                        uint32_t cm = 0u;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) if (cb + j >= c_lo && cb + j < c_hi) cm |= 0xFEu << (8 * j);
+                        const int nv = min(7, dh - 7 * seg);
+                        word = raw & cm & (((0xFF00u >> nv) & 0xFFu) * 0x01010101u);
+                        base_off = (7 * seg + 3) * FS_TP + 4 * (w0 + gidx);
+                    }
+                    const int cnt = __popc(word);
+                    int incl = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (wn + total > FS_WQ) {                                 // queue full: score what is queued, NMS will scan the cell
+                        __syncwarp();
+                        for (int i = lane; i < wn; i += 32) {
+                            const int off = wq[i];
+                            const int s = fast_score_packed(s_img + off);
+                            const int tr = off / FS_TP, tc = off - tr * FS_TP - ax;
+                            s_sc[(tr - 2) * FS_SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
+                        }
+                        __syncwarp();
+                        wn = 0; wovf = true;
+                    }
+                    int slot = wn + incl - cnt;
+                    while (word) {
+                        const int bit = __ffs((int)word) - 1;
+                        word &= word - 1;
+                        wq[slot++] = (uint16_t)(base_off + (7 - (bit & 7)) * FS_TP + (bit >> 3));
+                    }
+                    wn += total;
+                }
+                __syncwarp();
+                for (int i = lane; i < wn; i += 32) {
+                    const int off = wq[i];
+                    const int s = fast_score_packed(s_img + off);
+                    const int tr = off / FS_TP, tc = off - tr * FS_TP - ax;
+                    s_sc[(tr - 2) * FS_SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
+                }
+                __syncwarp();
+                const int cw = c_hi - c_lo;
+                const int nitems = wovf ? cw * dh : wn;
+                const float invw = 1.0f / (float)cw;
+                for (int i = lane; i < nitems; i += 32) {
+                    int r, c;
+                    if (wovf) { r = __float2int_rd(((float)i + 0.5f) * invw); c = c_lo + i - r * cw; }
+                    else { const int off = wq[i]; const int tr = off / FS_TP; r = tr - 3; c = off - tr * FS_TP - ax - 3; }
+                    const uint8_t *q = &s_sc[(r + 1) * FS_SP + (c + 1)];
+                    const int s = q[0];
+                    if (s == 0) continue;
+                    bool ok = s > q[-FS_SP] && s > q[FS_SP];
+                    if (c > c_lo) ok = ok && s > q[-1] && s > q[-FS_SP - 1] && s > q[FS_SP - 1];
+                    if (c < c_hi - 1) ok = ok && s > q[1] && s > q[-FS_SP + 1] && s > q[FS_SP + 1];
+                    if (ok) {
+                        const uint32_t val = orbx_pack(T.cj0 * wcell + c + 3, T.ci * T.hcell + r + 3, s);
+                        const int o = atomicAdd(&s_nout, 1);
+                        if (o < FS_OUT_CAP) s_out[o] = val;
+                        else {
+                            const int go = atomicAdd(gcnt, 1);
+                            if (go < g.cand_cap) gdst[go] = val; else atomicOr(P.status, ORBX_DS_CAND_OVERFLOW);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+        }
+        // ---- flush the item's candidates: one global atomic ----
+        const int n = min(s_nout, FS_OUT_CAP);
+        if (n > 0) {
+            if (threadIdx.x == 0) s_base = atomicAdd(gcnt, n);
+            __syncthreads();
+            const int base = s_base;
+            for (int i = threadIdx.x; i < n; i += FS_THREADS) if (base + i < g.cand_cap) gdst[base + i] = s_out[i];
+            if (threadIdx.x == 0 && base + n > g.cand_cap) atomicOr(P.status, ORBX_DS_CAND_OVERFLOW);
+        }
+        __syncthreads();                                                // every reader of tile `buf` and of the queues is done
     }
-    __syncthreads();
-    const int n = min(s_nout, FS_OUT_CAP);
-    if (n == 0) return;
-    if (threadIdx.x == 0) s_base = atomicAdd(gcnt, n);
-    __syncthreads();
-    const int base = s_base;
-    for (int i = threadIdx.x; i < n; i += FS_THREADS) {
-        if (base + i < g.cand_cap) gdst[base + i] = s_out[i];
-    }
-    if (threadIdx.x == 0 && base + n > g.cand_cap) atomicOr(P.status, ORBX_DS_CAND_OVERFLOW);
 }
 
-void launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride)
+// ---- host: TMA descriptors (driver entry point fetched through the runtime: no libcuda link dependency) ----
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled get_encode()
 {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_tmapEncodeTiled)p;
+    }
+    return fn;
+}
+
+// level as a 3-D tensor of u32 elements: (row pitch / 4) x rows x frames; box = FS_TPW x (hCell + 6) x 1, zero fill outside
+static bool encode_level(CUtensorMap *m, const uint8_t *base, size_t pitch, int rows, size_t fstride, int frames, int box_rows)
+{
+    PFN_tmapEncodeTiled enc = get_encode();
+    if (!enc || ((uintptr_t)base & 15) || (pitch & 15) || pitch == 0) return false;
+    if (frames <= 1 || fstride < pitch) { frames = 1; fstride = pitch * (size_t)rows; }
+    fstride = (fstride + 15) & ~(size_t)15;
+    const cuuint64_t dims[3] = { (cuuint64_t)(pitch / 4), (cuuint64_t)rows, (cuuint64_t)frames };
+    const cuuint64_t strides[2] = { (cuuint64_t)pitch, (cuuint64_t)fstride };
+    const cuuint32_t box[3] = { FS_TPW, (cuuint32_t)box_rows, 1 };
+    const cuuint32_t estr[3] = { 1, 1, 1 };
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride)
+{
+    const FrameGeom &G = h->geo;
+    if (G.total_strips <= 0) return 0;
+    if (!h->tmap_valid) {
+        for (int l = 1; l < G.nlevels; l++)
+            if (!encode_level(&h->tmap[l], h->d_pyr + G.lv[l].off, (size_t)G.lv[l].pitch, G.lv[l].h, h->pyr_slab, h->prm.max_batch, G.lv[l].hcell + 6)) return -1;
+        h->tmap_valid = true; h->tmap_l0 = nullptr;
+    }
+    if (h->tmap_l0 != l0 || h->tmap_l0_step != l0_step || h->tmap_l0_fstride != l0_fstride || h->tmap_l0_frames < nframes) {
+        if (!encode_level(&h->tmap[0], l0, l0_step, G.lv[0].h, l0_fstride, nframes, G.lv[0].hcell + 6)) return -1;
+        h->tmap_l0 = l0; h->tmap_l0_step = l0_step; h->tmap_l0_fstride = l0_fstride; h->tmap_l0_frames = nframes;
+    }
+    FastMaps M;
+    memcpy(M.m, h->tmap, sizeof(M.m));
     FastParams P;
-    P.l0 = l0; P.l0_step = l0_step; P.l0_fstride = l0_fstride;
-    P.pyr = h->d_pyr; P.pyr_slab = h->pyr_slab;
-    P.cand = h->d_cand; P.cand_slab = h->geo.cand_entries;
+    P.cand = h->d_cand; P.cand_slab = G.cand_entries;
     P.ncand = h->d_ncand;
-    P.strips = h->d_strips;
+    P.strips = h->d_strips; P.nstrips = G.total_strips; P.nitems = G.total_strips * nframes;
     P.ini_th = h->prm.ini_th_fast; P.min_th = h->prm.min_th_fast;
     P.status = h->d_status;
-    P.tile_rows = h->geo.max_hcell + 6;
-    const size_t smem = FS_PAD + (size_t)(P.tile_rows + FS_PADROWS) * FS_TP + (size_t)(P.tile_rows - 4) * FS_SP;
+    P.tile_rows = G.max_hcell + 6;
+    const int tile_bytes = ((P.tile_rows + FS_PADROWS) * FS_TP + 127) & ~127;
+    const size_t smem = 128 + 2 * (size_t)tile_bytes + (size_t)(P.tile_rows - 4) * FS_SP;
     static size_t configured = 0;
-    if (smem > configured) {
+    if (smem > configured || h->fast_grid_cap <= 0) {
         cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
+        configured = std::max(configured, smem);
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fast_cells, FS_THREADS, smem);
+        h->fast_grid_cap = std::max(1, occ) * h->sm_count;
     }
-    dim3 grid(h->geo.total_strips, nframes);
+    const int grid = std::min(P.nitems, h->fast_grid_cap);
     ProfScope ps(h, ORBX_K_FAST);
-    k_fast_cells<<<grid, FS_THREADS, smem, h->stream>>>(P, h->d_geo);
+    k_fast_cells<<<grid, FS_THREADS, smem, h->stream>>>(M, P, h->d_geo);
+    return 0;
 }

@@ -109,10 +109,16 @@ static bool build_geometry(const orbx_handle *h, int w, int hgt, FrameGeom &G, s
             max_hcell = std::max(max_hcell, g.hcell);
         } else { g.strips_per_row = 0; g.cells_per_strip = 1; }
         g.strip_first = strips; strips += g.strips_per_row * g.nrows;
-        // strip descriptors for k_fast_cells: level:4 | cells:4 | cell row:12 | first cell column:12
+        // strip descriptors for k_fast_cells: level:4 | cells:4 | cell row:12 | first cell column:12.  Cells the reference
+        // skips (iniY >= maxBorderY-3, iniX >= maxBorderX-6; ORBextractor.cpp:811-816) are trimmed here.
         if (strip_tab) for (int ci = 0; ci < g.nrows; ci++) for (int sj = 0; sj < g.strips_per_row; sj++) {
-            const int cj0 = sj * g.cells_per_strip, nc = std::min(g.cells_per_strip, g.ncols - cj0);
-            strip_tab->push_back((uint32_t)l | ((uint32_t)std::max(nc, 0) << 4) | ((uint32_t)ci << 8) | ((uint32_t)cj0 << 20));
+            const int maxBX = g.w - ORBX_BORDER, maxBY = g.h - ORBX_BORDER;
+            const int cj0 = sj * g.cells_per_strip;
+            int nc = std::min(g.cells_per_strip, g.ncols - cj0);
+            if (ORBX_BORDER + ci * g.hcell >= maxBY - 3) continue;
+            while (nc > 0 && ORBX_BORDER + (cj0 + nc - 1) * g.wcell >= maxBX - 6) nc--;
+            if (nc <= 0) continue;
+            strip_tab->push_back((uint32_t)l | ((uint32_t)nc << 4) | ((uint32_t)ci << 8) | ((uint32_t)cj0 << 20));
         }
         g.blur_tx = (g.w + ORBX_BLUR_TW - 1) / ORBX_BLUR_TW; g.blur_ty = (g.h + 4 * ORBX_BLUR_H - 1) / (4 * ORBX_BLUR_H);
         g.blur_first = tiles; tiles += g.blur_tx * g.blur_ty;
@@ -162,12 +168,14 @@ static orbx_status set_geometry(orbx_handle *h, int w, int hgt)
     if (G.pyr_bytes * B > h->pyr_cap || G.blur_bytes * B > h->blur_cap || G.cand_entries * B > h->cand_cap ||
         (size_t)G.sel_entries * B > h->sel_cap || (int)xt.size() > h->tab_cap || (int)yt.size() > h->tab_cap ||
         G.sel_entries > h->max_kp || (int)strips.size() > h->strip_cap) { h->err = "frame geometry does not fit the arenas sized at create"; return ORBX_E_INVALID; }
+    G.total_strips = (int)strips.size();
     ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
     ORBX_CUDA(h, cudaMemcpy(h->d_geo, &G, sizeof(G), cudaMemcpyHostToDevice));
     if (!xt.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_xtab, xt.data(), xt.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
     if (!yt.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_ytab, yt.data(), yt.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
     if (!strips.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_strips, strips.data(), strips.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    h->geo = G; h->pyr_slab = G.pyr_bytes; h->blur_slab = G.blur_bytes;
+    G.total_strips = (int)strips.size();
+    h->geo = G; h->pyr_slab = G.pyr_bytes; h->blur_slab = G.blur_bytes; h->tmap_valid = false;
     return ORBX_OK;
 }
 
@@ -318,7 +326,7 @@ static orbx_status run_pipeline(orbx_handle *h, int nframes, const uint8_t *l0, 
     const int nl = h->geo.nlevels;
     ORBX_CUDA(h, cudaMemsetAsync(h->d_ncand, 0, (size_t)nframes * nl * sizeof(int32_t), h->stream));
     for (int l = 1; l < nl; l++) launch_resize_level(h, l, nframes, l0, l0_step, l0_fstride);   // ComputePyramid
-    launch_fast(h, nframes, l0, l0_step, l0_fstride);                                            // cell FAST
+    if (launch_fast(h, nframes, l0, l0_step, l0_fstride) != 0) { h->err = "cuTensorMapEncodeTiled failed (frame base/step must be 16-byte aligned)"; return ORBX_E_CUDA; }   // cell FAST
     launch_quadtree(h, nframes);                                                                 // DistributeOctTree
     launch_blur(h, nframes, l0, l0_step, l0_fstride);                                            // GaussianBlur per level
     const bool filtered = d_depth != nullptr || nboxes > 0;

@@ -1,5 +1,6 @@
 // orbx_internal.h — shared declarations of the sm_100a ORB path (not part of the ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -14,7 +15,7 @@
 #define ORBX_PATCH 31
 #define ORBX_BLUR_TW 128             // blur tile: 128 px x (4 warps x ORBX_BLUR_H rows) per CTA (k_blur.cu)
 #define ORBX_BLUR_H 35
-#define ORBX_FAST_MAX_W 248          // max detection width (px) of one FAST strip: <= 64 aligned 4-pixel words (k_fast.cu)
+#define ORBX_FAST_MAX_W 240          // max detection width (px) of one FAST strip: 16-byte aligned TMA box of 288 bytes (k_fast.cu)
 
 // candidate / selected-keypoint packing: x:12 | y:12 | score:8, coordinates relative to the border box
 __host__ __device__ inline uint32_t orbx_pack(int x, int y, int s) { return (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24); }
@@ -82,6 +83,10 @@ struct orbx_handle {
     FrameGeom *d_geo;
     ResizeTab *d_xtab, *d_ytab; int tab_cap;
     uint32_t *d_strips; int strip_cap;   // FAST strip descriptors (k_fast.cu)
+    // TMA tensor maps of the pyramid levels (k_fast.cu): levels >= 1 depend on the geometry only, level 0 on the caller's frames
+    CUtensorMap tmap[ORBX_MAX_LEVELS]; bool tmap_valid;
+    const uint8_t *tmap_l0; size_t tmap_l0_step, tmap_l0_fstride; int tmap_l0_frames;
+    int fast_grid_cap;                   // resident CTAs of the persistent FAST kernel
     // arenas, sized for max_width x max_height x max_batch
     uint8_t *d_pyr, *d_blur;     size_t pyr_slab, blur_slab;          // current per-frame strides
     size_t pyr_cap, blur_cap;                                          // arena bytes
@@ -142,7 +147,7 @@ struct orbx_db {
 
 // ---- kernel launchers (one per .cu) ----
 void launch_resize_level(orbx_handle *h, int level, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
-void launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
+int  launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);   // -1: TMA descriptor encode failed
 void launch_quadtree(orbx_handle *h, int nframes);
 void launch_quadtree_geo(orbx_handle *h, const FrameGeom *d_geo, int nlevels, int nframes, int node_cap, size_t cand_slab, int sel_slab);
 void launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
