@@ -286,9 +286,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e = float(t.item())
     e2e = {"value": world * Be * K / (ms_e * 1e-3), "unit": "frames/s",
-           "h2d_bytes_per_step": nbytes_g + nbytes_d,
+           # gray frames are DMA'd; the pinned depth maps are NOT copied: the depth filter gathers one 32-byte PCIe sector per
+           # selected keypoint in place (<= max_keypoints per frame) — counted here at that upper bound
+           "h2d_bytes_per_step": nbytes_g + Be * CAP * 32, "depth_bytes_resident_on_host": nbytes_d,
            "d2h_bytes_per_step": Be * (CAP * (28 + 32 + 16) + 8),
-           "api": "orbx_track_batch (host pinned buffers)", "ms_per_step": ms_e / K, "host_wall_ms_per_step": wall * 1e3 / K}
+           "api": "orbx_track_batch (host pinned buffers; 3-stream chunk pipeline, zero-copy depth gather)", "ms_per_step": ms_e / K, "host_wall_ms_per_step": wall * 1e3 / K}
 
     # ---- per-frame latency, batch = 1 through the same host call (configs[1] p50) ----
     lat = []

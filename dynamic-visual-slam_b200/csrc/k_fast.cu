@@ -42,10 +42,14 @@
 #define FS_TPW (FS_TP / 4)
 #define FS_PADROWS 6             // rows behind the tile: a 7-row sweep unit may start on the last detection row
 #define FS_SP 272                // score-map pitch: >= detection width + 2, multiple of 16
-#define FS_QCAP 6144             // survivor queue (u16 tile offsets); FS_WARPS x FS_WQ in the retry phase
-#define FS_WQ (FS_QCAP / FS_WARPS)   // per-warp queue of the retry phase, >= 32 lanes x 28 flags
-#define FS_OUT_CAP 1024          // staged outputs; beyond it survivors are written straight to the global list
+#define FS_QCAP 4096             // survivor queue (u16 tile offsets); FS_RWARPS x FS_WQ in the retry phase
+#define FS_RWARPS 4               // warps that run cell retries concurrently
+#define FS_WQ (FS_QCAP / FS_RWARPS)  // per-warp queue of the retry phase, >= 32 lanes x 28 flags
+#define FS_OUT_CAP 512          // staged outputs; beyond it survivors are written straight to the global list
 #define FS_MAX_CELLS 8
+#ifndef FS_NBUF
+#define FS_NBUF 2                // tile buffers: 2 = the next item's tile is in flight while this one is processed
+#endif
 
 struct FastMaps { CUtensorMap m[ORBX_MAX_LEVELS]; };
 
@@ -190,10 +194,10 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(const __grid_constant
     __shared__ uint16_t s_q[FS_QCAP];
     __shared__ uint32_t s_out[FS_OUT_CAP];
     __shared__ __align__(8) uint64_t s_full[2];
-    __shared__ int s_qn, s_nout, s_base, s_ovf, s_next;
-    __shared__ int s_ccnt[FS_MAX_CELLS], s_redo[FS_MAX_CELLS];
+    __shared__ int s_qn, s_nout;
+    __shared__ int s_ccnt[FS_MAX_CELLS];
     const int tile_bytes = ((P.tile_rows + FS_PADROWS) * FS_TP + 127) & ~127;
-    uint8_t *s_sc = s_dyn + 2 * tile_bytes;                          // (tile_rows - 4) x FS_SP score map with a zero ring
+    uint8_t *s_sc = s_dyn + FS_NBUF * tile_bytes;                          // (tile_rows - 4) x FS_SP score map with a zero ring
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nl = G->nlevels;
 
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(const __grid_constant
     }
     __syncthreads();
     // prologue: the first item's tile
-    if (threadIdx.x == 0 && (int)blockIdx.x < P.nitems) {
+    if (FS_NBUF == 2 && threadIdx.x == 0 && (int)blockIdx.x < P.nitems) {
         const FastItem t = fast_item(P, G, blockIdx.x);
         mbar_expect_tx(&s_full[0], (uint32_t)((t.hcell + 6) * FS_TP));
         tma_load_3d(s_dyn, &M.m[t.level], ((t.iniX & ~15) >> 2) - 4, t.iniY, t.f, &s_full[0]);
@@ -212,22 +216,22 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(const __grid_constant
 
     int it_n = 0;
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x, it_n++) {
-        const int buf = it_n & 1;
+        const int buf = FS_NBUF == 2 ? (it_n & 1) : 1;
         // next item's tile into the other buffer (its previous readers passed the barrier that ended the last iteration)
-        if (threadIdx.x == 0 && item + (int)gridDim.x < P.nitems) {
-            const FastItem t = fast_item(P, G, item + gridDim.x);
+        if (threadIdx.x == 0 && (FS_NBUF == 1 || item + (int)gridDim.x < P.nitems)) {
+            const FastItem t = fast_item(P, G, FS_NBUF == 2 ? item + gridDim.x : item);
             mbar_expect_tx(&s_full[buf ^ 1], (uint32_t)((t.hcell + 6) * FS_TP));
-            tma_load_3d(s_dyn + (buf ^ 1) * tile_bytes, &M.m[t.level], ((t.iniX & ~15) >> 2) - 4, t.iniY, t.f, &s_full[buf ^ 1]);
+            tma_load_3d(s_dyn + (FS_NBUF == 2 ? (buf ^ 1) : 0) * tile_bytes, &M.m[t.level], ((t.iniX & ~15) >> 2) - 4, t.iniY, t.f, &s_full[buf ^ 1]);
         }
         const FastItem T = fast_item(P, G, item);
         const LevelGeom &g = G->lv[T.level];
         const int ax = T.ax, dw = T.dw, dh = T.dh, wcell = T.wcell;
-        const uint8_t *s_img = s_dyn + buf * tile_bytes;
+        const uint8_t *s_img = s_dyn + (FS_NBUF == 2 ? buf : 0) * tile_bytes;
         // zero the score map (1-px ring included) while the tile lands
         for (int i = threadIdx.x; i < ((dh + 2) * FS_SP) / 16; i += FS_THREADS) reinterpret_cast<uint4 *>(s_sc)[i] = make_uint4(0, 0, 0, 0);
-        if (threadIdx.x == 0) { s_nout = 0; s_qn = 0; s_ovf = 0; s_next = 0; }
+        if (threadIdx.x == 0) { s_nout = 0; s_qn = 0; }
         if (threadIdx.x < FS_MAX_CELLS) s_ccnt[threadIdx.x] = 0;
-        mbar_wait(&s_full[buf], (uint32_t)((it_n >> 1) & 1));
+        mbar_wait(&s_full[FS_NBUF == 2 ? buf : 0], (uint32_t)(FS_NBUF == 2 ? ((it_n >> 1) & 1) : (it_n & 1)));
         __syncthreads();
 
         // ---- block-wide packed sweep at iniThFAST ----
@@ -324,19 +328,15 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(const __grid_constant
         }
         __syncthreads();
         // ---- the reference retries a cell at minThFAST iff iniThFAST produced nothing (:843-846): one warp per such cell ----
-        if (threadIdx.x == 0) {
-            int n = 0;
-            for (int c = 0; c < T.ncell; c++) if (s_ccnt[c] == 0) s_redo[n++] = c;
-            s_next = n;
-        }
-        __syncthreads();
-        const int nredo = s_next;
+        int nredo = 0;
+        uint32_t redo_cells = 0u;                                       // up to 8 cell indices, 4 bits each (uniform)
+        for (int c = 0; c < T.ncell; c++) if (s_ccnt[c] == 0) { redo_cells |= (uint32_t)c << (4 * nredo); nredo++; }
         if (nredo > 0) {
             fast_masks(P.min_th, HM, KK);
             const int th = P.min_th;
             uint16_t *wq = s_q + warp * FS_WQ;
-            for (int ri = warp; ri < nredo; ri += FS_WARPS) {
-                const int cell = s_redo[ri];
+            for (int ri = warp; ri < nredo && warp < FS_RWARPS; ri += FS_RWARPS) {
+                const int cell = (int)((redo_cells >> (4 * ri)) & 15u);
                 const int c_lo = cell * wcell, c_hi = min(c_lo + wcell, dw);          // detection columns of the cell
                 const int ga = ((ax + 3 + c_lo) >> 2) - w0, nG = ((ax + 3 + c_hi - 1) >> 2) - w0 - ga + 1;
                 const int units = nG * nseg;
@@ -417,14 +417,16 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(const __grid_constant
             }
             __syncthreads();
         }
-        // ---- flush the item's candidates: one global atomic ----
-        const int n = min(s_nout, FS_OUT_CAP);
-        if (n > 0) {
-            if (threadIdx.x == 0) s_base = atomicAdd(gcnt, n);
-            __syncthreads();
-            const int base = s_base;
-            for (int i = threadIdx.x; i < n; i += FS_THREADS) if (base + i < g.cand_cap) gdst[base + i] = s_out[i];
-            if (threadIdx.x == 0 && base + n > g.cand_cap) atomicOr(P.status, ORBX_DS_CAND_OVERFLOW);
+        // ---- flush the item's candidates: one global atomic, warp 0 ----
+        if (warp == 0) {
+            const int n = min(s_nout, FS_OUT_CAP);
+            if (n > 0) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(gcnt, n);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                for (int i = lane; i < n; i += 32) if (base + i < g.cand_cap) gdst[base + i] = s_out[i];
+                if (lane == 0 && base + n > g.cand_cap) atomicOr(P.status, ORBX_DS_CAND_OVERFLOW);
+            }
         }
         __syncthreads();                                                // every reader of tile `buf` and of the queues is done
     }
@@ -484,7 +486,7 @@ int launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, 
     P.status = h->d_status;
     P.tile_rows = G.max_hcell + 6;
     const int tile_bytes = ((P.tile_rows + FS_PADROWS) * FS_TP + 127) & ~127;
-    const size_t smem = 128 + 2 * (size_t)tile_bytes + (size_t)(P.tile_rows - 4) * FS_SP;
+    const size_t smem = 128 + FS_NBUF * (size_t)tile_bytes + (size_t)(P.tile_rows - 4) * FS_SP;
     static size_t configured = 0;
     if (smem > configured || h->fast_grid_cap <= 0) {
         cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -11,6 +11,7 @@
 
 static std::string g_create_err;
 static orbx_status grow(orbx_handle *h, uint8_t **p, size_t *cap, size_t need);
+static const void *mapped_device_view(const void *host);
 static inline int cv_round_f(float v) { return (int)lrintf(v); }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -195,6 +196,8 @@ extern "C" void orbx_destroy(orbx_handle *h)
     if (h->ev_b) cudaEventDestroy(h->ev_b);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->out_stream) cudaStreamDestroy(h->out_stream);
+    for (int i = 0; i < 2; i++) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]); if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]); }
     delete h;
 }
 
@@ -223,6 +226,12 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     h->sm_count = prop.multiProcessorCount;
     CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CREATE_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+        CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+        CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+    }
     CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
     CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
     build_tables(h);
@@ -232,14 +241,17 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
         g_create_err = "unsupported max_width x max_height geometry"; orbx_destroy(h); return ORBX_E_UNSUPPORTED;
     }
     const size_t B = (size_t)p.max_batch;
+    // host-buffer calls are pipelined in chunks of `chunk` frames over two input and two output slots
+    h->chunk = p.reserved_[0] > 0 ? std::min(p.reserved_[0], p.max_batch) : std::max(1, std::min(32, p.max_batch / 8));
+    const size_t S = std::max(B, (size_t)2 * h->chunk);          // frames held by the staging arenas
     // arenas are sized for the max geometry with 12% headroom so that smaller frames with unlucky padding still fit
     h->pyr_cap = (G.pyr_bytes + G.pyr_bytes / 8 + 4096) * B; h->blur_cap = (G.blur_bytes + G.blur_bytes / 8 + 4096) * B;
     h->cand_cap = (G.cand_entries + G.cand_entries / 8 + 4096 * p.nlevels) * B;
     h->sel_cap = (size_t)(G.sel_entries + 64 * p.nlevels) * B;
     h->max_kp = std::max(p.max_keypoints, G.sel_entries + 64 * p.nlevels);
     h->tab_cap = 2 * (p.max_width + p.max_height) * 6 + 1024;
-    h->in_cap = align_up((size_t)p.max_width, 128) * p.max_height * B;
-    h->depth_cap = align_up((size_t)p.max_width * 2, 128) * p.max_height * B;
+    h->in_cap = align_up((size_t)p.max_width, 128) * p.max_height * S;
+    h->depth_cap = align_up((size_t)p.max_width * 2, 128) * p.max_height * S;
     CREATE_CUDA(cudaMalloc(&h->d_geo, sizeof(FrameGeom)));
     h->strip_cap = G.total_cells + 64 * p.nlevels;
     CREATE_CUDA(cudaMalloc(&h->d_strips, sizeof(uint32_t) * h->strip_cap));
@@ -260,9 +272,9 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     CREATE_CUDA(cudaMalloc(&h->d_kps_all, B * h->max_kp * sizeof(orbx_keypoint)));
     CREATE_CUDA(cudaMalloc(&h->d_desc_all, B * h->max_kp * ORBX_DESC_BYTES));
     CREATE_CUDA(cudaMalloc(&h->d_count_all, B * sizeof(int32_t)));
-    CREATE_CUDA(cudaMalloc(&h->d_kps_out, B * h->max_kp * sizeof(orbx_keypoint)));
-    CREATE_CUDA(cudaMalloc(&h->d_desc_out, B * h->max_kp * ORBX_DESC_BYTES));
-    CREATE_CUDA(cudaMalloc(&h->d_count_out, B * sizeof(int32_t)));
+    CREATE_CUDA(cudaMalloc(&h->d_kps_out, S * h->max_kp * sizeof(orbx_keypoint)));
+    CREATE_CUDA(cudaMalloc(&h->d_desc_out, S * h->max_kp * ORBX_DESC_BYTES));
+    CREATE_CUDA(cudaMalloc(&h->d_count_out, S * sizeof(int32_t)));
     CREATE_CUDA(cudaMalloc(&h->d_prev_desc, (size_t)h->max_kp * ORBX_DESC_BYTES));
     CREATE_CUDA(cudaMalloc(&h->d_prev_count, sizeof(int32_t)));
     CREATE_CUDA(cudaMemset(h->d_prev_count, 0, sizeof(int32_t)));
@@ -369,7 +381,8 @@ extern "C" orbx_status orbx_extract_filtered(orbx_handle *h, const uint8_t *gray
     if (st != ORBX_OK) return st;
     const size_t pitch = align_up((size_t)width, 128), dpitch = align_up((size_t)width * 2, 128);
     ORBX_CUDA(h, cudaMemcpy2DAsync(h->d_in, pitch, gray, step, (size_t)width, (size_t)height, cudaMemcpyHostToDevice, h->stream));
-    if (depth) ORBX_CUDA(h, cudaMemcpy2DAsync(h->d_depth_in, dpitch, depth, dstep, (size_t)width * 2, (size_t)height, cudaMemcpyHostToDevice, h->stream));
+    const uint16_t *depth_zc = depth ? (const uint16_t *)mapped_device_view(depth) : nullptr;      // pinned depth is gathered in place
+    if (depth && !depth_zc) ORBX_CUDA(h, cudaMemcpy2DAsync(h->d_depth_in, dpitch, depth, dstep, (size_t)width * 2, (size_t)height, cudaMemcpyHostToDevice, h->stream));
     if (nboxes > 0) {
         if (nboxes > h->boxes_cap) {
             cudaStreamSynchronize(h->stream);
@@ -379,7 +392,7 @@ extern "C" orbx_status orbx_extract_filtered(orbx_handle *h, const uint8_t *gray
         }
         ORBX_CUDA(h, cudaMemcpyAsync(h->d_boxes, boxes, (size_t)nboxes * sizeof(orbx_box), cudaMemcpyHostToDevice, h->stream));
     }
-    st = run_pipeline(h, 1, h->d_in, pitch, 0, depth ? h->d_depth_in : nullptr, dpitch, 0, h->d_boxes, nboxes, drop_mask,
+    st = run_pipeline(h, 1, h->d_in, pitch, 0, depth_zc ? depth_zc : (depth ? h->d_depth_in : nullptr), depth_zc ? dstep : dpitch, 0, h->d_boxes, nboxes, drop_mask,
                       h->d_kps_out, h->d_desc_out, h->max_kp, h->d_count_out);
     if (st != ORBX_OK) return st;
     // one packed D2H: [count | keypoints | descriptors] for min(cap, max_kp) entries
@@ -404,44 +417,6 @@ extern "C" orbx_status orbx_extract(orbx_handle *h, const uint8_t *gray, int32_t
                                     orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *n_out)
 {
     return orbx_extract_filtered(h, gray, width, height, step, nullptr, 0, nullptr, 0, 0, kps, desc, cap, n_out);
-}
-
-extern "C" orbx_status orbx_extract_batch(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
-                                          size_t step, const uint16_t *depth, size_t dstep,
-                                          orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *counts)
-{
-    if (!h) return ORBX_E_INVALID;
-    cudaSetDevice(h->device);
-    if (!gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }
-    if (nframes < 0 || !kps || !desc || !counts || cap < 1 || step < (size_t)width) { h->err = "bad arguments"; return ORBX_E_INVALID; }
-    orbx_status st = set_geometry(h, width, height);
-    if (st != ORBX_OK) return st;
-    const size_t pitch = align_up((size_t)width, 128), dpitch = align_up((size_t)width * 2, 128);
-    const size_t fstride = pitch * height, dfstride = dpitch * height;
-    const int B = h->prm.max_batch;
-    const int kcap = std::min(cap, h->max_kp);
-    for (int f0 = 0; f0 < nframes; f0 += B) {
-        const int nb = std::min(B, nframes - f0);
-        for (int f = 0; f < nb; f++) {
-            ORBX_CUDA(h, cudaMemcpy2DAsync(h->d_in + (size_t)f * fstride, pitch, gray + (size_t)(f0 + f) * height * step, step,
-                                           (size_t)width, (size_t)height, cudaMemcpyHostToDevice, h->stream));
-            if (depth) ORBX_CUDA(h, cudaMemcpy2DAsync((uint8_t *)h->d_depth_in + (size_t)f * dfstride, dpitch,
-                                                      (const uint8_t *)depth + (size_t)(f0 + f) * height * dstep, dstep,
-                                                      (size_t)width * 2, (size_t)height, cudaMemcpyHostToDevice, h->stream));
-        }
-        st = run_pipeline(h, nb, h->d_in, pitch, fstride, depth ? h->d_depth_in : nullptr, dpitch, dfstride, nullptr, 0, 0,
-                          h->d_kps_out, h->d_desc_out, h->max_kp, h->d_count_out);
-        if (st != ORBX_OK) return st;
-        ORBX_CUDA(h, cudaMemcpyAsync(counts + f0, h->d_count_out, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-        ORBX_CUDA(h, cudaMemcpy2DAsync(kps + (size_t)f0 * cap, (size_t)cap * sizeof(orbx_keypoint), h->d_kps_out, (size_t)h->max_kp * sizeof(orbx_keypoint),
-                                       (size_t)kcap * sizeof(orbx_keypoint), (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
-        ORBX_CUDA(h, cudaMemcpy2DAsync(desc + (size_t)f0 * cap * ORBX_DESC_BYTES, (size_t)cap * ORBX_DESC_BYTES, h->d_desc_out, (size_t)h->max_kp * ORBX_DESC_BYTES,
-                                       (size_t)kcap * ORBX_DESC_BYTES, (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
-        st = check_device_status(h);
-        if (st != ORBX_OK) return st;
-        for (int f = 0; f < nb; f++) if (counts[f0 + f] > cap) { h->err = "output capacity too small"; return ORBX_E_CAPACITY; }
-    }
-    return ORBX_OK;
 }
 
 // ---- stream step: extraction + depth filter + match against the previous frame (frontend.cpp:1094-1132) ----
@@ -494,6 +469,108 @@ extern "C" orbx_status orbx_track_batch_device(orbx_handle *h, const uint8_t *d_
     return track_device(h, d_gray, nframes, width, height, step, frame_stride, d_depth, dstep, dframe_stride, d_kps, d_desc, cap, d_counts, d_matches, d_mcounts, max_dist);
 }
 
+// Device view of a host buffer the GPU can read in place (pinned / registered, mapped under UVA); nullptr for pageable memory.
+static const void *mapped_device_view(const void *host)
+{
+    cudaPointerAttributes a;
+    if (!host || cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+    return a.devicePointer;
+}
+
+// Host-buffer batch driver shared by orbx_extract_batch and orbx_track_batch.  The frames are cut into chunks of
+// h->chunk frames and pipelined over three streams with two input and two output slots:
+//     copy stream : H2D of chunk i+1          (gray; depth only if it is pageable)
+//     main stream : kernels of chunk i
+//     out stream  : D2H of chunk i-1          (counts, keypoints, descriptors, matches)
+// Depth maps in pinned host memory are NOT copied: the post-selection depth filter gathers its ~1000 samples per
+// frame straight from the mapped host buffer (one 32-byte PCIe read each instead of 1.8 MB per frame).
+static orbx_status host_batch(orbx_handle *h, bool track, const uint8_t *gray, int nframes, int width, int height, size_t step,
+                              const uint16_t *depth, size_t dstep, orbx_keypoint *kps, uint8_t *desc, int cap, int32_t *counts,
+                              orbx_dmatch *matches, int32_t *mcounts, float max_dist)
+{
+    orbx_status st = set_geometry(h, width, height);
+    if (st != ORBX_OK) return st;
+    if (nframes == 0) return ORBX_OK;
+    const size_t pitch = align_up((size_t)width, 128), dpitch = align_up((size_t)width * 2, 128);
+    const size_t fstride = pitch * height, dfstride = dpitch * height;
+    const int C = h->chunk;
+    const int kcap = std::min(cap, h->max_kp);
+    const size_t slot_kp = (size_t)C * h->max_kp;
+    orbx_dmatch *d_m = nullptr; int32_t *d_mc = nullptr;
+    if (track) {
+        if ((st = grow(h, (uint8_t **)&h->d_mout, &h->mout_cap, 2 * slot_kp * sizeof(orbx_dmatch) + 2 * (size_t)C * sizeof(int32_t))) != ORBX_OK) return st;
+        d_m = h->d_mout; d_mc = (int32_t *)((uint8_t *)h->d_mout + 2 * slot_kp * sizeof(orbx_dmatch));
+    }
+    const uint8_t *depth_zc = depth ? (const uint8_t *)mapped_device_view(depth) : nullptr;
+    const bool tight = (step == (size_t)width) && (pitch == (size_t)width);
+    // the main stream may still hold work of an earlier call that reads the slots
+    ORBX_CUDA(h, cudaEventRecord(h->ev_comp[0], h->stream));
+    ORBX_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_comp[0], 0));
+    const int nchunks = (nframes + C - 1) / C;
+    for (int i = 0; i < nchunks; i++) {
+        const int slot = i & 1, f0 = i * C, nb = std::min(C, nframes - f0);
+        uint8_t *d_g = h->d_in + (size_t)slot * C * fstride;
+        uint8_t *d_d = (uint8_t *)h->d_depth_in + (size_t)slot * C * dfstride;
+        // ---- H2D (copy stream): the input slot is free once the kernels of chunk i-2 are done ----
+        if (i >= 2) ORBX_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_comp[slot], 0));
+        if (tight) ORBX_CUDA(h, cudaMemcpyAsync(d_g, gray + (size_t)f0 * height * step, (size_t)nb * fstride, cudaMemcpyHostToDevice, h->copy_stream));
+        else for (int f = 0; f < nb; f++)
+            ORBX_CUDA(h, cudaMemcpy2DAsync(d_g + (size_t)f * fstride, pitch, gray + (size_t)(f0 + f) * height * step, step,
+                                           (size_t)width, (size_t)height, cudaMemcpyHostToDevice, h->copy_stream));
+        if (depth && !depth_zc) {
+            if (dstep == dpitch) ORBX_CUDA(h, cudaMemcpyAsync(d_d, (const uint8_t *)depth + (size_t)f0 * height * dstep, (size_t)nb * dfstride, cudaMemcpyHostToDevice, h->copy_stream));
+            else for (int f = 0; f < nb; f++)
+                ORBX_CUDA(h, cudaMemcpy2DAsync(d_d + (size_t)f * dfstride, dpitch, (const uint8_t *)depth + (size_t)(f0 + f) * height * dstep, dstep,
+                                               (size_t)width * 2, (size_t)height, cudaMemcpyHostToDevice, h->copy_stream));
+        }
+        ORBX_CUDA(h, cudaEventRecord(h->ev_in[slot], h->copy_stream));
+        // ---- kernels (main stream): the output slot is free once the D2H of chunk i-2 is done ----
+        ORBX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_in[slot], 0));
+        if (i >= 2) ORBX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_out[slot], 0));
+        orbx_keypoint *o_k = h->d_kps_out + (size_t)slot * slot_kp;
+        uint8_t *o_d = h->d_desc_out + (size_t)slot * slot_kp * ORBX_DESC_BYTES;
+        int32_t *o_c = h->d_count_out + slot * C;
+        const uint16_t *dd = nullptr; size_t dds = 0, ddf = 0;
+        if (depth_zc) { dd = (const uint16_t *)(depth_zc + (size_t)f0 * height * dstep); dds = dstep; ddf = (size_t)height * dstep; }
+        else if (depth) { dd = (const uint16_t *)d_d; dds = dpitch; ddf = dfstride; }
+        if (track) st = track_device(h, d_g, nb, width, height, pitch, fstride, dd, dds, ddf, o_k, o_d, h->max_kp, o_c,
+                                     d_m + (size_t)slot * slot_kp, d_mc + slot * C, max_dist);
+        else st = run_pipeline(h, nb, d_g, pitch, fstride, dd, dds, ddf, nullptr, 0, 0, o_k, o_d, h->max_kp, o_c);
+        if (st != ORBX_OK) { cudaStreamSynchronize(h->copy_stream); cudaStreamSynchronize(h->out_stream); cudaStreamSynchronize(h->stream); return st; }
+        ORBX_CUDA(h, cudaEventRecord(h->ev_comp[slot], h->stream));
+        // ---- D2H (out stream) ----
+        ORBX_CUDA(h, cudaStreamWaitEvent(h->out_stream, h->ev_comp[slot], 0));
+        ORBX_CUDA(h, cudaMemcpyAsync(counts + f0, o_c, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, h->out_stream));
+        ORBX_CUDA(h, cudaMemcpy2DAsync(kps + (size_t)f0 * cap, (size_t)cap * sizeof(orbx_keypoint), o_k, (size_t)h->max_kp * sizeof(orbx_keypoint),
+                                       (size_t)kcap * sizeof(orbx_keypoint), (size_t)nb, cudaMemcpyDeviceToHost, h->out_stream));
+        ORBX_CUDA(h, cudaMemcpy2DAsync(desc + (size_t)f0 * cap * ORBX_DESC_BYTES, (size_t)cap * ORBX_DESC_BYTES, o_d, (size_t)h->max_kp * ORBX_DESC_BYTES,
+                                       (size_t)kcap * ORBX_DESC_BYTES, (size_t)nb, cudaMemcpyDeviceToHost, h->out_stream));
+        if (track) {
+            ORBX_CUDA(h, cudaMemcpyAsync(mcounts + f0, d_mc + slot * C, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, h->out_stream));
+            ORBX_CUDA(h, cudaMemcpy2DAsync(matches + (size_t)f0 * cap, (size_t)cap * sizeof(orbx_dmatch), d_m + (size_t)slot * slot_kp, (size_t)h->max_kp * sizeof(orbx_dmatch),
+                                           (size_t)kcap * sizeof(orbx_dmatch), (size_t)nb, cudaMemcpyDeviceToHost, h->out_stream));
+        }
+        ORBX_CUDA(h, cudaEventRecord(h->ev_out[slot], h->out_stream));
+    }
+    ORBX_CUDA(h, cudaStreamSynchronize(h->out_stream));
+    st = check_device_status(h);
+    if (st != ORBX_OK) return st;
+    for (int f = 0; f < nframes; f++) if (counts[f] > cap) { h->err = "output capacity too small"; return ORBX_E_CAPACITY; }
+    return ORBX_OK;
+}
+
+extern "C" orbx_status orbx_extract_batch(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
+                                          size_t step, const uint16_t *depth, size_t dstep,
+                                          orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *counts)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    if (!gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }
+    if (nframes < 0 || !kps || !desc || !counts || cap < 1 || step < (size_t)width || (depth && dstep < (size_t)width * 2)) { h->err = "bad arguments"; return ORBX_E_INVALID; }
+    return host_batch(h, false, gray, nframes, width, height, step, depth, dstep, kps, desc, cap, counts, nullptr, nullptr, 0.f);
+}
+
 extern "C" orbx_status orbx_track_batch(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
                                         size_t step, const uint16_t *depth, size_t dstep,
                                         orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *counts,
@@ -502,47 +579,8 @@ extern "C" orbx_status orbx_track_batch(orbx_handle *h, const uint8_t *gray, int
     if (!h) return ORBX_E_INVALID;
     cudaSetDevice(h->device);
     if (!gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }
-    if (nframes < 0 || !kps || !desc || !counts || !matches || !mcounts || cap < 1 || step < (size_t)width) { h->err = "bad arguments"; return ORBX_E_INVALID; }
-    orbx_status st = set_geometry(h, width, height);
-    if (st != ORBX_OK) return st;
-    const size_t pitch = align_up((size_t)width, 128), dpitch = align_up((size_t)width * 2, 128);
-    const size_t fstride = pitch * height, dfstride = dpitch * height;
-    const int B = h->prm.max_batch;
-    const int kcap = std::min(cap, h->max_kp);
-    // device-side match output lives in the matcher scratch, sized [B][max_kp]
-    if ((st = grow(h, (uint8_t **)&h->d_mout, &h->mout_cap, (size_t)B * h->max_kp * sizeof(orbx_dmatch) + (size_t)B * sizeof(int32_t))) != ORBX_OK) return st;
-    orbx_dmatch *d_m = h->d_mout;
-    int32_t *d_mc = (int32_t *)((uint8_t *)h->d_mout + (size_t)B * h->max_kp * sizeof(orbx_dmatch));
-    const bool tight = (step == (size_t)width) && (pitch == (size_t)width);
-    for (int f0 = 0; f0 < nframes; f0 += B) {
-        const int nb = std::min(B, nframes - f0);
-        if (tight) ORBX_CUDA(h, cudaMemcpyAsync(h->d_in, gray + (size_t)f0 * height * step, (size_t)nb * fstride, cudaMemcpyHostToDevice, h->stream));
-        else for (int f = 0; f < nb; f++)
-            ORBX_CUDA(h, cudaMemcpy2DAsync(h->d_in + (size_t)f * fstride, pitch, gray + (size_t)(f0 + f) * height * step, step,
-                                           (size_t)width, (size_t)height, cudaMemcpyHostToDevice, h->stream));
-        if (depth) {
-            if (dstep == dpitch) ORBX_CUDA(h, cudaMemcpyAsync(h->d_depth_in, (const uint8_t *)depth + (size_t)f0 * height * dstep, (size_t)nb * dfstride, cudaMemcpyHostToDevice, h->stream));
-            else for (int f = 0; f < nb; f++)
-                ORBX_CUDA(h, cudaMemcpy2DAsync((uint8_t *)h->d_depth_in + (size_t)f * dfstride, dpitch,
-                                               (const uint8_t *)depth + (size_t)(f0 + f) * height * dstep, dstep,
-                                               (size_t)width * 2, (size_t)height, cudaMemcpyHostToDevice, h->stream));
-        }
-        st = track_device(h, h->d_in, nb, width, height, pitch, fstride, depth ? h->d_depth_in : nullptr, dpitch, dfstride,
-                          h->d_kps_out, h->d_desc_out, h->max_kp, h->d_count_out, d_m, d_mc, max_dist);
-        if (st != ORBX_OK) return st;
-        ORBX_CUDA(h, cudaMemcpyAsync(counts + f0, h->d_count_out, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-        ORBX_CUDA(h, cudaMemcpyAsync(mcounts + f0, d_mc, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-        ORBX_CUDA(h, cudaMemcpy2DAsync(kps + (size_t)f0 * cap, (size_t)cap * sizeof(orbx_keypoint), h->d_kps_out, (size_t)h->max_kp * sizeof(orbx_keypoint),
-                                       (size_t)kcap * sizeof(orbx_keypoint), (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
-        ORBX_CUDA(h, cudaMemcpy2DAsync(desc + (size_t)f0 * cap * ORBX_DESC_BYTES, (size_t)cap * ORBX_DESC_BYTES, h->d_desc_out, (size_t)h->max_kp * ORBX_DESC_BYTES,
-                                       (size_t)kcap * ORBX_DESC_BYTES, (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
-        ORBX_CUDA(h, cudaMemcpy2DAsync(matches + (size_t)f0 * cap, (size_t)cap * sizeof(orbx_dmatch), d_m, (size_t)h->max_kp * sizeof(orbx_dmatch),
-                                       (size_t)kcap * sizeof(orbx_dmatch), (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
-        st = check_device_status(h);
-        if (st != ORBX_OK) return st;
-        for (int f = 0; f < nb; f++) if (counts[f0 + f] > cap) { h->err = "output capacity too small"; return ORBX_E_CAPACITY; }
-    }
-    return ORBX_OK;
+    if (nframes < 0 || !kps || !desc || !counts || !matches || !mcounts || cap < 1 || step < (size_t)width || (depth && dstep < (size_t)width * 2)) { h->err = "bad arguments"; return ORBX_E_INVALID; }
+    return host_batch(h, true, gray, nframes, width, height, step, depth, dstep, kps, desc, cap, counts, matches, mcounts, max_dist);
 }
 
 // ---- stage access (mvImagePyramid is public in the reference, ORBextractor.hpp:84) ----

@@ -69,8 +69,10 @@ struct ResizeTab { int32_t ofs; int16_t a0, a1; };   // 8 bytes
 struct orbx_handle {
     orbx_params prm;
     int device;
-    cudaStream_t stream, copy_stream;
+    cudaStream_t stream, copy_stream, out_stream;
     cudaEvent_t ev_a, ev_b;
+    cudaEvent_t ev_in[2], ev_comp[2], ev_out[2];   // host-batch pipeline: input slot filled / kernels done / outputs copied
+    int chunk;                                      // frames per pipeline chunk of the host-buffer batch calls
     std::string err;
     int64_t launches;
     // extractor tables (ORBextractor.cpp:409-469)

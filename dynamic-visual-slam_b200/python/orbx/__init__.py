@@ -129,12 +129,38 @@ def _p(a):
     return a.ctypes.data_as(ct.c_void_p) if a is not None else None
 
 
+class PinnedArray:
+    """numpy view of page-locked host memory from orbx_alloc_pinned (freed on close / garbage collection).
+    Pinned inputs are DMA'd without a staging copy, and pinned depth maps are read in place by the GPU."""
+
+    def __init__(self, shape, dtype):
+        L = load()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = L.orbx_alloc_pinned(max(self.nbytes, 1))
+        if not self.ptr:
+            raise MemoryError("orbx_alloc_pinned failed")
+        buf = (ct.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            load().orbx_free_pinned(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ORBextractor:
     """ORB_SLAM3::ORBextractor over the C ABI (reference ORBextractor.hpp:44-111)."""
 
     def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7,
                  max_width=1280, max_height=720, max_batch=1, device=0, depth_min=0.3, depth_max=3.0,
-                 max_keypoints=0, cand_divisor=0):
+                 max_keypoints=0, cand_divisor=0, host_chunk=0):
         L = load()
         p = Params()
         L.orbx_default_params(ct.byref(p))
@@ -142,6 +168,7 @@ class ORBextractor:
         p.ini_th_fast, p.min_th_fast = iniThFAST, minThFAST
         p.max_width, p.max_height, p.max_batch, p.device = max_width, max_height, max_batch, device
         p.depth_min, p.depth_max, p.max_keypoints, p.cand_divisor = depth_min, depth_max, max_keypoints, cand_divisor
+        p.reserved_[0] = host_chunk
         self._h = ct.c_void_p()
         st = L.orbx_create(ct.byref(p), ct.byref(self._h))
         if st != OK:

@@ -70,7 +70,7 @@ typedef struct {
     int32_t max_keypoints;    /* per-frame output capacity; 0 = nfeatures + 4*nlevels + 64 */
     int32_t cand_divisor;     /* candidate-list capacity per level = max(4096, pixels/cand_divisor); 0 = 16 */
     int32_t device;           /* CUDA device ordinal */
-    int32_t reserved_[3];
+    int32_t reserved_[3];     /* [0]: frames per pipeline chunk of the host-buffer batch calls, 0 = auto (max_batch/8, 1..32) */
 } orbx_params;
 
 typedef struct orbx_handle orbx_handle;
@@ -112,7 +112,9 @@ orbx_status orbx_extract_filtered(orbx_handle *h, const uint8_t *gray, int32_t w
 
 /* frame-parallel batch, HOST buffers: frames tightly packed (frame f at gray + f*height*step).
  * depth nullable.  kps/desc have room for cap_per_frame entries per frame; counts[nframes].
- * Internally chunks by max_batch and overlaps H2D / compute / D2H.                              */
+ * Internally cut into chunks that are pipelined over three streams (H2D of chunk i+1, kernels of chunk i,
+ * D2H of chunk i-1).  A depth buffer in pinned host memory (orbx_alloc_pinned / cudaHostRegister) is not
+ * copied at all: the depth filter gathers its samples from it in place.                            */
 orbx_status orbx_extract_batch(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
                                size_t step, const uint16_t *depth, size_t dstep,
                                orbx_keypoint *kps, uint8_t *desc, int32_t cap_per_frame, int32_t *counts);

@@ -1,0 +1,136 @@
+"""GPU parity of the batch / stream entry points (host buffers through the 3-stream pipeline, pinned zero-copy depth,
+device buffers) against the oracle running the reference's per-frame sequence:
+extract -> filterDepth -> match(filtered, prev_filtered) + distance < 50 -> prev = filtered  (reference frontend.cpp:1094-1132, 1258-1259)."""
+import ctypes as ct
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+W, H, N, SEED = 640, 480, 11, 21
+
+
+@pytest.fixture(scope="module")
+def stream_ref(oracle):
+    orc = oracle.COracle()
+    frames = np.stack([oracle.synth_gray(SEED, f, W, H) for f in range(N)])
+    depths = np.stack([oracle.synth_depth(SEED, f, W, H) for f in range(N)])
+    ref, prev = [], None
+    for f in range(N):
+        r = orc.extract(frames[f])
+        fk, fd, _ = oracle.filter_depth(r["kps"], r["desc"], depths[f])
+        m = oracle.match(fd, prev) if prev is not None and len(prev) and len(fd) else np.zeros(0, oracle.DM_DTYPE)
+        ref.append(dict(raw_kps=r["kps"], raw_desc=r["desc"], kps=fk, desc=fd, good=m[m["distance"] < 50.0]))
+        prev = fd
+    return frames, depths, ref
+
+
+def _check_track(out, ref, n0=0):
+    kps, desc, counts, matches, mcounts = out
+    for i in range(len(counts)):
+        r = ref[n0 + i]
+        assert counts[i] == len(r["kps"]), ("count frame %d" % (n0 + i), counts[i], len(r["kps"]))
+        assert np.array_equal(kps[i, :counts[i]].view(np.uint8), r["kps"].view(np.uint8)), "keypoints frame %d" % (n0 + i)
+        assert np.array_equal(desc[i, :counts[i]], r["desc"]), "descriptors frame %d" % (n0 + i)
+        assert mcounts[i] == len(r["good"]), ("matches frame %d" % (n0 + i), mcounts[i], len(r["good"]))
+        assert np.array_equal(matches[i, :mcounts[i]].view(np.uint8), r["good"].view(np.uint8)), "matches frame %d" % (n0 + i)
+
+
+@pytest.mark.parametrize("max_batch,chunk", [(4, 0), (8, 3), (16, 0), (1, 0)])
+def test_track_batch_host_pageable(built, stream_ref, max_batch, chunk):
+    import orbx
+    frames, depths, ref = stream_ref
+    ex = orbx.ORBextractor(max_width=W, max_height=H, max_batch=max_batch, host_chunk=chunk)
+    try:
+        # two calls: the second continues from the carried previous-frame descriptors
+        _check_track(ex.track_batch(frames[:6], depths[:6]), ref, 0)
+        _check_track(ex.track_batch(frames[6:], depths[6:]), ref, 6)
+        # after a reset the first frame has no predecessor again (reference first frame, frontend.cpp:1277-1317)
+        ex.track_reset()
+        out = ex.track_batch(frames[3:5], depths[3:5])
+        assert out[4][0] == 0 and out[4][1] == len(ref[4]["good"])
+    finally:
+        ex.close()
+
+
+def test_track_batch_host_pinned_zero_copy_depth(built, stream_ref):
+    import orbx
+    frames, depths, ref = stream_ref
+    pg, pd = orbx.PinnedArray(frames.shape, np.uint8), orbx.PinnedArray(depths.shape, np.uint16)
+    pg.array[...] = frames
+    pd.array[...] = depths
+    ex = orbx.ORBextractor(max_width=W, max_height=H, max_batch=4)
+    try:
+        _check_track(ex.track_batch(pg.array, pd.array), ref, 0)
+        # single-frame call with pinned depth (gathered in place)
+        fk, fd = ex(pg.array[2], depth=pd.array[2])
+        assert np.array_equal(fk.view(np.uint8), ref[2]["kps"].view(np.uint8)) and np.array_equal(fd, ref[2]["desc"])
+    finally:
+        ex.close()
+        pg.close(); pd.close()
+
+
+def test_extract_batch_host(built, stream_ref):
+    import orbx
+    frames, depths, ref = stream_ref
+    ex = orbx.ORBextractor(max_width=W, max_height=H, max_batch=4)
+    try:
+        kps, desc, counts = ex.extract_batch(frames)
+        for i in range(N):
+            assert counts[i] == len(ref[i]["raw_kps"])
+            assert np.array_equal(kps[i, :counts[i]].view(np.uint8), ref[i]["raw_kps"].view(np.uint8))
+            assert np.array_equal(desc[i, :counts[i]], ref[i]["raw_desc"])
+        kps, desc, counts = ex.extract_batch(frames, depth=depths)
+        for i in range(N):
+            assert counts[i] == len(ref[i]["kps"]) and np.array_equal(desc[i, :counts[i]], ref[i]["desc"])
+        # capacity error is reported, not truncated silently
+        with pytest.raises(orbx.OrbxError) as e:
+            ex.extract_batch(frames[:2], cap=100)
+        assert e.value.status == orbx.E_CAPACITY
+    finally:
+        ex.close()
+
+
+def test_track_batch_device(built, stream_ref):
+    import torch
+    import orbx
+    frames, depths, ref = stream_ref
+    dev = torch.device("cuda", 0)
+    ex = orbx.ORBextractor(max_width=W, max_height=H, max_batch=N, max_keypoints=1536)
+    try:
+        CAP = 1536
+        g = torch.from_numpy(frames).to(dev)
+        d = torch.from_numpy(depths.view(np.int16)).to(dev)
+        kps = torch.zeros((N, CAP, 28), dtype=torch.uint8, device=dev)
+        desc = torch.zeros((N, CAP, 32), dtype=torch.uint8, device=dev)
+        cnt = torch.zeros(N, dtype=torch.int32, device=dev)
+        m = torch.zeros((N, CAP, 16), dtype=torch.uint8, device=dev)
+        mc = torch.zeros(N, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        ex._check(ex.L.orbx_track_batch_device(ex.handle, g.data_ptr(), N, W, H, W, W * H, d.data_ptr(), 2 * W, 2 * W * H,
+                                               kps.data_ptr(), desc.data_ptr(), CAP, cnt.data_ptr(), m.data_ptr(), mc.data_ptr(), ct.c_float(50.0)))
+        ex.sync()
+        out = (kps.cpu().numpy().view(orbx.KP_DTYPE).reshape(N, CAP), desc.cpu().numpy(), cnt.cpu().numpy(),
+               m.cpu().numpy().view(orbx.DM_DTYPE).reshape(N, CAP), mc.cpu().numpy())
+        _check_track(out, ref, 0)
+    finally:
+        ex.close()
+
+
+def test_empty_and_featureless_frames(built):
+    import orbx
+    ex = orbx.ORBextractor(max_width=320, max_height=240)
+    try:
+        assert ex(np.zeros((0, 0), np.uint8)) == -1                       # reference returns -1 (ORBextractor.cpp:1090-1091)
+        k, d = ex(np.full((240, 320), 77, np.uint8))
+        assert len(k) == 0 and d.shape == (0, 32)
+        with pytest.raises(TypeError):
+            ex(np.zeros((240, 320), np.float32))
+        with pytest.raises(orbx.OrbxError):                                # larger than the arenas sized at create
+            ex(np.zeros((480, 640), np.uint8))
+        assert len(ex.match(np.zeros((0, 32), np.uint8), np.zeros((5, 32), np.uint8))) == 0
+        m = ex.match(np.zeros((3, 32), np.uint8), np.zeros((0, 32), np.uint8))
+        assert len(m) == 0
+    finally:
+        ex.close()
