@@ -3,24 +3,27 @@
 // level (reference ORBextractor.cpp:1132-1133).  Arithmetic: SURVEY.md App. A.3 — taps
 // [18,34,48,56,48,34,18]/256, row pass in u16, column pass in u32, one rounding (c + 32768) >> 16.
 //
-// HBM-bound stage, all levels of all frames in ONE launch, no shared memory: a thread owns 4 adjacent
-// columns (one aligned 32-bit word) and sweeps down ORBX_BLUR_H output rows.  Per input row it loads the
-// aligned words around its columns (coalesced 128-byte warp requests; neighbours hit L1; the loads of 7
-// rows are issued back to back for memory-level parallelism), forms the seven-tap windows with funnel
-// shifts and evaluates the row pass with two IDP.4A dot products per pixel; the column pass keeps a
-// 7-deep register window per column (rows unrolled by 7 so the window rotates statically) and the four
-// results leave as one 32-bit store.  Image borders cost nothing in the sweep: the reflect-101 mapping is
-// folded into per-thread PRMT selectors and load offsets computed once.
+// HBM-bound stage, all levels of all frames in ONE launch.  A CTA produces a 256 x hCell output tile: its input
+// window (3-px halo, 288 bytes x (hCell + 6) rows) arrives by ONE TMA load (the per-level tensor maps shared with
+// k_fast.cu; the unit zero-fills outside the image), border tiles then mirror the missing halo in shared memory
+// (reflect-101), and every thread sweeps 4 adjacent columns (one aligned 32-bit word) down half the tile: three
+// LDS.32 per input row, the seven-tap row pass as two IDP.4A dot products per pixel on funnel-shifted windows,
+// the column pass on a 7-deep register window per column (rows unrolled by 7 so the window rotates statically),
+// one PRMT tree to pack the four results and one 32-bit coalesced store.  No per-row address or border arithmetic.
 #include "orbx_internal.h"
+#include "orbx_tma.h"
+#include <cstring>
+
+#define BL_THREADS 128
+#define BL_GROUPS 64                 // 4-pixel column groups per tile row: 256 output columns
+#define BL_TW (4 * BL_GROUPS)
+#define BL_PADROWS 8                 // rows behind the tile: the unrolled sweep may overrun a band by < 7 rows
 
 struct BlurParams {
-    const uint8_t *l0; size_t l0_step, l0_fstride;
-    const uint8_t *pyr; size_t pyr_slab;
     uint8_t *blur; size_t blur_slab;
+    const uint32_t *tiles;           // level:4 | tile column:12 | tile row:16
+    int tile_rows;                   // max (hCell + 6) over the levels
 };
-
-// reflect-101 with a single fold (valid for -len < p < 2*len - 1; levels are at least 8 px)
-__device__ __forceinline__ int reflect1(int p, int len) { p = p < 0 ? -p : p; return p >= len ? 2 * len - 2 - p : p; }
 
 // row pass for the 4 pixels of word C given its left / right neighbours: 2 x IDP.4A per pixel
 __device__ __forceinline__ void hpass4(uint32_t L, uint32_t C, uint32_t R, int &h0, int &h1, int &h2, int &h3)
@@ -33,100 +36,101 @@ __device__ __forceinline__ void hpass4(uint32_t L, uint32_t C, uint32_t R, int &
     h3 = __dp4a(C, KLO, __dp4a(R, KHI, 0u));
 }
 
-// Border handling without branches in the sweep: every thread loads four aligned words per row from
-// thread-constant offsets (oL, oC, oRa, oRb) and rebuilds its 12-byte window [x-4, x+8) with three PRMTs
-// whose selectors encode the reflect-101 mapping.  Interior threads get the identity mapping.
-struct BlurTaps { int oL, oRa, oRb; uint32_t selL, selC, selR; };
-
-__device__ BlurTaps blur_taps(int x, int w)
+__global__ void __launch_bounds__(BL_THREADS) k_blur7(const __grid_constant__ LevelMaps M, BlurParams P, const FrameGeom *__restrict__ G)
 {
-    BlurTaps t;
-    // L' = positions x-4..x-1 from PRMT(word@oL, word@x)
-    if (x == 0) { t.oL = 4; t.selL = 0x5670u; }             // 4,3,2,1 <- (word@4).b0, (word@0).b3,b2,b1
-    else { t.oL = x - 4; t.selL = 0x3210u; }
-    // C' = positions x..x+3 from PRMT(word@oL, word@x); reflected sources lie in word@x or word@(x-4)
-    uint32_t sc = 0;
-    for (int j = 0; j < 4; j++) {
-        const int s = reflect1(x + j, w);
-        const uint32_t idx = s >= x ? 4u + (uint32_t)(s - x) : (uint32_t)(s - (x - 4));
-        sc |= idx << (4 * j);
-    }
-    t.selC = sc;
-    // R' = positions x+4..x+7 from PRMT(word@oRa, word@oRb) with oRb = oRa + 4 (or equal when one word suffices)
-    int smin = 1 << 30, smax = -1;
-    for (int j = 0; j < 4; j++) { const int s = reflect1(x + 4 + j, w); smin = min(smin, s); smax = max(smax, s); }
-    t.oRa = smin & ~3; t.oRb = smax & ~3;
-    uint32_t sr = 0;
-    for (int j = 0; j < 4; j++) {
-        const int s = reflect1(x + 4 + j, w);
-        const uint32_t idx = (s & ~3) == t.oRa ? (uint32_t)(s & 3) : 4u + (uint32_t)(s & 3);
-        sr |= idx << (4 * j);
-    }
-    t.selR = sr;
-    return t;
-}
-
-__global__ void __launch_bounds__(128) k_blur7(BlurParams P, const FrameGeom *__restrict__ G)
-{
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
+    uint8_t *s_img = s_raw + ((128u - (smem_u32(s_raw) & 127u)) & 127u);          // TMA destination: 128-byte aligned
     const int f = blockIdx.y;
-    int level = 0;
-    const int nl = G->nlevels;
-    for (int l = 1; l < nl; l++) if ((int)blockIdx.x >= G->lv[l].blur_first) level = l;
+    const uint32_t td = __ldg(P.tiles + blockIdx.x);
+    const int level = (int)(td & 15u), tx = (int)((td >> 4) & 0xFFFu), ty = (int)(td >> 16);
     const LevelGeom &g = G->lv[level];
-    const int t = blockIdx.x - g.blur_first;
-    const int tx = t % g.blur_tx, ty = t / g.blur_tx;
-    const int w = g.w, hgt = g.h;
-    const int x = tx * ORBX_BLUR_TW + (threadIdx.x & 31) * 4;
-    const int ybase = ty * (4 * ORBX_BLUR_H) + (threadIdx.x >> 5) * ORBX_BLUR_H;
-    if (x >= w || ybase >= hgt) return;
-    const uint8_t *src; size_t step;
-    if (level == 0) { src = P.l0 + (size_t)f * P.l0_fstride; step = P.l0_step; }
-    else { src = P.pyr + (size_t)f * P.pyr_slab + g.off; step = (size_t)g.pitch; }
-    uint8_t *dst = P.blur + (size_t)f * P.blur_slab + g.boff + x;
-    const BlurTaps tp = blur_taps(x, w);
+    const int w = g.w, hgt = g.h, TH = g.hcell;                                     // tile = BL_TW x hCell output pixels
+    const int x0 = tx * BL_TW, y0 = ty * TH;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&s_bar, (uint32_t)((TH + 6) * ORBX_TMA_BOX_BYTES));
+        // box column 0 = image column x0 - 16, box row 0 = image row y0 - 3
+        tma_load_3d(s_img, &M.m[level], (x0 >> 2) - 4, y0 - 3, f, &s_bar);
+    }
+    __syncthreads();                                                                 // barrier initialised before anyone polls it
+    mbar_wait(&s_bar, 0);
+    // ---- reflect-101 halo of border tiles (image pixel (x, y) lives at s_img[(y - y0 + 3) * 288 + x - x0 + 16]) ----
+    const bool edge_l = x0 == 0, edge_r = x0 + BL_TW + 3 > w, edge_t = y0 == 0, edge_b = y0 + TH + 3 > hgt;
+    if (edge_l || edge_r) {
+        for (int r = threadIdx.x; r < TH + 6; r += BL_THREADS) {
+            const int y = y0 - 3 + r;
+            if (y < 0 || y >= hgt) continue;
+            uint8_t *row = s_img + r * ORBX_TMA_BOX_BYTES + 16 - x0;                 // row[x] = pixel x
+            if (edge_l) { row[-1] = row[1]; row[-2] = row[2]; row[-3] = row[3]; }
+            if (edge_r) { row[w] = row[w - 2]; row[w + 1] = row[w - 3]; row[w + 2] = row[w - 4]; }
+        }
+        __syncthreads();
+    }
+    if (edge_t || edge_b) {
+        for (int i = threadIdx.x; i < 6 * ORBX_TMA_BOX_WORDS; i += BL_THREADS) {
+            const int k = i / ORBX_TMA_BOX_WORDS, wd = i - k * ORBX_TMA_BOX_WORDS;   // k: 0..2 top rows -1..-3, 3..5 bottom rows h..h+2
+            uint32_t *sw = reinterpret_cast<uint32_t *>(s_img);
+            if (k < 3) { if (edge_t) sw[(2 - k) * ORBX_TMA_BOX_WORDS + wd] = sw[(4 + k) * ORBX_TMA_BOX_WORDS + wd]; }
+            else if (edge_b) {
+                const int d = k - 3, rdst = hgt + d - y0 + 3, rsrc = hgt - 2 - d - y0 + 3;
+                if (rdst < TH + 6) sw[rdst * ORBX_TMA_BOX_WORDS + wd] = sw[rsrc * ORBX_TMA_BOX_WORDS + wd];
+            }
+        }
+        __syncthreads();
+    }
+    // ---- sweep: thread = 4 columns x half the tile rows ----
+    const int grp = threadIdx.x & (BL_GROUPS - 1), band = threadIdx.x / BL_GROUPS;
+    const int x = x0 + 4 * grp;
+    if (x >= w) return;
+    const int RB = (TH + 1) >> 1;
+    const int rb = band * RB, re = min(min(TH, rb + RB), hgt - y0);                  // tile-relative output rows [rb, re)
+    if (rb >= re) return;
+    const uint32_t *colw = reinterpret_cast<const uint32_t *>(s_img) + 4 + grp + rb * ORBX_TMA_BOX_WORDS;   // word of input row (rb - 3)
+    uint8_t *dst = P.blur + (size_t)f * P.blur_slab + g.boff + (size_t)(y0 + rb) * g.bpitch + x;
 
     int win[4][7];
 #pragma unroll
     for (int k = 0; k < 6; k++) {
-        const uint8_t *row = src + (size_t)reflect1(ybase - 3 + k, hgt) * step;
-        const uint32_t wl = __ldg(reinterpret_cast<const uint32_t *>(row + tp.oL)), wc = __ldg(reinterpret_cast<const uint32_t *>(row + x));
-        const uint32_t wa = __ldg(reinterpret_cast<const uint32_t *>(row + tp.oRa)), wb = __ldg(reinterpret_cast<const uint32_t *>(row + tp.oRb));
-        hpass4(__byte_perm(wl, wc, tp.selL), __byte_perm(wl, wc, tp.selC), __byte_perm(wa, wb, tp.selR), win[0][k], win[1][k], win[2][k], win[3][k]);
+        const uint32_t *q = colw + k * ORBX_TMA_BOX_WORDS;
+        hpass4(q[-1], q[0], q[1], win[0][k], win[1][k], win[2][k], win[3][k]);
     }
-    for (int r0 = 0; r0 < ORBX_BLUR_H; r0 += 7) {
-        // issue the loads of the next 7 input rows back to back (memory-level parallelism), then compute
-        uint32_t wl[7], wc[7], wa[7], wb[7];
+    const int nrows = re - rb;
+    for (int r0 = 0; r0 < nrows; r0 += 7) {
 #pragma unroll
         for (int k = 0; k < 7; k++) {
-            const uint8_t *row = src + (size_t)reflect1(min(ybase + r0 + k + 3, hgt + 2), hgt) * step;
-            wl[k] = __ldg(reinterpret_cast<const uint32_t *>(row + tp.oL)); wc[k] = __ldg(reinterpret_cast<const uint32_t *>(row + x));
-            wa[k] = __ldg(reinterpret_cast<const uint32_t *>(row + tp.oRa)); wb[k] = __ldg(reinterpret_cast<const uint32_t *>(row + tp.oRb));
-        }
+            const uint32_t *q = colw + (r0 + k + 6) * ORBX_TMA_BOX_WORDS;
+            hpass4(q[-1], q[0], q[1], win[0][(k + 6) % 7], win[1][(k + 6) % 7], win[2][(k + 6) % 7], win[3][(k + 6) % 7]);
+            uint32_t acc[4];
 #pragma unroll
-        for (int k = 0; k < 7; k++) {
-            const int y = ybase + r0 + k;
-            hpass4(__byte_perm(wl[k], wc[k], tp.selL), __byte_perm(wl[k], wc[k], tp.selC), __byte_perm(wa[k], wb[k], tp.selR),
-                   win[0][(k + 6) % 7], win[1][(k + 6) % 7], win[2][(k + 6) % 7], win[3][(k + 6) % 7]);
-            uint32_t packed = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t acc = 32768u + 18u * (uint32_t)(win[j][k % 7] + win[j][(k + 6) % 7]) +
-                                     34u * (uint32_t)(win[j][(k + 1) % 7] + win[j][(k + 5) % 7]) +
-                                     48u * (uint32_t)(win[j][(k + 2) % 7] + win[j][(k + 4) % 7]) + 56u * (uint32_t)win[j][(k + 3) % 7];
-                packed |= (acc >> 16) << (8 * j);
-            }
-            if (y < hgt) *reinterpret_cast<uint32_t *>(dst + (size_t)y * g.bpitch) = packed;   // pitch % 128 == 0: the word is in-bounds
+            for (int j = 0; j < 4; j++)
+                acc[j] = 32768u + 18u * (uint32_t)(win[j][k % 7] + win[j][(k + 6) % 7]) +
+                         34u * (uint32_t)(win[j][(k + 1) % 7] + win[j][(k + 5) % 7]) +
+                         48u * (uint32_t)(win[j][(k + 2) % 7] + win[j][(k + 4) % 7]) + 56u * (uint32_t)win[j][(k + 3) % 7];
+            // byte 2 of each accumulator = (acc >> 16) & 255 (acc < 2^24)
+            const uint32_t packed = __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
+            if (r0 + k < nrows) *reinterpret_cast<uint32_t *>(dst + (size_t)(r0 + k) * g.bpitch) = packed;   // pitch % 128 == 0: the word is in-bounds
         }
     }
 }
 
-void launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride)
+int launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride)
 {
+    if (h->geo.total_blur_tiles <= 0) return 0;
+    if (orbx_ensure_tmaps(h, nframes, l0, l0_step, l0_fstride) != 0) return -1;
+    LevelMaps M;
+    memcpy(M.m, h->tmap, sizeof(M.m));
     BlurParams P;
-    P.l0 = l0; P.l0_step = l0_step; P.l0_fstride = l0_fstride;
-    P.pyr = h->d_pyr; P.pyr_slab = h->pyr_slab;
     P.blur = h->d_blur; P.blur_slab = h->blur_slab;
+    P.tiles = h->d_blur_tiles;
+    P.tile_rows = h->geo.max_hcell + 6;
+    const size_t smem = 128 + (size_t)(P.tile_rows + BL_PADROWS) * ORBX_TMA_BOX_BYTES;
+    static size_t configured = 0;
+    if (smem > configured) { cudaFuncSetAttribute(k_blur7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
     dim3 grid(h->geo.total_blur_tiles, nframes);
     ProfScope ps(h, ORBX_K_BLUR);
-    k_blur7<<<grid, 128, 0, h->stream>>>(P, h->d_geo);
+    k_blur7<<<grid, BL_THREADS, smem, h->stream>>>(M, P, h->d_geo);
+    return 0;
 }

@@ -33,6 +33,7 @@
 // max(mn9, -mx9)) produced wrong results on sm_100a with nvcc 12.9 (the negation feeding a fused
 // 3-input VIMNMX3 was lost); the raw-value formulation below has no negated min/max operands.
 #include "orbx_internal.h"
+#include "orbx_tma.h"
 #include <algorithm>
 #include <cstring>
 
@@ -50,8 +51,6 @@
 #ifndef FS_NBUF
 #define FS_NBUF 2                // tile buffers: 2 = the next item's tile is in flight while this one is processed
 #endif
-
-struct FastMaps { CUtensorMap m[ORBX_MAX_LEVELS]; };
 
 struct FastParams {
     uint32_t *cand; size_t cand_slab;
@@ -144,30 +143,6 @@ __device__ __forceinline__ void fast_masks(int th, uint32_t &HM, uint32_t &KK)
     KK = (0x80u - (1u << sh)) * 0x01010101u;
 }
 
-// ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG, SYNCS) ----
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t ok;
-    do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
-}
-
 // geometry of one work item, derived from its strip descriptor
 struct FastItem { int f, level, ci, cj0, ncell, wcell, hcell, iniX, iniY, ax, rw, rh, dw, dh; };
 __device__ __forceinline__ FastItem fast_item(const FastParams &P, const FrameGeom *__restrict__ G, int item)
@@ -187,7 +162,7 @@ __device__ __forceinline__ FastItem fast_item(const FastParams &P, const FrameGe
     return t;
 }
 
-__global__ void __launch_bounds__(FS_THREADS) k_fast_cells(const __grid_constant__ FastMaps M, FastParams P, const FrameGeom *__restrict__ G)
+__global__ void __launch_bounds__(FS_THREADS) k_fast_cells(const __grid_constant__ LevelMaps M, FastParams P, const FrameGeom *__restrict__ G)
 {
     extern __shared__ __align__(128) uint8_t s_dyn_raw[];
     uint8_t *s_dyn = s_dyn_raw + ((128u - (smem_u32(s_dyn_raw) & 127u)) & 127u);      // TMA destinations are 128-byte aligned
@@ -451,22 +426,23 @@ static PFN_tmapEncodeTiled get_encode()
 // level as a 3-D tensor of u32 elements: (row pitch / 4) x rows x frames; box = FS_TPW x (hCell + 6) x 1, zero fill outside
 static bool encode_level(CUtensorMap *m, const uint8_t *base, size_t pitch, int rows, size_t fstride, int frames, int box_rows)
 {
+    static_assert(FS_TPW == ORBX_TMA_BOX_WORDS, "FAST tile pitch = TMA box width");
     PFN_tmapEncodeTiled enc = get_encode();
     if (!enc || ((uintptr_t)base & 15) || (pitch & 15) || pitch == 0) return false;
     if (frames <= 1 || fstride < pitch) { frames = 1; fstride = pitch * (size_t)rows; }
     fstride = (fstride + 15) & ~(size_t)15;
     const cuuint64_t dims[3] = { (cuuint64_t)(pitch / 4), (cuuint64_t)rows, (cuuint64_t)frames };
     const cuuint64_t strides[2] = { (cuuint64_t)pitch, (cuuint64_t)fstride };
-    const cuuint32_t box[3] = { FS_TPW, (cuuint32_t)box_rows, 1 };
+    const cuuint32_t box[3] = { ORBX_TMA_BOX_WORDS, (cuuint32_t)box_rows, 1 };
     const cuuint32_t estr[3] = { 1, 1, 1 };
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride)
+// tensor maps of the current geometry: levels >= 1 are fixed per geometry, level 0 follows the caller's frames
+int orbx_ensure_tmaps(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride)
 {
     const FrameGeom &G = h->geo;
-    if (G.total_strips <= 0) return 0;
     if (!h->tmap_valid) {
         for (int l = 1; l < G.nlevels; l++)
             if (!encode_level(&h->tmap[l], h->d_pyr + G.lv[l].off, (size_t)G.lv[l].pitch, G.lv[l].h, h->pyr_slab, h->prm.max_batch, G.lv[l].hcell + 6)) return -1;
@@ -476,7 +452,15 @@ int launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, 
         if (!encode_level(&h->tmap[0], l0, l0_step, G.lv[0].h, l0_fstride, nframes, G.lv[0].hcell + 6)) return -1;
         h->tmap_l0 = l0; h->tmap_l0_step = l0_step; h->tmap_l0_fstride = l0_fstride; h->tmap_l0_frames = nframes;
     }
-    FastMaps M;
+    return 0;
+}
+
+int launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride)
+{
+    const FrameGeom &G = h->geo;
+    if (G.total_strips <= 0) return 0;
+    if (orbx_ensure_tmaps(h, nframes, l0, l0_step, l0_fstride) != 0) return -1;
+    LevelMaps M;
     memcpy(M.m, h->tmap, sizeof(M.m));
     FastParams P;
     P.cand = h->d_cand; P.cand_slab = G.cand_entries;

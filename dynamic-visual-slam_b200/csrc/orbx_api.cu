@@ -75,7 +75,7 @@ static void resize_table(int ssize, int dsize, bool horizontal, ResizeTab *out)
 
 // geometry for one input size; returns false when the reference itself is undefined for it
 static bool build_geometry(const orbx_handle *h, int w, int hgt, FrameGeom &G, std::vector<ResizeTab> *xt, std::vector<ResizeTab> *yt,
-                           std::vector<uint32_t> *strip_tab = nullptr)
+                           std::vector<uint32_t> *strip_tab = nullptr, std::vector<uint32_t> *blur_tab = nullptr)
 {
     memset(&G, 0, sizeof(G));
     const orbx_params &p = h->prm;
@@ -121,8 +121,11 @@ static bool build_geometry(const orbx_handle *h, int w, int hgt, FrameGeom &G, s
             if (nc <= 0) continue;
             strip_tab->push_back((uint32_t)l | ((uint32_t)nc << 4) | ((uint32_t)ci << 8) | ((uint32_t)cj0 << 20));
         }
-        g.blur_tx = (g.w + ORBX_BLUR_TW - 1) / ORBX_BLUR_TW; g.blur_ty = (g.h + 4 * ORBX_BLUR_H - 1) / (4 * ORBX_BLUR_H);
+        // blur tiles: 256 columns x hCell rows (the box of the level's tensor map is hCell + 6 rows); level:4 | column:12 | row:16
+        g.blur_tx = (g.w + ORBX_BLUR_TW - 1) / ORBX_BLUR_TW; g.blur_ty = (g.h + g.hcell - 1) / g.hcell;
         g.blur_first = tiles; tiles += g.blur_tx * g.blur_ty;
+        if (blur_tab) for (int ty = 0; ty < g.blur_ty; ty++) for (int tx = 0; tx < g.blur_tx; tx++)
+            blur_tab->push_back((uint32_t)l | ((uint32_t)tx << 4) | ((uint32_t)ty << 16));
         g.cand_cap = (int)align_up((size_t)std::max(4096, g.w * g.h / cdiv), 64);
         g.cand_off = coff; coff += (size_t)g.cand_cap;
         g.sel_cap = (int)align_up((size_t)std::max(g.N + 4, 4 * g.nini + 4), 8);
@@ -163,18 +166,19 @@ static orbx_status set_geometry(orbx_handle *h, int w, int hgt)
     if (h->geo.width == w && h->geo.height == hgt) return ORBX_OK;
     if (w > h->prm.max_width || hgt > h->prm.max_height) { h->err = "frame larger than max_width x max_height"; return ORBX_E_INVALID; }
     if (w > 4096 + 2 * ORBX_BORDER || hgt > 4096 + 2 * ORBX_BORDER) { h->err = "frame larger than 4128 px"; return ORBX_E_UNSUPPORTED; }
-    FrameGeom G; std::vector<ResizeTab> xt, yt; std::vector<uint32_t> strips;
-    if (!build_geometry(h, w, hgt, G, &xt, &yt, &strips)) { h->err = "unsupported frame geometry (aspect ratio gives 0 or > 64 quadtree roots, or a level vanishes)"; return ORBX_E_UNSUPPORTED; }
+    FrameGeom G; std::vector<ResizeTab> xt, yt; std::vector<uint32_t> strips, btiles;
+    if (!build_geometry(h, w, hgt, G, &xt, &yt, &strips, &btiles)) { h->err = "unsupported frame geometry (aspect ratio gives 0 or > 64 quadtree roots, or a level vanishes)"; return ORBX_E_UNSUPPORTED; }
     const size_t B = (size_t)h->prm.max_batch;
     if (G.pyr_bytes * B > h->pyr_cap || G.blur_bytes * B > h->blur_cap || G.cand_entries * B > h->cand_cap ||
         (size_t)G.sel_entries * B > h->sel_cap || (int)xt.size() > h->tab_cap || (int)yt.size() > h->tab_cap ||
-        G.sel_entries > h->max_kp || (int)strips.size() > h->strip_cap) { h->err = "frame geometry does not fit the arenas sized at create"; return ORBX_E_INVALID; }
+        G.sel_entries > h->max_kp || (int)strips.size() > h->strip_cap || (int)btiles.size() > h->blur_tile_cap) { h->err = "frame geometry does not fit the arenas sized at create"; return ORBX_E_INVALID; }
     G.total_strips = (int)strips.size();
     ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
     ORBX_CUDA(h, cudaMemcpy(h->d_geo, &G, sizeof(G), cudaMemcpyHostToDevice));
     if (!xt.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_xtab, xt.data(), xt.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
     if (!yt.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_ytab, yt.data(), yt.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
     if (!strips.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_strips, strips.data(), strips.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (!btiles.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_blur_tiles, btiles.data(), btiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     G.total_strips = (int)strips.size();
     h->geo = G; h->pyr_slab = G.pyr_bytes; h->blur_slab = G.blur_bytes; h->tmap_valid = false;
     return ORBX_OK;
@@ -186,7 +190,7 @@ extern "C" void orbx_destroy(orbx_handle *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
-    void *dev[] = { h->d_strips, h->d_prev_desc, h->d_prev_count, h->d_geo, h->d_xtab, h->d_ytab, h->d_pyr, h->d_blur, h->d_in, h->d_depth_in, h->d_cand, h->d_cand2, h->d_qtmp,
+    void *dev[] = { h->d_blur_tiles, h->d_strips, h->d_prev_desc, h->d_prev_count, h->d_geo, h->d_xtab, h->d_ytab, h->d_pyr, h->d_blur, h->d_in, h->d_depth_in, h->d_cand, h->d_cand2, h->d_qtmp,
                     h->d_owner, h->d_owner2, h->d_ncand, h->d_sel, h->d_nsel, h->d_kps_all, h->d_desc_all, h->d_count_all,
                     h->d_kps_out, h->d_desc_out, h->d_count_out, h->d_boxes, h->d_status, h->d_mpart, h->d_mq, h->d_mt, h->d_mout, h->d_mcount };
     for (void *p : dev) if (p) cudaFree(p);
@@ -255,6 +259,8 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     CREATE_CUDA(cudaMalloc(&h->d_geo, sizeof(FrameGeom)));
     h->strip_cap = G.total_cells + 64 * p.nlevels;
     CREATE_CUDA(cudaMalloc(&h->d_strips, sizeof(uint32_t) * h->strip_cap));
+    h->blur_tile_cap = G.total_blur_tiles + G.total_blur_tiles / 4 + 64 * p.nlevels;
+    CREATE_CUDA(cudaMalloc(&h->d_blur_tiles, sizeof(uint32_t) * h->blur_tile_cap));
     CREATE_CUDA(cudaMalloc(&h->d_xtab, sizeof(ResizeTab) * h->tab_cap));
     CREATE_CUDA(cudaMalloc(&h->d_ytab, sizeof(ResizeTab) * h->tab_cap));
     CREATE_CUDA(cudaMalloc(&h->d_pyr, h->pyr_cap));
@@ -340,7 +346,7 @@ static orbx_status run_pipeline(orbx_handle *h, int nframes, const uint8_t *l0, 
     for (int l = 1; l < nl; l++) launch_resize_level(h, l, nframes, l0, l0_step, l0_fstride);   // ComputePyramid
     if (launch_fast(h, nframes, l0, l0_step, l0_fstride) != 0) { h->err = "cuTensorMapEncodeTiled failed (frame base/step must be 16-byte aligned)"; return ORBX_E_CUDA; }   // cell FAST
     launch_quadtree(h, nframes);                                                                 // DistributeOctTree
-    launch_blur(h, nframes, l0, l0_step, l0_fstride);                                            // GaussianBlur per level
+    if (launch_blur(h, nframes, l0, l0_step, l0_fstride) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return ORBX_E_CUDA; }                // GaussianBlur per level
     const bool filtered = d_depth != nullptr || nboxes > 0;
     if (!filtered) launch_describe_to(h, nframes, l0, l0_step, l0_fstride, d_kps, d_desc, cap, d_counts);
     else {

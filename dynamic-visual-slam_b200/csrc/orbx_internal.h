@@ -13,8 +13,7 @@
 #define ORBX_CELL_W 35               // W, ORBextractor.cpp:783
 #define ORBX_HALF_PATCH 15
 #define ORBX_PATCH 31
-#define ORBX_BLUR_TW 128             // blur tile: 128 px x (4 warps x ORBX_BLUR_H rows) per CTA (k_blur.cu)
-#define ORBX_BLUR_H 35
+#define ORBX_BLUR_TW 256             // blur tile: 256 px x hCell rows per CTA (k_blur.cu)
 #define ORBX_FAST_MAX_W 240          // max detection width (px) of one FAST strip: 16-byte aligned TMA box of 288 bytes (k_fast.cu)
 
 // candidate / selected-keypoint packing: x:12 | y:12 | score:8, coordinates relative to the border box
@@ -85,6 +84,7 @@ struct orbx_handle {
     FrameGeom *d_geo;
     ResizeTab *d_xtab, *d_ytab; int tab_cap;
     uint32_t *d_strips; int strip_cap;   // FAST strip descriptors (k_fast.cu)
+    uint32_t *d_blur_tiles; int blur_tile_cap;   // blur tile descriptors (k_blur.cu)
     // TMA tensor maps of the pyramid levels (k_fast.cu): levels >= 1 depend on the geometry only, level 0 on the caller's frames
     CUtensorMap tmap[ORBX_MAX_LEVELS]; bool tmap_valid;
     const uint8_t *tmap_l0; size_t tmap_l0_step, tmap_l0_fstride; int tmap_l0_frames;
@@ -149,10 +149,11 @@ struct orbx_db {
 
 // ---- kernel launchers (one per .cu) ----
 void launch_resize_level(orbx_handle *h, int level, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
+int  orbx_ensure_tmaps(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
 int  launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);   // -1: TMA descriptor encode failed
 void launch_quadtree(orbx_handle *h, int nframes);
 void launch_quadtree_geo(orbx_handle *h, const FrameGeom *d_geo, int nlevels, int nframes, int node_cap, size_t cand_slab, int sel_slab);
-void launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
+int  launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
 void launch_describe_to(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride,
                         orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts);
 void upload_umax(const int *umax);
