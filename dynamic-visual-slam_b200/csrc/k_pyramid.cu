@@ -1,115 +1,122 @@
-// k_pyramid.cu — 8-level scale-1.2 image pyramid, fixed-point bilinear (cv::resize INTER_LINEAR, CV_8UC1).
-// Replaces ORBextractor::ComputePyramid (reference ORBextractor.cpp:1169-1194; resize call :1182).
-// Arithmetic: SURVEY.md App. A.1 — 11-bit coefficients, horizontal pass in int32, vertical pass
-//   out = (((b0*(R0>>4))>>16) + ((b1*(R1>>4))>>16) + 2) >> 2.
-// The coefficient tables are built on the host exactly as OpenCV builds them (orbx_api.cu) so the
-// kernel is pure integer.  The 19-px REFLECT_101 border of the reference is never read downstream
+// k_pyramid.cu — ORBextractor::ComputePyramid (reference ORBextractor.cpp:1169-1194).
+// Level l = cv::resize(level l-1, INTER_LINEAR), chained level to level.  Arithmetic restated from
+// OpenCV's 8-bit fixed-point bilinear path: 11-bit horizontal/vertical
+// coefficients (host-built tables, orbx_api.cu), out = (((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2) >> 2;
+// the kernel is pure integer.  The 19-px REFLECT_101 border of the reference is never read downstream
 //  and is not materialised.
 //
-// HBM-bound stage.  One CTA produces a 128 x 64 output tile: the source window the tile needs
-// (about 1.2x larger per axis) is staged in shared memory with aligned 128-bit loads issued back to
-// back (memory-level parallelism), then each thread sweeps 8 output rows for 4 adjacent columns with
-// its four horizontal table entries in registers; the horizontal interpolation of a source row is
-// reused by the next output row when they share it (5 rows out of 6 at scale 1.2).  Results leave as
-// one 32-bit store per thread and row (rows are 128-byte pitched).
+// HBM-bound stage, one launch per level.  A CTA produces an rz_tw x rz_th output tile (192 x 64 at scale 1.2): the
+// source window it needs (about 1.2x larger per axis, 16-byte aligned start) arrives by ONE TMA load into shared
+// memory, the tile's vertical table (source row offsets + coefficients, clamped) is staged beside it, and each
+// thread owns 4 adjacent output columns — their horizontal table entries live in registers — and walks down a
+// quarter of the tile's rows.  The horizontal interpolation of a source row is reused by the next output row
+// when they share it (5 rows out of 6 at scale 1.2).  Results leave as one 32-bit coalesced store per thread and
+// row (rows are 128-byte pitched).
 #include "orbx_internal.h"
+#include "orbx_tma.h"
+#include <algorithm>
+#include <cstring>
 
-#define RZ_TW 128
-#define RZ_TH 64
-#define RZ_ROWS_PER_WARP 8
+#define RZ_GROUPS 48                 // 4-pixel column groups per tile row (rz_tw <= 192)
+#define RZ_BANDS 4
+#define RZ_THREADS (RZ_GROUPS * RZ_BANDS)
+#define RZ_MAX_TH 64
 
 struct ResizeParams {
-    const uint8_t *src; size_t src_step, src_fstride;
     uint8_t *dst; size_t dst_step, dst_fstride;
     int sw, sh, dw, dh;
     const ResizeTab *xtab, *ytab;
-    int smem_pitch, smem_rows;
+    int tw, th;                      // output tile
+    int src_level;
 };
 
-__global__ void __launch_bounds__(256) k_resize_linear(ResizeParams P)
+__global__ void __launch_bounds__(RZ_THREADS) k_resize_linear(const __grid_constant__ LevelMaps M, ResizeParams P)
 {
-    extern __shared__ __align__(16) uint8_t s_src[];
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int4 s_rt[RZ_MAX_TH];                                              // per output row: smem offsets of its two source rows, b0, b1
+    uint8_t *s_img = s_raw + ((128u - (smem_u32(s_raw) & 127u)) & 127u);          // TMA destination: 128-byte aligned
     const int f = blockIdx.z;
-    const int x0 = blockIdx.x * RZ_TW, y0 = blockIdx.y * RZ_TH;
-    const int x1 = min(x0 + RZ_TW, P.dw) - 1, y1 = min(y0 + RZ_TH, P.dh) - 1;
-    // source window of this tile
-    const int sxlo = P.xtab[x0].ofs, sxhi = min(P.xtab[x1].ofs + 1, P.sw - 1);
-    const int sylo = max(0, min(P.ytab[y0].ofs, P.sh - 1)), syhi = max(0, min(P.ytab[y1].ofs + 1, P.sh - 1));
-    const int abase = sxlo & ~15;
-    const int vecs = (sxhi - abase + 16) >> 4;
-    const int rows = syhi - sylo + 1;
-    const uint8_t *S = P.src + (size_t)f * P.src_fstride + (size_t)sylo * P.src_step + abase;
-    const int pitch = P.smem_pitch;
-    for (int i = threadIdx.x; i < rows * 16; i += 256) {
-        const int r = i >> 4;
-        for (int vi = i & 15; vi < vecs; vi += 16)
-            reinterpret_cast<uint4 *>(s_src + r * pitch)[vi] = __ldg(reinterpret_cast<const uint4 *>(S + (size_t)r * P.src_step) + vi);
+    const int x0 = blockIdx.x * P.tw, y0 = blockIdx.y * P.th;
+    const int x1 = min(x0 + P.tw, P.dw) - 1, y1 = min(y0 + P.th, P.dh) - 1;
+    // source window of this tile: columns from a 16-byte boundary, rows from the first source row
+    const int abase = __ldg(&P.xtab[x0].ofs) & ~15;
+    const int sylo = max(0, min(__ldg(&P.ytab[y0].ofs), P.sh - 1));
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&s_bar, (uint32_t)(ORBX_RZ_BOX_ROWS * ORBX_TMA_BOX_BYTES));
+        tma_load_3d(s_img, &M.m[P.src_level], abase >> 2, sylo, f, &s_bar);
     }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x4 = x0 + lane * 4;
-    if (x4 >= P.dw) return;
-    // horizontal table entries of the 4 columns (offsets relative to the staged window)
-    int o0[4], o1[4], a0[4], a1[4];
+    for (int r = threadIdx.x; r <= y1 - y0; r += RZ_THREADS) {
+        const ResizeTab ty = P.ytab[y0 + r];
+        const int sy0 = max(0, min(ty.ofs, P.sh - 1)), sy1 = max(0, min(ty.ofs + 1, P.sh - 1));
+        s_rt[r] = make_int4((sy0 - sylo) * ORBX_TMA_BOX_BYTES, (sy1 - sylo) * ORBX_TMA_BOX_BYTES, ty.a0, ty.a1);
+    }
+    const int grp = threadIdx.x % RZ_GROUPS, band = threadIdx.x / RZ_GROUPS;
+    const int x4 = x0 + 4 * grp;
+    // horizontal table entries of the 4 columns: byte offsets inside the staged window (the right neighbour of the last
+    // source column has coefficient 0, App. A.1) and the two coefficients
+    int o[4], a0[4], a1[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const ResizeTab tx = P.xtab[min(x4 + i, P.dw - 1)];
-        o0[i] = tx.ofs - abase;
-        o1[i] = min(tx.ofs + 1, P.sw - 1) - abase;
-        a0[i] = tx.a0; a1[i] = tx.a1;
+        o[i] = tx.ofs - abase; a0[i] = tx.a0; a1[i] = tx.a1;
     }
-    int cached_row = -1000000, hc[4] = { 0, 0, 0, 0 };
-    uint8_t *D = P.dst + (size_t)f * P.dst_fstride + x4;
-    for (int k = 0; k < RZ_ROWS_PER_WARP; k++) {
-        const int y = y0 + warp * RZ_ROWS_PER_WARP + k;
-        if (y > y1) break;
-        const ResizeTab ty = P.ytab[y];
-        const int sy0 = max(0, min(ty.ofs, P.sh - 1)), sy1 = max(0, min(ty.ofs + 1, P.sh - 1));
-        int h0[4], h1[4];
-        if (sy0 == cached_row) {
+    __syncthreads();                                                                 // barrier initialised, row table staged
+    mbar_wait(&s_bar, 0);
+    if (x4 > x1) return;
+    const int nrows = y1 - y0 + 1, RB = (nrows + RZ_BANDS - 1) / RZ_BANDS;
+    const int rb = band * RB, re = min(nrows, rb + RB);
+    uint8_t *D = P.dst + (size_t)f * P.dst_fstride + (size_t)(y0 + rb) * P.dst_step + x4;
+    int prev_off = -1, tp[4] = { 0, 0, 0, 0 };                                       // (h >> 4) of the last source row interpolated
+    for (int r = rb; r < re; r++, D += P.dst_step) {
+        const int4 e = s_rt[r];
+        int t0[4], t1[4];
+        if (e.x == prev_off) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) h0[i] = hc[i];
+            for (int i = 0; i < 4; i++) t0[i] = tp[i];
         } else {
-            const uint8_t *r0 = s_src + (sy0 - sylo) * pitch;
+            const uint8_t *q = s_img + e.x;
 #pragma unroll
-            for (int i = 0; i < 4; i++) h0[i] = (int)r0[o0[i]] * a0[i] + (int)r0[o1[i]] * a1[i];
+            for (int i = 0; i < 4; i++) t0[i] = ((int)q[o[i]] * a0[i] + (int)q[o[i] + 1] * a1[i]) >> 4;
         }
-        if (sy1 == sy0) {
+        if (e.y == e.x) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) h1[i] = h0[i];
+            for (int i = 0; i < 4; i++) t1[i] = t0[i];
         } else {
-            const uint8_t *r1 = s_src + (sy1 - sylo) * pitch;
+            const uint8_t *q = s_img + e.y;
 #pragma unroll
-            for (int i = 0; i < 4; i++) h1[i] = (int)r1[o0[i]] * a0[i] + (int)r1[o1[i]] * a1[i];
+            for (int i = 0; i < 4; i++) t1[i] = ((int)q[o[i]] * a0[i] + (int)q[o[i] + 1] * a1[i]) >> 4;
         }
-        cached_row = sy1;
-        const int b0 = ty.a0, b1 = ty.a1;
-        uint32_t packed = 0;
+        prev_off = e.y;
+        uint32_t v[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            hc[i] = h1[i];
-            int v = (((b0 * (h0[i] >> 4)) >> 16) + ((b1 * (h1[i] >> 4)) >> 16) + 2) >> 2;
-            v = v < 0 ? 0 : (v > 255 ? 255 : v);
-            packed |= (uint32_t)v << (8 * i);
+            tp[i] = t1[i];
+            v[i] = (uint32_t)min((((e.z * t0[i]) >> 16) + ((e.w * t1[i]) >> 16) + 2) >> 2, 255);
         }
-        *reinterpret_cast<uint32_t *>(D + (size_t)y * P.dst_step) = packed;     // pitch is a multiple of 128: the word is in-bounds
+        *reinterpret_cast<uint32_t *>(D) = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);   // pitch % 128 == 0: in-bounds
     }
 }
 
-void launch_resize_level(orbx_handle *h, int level, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride)
+int launch_resize_level(orbx_handle *h, int level, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride)
 {
     const LevelGeom &gs = h->geo.lv[level - 1], &gd = h->geo.lv[level];
+    if (orbx_ensure_tmaps(h, nframes, l0, l0_step, l0_fstride) != 0) return -1;
+    LevelMaps M;
+    memcpy(M.m, h->tmap_rz, sizeof(M.m));
     ResizeParams P;
-    if (level == 1) { P.src = l0; P.src_step = l0_step; P.src_fstride = l0_fstride; }
-    else { P.src = h->d_pyr + gs.off; P.src_step = (size_t)gs.pitch; P.src_fstride = h->pyr_slab; }
     P.dst = h->d_pyr + gd.off; P.dst_step = (size_t)gd.pitch; P.dst_fstride = h->pyr_slab;
     P.sw = gs.w; P.sh = gs.h; P.dw = gd.w; P.dh = gd.h;
     P.xtab = h->d_xtab + gd.xtab_off; P.ytab = h->d_ytab + gd.ytab_off;
-    P.smem_pitch = h->geo.rz_pitch; P.smem_rows = h->geo.rz_rows;
-    const size_t smem = (size_t)P.smem_pitch * P.smem_rows;
-    static size_t configured = 0;
-    if (smem > configured) { cudaFuncSetAttribute(k_resize_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
-    dim3 grid((gd.w + RZ_TW - 1) / RZ_TW, (gd.h + RZ_TH - 1) / RZ_TH, nframes);
+    P.tw = h->geo.rz_tw; P.th = h->geo.rz_th; P.src_level = level - 1;
+    const size_t smem = 128 + (size_t)ORBX_RZ_BOX_ROWS * ORBX_TMA_BOX_BYTES;
+    static bool configured = false;
+    if (!configured) { cudaFuncSetAttribute(k_resize_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+    dim3 grid((gd.w + P.tw - 1) / P.tw, (gd.h + P.th - 1) / P.th, nframes);
     ProfScope ps(h, ORBX_K_RESIZE);
-    k_resize_linear<<<grid, 256, smem, h->stream>>>(P);
+    k_resize_linear<<<grid, RZ_THREADS, smem, h->stream>>>(M, P);
+    return 0;
 }

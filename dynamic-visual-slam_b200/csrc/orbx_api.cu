@@ -138,24 +138,27 @@ static bool build_geometry(const orbx_handle *h, int w, int hgt, FrameGeom &G, s
             resize_table(G.lv[l - 1].h, g.h, false, yt->data() + g.ytab_off);
         }
     }
-    // source window of a 128 x 64 resize tile, maximised over levels and tiles (k_pyramid.cu)
-    int rzp = 16, rzr = 1;
-    if (xt && yt) for (int l = 1; l < p.nlevels; l++) {
-        const LevelGeom &g = G.lv[l];
-        const ResizeTab *tx = xt->data() + g.xtab_off, *ty = yt->data() + g.ytab_off;
-        for (int x0 = 0; x0 < g.w; x0 += 128) {
-            const int x1 = std::min(x0 + 128, g.w) - 1;
-            const int lo = tx[x0].ofs & ~15, hi = std::min(tx[x1].ofs + 1, G.lv[l - 1].w - 1);
-            rzp = std::max(rzp, ((hi - lo + 16) >> 4) * 16);
+    // output tile of the resize kernel (k_pyramid.cu): the largest (multiple of 16) x (multiple of 8) tile, at most 192 x 64,
+    // whose source window fits the 288-byte x ORBX_RZ_BOX_ROWS TMA box at every level
+    int rtw = 192, rth = 64;
+    if (xt && yt) for (bool fits = false; !fits;) {
+        fits = true;
+        for (int l = 1; l < p.nlevels && fits; l++) {
+            const LevelGeom &g = G.lv[l];
+            const ResizeTab *tx = xt->data() + g.xtab_off, *ty = yt->data() + g.ytab_off;
+            for (int x0 = 0; x0 < g.w && fits; x0 += rtw) {
+                const int x1 = std::min(x0 + rtw, g.w) - 1;
+                if (tx[x1].ofs + 1 - (tx[x0].ofs & ~15) >= 288) fits = false;
+            }
+            for (int y0 = 0; y0 < g.h && fits; y0 += rth) {
+                const int y1 = std::min(y0 + rth, g.h) - 1;
+                const int lo = std::max(0, std::min(ty[y0].ofs, G.lv[l - 1].h - 1)), hi = std::max(0, std::min(ty[y1].ofs + 1, G.lv[l - 1].h - 1));
+                if (hi - lo + 1 > 80) fits = false;
+            }
         }
-        for (int y0 = 0; y0 < g.h; y0 += 64) {
-            const int y1 = std::min(y0 + 64, g.h) - 1;
-            const int lo = std::max(0, std::min(ty[y0].ofs, G.lv[l - 1].h - 1)), hi = std::max(0, std::min(ty[y1].ofs + 1, G.lv[l - 1].h - 1));
-            rzr = std::max(rzr, hi - lo + 1);
-        }
+        if (!fits) { if (rtw > 16) rtw -= 16; if (rth > 8) rth -= 8; if (rtw <= 16 && rth <= 8) return false; }
     }
-    G.rz_pitch = rzp; G.rz_rows = rzr;
-    if ((size_t)rzp * rzr > 200 * 1024) return false;
+    G.rz_tw = rtw; G.rz_th = rth;
     G.total_cells = cells; G.total_blur_tiles = tiles; G.total_strips = std::max(strips, 1); G.max_hcell = max_hcell;
     G.pyr_bytes = std::max<size_t>(off, 256); G.blur_bytes = boff; G.cand_entries = coff; G.sel_entries = soff; G.node_cap_max = ncmax;
     return true;
@@ -343,7 +346,8 @@ static orbx_status run_pipeline(orbx_handle *h, int nframes, const uint8_t *l0, 
 {
     const int nl = h->geo.nlevels;
     ORBX_CUDA(h, cudaMemsetAsync(h->d_ncand, 0, (size_t)nframes * nl * sizeof(int32_t), h->stream));
-    for (int l = 1; l < nl; l++) launch_resize_level(h, l, nframes, l0, l0_step, l0_fstride);   // ComputePyramid
+    for (int l = 1; l < nl; l++)                                                                 // ComputePyramid
+        if (launch_resize_level(h, l, nframes, l0, l0_step, l0_fstride) != 0) { h->err = "cuTensorMapEncodeTiled failed (frame base/step must be 16-byte aligned)"; return ORBX_E_CUDA; }
     if (launch_fast(h, nframes, l0, l0_step, l0_fstride) != 0) { h->err = "cuTensorMapEncodeTiled failed (frame base/step must be 16-byte aligned)"; return ORBX_E_CUDA; }   // cell FAST
     launch_quadtree(h, nframes);                                                                 // DistributeOctTree
     if (launch_blur(h, nframes, l0, l0_step, l0_fstride) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return ORBX_E_CUDA; }                // GaussianBlur per level

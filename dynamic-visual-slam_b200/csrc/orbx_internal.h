@@ -51,7 +51,7 @@ struct FrameGeom {
     int nlevels;
     int width, height;
     int total_cells, total_blur_tiles, total_strips, max_hcell;
-    int rz_pitch, rz_rows;   // shared-memory window of the resize kernel (max over levels and tiles)
+    int rz_tw, rz_th;        // output tile of the resize kernel: its source window fits the 288-byte x 80-row TMA box at every level
     size_t pyr_bytes;        // per-frame pyramid slab size (levels 1..)
     size_t blur_bytes;       // per-frame blurred slab size (levels 0..)
     size_t cand_entries;     // per-frame candidate slab entries
@@ -86,7 +86,8 @@ struct orbx_handle {
     uint32_t *d_strips; int strip_cap;   // FAST strip descriptors (k_fast.cu)
     uint32_t *d_blur_tiles; int blur_tile_cap;   // blur tile descriptors (k_blur.cu)
     // TMA tensor maps of the pyramid levels (k_fast.cu): levels >= 1 depend on the geometry only, level 0 on the caller's frames
-    CUtensorMap tmap[ORBX_MAX_LEVELS]; bool tmap_valid;
+    CUtensorMap tmap[ORBX_MAX_LEVELS]; bool tmap_valid;      // box rows = hCell + 6 (FAST strips, blur tiles)
+    CUtensorMap tmap_rz[ORBX_MAX_LEVELS];                    // box rows = ORBX_RZ_BOX_ROWS (resize source windows)
     const uint8_t *tmap_l0; size_t tmap_l0_step, tmap_l0_fstride; int tmap_l0_frames;
     int fast_grid_cap;                   // resident CTAs of the persistent FAST kernel
     // arenas, sized for max_width x max_height x max_batch
@@ -148,7 +149,7 @@ struct orbx_db {
 #define ORBX_DS_KP_OVERFLOW   4
 
 // ---- kernel launchers (one per .cu) ----
-void launch_resize_level(orbx_handle *h, int level, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
+int  launch_resize_level(orbx_handle *h, int level, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
 int  orbx_ensure_tmaps(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
 int  launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);   // -1: TMA descriptor encode failed
 void launch_quadtree(orbx_handle *h, int nframes);

@@ -9,6 +9,7 @@
 
 #define ORBX_TMA_BOX_WORDS 72            // 288 bytes
 #define ORBX_TMA_BOX_BYTES (ORBX_TMA_BOX_WORDS * 4)
+#define ORBX_RZ_BOX_ROWS 80               // source rows staged per resize tile (k_pyramid.cu)
 
 struct LevelMaps { CUtensorMap m[ORBX_MAX_LEVELS]; };
 
