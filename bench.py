@@ -40,6 +40,20 @@ ALG_BYTES = {
 }
 
 
+def ncu_traffic(kernel, frames, launches_per_step):
+    """DRAM bytes per launch of `kernel` from the newest committed ncu --set full summary (profiles/*_traffic.json), scaled
+    from the capture's batch to this run's; None when no capture is committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None, None
+    try:
+        t = json.load(open(files[-1])).get(kernel)
+        return (t["dram_bytes_per_frame_per_step"] * frames / max(1.0, launches_per_step), os.path.basename(files[-1])) if t else (None, None)
+    except Exception:
+        return None, None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -241,8 +255,9 @@ def main():
     dom = max(dense, key=lambda n: kernels[n]["ms_per_step"]) if dense else None
     roofline = None
     if dom:
+        traffic, traffic_src = ncu_traffic(dom, B, kernels[dom]["launches_per_step"])
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
-                    "frac": kernels[dom]["frac_of_hbm"], "traffic": None, "peak_source": peak_src,
+                    "frac": kernels[dom]["frac_of_hbm"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": ALG_BYTES[dom] * B / max(1.0, kernels[dom]["launches_per_step"]),
                     "dominant_overall": max(kernels, key=lambda n: kernels[n]["ms_per_step"])}
 
