@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(BL_THREADS) k_blur7(const __grid_constant__ Le
     }
 }
 
-int launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride)
+int launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride, cudaStream_t st)
 {
     if (h->geo.total_blur_tiles <= 0) return 0;
     if (orbx_ensure_tmaps(h, nframes, l0, l0_step, l0_fstride) != 0) return -1;
@@ -130,7 +130,7 @@ int launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, 
     static size_t configured = 0;
     if (smem > configured) { cudaFuncSetAttribute(k_blur7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
     dim3 grid(h->geo.total_blur_tiles, nframes);
-    ProfScope ps(h, ORBX_K_BLUR);
-    k_blur7<<<grid, BL_THREADS, smem, h->stream>>>(M, P, h->d_geo);
+    ProfScope ps(h, ORBX_K_BLUR, st);
+    k_blur7<<<grid, BL_THREADS, smem, st>>>(M, P, h->d_geo);
     return 0;
 }

@@ -44,8 +44,10 @@ __global__ void __launch_bounds__(MT_THREADS) k_match_partial(MatchParams P)
     const int nt = P.nt_arr ? P.nt_arr[ts] : P.nt_imm;
     const int qi = blockIdx.x * MT_THREADS + threadIdx.x;
     if (blockIdx.x * MT_THREADS >= nq) return;
-    const int r0 = blockIdx.y * P.rows_per_split;
-    const int r1 = min(nt, r0 + P.rows_per_split);
+    // the train set is cut into gridDim.y equal parts of the problem's OWN row count (multiple of 8 rows)
+    const int rps = P.nt_arr ? ((((nt + P.nsplit - 1) / P.nsplit) + 7) & ~7) : P.rows_per_split;
+    const int r0 = blockIdx.y * rps;
+    const int r1 = min(nt, r0 + rps);
     const uint8_t *qbase = P.q + (size_t)qs * P.q_stride;
     const uint4 *tbase = reinterpret_cast<const uint4 *>(P.t + (size_t)ts * P.t_stride);
     uint32_t q[8];
@@ -166,9 +168,9 @@ __global__ void __launch_bounds__(256) k_match_epilogue(MatchEpiParams P)
 static int pick_split(orbx_handle *h, int nq_max, int nt_max, int nproblems, int *rows_per_split)
 {
     const int qtiles = (nq_max + MT_THREADS - 1) / MT_THREADS;
-    const long ctas_wanted = (long)h->sm_count * 8;
+    const long ctas_wanted = (long)h->sm_count * 24;
     long split = (ctas_wanted + (long)qtiles * nproblems - 1) / ((long)qtiles * nproblems);
-    const long max_split = (nt_max + MT_TILE - 1) / MT_TILE;
+    const long max_split = (nt_max + 63) / 64;
     if (split > max_split) split = max_split;
     if (split < 1) split = 1;
     long rps = (nt_max + split - 1) / split;

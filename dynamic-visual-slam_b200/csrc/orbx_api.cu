@@ -204,6 +204,9 @@ extern "C" void orbx_destroy(orbx_handle *h)
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->out_stream) cudaStreamDestroy(h->out_stream);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (int i = 0; i < 2; i++) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]); if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]); }
     delete h;
 }
@@ -234,6 +237,9 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CREATE_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CREATE_CUDA(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) {
         CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
         CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
@@ -321,6 +327,12 @@ extern "C" orbx_status orbx_sync(orbx_handle *h)
     cudaSetDevice(h->device);
     return check_device_status(h);
 }
+extern "C" orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t value)
+{
+    if (!h) return ORBX_E_INVALID;
+    if (option == ORBX_OPT_SERIAL) { h->opt_serial = value ? 1 : 0; return ORBX_OK; }
+    h->err = "unknown option"; return ORBX_E_INVALID;
+}
 extern "C" void *orbx_stream(orbx_handle *h) { return h ? (void *)h->stream : nullptr; }
 extern "C" int64_t orbx_launch_count(const orbx_handle *h) { return h ? h->launches : 0; }
 
@@ -348,9 +360,18 @@ static orbx_status run_pipeline(orbx_handle *h, int nframes, const uint8_t *l0, 
     ORBX_CUDA(h, cudaMemsetAsync(h->d_ncand, 0, (size_t)nframes * nl * sizeof(int32_t), h->stream));
     for (int l = 1; l < nl; l++)                                                                 // ComputePyramid
         if (launch_resize_level(h, l, nframes, l0, l0_step, l0_fstride) != 0) { h->err = "cuTensorMapEncodeTiled failed (frame base/step must be 16-byte aligned)"; return ORBX_E_CUDA; }
+    // the blur needs only the pyramid, the quadtree only the FAST candidates: the (throughput-bound) blur runs on the aux
+    // stream beside FAST and the (latency-bound, low-occupancy) quadtree
+    cudaStream_t bst = h->opt_serial ? h->stream : h->aux_stream;
+    if (!h->opt_serial) {
+        ORBX_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+        ORBX_CUDA(h, cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+    }
     if (launch_fast(h, nframes, l0, l0_step, l0_fstride) != 0) { h->err = "cuTensorMapEncodeTiled failed (frame base/step must be 16-byte aligned)"; return ORBX_E_CUDA; }   // cell FAST
+    if (launch_blur(h, nframes, l0, l0_step, l0_fstride, bst) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return ORBX_E_CUDA; }   // GaussianBlur per level
+    if (!h->opt_serial) ORBX_CUDA(h, cudaEventRecord(h->ev_join, h->aux_stream));
     launch_quadtree(h, nframes);                                                                 // DistributeOctTree
-    if (launch_blur(h, nframes, l0, l0_step, l0_fstride) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return ORBX_E_CUDA; }                // GaussianBlur per level
+    if (!h->opt_serial) ORBX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     const bool filtered = d_depth != nullptr || nboxes > 0;
     if (!filtered) launch_describe_to(h, nframes, l0, l0_step, l0_fstride, d_kps, d_desc, cap, d_counts);
     else {

@@ -68,7 +68,9 @@ struct ResizeTab { int32_t ofs; int16_t a0, a1; };   // 8 bytes
 struct orbx_handle {
     orbx_params prm;
     int device;
-    cudaStream_t stream, copy_stream, out_stream;
+    cudaStream_t stream, copy_stream, out_stream, aux_stream;   // aux: blur runs beside FAST + quadtree
+    cudaEvent_t ev_fork, ev_join;
+    int opt_serial;
     cudaEvent_t ev_a, ev_b;
     cudaEvent_t ev_in[2], ev_comp[2], ev_out[2];   // host-batch pipeline: input slot filled / kernels done / outputs copied
     int chunk;                                      // frames per pipeline chunk of the host-buffer batch calls
@@ -124,13 +126,13 @@ struct orbx_handle {
 };
 
 struct ProfScope {
-    orbx_handle *h; int idx;
-    ProfScope(orbx_handle *hh, int id) : h(hh), idx(-1) {
+    orbx_handle *h; int idx; cudaStream_t st;
+    ProfScope(orbx_handle *hh, int id, cudaStream_t s = nullptr) : h(hh), idx(-1), st(s ? s : hh->stream) {
         if (h->prof_on && (size_t)(2 * h->prof_n + 1) < h->prof_ev.size()) {
-            idx = h->prof_n++; h->prof_id[idx] = id; cudaEventRecord(h->prof_ev[2 * idx], h->stream);
+            idx = h->prof_n++; h->prof_id[idx] = id; cudaEventRecord(h->prof_ev[2 * idx], st);
         }
     }
-    ~ProfScope() { if (idx >= 0) cudaEventRecord(h->prof_ev[2 * idx + 1], h->stream); h->launches++; }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(h->prof_ev[2 * idx + 1], st); h->launches++; }
 };
 
 struct orbx_db {
@@ -154,7 +156,7 @@ int  orbx_ensure_tmaps(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0
 int  launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);   // -1: TMA descriptor encode failed
 void launch_quadtree(orbx_handle *h, int nframes);
 void launch_quadtree_geo(orbx_handle *h, const FrameGeom *d_geo, int nlevels, int nframes, int node_cap, size_t cand_slab, int sel_slab);
-int  launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
+int  launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride, cudaStream_t st);
 void launch_describe_to(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride,
                         orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts);
 void upload_umax(const int *umax);

@@ -62,6 +62,7 @@ def load():
         "orbx_last_error": (ct.c_char_p, [vp]),
         "orbx_version": (ct.c_char_p, []),
         "orbx_sync": (i32, [vp]),
+        "orbx_set_option": (i32, [vp, i32, i32]),
         "orbx_stream": (vp, [vp]),
         "orbx_get_levels": (i32, [vp]),
         "orbx_get_scale_factor": (f32, [vp]),
@@ -200,6 +201,10 @@ class ORBextractor:
 
     def sync(self):
         self._check(self.L.orbx_sync(self._h))
+
+    def set_serial(self, on=True):
+        """ORBX_OPT_SERIAL: one stream, kernels in order (isolated per-kernel timings) instead of the overlapped schedule."""
+        self._check(self.L.orbx_set_option(self._h, 1, 1 if on else 0))
 
     @property
     def stream(self):

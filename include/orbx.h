@@ -208,6 +208,12 @@ orbx_status orbx_synth_depth_device(orbx_handle *h, uint32_t seed, int32_t first
                                     int32_t width, int32_t height, uint16_t *d_out, size_t step_bytes, size_t frame_stride_bytes);
 orbx_status orbx_synth_descriptors_device(orbx_handle *h, uint32_t seed, uint64_t first_row, int64_t nrows, uint8_t *d_out);
 
+/* ---- options ----
+ * ORBX_OPT_SERIAL: 1 = launch every kernel of a step on the handle's one stream, in order (per-kernel event timings are
+ * then isolated, as the roofline accounting wants); 0 (default) = the blur runs on a second stream beside FAST + quadtree. */
+#define ORBX_OPT_SERIAL 1
+orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t value);
+
 /* ---- utilities ---- */
 void *orbx_alloc_pinned(size_t bytes);
 void  orbx_free_pinned(void *p);
