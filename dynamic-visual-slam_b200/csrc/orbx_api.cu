@@ -255,8 +255,9 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     }
     const size_t B = (size_t)p.max_batch;
     // host-buffer calls are pipelined in chunks of `chunk` frames over two input and two output slots
-    h->chunk = p.reserved_[0] > 0 ? std::min(p.reserved_[0], p.max_batch) : std::max(1, std::min(32, p.max_batch / 8));
-    const size_t S = std::max(B, (size_t)2 * h->chunk);          // frames held by the staging arenas
+    h->chunk = p.reserved_[0] > 0 ? std::min(p.reserved_[0], p.max_batch) : std::max(1, std::min(32, p.max_batch / 4));
+    h->seq = 0; h->pending[0].active = h->pending[1].active = false;
+    const size_t S = 2 * B;                                       // the staging arenas hold two slots of max_batch frames
     // arenas are sized for the max geometry with 12% headroom so that smaller frames with unlucky padding still fit
     h->pyr_cap = (G.pyr_bytes + G.pyr_bytes / 8 + 4096) * B; h->blur_cap = (G.blur_bytes + G.blur_bytes / 8 + 4096) * B;
     h->cand_cap = (G.cand_entries + G.cand_entries / 8 + 4096 * p.nlevels) * B;
@@ -302,6 +303,7 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     h->h_out_bytes = B * ((size_t)h->max_kp * (sizeof(orbx_keypoint) + ORBX_DESC_BYTES) + 64);
     CREATE_CUDA(cudaMallocHost(&h->h_out, h->h_out_bytes));
     CREATE_CUDA(cudaMallocHost(&h->h_status, 64));
+    memset(h->h_status, 0, 64);
     orbx_status st = set_geometry(h, p.max_width, p.max_height);
     if (st != ORBX_OK) { g_create_err = h->err; orbx_destroy(h); return st; }
     *out = h;
@@ -408,6 +410,7 @@ extern "C" orbx_status orbx_extract_filtered(orbx_handle *h, const uint8_t *gray
     if (n_out) *n_out = 0;
     if (!gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }        // ORBextractor.cpp:1090-1091
     if (!kps || !desc || !n_out || cap < 0 || step < (size_t)width || nboxes < 0 || (nboxes > 0 && !boxes)) { h->err = "bad arguments"; return ORBX_E_INVALID; }
+    if (h->pending[0].active || h->pending[1].active) { h->err = "an asynchronous batch is outstanding: call orbx_batch_wait first"; return ORBX_E_INVALID; }
     orbx_status st = set_geometry(h, width, height);
     if (st != ORBX_OK) return st;
     const size_t pitch = align_up((size_t)width, 128), dpitch = align_up((size_t)width * 2, 128);
@@ -509,86 +512,164 @@ static const void *mapped_device_view(const void *host)
     return a.devicePointer;
 }
 
-// Host-buffer batch driver shared by orbx_extract_batch and orbx_track_batch.  The frames are cut into chunks of
-// h->chunk frames and pipelined over three streams with two input and two output slots:
-//     copy stream : H2D of chunk i+1          (gray; depth only if it is pageable)
-//     main stream : kernels of chunk i
-//     out stream  : D2H of chunk i-1          (counts, keypoints, descriptors, matches)
-// Depth maps in pinned host memory are NOT copied: the post-selection depth filter gathers its ~1000 samples per
-// frame straight from the mapped host buffer (one 32-byte PCIe read each instead of 1.8 MB per frame).
-static orbx_status host_batch(orbx_handle *h, bool track, const uint8_t *gray, int nframes, int width, int height, size_t step,
-                              const uint16_t *depth, size_t dstep, orbx_keypoint *kps, uint8_t *desc, int cap, int32_t *counts,
-                              orbx_dmatch *matches, int32_t *mcounts, float max_dist)
+// Host-buffer batch driver.  Work is enqueued in CHUNKS of at most max_batch frames; a chunk owns one of two staging slots
+// (input frames, output keypoints / descriptors / matches) and flows over three streams:
+//     copy stream : H2D of the chunk's frames      (gray; depth only if it is pageable)
+//     main stream : its kernels
+//     out stream  : D2H of its results             (counts, keypoints, descriptors, matches, device status word)
+// so the H2D of chunk i+1 and the D2H of chunk i-1 run under the kernels of chunk i.  The synchronous calls cut their frames
+// into chunks of h->chunk frames; the *_submit / orbx_batch_wait pair enqueues one chunk per call and lets the CALLER keep two
+// batches in flight (full-batch kernel efficiency, copies hidden).
+// Depth maps in pinned host memory are NOT copied: the post-selection depth filter gathers its ~1000 samples per frame
+// straight from the mapped host buffer (one 32-byte PCIe read each instead of 1.8 MB per frame).
+struct BatchArgs {
+    bool track; const uint8_t *gray; int width, height; size_t step; const uint16_t *depth; size_t dstep;
+    orbx_keypoint *kps; uint8_t *desc; int cap; int32_t *counts; orbx_dmatch *matches; int32_t *mcounts; float max_dist;
+};
+
+static orbx_status enqueue_chunk(orbx_handle *h, const BatchArgs &A, int f0, int nb)
 {
-    orbx_status st = set_geometry(h, width, height);
-    if (st != ORBX_OK) return st;
-    if (nframes == 0) return ORBX_OK;
+    const int slot = (int)(h->seq & 1);
+    const int width = A.width, height = A.height;
     const size_t pitch = align_up((size_t)width, 128), dpitch = align_up((size_t)width * 2, 128);
     const size_t fstride = pitch * height, dfstride = dpitch * height;
-    const int C = h->chunk;
-    const int kcap = std::min(cap, h->max_kp);
-    const size_t slot_kp = (size_t)C * h->max_kp;
+    const int SC = h->prm.max_batch;                              // slot capacity in frames
+    const int kcap = std::min(A.cap, h->max_kp);
+    const size_t slot_kp = (size_t)SC * h->max_kp;
+    orbx_status st;
     orbx_dmatch *d_m = nullptr; int32_t *d_mc = nullptr;
-    if (track) {
-        if ((st = grow(h, (uint8_t **)&h->d_mout, &h->mout_cap, 2 * slot_kp * sizeof(orbx_dmatch) + 2 * (size_t)C * sizeof(int32_t))) != ORBX_OK) return st;
-        d_m = h->d_mout; d_mc = (int32_t *)((uint8_t *)h->d_mout + 2 * slot_kp * sizeof(orbx_dmatch));
+    if (A.track) {
+        if (h->mout_cap < 2 * slot_kp * sizeof(orbx_dmatch) + 2 * (size_t)SC * sizeof(int32_t)) {
+            cudaStreamSynchronize(h->out_stream);                   // an older chunk may still be copying out of the old buffer
+            if ((st = grow(h, (uint8_t **)&h->d_mout, &h->mout_cap, 2 * slot_kp * sizeof(orbx_dmatch) + 2 * (size_t)SC * sizeof(int32_t))) != ORBX_OK) return st;
+        }
+        d_m = h->d_mout + (size_t)slot * slot_kp;
+        d_mc = (int32_t *)((uint8_t *)h->d_mout + 2 * slot_kp * sizeof(orbx_dmatch)) + slot * SC;
     }
-    const uint8_t *depth_zc = depth ? (const uint8_t *)mapped_device_view(depth) : nullptr;
-    const bool tight = (step == (size_t)width) && (pitch == (size_t)width);
-    // the main stream may still hold work of an earlier call that reads the slots
-    ORBX_CUDA(h, cudaEventRecord(h->ev_comp[0], h->stream));
-    ORBX_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_comp[0], 0));
-    const int nchunks = (nframes + C - 1) / C;
-    for (int i = 0; i < nchunks; i++) {
-        const int slot = i & 1, f0 = i * C, nb = std::min(C, nframes - f0);
-        uint8_t *d_g = h->d_in + (size_t)slot * C * fstride;
-        uint8_t *d_d = (uint8_t *)h->d_depth_in + (size_t)slot * C * dfstride;
-        // ---- H2D (copy stream): the input slot is free once the kernels of chunk i-2 are done ----
-        if (i >= 2) ORBX_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_comp[slot], 0));
-        if (tight) ORBX_CUDA(h, cudaMemcpyAsync(d_g, gray + (size_t)f0 * height * step, (size_t)nb * fstride, cudaMemcpyHostToDevice, h->copy_stream));
+    const uint8_t *depth_zc = A.depth ? (const uint8_t *)mapped_device_view(A.depth) : nullptr;
+    const bool tight = (A.step == (size_t)width) && (pitch == (size_t)width);
+    uint8_t *d_g = h->d_in + (size_t)slot * SC * fstride;
+    uint8_t *d_d = (uint8_t *)h->d_depth_in + (size_t)slot * SC * dfstride;
+    // ---- H2D (copy stream): the input slot is free once the kernels of the chunk that used it last are done ----
+    ORBX_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_comp[slot], 0));
+    if (tight) ORBX_CUDA(h, cudaMemcpyAsync(d_g, A.gray + (size_t)f0 * height * A.step, (size_t)nb * fstride, cudaMemcpyHostToDevice, h->copy_stream));
+    else for (int f = 0; f < nb; f++)
+        ORBX_CUDA(h, cudaMemcpy2DAsync(d_g + (size_t)f * fstride, pitch, A.gray + (size_t)(f0 + f) * height * A.step, A.step,
+                                       (size_t)width, (size_t)height, cudaMemcpyHostToDevice, h->copy_stream));
+    if (A.depth && !depth_zc) {
+        if (A.dstep == dpitch) ORBX_CUDA(h, cudaMemcpyAsync(d_d, (const uint8_t *)A.depth + (size_t)f0 * height * A.dstep, (size_t)nb * dfstride, cudaMemcpyHostToDevice, h->copy_stream));
         else for (int f = 0; f < nb; f++)
-            ORBX_CUDA(h, cudaMemcpy2DAsync(d_g + (size_t)f * fstride, pitch, gray + (size_t)(f0 + f) * height * step, step,
-                                           (size_t)width, (size_t)height, cudaMemcpyHostToDevice, h->copy_stream));
-        if (depth && !depth_zc) {
-            if (dstep == dpitch) ORBX_CUDA(h, cudaMemcpyAsync(d_d, (const uint8_t *)depth + (size_t)f0 * height * dstep, (size_t)nb * dfstride, cudaMemcpyHostToDevice, h->copy_stream));
-            else for (int f = 0; f < nb; f++)
-                ORBX_CUDA(h, cudaMemcpy2DAsync(d_d + (size_t)f * dfstride, dpitch, (const uint8_t *)depth + (size_t)(f0 + f) * height * dstep, dstep,
-                                               (size_t)width * 2, (size_t)height, cudaMemcpyHostToDevice, h->copy_stream));
-        }
-        ORBX_CUDA(h, cudaEventRecord(h->ev_in[slot], h->copy_stream));
-        // ---- kernels (main stream): the output slot is free once the D2H of chunk i-2 is done ----
-        ORBX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_in[slot], 0));
-        if (i >= 2) ORBX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_out[slot], 0));
-        orbx_keypoint *o_k = h->d_kps_out + (size_t)slot * slot_kp;
-        uint8_t *o_d = h->d_desc_out + (size_t)slot * slot_kp * ORBX_DESC_BYTES;
-        int32_t *o_c = h->d_count_out + slot * C;
-        const uint16_t *dd = nullptr; size_t dds = 0, ddf = 0;
-        if (depth_zc) { dd = (const uint16_t *)(depth_zc + (size_t)f0 * height * dstep); dds = dstep; ddf = (size_t)height * dstep; }
-        else if (depth) { dd = (const uint16_t *)d_d; dds = dpitch; ddf = dfstride; }
-        if (track) st = track_device(h, d_g, nb, width, height, pitch, fstride, dd, dds, ddf, o_k, o_d, h->max_kp, o_c,
-                                     d_m + (size_t)slot * slot_kp, d_mc + slot * C, max_dist);
-        else st = run_pipeline(h, nb, d_g, pitch, fstride, dd, dds, ddf, nullptr, 0, 0, o_k, o_d, h->max_kp, o_c);
-        if (st != ORBX_OK) { cudaStreamSynchronize(h->copy_stream); cudaStreamSynchronize(h->out_stream); cudaStreamSynchronize(h->stream); return st; }
-        ORBX_CUDA(h, cudaEventRecord(h->ev_comp[slot], h->stream));
-        // ---- D2H (out stream) ----
-        ORBX_CUDA(h, cudaStreamWaitEvent(h->out_stream, h->ev_comp[slot], 0));
-        ORBX_CUDA(h, cudaMemcpyAsync(counts + f0, o_c, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, h->out_stream));
-        ORBX_CUDA(h, cudaMemcpy2DAsync(kps + (size_t)f0 * cap, (size_t)cap * sizeof(orbx_keypoint), o_k, (size_t)h->max_kp * sizeof(orbx_keypoint),
-                                       (size_t)kcap * sizeof(orbx_keypoint), (size_t)nb, cudaMemcpyDeviceToHost, h->out_stream));
-        ORBX_CUDA(h, cudaMemcpy2DAsync(desc + (size_t)f0 * cap * ORBX_DESC_BYTES, (size_t)cap * ORBX_DESC_BYTES, o_d, (size_t)h->max_kp * ORBX_DESC_BYTES,
-                                       (size_t)kcap * ORBX_DESC_BYTES, (size_t)nb, cudaMemcpyDeviceToHost, h->out_stream));
-        if (track) {
-            ORBX_CUDA(h, cudaMemcpyAsync(mcounts + f0, d_mc + slot * C, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, h->out_stream));
-            ORBX_CUDA(h, cudaMemcpy2DAsync(matches + (size_t)f0 * cap, (size_t)cap * sizeof(orbx_dmatch), d_m + (size_t)slot * slot_kp, (size_t)h->max_kp * sizeof(orbx_dmatch),
-                                           (size_t)kcap * sizeof(orbx_dmatch), (size_t)nb, cudaMemcpyDeviceToHost, h->out_stream));
-        }
-        ORBX_CUDA(h, cudaEventRecord(h->ev_out[slot], h->out_stream));
+            ORBX_CUDA(h, cudaMemcpy2DAsync(d_d + (size_t)f * dfstride, dpitch, (const uint8_t *)A.depth + (size_t)(f0 + f) * height * A.dstep, A.dstep,
+                                           (size_t)width * 2, (size_t)height, cudaMemcpyHostToDevice, h->copy_stream));
     }
-    ORBX_CUDA(h, cudaStreamSynchronize(h->out_stream));
-    st = check_device_status(h);
+    ORBX_CUDA(h, cudaEventRecord(h->ev_in[slot], h->copy_stream));
+    // ---- kernels (main stream): the output slot is free once the D2H of the chunk that used it last is done ----
+    ORBX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_in[slot], 0));
+    ORBX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_out[slot], 0));
+    orbx_keypoint *o_k = h->d_kps_out + (size_t)slot * slot_kp;
+    uint8_t *o_d = h->d_desc_out + (size_t)slot * slot_kp * ORBX_DESC_BYTES;
+    int32_t *o_c = h->d_count_out + slot * SC;
+    const uint16_t *dd = nullptr; size_t dds = 0, ddf = 0;
+    if (depth_zc) { dd = (const uint16_t *)(depth_zc + (size_t)f0 * height * A.dstep); dds = A.dstep; ddf = (size_t)height * A.dstep; }
+    else if (A.depth) { dd = (const uint16_t *)d_d; dds = dpitch; ddf = dfstride; }
+    if (A.track) st = track_device(h, d_g, nb, width, height, pitch, fstride, dd, dds, ddf, o_k, o_d, h->max_kp, o_c, d_m, d_mc, A.max_dist);
+    else st = run_pipeline(h, nb, d_g, pitch, fstride, dd, dds, ddf, nullptr, 0, 0, o_k, o_d, h->max_kp, o_c);
     if (st != ORBX_OK) return st;
+    ORBX_CUDA(h, cudaEventRecord(h->ev_comp[slot], h->stream));
+    // ---- D2H (out stream) ----
+    ORBX_CUDA(h, cudaStreamWaitEvent(h->out_stream, h->ev_comp[slot], 0));
+    ORBX_CUDA(h, cudaMemcpyAsync(A.counts + f0, o_c, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, h->out_stream));
+    ORBX_CUDA(h, cudaMemcpy2DAsync(A.kps + (size_t)f0 * A.cap, (size_t)A.cap * sizeof(orbx_keypoint), o_k, (size_t)h->max_kp * sizeof(orbx_keypoint),
+                                   (size_t)kcap * sizeof(orbx_keypoint), (size_t)nb, cudaMemcpyDeviceToHost, h->out_stream));
+    ORBX_CUDA(h, cudaMemcpy2DAsync(A.desc + (size_t)f0 * A.cap * ORBX_DESC_BYTES, (size_t)A.cap * ORBX_DESC_BYTES, o_d, (size_t)h->max_kp * ORBX_DESC_BYTES,
+                                   (size_t)kcap * ORBX_DESC_BYTES, (size_t)nb, cudaMemcpyDeviceToHost, h->out_stream));
+    if (A.track) {
+        ORBX_CUDA(h, cudaMemcpyAsync(A.mcounts + f0, d_mc, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, h->out_stream));
+        ORBX_CUDA(h, cudaMemcpy2DAsync(A.matches + (size_t)f0 * A.cap, (size_t)A.cap * sizeof(orbx_dmatch), d_m, (size_t)h->max_kp * sizeof(orbx_dmatch),
+                                       (size_t)kcap * sizeof(orbx_dmatch), (size_t)nb, cudaMemcpyDeviceToHost, h->out_stream));
+    }
+    ORBX_CUDA(h, cudaMemcpyAsync(h->h_status + 1 + slot, h->d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, h->out_stream));
+    ORBX_CUDA(h, cudaEventRecord(h->ev_out[slot], h->out_stream));
+    h->seq++;
+    return ORBX_OK;
+}
+
+// completion of the chunk in `slot`: results are in the caller's buffers; device capacity flags and output capacity are reported here
+static orbx_status finish_slot(orbx_handle *h, int slot, const int32_t *counts, int nframes, int cap)
+{
+    ORBX_CUDA(h, cudaEventSynchronize(h->ev_out[slot]));
+    const int s = h->h_status[1 + slot];
+    if (s != 0) {
+        h->h_status[1 + slot] = 0;
+        cudaMemsetAsync(h->d_status, 0, sizeof(int32_t), h->stream);
+        h->err = std::string("device capacity exceeded:") + ((s & ORBX_DS_CAND_OVERFLOW) ? " candidate list (lower cand_divisor)" : "") +
+                 ((s & ORBX_DS_NODE_OVERFLOW) ? " quadtree nodes" : "") + ((s & ORBX_DS_KP_OVERFLOW) ? " keypoint output (raise cap / max_keypoints)" : "");
+        return ORBX_E_CAPACITY;
+    }
     for (int f = 0; f < nframes; f++) if (counts[f] > cap) { h->err = "output capacity too small"; return ORBX_E_CAPACITY; }
     return ORBX_OK;
+}
+
+static orbx_status drain_all(orbx_handle *h)
+{
+    cudaStreamSynchronize(h->copy_stream); cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->out_stream);
+    h->pending[0].active = h->pending[1].active = false;
+    return ORBX_OK;
+}
+
+static orbx_status host_batch(orbx_handle *h, const BatchArgs &A, int nframes)
+{
+    if (h->pending[0].active || h->pending[1].active) { h->err = "an asynchronous batch is outstanding: call orbx_batch_wait first"; return ORBX_E_INVALID; }
+    orbx_status st = set_geometry(h, A.width, A.height);
+    if (st != ORBX_OK) return st;
+    const int C = h->chunk;
+    for (int f0 = 0; f0 < nframes; f0 += C) {
+        const int nb = std::min(C, nframes - f0);
+        if ((st = enqueue_chunk(h, A, f0, nb)) != ORBX_OK) { drain_all(h); return st; }
+    }
+    ORBX_CUDA(h, cudaStreamSynchronize(h->out_stream));
+    if ((st = finish_slot(h, 0, A.counts, nframes, A.cap)) != ORBX_OK) return st;
+    return finish_slot(h, 1, A.counts, 0, A.cap);
+}
+
+static orbx_status submit_batch(orbx_handle *h, const BatchArgs &A, int nframes, int32_t *ticket)
+{
+    if (!ticket) { h->err = "null ticket"; return ORBX_E_INVALID; }
+    if (nframes < 1 || nframes > h->prm.max_batch) { h->err = "an asynchronous submission holds 1..max_batch frames"; return ORBX_E_INVALID; }
+    const int slot = (int)(h->seq & 1);
+    if (h->pending[slot].active) { h->err = "two batches are already in flight: wait for the older ticket first"; return ORBX_E_INVALID; }
+    orbx_status st = set_geometry(h, A.width, A.height);      // (a geometry change synchronises the streams itself)
+    if (st != ORBX_OK) return st;
+    const uint64_t t = h->seq;
+    if ((st = enqueue_chunk(h, A, 0, nframes)) != ORBX_OK) { drain_all(h); return st; }
+    h->pending[slot].active = true; h->pending[slot].ticket = t; h->pending[slot].counts = A.counts; h->pending[slot].nframes = nframes; h->pending[slot].cap = A.cap;
+    *ticket = (int32_t)(t & 0x7FFFFFFF);
+    return ORBX_OK;
+}
+
+extern "C" orbx_status orbx_batch_wait(orbx_handle *h, int32_t ticket)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    for (int slot = 0; slot < 2; slot++) {
+        if (h->pending[slot].active && (int32_t)(h->pending[slot].ticket & 0x7FFFFFFF) == ticket) {
+            // tickets complete in submission order: the other slot's older ticket, if any, must be collected first
+            const int o = slot ^ 1;
+            if (h->pending[o].active && h->pending[o].ticket < h->pending[slot].ticket) { h->err = "wait for the older ticket first"; return ORBX_E_INVALID; }
+            h->pending[slot].active = false;
+            return finish_slot(h, slot, h->pending[slot].counts, h->pending[slot].nframes, h->pending[slot].cap);
+        }
+    }
+    h->err = "unknown ticket";
+    return ORBX_E_INVALID;
+}
+
+static bool batch_args_ok(orbx_handle *h, const BatchArgs &A, int nframes)
+{
+    if (!A.gray || A.width <= 0 || A.height <= 0) { h->err = "empty image"; return false; }
+    if (nframes < 0 || !A.kps || !A.desc || !A.counts || A.cap < 1 || A.step < (size_t)A.width || (A.depth && A.dstep < (size_t)A.width * 2) ||
+        (A.track && (!A.matches || !A.mcounts))) { h->err = "bad arguments"; return false; }
+    return true;
 }
 
 extern "C" orbx_status orbx_extract_batch(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
@@ -597,9 +678,10 @@ extern "C" orbx_status orbx_extract_batch(orbx_handle *h, const uint8_t *gray, i
 {
     if (!h) return ORBX_E_INVALID;
     cudaSetDevice(h->device);
+    const BatchArgs A = { false, gray, width, height, step, depth, dstep, kps, desc, cap, counts, nullptr, nullptr, 0.f };
     if (!gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }
-    if (nframes < 0 || !kps || !desc || !counts || cap < 1 || step < (size_t)width || (depth && dstep < (size_t)width * 2)) { h->err = "bad arguments"; return ORBX_E_INVALID; }
-    return host_batch(h, false, gray, nframes, width, height, step, depth, dstep, kps, desc, cap, counts, nullptr, nullptr, 0.f);
+    if (!batch_args_ok(h, A, nframes)) return ORBX_E_INVALID;
+    return host_batch(h, A, nframes);
 }
 
 extern "C" orbx_status orbx_track_batch(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
@@ -609,9 +691,35 @@ extern "C" orbx_status orbx_track_batch(orbx_handle *h, const uint8_t *gray, int
 {
     if (!h) return ORBX_E_INVALID;
     cudaSetDevice(h->device);
+    const BatchArgs A = { true, gray, width, height, step, depth, dstep, kps, desc, cap, counts, matches, mcounts, max_dist };
     if (!gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }
-    if (nframes < 0 || !kps || !desc || !counts || !matches || !mcounts || cap < 1 || step < (size_t)width || (depth && dstep < (size_t)width * 2)) { h->err = "bad arguments"; return ORBX_E_INVALID; }
-    return host_batch(h, true, gray, nframes, width, height, step, depth, dstep, kps, desc, cap, counts, matches, mcounts, max_dist);
+    if (!batch_args_ok(h, A, nframes)) return ORBX_E_INVALID;
+    return host_batch(h, A, nframes);
+}
+
+extern "C" orbx_status orbx_extract_batch_submit(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
+                                                 size_t step, const uint16_t *depth, size_t dstep,
+                                                 orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *counts, int32_t *ticket)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    const BatchArgs A = { false, gray, width, height, step, depth, dstep, kps, desc, cap, counts, nullptr, nullptr, 0.f };
+    if (!gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }
+    if (!batch_args_ok(h, A, nframes)) return ORBX_E_INVALID;
+    return submit_batch(h, A, nframes, ticket);
+}
+
+extern "C" orbx_status orbx_track_batch_submit(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
+                                               size_t step, const uint16_t *depth, size_t dstep,
+                                               orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *counts,
+                                               orbx_dmatch *matches, int32_t *mcounts, float max_dist, int32_t *ticket)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    const BatchArgs A = { true, gray, width, height, step, depth, dstep, kps, desc, cap, counts, matches, mcounts, max_dist };
+    if (!gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }
+    if (!batch_args_ok(h, A, nframes)) return ORBX_E_INVALID;
+    return submit_batch(h, A, nframes, ticket);
 }
 
 // ---- stage access (mvImagePyramid is public in the reference, ORBextractor.hpp:84) ----

@@ -73,7 +73,9 @@ struct orbx_handle {
     int opt_serial;
     cudaEvent_t ev_a, ev_b;
     cudaEvent_t ev_in[2], ev_comp[2], ev_out[2];   // host-batch pipeline: input slot filled / kernels done / outputs copied
-    int chunk;                                      // frames per pipeline chunk of the host-buffer batch calls
+    int chunk;                                      // frames per pipeline chunk of the synchronous host-buffer batch calls
+    uint64_t seq;                                   // chunks enqueued so far; chunk n uses staging slot n & 1
+    struct { bool active; uint64_t ticket; const int32_t *counts; int nframes, cap; } pending[2];   // asynchronous submissions
     std::string err;
     int64_t launches;
     // extractor tables (ORBextractor.cpp:409-469)

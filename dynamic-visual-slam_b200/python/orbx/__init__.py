@@ -110,6 +110,9 @@ def load():
         "orbx_track_batch_device": (i32, [vp, vp, i32, i32, i32, sz, sz, vp, sz, sz, vp, vp, i32, vp, vp, vp, f32]),
         "orbx_track_batch": (i32, [vp, vp, i32, i32, i32, sz, vp, sz, vp, vp, i32, vp, vp, vp, f32]),
         "orbx_track_reset": (None, [vp]),
+        "orbx_extract_batch_submit": (i32, [vp, vp, i32, i32, i32, sz, vp, sz, vp, vp, i32, vp, vp]),
+        "orbx_track_batch_submit": (i32, [vp, vp, i32, i32, i32, sz, vp, sz, vp, vp, i32, vp, vp, vp, f32, vp]),
+        "orbx_batch_wait": (i32, [vp, i32]),
         "orbx_profile_enable": (None, [vp, i32]),
         "orbx_profile_kernels": (i32, []),
         "orbx_profile_name": (ct.c_char_p, [i32]),
@@ -322,6 +325,22 @@ class ORBextractor:
         self._check(self.L.orbx_track_batch(self._h, _p(frames), nf, w, h, frames.strides[1], dptr, dstep,
                                             _p(kps), _p(desc), cap, _p(counts), _p(matches), _p(mcounts), ct.c_float(max_dist)))
         return kps, desc, counts, matches, mcounts
+
+    def track_batch_submit(self, frames, depth, out, max_dist=50.0):
+        """Asynchronous track_batch: `frames` [n,h,w] u8 / `depth` [n,h,w] u16 (pinned for real overlap) and `out` = dict of
+        pre-allocated arrays kps [n,cap] KP_DTYPE, desc [n,cap,32], counts [n], matches [n,cap] DM_DTYPE, mcounts [n].
+        Returns a ticket for batch_wait(); at most two batches may be in flight."""
+        nf, h, w = frames.shape
+        cap = out["kps"].shape[1]
+        t = ct.c_int32()
+        self._check(self.L.orbx_track_batch_submit(self._h, _p(frames), nf, w, h, frames.strides[1],
+                                                   _p(depth) if depth is not None else None, depth.strides[1] if depth is not None else 0,
+                                                   _p(out["kps"]), _p(out["desc"]), cap, _p(out["counts"]), _p(out["matches"]), _p(out["mcounts"]),
+                                                   ct.c_float(max_dist), ct.byref(t)))
+        return t.value
+
+    def batch_wait(self, ticket):
+        self._check(self.L.orbx_batch_wait(self._h, ticket))
 
     def profile_enable(self, on=True):
         self.L.orbx_profile_enable(self._h, 1 if on else 0)

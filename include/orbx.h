@@ -70,7 +70,7 @@ typedef struct {
     int32_t max_keypoints;    /* per-frame output capacity; 0 = nfeatures + 4*nlevels + 64 */
     int32_t cand_divisor;     /* candidate-list capacity per level = max(4096, pixels/cand_divisor); 0 = 16 */
     int32_t device;           /* CUDA device ordinal */
-    int32_t reserved_[3];     /* [0]: frames per pipeline chunk of the host-buffer batch calls, 0 = auto (max_batch/8, 1..32) */
+    int32_t reserved_[3];     /* [0]: frames per pipeline chunk of the host-buffer batch calls, 0 = auto (max_batch/4, 1..32) */
 } orbx_params;
 
 typedef struct orbx_handle orbx_handle;
@@ -148,6 +148,20 @@ orbx_status orbx_track_batch(orbx_handle *h, const uint8_t *gray, int32_t nframe
                              orbx_keypoint *kps, uint8_t *desc, int32_t cap_per_frame, int32_t *counts,
                              orbx_dmatch *matches, int32_t *match_counts, float max_dist);
 void        orbx_track_reset(orbx_handle *h);
+
+/* Asynchronous variants of the two host-buffer batch calls: enqueue ONE batch (1..max_batch frames) and return a ticket;
+ * orbx_batch_wait(ticket) blocks until that batch's results are in the caller's buffers and reports its status.  Two batches
+ * may be in flight, collected in submission order: submit(k+1) before wait(k) hides the H2D of batch k+1 and the D2H of batch
+ * k-1 under the kernels of batch k.  Input and output buffers must stay valid until the wait returns and should be pinned
+ * (orbx_alloc_pinned).  While a ticket is outstanding only *_submit / orbx_batch_wait may be called on the handle.        */
+orbx_status orbx_extract_batch_submit(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
+                                      size_t step, const uint16_t *depth, size_t dstep,
+                                      orbx_keypoint *kps, uint8_t *desc, int32_t cap_per_frame, int32_t *counts, int32_t *ticket);
+orbx_status orbx_track_batch_submit(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
+                                    size_t step, const uint16_t *depth, size_t dstep,
+                                    orbx_keypoint *kps, uint8_t *desc, int32_t cap_per_frame, int32_t *counts,
+                                    orbx_dmatch *matches, int32_t *match_counts, float max_dist, int32_t *ticket);
+orbx_status orbx_batch_wait(orbx_handle *h, int32_t ticket);
 
 /* ---- matching: cv::BFMatcher(NORM_HAMMING) ----
  * k = 1: BFMatcher::match.   max_dist <= 0: one DMatch per query, query order (exactly match()).

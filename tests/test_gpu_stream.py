@@ -71,6 +71,42 @@ def test_track_batch_host_pinned_zero_copy_depth(built, stream_ref):
         pg.close(); pd.close()
 
 
+def test_track_batch_async_two_in_flight(built, stream_ref):
+    """submit(k+1) before wait(k): results identical to the synchronous sequence, tickets collected in order."""
+    import orbx
+    frames, depths, ref = stream_ref
+    B, CAP = 3, 2048
+    pg, pd = orbx.PinnedArray(frames.shape, np.uint8), orbx.PinnedArray(depths.shape, np.uint16)
+    pg.array[...] = frames
+    pd.array[...] = depths
+    ex = orbx.ORBextractor(max_width=W, max_height=H, max_batch=B)
+    outs = [dict(kps=np.zeros((B, CAP), orbx.KP_DTYPE), desc=np.zeros((B, CAP, 32), np.uint8), counts=np.zeros(B, np.int32),
+                 matches=np.zeros((B, CAP), orbx.DM_DTYPE), mcounts=np.zeros(B, np.int32)) for _ in range(2)]
+    try:
+        spans = [(f0, min(N, f0 + B)) for f0 in range(0, N, B)]
+        tickets = []
+        for k, (a, b) in enumerate(spans):
+            tickets.append(ex.track_batch_submit(pg.array[a:b], pd.array[a:b], outs[k & 1]))
+            if k >= 1:                                               # collect batch k-1 while batch k is in flight
+                ex.batch_wait(tickets[k - 1])
+                a0, b0 = spans[k - 1]
+                o = outs[(k - 1) & 1]
+                _check_track((o["kps"][:b0 - a0], o["desc"][:b0 - a0], o["counts"][:b0 - a0], o["matches"][:b0 - a0], o["mcounts"][:b0 - a0]), ref, a0)
+        with pytest.raises(orbx.OrbxError):                          # a synchronous call while a ticket is outstanding is refused
+            ex(frames[0])
+        ex.batch_wait(tickets[-1])
+        a0, b0 = spans[-1]
+        o = outs[(len(spans) - 1) & 1]
+        _check_track((o["kps"][:b0 - a0], o["desc"][:b0 - a0], o["counts"][:b0 - a0], o["matches"][:b0 - a0], o["mcounts"][:b0 - a0]), ref, a0)
+        with pytest.raises(orbx.OrbxError):
+            ex.batch_wait(12345)
+        k0, _ = ex(frames[0])                                        # back to synchronous use
+        assert len(k0) == len(ref[0]["raw_kps"])
+    finally:
+        ex.close()
+        pg.close(); pd.close()
+
+
 def test_extract_batch_host(built, stream_ref):
     import orbx
     frames, depths, ref = stream_ref
