@@ -88,13 +88,12 @@ __device__ unsigned long long block_scan_excl(unsigned long long *s_val, int n, 
 }
 
 // ---- libstdc++ std::sort restated (introsort, threshold 16) on (cnt, ulx, payload) triples ----
-struct SrtE { int cnt, ulx, pay; };
-__device__ __forceinline__ bool srt_less(const SrtE &a, const SrtE &b)
-{
-    if (a.cnt < b.cnt) return true;
-    if (a.cnt > b.cnt) return false;
-    return a.ulx < b.ulx;
-}
+// one element = one 64-bit word: count:32 | UL.x:16 | node index:16, so a comparison of (count, UL.x) is one shifted compare
+// and every move of the single-thread sort is one LDS/STS.64
+typedef unsigned long long SrtE;
+__device__ __forceinline__ SrtE srt_make(unsigned cnt, int ulx, int pay) { return ((SrtE)cnt << 32) | ((SrtE)(ulx & 0xFFFF) << 16) | (SrtE)(pay & 0xFFFF); }
+__device__ __forceinline__ int srt_pay(SrtE e) { return (int)(e & 0xFFFFu); }
+__device__ __forceinline__ bool srt_less(const SrtE &a, const SrtE &b) { return (a >> 16) < (b >> 16); }
 __device__ __forceinline__ void srt_swap(SrtE *a, SrtE *b) { SrtE t = *a; *a = *b; *b = t; }
 __device__ void srt_adjust_heap(SrtE *first, int hole, int len, SrtE value)
 {
@@ -286,11 +285,11 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(QtParams P, const Frame
         if (state == 2 || ++guard > 64) break;
         // visit order: normal = reverse creation order (list order); sorted = descending (count, UL.x)
         if (state == 1) {
-            for (int k = threadIdx.x; k < M; k += QT_THREADS) { s_srt[k].cnt = (int)cur.cnt[k]; s_srt[k].ulx = cur.x0[k]; s_srt[k].pay = k; }
+            for (int k = threadIdx.x; k < M; k += QT_THREADS) s_srt[k] = srt_make(cur.cnt[k], cur.x0[k], k);
             __syncthreads();
             if (threadIdx.x == 0) srt_sort(s_srt, M);
             __syncthreads();
-            for (int v = threadIdx.x; v < M; v += QT_THREADS) { const int k = s_srt[M - 1 - v].pay; s_vis[v] = (unsigned short)k; s_rank[k] = (unsigned short)v; }
+            for (int v = threadIdx.x; v < M; v += QT_THREADS) { const int k = srt_pay(s_srt[M - 1 - v]); s_vis[v] = (unsigned short)k; s_rank[k] = (unsigned short)v; }
         } else {
             for (int v = threadIdx.x; v < M; v += QT_THREADS) { const int k = M - 1 - v; s_vis[v] = (unsigned short)k; s_rank[k] = (unsigned short)v; }
         }
