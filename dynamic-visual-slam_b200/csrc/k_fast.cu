@@ -209,27 +209,51 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(const __grid_constant
         mbar_wait(&s_full[FS_NBUF == 2 ? buf : 0], (uint32_t)(FS_NBUF == 2 ? ((it_n >> 1) & 1) : (it_n & 1)));
         __syncthreads();
 
-        // ---- block-wide packed sweep at iniThFAST ----
         const int w0 = (ax + 3) >> 2;                                  // tile word holding detection column 0
         const int nGs = ((ax + 3 + dw - 1) >> 2) - w0 + 1;             // words holding detection columns (<= 64)
         const int nseg = (dh + 6) / 7;
         const uint32_t *words = reinterpret_cast<const uint32_t *>(s_img);
-        uint32_t HM, KK;
-        fast_masks(P.ini_th, HM, KK);
-        {
-            const float inv = 1.0f / (float)nGs;
-            const int units = nGs * nseg;
+        uint32_t *gdst = P.cand + (size_t)T.f * P.cand_slab + g.cand_off;
+        int32_t *gcnt = &P.ncand[T.f * nl + T.level];
+        const float invc = 1.0f / (float)wcell;
+        // pass 0: every cell at iniThFAST.  pass 1: the cells that produced nothing, at minThFAST (the reference's retry, :843-846).
+        // Both passes are block-wide, so the retry of one or two cells is spread over all warps instead of stalling them.
+        int nredo = 0;
+        uint32_t redo_cells = 0u, redo_mask = 0u;                       // pass 1: up to 8 cell indices, 4 bits each / bit per cell (uniform)
+        for (int pass = 0; pass < 2; pass++) {
+            const int th = pass == 0 ? P.ini_th : P.min_th;
+            uint32_t HM, KK;
+            fast_masks(th, HM, KK);
+            // ---- packed sweep: pass 0 = all words of the strip, pass 1 = the words of the retried cells ----
+            int units = nGs * nseg;
+            if (pass == 1) {
+                units = 0;
+                for (int r = 0; r < nredo; r++) {
+                    const int c = (int)((redo_cells >> (4 * r)) & 15u), c_lo = c * wcell, c_hi = min(c_lo + wcell, dw);
+                    units += ((((ax + 3 + c_hi - 1) >> 2) - ((ax + 3 + c_lo) >> 2)) + 1) * nseg;
+                }
+            }
             for (int u0 = 0; u0 < units; u0 += FS_THREADS) {
                 const int u = u0 + threadIdx.x;
                 uint32_t word = 0u;
                 int base_off = 0;
                 if (u < units) {
-                    const int seg = __float2int_rd(((float)u + 0.5f) * inv), gidx = u - seg * nGs;
+                    int uu = u, gfirst = 0, nG = nGs, c_lo = 0, c_hi = dw;
+                    if (pass == 1) {
+                        for (int r = 0; r < nredo; r++) {
+                            const int c = (int)((redo_cells >> (4 * r)) & 15u);
+                            c_lo = c * wcell; c_hi = min(c_lo + wcell, dw);
+                            gfirst = ((ax + 3 + c_lo) >> 2) - w0; nG = ((ax + 3 + c_hi - 1) >> 2) - w0 - gfirst + 1;
+                            if (uu < nG * nseg) break;
+                            uu -= nG * nseg;
+                        }
+                    }
+                    const int seg = __float2int_rd(((float)uu + 0.5f) / (float)nG), gidx = gfirst + uu - seg * nG;
                     const uint32_t raw = fast_sweep7(words + (7 * seg) * FS_TPW + w0 + gidx, HM, KK);
                     const int cb = 4 * (w0 + gidx) - (ax + 3);                // detection column of byte 0
                     uint32_t cm = 0u;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) if (cb + j >= 0 && cb + j < dw) cm |= 0xFEu << (8 * j);
+                    for (int j = 0; j < 4; j++) if (cb + j >= c_lo && cb + j < c_hi) cm |= 0xFEu << (8 * j);
                     const int nv = min(7, dh - 7 * seg);
                     word = raw & cm & (((0xFF00u >> nv) & 0xFFu) * 0x01010101u);
                     base_off = (7 * seg + 3) * FS_TP + 4 * (w0 + gidx);
@@ -249,33 +273,27 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(const __grid_constant
                     slot++;
                 }
             }
-        }
-        __syncthreads();
-        const bool ovf = s_qn > FS_QCAP;                                // uniform
-        const int qn = ovf ? 0 : s_qn;
-        const int th0 = P.ini_th;
-        // ---- exact score (ROI coords = detection coords + 3): queue entries, or every pixel if the queue overflowed ----
-        if (!ovf) {
-            for (int i = threadIdx.x; i < qn; i += FS_THREADS) {
-                const int off = s_q[i];
-                const int s = fast_score_packed(s_img + off);
-                const int tr = off / FS_TP, tc = off - tr * FS_TP - ax;
-                s_sc[(tr - 2) * FS_SP + (tc - 2)] = (uint8_t)(s > th0 ? s - 1 : 0);
+            __syncthreads();
+            const bool ovf = s_qn > FS_QCAP;                            // uniform
+            const int qn = ovf ? 0 : s_qn;
+            // ---- exact score (ROI coords = detection coords + 3): queue entries, or every pixel if the queue overflowed ----
+            if (!ovf) {
+                for (int i = threadIdx.x; i < qn; i += FS_THREADS) {
+                    const int off = s_q[i];
+                    const int s = fast_score_packed(s_img + off);
+                    const int tr = off / FS_TP, tc = off - tr * FS_TP - ax;
+                    s_sc[(tr - 2) * FS_SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
+                }
+            } else {
+                for (int i = threadIdx.x; i < dw * dh; i += FS_THREADS) {
+                    const int r = i / dw, c = i - r * dw;
+                    const int s = fast_score_packed(s_img + (r + 3) * FS_TP + ax + c + 3);
+                    s_sc[(r + 1) * FS_SP + (c + 1)] = (uint8_t)(s > th ? s - 1 : 0);
+                }
             }
-        } else {
-            for (int i = threadIdx.x; i < dw * dh; i += FS_THREADS) {
-                const int r = i / dw, c = i - r * dw;
-                const int s = fast_score_packed(s_img + (r + 3) * FS_TP + ax + c + 3);
-                s_sc[(r + 1) * FS_SP + (c + 1)] = (uint8_t)(s > th0 ? s - 1 : 0);
-            }
-        }
-        __syncthreads();
-        uint32_t *gdst = P.cand + (size_t)T.f * P.cand_slab + g.cand_off;
-        int32_t *gcnt = &P.ncand[T.f * nl + T.level];
-        // ---- strict 3x3 NMS inside each cell ----
-        {
+            __syncthreads();
+            // ---- strict 3x3 NMS inside each cell ----
             const int nitems = ovf ? dw * dh : qn;
-            const float invc = 1.0f / (float)wcell;
             for (int i = threadIdx.x; i < nitems; i += FS_THREADS) {
                 int r, c;
                 if (ovf) { r = i / dw; c = i - r * dw; }
@@ -284,12 +302,13 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(const __grid_constant
                 const int s = q[0];
                 if (s == 0) continue;
                 const int cell = min(__float2int_rd(((float)c + 0.5f) * invc), T.ncell - 1);
+                if (pass == 1 && !((redo_mask >> cell) & 1u)) continue;   // (overflow scan only: cells that already have keypoints)
                 const int c_lo = cell * wcell, c_hi = min(c_lo + wcell, dw);
                 bool ok = s > q[-FS_SP] && s > q[FS_SP];
                 if (c > c_lo) ok = ok && s > q[-1] && s > q[-FS_SP - 1] && s > q[FS_SP - 1];
                 if (c < c_hi - 1) ok = ok && s > q[1] && s > q[-FS_SP + 1] && s > q[FS_SP + 1];
                 if (ok) {
-                    atomicAdd(&s_ccnt[cell], 1);
+                    if (pass == 0) atomicAdd(&s_ccnt[cell], 1);
                     // box-relative coordinates: kp.pt + (j*wCell, i*hCell) — ORBextractor.cpp:865-866
                     const uint32_t val = orbx_pack(T.cj0 * wcell + c + 3, T.ci * T.hcell + r + 3, s);
                     const int o = atomicAdd(&s_nout, 1);
@@ -300,96 +319,11 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(const __grid_constant
                     }
                 }
             }
-        }
-        __syncthreads();
-        // ---- the reference retries a cell at minThFAST iff iniThFAST produced nothing (:843-846): one warp per such cell ----
-        int nredo = 0;
-        uint32_t redo_cells = 0u;                                       // up to 8 cell indices, 4 bits each (uniform)
-        for (int c = 0; c < T.ncell; c++) if (s_ccnt[c] == 0) { redo_cells |= (uint32_t)c << (4 * nredo); nredo++; }
-        if (nredo > 0) {
-            fast_masks(P.min_th, HM, KK);
-            const int th = P.min_th;
-            uint16_t *wq = s_q + warp * FS_WQ;
-            for (int ri = warp; ri < nredo && warp < FS_RWARPS; ri += FS_RWARPS) {
-                const int cell = (int)((redo_cells >> (4 * ri)) & 15u);
-                const int c_lo = cell * wcell, c_hi = min(c_lo + wcell, dw);          // detection columns of the cell
-                const int ga = ((ax + 3 + c_lo) >> 2) - w0, nG = ((ax + 3 + c_hi - 1) >> 2) - w0 - ga + 1;
-                const int units = nG * nseg;
-                const float inv = 1.0f / (float)nG;
-                int wn = 0;
-                bool wovf = false;
-                for (int u0 = 0; u0 < units; u0 += 32) {
-                    const int u = u0 + lane;
-                    uint32_t word = 0u;
-                    int base_off = 0;
-                    if (u < units) {
-                        const int seg = __float2int_rd(((float)u + 0.5f) * inv), gidx = ga + u - seg * nG;
-                        const uint32_t raw = fast_sweep7(words + (7 * seg) * FS_TPW + w0 + gidx, HM, KK);
-                        const int cb = 4 * (w0 + gidx) - (ax + 3);
-                        uint32_t cm = 0u;
-#pragma unroll
-                        for (int j = 0; j < 4; j++) if (cb + j >= c_lo && cb + j < c_hi) cm |= 0xFEu << (8 * j);
-                        const int nv = min(7, dh - 7 * seg);
-                        word = raw & cm & (((0xFF00u >> nv) & 0xFFu) * 0x01010101u);
-                        base_off = (7 * seg + 3) * FS_TP + 4 * (w0 + gidx);
-                    }
-                    const int cnt = __popc(word);
-                    int incl = cnt;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-                    const int total = __shfl_sync(0xffffffffu, incl, 31);
-                    if (wn + total > FS_WQ) {                                 // queue full: score what is queued, NMS will scan the cell
-                        __syncwarp();
-                        for (int i = lane; i < wn; i += 32) {
-                            const int off = wq[i];
-                            const int s = fast_score_packed(s_img + off);
-                            const int tr = off / FS_TP, tc = off - tr * FS_TP - ax;
-                            s_sc[(tr - 2) * FS_SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
-                        }
-                        __syncwarp();
-                        wn = 0; wovf = true;
-                    }
-                    int slot = wn + incl - cnt;
-                    while (word) {
-                        const int bit = __ffs((int)word) - 1;
-                        word &= word - 1;
-                        wq[slot++] = (uint16_t)(base_off + (7 - (bit & 7)) * FS_TP + (bit >> 3));
-                    }
-                    wn += total;
-                }
-                __syncwarp();
-                for (int i = lane; i < wn; i += 32) {
-                    const int off = wq[i];
-                    const int s = fast_score_packed(s_img + off);
-                    const int tr = off / FS_TP, tc = off - tr * FS_TP - ax;
-                    s_sc[(tr - 2) * FS_SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
-                }
-                __syncwarp();
-                const int cw = c_hi - c_lo;
-                const int nitems = wovf ? cw * dh : wn;
-                const float invw = 1.0f / (float)cw;
-                for (int i = lane; i < nitems; i += 32) {
-                    int r, c;
-                    if (wovf) { r = __float2int_rd(((float)i + 0.5f) * invw); c = c_lo + i - r * cw; }
-                    else { const int off = wq[i]; const int tr = off / FS_TP; r = tr - 3; c = off - tr * FS_TP - ax - 3; }
-                    const uint8_t *q = &s_sc[(r + 1) * FS_SP + (c + 1)];
-                    const int s = q[0];
-                    if (s == 0) continue;
-                    bool ok = s > q[-FS_SP] && s > q[FS_SP];
-                    if (c > c_lo) ok = ok && s > q[-1] && s > q[-FS_SP - 1] && s > q[FS_SP - 1];
-                    if (c < c_hi - 1) ok = ok && s > q[1] && s > q[-FS_SP + 1] && s > q[FS_SP + 1];
-                    if (ok) {
-                        const uint32_t val = orbx_pack(T.cj0 * wcell + c + 3, T.ci * T.hcell + r + 3, s);
-                        const int o = atomicAdd(&s_nout, 1);
-                        if (o < FS_OUT_CAP) s_out[o] = val;
-                        else {
-                            const int go = atomicAdd(gcnt, 1);
-                            if (go < g.cand_cap) gdst[go] = val; else atomicOr(P.status, ORBX_DS_CAND_OVERFLOW);
-                        }
-                    }
-                }
-                __syncwarp();
-            }
+            __syncthreads();
+            if (pass == 1) break;
+            for (int c = 0; c < T.ncell; c++) if (s_ccnt[c] == 0) { redo_cells |= (uint32_t)c << (4 * nredo); redo_mask |= 1u << c; nredo++; }
+            if (nredo == 0) break;
+            if (threadIdx.x == 0) s_qn = 0;
             __syncthreads();
         }
         // ---- flush the item's candidates: one global atomic, warp 0 ----
