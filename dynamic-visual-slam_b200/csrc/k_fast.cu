@@ -6,27 +6,26 @@
 //   corner iff S > th; score = S - 1; strict 3x3 NMS INSIDE the cell's ROI (scores outside the
 //   cell's detection area read as 0).
 //
-// Design.  A work item is a horizontal run of cells of one cell row of one level of one frame (a "strip",
-// described by a host-built table).  The kernel is PERSISTENT: one CTA per resident slot loops over the items of
-// the whole batch, and the strip's ROI arrives in shared memory by TMA (cp.async.bulk.tensor, one descriptor per
-// pyramid level, frames as the third tensor dimension) into a double buffer: the tile of item i+1 is in flight
-// while item i is processed, so no thread ever issues a staging load or waits for one.
-//   1. packed sweep, block-wide: a sweep unit is one aligned 32-bit word of the tile (4 adjacent pixels) x 7
-//      rows, walked with a 7-row register window (3 LDS.32 + 4 PRMT per row of 4 pixels).  Per row it
+// Design.  The reference's unit of work is the CELL (FAST, NMS and the threshold retry all run on one cell ROI), and here a
+// cell is owned by ONE WARP from start to finish: there is no block barrier anywhere in the kernel.
+//   * persistent one-warp CTAs loop over the (frame, level, cell) items of the whole batch (host-built cell table);
+//   * the cell's ROI (+3 px ring margin, 16-byte aligned start) arrives in the warp's shared memory by TMA
+//     (cp.async.bulk.tensor.3d, one descriptor per pyramid level, frames as the third tensor dimension); the next
+//     cell's window is prefetched into L2 (cp.async.bulk.prefetch.tensor) while the current one is processed;
+//   1. packed sweep: a sweep unit is one aligned 32-bit word of the tile (4 adjacent pixels) x 7 rows, walked with a
+//      7-row register window (3 LDS.32 + 4 PRMT per row of 4 pixels); lanes take the cell's units round-robin.  Per row it
 //      evaluates a polarity-agnostic pre-test on the four opposite ring pairs (0,8) (4,12) (2,10) (6,14):
 //      |I(ring) - I(p)| for 4 pixels is ONE VABSDIFF4.U8; "some member of the pair differs by more than T"
 //      with T = 2^k - 1 <= th is an OR, a mask and one add per pair (SWAR, no per-byte compares).  Every
 //      9-arc contains a member of each opposite pair, so the test is an exact NECESSARY condition for
-//      S > th; it is loose by design (T <= th, sign ignored) and passes ~5 % of the pixels.  Survivors go
-//      straight into one shared queue (warp-aggregated slot allocation);
-//   2. exact score of the queued survivors, dense over the block: the 16-arc min/max network runs on packed
+//      S > th; it is loose by design (T <= th, sign ignored) and passes ~5 % of the pixels.  Survivors are
+//      compacted into the warp's queue with shuffle prefix sums;
+//   2. exact score of the queued survivors, dense over the lanes: the 16-arc min/max network runs on packed
 //      u16x2 lanes (VIMNMX3.U16x2): low half = ring value, high half = 255 - ring value, so one instruction
 //      serves the darker and the brighter polarity;
-//   3. strict 3x3 NMS over the queue entries; neighbours in another cell are never read (the reference runs
-//      FAST per cell ROI, so they count as 0);
-//   4. a cell with no keypoint at iniThFAST is swept again at minThFAST (the reference's retry) by ONE warp —
-//      only that cell, not the strip.
-// Survivors are appended to the (frame, level) candidate list with one global atomic per item;
+//   3. strict 3x3 NMS over the queue entries (scores outside the cell count as 0, as in the reference's per-ROI FAST);
+//   4. a cell with no keypoint at iniThFAST is swept again at minThFAST (the reference's retry) by the same warp.
+// Keypoints are appended to the (frame, level) candidate list with one warp-aggregated global atomic per NMS step;
 // list order is arbitrary (the quadtree kernel is order-independent).
 //
 // Toolchain note: an earlier formulation on signed differences (d = I(p) - I(ring), score via
@@ -37,29 +36,20 @@
 #include <algorithm>
 #include <cstring>
 
-#define FS_THREADS 192
-#define FS_WARPS (FS_THREADS / 32)
-#define FS_TP 288                // tile pitch = TMA box width: 72 u32 elements >= 16 + 15 + ORBX_FAST_MAX_W + 6 + 4
+#define FS_TP 96                 // tile pitch = TMA box width: 24 u32 elements >= 15 (alignment) + 69 + 6 (widest cell ROI) + 4
 #define FS_TPW (FS_TP / 4)
 #define FS_PADROWS 6             // rows behind the tile: a 7-row sweep unit may start on the last detection row
-#define FS_SP 272                // score-map pitch: >= detection width + 2, multiple of 16
-#define FS_QCAP 4096             // survivor queue (u16 tile offsets); FS_RWARPS x FS_WQ in the retry phase
-#define FS_RWARPS 4               // warps that run cell retries concurrently
-#define FS_WQ (FS_QCAP / FS_RWARPS)  // per-warp queue of the retry phase, >= 32 lanes x 28 flags
-#define FS_OUT_CAP 512          // staged outputs; beyond it survivors are written straight to the global list
-#define FS_MAX_CELLS 8
-#ifndef FS_NBUF
-#define FS_NBUF 2                // tile buffers: 2 = the next item's tile is in flight while this one is processed
-#endif
+#define FS_WQ 1024               // survivor queue (u16 tile offsets) >= 32 lanes x 28 flags
 
 struct FastParams {
     uint32_t *cand; size_t cand_slab;
     int32_t *ncand;
-    const uint32_t *strips;      // level:4 | cells:4 | cell row:12 | first cell column:12
-    int nstrips, nitems;         // items = nstrips x frames
+    const uint32_t *cells;       // level:4 | cell row:14 | cell column:14
+    int ncells, nitems;          // items = ncells x frames
     int ini_th, min_th;
     int32_t *status;
     int tile_rows;               // max (hCell + 6) over the levels
+    int map_pitch;               // score-map pitch: >= max cell width + 2, multiple of 16
 };
 
 #define RO(dx, dy) ((dy) * FS_TP + (dx))
@@ -143,117 +133,90 @@ __device__ __forceinline__ void fast_masks(int th, uint32_t &HM, uint32_t &KK)
     KK = (0x80u - (1u << sh)) * 0x01010101u;
 }
 
-// geometry of one work item, derived from its strip descriptor
-struct FastItem { int f, level, ci, cj0, ncell, wcell, hcell, iniX, iniY, ax, rw, rh, dw, dh; };
+// geometry of one work item, derived from its cell descriptor
+struct FastItem { int f, level, ci, cj, wcell, hcell, iniX, iniY, ax, dw, dh; };
 __device__ __forceinline__ FastItem fast_item(const FastParams &P, const FrameGeom *__restrict__ G, int item)
 {
     FastItem t;
-    t.f = item / P.nstrips;
-    const uint32_t sd = __ldg(P.strips + (item - t.f * P.nstrips));
-    t.level = (int)(sd & 15u); t.ncell = (int)((sd >> 4) & 15u); t.ci = (int)((sd >> 8) & 0xFFFu); t.cj0 = (int)(sd >> 20);
+    t.f = item / P.ncells;
+    const uint32_t cd = __ldg(P.cells + (item - t.f * P.ncells));
+    t.level = (int)(cd & 15u); t.ci = (int)((cd >> 4) & 0x3FFFu); t.cj = (int)(cd >> 18);
     const LevelGeom &g = G->lv[t.level];
     t.wcell = g.wcell; t.hcell = g.hcell;
-    // strip ROI in image coordinates — ORBextractor.cpp:805-822 (cells cj0 .. cj0+ncell-1 of cell row ci)
-    t.iniX = ORBX_BORDER + t.cj0 * t.wcell; t.iniY = ORBX_BORDER + t.ci * t.hcell;
-    const int maxX = min(t.iniX + t.ncell * t.wcell + 6, g.w - ORBX_BORDER), maxY = min(t.iniY + t.hcell + 6, g.h - ORBX_BORDER);
-    t.rw = maxX - t.iniX; t.rh = maxY - t.iniY;
-    t.dw = t.rw - 6; t.dh = t.rh - 6;          // detection area of the strip, ROI-relative origin (3,3)
-    t.ax = 16 + (t.iniX & 15);                 // tile byte of ROI column 0: TMA boxes start on 16-byte columns; one 16-byte unit of left margin
+    // cell ROI in image coordinates — ORBextractor.cpp:805-822
+    t.iniX = ORBX_BORDER + t.cj * t.wcell; t.iniY = ORBX_BORDER + t.ci * t.hcell;
+    const int maxX = min(t.iniX + t.wcell + 6, g.w - ORBX_BORDER), maxY = min(t.iniY + t.hcell + 6, g.h - ORBX_BORDER);
+    t.dw = maxX - t.iniX - 6; t.dh = maxY - t.iniY - 6;      // detection area, ROI-relative origin (3,3)
+    t.ax = t.iniX & 15;                                      // tile byte of ROI column 0 (TMA boxes start on 16-byte columns)
     return t;
 }
 
-__global__ void __launch_bounds__(FS_THREADS) k_fast_cells(const __grid_constant__ LevelMaps M, FastParams P, const FrameGeom *__restrict__ G)
+__global__ void __launch_bounds__(32) k_fast_cells(const __grid_constant__ LevelMaps M, FastParams P, const FrameGeom *__restrict__ G)
 {
-    extern __shared__ __align__(128) uint8_t s_dyn_raw[];
-    uint8_t *s_dyn = s_dyn_raw + ((128u - (smem_u32(s_dyn_raw) & 127u)) & 127u);      // TMA destinations are 128-byte aligned
-    __shared__ uint16_t s_q[FS_QCAP];
-    __shared__ uint32_t s_out[FS_OUT_CAP];
-    __shared__ __align__(8) uint64_t s_full[2];
-    __shared__ int s_qn, s_nout;
-    __shared__ int s_ccnt[FS_MAX_CELLS];
-    const int tile_bytes = ((P.tile_rows + FS_PADROWS) * FS_TP + 127) & ~127;
-    uint8_t *s_sc = s_dyn + FS_NBUF * tile_bytes;                          // (tile_rows - 4) x FS_SP score map with a zero ring
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    __shared__ __align__(8) uint64_t s_full;
+    uint8_t *s_dyn = s_raw + ((128u - (smem_u32(s_raw) & 127u)) & 127u);
+    // layout: [queue | score map | tile]; the word left of tile column 0 (read, never used) falls into the map
+    uint16_t *wq = reinterpret_cast<uint16_t *>(s_dyn);
+    uint8_t *s_sc = s_dyn + FS_WQ * 2;                                                  // (tile_rows - 4) x map_pitch, zero ring
+    const int SP = P.map_pitch;
+    const int map_bytes = (((P.tile_rows - 4) * SP) + 127) & ~127;
+    uint8_t *s_img = s_sc + map_bytes;                                                   // (tile_rows + FS_PADROWS) x FS_TP, 128-byte aligned
+    const int lane = threadIdx.x;
     const int nl = G->nlevels;
 
-    if (threadIdx.x == 0) {
-        mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+    if (lane == 0) {
+        mbar_init(&s_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    __syncthreads();
-    // prologue: the first item's tile
-    if (FS_NBUF == 2 && threadIdx.x == 0 && (int)blockIdx.x < P.nitems) {
-        const FastItem t = fast_item(P, G, blockIdx.x);
-        mbar_expect_tx(&s_full[0], (uint32_t)((t.hcell + 6) * FS_TP));
-        tma_load_3d(s_dyn, &M.m[t.level], ((t.iniX & ~15) >> 2) - 4, t.iniY, t.f, &s_full[0]);
-    }
+    __syncwarp();
 
     int it_n = 0;
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x, it_n++) {
-        const int buf = FS_NBUF == 2 ? (it_n & 1) : 1;
-        // next item's tile into the other buffer (its previous readers passed the barrier that ended the last iteration)
-        if (threadIdx.x == 0 && (FS_NBUF == 1 || item + (int)gridDim.x < P.nitems)) {
-            const FastItem t = fast_item(P, G, FS_NBUF == 2 ? item + gridDim.x : item);
-            mbar_expect_tx(&s_full[buf ^ 1], (uint32_t)((t.hcell + 6) * FS_TP));
-            tma_load_3d(s_dyn + (FS_NBUF == 2 ? (buf ^ 1) : 0) * tile_bytes, &M.m[t.level], ((t.iniX & ~15) >> 2) - 4, t.iniY, t.f, &s_full[buf ^ 1]);
-        }
         const FastItem T = fast_item(P, G, item);
         const LevelGeom &g = G->lv[T.level];
-        const int ax = T.ax, dw = T.dw, dh = T.dh, wcell = T.wcell;
-        const uint8_t *s_img = s_dyn + (FS_NBUF == 2 ? buf : 0) * tile_bytes;
+        const int ax = T.ax, dw = T.dw, dh = T.dh;
+        if (lane == 0) {
+            // every lane finished reading the previous tile (the __syncwarp that ends the loop body)
+            mbar_expect_tx(&s_full, (uint32_t)((T.hcell + 6) * FS_TP));
+            tma_load_3d(s_img, &M.m[T.level], (T.iniX & ~15) >> 2, T.iniY, T.f, &s_full);
+            if (item + (int)gridDim.x < P.nitems) {                                     // next cell's window -> L2
+                const FastItem N = fast_item(P, G, item + gridDim.x);
+                tma_prefetch_3d(&M.m[N.level], (N.iniX & ~15) >> 2, N.iniY, N.f);
+            }
+        }
         // zero the score map (1-px ring included) while the tile lands
-        for (int i = threadIdx.x; i < ((dh + 2) * FS_SP) / 16; i += FS_THREADS) reinterpret_cast<uint4 *>(s_sc)[i] = make_uint4(0, 0, 0, 0);
-        if (threadIdx.x == 0) { s_nout = 0; s_qn = 0; }
-        if (threadIdx.x < FS_MAX_CELLS) s_ccnt[threadIdx.x] = 0;
-        mbar_wait(&s_full[FS_NBUF == 2 ? buf : 0], (uint32_t)(FS_NBUF == 2 ? ((it_n >> 1) & 1) : (it_n & 1)));
-        __syncthreads();
+        for (int i = lane; i < ((dh + 2) * SP) / 16; i += 32) reinterpret_cast<uint4 *>(s_sc)[i] = make_uint4(0, 0, 0, 0);
+        mbar_wait(&s_full, (uint32_t)(it_n & 1));
+        __syncwarp();
 
         const int w0 = (ax + 3) >> 2;                                  // tile word holding detection column 0
-        const int nGs = ((ax + 3 + dw - 1) >> 2) - w0 + 1;             // words holding detection columns (<= 64)
+        const int nG = ((ax + 3 + dw - 1) >> 2) - w0 + 1;              // words holding detection columns (<= 19)
         const int nseg = (dh + 6) / 7;
+        const int units = nG * nseg;
+        const float inv = 1.0f / (float)nG;
         const uint32_t *words = reinterpret_cast<const uint32_t *>(s_img);
         uint32_t *gdst = P.cand + (size_t)T.f * P.cand_slab + g.cand_off;
         int32_t *gcnt = &P.ncand[T.f * nl + T.level];
-        const float invc = 1.0f / (float)wcell;
-        // pass 0: every cell at iniThFAST.  pass 1: the cells that produced nothing, at minThFAST (the reference's retry, :843-846).
-        // Both passes are block-wide, so the retry of one or two cells is spread over all warps instead of stalling them.
-        int nredo = 0;
-        uint32_t redo_cells = 0u, redo_mask = 0u;                       // pass 1: up to 8 cell indices, 4 bits each / bit per cell (uniform)
         for (int pass = 0; pass < 2; pass++) {
             const int th = pass == 0 ? P.ini_th : P.min_th;
             uint32_t HM, KK;
             fast_masks(th, HM, KK);
-            // ---- packed sweep: pass 0 = all words of the strip, pass 1 = the words of the retried cells ----
-            int units = nGs * nseg;
-            if (pass == 1) {
-                units = 0;
-                for (int r = 0; r < nredo; r++) {
-                    const int c = (int)((redo_cells >> (4 * r)) & 15u), c_lo = c * wcell, c_hi = min(c_lo + wcell, dw);
-                    units += ((((ax + 3 + c_hi - 1) >> 2) - ((ax + 3 + c_lo) >> 2)) + 1) * nseg;
-                }
-            }
-            for (int u0 = 0; u0 < units; u0 += FS_THREADS) {
-                const int u = u0 + threadIdx.x;
+            int qn = 0;
+            bool ovf = false;
+            // ---- packed sweep + compaction into the warp's queue ----
+            for (int u0 = 0; u0 < units; u0 += 32) {
+                const int u = u0 + lane;
                 uint32_t word = 0u;
                 int base_off = 0;
                 if (u < units) {
-                    int uu = u, gfirst = 0, nG = nGs, c_lo = 0, c_hi = dw;
-                    if (pass == 1) {
-                        for (int r = 0; r < nredo; r++) {
-                            const int c = (int)((redo_cells >> (4 * r)) & 15u);
-                            c_lo = c * wcell; c_hi = min(c_lo + wcell, dw);
-                            gfirst = ((ax + 3 + c_lo) >> 2) - w0; nG = ((ax + 3 + c_hi - 1) >> 2) - w0 - gfirst + 1;
-                            if (uu < nG * nseg) break;
-                            uu -= nG * nseg;
-                        }
-                    }
-                    const int seg = __float2int_rd(((float)uu + 0.5f) / (float)nG), gidx = gfirst + uu - seg * nG;
+                    const int seg = __float2int_rd(((float)u + 0.5f) * inv), gidx = u - seg * nG;
                     const uint32_t raw = fast_sweep7(words + (7 * seg) * FS_TPW + w0 + gidx, HM, KK);
                     const int cb = 4 * (w0 + gidx) - (ax + 3);                // detection column of byte 0
                     uint32_t cm = 0u;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) if (cb + j >= c_lo && cb + j < c_hi) cm |= 0xFEu << (8 * j);
+                    for (int j = 0; j < 4; j++) if (cb + j >= 0 && cb + j < dw) cm |= 0xFEu << (8 * j);
                     const int nv = min(7, dh - 7 * seg);
                     word = raw & cm & (((0xFF00u >> nv) & 0xFFu) * 0x01010101u);
                     base_off = (7 * seg + 3) * FS_TP + 4 * (w0 + gidx);
@@ -262,82 +225,71 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_cells(const __grid_constant
                 int incl = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-                int wbase = 0;
-                if (lane == 31 && incl > 0) wbase = atomicAdd(&s_qn, incl);
-                wbase = __shfl_sync(0xffffffffu, wbase, 31);
-                int slot = wbase + incl - cnt;
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                if (qn + total > FS_WQ) {                                     // queue full: score what is queued, NMS will scan the cell
+                    __syncwarp();
+                    for (int i = lane; i < qn; i += 32) {
+                        const int off = wq[i];
+                        const int s = fast_score_packed(s_img + off);
+                        const int tr = off / FS_TP, tc = off - tr * FS_TP - ax;
+                        s_sc[(tr - 2) * SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
+                    }
+                    __syncwarp();
+                    qn = 0; ovf = true;
+                }
+                int slot = qn + incl - cnt;
                 while (word) {
                     const int bit = __ffs((int)word) - 1;
                     word &= word - 1;
-                    if (slot < FS_QCAP) s_q[slot] = (uint16_t)(base_off + (7 - (bit & 7)) * FS_TP + (bit >> 3));
-                    slot++;
+                    wq[slot++] = (uint16_t)(base_off + (7 - (bit & 7)) * FS_TP + (bit >> 3));
                 }
+                qn += total;
             }
-            __syncthreads();
-            const bool ovf = s_qn > FS_QCAP;                            // uniform
-            const int qn = ovf ? 0 : s_qn;
-            // ---- exact score (ROI coords = detection coords + 3): queue entries, or every pixel if the queue overflowed ----
-            if (!ovf) {
-                for (int i = threadIdx.x; i < qn; i += FS_THREADS) {
-                    const int off = s_q[i];
-                    const int s = fast_score_packed(s_img + off);
-                    const int tr = off / FS_TP, tc = off - tr * FS_TP - ax;
-                    s_sc[(tr - 2) * FS_SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
-                }
-            } else {
-                for (int i = threadIdx.x; i < dw * dh; i += FS_THREADS) {
-                    const int r = i / dw, c = i - r * dw;
-                    const int s = fast_score_packed(s_img + (r + 3) * FS_TP + ax + c + 3);
-                    s_sc[(r + 1) * FS_SP + (c + 1)] = (uint8_t)(s > th ? s - 1 : 0);
-                }
+            __syncwarp();
+            // ---- exact score of the queued survivors (ROI coords = detection coords + 3) ----
+            for (int i = lane; i < qn; i += 32) {
+                const int off = wq[i];
+                const int s = fast_score_packed(s_img + off);
+                const int tr = off / FS_TP, tc = off - tr * FS_TP - ax;
+                s_sc[(tr - 2) * SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
             }
-            __syncthreads();
-            // ---- strict 3x3 NMS inside each cell ----
+            __syncwarp();
+            // ---- strict 3x3 NMS inside the cell: queue entries, or every pixel of the cell if the queue overflowed ----
             const int nitems = ovf ? dw * dh : qn;
-            for (int i = threadIdx.x; i < nitems; i += FS_THREADS) {
-                int r, c;
-                if (ovf) { r = i / dw; c = i - r * dw; }
-                else { const int off = s_q[i]; const int tr = off / FS_TP; r = tr - 3; c = off - tr * FS_TP - ax - 3; }
-                const uint8_t *q = &s_sc[(r + 1) * FS_SP + (c + 1)];
-                const int s = q[0];
-                if (s == 0) continue;
-                const int cell = min(__float2int_rd(((float)c + 0.5f) * invc), T.ncell - 1);
-                if (pass == 1 && !((redo_mask >> cell) & 1u)) continue;   // (overflow scan only: cells that already have keypoints)
-                const int c_lo = cell * wcell, c_hi = min(c_lo + wcell, dw);
-                bool ok = s > q[-FS_SP] && s > q[FS_SP];
-                if (c > c_lo) ok = ok && s > q[-1] && s > q[-FS_SP - 1] && s > q[FS_SP - 1];
-                if (c < c_hi - 1) ok = ok && s > q[1] && s > q[-FS_SP + 1] && s > q[FS_SP + 1];
-                if (ok) {
-                    if (pass == 0) atomicAdd(&s_ccnt[cell], 1);
-                    // box-relative coordinates: kp.pt + (j*wCell, i*hCell) — ORBextractor.cpp:865-866
-                    const uint32_t val = orbx_pack(T.cj0 * wcell + c + 3, T.ci * T.hcell + r + 3, s);
-                    const int o = atomicAdd(&s_nout, 1);
-                    if (o < FS_OUT_CAP) s_out[o] = val;
-                    else {                                                    // staging full: straight to the global list
-                        const int go = atomicAdd(gcnt, 1);
-                        if (go < g.cand_cap) gdst[go] = val; else atomicOr(P.status, ORBX_DS_CAND_OVERFLOW);
+            const float invw = 1.0f / (float)dw;
+            int found = 0;
+            for (int i0 = 0; i0 < nitems; i0 += 32) {
+                const int i = i0 + lane;
+                bool ok = false;
+                int r = 0, c = 0, s = 0;
+                if (i < nitems) {
+                    if (ovf) { r = __float2int_rd(((float)i + 0.5f) * invw); c = i - r * dw; }
+                    else { const int off = wq[i]; const int tr = off / FS_TP; r = tr - 3; c = off - tr * FS_TP - ax - 3; }
+                    const uint8_t *q = &s_sc[(r + 1) * SP + (c + 1)];
+                    s = q[0];
+                    // the zero ring around the map stands for "outside the cell's detection area"
+                    if (s != 0) ok = s > q[-SP] && s > q[SP] && s > q[-1] && s > q[-SP - 1] && s > q[SP - 1] && s > q[1] && s > q[-SP + 1] && s > q[SP + 1];
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, ok);
+                if (bal) {
+                    const int nk = __popc(bal);
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(gcnt, nk);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (ok) {
+                        // box-relative coordinates: kp.pt + (j*wCell, i*hCell) — ORBextractor.cpp:865-866
+                        const int go = base + __popc(bal & ((1u << lane) - 1u));
+                        if (go < g.cand_cap) gdst[go] = orbx_pack(T.cj * T.wcell + c + 3, T.ci * T.hcell + r + 3, s);
+                        else atomicOr(P.status, ORBX_DS_CAND_OVERFLOW);
                     }
+                    found += nk;
                 }
             }
-            __syncthreads();
-            if (pass == 1) break;
-            for (int c = 0; c < T.ncell; c++) if (s_ccnt[c] == 0) { redo_cells |= (uint32_t)c << (4 * nredo); redo_mask |= 1u << c; nredo++; }
-            if (nredo == 0) break;
-            if (threadIdx.x == 0) s_qn = 0;
-            __syncthreads();
+            // the reference retries a cell at minThFAST iff iniThFAST produced nothing (:843-846)
+            if (found > 0 || pass == 1) break;
+            __syncwarp();
         }
-        // ---- flush the item's candidates: one global atomic, warp 0 ----
-        if (warp == 0) {
-            const int n = min(s_nout, FS_OUT_CAP);
-            if (n > 0) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(gcnt, n);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                for (int i = lane; i < n; i += 32) if (base + i < g.cand_cap) gdst[base + i] = s_out[i];
-                if (lane == 0 && base + n > g.cand_cap) atomicOr(P.status, ORBX_DS_CAND_OVERFLOW);
-            }
-        }
-        __syncthreads();                                                // every reader of tile `buf` and of the queues is done
+        __syncwarp();                                                   // every lane is done with the tile, the map and the queue
     }
 }
 
@@ -358,16 +310,15 @@ static PFN_tmapEncodeTiled get_encode()
 }
 
 // level as a 3-D tensor of u32 elements: (row pitch / 4) x rows x frames; box = FS_TPW x (hCell + 6) x 1, zero fill outside
-static bool encode_level(CUtensorMap *m, const uint8_t *base, size_t pitch, int rows, size_t fstride, int frames, int box_rows)
+static bool encode_level(CUtensorMap *m, const uint8_t *base, size_t pitch, int rows, size_t fstride, int frames, int box_rows, int box_words = ORBX_TMA_BOX_WORDS)
 {
-    static_assert(FS_TPW == ORBX_TMA_BOX_WORDS, "FAST tile pitch = TMA box width");
     PFN_tmapEncodeTiled enc = get_encode();
     if (!enc || ((uintptr_t)base & 15) || (pitch & 15) || pitch == 0) return false;
     if (frames <= 1 || fstride < pitch) { frames = 1; fstride = pitch * (size_t)rows; }
     fstride = (fstride + 15) & ~(size_t)15;
     const cuuint64_t dims[3] = { (cuuint64_t)(pitch / 4), (cuuint64_t)rows, (cuuint64_t)frames };
     const cuuint64_t strides[2] = { (cuuint64_t)pitch, (cuuint64_t)fstride };
-    const cuuint32_t box[3] = { ORBX_TMA_BOX_WORDS, (cuuint32_t)box_rows, 1 };
+    const cuuint32_t box[3] = { (cuuint32_t)box_words, (cuuint32_t)box_rows, 1 };
     const cuuint32_t estr[3] = { 1, 1, 1 };
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -380,12 +331,14 @@ int orbx_ensure_tmaps(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_
     if (!h->tmap_valid) {
         for (int l = 1; l < G.nlevels; l++)
             if (!encode_level(&h->tmap[l], h->d_pyr + G.lv[l].off, (size_t)G.lv[l].pitch, G.lv[l].h, h->pyr_slab, h->prm.max_batch, G.lv[l].hcell + 6) ||
-                !encode_level(&h->tmap_rz[l], h->d_pyr + G.lv[l].off, (size_t)G.lv[l].pitch, G.lv[l].h, h->pyr_slab, h->prm.max_batch, ORBX_RZ_BOX_ROWS)) return -1;
+                !encode_level(&h->tmap_rz[l], h->d_pyr + G.lv[l].off, (size_t)G.lv[l].pitch, G.lv[l].h, h->pyr_slab, h->prm.max_batch, ORBX_RZ_BOX_ROWS) ||
+                !encode_level(&h->tmap_cell[l], h->d_pyr + G.lv[l].off, (size_t)G.lv[l].pitch, G.lv[l].h, h->pyr_slab, h->prm.max_batch, G.lv[l].hcell + 6, FS_TPW)) return -1;
         h->tmap_valid = true; h->tmap_l0 = nullptr;
     }
     if (h->tmap_l0 != l0 || h->tmap_l0_step != l0_step || h->tmap_l0_fstride != l0_fstride || h->tmap_l0_frames < nframes) {
         if (!encode_level(&h->tmap[0], l0, l0_step, G.lv[0].h, l0_fstride, nframes, G.lv[0].hcell + 6) ||
-            !encode_level(&h->tmap_rz[0], l0, l0_step, G.lv[0].h, l0_fstride, nframes, ORBX_RZ_BOX_ROWS)) return -1;
+            !encode_level(&h->tmap_rz[0], l0, l0_step, G.lv[0].h, l0_fstride, nframes, ORBX_RZ_BOX_ROWS) ||
+            !encode_level(&h->tmap_cell[0], l0, l0_step, G.lv[0].h, l0_fstride, nframes, G.lv[0].hcell + 6, FS_TPW)) return -1;
         h->tmap_l0 = l0; h->tmap_l0_step = l0_step; h->tmap_l0_fstride = l0_fstride; h->tmap_l0_frames = nframes;
     }
     return 0;
@@ -394,29 +347,30 @@ int orbx_ensure_tmaps(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_
 int launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride)
 {
     const FrameGeom &G = h->geo;
-    if (G.total_strips <= 0) return 0;
+    if (G.total_cells_valid <= 0) return 0;
     if (orbx_ensure_tmaps(h, nframes, l0, l0_step, l0_fstride) != 0) return -1;
     LevelMaps M;
-    memcpy(M.m, h->tmap, sizeof(M.m));
+    memcpy(M.m, h->tmap_cell, sizeof(M.m));
     FastParams P;
     P.cand = h->d_cand; P.cand_slab = G.cand_entries;
     P.ncand = h->d_ncand;
-    P.strips = h->d_strips; P.nstrips = G.total_strips; P.nitems = G.total_strips * nframes;
+    P.cells = h->d_cells; P.ncells = G.total_cells_valid; P.nitems = G.total_cells_valid * nframes;
     P.ini_th = h->prm.ini_th_fast; P.min_th = h->prm.min_th_fast;
     P.status = h->d_status;
     P.tile_rows = G.max_hcell + 6;
-    const int tile_bytes = ((P.tile_rows + FS_PADROWS) * FS_TP + 127) & ~127;
-    const size_t smem = 128 + FS_NBUF * (size_t)tile_bytes + (size_t)(P.tile_rows - 4) * FS_SP;
+    P.map_pitch = (G.max_wcell + 2 + 15) & ~15;
+    const size_t map_bytes = (size_t)((((P.tile_rows - 4) * P.map_pitch) + 127) & ~127);
+    const size_t smem = 128 + FS_WQ * 2 + map_bytes + (size_t)(P.tile_rows + FS_PADROWS) * FS_TP;
     static size_t configured = 0;
     if (smem > configured || h->fast_grid_cap <= 0) {
         cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = std::max(configured, smem);
         int occ = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fast_cells, FS_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fast_cells, 32, smem);
         h->fast_grid_cap = std::max(1, occ) * h->sm_count;
     }
     const int grid = std::min(P.nitems, h->fast_grid_cap);
     ProfScope ps(h, ORBX_K_FAST);
-    k_fast_cells<<<grid, FS_THREADS, smem, h->stream>>>(M, P, h->d_geo);
+    k_fast_cells<<<grid, 32, smem, h->stream>>>(M, P, h->d_geo);
     return 0;
 }

@@ -75,13 +75,14 @@ static void resize_table(int ssize, int dsize, bool horizontal, ResizeTab *out)
 
 // geometry for one input size; returns false when the reference itself is undefined for it
 static bool build_geometry(const orbx_handle *h, int w, int hgt, FrameGeom &G, std::vector<ResizeTab> *xt, std::vector<ResizeTab> *yt,
-                           std::vector<uint32_t> *strip_tab = nullptr, std::vector<uint32_t> *blur_tab = nullptr)
+                           std::vector<uint32_t> *strip_tab = nullptr, std::vector<uint32_t> *blur_tab = nullptr,
+                           std::vector<uint32_t> *cell_tab = nullptr)
 {
     memset(&G, 0, sizeof(G));
     const orbx_params &p = h->prm;
     G.nlevels = p.nlevels; G.width = w; G.height = hgt;
     const int cdiv = p.cand_divisor > 0 ? p.cand_divisor : 16;
-    size_t off = 0, boff = 0, coff = 0; int soff = 0, cells = 0, tiles = 0, ncmax = 8, strips = 0, max_hcell = 1;
+    size_t off = 0, boff = 0, coff = 0; int soff = 0, cells = 0, tiles = 0, ncmax = 8, strips = 0, max_hcell = 1, max_wcell = 1, cells_valid = 0;
     for (int l = 0; l < p.nlevels; l++) {
         LevelGeom &g = G.lv[l];
         g.w = cv_round_f((float)w * h->inv_scale[l]);                     // ORBextractor.cpp:1174
@@ -110,7 +111,15 @@ static bool build_geometry(const orbx_handle *h, int w, int hgt, FrameGeom &G, s
             max_hcell = std::max(max_hcell, g.hcell);
         } else { g.strips_per_row = 0; g.cells_per_strip = 1; }
         g.strip_first = strips; strips += g.strips_per_row * g.nrows;
-        // strip descriptors for k_fast_cells: level:4 | cells:4 | cell row:12 | first cell column:12.  Cells the reference
+        // cell descriptors for k_fast_cells: level:4 | cell row:14 | cell column:14.  Cells the reference skips
+        // (iniY >= maxBorderY-3, iniX >= maxBorderX-6; ORBextractor.cpp:811-816) are left out.
+        for (int ci = 0; ci < g.nrows; ci++) for (int cj = 0; cj < g.ncols; cj++) {
+            if (ORBX_BORDER + ci * g.hcell >= g.h - ORBX_BORDER - 3 || ORBX_BORDER + cj * g.wcell >= g.w - ORBX_BORDER - 6) continue;
+            cells_valid++;
+            if (cell_tab) cell_tab->push_back((uint32_t)l | ((uint32_t)ci << 4) | ((uint32_t)cj << 18));
+        }
+        if (g.ncols > 0) max_wcell = std::max(max_wcell, g.wcell);
+        // strip descriptors (unused by the warp-per-cell FAST kernel, kept for the geometry report): level:4 | cells:4 | cell row:12 | first cell column:12.  Cells the reference
         // skips (iniY >= maxBorderY-3, iniX >= maxBorderX-6; ORBextractor.cpp:811-816) are trimmed here.
         if (strip_tab) for (int ci = 0; ci < g.nrows; ci++) for (int sj = 0; sj < g.strips_per_row; sj++) {
             const int maxBX = g.w - ORBX_BORDER, maxBY = g.h - ORBX_BORDER;
@@ -159,7 +168,7 @@ static bool build_geometry(const orbx_handle *h, int w, int hgt, FrameGeom &G, s
         if (!fits) { if (rtw > 16) rtw -= 16; if (rth > 8) rth -= 8; if (rtw <= 16 && rth <= 8) return false; }
     }
     G.rz_tw = rtw; G.rz_th = rth;
-    G.total_cells = cells; G.total_blur_tiles = tiles; G.total_strips = std::max(strips, 1); G.max_hcell = max_hcell;
+    G.total_cells = cells; G.total_blur_tiles = tiles; G.total_strips = std::max(strips, 1); G.max_hcell = max_hcell; G.max_wcell = max_wcell; G.total_cells_valid = cells_valid;
     G.pyr_bytes = std::max<size_t>(off, 256); G.blur_bytes = boff; G.cand_entries = coff; G.sel_entries = soff; G.node_cap_max = ncmax;
     return true;
 }
@@ -169,18 +178,19 @@ static orbx_status set_geometry(orbx_handle *h, int w, int hgt)
     if (h->geo.width == w && h->geo.height == hgt) return ORBX_OK;
     if (w > h->prm.max_width || hgt > h->prm.max_height) { h->err = "frame larger than max_width x max_height"; return ORBX_E_INVALID; }
     if (w > 4096 + 2 * ORBX_BORDER || hgt > 4096 + 2 * ORBX_BORDER) { h->err = "frame larger than 4128 px"; return ORBX_E_UNSUPPORTED; }
-    FrameGeom G; std::vector<ResizeTab> xt, yt; std::vector<uint32_t> strips, btiles;
-    if (!build_geometry(h, w, hgt, G, &xt, &yt, &strips, &btiles)) { h->err = "unsupported frame geometry (aspect ratio gives 0 or > 64 quadtree roots, or a level vanishes)"; return ORBX_E_UNSUPPORTED; }
+    FrameGeom G; std::vector<ResizeTab> xt, yt; std::vector<uint32_t> strips, btiles, ctab;
+    if (!build_geometry(h, w, hgt, G, &xt, &yt, &strips, &btiles, &ctab)) { h->err = "unsupported frame geometry (aspect ratio gives 0 or > 64 quadtree roots, or a level vanishes)"; return ORBX_E_UNSUPPORTED; }
     const size_t B = (size_t)h->prm.max_batch;
     if (G.pyr_bytes * B > h->pyr_cap || G.blur_bytes * B > h->blur_cap || G.cand_entries * B > h->cand_cap ||
         (size_t)G.sel_entries * B > h->sel_cap || (int)xt.size() > h->tab_cap || (int)yt.size() > h->tab_cap ||
-        G.sel_entries > h->max_kp || (int)strips.size() > h->strip_cap || (int)btiles.size() > h->blur_tile_cap) { h->err = "frame geometry does not fit the arenas sized at create"; return ORBX_E_INVALID; }
+        G.sel_entries > h->max_kp || (int)strips.size() > h->strip_cap || (int)btiles.size() > h->blur_tile_cap || (int)ctab.size() > h->cell_cap) { h->err = "frame geometry does not fit the arenas sized at create"; return ORBX_E_INVALID; }
     G.total_strips = (int)strips.size();
     ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
     ORBX_CUDA(h, cudaMemcpy(h->d_geo, &G, sizeof(G), cudaMemcpyHostToDevice));
     if (!xt.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_xtab, xt.data(), xt.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
     if (!yt.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_ytab, yt.data(), yt.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
     if (!strips.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_strips, strips.data(), strips.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (!ctab.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_cells, ctab.data(), ctab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     if (!btiles.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_blur_tiles, btiles.data(), btiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     G.total_strips = (int)strips.size();
     h->geo = G; h->pyr_slab = G.pyr_bytes; h->blur_slab = G.blur_bytes; h->tmap_valid = false;
@@ -193,7 +203,7 @@ extern "C" void orbx_destroy(orbx_handle *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
-    void *dev[] = { h->d_blur_tiles, h->d_strips, h->d_prev_desc, h->d_prev_count, h->d_geo, h->d_xtab, h->d_ytab, h->d_pyr, h->d_blur, h->d_in, h->d_depth_in, h->d_cand, h->d_cand2, h->d_qtmp,
+    void *dev[] = { h->d_cells, h->d_blur_tiles, h->d_strips, h->d_prev_desc, h->d_prev_count, h->d_geo, h->d_xtab, h->d_ytab, h->d_pyr, h->d_blur, h->d_in, h->d_depth_in, h->d_cand, h->d_cand2, h->d_qtmp,
                     h->d_owner, h->d_owner2, h->d_ncand, h->d_sel, h->d_nsel, h->d_kps_all, h->d_desc_all, h->d_count_all,
                     h->d_kps_out, h->d_desc_out, h->d_count_out, h->d_boxes, h->d_status, h->d_mpart, h->d_mq, h->d_mt, h->d_mout, h->d_mcount };
     for (void *p : dev) if (p) cudaFree(p);
@@ -269,6 +279,8 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     CREATE_CUDA(cudaMalloc(&h->d_geo, sizeof(FrameGeom)));
     h->strip_cap = G.total_cells + 64 * p.nlevels;
     CREATE_CUDA(cudaMalloc(&h->d_strips, sizeof(uint32_t) * h->strip_cap));
+    h->cell_cap = G.total_cells + G.total_cells / 4 + 64 * p.nlevels;
+    CREATE_CUDA(cudaMalloc(&h->d_cells, sizeof(uint32_t) * h->cell_cap));
     h->blur_tile_cap = G.total_blur_tiles + G.total_blur_tiles / 4 + 64 * p.nlevels;
     CREATE_CUDA(cudaMalloc(&h->d_blur_tiles, sizeof(uint32_t) * h->blur_tile_cap));
     CREATE_CUDA(cudaMalloc(&h->d_xtab, sizeof(ResizeTab) * h->tab_cap));

@@ -50,7 +50,7 @@ struct LevelGeom {
 struct FrameGeom {
     int nlevels;
     int width, height;
-    int total_cells, total_blur_tiles, total_strips, max_hcell;
+    int total_cells, total_blur_tiles, total_strips, max_hcell, max_wcell, total_cells_valid;
     int rz_tw, rz_th;        // output tile of the resize kernel: its source window fits the 288-byte x 80-row TMA box at every level
     size_t pyr_bytes;        // per-frame pyramid slab size (levels 1..)
     size_t blur_bytes;       // per-frame blurred slab size (levels 0..)
@@ -92,6 +92,8 @@ struct orbx_handle {
     // TMA tensor maps of the pyramid levels (k_fast.cu): levels >= 1 depend on the geometry only, level 0 on the caller's frames
     CUtensorMap tmap[ORBX_MAX_LEVELS]; bool tmap_valid;      // box rows = hCell + 6 (FAST strips, blur tiles)
     CUtensorMap tmap_rz[ORBX_MAX_LEVELS];                    // box rows = ORBX_RZ_BOX_ROWS (resize source windows)
+    CUtensorMap tmap_cell[ORBX_MAX_LEVELS];                  // box = 96 bytes x (hCell + 6) rows (FAST cell windows)
+    uint32_t *d_cells; int cell_cap;                         // FAST cell descriptors (k_fast.cu)
     const uint8_t *tmap_l0; size_t tmap_l0_step, tmap_l0_fstride; int tmap_l0_frames;
     int fast_grid_cap;                   // resident CTAs of the persistent FAST kernel
     // arenas, sized for max_width x max_height x max_batch
