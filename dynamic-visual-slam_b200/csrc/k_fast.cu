@@ -39,7 +39,7 @@
 #define FS_TP 96                 // tile pitch = TMA box width: 24 u32 elements >= 15 (alignment) + 69 + 6 (widest cell ROI) + 4
 #define FS_TPW (FS_TP / 4)
 #define FS_PADROWS 6             // rows behind the tile: a 7-row sweep unit may start on the last detection row
-#define FS_WQ 1024               // survivor queue (u16 tile offsets) >= 32 lanes x 28 flags
+#define FS_WQ 512                // survivor queue (u16 tile offsets); a sweep step with more survivors than this is scored in place
 
 struct FastParams {
     uint32_t *cand; size_t cand_slab;
@@ -236,6 +236,17 @@ __global__ void __launch_bounds__(32) k_fast_cells(const __grid_constant__ Level
                     }
                     __syncwarp();
                     qn = 0; ovf = true;
+                    if (total > FS_WQ) {                                      // this step alone does not fit: score its survivors in place
+                        while (word) {
+                            const int bit = __ffs((int)word) - 1;
+                            word &= word - 1;
+                            const int off = base_off + (7 - (bit & 7)) * FS_TP + (bit >> 3);
+                            const int s = fast_score_packed(s_img + off);
+                            const int tr = off / FS_TP, tc = off - tr * FS_TP - ax;
+                            s_sc[(tr - 2) * SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
+                        }
+                        continue;
+                    }
                 }
                 int slot = qn + incl - cnt;
                 while (word) {
