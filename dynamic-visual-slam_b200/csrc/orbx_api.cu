@@ -873,6 +873,8 @@ extern "C" void orbx_db_destroy(orbx_db *db)
     if (db->d_rows) cudaFree(db->d_rows);
     if (db->d_q) cudaFree(db->d_q);
     if (db->d_out) cudaFree(db->d_out);
+    if (db->d_pos) cudaFree(db->d_pos);
+    if (db->d_qpx) cudaFree(db->d_qpx);
     delete db;
 }
 extern "C" int64_t orbx_db_rows(const orbx_db *db) { return db ? db->rows : 0; }
@@ -958,6 +960,64 @@ extern "C" orbx_status orbx_db_query_radius(orbx_db *db, const uint8_t *q, int32
     if (n > cap) { h->err = "radius output capacity too small"; return ORBX_E_CAPACITY; }
     if (n > 0) ORBX_CUDA(h, cudaMemcpy(out, db->d_out, (size_t)n * sizeof(orbx_dmatch), cudaMemcpyDeviceToHost));
     std::sort(out, out + n, [](const orbx_dmatch &a, const orbx_dmatch &b) { return a.queryIdx != b.queryIdx ? a.queryIdx < b.queryIdx : a.trainIdx < b.trainIdx; });
+    return ORBX_OK;
+}
+
+// ---- reprojection-gated association (Backend::associateObservation, backend.cpp:1064-1120) ----
+static orbx_status db_positions(orbx_db *db, int64_t first, int64_t n, const float *src, cudaMemcpyKind kind)
+{
+    if (!db || first < 0 || n < 0 || (n > 0 && !src)) return ORBX_E_INVALID;
+    orbx_handle *h = db->h; cudaSetDevice(h->device);
+    if (first + n > db->cap) { h->err = "positions beyond the database capacity"; return ORBX_E_CAPACITY; }
+    if (!db->d_pos) {
+        ORBX_CUDA(h, cudaMalloc(&db->d_pos, (size_t)db->cap * 3 * sizeof(float)));
+        ORBX_CUDA(h, cudaMemsetAsync(db->d_pos, 0, (size_t)db->cap * 3 * sizeof(float), h->stream));
+    }
+    if (n > 0) ORBX_CUDA(h, cudaMemcpyAsync(db->d_pos + (size_t)first * 3, src, (size_t)n * 3 * sizeof(float), kind, h->stream));
+    if (kind == cudaMemcpyHostToDevice) ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+extern "C" orbx_status orbx_db_set_positions(orbx_db *db, int64_t first, int64_t n, const float *xyz) { return db_positions(db, first, n, xyz, cudaMemcpyHostToDevice); }
+extern "C" orbx_status orbx_db_set_positions_device(orbx_db *db, int64_t first, int64_t n, const float *d_xyz) { return db_positions(db, first, n, d_xyz, cudaMemcpyDeviceToDevice); }
+
+extern "C" orbx_status orbx_db_associate_device(orbx_db *db, const uint8_t *d_q, const float *d_qpx, int32_t nq, const orbx_pose *pose,
+                                                float max_dist, double max_err, orbx_assoc *d_out)
+{
+    if (!db || nq < 0 || !pose || !d_out || (nq > 0 && (!d_q || !d_qpx))) return ORBX_E_INVALID;
+    orbx_handle *h = db->h; cudaSetDevice(h->device);
+    if (nq == 0) return ORBX_OK;
+    if (db->rows > 0 && !db->d_pos) { h->err = "orbx_db_set_positions has not been called"; return ORBX_E_INVALID; }
+    if (db->rows > 0x7FFFFFFF) { h->err = "shard too large"; return ORBX_E_UNSUPPORTED; }
+    if (launch_assoc(h, d_q, d_qpx, nq, db->d_rows, db->d_pos, (int)db->rows, db->first_index, pose, max_dist, max_err, d_out) != 0) {
+        h->err = "out of device memory (association scratch)"; return ORBX_E_NOMEM;
+    }
+    ORBX_CUDA(h, cudaGetLastError());
+    return ORBX_OK;
+}
+extern "C" orbx_status orbx_db_associate(orbx_db *db, const uint8_t *q, const float *qpx, int32_t nq, const orbx_pose *pose,
+                                         float max_dist, double max_err, orbx_assoc *out)
+{
+    if (!db || nq < 0 || !pose || !out || (nq > 0 && (!q || !qpx))) return ORBX_E_INVALID;
+    orbx_handle *h = db->h; cudaSetDevice(h->device);
+    if (nq == 0) return ORBX_OK;
+    orbx_status st = db_stage_queries(db, q, nq, (size_t)nq * sizeof(orbx_assoc));
+    if (st != ORBX_OK) return st;
+    if ((size_t)nq * 2 * sizeof(float) > db->qpx_cap) {
+        if (db->d_qpx) { cudaStreamSynchronize(h->stream); cudaFree(db->d_qpx); db->d_qpx = nullptr; db->qpx_cap = 0; }
+        ORBX_CUDA(h, cudaMalloc(&db->d_qpx, (size_t)nq * 2 * sizeof(float))); db->qpx_cap = (size_t)nq * 2 * sizeof(float);
+    }
+    ORBX_CUDA(h, cudaMemcpyAsync(db->d_qpx, qpx, (size_t)nq * 2 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    if ((st = orbx_db_associate_device(db, db->d_q, db->d_qpx, nq, pose, max_dist, max_err, (orbx_assoc *)db->d_out)) != ORBX_OK) return st;
+    ORBX_CUDA(h, cudaMemcpyAsync(out, db->d_out, (size_t)nq * sizeof(orbx_assoc), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+extern "C" orbx_status orbx_merge_assoc_device(orbx_handle *h, const orbx_assoc *d_parts, int32_t nshards, int32_t nq, orbx_assoc *d_out)
+{
+    if (!h || !d_parts || !d_out || nshards < 1 || nq < 0) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    launch_assoc_merge(h, d_parts, nshards, nq, d_out);
+    ORBX_CUDA(h, cudaGetLastError());
     return ORBX_OK;
 }
 

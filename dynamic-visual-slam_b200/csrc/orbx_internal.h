@@ -142,6 +142,8 @@ struct ProfScope {
 struct orbx_db {
     orbx_handle *h;
     uint8_t *d_rows; int64_t cap, rows; uint32_t first_index;
+    float *d_pos;                      // landmark positions (xyz per row), allocated by orbx_db_set_positions
+    float *d_qpx; size_t qpx_cap;      // staged query pixels of the host association call
     uint32_t *d_part; size_t part_cap;
     uint8_t *d_q; size_t q_cap; orbx_top2 *d_out; size_t out_cap;
 };
@@ -174,6 +176,9 @@ int  launch_match_core(orbx_handle *h, const uint8_t *d_q, const int32_t *d_nq, 
                        orbx_top2 *d_top2);
 void launch_match_radius(orbx_handle *h, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, uint32_t row_base,
                          float max_dist, orbx_dmatch *d_out, int cap, int32_t *d_n_out);
+int  launch_assoc(orbx_handle *h, const uint8_t *d_q, const float *d_qpx, int nq, const uint8_t *d_t, const float *d_pos, int nt, uint32_t row_base,
+                  const orbx_pose *pose, float max_dist, double max_err, orbx_assoc *d_out);
+void launch_assoc_merge(orbx_handle *h, const orbx_assoc *d_parts, int nparts, int nq, orbx_assoc *d_out);
 void launch_merge_top2(orbx_handle *h, const orbx_top2 *d_parts, int nshards, int nq, orbx_top2 *d_out);
 void launch_synth_gray(orbx_handle *h, uint32_t seed, int first, int n, int w, int hh, uint8_t *d, size_t step, size_t fstride);
 void launch_synth_depth(orbx_handle *h, uint32_t seed, int first, int n, int w, int hh, uint16_t *d, size_t step, size_t fstride);

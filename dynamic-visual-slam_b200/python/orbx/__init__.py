@@ -25,7 +25,10 @@ KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4
 DM_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
 BOX_DTYPE = np.dtype([("cx", "<f8"), ("cy", "<f8"), ("w", "<f8"), ("h", "<f8"), ("class_id", "<i4"), ("pad", "<i4")])
 TOP2_DTYPE = np.dtype([("dist0", "<u4"), ("idx0", "<u4"), ("dist1", "<u4"), ("idx1", "<u4")])
+ASSOC_DTYPE = np.dtype([("reproj_error", "<f8"), ("landmark", "<i4"), ("distance", "<f4")])
+POSE_DTYPE = np.dtype([("R", "<f8", (9,)), ("t", "<f8", (3,)), ("fx", "<f8"), ("fy", "<f8"), ("cx", "<f8"), ("cy", "<f8")])
 assert KP_DTYPE.itemsize == 28 and DM_DTYPE.itemsize == 16 and BOX_DTYPE.itemsize == 40 and TOP2_DTYPE.itemsize == 16
+assert ASSOC_DTYPE.itemsize == 16 and POSE_DTYPE.itemsize == 128
 
 
 class Params(ct.Structure):
@@ -88,6 +91,11 @@ def load():
         "orbx_db_query_top2": (i32, [vp, vp, i32, vp]),
         "orbx_merge_top2_device": (i32, [vp, vp, i32, i32, vp]),
         "orbx_db_query_radius": (i32, [vp, vp, i32, f32, vp, i32, vp]),
+        "orbx_db_set_positions": (i32, [vp, i64, i64, vp]),
+        "orbx_db_set_positions_device": (i32, [vp, i64, i64, vp]),
+        "orbx_db_associate": (i32, [vp, vp, vp, i32, vp, f32, ct.c_double, vp]),
+        "orbx_db_associate_device": (i32, [vp, vp, vp, i32, vp, f32, ct.c_double, vp]),
+        "orbx_merge_assoc_device": (i32, [vp, vp, i32, i32, vp]),
         "orbx_get_pyramid_level": (i32, [vp, i32, i32, vp, sz]),
         "orbx_get_blurred_level": (i32, [vp, i32, i32, vp, sz]),
         "orbx_get_candidates": (i32, [vp, i32, i32, vp, i32, vp]),
@@ -475,6 +483,27 @@ class LandmarkDB:
 
     def query_top2_device(self, d_query, nq, d_out):
         self.ex._check(self.L.orbx_db_query_top2_device(self._db, d_query, nq, d_out))
+
+    def set_positions(self, xyz, first_row=0):
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        self.ex._check(self.L.orbx_db_set_positions(self._db, first_row, len(xyz), _p(xyz)))
+
+    @staticmethod
+    def pose(R, t, fx, fy, cx, cy):
+        p = np.zeros(1, POSE_DTYPE)
+        p["R"][0] = np.asarray(R, np.float64).reshape(9)
+        p["t"][0] = np.asarray(t, np.float64).reshape(3)
+        p["fx"], p["fy"], p["cx"], p["cy"] = fx, fy, cx, cy
+        return p
+
+    def associate(self, query, query_px, pose, max_desc_dist=50.0, max_reproj_err=5.0):
+        """Backend::associateObservation for a batch of observations: ASSOC_DTYPE per observation (landmark = global row or -1)."""
+        query = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+        query_px = np.ascontiguousarray(query_px, np.float32).reshape(-1, 2)
+        out = np.zeros(len(query), ASSOC_DTYPE)
+        self.ex._check(self.L.orbx_db_associate(self._db, _p(query), _p(query_px), len(query), _p(pose), ct.c_float(max_desc_dist),
+                                                ct.c_double(max_reproj_err), _p(out)))
+        return out
 
     def query_radius(self, query, max_dist=50.0, cap=1 << 20):
         query = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)

@@ -52,6 +52,10 @@ typedef struct { int32_t queryIdx, trainIdx, imgIdx; float distance; } orbx_dmat
 typedef struct { double cx, cy, w, h; int32_t class_id; int32_t pad_; } orbx_box;
 /* per-shard top-2 of a landmark-database query (association, backend.cpp:1064-1083) */
 typedef struct { uint32_t dist0, idx0, dist1, idx1; } orbx_top2;
+/* camera pose and intrinsics of Backend::reprojectPoint (backend.cpp:1153-1173): point_camera = R.t() * (X - t), R row-major */
+typedef struct { double R[9]; double t[3]; double fx, fy, cx, cy; } orbx_pose;
+/* result of the reprojection-gated association of one observation: landmark = global row or -1 (backend.cpp:1064-1120) */
+typedef struct { double reproj_error; int32_t landmark; float distance; } orbx_assoc;
 
 typedef struct {
     /* ORBextractor ctor arguments — defaults are the reference's literals, frontend.cpp:205-211 */
@@ -204,6 +208,20 @@ orbx_status orbx_merge_top2_device(orbx_handle *h, const orbx_top2 *d_parts, int
  * (queryIdx, trainIdx = global idx, imgIdx = 0, distance), sorted by (queryIdx, trainIdx).        */
 orbx_status orbx_db_query_radius(orbx_db *db, const uint8_t *query, int32_t nq, float max_dist,
                                  orbx_dmatch *out, int32_t cap, int32_t *n_out);
+
+/* ---- Backend::associateObservation as one call (backend.cpp:1064-1120): descriptor candidates (distance < max_desc_dist), then the
+ * candidate with the smallest reprojection error, if that error is < max_reproj_err.  Landmark positions (float xyz per row, the
+ * reference's cv::Point3f) are attached to the shard's rows with orbx_db_set_positions.  query_px: nq x 2 floats (obs.pixel).
+ * All observations of the call see ONE snapshot of the positions (the reference re-triangulates a landmark right after each
+ * association, backend.cpp:772; a caller that needs that ordering re-submits the affected observations).  Equal errors: lowest row.
+ * Sharded databases: per-shard results -> all-gather -> orbx_merge_assoc_device.                                                  */
+orbx_status orbx_db_set_positions(orbx_db *db, int64_t first_row, int64_t nrows, const float *xyz_host);
+orbx_status orbx_db_set_positions_device(orbx_db *db, int64_t first_row, int64_t nrows, const float *d_xyz);
+orbx_status orbx_db_associate(orbx_db *db, const uint8_t *query, const float *query_px, int32_t nq, const orbx_pose *pose,
+                              float max_desc_dist /*50*/, double max_reproj_err /*5*/, orbx_assoc *out);
+orbx_status orbx_db_associate_device(orbx_db *db, const uint8_t *d_query, const float *d_query_px, int32_t nq, const orbx_pose *pose,
+                                     float max_desc_dist, double max_reproj_err, orbx_assoc *d_out);
+orbx_status orbx_merge_assoc_device(orbx_handle *h, const orbx_assoc *d_parts, int32_t nshards, int32_t nq, orbx_assoc *d_out);
 
 /* ---- stage access for parity tests (the reference exposes mvImagePyramid publicly, ORBextractor.hpp:84) ----
  * Valid after an extract call, for frame slot `frame` of the last batch.  Host outputs.          */

@@ -213,6 +213,31 @@ def knn2(q, t, nthreads=0):
     return out
 
 
+def reproject(p3, R, t, fx, fy, cx, cy):
+    p3 = np.ascontiguousarray(p3, np.float32)
+    R = np.ascontiguousarray(R, np.float64)
+    t = np.ascontiguousarray(t, np.float64).reshape(3)
+    uv = np.zeros(2, np.float32)
+    lib().orc_reproject(_p(p3), _p(R), _p(t), ct.c_double(fx), ct.c_double(fy), ct.c_double(cx), ct.c_double(cy), _p(uv))
+    return uv
+
+
+def associate(q, qpx, rows, pos, R, t, fx, fy, cx, cy, max_desc=50.0, max_reproj=5.0, nthreads=0):
+    """Backend::associateObservation for a batch: returns (landmark row or -1, reprojection error, Hamming distance)."""
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+    qpx = np.ascontiguousarray(qpx, np.float32).reshape(-1, 2)
+    rows = np.ascontiguousarray(rows, np.uint8).reshape(-1, 32)
+    pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+    R = np.ascontiguousarray(R, np.float64)
+    t = np.ascontiguousarray(t, np.float64).reshape(3)
+    idx = np.zeros(len(q), np.int32)
+    err = np.zeros(len(q), np.float64)
+    dist = np.zeros(len(q), np.float32)
+    lib().orc_associate(_p(q), _p(qpx), len(q), _p(rows), _p(pos), len(rows), _p(R), _p(t), ct.c_double(fx), ct.c_double(fy),
+                        ct.c_double(cx), ct.c_double(cy), ct.c_double(max_desc), ct.c_double(max_reproj), _p(idx), _p(err), _p(dist), nthreads)
+    return idx, err, dist
+
+
 def synth_gray(seed, frame, w, h):
     out = np.zeros((h, w), np.uint8)
     lib().orc_synth_gray(ct.c_uint32(seed), frame, w, h, _p(out), ct.c_size_t(w))

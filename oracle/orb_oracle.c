@@ -8,6 +8,7 @@
  */
 #include "orb_oracle.h"
 #include <math.h>
+#include <float.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -894,5 +895,44 @@ void orc_synth_descriptors(uint32_t seed, uint64_t first_row, int nrows, uint8_t
             uint32_t v = syn_hash((uint32_t)row, (uint32_t)(row >> 32) * 8u + (uint32_t)k, seed);
             memcpy(out + (size_t)r * 32 + 4 * k, &v, 4);
         }
+    }
+}
+
+/* ---- Backend::reprojectPoint (reference backend.cpp:1153-1173) ----
+ * point_camera = R.t() * (point_world - t) in double; cv::Mat's 3x3 * 3x1 product accumulates (a0*b0 + a1*b1) + a2*b2 without FMA
+ * (pinned against cv2.gemm in tests/test_oracle_vs_cv2.py); z <= 0 gives (-1, -1); u = (float)(fx*x/z + cx).  R row-major. */
+void orc_reproject(const float *p, const double *R, const double *t, double fx, double fy, double cx, double cy, float *uv)
+{
+    const double d0 = (double)p[0] - t[0], d1 = (double)p[1] - t[1], d2 = (double)p[2] - t[2];
+    double pc[3];
+    for (int i = 0; i < 3; i++) pc[i] = (R[0 * 3 + i] * d0 + R[1 * 3 + i] * d1) + R[2 * 3 + i] * d2;
+    if (pc[2] <= 0) { uv[0] = -1.f; uv[1] = -1.f; return; }
+    uv[0] = (float)(fx * pc[0] / pc[2] + cx);
+    uv[1] = (float)(fy * pc[1] / pc[2] + cy);
+}
+
+/* ---- Backend::associateObservation (reference backend.cpp:1064-1120) for a batch of observations of one category ----
+ * candidates: every landmark with Hamming distance < max_desc (:1068-1077); among them the one with the smallest reprojection
+ * error cv::norm(obs.pixel - reprojection) (double), if that error is < max_reproj (:1091-1111).  The reference walks an
+ * unordered_map, so the winner among EXACTLY equal errors is unspecified there; here the lowest landmark row wins.
+ * out_idx[i] = landmark row or -1, out_err[i] = its error (DBL_MAX if none), out_dist[i] = its Hamming distance. */
+void orc_associate(const uint8_t *q, const float *qpx, int nq, const uint8_t *rows, const float *pos, int nrows,
+                   const double *R, const double *t, double fx, double fy, double cx, double cy,
+                   double max_desc, double max_reproj, int32_t *out_idx, double *out_err, float *out_dist, int nthreads)
+{
+    (void)nthreads;
+#pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : omp_get_max_threads())
+    for (int i = 0; i < nq; i++) {
+        int best = -1; double best_err = DBL_MAX; float best_d = 0.f;
+        for (int j = 0; j < nrows; j++) {
+            const float d = (float)orc_hamming(q + (size_t)i * 32, rows + (size_t)j * 32);
+            if (!((double)d < max_desc)) continue;
+            float uv[2];
+            orc_reproject(pos + (size_t)j * 3, R, t, fx, fy, cx, cy, uv);
+            const float ex = qpx[2 * i] - uv[0], ey = qpx[2 * i + 1] - uv[1];
+            const double err = sqrt((double)ex * ex + (double)ey * ey);
+            if (err < max_reproj && err < best_err) { best = j; best_err = err; best_d = d; }
+        }
+        out_idx[i] = best; out_err[i] = best_err; out_dist[i] = best_d;
     }
 }

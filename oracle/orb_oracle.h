@@ -92,6 +92,13 @@ int  orc_match(const uint8_t *q, int nq, const uint8_t *t, int nt, orc_dmatch *o
 /* knnMatch k=2: out[2*i], out[2*i+1]; trainIdx=-1 when fewer than k train rows */
 int  orc_knn2(const uint8_t *q, int nq, const uint8_t *t, int nt, orc_dmatch *out, int nthreads);
 
+/* Backend::reprojectPoint (backend.cpp:1153-1173); R row-major 3x3, (-1,-1) behind the camera */
+void orc_reproject(const float *p, const double *R, const double *t, double fx, double fy, double cx, double cy, float *uv);
+/* Backend::associateObservation (backend.cpp:1064-1120) over a batch of observations of one category */
+void orc_associate(const uint8_t *q, const float *qpx, int nq, const uint8_t *rows, const float *pos, int nrows,
+                   const double *R, const double *t, double fx, double fy, double cx, double cy,
+                   double max_desc, double max_reproj, int32_t *out_idx, double *out_err, float *out_dist, int nthreads);
+
 /* seeded integer-only synthetic inputs (identical bytes on host and device) */
 void orc_synth_gray(uint32_t seed, int frame, int w, int h, uint8_t *out, size_t step);
 void orc_synth_depth(uint32_t seed, int frame, int w, int h, uint16_t *out, size_t step_elems);

@@ -93,3 +93,42 @@ def test_quadtree_vs_list_restatement(oracle):
         c["x"], c["y"], c["score"] = [k[0] for k in keys], [k[1] for k in keys], [k[2] for k in keys]
         got = oracle.distribute_octtree(c, 16, 16 + W, 16, 16 + H, N)
         assert list(zip(got["x"].tolist(), got["y"].tolist(), got["score"].tolist())) == [tuple(k) for k in want], (n, W, H, N)
+
+
+def test_reproject_and_associate_vs_cv2(oracle):
+    """Backend::reprojectPoint / associateObservation (reference backend.cpp:1064-1173): the C oracle against a literal cv2/numpy statement
+    (cv2.gemm for R.t()*(X - t), float32 pixel, double norm)."""
+    rng = np.random.default_rng(17)
+    R, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    t = rng.standard_normal(3)
+    fx, fy, cx, cy = 615.3, 615.9, 640.2, 360.4
+    n, nq = 400, 60
+    rows = oracle.synth_descriptors(7, 0, n)
+    pc = np.stack([rng.uniform(-2, 2, n), rng.uniform(-1, 1, n), rng.uniform(-1.0, 5.0, n)], 1)
+    pos = (pc @ R.T + t).astype(np.float32)
+
+    def reproj(p):
+        pcam = cv2.gemm(R, p.astype(np.float64).reshape(3, 1) - t.reshape(3, 1), 1.0, None, 0.0, flags=cv2.GEMM_1_T)
+        x, y, z = pcam[0, 0], pcam[1, 0], pcam[2, 0]
+        if z <= 0:
+            return np.array([-1, -1], np.float32)
+        return np.array([np.float32(fx * x / z + cx), np.float32(fy * y / z + cy)], np.float32)
+
+    for j in range(n):
+        assert np.array_equal(oracle.reproject(pos[j], R, t, fx, fy, cx, cy).view(np.uint32), reproj(pos[j]).view(np.uint32))
+    src = rng.integers(0, n, nq)
+    q = rows[src].copy()
+    q[::3, 5] ^= 0xFF
+    qpx = (np.stack([reproj(pos[j]) for j in src]) + rng.normal(0, 3, (nq, 2))).astype(np.float32)
+    idx, err, dist = oracle.associate(q, qpx, rows, pos, R, t, fx, fy, cx, cy)
+    bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+    for i in range(nq):
+        best, best_err = -1, np.finfo(np.float64).max
+        for j in range(n):
+            m = bf.match(q[i:i + 1], rows[j:j + 1])                       # the reference's 1x1 match per landmark (backend.cpp:1072)
+            if m and m[0].distance < 50.0:
+                d = qpx[i] - reproj(pos[j])                               # Point2f difference in float
+                e = np.sqrt(np.float64(d[0]) * np.float64(d[0]) + np.float64(d[1]) * np.float64(d[1]))
+                if e < 5.0 and e < best_err:
+                    best, best_err = j, e
+        assert idx[i] == best and (best < 0 or err[i] == best_err)
