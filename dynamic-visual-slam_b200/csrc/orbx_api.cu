@@ -203,7 +203,7 @@ extern "C" void orbx_destroy(orbx_handle *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
-    void *dev[] = { h->d_cells, h->d_blur_tiles, h->d_strips, h->d_prev_desc, h->d_prev_count, h->d_geo, h->d_xtab, h->d_ytab, h->d_pyr, h->d_blur, h->d_in, h->d_depth_in, h->d_cand, h->d_cand2, h->d_qtmp,
+    void *dev[] = { h->d_bgr, h->d_cells, h->d_blur_tiles, h->d_strips, h->d_prev_desc, h->d_prev_count, h->d_geo, h->d_xtab, h->d_ytab, h->d_pyr, h->d_blur, h->d_in, h->d_depth_in, h->d_cand, h->d_cand2, h->d_qtmp,
                     h->d_owner, h->d_owner2, h->d_ncand, h->d_sel, h->d_nsel, h->d_kps_all, h->d_desc_all, h->d_count_all,
                     h->d_kps_out, h->d_desc_out, h->d_count_out, h->d_boxes, h->d_status, h->d_mpart, h->d_mq, h->d_mt, h->d_mout, h->d_mcount };
     for (void *p : dev) if (p) cudaFree(p);
@@ -413,20 +413,26 @@ extern "C" orbx_status orbx_extract_batch_device(orbx_handle *h, const uint8_t *
     return run_pipeline(h, nframes, d_gray, step, frame_stride, d_depth, dstep, dframe_stride, nullptr, 0, 0, d_kps, d_desc, cap, d_counts);
 }
 
-extern "C" orbx_status orbx_extract_filtered(orbx_handle *h, const uint8_t *gray, int32_t width, int32_t height, size_t step,
-                                             const uint16_t *depth, size_t dstep, const orbx_box *boxes, int32_t nboxes, uint64_t drop_mask,
-                                             orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *n_out)
+static orbx_status extract_one(orbx_handle *h, bool is_bgr, const uint8_t *gray, int32_t width, int32_t height, size_t step,
+                               const uint16_t *depth, size_t dstep, const orbx_box *boxes, int32_t nboxes, uint64_t drop_mask,
+                               orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *n_out)
 {
     if (!h) return ORBX_E_INVALID;
     cudaSetDevice(h->device);
     if (n_out) *n_out = 0;
     if (!gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }        // ORBextractor.cpp:1090-1091
-    if (!kps || !desc || !n_out || cap < 0 || step < (size_t)width || nboxes < 0 || (nboxes > 0 && !boxes)) { h->err = "bad arguments"; return ORBX_E_INVALID; }
+    if (!kps || !desc || !n_out || cap < 0 || step < (size_t)width * (is_bgr ? 3 : 1) || nboxes < 0 || (nboxes > 0 && !boxes)) { h->err = "bad arguments"; return ORBX_E_INVALID; }
     if (h->pending[0].active || h->pending[1].active) { h->err = "an asynchronous batch is outstanding: call orbx_batch_wait first"; return ORBX_E_INVALID; }
     orbx_status st = set_geometry(h, width, height);
     if (st != ORBX_OK) return st;
     const size_t pitch = align_up((size_t)width, 128), dpitch = align_up((size_t)width * 2, 128);
-    ORBX_CUDA(h, cudaMemcpy2DAsync(h->d_in, pitch, gray, step, (size_t)width, (size_t)height, cudaMemcpyHostToDevice, h->stream));
+    if (!is_bgr) ORBX_CUDA(h, cudaMemcpy2DAsync(h->d_in, pitch, gray, step, (size_t)width, (size_t)height, cudaMemcpyHostToDevice, h->stream));
+    else {                                                          // cvtColor(BGR2GRAY) on the device, frontend.cpp:1084
+        const size_t bpitch = align_up((size_t)width * 3, 128);
+        if ((st = grow(h, &h->d_bgr, &h->bgr_cap, bpitch * height)) != ORBX_OK) return st;
+        ORBX_CUDA(h, cudaMemcpy2DAsync(h->d_bgr, bpitch, gray, step, (size_t)width * 3, (size_t)height, cudaMemcpyHostToDevice, h->stream));
+        launch_bgr2gray(h, h->d_bgr, bpitch, 0, h->d_in, pitch, 0, width, height, 1, h->stream);
+    }
     const uint16_t *depth_zc = depth ? (const uint16_t *)mapped_device_view(depth) : nullptr;      // pinned depth is gathered in place
     if (depth && !depth_zc) ORBX_CUDA(h, cudaMemcpy2DAsync(h->d_depth_in, dpitch, depth, dstep, (size_t)width * 2, (size_t)height, cudaMemcpyHostToDevice, h->stream));
     if (nboxes > 0) {
@@ -456,6 +462,31 @@ extern "C" orbx_status orbx_extract_filtered(orbx_handle *h, const uint8_t *gray
     memcpy(kps, hb + 64, (size_t)n * sizeof(orbx_keypoint));
     memcpy(desc, hb + 64 + (size_t)h->max_kp * sizeof(orbx_keypoint), (size_t)n * ORBX_DESC_BYTES);
     *n_out = n;
+    return ORBX_OK;
+}
+
+extern "C" orbx_status orbx_extract_filtered(orbx_handle *h, const uint8_t *gray, int32_t width, int32_t height, size_t step,
+                                             const uint16_t *depth, size_t dstep, const orbx_box *boxes, int32_t nboxes, uint64_t drop_mask,
+                                             orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *n_out)
+{
+    return extract_one(h, false, gray, width, height, step, depth, dstep, boxes, nboxes, drop_mask, kps, desc, cap, n_out);
+}
+extern "C" orbx_status orbx_extract_bgr(orbx_handle *h, const uint8_t *bgr, int32_t width, int32_t height, size_t step,
+                                        const uint16_t *depth, size_t dstep, const orbx_box *boxes, int32_t nboxes, uint64_t drop_mask,
+                                        orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *n_out)
+{
+    return extract_one(h, true, bgr, width, height, step, depth, dstep, boxes, nboxes, drop_mask, kps, desc, cap, n_out);
+}
+extern "C" orbx_status orbx_bgr2gray_device(orbx_handle *h, const uint8_t *d_bgr, int32_t nframes, int32_t width, int32_t height, size_t step,
+                                            size_t fstride, uint8_t *d_gray, size_t gstep, size_t gfstride)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    if (!d_bgr || !d_gray || nframes < 1 || width < 1 || height < 1 || step < (size_t)width * 3 || gstep < (size_t)((width + 3) & ~3) || (gstep & 3) || ((uintptr_t)d_gray & 3)) {
+        h->err = "bad bgr2gray arguments (gray rows must be 4-byte aligned and hold a multiple of 4 pixels)"; return ORBX_E_INVALID;
+    }
+    launch_bgr2gray(h, d_bgr, step, fstride, d_gray, gstep, gfstride, width, height, nframes, h->stream);
+    ORBX_CUDA(h, cudaGetLastError());
     return ORBX_OK;
 }
 

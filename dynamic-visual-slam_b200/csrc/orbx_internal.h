@@ -100,6 +100,7 @@ struct orbx_handle {
     uint8_t *d_pyr, *d_blur;     size_t pyr_slab, blur_slab;          // current per-frame strides
     size_t pyr_cap, blur_cap;                                          // arena bytes
     uint8_t *d_in; size_t in_cap;          // staging for host-API inputs (gray)
+    uint8_t *d_bgr; size_t bgr_cap;        // staging for the BGR single-frame call (grown on first use)
     uint16_t *d_depth_in; size_t depth_cap;
     uint32_t *d_cand, *d_cand2;  size_t cand_cap;        // candidate values (entries), ping-pong for the quadtree
     uint32_t *d_qtmp; uint16_t *d_owner, *d_owner2;
@@ -179,6 +180,8 @@ void launch_match_radius(orbx_handle *h, const uint8_t *d_q, int nq, const uint8
 int  launch_assoc(orbx_handle *h, const uint8_t *d_q, const float *d_qpx, int nq, const uint8_t *d_t, const float *d_pos, int nt, uint32_t row_base,
                   const orbx_pose *pose, float max_dist, double max_err, orbx_assoc *d_out);
 void launch_assoc_merge(orbx_handle *h, const orbx_assoc *d_parts, int nparts, int nq, orbx_assoc *d_out);
+void launch_bgr2gray(orbx_handle *h, const uint8_t *d_bgr, size_t sstep, size_t sfstride, uint8_t *d_gray, size_t dstep, size_t dfstride,
+                     int w, int hgt, int nframes, cudaStream_t st);
 void launch_merge_top2(orbx_handle *h, const orbx_top2 *d_parts, int nshards, int nq, orbx_top2 *d_out);
 void launch_synth_gray(orbx_handle *h, uint32_t seed, int first, int n, int w, int hh, uint8_t *d, size_t step, size_t fstride);
 void launch_synth_depth(orbx_handle *h, uint32_t seed, int first, int n, int w, int hh, uint16_t *d, size_t step, size_t fstride);

@@ -78,6 +78,8 @@ def load():
         "orbx_extract": (i32, [vp, vp, i32, i32, sz, vp, vp, i32, vp]),
         "orbx_extract_filtered": (i32, [vp, vp, i32, i32, sz, vp, sz, vp, i32, u64, vp, vp, i32, vp]),
         "orbx_extract_batch": (i32, [vp, vp, i32, i32, i32, sz, vp, sz, vp, vp, i32, vp]),
+        "orbx_extract_bgr": (i32, [vp, vp, i32, i32, sz, vp, sz, vp, i32, u64, vp, vp, i32, vp]),
+        "orbx_bgr2gray_device": (i32, [vp, vp, i32, i32, i32, sz, sz, vp, sz, sz]),
         "orbx_extract_batch_device": (i32, [vp, vp, i32, i32, i32, sz, sz, vp, sz, sz, vp, vp, i32, vp]),
         "orbx_match": (i32, [vp, vp, i32, vp, i32, i32, f32, f32, vp, vp]),
         "orbx_match_device": (i32, [vp, vp, i32, vp, i32, i32, f32, f32, vp, vp]),
@@ -289,6 +291,22 @@ class ORBextractor:
             st = self.L.orbx_extract_filtered(self._h, _p(image), w, h, image.strides[0], dptr, dstep, bptr, nb,
                                               ct.c_uint64(drop_class_mask), _p(kps), _p(desc), cap, ct.byref(n))
         self._check(st)
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_bgr(self, bgr, depth=None, cap=4096):
+        """cvtColor(BGR2GRAY) on the device + operator() (+ filterDepth): the frontend's ingest, reference frontend.cpp:1084-1100."""
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        h, w, _ = bgr.shape
+        self._last_w, self._last_h = w, h
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = ct.c_int32()
+        dptr, dstep = None, 0
+        if depth is not None:
+            depth = np.ascontiguousarray(depth, np.uint16)
+            dptr, dstep = _p(depth), depth.strides[0]
+        self._check(self.L.orbx_extract_bgr(self._h, _p(bgr), w, h, bgr.strides[0], dptr, dstep, None, 0, ct.c_uint64(0),
+                                            _p(kps), _p(desc), cap, ct.byref(n)))
         return kps[:n.value].copy(), desc[:n.value].copy()
 
     def extract_batch(self, frames, depth=None, cap=2048):

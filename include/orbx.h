@@ -114,6 +114,15 @@ orbx_status orbx_extract_filtered(orbx_handle *h, const uint8_t *gray, int32_t w
                                   const orbx_box *boxes, int32_t nboxes, uint64_t drop_class_mask,
                                   orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *n_out);
 
+/* ---- ingest: cv::cvtColor(BGR2GRAY) on the device (reference frontend.cpp:1084, the step before the hot path) ----
+ * orbx_bgr2gray_device converts nframes packed-BGR (CV_8UC3) device frames into gray frames (dst step % 4 == 0), asynchronously.
+ * orbx_extract_bgr = H2D of ONE host BGR frame + conversion + orbx_extract_filtered's pipeline (depth / boxes nullable).      */
+orbx_status orbx_bgr2gray_device(orbx_handle *h, const uint8_t *d_bgr, int32_t nframes, int32_t width, int32_t height, size_t step,
+                                 size_t frame_stride, uint8_t *d_gray, size_t gray_step, size_t gray_frame_stride);
+orbx_status orbx_extract_bgr(orbx_handle *h, const uint8_t *bgr, int32_t width, int32_t height, size_t step,
+                             const uint16_t *depth, size_t dstep, const orbx_box *boxes, int32_t nboxes, uint64_t drop_class_mask,
+                             orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *n_out);
+
 /* frame-parallel batch, HOST buffers: frames tightly packed (frame f at gray + f*height*step).
  * depth nullable.  kps/desc have room for cap_per_frame entries per frame; counts[nframes].
  * Internally cut into chunks that are pipelined over three streams (H2D of chunk i+1, kernels of chunk i,

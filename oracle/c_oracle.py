@@ -238,6 +238,14 @@ def associate(q, qpx, rows, pos, R, t, fx, fy, cx, cy, max_desc=50.0, max_reproj
     return idx, err, dist
 
 
+def bgr2gray(bgr):
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    h, w, _ = bgr.shape
+    out = np.zeros((h, w), np.uint8)
+    lib().orc_bgr2gray(_p(bgr), w, h, ct.c_size_t(bgr.strides[0]), _p(out), ct.c_size_t(w))
+    return out
+
+
 def synth_gray(seed, frame, w, h):
     out = np.zeros((h, w), np.uint8)
     lib().orc_synth_gray(ct.c_uint32(seed), frame, w, h, _p(out), ct.c_size_t(w))

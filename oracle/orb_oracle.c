@@ -936,3 +936,12 @@ void orc_associate(const uint8_t *q, const float *qpx, int nq, const uint8_t *ro
         out_idx[i] = best; out_err[i] = best_err; out_dist[i] = best_d;
     }
 }
+
+/* cv::cvtColor(BGR2GRAY) on CV_8UC3 (reference frontend.cpp:1084): (3735*B + 19235*G + 9798*R + 16384) >> 15 */
+void orc_bgr2gray(const uint8_t *bgr, int w, int h, size_t sstep, uint8_t *gray, size_t dstep)
+{
+    for (int y = 0; y < h; y++) {
+        const uint8_t *s = bgr + (size_t)y * sstep; uint8_t *d = gray + (size_t)y * dstep;
+        for (int x = 0; x < w; x++) d[x] = (uint8_t)((3735 * s[3 * x] + 19235 * s[3 * x + 1] + 9798 * s[3 * x + 2] + 16384) >> 15);
+    }
+}

@@ -99,6 +99,9 @@ void orc_associate(const uint8_t *q, const float *qpx, int nq, const uint8_t *ro
                    const double *R, const double *t, double fx, double fy, double cx, double cy,
                    double max_desc, double max_reproj, int32_t *out_idx, double *out_err, float *out_dist, int nthreads);
 
+/* cv::cvtColor(BGR2GRAY), reference frontend.cpp:1084 */
+void orc_bgr2gray(const uint8_t *bgr, int w, int h, size_t sstep, uint8_t *gray, size_t dstep);
+
 /* seeded integer-only synthetic inputs (identical bytes on host and device) */
 void orc_synth_gray(uint32_t seed, int frame, int w, int h, uint8_t *out, size_t step);
 void orc_synth_depth(uint32_t seed, int frame, int w, int h, uint16_t *out, size_t step_elems);

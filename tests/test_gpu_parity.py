@@ -85,3 +85,28 @@ def test_depth_filter(ex, oracle):
     assert 0 < len(ok) < len(kps)
     assert np.array_equal(fk.view(np.uint8), ok.view(np.uint8))
     assert np.array_equal(fd, od)
+
+
+def test_bgr_ingest(ex, oracle):
+    """cvtColor(BGR2GRAY) on the device + extraction == the reference's host-side conversion followed by extraction."""
+    import torch
+    import orbx
+    w, h = 741, 417
+    g = oracle.synth_gray(13, 0, w, h)
+    rng = np.random.default_rng(4)
+    bgr = np.clip(np.stack([g, g, g], 2).astype(np.int32) + rng.integers(-12, 13, (h, w, 3)), 0, 255).astype(np.uint8)
+    gray = oracle.bgr2gray(bgr)
+    ref = oracle.COracle().extract(gray)
+    k, d = ex.extract_bgr(bgr)
+    assert np.array_equal(k.view(np.uint8), ref["kps"].view(np.uint8)) and np.array_equal(d, ref["desc"])
+    assert np.array_equal(ex.pyramid_level(0), gray)
+    # the batched device conversion
+    dev = torch.device("cuda", 0)
+    src = torch.from_numpy(np.stack([bgr, bgr[::-1].copy()])).to(dev)
+    gp = (w + 3) & ~3
+    dst = torch.zeros((2, h, gp), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    ex._check(ex.L.orbx_bgr2gray_device(ex.handle, src.data_ptr(), 2, w, h, 3 * w, 3 * w * h, dst.data_ptr(), gp, gp * h))
+    ex.sync()
+    out = dst.cpu().numpy()
+    assert np.array_equal(out[0, :, :w], gray) and np.array_equal(out[1, :, :w], gray[::-1])

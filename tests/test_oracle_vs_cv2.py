@@ -132,3 +132,12 @@ def test_reproject_and_associate_vs_cv2(oracle):
                 if e < 5.0 and e < best_err:
                     best, best_err = j, e
         assert idx[i] == best and (best < 0 or err[i] == best_err)
+
+
+def test_bgr2gray_vs_cv2(oracle):
+    """cv::cvtColor(BGR2GRAY) (reference frontend.cpp:1084): identity on equal channels, integer formula otherwise."""
+    rng = np.random.default_rng(2)
+    bgr = rng.integers(0, 256, (97, 131, 3), dtype=np.uint8)
+    assert np.array_equal(oracle.bgr2gray(bgr), cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
+    g = rng.integers(0, 256, (50, 64), dtype=np.uint8)
+    assert np.array_equal(oracle.bgr2gray(np.stack([g, g, g], 2)), g)
