@@ -36,9 +36,9 @@
 #include <algorithm>
 #include <cstring>
 
-#define FS_TP 96                 // tile pitch = TMA box width: 24 u32 elements >= 15 (alignment) + 69 + 6 (widest cell ROI) + 4
-#define FS_TPW (FS_TP / 4)
-#define FS_PADROWS 6             // rows behind the tile: a 7-row sweep unit may start on the last detection row
+// tile pitch TP = TMA box width, a template parameter: 80 bytes when every cell ROI (15 alignment + wCell + 6 + 4) fits, else 96
+// (wCell <= 69).  A 7-row sweep unit may start on the last detection row: the rows it reads past the tile fall into the score map
+// that follows the tile in shared memory (their flags are masked).
 #define FS_WQ 512                // survivor queue (u16 tile offsets); a sweep step with more survivors than this is scored in place
 
 struct FastParams {
@@ -52,14 +52,14 @@ struct FastParams {
     int map_pitch;               // score-map pitch: >= max cell width + 2, multiple of 16
 };
 
-#define RO(dx, dy) ((dy) * FS_TP + (dx))
+#define RO(dx, dy) ((dy) * TP + (dx))
 
 // S on the raw ring values: S = max( I(p) - min_k max9_k(ring), max_k min9_k(ring) - I(p) ).
 // Packed lanes: lo16 = r, hi16 = 255 - r  =>  a lane-wise min yields (min r, 255 - max r).
 // min9_k = min3( min3(r_k..r_k+2), min3(r_k+3..r_k+5), min3(r_k+6..r_k+8) ): 40 three-input min/max in all.
 __device__ __forceinline__ uint32_t vmin3u2(uint32_t a, uint32_t b, uint32_t c) { return __vminu2(__vminu2(a, b), c); }
 __device__ __forceinline__ uint32_t vmax3u2(uint32_t a, uint32_t b, uint32_t c) { return __vmaxu2(__vmaxu2(a, b), c); }
-__device__ __forceinline__ int fast_score_packed(const uint8_t *p)
+template <int TP> __device__ __forceinline__ int fast_score_packed(const uint8_t *p)
 {
     const int v = p[0];
     uint32_t r[16];
@@ -101,15 +101,15 @@ __device__ __forceinline__ FastRow fast_row(const uint32_t *q)
 
 // Pre-test of 7 detection rows x 4 pixels.  q = the item's word in tile row r0 (= ring row dy = -3 of the first
 // detection row).  Result: bit (7-k) of byte j set iff pixel (row r0 + k, byte j) may be a corner at threshold T.
-__device__ __noinline__ uint32_t fast_sweep7(const uint32_t *q, uint32_t HM, uint32_t KK)
+template <int TP> __device__ __noinline__ uint32_t fast_sweep7(const uint32_t *q, uint32_t HM, uint32_t KK)
 {
     FastRow w[7];
 #pragma unroll
-    for (int k = 0; k < 6; k++) w[k] = fast_row(q + k * FS_TPW);
+    for (int k = 0; k < 6; k++) w[k] = fast_row(q + k * (TP / 4));
     uint32_t fl = 0u;
 #pragma unroll
     for (int k = 0; k < 7; k++) {
-        w[(k + 6) % 7] = fast_row(q + (k + 6) * FS_TPW);                       // ring row dy = +3 of detection row k
+        w[(k + 6) % 7] = fast_row(q + (k + 6) * (TP / 4));                       // ring row dy = +3 of detection row k
         const uint32_t C0 = w[(k + 3) % 7].C;
         const uint32_t p08 = __vabsdiffu4(w[(k + 6) % 7].C, C0) | __vabsdiffu4(w[k % 7].C, C0);
         const uint32_t p4c = __vabsdiffu4(w[(k + 3) % 7].P3, C0) | __vabsdiffu4(w[(k + 3) % 7].M3, C0);
@@ -151,17 +151,18 @@ __device__ __forceinline__ FastItem fast_item(const FastParams &P, const FrameGe
     return t;
 }
 
-__global__ void __launch_bounds__(32) k_fast_cells(const __grid_constant__ LevelMaps M, FastParams P, const FrameGeom *__restrict__ G)
+template <int TP> __global__ void __launch_bounds__(32) k_fast_cells(const __grid_constant__ LevelMaps M, FastParams P, const FrameGeom *__restrict__ G)
 {
     extern __shared__ __align__(128) uint8_t s_raw[];
     __shared__ __align__(8) uint64_t s_full;
     uint8_t *s_dyn = s_raw + ((128u - (smem_u32(s_raw) & 127u)) & 127u);
-    // layout: [queue | score map | tile]; the word left of tile column 0 (read, never used) falls into the map
-    uint16_t *wq = reinterpret_cast<uint16_t *>(s_dyn);
-    uint8_t *s_sc = s_dyn + FS_WQ * 2;                                                  // (tile_rows - 4) x map_pitch, zero ring
+    // layout: [128-byte pad | tile | score map | queue]: the word left of tile column 0 (read, never used) falls into the pad
+    uint8_t *s_img = s_dyn + 128;                                                        // tile_rows x TP, 128-byte aligned (TMA destination)
+    const int tile_bytes = ((P.tile_rows * TP) + 127) & ~127;
+    uint8_t *s_sc = s_img + tile_bytes;                                                  // (tile_rows - 4) x map_pitch, zero ring
     const int SP = P.map_pitch;
     const int map_bytes = (((P.tile_rows - 4) * SP) + 127) & ~127;
-    uint8_t *s_img = s_sc + map_bytes;                                                   // (tile_rows + FS_PADROWS) x FS_TP, 128-byte aligned
+    uint16_t *wq = reinterpret_cast<uint16_t *>(s_sc + map_bytes);
     const int lane = threadIdx.x;
     const int nl = G->nlevels;
 
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(32) k_fast_cells(const __grid_constant__ Level
         const int ax = T.ax, dw = T.dw, dh = T.dh;
         if (lane == 0) {
             // every lane finished reading the previous tile (the __syncwarp that ends the loop body)
-            mbar_expect_tx(&s_full, (uint32_t)((T.hcell + 6) * FS_TP));
+            mbar_expect_tx(&s_full, (uint32_t)((T.hcell + 6) * TP));
             tma_load_3d(s_img, &M.m[T.level], (T.iniX & ~15) >> 2, T.iniY, T.f, &s_full);
             if (item + (int)gridDim.x < P.nitems) {                                     // next cell's window -> L2
                 const FastItem N = fast_item(P, G, item + gridDim.x);
@@ -212,14 +213,14 @@ __global__ void __launch_bounds__(32) k_fast_cells(const __grid_constant__ Level
                 int base_off = 0;
                 if (u < units) {
                     const int seg = __float2int_rd(((float)u + 0.5f) * inv), gidx = u - seg * nG;
-                    const uint32_t raw = fast_sweep7(words + (7 * seg) * FS_TPW + w0 + gidx, HM, KK);
+                    const uint32_t raw = fast_sweep7<TP>(words + (7 * seg) * (TP / 4) + w0 + gidx, HM, KK);
                     const int cb = 4 * (w0 + gidx) - (ax + 3);                // detection column of byte 0
                     uint32_t cm = 0u;
 #pragma unroll
                     for (int j = 0; j < 4; j++) if (cb + j >= 0 && cb + j < dw) cm |= 0xFEu << (8 * j);
                     const int nv = min(7, dh - 7 * seg);
                     word = raw & cm & (((0xFF00u >> nv) & 0xFFu) * 0x01010101u);
-                    base_off = (7 * seg + 3) * FS_TP + 4 * (w0 + gidx);
+                    base_off = (7 * seg + 3) * TP + 4 * (w0 + gidx);
                 }
                 const int cnt = __popc(word);
                 int incl = cnt;
@@ -230,8 +231,8 @@ __global__ void __launch_bounds__(32) k_fast_cells(const __grid_constant__ Level
                     __syncwarp();
                     for (int i = lane; i < qn; i += 32) {
                         const int off = wq[i];
-                        const int s = fast_score_packed(s_img + off);
-                        const int tr = off / FS_TP, tc = off - tr * FS_TP - ax;
+                        const int s = fast_score_packed<TP>(s_img + off);
+                        const int tr = off / TP, tc = off - tr * TP - ax;
                         s_sc[(tr - 2) * SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
                     }
                     __syncwarp();
@@ -240,9 +241,9 @@ __global__ void __launch_bounds__(32) k_fast_cells(const __grid_constant__ Level
                         while (word) {
                             const int bit = __ffs((int)word) - 1;
                             word &= word - 1;
-                            const int off = base_off + (7 - (bit & 7)) * FS_TP + (bit >> 3);
-                            const int s = fast_score_packed(s_img + off);
-                            const int tr = off / FS_TP, tc = off - tr * FS_TP - ax;
+                            const int off = base_off + (7 - (bit & 7)) * TP + (bit >> 3);
+                            const int s = fast_score_packed<TP>(s_img + off);
+                            const int tr = off / TP, tc = off - tr * TP - ax;
                             s_sc[(tr - 2) * SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
                         }
                         continue;
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(32) k_fast_cells(const __grid_constant__ Level
                 while (word) {
                     const int bit = __ffs((int)word) - 1;
                     word &= word - 1;
-                    wq[slot++] = (uint16_t)(base_off + (7 - (bit & 7)) * FS_TP + (bit >> 3));
+                    wq[slot++] = (uint16_t)(base_off + (7 - (bit & 7)) * TP + (bit >> 3));
                 }
                 qn += total;
             }
@@ -260,8 +261,8 @@ __global__ void __launch_bounds__(32) k_fast_cells(const __grid_constant__ Level
             // ---- exact score of the queued survivors (ROI coords = detection coords + 3) ----
             for (int i = lane; i < qn; i += 32) {
                 const int off = wq[i];
-                const int s = fast_score_packed(s_img + off);
-                const int tr = off / FS_TP, tc = off - tr * FS_TP - ax;
+                const int s = fast_score_packed<TP>(s_img + off);
+                const int tr = off / TP, tc = off - tr * TP - ax;
                 s_sc[(tr - 2) * SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
             }
             __syncwarp();
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(32) k_fast_cells(const __grid_constant__ Level
                 int r = 0, c = 0, s = 0;
                 if (i < nitems) {
                     if (ovf) { r = __float2int_rd(((float)i + 0.5f) * invw); c = i - r * dw; }
-                    else { const int off = wq[i]; const int tr = off / FS_TP; r = tr - 3; c = off - tr * FS_TP - ax - 3; }
+                    else { const int off = wq[i]; const int tr = off / TP; r = tr - 3; c = off - tr * TP - ax - 3; }
                     const uint8_t *q = &s_sc[(r + 1) * SP + (c + 1)];
                     s = q[0];
                     // the zero ring around the map stands for "outside the cell's detection area"
@@ -335,6 +336,9 @@ static bool encode_level(CUtensorMap *m, const uint8_t *base, size_t pitch, int 
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// FAST tile pitch (= TMA box width) for the geometry: 15 alignment bytes + the widest cell ROI (wCell + 6) + one spare word
+static int fast_tile_pitch(const FrameGeom &G) { return G.max_wcell + 25 <= 80 ? 80 : 96; }
+
 // tensor maps of the current geometry: levels >= 1 are fixed per geometry, level 0 follows the caller's frames
 int orbx_ensure_tmaps(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride)
 {
@@ -343,13 +347,13 @@ int orbx_ensure_tmaps(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_
         for (int l = 1; l < G.nlevels; l++)
             if (!encode_level(&h->tmap[l], h->d_pyr + G.lv[l].off, (size_t)G.lv[l].pitch, G.lv[l].h, h->pyr_slab, h->prm.max_batch, G.lv[l].hcell + 6) ||
                 !encode_level(&h->tmap_rz[l], h->d_pyr + G.lv[l].off, (size_t)G.lv[l].pitch, G.lv[l].h, h->pyr_slab, h->prm.max_batch, ORBX_RZ_BOX_ROWS) ||
-                !encode_level(&h->tmap_cell[l], h->d_pyr + G.lv[l].off, (size_t)G.lv[l].pitch, G.lv[l].h, h->pyr_slab, h->prm.max_batch, G.lv[l].hcell + 6, FS_TPW)) return -1;
+                !encode_level(&h->tmap_cell[l], h->d_pyr + G.lv[l].off, (size_t)G.lv[l].pitch, G.lv[l].h, h->pyr_slab, h->prm.max_batch, G.lv[l].hcell + 6, fast_tile_pitch(G) / 4)) return -1;
         h->tmap_valid = true; h->tmap_l0 = nullptr;
     }
     if (h->tmap_l0 != l0 || h->tmap_l0_step != l0_step || h->tmap_l0_fstride != l0_fstride || h->tmap_l0_frames < nframes) {
         if (!encode_level(&h->tmap[0], l0, l0_step, G.lv[0].h, l0_fstride, nframes, G.lv[0].hcell + 6) ||
             !encode_level(&h->tmap_rz[0], l0, l0_step, G.lv[0].h, l0_fstride, nframes, ORBX_RZ_BOX_ROWS) ||
-            !encode_level(&h->tmap_cell[0], l0, l0_step, G.lv[0].h, l0_fstride, nframes, G.lv[0].hcell + 6, FS_TPW)) return -1;
+            !encode_level(&h->tmap_cell[0], l0, l0_step, G.lv[0].h, l0_fstride, nframes, G.lv[0].hcell + 6, fast_tile_pitch(G) / 4)) return -1;
         h->tmap_l0 = l0; h->tmap_l0_step = l0_step; h->tmap_l0_fstride = l0_fstride; h->tmap_l0_frames = nframes;
     }
     return 0;
@@ -370,18 +374,18 @@ int launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, 
     P.status = h->d_status;
     P.tile_rows = G.max_hcell + 6;
     P.map_pitch = (G.max_wcell + 2 + 15) & ~15;
+    const int TP = fast_tile_pitch(G);
     const size_t map_bytes = (size_t)((((P.tile_rows - 4) * P.map_pitch) + 127) & ~127);
-    const size_t smem = 128 + FS_WQ * 2 + map_bytes + (size_t)(P.tile_rows + FS_PADROWS) * FS_TP;
-    static size_t configured = 0;
-    if (smem > configured || h->fast_grid_cap <= 0) {
-        cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = std::max(configured, smem);
+    const size_t smem = 128 + 128 + (size_t)(((P.tile_rows * TP) + 127) & ~127) + map_bytes + FS_WQ * 2;
+    auto kern = TP == 80 ? k_fast_cells<80> : k_fast_cells<96>;
+    if (smem != h->fast_smem || TP != h->fast_tp) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int occ = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fast_cells, 32, smem);
-        h->fast_grid_cap = std::max(1, occ) * h->sm_count;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem);
+        h->fast_grid_cap = std::max(1, occ) * h->sm_count; h->fast_smem = smem; h->fast_tp = TP;
     }
     const int grid = std::min(P.nitems, h->fast_grid_cap);
     ProfScope ps(h, ORBX_K_FAST);
-    k_fast_cells<<<grid, 32, smem, h->stream>>>(M, P, h->d_geo);
+    kern<<<grid, 32, smem, h->stream>>>(M, P, h->d_geo);
     return 0;
 }
