@@ -95,3 +95,83 @@ void launch_filter(orbx_handle *h, int nframes, const uint16_t *d_depth, size_t 
     ProfScope ps(h, ORBX_K_FILTER);
     k_filter<<<nframes, 256, 0, h->stream>>>(P);
 }
+
+// ---- keyframe packing: the landmark / observation loop of Frontend::publishKeyframe (reference frontend.cpp:731-776) ----
+// per keypoint: depth at round(pt) (half away from zero) * 0.001f, back-projection in FLOAT with the float intrinsics
+// ((pt.x - cx) * d / fx, ...), kept iff z > 0.3 && z < 3.0 (float against double literals), world = R * p + t in double with
+// cv::Mat's accumulation order and no FMA; one 80-byte record (Landmark + Observation of Keyframe.msg) per kept keypoint,
+// order preserved (stable ballot compaction, one CTA per frame).
+struct PackParams {
+    const orbx_keypoint *kps; const uint8_t *desc; const int32_t *counts; int cap_in;
+    const uint16_t *depth; size_t dstep, dfstride; int dw, dh;     // steps in BYTES
+    orbx_kfparams K;
+    orbx_kfrecord *out; int32_t *nout; int cap_out;
+    int32_t *status;
+};
+
+__global__ void __launch_bounds__(256) k_pack_keyframe(PackParams P)
+{
+    __shared__ int s_warp[9];
+    __shared__ int s_base;
+    const int f = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int n = min(P.counts[f], P.cap_in);
+    const orbx_keypoint *kin = P.kps + (size_t)f * P.cap_in;
+    const uint8_t *din = P.desc + (size_t)f * P.cap_in * ORBX_DESC_BYTES;
+    orbx_kfrecord *out = P.out + (size_t)f * P.cap_out;
+    const uint8_t *dimg = reinterpret_cast<const uint8_t *>(P.depth) + (size_t)f * P.dfstride;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 256) {
+        const int i = base + threadIdx.x;
+        bool keep = false;
+        float px = 0.f, py = 0.f, X = 0.f, Y = 0.f, Z = 0.f;
+        if (i < n) {
+            px = kin[i].x; py = kin[i].y;
+            const int x = (int)roundf(px), y = (int)roundf(py);
+            if (x >= 0 && y >= 0 && x < P.dw && y < P.dh) {
+                Z = __fmul_rn((float)__ldg(reinterpret_cast<const uint16_t *>(dimg + (size_t)y * P.dstep) + x), 0.001f);
+                X = __fdiv_rn(__fmul_rn(__fsub_rn(px, P.K.cx), Z), P.K.fx);
+                Y = __fdiv_rn(__fmul_rn(__fsub_rn(py, P.K.cy), Z), P.K.fy);
+                keep = (double)Z > 0.3 && (double)Z < 3.0;
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        if (threadIdx.x == 0) { int run = 0; for (int w = 0; w < 8; w++) { const int c = s_warp[w]; s_warp[w] = run; run += c; } s_warp[8] = run; }
+        __syncthreads();
+        if (keep) {
+            const int o = s_base + s_warp[wid] + __popc(bal & ((1u << lane) - 1u));
+            if (o < P.cap_out) {
+                orbx_kfrecord r;
+                r.landmark_id = (uint64_t)i;
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    r.position[k] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.K.R[3 * k], (double)X), __dmul_rn(P.K.R[3 * k + 1], (double)Y)),
+                                                        __dmul_rn(P.K.R[3 * k + 2], (double)Z)), P.K.t[k]);
+                r.pixel_x = (double)px; r.pixel_y = (double)py;
+                const uint4 *dp = reinterpret_cast<const uint4 *>(din + (size_t)i * ORBX_DESC_BYTES);
+                *reinterpret_cast<uint4 *>(r.descriptor) = dp[0];
+                *reinterpret_cast<uint4 *>(r.descriptor + 16) = dp[1];
+                out[o] = r;
+            } else atomicOr(P.status, ORBX_DS_KP_OVERFLOW);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += s_warp[8];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) P.nout[f] = min(s_base, P.cap_out);
+}
+
+void launch_pack_keyframe(orbx_handle *h, int nframes, const orbx_keypoint *d_kps, const uint8_t *d_desc, const int32_t *d_counts, int cap_in,
+                          const uint16_t *d_depth, size_t dstep, size_t dfstride, int dw, int dh, const orbx_kfparams *K,
+                          orbx_kfrecord *d_out, int32_t *d_nout, int cap_out)
+{
+    PackParams P;
+    P.kps = d_kps; P.desc = d_desc; P.counts = d_counts; P.cap_in = cap_in;
+    P.depth = d_depth; P.dstep = dstep; P.dfstride = dfstride; P.dw = dw; P.dh = dh;
+    P.K = *K; P.out = d_out; P.nout = d_nout; P.cap_out = cap_out; P.status = h->d_status;
+    ProfScope ps(h, ORBX_K_OTHER);
+    k_pack_keyframe<<<nframes, 256, 0, h->stream>>>(P);
+}

@@ -1052,6 +1052,56 @@ extern "C" orbx_status orbx_merge_assoc_device(orbx_handle *h, const orbx_assoc 
     return ORBX_OK;
 }
 
+// ---- keyframe packing (Frontend::publishKeyframe, frontend.cpp:731-776) ----
+extern "C" orbx_status orbx_pack_keyframe_device(orbx_handle *h, int32_t nframes, const orbx_keypoint *d_kps, const uint8_t *d_desc,
+                                                 const int32_t *d_counts, int32_t cap, const uint16_t *d_depth, int32_t width, int32_t height,
+                                                 size_t dstep, size_t dfstride, const orbx_kfparams *K,
+                                                 orbx_kfrecord *d_out, int32_t *d_nout, int32_t out_cap)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    if (nframes < 1 || !d_kps || !d_desc || !d_counts || cap < 1 || !d_depth || width < 1 || height < 1 || dstep < (size_t)width * 2 || (dstep & 1) ||
+        !K || !d_out || !d_nout || out_cap < 1) { h->err = "bad keyframe packing arguments"; return ORBX_E_INVALID; }
+    launch_pack_keyframe(h, nframes, d_kps, d_desc, d_counts, cap, d_depth, dstep, dfstride, width, height, K, d_out, d_nout, out_cap);
+    ORBX_CUDA(h, cudaGetLastError());
+    return ORBX_OK;
+}
+extern "C" orbx_status orbx_pack_keyframe(orbx_handle *h, const orbx_keypoint *kps, const uint8_t *desc, int32_t n, const uint16_t *depth,
+                                          int32_t width, int32_t height, size_t dstep, const orbx_kfparams *K,
+                                          orbx_kfrecord *out, int32_t cap, int32_t *n_out)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    if (n_out) *n_out = 0;
+    if (n < 0 || (n > 0 && (!kps || !desc)) || !depth || width < 1 || height < 1 || dstep < (size_t)width * 2 || !K || !out || !n_out || cap < 0) { h->err = "bad keyframe packing arguments"; return ORBX_E_INVALID; }
+    if (n == 0) return ORBX_OK;
+    if (n > h->max_kp) { h->err = "more keypoints than the handle's max_keypoints"; return ORBX_E_CAPACITY; }
+    if (width > h->prm.max_width || height > h->prm.max_height) { h->err = "depth image larger than max_width x max_height"; return ORBX_E_INVALID; }
+    if (h->pending[0].active || h->pending[1].active) { h->err = "an asynchronous batch is outstanding: call orbx_batch_wait first"; return ORBX_E_INVALID; }
+    orbx_status st;
+    const size_t dpitch = align_up((size_t)width * 2, 128);
+    const size_t need = (size_t)h->max_kp * sizeof(orbx_kfrecord) + 64;
+    if ((st = grow(h, (uint8_t **)&h->d_mout, &h->mout_cap, need)) != ORBX_OK) return st;
+    orbx_kfrecord *d_rec = (orbx_kfrecord *)h->d_mout;
+    const uint16_t *dd = (const uint16_t *)mapped_device_view(depth);           // pinned depth is gathered in place
+    size_t dds = dstep;
+    if (!dd) {
+        ORBX_CUDA(h, cudaMemcpy2DAsync(h->d_depth_in, dpitch, depth, dstep, (size_t)width * 2, (size_t)height, cudaMemcpyHostToDevice, h->stream));
+        dd = h->d_depth_in; dds = dpitch;
+    }
+    ORBX_CUDA(h, cudaMemcpyAsync(h->d_kps_all, kps, (size_t)n * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(h, cudaMemcpyAsync(h->d_desc_all, desc, (size_t)n * ORBX_DESC_BYTES, cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(h, cudaMemcpyAsync(h->d_count_all, &n, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    launch_pack_keyframe(h, 1, h->d_kps_all, h->d_desc_all, h->d_count_all, h->max_kp, dd, dds, 0, width, height, K, d_rec, h->d_mcount, h->max_kp);
+    int32_t m = 0;
+    ORBX_CUDA(h, cudaMemcpyAsync(&m, h->d_mcount, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    *n_out = m;
+    if (m > cap) { h->err = "keyframe record capacity too small"; return ORBX_E_CAPACITY; }
+    if (m > 0) ORBX_CUDA(h, cudaMemcpy(out, d_rec, (size_t)m * sizeof(orbx_kfrecord), cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
 // ---- synthetic inputs ----
 extern "C" orbx_status orbx_synth_gray_device(orbx_handle *h, uint32_t seed, int32_t first, int32_t n, int32_t w, int32_t hgt, uint8_t *d, size_t step, size_t fstride)
 {

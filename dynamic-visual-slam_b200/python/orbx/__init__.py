@@ -28,7 +28,9 @@ TOP2_DTYPE = np.dtype([("dist0", "<u4"), ("idx0", "<u4"), ("dist1", "<u4"), ("id
 ASSOC_DTYPE = np.dtype([("reproj_error", "<f8"), ("landmark", "<i4"), ("distance", "<f4")])
 POSE_DTYPE = np.dtype([("R", "<f8", (9,)), ("t", "<f8", (3,)), ("fx", "<f8"), ("fy", "<f8"), ("cx", "<f8"), ("cy", "<f8")])
 assert KP_DTYPE.itemsize == 28 and DM_DTYPE.itemsize == 16 and BOX_DTYPE.itemsize == 40 and TOP2_DTYPE.itemsize == 16
-assert ASSOC_DTYPE.itemsize == 16 and POSE_DTYPE.itemsize == 128
+KFPARAMS_DTYPE = np.dtype([("R", "<f8", (9,)), ("t", "<f8", (3,)), ("fx", "<f4"), ("fy", "<f4"), ("cx", "<f4"), ("cy", "<f4")])
+KF_DTYPE = np.dtype([("landmark_id", "<u8"), ("position", "<f8", (3,)), ("pixel_x", "<f8"), ("pixel_y", "<f8"), ("descriptor", "u1", (32,))])
+assert ASSOC_DTYPE.itemsize == 16 and POSE_DTYPE.itemsize == 128 and KFPARAMS_DTYPE.itemsize == 112 and KF_DTYPE.itemsize == 80
 
 
 class Params(ct.Structure):
@@ -93,6 +95,8 @@ def load():
         "orbx_db_query_top2": (i32, [vp, vp, i32, vp]),
         "orbx_merge_top2_device": (i32, [vp, vp, i32, i32, vp]),
         "orbx_db_query_radius": (i32, [vp, vp, i32, f32, vp, i32, vp]),
+        "orbx_pack_keyframe": (i32, [vp, vp, vp, i32, vp, i32, i32, sz, vp, vp, i32, vp]),
+        "orbx_pack_keyframe_device": (i32, [vp, i32, vp, vp, vp, i32, vp, i32, i32, sz, sz, vp, vp, vp, i32]),
         "orbx_db_set_positions": (i32, [vp, i64, i64, vp]),
         "orbx_db_set_positions_device": (i32, [vp, i64, i64, vp]),
         "orbx_db_associate": (i32, [vp, vp, vp, i32, vp, f32, ct.c_double, vp]),
@@ -308,6 +312,21 @@ class ORBextractor:
         self._check(self.L.orbx_extract_bgr(self._h, _p(bgr), w, h, bgr.strides[0], dptr, dstep, None, 0, ct.c_uint64(0),
                                             _p(kps), _p(desc), cap, ct.byref(n)))
         return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def pack_keyframe(self, kps, desc, depth, fx, fy, cx, cy, R, t):
+        """Landmark / observation records of Frontend::publishKeyframe (reference frontend.cpp:731-776)."""
+        kps = np.ascontiguousarray(kps, KP_DTYPE)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        depth = np.ascontiguousarray(depth, np.uint16)
+        K = np.zeros(1, KFPARAMS_DTYPE)
+        K["R"][0] = np.asarray(R, np.float64).reshape(9)
+        K["t"][0] = np.asarray(t, np.float64).reshape(3)
+        K["fx"], K["fy"], K["cx"], K["cy"] = fx, fy, cx, cy
+        out = np.zeros(max(len(kps), 1), KF_DTYPE)
+        n = ct.c_int32()
+        self._check(self.L.orbx_pack_keyframe(self._h, _p(kps), _p(desc), len(kps), _p(depth), depth.shape[1], depth.shape[0], depth.strides[0],
+                                              _p(K), _p(out), len(out), ct.byref(n)))
+        return out[:n.value].copy()
 
     def extract_batch(self, frames, depth=None, cap=2048):
         frames = np.ascontiguousarray(frames, dtype=np.uint8)

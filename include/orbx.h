@@ -54,6 +54,10 @@ typedef struct { double cx, cy, w, h; int32_t class_id; int32_t pad_; } orbx_box
 typedef struct { uint32_t dist0, idx0, dist1, idx1; } orbx_top2;
 /* camera pose and intrinsics of Backend::reprojectPoint (backend.cpp:1153-1173): point_camera = R.t() * (X - t), R row-major */
 typedef struct { double R[9]; double t[3]; double fx, fy, cx, cy; } orbx_pose;
+/* keyframe packing (Frontend::publishKeyframe, frontend.cpp:731-776): float intrinsics (frontend.cpp:278) and the camera-to-world pose */
+typedef struct { double R[9]; double t[3]; float fx, fy, cx, cy; } orbx_kfparams;
+/* one Landmark + Observation pair of Keyframe.msg (msg/Landmark.msg:5-8, msg/Observation.msg:5-12): 80 bytes */
+typedef struct { uint64_t landmark_id; double position[3]; double pixel_x, pixel_y; uint8_t descriptor[32]; } orbx_kfrecord;
 /* result of the reprojection-gated association of one observation: landmark = global row or -1 (backend.cpp:1064-1120) */
 typedef struct { double reproj_error; int32_t landmark; float distance; } orbx_assoc;
 
@@ -231,6 +235,18 @@ orbx_status orbx_db_associate(orbx_db *db, const uint8_t *query, const float *qu
 orbx_status orbx_db_associate_device(orbx_db *db, const uint8_t *d_query, const float *d_query_px, int32_t nq, const orbx_pose *pose,
                                      float max_desc_dist, double max_reproj_err, orbx_assoc *d_out);
 orbx_status orbx_merge_assoc_device(orbx_handle *h, const orbx_assoc *d_parts, int32_t nshards, int32_t nq, orbx_assoc *d_out);
+
+/* ---- keyframe packing: the landmark / observation loop of Frontend::publishKeyframe (frontend.cpp:731-776), SURVEY §8(f) rank 2 ----
+ * For every keypoint with a depth in (0.3, 3.0) m: back-projection with the float intrinsics, world transform R*p + t in double,
+ * one 80-byte record; order preserved; landmark_id = index of the keypoint in the input list, as in the reference.
+ * Device variant: per-frame lists laid out like the outputs of orbx_extract_batch_device; asynchronous.                  */
+orbx_status orbx_pack_keyframe_device(orbx_handle *h, int32_t nframes, const orbx_keypoint *d_kps, const uint8_t *d_desc,
+                                      const int32_t *d_counts, int32_t cap_per_frame, const uint16_t *d_depth, int32_t width, int32_t height,
+                                      size_t dstep, size_t dframe_stride, const orbx_kfparams *params,
+                                      orbx_kfrecord *d_out, int32_t *d_out_counts, int32_t out_cap_per_frame);
+orbx_status orbx_pack_keyframe(orbx_handle *h, const orbx_keypoint *kps, const uint8_t *desc, int32_t n, const uint16_t *depth,
+                               int32_t width, int32_t height, size_t dstep, const orbx_kfparams *params,
+                               orbx_kfrecord *out, int32_t cap, int32_t *n_out);
 
 /* ---- stage access for parity tests (the reference exposes mvImagePyramid publicly, ORBextractor.hpp:84) ----
  * Valid after an extract call, for frame slot `frame` of the last batch.  Host outputs.          */

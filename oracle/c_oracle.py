@@ -238,6 +238,23 @@ def associate(q, qpx, rows, pos, R, t, fx, fy, cx, cy, max_desc=50.0, max_reproj
     return idx, err, dist
 
 
+KF_DTYPE = np.dtype([("landmark_id", "<u8"), ("position", "<f8", (3,)), ("pixel_x", "<f8"), ("pixel_y", "<f8"), ("descriptor", "u1", (32,))])
+assert KF_DTYPE.itemsize == 80
+
+
+def pack_keyframe(kps, desc, depth, fx, fy, cx, cy, R, t):
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    depth = np.ascontiguousarray(depth, np.uint16)
+    R = np.ascontiguousarray(R, np.float64)
+    t = np.ascontiguousarray(t, np.float64).reshape(3)
+    out = np.zeros(max(len(kps), 1), KF_DTYPE)
+    lib().orc_pack_keyframe.restype = ct.c_int
+    m = lib().orc_pack_keyframe(_p(kps), _p(desc), len(kps), _p(depth), depth.shape[1], depth.shape[0], ct.c_size_t(depth.strides[0] // 2),
+                                ct.c_float(fx), ct.c_float(fy), ct.c_float(cx), ct.c_float(cy), _p(R), _p(t), _p(out))
+    return out[:m].copy()
+
+
 def bgr2gray(bgr):
     bgr = np.ascontiguousarray(bgr, np.uint8)
     h, w, _ = bgr.shape

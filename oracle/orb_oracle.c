@@ -945,3 +945,30 @@ void orc_bgr2gray(const uint8_t *bgr, int w, int h, size_t sstep, uint8_t *gray,
         for (int x = 0; x < w; x++) d[x] = (uint8_t)((3735 * s[3 * x] + 19235 * s[3 * x + 1] + 9798 * s[3 * x + 2] + 16384) >> 15);
     }
 }
+
+/* ---- Frontend::publishKeyframe, landmark / observation packing (reference frontend.cpp:731-776) ----
+ * per keypoint i: x = round(pt.x), y = round(pt.y) (half away from zero); d = depth_u16(y, x) * 0.001f; camera point
+ * ((pt.x - cx) * d / fx, (pt.y - cy) * d / fy, d) in float (rgb_fx_ .. are float members, :278); kept iff z > 0.3 && z < 3.0
+ * (float z against double literals); world = R * p + t in double (cv::Mat: ((r0*p0 + r1*p1) + r2*p2) + t, no FMA).
+ * Record = Landmark {id = i, position} + Observation {id = i, pixel_x, pixel_y (double from float), descriptor[32]}.
+ * The reference indexes the depth image unchecked (the keypoints it passes were depth-filtered); pixels outside the image are skipped here. */
+int orc_pack_keyframe(const orc_keypoint *kps, const uint8_t *desc, int n, const uint16_t *depth, int dw, int dh, size_t dstep_elems,
+                      float fx, float fy, float cx, float cy, const double *R, const double *t, orc_kfrecord *out)
+{
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        const float px = kps[i].x, py = kps[i].y;
+        const int x = (int)roundf(px), y = (int)roundf(py);
+        if (x < 0 || y < 0 || x >= dw || y >= dh) continue;
+        const float d = (float)depth[(size_t)y * dstep_elems + x] * 0.001f;
+        const float X = (px - cx) * d / fx, Y = (py - cy) * d / fy, Z = d;
+        if (!((double)Z > 0.3 && (double)Z < 3.0)) continue;
+        orc_kfrecord *r = &out[m++];
+        r->landmark_id = (uint64_t)i;
+        for (int k = 0; k < 3; k++)
+            r->position[k] = ((R[3 * k] * (double)X + R[3 * k + 1] * (double)Y) + R[3 * k + 2] * (double)Z) + t[k];
+        r->pixel_x = (double)px; r->pixel_y = (double)py;
+        memcpy(r->descriptor, desc + (size_t)i * 32, 32);
+    }
+    return m;
+}

@@ -99,6 +99,12 @@ void orc_associate(const uint8_t *q, const float *qpx, int nq, const uint8_t *ro
                    const double *R, const double *t, double fx, double fy, double cx, double cy,
                    double max_desc, double max_reproj, int32_t *out_idx, double *out_err, float *out_dist, int nthreads);
 
+/* one Landmark + Observation pair of Keyframe.msg (reference msg/Landmark.msg, msg/Observation.msg), 80 bytes */
+typedef struct { uint64_t landmark_id; double position[3]; double pixel_x, pixel_y; uint8_t descriptor[32]; } orc_kfrecord;
+/* Frontend::publishKeyframe packing loop (frontend.cpp:731-776); returns the number of records */
+int orc_pack_keyframe(const orc_keypoint *kps, const uint8_t *desc, int n, const uint16_t *depth, int dw, int dh, size_t dstep_elems,
+                      float fx, float fy, float cx, float cy, const double *R, const double *t, orc_kfrecord *out);
+
 /* cv::cvtColor(BGR2GRAY), reference frontend.cpp:1084 */
 void orc_bgr2gray(const uint8_t *bgr, int w, int h, size_t sstep, uint8_t *gray, size_t dstep);
 

@@ -170,3 +170,46 @@ def test_empty_and_featureless_frames(built):
         assert len(m) == 0
     finally:
         ex.close()
+
+
+def test_pack_keyframe(built, stream_ref, oracle):
+    """Keyframe.msg landmark / observation records (reference frontend.cpp:731-776): host call and batched device call vs the oracle."""
+    import torch
+    import orbx
+    frames, depths, ref = stream_ref
+    rng = np.random.default_rng(12)
+    R, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    t = rng.standard_normal(3)
+    fx, fy, cx, cy = 615.3, 615.9, 320.2, 240.4
+    ex = orbx.ORBextractor(max_width=W, max_height=H, max_batch=4)
+    try:
+        for f in (0, 5):
+            kps, desc = ref[f]["raw_kps"], ref[f]["raw_desc"]             # unfiltered list: the depth gate does the filtering
+            want = oracle.pack_keyframe(kps, desc, depths[f], fx, fy, cx, cy, R, t)
+            got = ex.pack_keyframe(kps, desc, depths[f], fx, fy, cx, cy, R, t)
+            assert 0 < len(want) < len(kps)
+            assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), "keyframe records frame %d" % f
+        # batched, device-resident: straight from the extractor's outputs
+        dev = torch.device("cuda", 0)
+        nb, CAP = 3, 1536
+        g = torch.from_numpy(frames[:nb]).to(dev)
+        d = torch.from_numpy(depths[:nb].view(np.int16)).to(dev)
+        kps = torch.zeros((nb, CAP, 28), dtype=torch.uint8, device=dev)
+        desc = torch.zeros((nb, CAP, 32), dtype=torch.uint8, device=dev)
+        cnt = torch.zeros(nb, dtype=torch.int32, device=dev)
+        rec = torch.zeros((nb, CAP, 80), dtype=torch.uint8, device=dev)
+        rcnt = torch.zeros(nb, dtype=torch.int32, device=dev)
+        K = np.zeros(1, orbx.KFPARAMS_DTYPE)
+        K["R"][0], K["t"][0] = R.reshape(9), t
+        K["fx"], K["fy"], K["cx"], K["cy"] = fx, fy, cx, cy
+        torch.cuda.synchronize()
+        ex.extract_batch_device(g.data_ptr(), nb, W, H, W, W * H, kps.data_ptr(), desc.data_ptr(), CAP, cnt.data_ptr())
+        ex._check(ex.L.orbx_pack_keyframe_device(ex.handle, nb, kps.data_ptr(), desc.data_ptr(), cnt.data_ptr(), CAP, d.data_ptr(), W, H, 2 * W, 2 * W * H,
+                                                 K.ctypes.data_as(ct.c_void_p), rec.data_ptr(), rcnt.data_ptr(), CAP))
+        ex.sync()
+        rc, rr = rcnt.cpu().numpy(), rec.cpu().numpy().view(orbx.KF_DTYPE).reshape(nb, CAP)
+        for f in range(nb):
+            want = oracle.pack_keyframe(ref[f]["raw_kps"], ref[f]["raw_desc"], depths[f], fx, fy, cx, cy, R, t)
+            assert rc[f] == len(want) and np.array_equal(rr[f, :rc[f]].view(np.uint8), want.view(np.uint8))
+    finally:
+        ex.close()

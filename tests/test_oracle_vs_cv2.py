@@ -141,3 +141,29 @@ def test_bgr2gray_vs_cv2(oracle):
     assert np.array_equal(oracle.bgr2gray(bgr), cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
     g = rng.integers(0, 256, (50, 64), dtype=np.uint8)
     assert np.array_equal(oracle.bgr2gray(np.stack([g, g, g], 2)), g)
+
+
+def test_pack_keyframe_vs_cv2(oracle):
+    """Frontend::publishKeyframe packing loop (reference frontend.cpp:731-776) against a literal numpy/cv2 statement."""
+    w, h = 320, 240
+    g = oracle.synth_gray(6, 0, w, h)
+    depth = oracle.synth_depth(6, 0, w, h)
+    r = oracle.COracle().extract(g)
+    rng = np.random.default_rng(8)
+    R, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    t = rng.standard_normal(3)
+    fx, fy, cx, cy = np.float32(305.4), np.float32(306.1), np.float32(160.3), np.float32(119.7)
+    rec = oracle.pack_keyframe(r["kps"], r["desc"], depth, fx, fy, cx, cy, R, t)
+    want = []
+    for i, kp in enumerate(r["kps"]):
+        x, y = int(np.floor(abs(kp["x"]) + 0.5) * np.sign(kp["x"])), int(np.floor(abs(kp["y"]) + 0.5) * np.sign(kp["y"]))
+        d = np.float32(depth[y, x]) * np.float32(0.001)
+        X = np.float32(np.float32(kp["x"] - cx) * d) / fx
+        Y = np.float32(np.float32(kp["y"] - cy) * d) / fy
+        if float(d) > 0.3 and float(d) < 3.0:
+            pw = cv2.gemm(R, np.array([[X], [Y], [d]], np.float64), 1.0, t.reshape(3, 1), 1.0).ravel()
+            want.append((i, pw, float(kp["x"]), float(kp["y"]), r["desc"][i]))
+    assert len(rec) == len(want) and 0 < len(rec) < len(r["kps"])
+    for a, (i, pw, px, py, dsc) in zip(rec, want):
+        assert a["landmark_id"] == i and np.array_equal(a["position"].view(np.uint64), pw.view(np.uint64))
+        assert a["pixel_x"] == px and a["pixel_y"] == py and np.array_equal(a["descriptor"], dsc)
