@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(BL_THREADS) k_blur7(const __grid_constant__ Le
     __syncthreads();                                                                 // barrier initialised before anyone polls it
     mbar_wait(&s_bar, 0);
     // ---- reflect-101 halo of border tiles (image pixel (x, y) lives at s_img[(y - y0 + 3) * 288 + x - x0 + 16]) ----
-    const bool edge_l = x0 == 0, edge_r = x0 + BL_TW + 3 > w, edge_t = y0 == 0, edge_b = y0 + TH + 3 > hgt;
+    const bool edge_l = x0 == 0, edge_r = x0 + BL_TW + 3 > w, edge_t = y0 < 3, edge_b = y0 + TH + 3 > hgt;
     if (edge_l || edge_r) {
         for (int r = threadIdx.x; r < TH + 6; r += BL_THREADS) {
             const int y = y0 - 3 + r;
@@ -70,14 +70,14 @@ __global__ void __launch_bounds__(BL_THREADS) k_blur7(const __grid_constant__ Le
         __syncthreads();
     }
     if (edge_t || edge_b) {
-        for (int i = threadIdx.x; i < 6 * ORBX_TMA_BOX_WORDS; i += BL_THREADS) {
-            const int k = i / ORBX_TMA_BOX_WORDS, wd = i - k * ORBX_TMA_BOX_WORDS;   // k: 0..2 top rows -1..-3, 3..5 bottom rows h..h+2
-            uint32_t *sw = reinterpret_cast<uint32_t *>(s_img);
-            if (k < 3) { if (edge_t) sw[(2 - k) * ORBX_TMA_BOX_WORDS + wd] = sw[(4 + k) * ORBX_TMA_BOX_WORDS + wd]; }
-            else if (edge_b) {
-                const int d = k - 3, rdst = hgt + d - y0 + 3, rsrc = hgt - 2 - d - y0 + 3;
-                if (rdst < TH + 6) sw[rdst * ORBX_TMA_BOX_WORDS + wd] = sw[rsrc * ORBX_TMA_BOX_WORDS + wd];
-            }
+        // rows above / below the image mirror the (column-patched) rows inside it: y -> -y resp. 2(h-1) - y
+        uint32_t *sw = reinterpret_cast<uint32_t *>(s_img);
+        for (int i = threadIdx.x; i < (TH + 6) * ORBX_TMA_BOX_WORDS; i += BL_THREADS) {
+            const int r = i / ORBX_TMA_BOX_WORDS, wd = i - r * ORBX_TMA_BOX_WORDS;
+            const int y = y0 - 3 + r;
+            if (y >= 0 && y < hgt) continue;
+            const int ys = y < 0 ? -y : 2 * hgt - 2 - y, rs = ys - y0 + 3;
+            if (ys >= 0 && ys < hgt && rs >= 0 && rs < TH + 6) sw[r * ORBX_TMA_BOX_WORDS + wd] = sw[rs * ORBX_TMA_BOX_WORDS + wd];
         }
         __syncthreads();
     }

@@ -102,7 +102,8 @@ static bool build_geometry(const orbx_handle *h, int w, int hgt, FrameGeom &G, s
             g.nini = (int)roundf((float)W / H);                                                           // :559
             if (g.nini < 1 || g.nini > 64) return false;          // reference divides by zero for nini == 0
             g.hx = (float)W / g.nini;                                                                     // :560
-        } else { g.ncols = g.nrows = 0; g.wcell = g.hcell = 1; g.nini = 0; g.hx = 1.f; }
+        } else { g.ncols = g.nrows = 0; g.wcell = 1; g.hcell = std::max(8, std::min(32, g.h)); g.nini = 0; g.hx = 1.f; }   // no cell grid: hcell only sizes the blur tiles
+        max_hcell = std::max(max_hcell, g.hcell);
         g.cell_first = cells; cells += g.ncols * g.nrows;
         if (g.ncols > 0) {
             const int cps_max = std::max(1, std::min(8, ORBX_FAST_MAX_W / g.wcell));

@@ -9,7 +9,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-SIZES = [(1280, 720, 7), (640, 480, 3), (741, 417, 11)]
+SIZES = [(1280, 720, 7), (640, 480, 3), (741, 417, 11), (200, 150, 9)]
 
 
 @pytest.fixture(scope="module")
@@ -53,6 +53,26 @@ def test_stages_bit_exact(ex, oracle, w, h, seed):
     assert len(kps) == len(ref["kps"])
     assert np.array_equal(kps.view(np.uint8), ref["kps"].view(np.uint8)), "keypoints"
     assert np.array_equal(desc, ref["desc"]), "descriptors"
+
+
+def test_full_hd_and_other_parameters(built, oracle):
+    """1920x1080 and non-default extractor parameters (nfeatures, scale factor, levels, thresholds) stay bit-exact."""
+    import orbx
+    for (w, h, kw) in [(1920, 1080, dict()), (960, 540, dict(nfeatures=2000, scaleFactor=1.3, nlevels=6, iniThFAST=30, minThFAST=10)),
+                       (800, 600, dict(nfeatures=500, scaleFactor=1.1, nlevels=10, iniThFAST=12, minThFAST=5))]:
+        e = orbx.ORBextractor(max_width=w, max_height=h, **kw)
+        try:
+            g = oracle.synth_gray(31, 1, w, h)
+            ref = oracle.COracle(**kw).extract(g, trace=True)
+            kps, desc = e(g, cap=8192)
+            nl = kw.get("nlevels", 8)
+            for l in range(nl):
+                assert np.array_equal(e.pyramid_level(l), ref["pyramid"][l]), ("pyramid", w, h, l)
+                assert np.array_equal(e.blurred_level(l), ref["blurred"][l]), ("blurred", w, h, l)
+            assert list(e.level_counts()) == ref["nkeys"]
+            assert np.array_equal(kps.view(np.uint8), ref["kps"].view(np.uint8)) and np.array_equal(desc, ref["desc"]), (w, h, kw)
+        finally:
+            e.close()
 
 
 def test_match_bit_exact(ex, oracle):
