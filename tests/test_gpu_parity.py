@@ -75,6 +75,26 @@ def test_full_hd_and_other_parameters(built, oracle):
             e.close()
 
 
+@pytest.mark.parametrize("w,h", [(257, 193), (511, 383), (513, 385), (1027, 771), (389, 263), (1281, 721), (833, 479), (1279, 719), (96, 80)])
+def test_awkward_sizes(built, oracle, w, h):
+    """Sizes around the tile boundaries of the kernels (256-px blur tiles, 192-px resize tiles, 16-byte TMA columns)."""
+    import orbx
+    e = orbx.ORBextractor(max_width=w, max_height=h)
+    try:
+        g = oracle.synth_gray(w * 7 + h, 0, w, h)
+        ref = oracle.COracle().extract(g, trace=True)
+        kps, desc = e(g, cap=8192)
+        for l in range(8):
+            assert np.array_equal(e.pyramid_level(l), ref["pyramid"][l]), ("pyramid", l)
+            assert np.array_equal(e.blurred_level(l), ref["blurred"][l]), ("blurred", l)
+            c = e.candidates(l)
+            r = ref["cands"][l]
+            assert sorted(map(tuple, c.tolist())) == sorted(zip(r["x"].tolist(), r["y"].tolist(), r["score"].tolist())), ("FAST", l)
+        assert np.array_equal(kps.view(np.uint8), ref["kps"].view(np.uint8)) and np.array_equal(desc, ref["desc"])
+    finally:
+        e.close()
+
+
 def test_match_bit_exact(ex, oracle):
     w, h = 1280, 720
     g0, g1 = oracle.synth_gray(7, 0, w, h), oracle.synth_gray(7, 1, w, h)
