@@ -127,8 +127,7 @@ int launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, 
     P.tiles = h->d_blur_tiles;
     P.tile_rows = h->geo.max_hcell + 6;
     const size_t smem = 128 + (size_t)(P.tile_rows + BL_PADROWS) * ORBX_TMA_BOX_BYTES;
-    static size_t configured = 0;
-    if (smem > configured) { cudaFuncSetAttribute(k_blur7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = smem; }
+    if (smem > h->blur_smem) { cudaFuncSetAttribute(k_blur7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); h->blur_smem = smem; }
     dim3 grid(h->geo.total_blur_tiles, nframes);
     ProfScope ps(h, ORBX_K_BLUR, st);
     k_blur7<<<grid, BL_THREADS, smem, st>>>(M, P, h->d_geo);

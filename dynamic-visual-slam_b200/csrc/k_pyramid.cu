@@ -113,8 +113,7 @@ int launch_resize_level(orbx_handle *h, int level, int nframes, const uint8_t *l
     P.xtab = h->d_xtab + gd.xtab_off; P.ytab = h->d_ytab + gd.ytab_off;
     P.tw = h->geo.rz_tw; P.th = h->geo.rz_th; P.src_level = level - 1;
     const size_t smem = 128 + (size_t)ORBX_RZ_BOX_ROWS * ORBX_TMA_BOX_BYTES;
-    static bool configured = false;
-    if (!configured) { cudaFuncSetAttribute(k_resize_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+    if (!h->rz_configured) { cudaFuncSetAttribute(k_resize_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); h->rz_configured = true; }
     dim3 grid((gd.w + P.tw - 1) / P.tw, (gd.h + P.th - 1) / P.th, nframes);
     ProfScope ps(h, ORBX_K_RESIZE);
     k_resize_linear<<<grid, RZ_THREADS, smem, h->stream>>>(M, P);

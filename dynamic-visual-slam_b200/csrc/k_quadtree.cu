@@ -451,10 +451,9 @@ void launch_quadtree_geo(orbx_handle *h, const FrameGeom *d_geo, int nlevels, in
     P.sel = h->d_sel; P.sel_slab = sel_slab; P.nsel = h->d_nsel; P.status = h->d_status;
     P.node_cap = node_cap;
     const size_t smem = quadtree_smem(node_cap);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 48 * 1024 && smem > h->quad_smem) {
         cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
+        h->quad_smem = smem;
     }
     dim3 grid(nlevels, nframes);
     ProfScope ps(h, ORBX_K_QUADTREE);

@@ -95,6 +95,7 @@ struct orbx_handle {
     CUtensorMap tmap_cell[ORBX_MAX_LEVELS];                  // box = 96 bytes x (hCell + 6) rows (FAST cell windows)
     uint32_t *d_cells; int cell_cap;                         // FAST cell descriptors (k_fast.cu)
     const uint8_t *tmap_l0; size_t tmap_l0_step, tmap_l0_fstride; int tmap_l0_frames;
+    size_t blur_smem, quad_smem; bool rz_configured;      // per-handle (= per-device) dynamic shared memory opt-ins
     int fast_grid_cap; size_t fast_smem; int fast_tp;   // resident CTAs / dynamic smem / tile pitch of the persistent FAST kernel
     // arenas, sized for max_width x max_height x max_batch
     uint8_t *d_pyr, *d_blur;     size_t pyr_slab, blur_slab;          // current per-frame strides

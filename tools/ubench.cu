@@ -19,6 +19,8 @@ template <int OP> __device__ __forceinline__ uint32_t op(uint32_t a, uint32_t b,
     if (OP == 10) return __popc(a ^ b);                         // LOP3 + POPC
     if (OP == 11) return __funnelshift_r(a, b, 8);              // SHF
     if (OP == 12) return __vsadu4(a, b) + c;                    // VABSDIFF4 accumulate
+    if (OP == 13) return __umulhi(a, b) + c;                    // IMAD.HI
+    if (OP == 14) return __dp2a_lo(a, b, c);                    // IDP.2A
     return a;
 }
 template <int OP> __global__ void k(uint32_t *out, uint32_t seed)
@@ -69,7 +71,7 @@ int main()
     run<1>("VIMNMX.U16x2", d, sms); run<2>("VIMNMX3.U16x2", d, sms);
     run<7>("VIMNMX.U32", d, sms); run<8>("VIMNMX3.U32", d, sms);
     run<3>("PRMT", d, sms); run<4>("LOP3", d, sms); run<5>("IADD", d, sms); run<6>("IMAD", d, sms);
-    run<9>("IDP.4A", d, sms); run<10>("LOP3+POPC", d, sms); run<11>("SHF", d, sms);
+    run<9>("IDP.4A", d, sms); run<13>("IMAD.HI", d, sms); run<14>("IDP.2A", d, sms); run<10>("LOP3+POPC", d, sms); run<11>("SHF", d, sms);
     for (int w = 1; w <= 4; w += 3) {
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         k_lds<<<sms * 8, 256>>>(d, w); cudaDeviceSynchronize();
