@@ -34,6 +34,15 @@ def boundary_pairs(total_frames, world):
     return out
 
 
+def stream_block(total_frames, world, rank):
+    """Frame-to-frame matching over a stream that is block-partitioned across ranks (BASELINE configs[1]/[2]):
+    rank r owns frames [first, first + count); to match its first frame against frame first-1 — which lives on rank r-1 — it
+    re-extracts that one frame as a PREAMBLE (cheaper than a peer copy that would serialise the ranks) and discards its outputs.
+    Returns (first, count, preamble) with preamble = first - 1 or None for the rank that holds frame 0."""
+    first, count = block_range(total_frames, world, rank)
+    return first, count, (first - 1 if first > 0 and count > 0 else None)
+
+
 class ShardedLandmarkDB:
     """Row-sharded landmark database with an all-gather merge (BASELINE configs[3]).
 

@@ -213,3 +213,21 @@ def test_pack_keyframe(built, stream_ref, oracle):
             assert rc[f] == len(want) and np.array_equal(rr[f, :rc[f]].view(np.uint8), want.view(np.uint8))
     finally:
         ex.close()
+
+
+def test_stream_blocks_with_preamble(built, stream_ref):
+    """A stream cut into rank blocks (sharding.stream_block): with the one-frame preamble every block reproduces the matches of
+    the unsharded stream, including the pair that straddles the block boundary."""
+    import orbx
+    from orbx import sharding
+    frames, depths, ref = stream_ref
+    world = 3
+    for rank in range(world):
+        first, count, pre = sharding.stream_block(N, world, rank)
+        ex = orbx.ORBextractor(max_width=W, max_height=H, max_batch=4)
+        try:
+            if pre is not None:
+                ex.track_batch(frames[pre:pre + 1], depths[pre:pre + 1])        # outputs discarded: only the carried descriptors matter
+            _check_track(ex.track_batch(frames[first:first + count], depths[first:first + count]), ref, first)
+        finally:
+            ex.close()

@@ -102,6 +102,10 @@ def test_block_range_partitions():
     assert sharding.boundary_pairs(4096, 8) == [(512 * r, 512 * r - 1) for r in range(1, 8)]
     with pytest.raises(ValueError):
         sharding.block_range(10, 2, 2)
+    # stream blocks: every rank but the first re-extracts its predecessor frame as a preamble
+    assert sharding.stream_block(4096, 8, 0) == (0, 512, None)
+    assert sharding.stream_block(4096, 8, 3) == (1536, 512, 1535)
+    assert sharding.stream_block(3, 8, 5) == (3, 0, None)
 
 
 def test_merge_reference_handles_missing_entries():
