@@ -7,11 +7,21 @@ tag, launches, rep = sys.argv[1], sys.argv[2], sys.argv[3]
 bench = json.load(open(sys.argv[4])) if len(sys.argv) > 4 else None
 root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles")
 os.makedirs(root, exist_ok=True)
+import re
+
+
+def kname(full):
+    """'void k_fast_cells<80>(LevelMaps, ...)' -> 'k_fast_cells'"""
+    n = full.split("(")[0].strip()
+    n = re.sub(r"^void\s+", "", n)
+    return re.sub(r"<.*$", "", n)
+
+
 rows = [r for r in csv.reader(open(launches)) if len(r) > 10 and r[0].isdigit()]
 out = [("id", "kernel", "block", "grid", "gpu__time_duration_ns")]
 agg = collections.OrderedDict()
 for r in rows:
-    name = r[4].split("(")[0]
+    name = kname(r[4])
     out.append((r[0], name, r[7], r[8], r[-1]))
     a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += float(r[-1])
 csv.writer(open(os.path.join(root, tag + "_launches.csv"), "w")).writerows(out)
@@ -31,7 +41,7 @@ idx = {c: i for i, c in enumerate(hdr)}
 krows = [["kernel"] + ["%s [%s]" % (w, units[idx[w]]) for w in want if w in idx]]
 seen = {}
 for r in rr[2:]:
-    name = r[idx["Kernel Name"]].split("(")[0]
+    name = kname(r[idx["Kernel Name"]])
     seen[name] = seen.get(name, 0) + 1
     krows.append(["%s#%d" % (name, seen[name])] + [r[idx[w]] for w in want if w in idx])
 csv.writer(open(os.path.join(root, tag + "_kernels.csv"), "w")).writerows(krows)
@@ -40,7 +50,7 @@ FRAMES = 32                                       # tools/profile_round.sh captu
 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 traffic = {}
 for r in rr[2:]:
-    name = r[idx["Kernel Name"]].split("(")[0]
+    name = kname(r[idx["Kernel Name"]])
     b = sum(float(r[idx[m]]) * scale.get(units[idx[m]], 1.0) for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
     t = traffic.setdefault(name, {"launches": 0, "dram_bytes": 0.0})
     t["launches"] += 1; t["dram_bytes"] += b
