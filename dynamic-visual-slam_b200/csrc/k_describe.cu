@@ -201,6 +201,35 @@ void launch_describe_to(orbx_handle *h, int nframes, const uint8_t *l0, size_t l
     k_describe<<<grid, DESC_WARPS * 32, 0, h->stream>>>(P, h->d_geo);
 }
 
+// ---- Harris response of given points of one pyramid level (cv::ORB's HarrisResponses; HARRIS_SCORE of ORBextractor.hpp:48) ----
+// integer 7x7 sums of the Sobel-like derivatives, then the fp32 expression in OpenCV's operation order (no FMA)
+__global__ void k_harris(const uint8_t *img, size_t step, int w, int h, const int32_t *xy, int n, int bs, float k, float *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x0 = xy[2 * i], y0 = xy[2 * i + 1], r = bs / 2;
+    if (x0 - r - 1 < 0 || y0 - r - 1 < 0 || x0 + r + 1 >= w || y0 + r + 1 >= h) { out[i] = 0.f; return; }
+    int a = 0, b = 0, c = 0;
+    const int st = (int)step;
+    for (int u = 0; u < bs; u++) for (int v = 0; v < bs; v++) {
+        const uint8_t *p = img + (size_t)(y0 - r + u) * step + (x0 - r + v);
+        const int Ix = ((int)__ldg(p + 1) - (int)__ldg(p - 1)) * 2 + ((int)__ldg(p - st + 1) - (int)__ldg(p - st - 1)) + ((int)__ldg(p + st + 1) - (int)__ldg(p + st - 1));
+        const int Iy = ((int)__ldg(p + st) - (int)__ldg(p - st)) * 2 + ((int)__ldg(p + st - 1) - (int)__ldg(p - st - 1)) + ((int)__ldg(p + st + 1) - (int)__ldg(p - st + 1));
+        a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
+    }
+    const float scale = __fdiv_rn(1.f, __fmul_rn((float)(4 * bs), 255.f));
+    const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+    const float fa = (float)a, fb = (float)b, fc = (float)c, sum = __fadd_rn(fa, fb);
+    const float v = __fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(k, sum), sum));
+    out[i] = __fmul_rn(v, s4);
+}
+void launch_harris(orbx_handle *h, const uint8_t *img, size_t step, int w, int hgt, const int32_t *d_xy, int n, int bs, float k, float *d_out)
+{
+    if (n <= 0) return;
+    ProfScope ps(h, ORBX_K_OTHER);
+    k_harris<<<(n + 127) / 128, 128, 0, h->stream>>>(img, step, w, hgt, d_xy, n, bs, k, d_out);
+}
+
 // ---- device self-tests of the floating-point restatements ----
 __global__ void k_test_trig(const float *in, int n, float *oc, float *os)
 {

@@ -805,6 +805,24 @@ extern "C" orbx_status orbx_get_candidates(orbx_handle *h, int32_t frame, int32_
     for (int i = 0; i < n; i++) { out_xys[3 * i] = orbx_px(tmp[i]); out_xys[3 * i + 1] = orbx_py(tmp[i]); out_xys[3 * i + 2] = orbx_ps(tmp[i]); }
     return ORBX_OK;
 }
+extern "C" orbx_status orbx_harris_responses(orbx_handle *h, int32_t frame, int32_t level, const int32_t *xy, int32_t n, int32_t bs, float k, float *out)
+{
+    if (!h || level < 0 || level >= h->geo.nlevels || frame < 0 || frame >= h->last_batch || n < 0 || (n > 0 && (!xy || !out)) || bs < 1 || bs > 31 || !(bs & 1)) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    if (n == 0) return ORBX_OK;
+    const LevelGeom &g = h->geo.lv[level];
+    const uint8_t *src; size_t step;
+    if (level == 0) { src = h->last_l0 + (size_t)frame * h->last_l0_fstride; step = h->last_l0_step; }
+    else { src = h->d_pyr + (size_t)frame * h->pyr_slab + g.off; step = g.pitch; }
+    orbx_status st;
+    if ((st = grow(h, &h->d_mq, &h->mq_cap, (size_t)n * 12)) != ORBX_OK) return st;
+    int32_t *d_xy = (int32_t *)h->d_mq; float *d_o = (float *)(h->d_mq + (size_t)n * 8);
+    ORBX_CUDA(h, cudaMemcpyAsync(d_xy, xy, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    launch_harris(h, src, step, g.w, g.h, d_xy, n, bs, k, d_o);
+    ORBX_CUDA(h, cudaMemcpyAsync(out, d_o, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
 extern "C" orbx_status orbx_get_level_counts(orbx_handle *h, int32_t frame, int32_t *out)
 {
     if (!h || !out || frame < 0 || frame >= h->last_batch) return ORBX_E_INVALID;

@@ -184,6 +184,7 @@ void launch_assoc_merge(orbx_handle *h, const orbx_assoc *d_parts, int nparts, i
 void launch_pack_keyframe(orbx_handle *h, int nframes, const orbx_keypoint *d_kps, const uint8_t *d_desc, const int32_t *d_counts, int cap_in,
                           const uint16_t *d_depth, size_t dstep, size_t dfstride, int dw, int dh, const orbx_kfparams *K,
                           orbx_kfrecord *d_out, int32_t *d_nout, int cap_out);
+void launch_harris(orbx_handle *h, const uint8_t *img, size_t step, int w, int hgt, const int32_t *d_xy, int n, int bs, float k, float *d_out);
 void launch_bgr2gray(orbx_handle *h, const uint8_t *d_bgr, size_t sstep, size_t sfstride, uint8_t *d_gray, size_t dstep, size_t dfstride,
                      int w, int hgt, int nframes, cudaStream_t st);
 void launch_merge_top2(orbx_handle *h, const orbx_top2 *d_parts, int nshards, int nq, orbx_top2 *d_out);

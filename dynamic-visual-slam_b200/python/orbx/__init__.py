@@ -106,6 +106,7 @@ def load():
         "orbx_get_blurred_level": (i32, [vp, i32, i32, vp, sz]),
         "orbx_get_candidates": (i32, [vp, i32, i32, vp, i32, vp]),
         "orbx_get_level_counts": (i32, [vp, i32, vp]),
+        "orbx_harris_responses": (i32, [vp, i32, i32, vp, i32, i32, f32, vp]),
         "orbx_synth_gray_device": (i32, [vp, u32, i32, i32, i32, i32, vp, sz, sz]),
         "orbx_synth_depth_device": (i32, [vp, u32, i32, i32, i32, i32, vp, sz, sz]),
         "orbx_synth_descriptors_device": (i32, [vp, u32, u64, i64, vp]),
@@ -419,6 +420,13 @@ class ORBextractor:
     def level_counts(self, frame=0):
         out = np.zeros(self.nlevels, np.int32)
         self._check(self.L.orbx_get_level_counts(self._h, frame, _p(out)))
+        return out
+
+    def harris_responses(self, level, xy, frame=0, block=7, k=0.04):
+        """cv::ORB's Harris response at integer (x, y) points of a pyramid level of the last extracted frame."""
+        xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)
+        out = np.zeros(len(xy), np.float32)
+        self._check(self.L.orbx_harris_responses(self._h, frame, level, _p(xy), len(xy), block, ct.c_float(k), _p(out)))
         return out
 
     def set_size(self, w, h):

@@ -252,6 +252,10 @@ orbx_status orbx_pack_keyframe(orbx_handle *h, const orbx_keypoint *kps, const u
  * Valid after an extract call, for frame slot `frame` of the last batch.  Host outputs.          */
 orbx_status orbx_get_pyramid_level(orbx_handle *h, int32_t frame, int32_t level, uint8_t *out, size_t out_step);
 orbx_status orbx_get_blurred_level(orbx_handle *h, int32_t frame, int32_t level, uint8_t *out, size_t out_step);
+/* Harris corner response (cv::ORB's HarrisResponses, block 7, k 0.04: the HARRIS_SCORE the reference's ORBextractor.hpp:48 names but
+ * never computes) of n points, given as (x, y) int32 pairs in the coordinates of pyramid level `level` of frame slot `frame` of the
+ * last batch.  Points closer than block/2 + 1 to the level's edge score 0.                                                    */
+orbx_status orbx_harris_responses(orbx_handle *h, int32_t frame, int32_t level, const int32_t *xy, int32_t n, int32_t block_size, float k, float *out);
 /* FAST candidates of a level before distribution: packed (x, y, score) relative to the border box,
  * unordered.  out_xys: int32 triples.                                                             */
 orbx_status orbx_get_candidates(orbx_handle *h, int32_t frame, int32_t level, int32_t *out_xys, int32_t cap, int32_t *n_out);

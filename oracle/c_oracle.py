@@ -255,6 +255,13 @@ def pack_keyframe(kps, desc, depth, fx, fy, cx, cy, R, t):
     return out[:m].copy()
 
 
+def harris_response(img, x, y, block=7, k=0.04):
+    img = np.ascontiguousarray(img, np.uint8)
+    f = lib().orc_harris_response
+    f.restype = ct.c_float
+    return float(f(_p(img), ct.c_size_t(img.strides[0]), int(x), int(y), int(block), ct.c_float(k)))
+
+
 def bgr2gray(bgr):
     bgr = np.ascontiguousarray(bgr, np.uint8)
     h, w, _ = bgr.shape

@@ -972,3 +972,23 @@ int orc_pack_keyframe(const orc_keypoint *kps, const uint8_t *desc, int n, const
     }
     return m;
 }
+
+/* Harris corner response as cv::ORB computes it (OpenCV features2d orb.cpp HarrisResponses; the reference's ORBextractor.hpp:48 names
+ * HARRIS_SCORE but never computes it): blockSize x blockSize sums of Ix^2, Iy^2, IxIy with
+ * Ix = 2(I[x+1]-I[x-1]) + (I[y-1][x+1]-I[y-1][x-1]) + (I[y+1][x+1]-I[y+1][x-1]) (Iy alike), integer; response in fp32 =
+ * (a*b - c*c - k*(a+b)^2) * (1/(4*blockSize*255))^4.  Pinned against cv2.ORB_create(nlevels=1) responses (exact). */
+float orc_harris_response(const uint8_t *img, size_t step, int x0, int y0, int blockSize, float k)
+{
+    const int r = blockSize / 2;
+    int a = 0, b = 0, c = 0;
+    for (int i = 0; i < blockSize; i++) for (int j = 0; j < blockSize; j++) {
+        const uint8_t *p = img + (size_t)(y0 - r + i) * step + (x0 - r + j);
+        const int st = (int)step;
+        const int Ix = (p[1] - p[-1]) * 2 + (p[-st + 1] - p[-st - 1]) + (p[st + 1] - p[st - 1]);
+        const int Iy = (p[st] - p[-st]) * 2 + (p[st - 1] - p[-st - 1]) + (p[st + 1] - p[-st + 1]);
+        a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
+    }
+    const float scale = 1.f / ((1 << 2) * blockSize * 255.f);
+    const float s4 = scale * scale * scale * scale;
+    return ((float)a * b - (float)c * c - k * ((float)a + b) * ((float)a + b)) * s4;
+}

@@ -105,6 +105,9 @@ typedef struct { uint64_t landmark_id; double position[3]; double pixel_x, pixel
 int orc_pack_keyframe(const orc_keypoint *kps, const uint8_t *desc, int n, const uint16_t *depth, int dw, int dh, size_t dstep_elems,
                       float fx, float fy, float cx, float cy, const double *R, const double *t, orc_kfrecord *out);
 
+/* cv::ORB's HarrisResponses for one point (HARRIS_SCORE, ORBextractor.hpp:48) */
+float orc_harris_response(const uint8_t *img, size_t step, int x0, int y0, int blockSize, float k);
+
 /* cv::cvtColor(BGR2GRAY), reference frontend.cpp:1084 */
 void orc_bgr2gray(const uint8_t *bgr, int w, int h, size_t sstep, uint8_t *gray, size_t dstep);
 

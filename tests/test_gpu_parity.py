@@ -150,3 +150,20 @@ def test_bgr_ingest(ex, oracle):
     ex.sync()
     out = dst.cpu().numpy()
     assert np.array_equal(out[0, :, :w], gray) and np.array_equal(out[1, :, :w], gray[::-1])
+
+
+def test_harris_responses(ex, oracle):
+    """Harris score (HARRIS_SCORE of ORBextractor.hpp:48 / cv::ORB's HarrisResponses) at the retained keypoints of every level: within 1e-4
+    relative of the oracle (north_star's bar; the arithmetic is integer sums + 7 fp32 operations, so it is in fact bit-identical)."""
+    w, h = 1280, 720
+    g = oracle.synth_gray(7, 0, w, h)
+    orc = oracle.COracle()
+    ref = orc.extract(g, trace=True)
+    kps, _ = ex(g)
+    for l in range(8):
+        sel = kps[kps["octave"] == l]
+        xy = np.stack([np.rint(sel["x"] / orc.scale[l]), np.rint(sel["y"] / orc.scale[l])], 1).astype(np.int32)
+        got = ex.harris_responses(l, xy)
+        want = np.array([oracle.harris_response(ref["pyramid"][l], x, y) for x, y in xy], np.float32)
+        assert len(got) > 30 and np.all(np.abs(got - want) <= 1e-4 * np.abs(want))
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))

@@ -167,3 +167,13 @@ def test_pack_keyframe_vs_cv2(oracle):
     for a, (i, pw, px, py, dsc) in zip(rec, want):
         assert a["landmark_id"] == i and np.array_equal(a["position"].view(np.uint64), pw.view(np.uint64))
         assert a["pixel_x"] == px and a["pixel_y"] == py and np.array_equal(a["descriptor"], dsc)
+
+
+def test_harris_response_vs_cv_orb(oracle):
+    """HARRIS_SCORE: the oracle's Harris response equals cv::ORB's keypoint.response on a single-level cv2.ORB (north_star: <= 1e-4 rel)."""
+    g = oracle.synth_gray(3, 0, 640, 480)
+    kps = cv2.ORB_create(nfeatures=500, nlevels=1).detect(g)
+    assert len(kps) > 100
+    for kp in kps:
+        got = oracle.harris_response(g, int(round(kp.pt[0])), int(round(kp.pt[1])))
+        assert abs(got - kp.response) <= 1e-4 * abs(kp.response)
