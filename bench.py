@@ -30,7 +30,9 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 W, H = 1280, 720
 SEED = 20261018
-METRIC = "frames/s ORB extract+Hamming match, 1280x720"
+WORKLOAD = ("configs[1]: 1280x720 RGB-D stream, 8-level pyramid scale 1.2, depth-filtered extraction + "
+            "frame-to-frame matching (k=1, distance<50)")
+METRIC = "frames/s ORB extract+Hamming match, 1280x720, 1/2/4/8 B200; p50 latency"       # BASELINE.json "metric", verbatim
 # algorithmic bytes per 1280x720 frame, staged model; pixels summed over the 8 levels
 LEVEL_PX = [1280 * 720, 1067 * 600, 889 * 500, 741 * 417, 617 * 347, 514 * 289, 429 * 241, 357 * 201]
 ALG_BYTES = {
@@ -150,8 +152,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "configs[1]: 1280x720 RGB-D stream, depth-filtered extraction + frame-to-frame matching",
-                   "frames_per_step": S, "nfeatures": 1000, "nlevels": 8},
+        "config": {"workload": WORKLOAD, "frames_per_step": S, "width": W, "height": H, "nfeatures": 1000, "nlevels": 8},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -423,8 +424,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1]: 1280x720 RGB-D stream, 8-level pyramid scale 1.2, depth-filtered extraction + "
-                                   "frame-to-frame matching (k=1, distance<50)", "frames_per_step_per_gpu": B, "width": W, "height": H,
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "width": W, "height": H,
                        "nfeatures": 1000, "nlevels": 8, "l2_policy": "inputs larger than L2 (%.0f MB per step per GPU)" % (B * W * H * 3 / 1e6),
                        "sharding": "frame-parallel, no data-path collective",
                        "schedule": "blur on a second stream beside FAST + quadtree; `kernels`/`roofline` timed in a second pass of the same K steps with every kernel on one stream (ORBX_OPT_SERIAL)"},
