@@ -167,3 +167,30 @@ def test_harris_responses(ex, oracle):
         want = np.array([oracle.harris_response(ref["pyramid"][l], x, y) for x, y in xy], np.float32)
         assert len(got) > 30 and np.all(np.abs(got - want) <= 1e-4 * np.abs(want))
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_corner_dense_image_capacity(built, oracle):
+    """White noise makes almost every pixel a FAST corner: the default candidate lists overflow and the call says so
+    (ORBX_E_CAPACITY, nothing truncated silently); with cand_divisor=1 the same frame is bit-exact again."""
+    import orbx
+    w, h = 640, 480
+    g = np.random.default_rng(5).integers(0, 256, (h, w), dtype=np.uint8)
+    ref = oracle.COracle().extract(g, trace=True)
+    assert sum(len(c) for c in ref["cands"]) > 640 * 480 // 16
+    e = orbx.ORBextractor(max_width=w, max_height=h)
+    try:
+        with pytest.raises(orbx.OrbxError) as err:
+            e(g)
+        assert err.value.status == orbx.E_CAPACITY
+        k2, _ = e(oracle.synth_gray(3, 0, w, h))                      # the handle stays usable
+        assert len(k2) > 500
+    finally:
+        e.close()
+    e = orbx.ORBextractor(max_width=w, max_height=h, cand_divisor=1)
+    try:
+        kps, desc = e(g, cap=8192)
+        assert np.array_equal(kps.view(np.uint8), ref["kps"].view(np.uint8)) and np.array_equal(desc, ref["desc"])
+        for l in range(8):
+            assert len(e.candidates(l)) == len(ref["cands"][l])
+    finally:
+        e.close()
