@@ -410,11 +410,13 @@ def main():
         import c_oracle as co
         co.build()
         cores = os.cpu_count() or 1
-        S, REP = max(16, min(64, 2 * cores)), 8
+        S = max(16, min(64, 2 * cores))
         fr = np.stack([co.synth_gray(SEED, f, W, H) for f in range(S)])
         dp = np.stack([co.synth_depth(SEED, f, W, H) for f in range(S)])
         cpu_path.orc = co.COracle()
         cpu_path(fr[:4], dp[:4], cores)
+        dt1 = cpu_path(fr, dp, cores)[0]
+        REP = int(max(2, min(200, np.ceil(10.0 / max(dt1, 1e-3)))))          # a bounded sample of about 10 s of wall time on all cores
         dt = sum(cpu_path(fr, dp, cores)[0] for _ in range(REP))
         cpu_baseline = {"value": S * REP / dt, "unit": "frames/s", "cores": cores, "kind": "port",
                         "sample": "%d passes over %d frames of the same synthetic stream (%.1f s), extract+filterDepth+match, OpenMP over %d threads" % (REP, S, dt, cores)}
