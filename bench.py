@@ -271,11 +271,19 @@ def main():
                     "algorithmic_bytes_per_launch": ALG_BYTES[dom] * B / max(1.0, kernels[dom]["launches_per_step"]),
                     "dominant_overall": max(kernels, key=lambda n: kernels[n]["ms_per_step"])}
 
+    # matching is integer-issue-bound: 8 POPC per descriptor pair against the measured POPC issue peak (orbx_bench_popc)
+    match_roofline = None
+    if "k_match_partial" in kernels:
+        pairs = float((nkp[1:].astype(np.float64) * nkp[:-1]).sum() + float(nkp[0]) * float(nkp[-1]))      # frame f vs f-1; frame 0 vs the carried last frame
+        popc = ex.bench_popc()
+        t_s = kernels["k_match_partial"]["ms_per_step"] * 1e-3
+        match_roofline = {"kernel": "k_match_partial", "bound": "integer issue (POPC)", "pairs_per_step": pairs, "achieved": 8.0 * pairs / t_s,
+                          "peak": popc, "unit": "POPC/s", "frac": 8.0 * pairs / t_s / popc if popc > 0 else None, "peak_source": "measured (orbx_bench_popc)"}
     if args.kernels_only:
         clocks = sampler.stop()
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
-                              "ms_per_step": ms / K, "kernels": kernels, "roofline": roofline, "gpu_launches": int(gpu_launches), "clocks": clocks}))
+                              "ms_per_step": ms / K, "kernels": kernels, "roofline": roofline, "match_roofline": match_roofline, "gpu_launches": int(gpu_launches), "clocks": clocks}))
         return
     # ---- e2e: the host-buffer C-ABI calls, pinned host memory, H2D + D2H inside the timed region ----
     # The caller keeps two batches in flight (orbx_track_batch_submit / orbx_batch_wait): every step's frames are DMA'd from
@@ -430,7 +438,7 @@ def main():
                        "nfeatures": 1000, "nlevels": 8, "l2_policy": "inputs larger than L2 (%.0f MB per step per GPU)" % (B * W * H * 3 / 1e6),
                        "sharding": "frame-parallel, no data-path collective",
                        "schedule": "blur on a second stream beside FAST + quadtree; `kernels`/`roofline` timed in a second pass of the same K steps with every kernel on one stream (ORBX_OPT_SERIAL)"},
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "e2e": e2e, "latency": latency,
+            "roofline": roofline, "match_roofline": match_roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "e2e": e2e, "latency": latency,
             "association": assoc, "gpu_launches": int(gpu_launches), "clocks": clocks,
             "keypoints_per_frame": float(nkp.mean()), "matches_per_frame": float(nm.mean()),
         }
