@@ -16,7 +16,8 @@
 // Candidate values live in global scratch (ping-pong); node bookkeeping lives in shared memory.
 #include "orbx_internal.h"
 
-#define QT_THREADS 256
+// block size NT is a template parameter: 256 threads when the batch fills the machine with CTAs (one per frame x level), 1024
+// for small batches, where the kernel is a chain of dependent global-memory passes and wider blocks shorten every pass
 #define QT_NONE 0xFFFFu
 
 struct QtParams {
@@ -50,14 +51,14 @@ __device__ __forceinline__ QNodes carve_nodes(unsigned char *&p, int cap)
 }
 
 // block-wide exclusive scan of packed 3x16-bit counters held in s_val[0..n); returns total.
-// s_val is overwritten with the exclusive prefix.  Uses s_warp[QT_THREADS/32 + 1].
-__device__ unsigned long long block_scan_excl(unsigned long long *s_val, int n, unsigned long long *s_warp)
+// s_val is overwritten with the exclusive prefix.  Uses s_warp[NT/32 + 1].
+template <int NT> __device__ unsigned long long block_scan_excl(unsigned long long *s_val, int n, unsigned long long *s_warp)
 {
     __shared__ unsigned long long s_carry;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += QT_THREADS) {
+    for (int base = 0; base < n; base += NT) {
         const int i = base + threadIdx.x;
         unsigned long long v = i < n ? s_val[i] : 0ull, x = v;
 #pragma unroll
@@ -68,20 +69,20 @@ __device__ unsigned long long block_scan_excl(unsigned long long *s_val, int n, 
         if (lane == 31) s_warp[wid] = x;
         __syncthreads();
         if (wid == 0) {
-            unsigned long long wv = lane < QT_THREADS / 32 ? s_warp[lane] : 0ull, wx = wv;
+            unsigned long long wv = lane < NT / 32 ? s_warp[lane] : 0ull, wx = wv;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 unsigned long long y = __shfl_up_sync(0xffffffffu, wx, o);
                 if (lane >= o) wx += y;
             }
-            if (lane < QT_THREADS / 32) s_warp[lane] = wx - wv;
-            if (lane == QT_THREADS / 32 - 1) s_warp[QT_THREADS / 32] = wx;
+            if (lane < NT / 32) s_warp[lane] = wx - wv;
+            if (lane == NT / 32 - 1) s_warp[NT / 32] = wx;
         }
         __syncthreads();
         const unsigned long long carry = s_carry;
         if (i < n) s_val[i] = carry + s_warp[wid] + x - v;
         __syncthreads();
-        if (threadIdx.x == 0) s_carry = carry + s_warp[QT_THREADS / 32];
+        if (threadIdx.x == 0) s_carry = carry + s_warp[NT / 32];
         __syncthreads();
     }
     return s_carry;
@@ -202,10 +203,10 @@ __device__ void srt_sort(SrtE *a, int n)
     } else srt_insertion_sort(a, 0, n);
 }
 
-__global__ void __launch_bounds__(QT_THREADS) k_quadtree(QtParams P, const FrameGeom *__restrict__ G)
+template <int NT> __global__ void __launch_bounds__(NT) k_quadtree(QtParams P, const FrameGeom *__restrict__ G)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ unsigned long long s_warp[QT_THREADS / 32 + 1];
+    __shared__ unsigned long long s_warp[NT / 32 + 1];
     __shared__ int s_M, s_nleaf, s_seq0, s_size, s_nsplit, s_state;
 
     const int level = blockIdx.x;
@@ -241,9 +242,9 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(QtParams P, const Frame
     const float hX = g.hx;
 
     // ---- roots (ORBextractor.cpp:567-600).  Root i has creation number nini-1-i (push_back order). ----
-    for (int i = threadIdx.x; i < nini; i += QT_THREADS) s_c4[i] = 0;
+    for (int i = threadIdx.x; i < nini; i += NT) s_c4[i] = 0;
     __syncthreads();
-    for (int p = threadIdx.x; p < n; p += QT_THREADS) {
+    for (int p = threadIdx.x; p < n; p += NT) {
         const uint32_t c = A[p];
         int r = (int)((float)orbx_px(c) / hX);
         if (r >= nini) r = nini - 1;
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(QtParams P, const Frame
         s_M = M; s_nleaf = nl; s_seq0 = nini; s_size = M + nl; s_state = 0;
     }
     __syncthreads();
-    for (int p = threadIdx.x; p < n; p += QT_THREADS) {
+    for (int p = threadIdx.x; p < n; p += NT) {
         const uint32_t t = tmp[p];
         const int r = t & 255; const unsigned k = t >> 8;
         const unsigned np = (unsigned)s_scan[r] + k;
@@ -285,23 +286,23 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(QtParams P, const Frame
         if (state == 2 || ++guard > 64) break;
         // visit order: normal = reverse creation order (list order); sorted = descending (count, UL.x)
         if (state == 1) {
-            for (int k = threadIdx.x; k < M; k += QT_THREADS) s_srt[k] = srt_make(cur.cnt[k], cur.x0[k], k);
+            for (int k = threadIdx.x; k < M; k += NT) s_srt[k] = srt_make(cur.cnt[k], cur.x0[k], k);
             __syncthreads();
             if (threadIdx.x == 0) srt_sort(s_srt, M);
             __syncthreads();
-            for (int v = threadIdx.x; v < M; v += QT_THREADS) { const int k = srt_pay(s_srt[M - 1 - v]); s_vis[v] = (unsigned short)k; s_rank[k] = (unsigned short)v; }
+            for (int v = threadIdx.x; v < M; v += NT) { const int k = srt_pay(s_srt[M - 1 - v]); s_vis[v] = (unsigned short)k; s_rank[k] = (unsigned short)v; }
         } else {
-            for (int v = threadIdx.x; v < M; v += QT_THREADS) { const int k = M - 1 - v; s_vis[v] = (unsigned short)k; s_rank[k] = (unsigned short)v; }
+            for (int v = threadIdx.x; v < M; v += NT) { const int k = M - 1 - v; s_vis[v] = (unsigned short)k; s_rank[k] = (unsigned short)v; }
         }
         // split geometry (DivideNode :482-483) and zeroed quadrant counters
-        for (int k = threadIdx.x; k < M; k += QT_THREADS) {
+        for (int k = threadIdx.x; k < M; k += NT) {
             s_midx[k] = (short)(cur.x0[k] + (int)ceilf((float)(cur.x1[k] - cur.x0[k]) / 2));
             s_midy[k] = (short)(cur.y0[k] + (int)ceilf((float)(cur.y1[k] - cur.y0[k]) / 2));
             s_c4[4 * k] = s_c4[4 * k + 1] = s_c4[4 * k + 2] = s_c4[4 * k + 3] = 0;
         }
         __syncthreads();
         // quadrant of every live candidate (:515-529) and its rank inside the child
-        for (int p = threadIdx.x; p < n; p += QT_THREADS) {
+        for (int p = threadIdx.x; p < n; p += NT) {
             const unsigned k = oA[p];
             if (k == QT_NONE) continue;
             const uint32_t c = A[p];
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(QtParams P, const Frame
         }
         __syncthreads();
         // per visit rank: (#non-empty children, #expandable children, #singleton children)
-        for (int v = threadIdx.x; v < M; v += QT_THREADS) {
+        for (int v = threadIdx.x; v < M; v += NT) {
             const int k = s_vis[v];
             unsigned ne = 0, nm = 0, ns = 0;
 #pragma unroll
@@ -319,12 +320,12 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(QtParams P, const Frame
             s_scan[v] = (unsigned long long)ne | ((unsigned long long)nm << 16) | ((unsigned long long)ns << 32);
         }
         __syncthreads();
-        const unsigned long long tot = block_scan_excl(s_scan, M, s_warp);
+        const unsigned long long tot = block_scan_excl<NT>(s_scan, M, s_warp);
         // early stop of the sorted phase: first visit rank after which lNodes.size() >= N (:743-744)
         if (threadIdx.x == 0) s_nsplit = M;
         __syncthreads();
         if (state == 1) {
-            for (int v = threadIdx.x; v < M; v += QT_THREADS) {
+            for (int v = threadIdx.x; v < M; v += NT) {
                 const int k = s_vis[v];
                 unsigned ne = 0;
 #pragma unroll
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(QtParams P, const Frame
             return;
         }
         // create children (push_front n1..n4 :639-676) / keep unsplit nodes as final nodes
-        for (int v = threadIdx.x; v < M; v += QT_THREADS) {
+        for (int v = threadIdx.x; v < M; v += NT) {
             const int k = s_vis[v];
             if (v >= nsplit) {
                 const int j = nleaf0 + newLeaf + (v - nsplit);
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(QtParams P, const Frame
         }
         __syncthreads();
         // move candidates into their child's range
-        for (int p = threadIdx.x; p < n; p += QT_THREADS) {
+        for (int p = threadIdx.x; p < n; p += NT) {
             const unsigned k = oA[p];
             if (k == QT_NONE || s_rank[k] >= nsplit) { B[p] = A[p]; oB[p] = QT_NONE; continue; }
             const uint32_t t = tmp[p];
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(QtParams P, const Frame
     // remaining expandable nodes are final nodes too
     {
         const int M = s_M, nl = s_nleaf;
-        for (int k = threadIdx.x; k < M; k += QT_THREADS) { leaf.beg[nl + k] = cur.beg[k]; leaf.cnt[nl + k] = cur.cnt[k]; leaf.seq[nl + k] = cur.seq[k]; }
+        for (int k = threadIdx.x; k < M; k += NT) { leaf.beg[nl + k] = cur.beg[k]; leaf.cnt[nl + k] = cur.cnt[k]; leaf.seq[nl + k] = cur.seq[k]; }
         __syncthreads();
         if (threadIdx.x == 0) s_nleaf = nl + M;
         __syncthreads();
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(QtParams P, const Frame
     if (L > g.sel_cap) { if (threadIdx.x == 0) { atomicOr(P.status, ORBX_DS_NODE_OVERFLOW); P.nsel[slot] = 0; } return; }
     // ---- best candidate per node (:757-776), output in list order = descending creation number ----
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int i = wid; i < L; i += QT_THREADS / 32) {
+    for (int i = wid; i < L; i += NT / 32) {
         const unsigned b = leaf.beg[i], c = leaf.cnt[i];
         unsigned long long best = ~0ull;
         for (unsigned t = lane; t < c; t += 32) {
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(QtParams P, const Frame
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < L; i += QT_THREADS) {
+    for (int i = threadIdx.x; i < L; i += NT) {
         const unsigned sq = (unsigned)(s_scan[i] >> 32);
         int rank = 0;
         for (int j = 0; j < L; j++) rank += (unsigned)(s_scan[j] >> 32) > sq;
@@ -451,13 +452,16 @@ void launch_quadtree_geo(orbx_handle *h, const FrameGeom *d_geo, int nlevels, in
     P.sel = h->d_sel; P.sel_slab = sel_slab; P.nsel = h->d_nsel; P.status = h->d_status;
     P.node_cap = node_cap;
     const size_t smem = quadtree_smem(node_cap);
+    const bool wide = nlevels * nframes <= h->sm_count;                // at most one CTA per SM: latency-bound, use 1024-thread blocks
     if (smem > 48 * 1024 && smem > h->quad_smem) {
-        cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_quadtree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_quadtree<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         h->quad_smem = smem;
     }
     dim3 grid(nlevels, nframes);
     ProfScope ps(h, ORBX_K_QUADTREE);
-    k_quadtree<<<grid, QT_THREADS, smem, h->stream>>>(P, d_geo);
+    if (wide) k_quadtree<1024><<<grid, 1024, smem, h->stream>>>(P, d_geo);
+    else k_quadtree<256><<<grid, 256, smem, h->stream>>>(P, d_geo);
 }
 
 void launch_quadtree(orbx_handle *h, int nframes)
