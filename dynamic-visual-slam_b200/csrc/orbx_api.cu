@@ -373,8 +373,7 @@ static orbx_status run_pipeline(orbx_handle *h, int nframes, const uint8_t *l0, 
 {
     const int nl = h->geo.nlevels;
     ORBX_CUDA(h, cudaMemsetAsync(h->d_ncand, 0, (size_t)nframes * nl * sizeof(int32_t), h->stream));
-    for (int l = 1; l < nl; l++)                                                                 // ComputePyramid
-        if (launch_resize_level(h, l, nframes, l0, l0_step, l0_fstride) != 0) { h->err = "cuTensorMapEncodeTiled failed (frame base/step must be 16-byte aligned)"; return ORBX_E_CUDA; }
+    if (launch_pyramid(h, nframes, l0, l0_step, l0_fstride) != 0) { h->err = "cuTensorMapEncodeTiled failed (frame base/step must be 16-byte aligned)"; return ORBX_E_CUDA; }   // ComputePyramid
     // the blur needs only the pyramid, the quadtree only the FAST candidates: the (throughput-bound) blur runs on the aux
     // stream beside FAST and the (latency-bound, low-occupancy) quadtree
     cudaStream_t bst = h->opt_serial ? h->stream : h->aux_stream;

@@ -95,6 +95,7 @@ struct orbx_handle {
     CUtensorMap tmap_cell[ORBX_MAX_LEVELS];                  // box = 96 bytes x (hCell + 6) rows (FAST cell windows)
     uint32_t *d_cells; int cell_cap;                         // FAST cell descriptors (k_fast.cu)
     const uint8_t *tmap_l0; size_t tmap_l0_step, tmap_l0_fstride; int tmap_l0_frames;
+    int pyr_grid_cap;                                     // resident CTAs of the cooperative pyramid kernel (0 = not probed, -1 = unavailable)
     size_t blur_smem, quad_smem; bool rz_configured;      // per-handle (= per-device) dynamic shared memory opt-ins
     int fast_grid_cap; size_t fast_smem; int fast_tp;   // resident CTAs / dynamic smem / tile pitch of the persistent FAST kernel
     // arenas, sized for max_width x max_height x max_batch
@@ -159,6 +160,7 @@ struct orbx_db {
 #define ORBX_DS_KP_OVERFLOW   4
 
 // ---- kernel launchers (one per .cu) ----
+int  launch_pyramid(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
 int  launch_resize_level(orbx_handle *h, int level, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
 int  orbx_ensure_tmaps(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
 int  launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);   // -1: TMA descriptor encode failed
