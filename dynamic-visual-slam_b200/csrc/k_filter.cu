@@ -18,9 +18,9 @@ struct FilterParams {
     int32_t *status;
 };
 
-__global__ void __launch_bounds__(256) k_filter(FilterParams P)
+__global__ void __launch_bounds__(1024) k_filter(FilterParams P)
 {
-    __shared__ int s_warp[9];
+    __shared__ int s_warp[33];                              // one CTA per frame, any block size that is a multiple of 32
     __shared__ int s_base;
     const int f = blockIdx.x;
     const int n = P.nin[f];
@@ -31,7 +31,8 @@ __global__ void __launch_bounds__(256) k_filter(FilterParams P)
     uint8_t *dout = P.dout + (size_t)f * P.cap_out * ORBX_DESC_BYTES;
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += 256) {
+    const int nw = blockDim.x >> 5;
+    for (int base = 0; base < n; base += blockDim.x) {
         const int i = base + threadIdx.x;
         bool keep = false;
         orbx_keypoint kp;
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(256) k_filter(FilterParams P)
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) s_warp[wid] = __popc(bal);
         __syncthreads();
-        if (threadIdx.x == 0) { int run = 0; for (int w = 0; w < 8; w++) { const int c = s_warp[w]; s_warp[w] = run; run += c; } s_warp[8] = run; }
+        if (threadIdx.x == 0) { int run = 0; for (int w = 0; w < nw; w++) { const int c = s_warp[w]; s_warp[w] = run; run += c; } s_warp[32] = run; }
         __syncthreads();
         const int o = s_base + s_warp[wid] + __popc(bal & ((1u << lane) - 1u));
         if (keep) {
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(256) k_filter(FilterParams P)
             }
         }
         __syncthreads();
-        if (threadIdx.x == 0) s_base += s_warp[8];
+        if (threadIdx.x == 0) s_base += s_warp[32];
         __syncthreads();
     }
     if (threadIdx.x == 0) {
@@ -93,7 +94,7 @@ void launch_filter(orbx_handle *h, int nframes, const uint16_t *d_depth, size_t 
     P.boxes = d_boxes; P.nboxes = nboxes; P.drop_mask = drop_mask;
     P.kout = d_kps; P.dout = d_desc; P.nout = d_counts; P.cap_out = cap; P.status = h->d_status;
     ProfScope ps(h, ORBX_K_FILTER);
-    k_filter<<<nframes, 256, 0, h->stream>>>(P);
+    k_filter<<<nframes, 1024, 0, h->stream>>>(P);
 }
 
 // ---- keyframe packing: the landmark / observation loop of Frontend::publishKeyframe (reference frontend.cpp:731-776) ----
@@ -109,9 +110,9 @@ struct PackParams {
     int32_t *status;
 };
 
-__global__ void __launch_bounds__(256) k_pack_keyframe(PackParams P)
+__global__ void __launch_bounds__(1024) k_pack_keyframe(PackParams P)
 {
-    __shared__ int s_warp[9];
+    __shared__ int s_warp[33];
     __shared__ int s_base;
     const int f = blockIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -122,7 +123,8 @@ __global__ void __launch_bounds__(256) k_pack_keyframe(PackParams P)
     const uint8_t *dimg = reinterpret_cast<const uint8_t *>(P.depth) + (size_t)f * P.dfstride;
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += 256) {
+    const int nw = blockDim.x >> 5;
+    for (int base = 0; base < n; base += blockDim.x) {
         const int i = base + threadIdx.x;
         bool keep = false;
         float px = 0.f, py = 0.f, X = 0.f, Y = 0.f, Z = 0.f;
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(256) k_pack_keyframe(PackParams P)
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) s_warp[wid] = __popc(bal);
         __syncthreads();
-        if (threadIdx.x == 0) { int run = 0; for (int w = 0; w < 8; w++) { const int c = s_warp[w]; s_warp[w] = run; run += c; } s_warp[8] = run; }
+        if (threadIdx.x == 0) { int run = 0; for (int w = 0; w < nw; w++) { const int c = s_warp[w]; s_warp[w] = run; run += c; } s_warp[32] = run; }
         __syncthreads();
         if (keep) {
             const int o = s_base + s_warp[wid] + __popc(bal & ((1u << lane) - 1u));
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(256) k_pack_keyframe(PackParams P)
             } else atomicOr(P.status, ORBX_DS_KP_OVERFLOW);
         }
         __syncthreads();
-        if (threadIdx.x == 0) s_base += s_warp[8];
+        if (threadIdx.x == 0) s_base += s_warp[32];
         __syncthreads();
     }
     if (threadIdx.x == 0) P.nout[f] = min(s_base, P.cap_out);
@@ -173,5 +175,5 @@ void launch_pack_keyframe(orbx_handle *h, int nframes, const orbx_keypoint *d_kp
     P.depth = d_depth; P.dstep = dstep; P.dfstride = dfstride; P.dw = dw; P.dh = dh;
     P.K = *K; P.out = d_out; P.nout = d_nout; P.cap_out = cap_out; P.status = h->d_status;
     ProfScope ps(h, ORBX_K_OTHER);
-    k_pack_keyframe<<<nframes, 256, 0, h->stream>>>(P);
+    k_pack_keyframe<<<nframes, 1024, 0, h->stream>>>(P);
 }

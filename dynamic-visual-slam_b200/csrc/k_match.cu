@@ -97,9 +97,9 @@ __device__ __forceinline__ void top2_insert(unsigned long long &a, unsigned long
     b = b < hi ? b : hi;
 }
 
-__global__ void __launch_bounds__(256) k_match_epilogue(MatchEpiParams P)
+__global__ void __launch_bounds__(1024) k_match_epilogue(MatchEpiParams P)
 {
-    __shared__ int s_warp[9];
+    __shared__ int s_warp[33];                              // one CTA per problem, any block size that is a multiple of 32
     __shared__ int s_base;
     const int prob = blockIdx.x;
     const int qs = P.qsel ? P.qsel[prob] : prob, ts = P.tsel ? P.tsel[prob] : prob;
@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(256) k_match_epilogue(MatchEpiParams P)
     orbx_dmatch *out = P.out ? P.out + (size_t)prob * P.out_stride : nullptr;
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
-    for (int base = 0; base < nq; base += 256) {
+    const int nw = blockDim.x >> 5;
+    for (int base = 0; base < nq; base += blockDim.x) {
         const int qi = base + threadIdx.x;
         unsigned long long a = ~0ull, b = ~0ull;
         if (qi < nq && nt > 0) {
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(256) k_match_epilogue(MatchEpiParams P)
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) s_warp[wid] = __popc(bal);
         __syncthreads();
-        if (threadIdx.x == 0) { int run = 0; for (int w = 0; w < 8; w++) { const int c = s_warp[w]; s_warp[w] = run; run += c; } s_warp[8] = run; }
+        if (threadIdx.x == 0) { int run = 0; for (int w = 0; w < nw; w++) { const int c = s_warp[w]; s_warp[w] = run; run += c; } s_warp[32] = run; }
         __syncthreads();
         if (keep) {
             const int o = s_base + s_warp[wid] + __popc(bal & ((1u << lane) - 1u));
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(256) k_match_epilogue(MatchEpiParams P)
             out[o] = m;
         }
         __syncthreads();
-        if (threadIdx.x == 0) s_base += s_warp[8];
+        if (threadIdx.x == 0) s_base += s_warp[32];
         __syncthreads();
     }
     if (threadIdx.x == 0 && P.n_out) {
@@ -222,7 +223,7 @@ int launch_match_core(orbx_handle *h, const uint8_t *d_q, const int32_t *d_nq, i
     E.k = k; E.max_dist = max_dist; E.ratio_num = ratio_num;
     E.out = d_out; E.out_stride = out_stride; E.n_out = d_n_out; E.top2 = d_top2;
     ProfScope ps(h, ORBX_K_MATCH_EPI);
-    k_match_epilogue<<<nproblems, 256, 0, h->stream>>>(E);
+    k_match_epilogue<<<nproblems, 1024, 0, h->stream>>>(E);
     return 0;
 }
 
