@@ -203,11 +203,114 @@ __device__ void srt_sort(SrtE *a, int n)
     } else srt_insertion_sort(a, 0, n);
 }
 
+// ---- the same std::sort, block-parallel ----
+// libstdc++'s std::sort = __introsort_loop (median-of-3 pivot to the front, Hoare-style __unguarded_partition, recursion until a range
+// has <= 16 elements or the depth limit triggers heapsort) + __final_insertion_sort.  Two facts make it parallel WITHOUT changing where
+// it leaves equivalent elements:
+//   * a partition is determined by the ORIGINAL values of its range: the left scan stops at the positions whose element is not below the
+//     pivot (ascending), the right scan at those not above it (descending); the k-th stops of both sides are swapped while they have not
+//     crossed, and the cut is the first left stop after the last swap (or the last right stop if none lies before it).  So one warp does
+//     a whole partition with two ballot scans, a monotone count and independent swaps; disjoint ranges of one recursion depth go to
+//     different warps;
+//   * insertion sort is stable, so the final pass equals a stable sort of whatever the partitions left: a rank computation.
+// Checked against the single-thread restatement above (and through it against the real std::sort) on tie-heavy inputs.
+__device__ __forceinline__ void srt_median_to_first(SrtE *a, int first, int mid, int last)
+{
+    SrtE *r = a + first, *x = a + first + 1, *y = a + mid, *z = a + last - 1;
+    if (srt_less(*x, *y)) {
+        if (srt_less(*y, *z)) srt_swap(r, y);
+        else if (srt_less(*x, *z)) srt_swap(r, z);
+        else srt_swap(r, x);
+    } else if (srt_less(*x, *z)) srt_swap(r, x);
+    else if (srt_less(*y, *z)) srt_swap(r, z);
+    else srt_swap(r, y);
+}
+
+// __unguarded_partition(lo, hi, pivot) by one warp; Ls / Ra are scratch slices of at least hi - lo entries.  Returns the cut.
+__device__ int srt_warp_partition(SrtE *a, int lo, int hi, SrtE pivot, unsigned short *Ls, unsigned short *Ra)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    int nL = 0, nR = 0;
+    for (int base = lo; base < hi; base += 32) {
+        const int i = base + lane;
+        const bool in = i < hi;
+        const SrtE v = in ? a[i] : 0ull;
+        const bool fl = in && !srt_less(v, pivot), fr = in && !srt_less(pivot, v);
+        const unsigned bl = __ballot_sync(0xffffffffu, fl), br = __ballot_sync(0xffffffffu, fr);
+        if (fl) Ls[nL + __popc(bl & lt)] = (unsigned short)i;
+        if (fr) Ra[nR + __popc(br & lt)] = (unsigned short)i;          // ascending; the k-th right stop is Ra[nR - 1 - k]
+        nL += __popc(bl); nR += __popc(br);
+    }
+    __syncwarp();
+    const int nmin = min(nL, nR);
+    int K = 0;                                                           // number of swaps: stops cross monotonically
+    for (int base = 0; base < nmin; base += 32) {
+        const int k = base + lane;
+        const unsigned b = __ballot_sync(0xffffffffu, k < nmin && Ls[k] < Ra[nR - 1 - k]);
+        K += __popc(b);
+        if (b != 0xffffffffu) break;
+    }
+    int cut;
+    if (K < nL && (K == 0 || Ls[K] < Ra[nR - K])) cut = Ls[K]; else cut = Ra[nR - K];
+    for (int k = lane; k < K; k += 32) srt_swap(a + Ls[k], a + Ra[nR - 1 - k]);
+    __syncwarp();
+    return cut;
+}
+
+// all NT threads; a[0..n) in shared memory.  tmp: n elements; Ls, Ra: n entries each; lists: 4*cap words; cnt: 2 ints.
+template <int NT> __device__ void block_sort_exact(SrtE *a, int n, SrtE *tmp, unsigned short *Ls, unsigned short *Ra, unsigned *lists, int cap, int *cnt)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (n > 16) {
+        if (threadIdx.x == 0) {
+            int lg = 0;
+            while ((n >> (lg + 1)) > 0) lg++;
+            lists[0] = (unsigned)n << 16; lists[1] = (unsigned)(2 * lg); cnt[0] = 1; cnt[1] = 0;
+        }
+        __syncthreads();
+        unsigned *cur = lists, *nxt = lists + 2 * cap;
+        while (true) {
+            const int nr = cnt[0];
+            if (nr == 0) break;
+            for (int r = wid; r < nr; r += NT / 32) {
+                const int first = (int)(cur[2 * r] & 0xFFFFu), last = (int)(cur[2 * r] >> 16);
+                int depth = (int)cur[2 * r + 1];
+                if (depth == 0) { if (lane == 0) srt_heapsort(a + first, last - first); __syncwarp(); continue; }
+                depth--;
+                if (lane == 0) srt_median_to_first(a, first, first + (last - first) / 2, last);
+                __syncwarp();
+                const int cut = srt_warp_partition(a, first + 1, last, a[first], Ls + first, Ra + first);
+                if (lane == 0) {
+                    if (last - cut > 16) { const int sl = atomicAdd(&cnt[1], 1); nxt[2 * sl] = (unsigned)cut | ((unsigned)last << 16); nxt[2 * sl + 1] = (unsigned)depth; }
+                    if (cut - first > 16) { const int sl = atomicAdd(&cnt[1], 1); nxt[2 * sl] = (unsigned)first | ((unsigned)cut << 16); nxt[2 * sl + 1] = (unsigned)depth; }
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) { cnt[0] = cnt[1]; cnt[1] = 0; }
+            unsigned *t = cur; cur = nxt; nxt = t;
+            __syncthreads();
+        }
+    }
+    // __final_insertion_sort == stable sort of the current arrangement
+    for (int i = threadIdx.x; i < n; i += NT) {
+        const SrtE v = a[i];
+        const unsigned long long key = v >> 16;
+        int rank = 0;
+        for (int j = 0; j < n; j++) { const unsigned long long kj = a[j] >> 16; rank += (kj < key) || (kj == key && j < i); }
+        tmp[rank] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += NT) a[i] = tmp[i];
+    __syncthreads();
+}
+
 template <int NT> __global__ void __launch_bounds__(NT) k_quadtree(QtParams P, const FrameGeom *__restrict__ G)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ unsigned long long s_warp[NT / 32 + 1];
     __shared__ int s_M, s_nleaf, s_seq0, s_size, s_nsplit, s_state;
+    __shared__ int s_sortcnt[2];
 
     const int level = blockIdx.x;
     const int f = blockIdx.y;
@@ -288,8 +391,7 @@ template <int NT> __global__ void __launch_bounds__(NT) k_quadtree(QtParams P, c
         if (state == 1) {
             for (int k = threadIdx.x; k < M; k += NT) s_srt[k] = srt_make(cur.cnt[k], cur.x0[k], k);
             __syncthreads();
-            if (threadIdx.x == 0) srt_sort(s_srt, M);
-            __syncthreads();
+            block_sort_exact<NT>(s_srt, M, (SrtE *)s_scan, s_cown, s_cown + NC, s_c4, NC, s_sortcnt);
             for (int v = threadIdx.x; v < M; v += NT) { const int k = srt_pay(s_srt[M - 1 - v]); s_vis[v] = (unsigned short)k; s_rank[k] = (unsigned short)v; }
         } else {
             for (int v = threadIdx.x; v < M; v += NT) { const int k = M - 1 - v; s_vis[v] = (unsigned short)k; s_rank[k] = (unsigned short)v; }

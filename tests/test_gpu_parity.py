@@ -194,3 +194,51 @@ def test_corner_dense_image_capacity(built, oracle):
             assert len(e.candidates(l)) == len(ref["cands"][l])
     finally:
         e.close()
+
+
+def test_quadtree_alone_tie_heavy(ex, oracle):
+    """DistributeOctTree on its own (orbx_test_quadtree) against the oracle on candidate sets built to produce many comparator ties
+    (equal counts and equal UL.x), which is where the block-parallel restatement of std::sort must land exactly like libstdc++."""
+    rng = np.random.default_rng(77)
+    cases = [(3000, 1248, 688, 217), (1800, 1035, 568, 181), (900, 325, 209, 60), (5000, 1248, 688, 500), (400, 600, 300, 151), (2500, 857, 468, 1000)]
+    for n, W, H, N in cases:
+        for rep in range(3):
+            # points on a coarse lattice with jitter: many nodes end up with the same count
+            gx, gy = rng.integers(0, W // 8, n) * 8 + rng.integers(0, 2, n), rng.integers(0, H // 8, n) * 8 + rng.integers(0, 2, n)
+            pts = sorted(set(zip(np.minimum(gx, W - 1).tolist(), np.minimum(gy, H - 1).tolist())))
+            sc = rng.integers(7, 60, len(pts))
+            ncols = max(1, W // 35)
+            wcell, hcell = int(np.ceil(W / ncols)), int(np.ceil(H / max(1, H // 35)))
+            # the reference feeds the tree in cell-row-major, then raster order: reproduce that order for the oracle
+            order = sorted(range(len(pts)), key=lambda i: ((pts[i][1] - 3) // hcell if pts[i][1] >= 3 else 0, (pts[i][0] - 3) // wcell if pts[i][0] >= 3 else 0, pts[i][1], pts[i][0]))
+            c = np.zeros(len(pts), oracle.CAND_DTYPE)
+            c["x"], c["y"], c["score"] = [pts[i][0] for i in order], [pts[i][1] for i in order], [int(sc[i]) for i in order]
+            want = oracle.distribute_octtree(c, 16, 16 + W, 16, 16 + H, N)
+            xys = np.stack([c["x"], c["y"], c["score"]], 1).astype(np.int32)
+            got = ex.test_quadtree(xys[rng.permutation(len(xys))], W, H, wcell, hcell, ncols, N)      # device input order is arbitrary
+            assert got.tolist() == np.stack([want["x"], want["y"], want["score"]], 1).tolist(), (n, W, H, N, rep)
+
+
+def test_large_batch_uses_narrow_quadtree_blocks(built, oracle):
+    """More than one (frame, level) CTA per SM switches the quadtree to 256-thread blocks: same results."""
+    import torch
+    import orbx
+    w, h, nb, CAP = 320, 240, 24, 1024
+    frames = np.stack([oracle.synth_gray(40, f, w, h) for f in range(nb)])
+    ex2 = orbx.ORBextractor(max_width=w, max_height=h, max_batch=nb, max_keypoints=CAP)
+    try:
+        dev = torch.device("cuda", 0)
+        g = torch.from_numpy(frames).to(dev)
+        kps = torch.zeros((nb, CAP, 28), dtype=torch.uint8, device=dev)
+        desc = torch.zeros((nb, CAP, 32), dtype=torch.uint8, device=dev)
+        cnt = torch.zeros(nb, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        ex2.extract_batch_device(g.data_ptr(), nb, w, h, w, w * h, kps.data_ptr(), desc.data_ptr(), CAP, cnt.data_ptr())
+        ex2.sync()
+        kk, dd, cc = kps.cpu().numpy().view(orbx.KP_DTYPE).reshape(nb, CAP), desc.cpu().numpy(), cnt.cpu().numpy()
+        orc = oracle.COracle()
+        for f in (0, 7, 23):
+            ref = orc.extract(frames[f])
+            assert cc[f] == len(ref["kps"]) and np.array_equal(kk[f, :cc[f]].view(np.uint8), ref["kps"].view(np.uint8)) and np.array_equal(dd[f, :cc[f]], ref["desc"])
+    finally:
+        ex2.close()
