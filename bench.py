@@ -56,6 +56,27 @@ def ncu_traffic(kernel, frames, launches_per_step):
         return None, None
 
 
+def bind_to_gpu_numa(local_rank):
+    """Multi-rank runs: pin this process to the CPUs nvidia-smi reports as local to its GPU, so that the pinned staging buffers are
+    first-touched on that NUMA node and the H2D/D2H DMA does not cross sockets.  Best effort; returns the CPU list or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        for line in out.splitlines():
+            cols = line.split()
+            if cols and cols[0] == "GPU%d" % local_rank:
+                for c in cols[1:]:
+                    if c[0].isdigit() and ("-" in c or "," in c) and not c.startswith("NV"):
+                        cpus = set()
+                        for part in c.split(","):
+                            a, _, b = part.partition("-")
+                            cpus.update(range(int(a), int(b or a) + 1))
+                        os.sched_setaffinity(0, cpus)
+                        return c
+    except Exception:
+        pass
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -184,6 +205,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the ORB path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -436,7 +458,7 @@ def main():
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "width": W, "height": H,
                        "nfeatures": 1000, "nlevels": 8, "l2_policy": "inputs larger than L2 (%.0f MB per step per GPU)" % (B * W * H * 3 / 1e6),
-                       "sharding": "frame-parallel, no data-path collective",
+                       "sharding": "frame-parallel, no data-path collective", "cpu_affinity": numa,
                        "schedule": "blur on a second stream beside FAST + quadtree; `kernels`/`roofline` timed in a second pass of the same K steps with every kernel on one stream (ORBX_OPT_SERIAL)"},
             "roofline": roofline, "match_roofline": match_roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "e2e": e2e, "latency": latency,
             "association": assoc, "gpu_launches": int(gpu_launches), "clocks": clocks,
