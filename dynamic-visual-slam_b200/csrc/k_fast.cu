@@ -99,7 +99,7 @@ __device__ __forceinline__ FastRow fast_row(const uint32_t *q)
     return w;
 }
 
-// Pre-test of R <= 7 detection rows x 4 pixels.  q = the item's word in tile row r0 (= ring row dy = -3 of the first
+// Pre-test of R <= 8 detection rows x 4 pixels (8 flag bits per pixel column).  q = the item's word in tile row r0 (= ring row dy = -3 of the first
 // detection row).  Result: bit (7-k) of byte j set iff pixel (row r0 + k, byte j) may be a corner at threshold T.
 template <int TP> __device__ __noinline__ uint32_t fast_sweep7(const uint32_t *q, uint32_t HM, uint32_t KK, int R)
 {
@@ -108,8 +108,8 @@ template <int TP> __device__ __noinline__ uint32_t fast_sweep7(const uint32_t *q
     for (int k = 0; k < 6; k++) w[k] = fast_row(q + k * (TP / 4));
     uint32_t fl = 0u;
 #pragma unroll
-    for (int k = 0; k < 7; k++) {
-        if (k >= R) break;                                                       // units of R <= 7 rows (uniform)
+    for (int k = 0; k < 8; k++) {
+        if (k >= R) break;                                                       // units of R <= 8 rows (uniform); the window indices are mod 7
         w[(k + 6) % 7] = fast_row(q + (k + 6) * (TP / 4));                       // ring row dy = +3 of detection row k
         const uint32_t C0 = w[(k + 3) % 7].C;
         const uint32_t p08 = __vabsdiffu4(w[(k + 6) % 7].C, C0) | __vabsdiffu4(w[k % 7].C, C0);
@@ -195,11 +195,11 @@ template <int TP> __global__ void __launch_bounds__(32) k_fast_cells(const __gri
 
         const int w0 = (ax + 3) >> 2;                                  // tile word holding detection column 0
         const int nG = ((ax + 3 + dw - 1) >> 2) - w0 + 1;              // words holding detection columns (<= 19)
-        // rows per sweep unit: the R in 4..7 that minimises (warp iterations) x (cost of a unit = 6 window rows + R tested rows)
-        int R = 7, nseg = (dh + 6) / 7;
+        // rows per sweep unit: the R in 4..8 that minimises (warp iterations) x (cost of a unit = 6 window rows + R tested rows)
+        int R = 8, nseg = (dh + 7) / 8;
         {
-            int best = ((nG * nseg + 31) >> 5) * (42 + 30 * 7);
-            for (int r = 6; r >= 4; r--) {
+            int best = ((nG * nseg + 31) >> 5) * (42 + 30 * 8);
+            for (int r = 7; r >= 4; r--) {
                 const int ns = (dh + r - 1) / r, cost = ((nG * ns + 31) >> 5) * (42 + 30 * r);
                 if (cost < best) { best = cost; R = r; nseg = ns; }
             }
@@ -226,7 +226,7 @@ template <int TP> __global__ void __launch_bounds__(32) k_fast_cells(const __gri
                     const int cb = 4 * (w0 + gidx) - (ax + 3);                // detection column of byte 0
                     uint32_t cm = 0u;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) if (cb + j >= 0 && cb + j < dw) cm |= 0xFEu << (8 * j);
+                    for (int j = 0; j < 4; j++) if (cb + j >= 0 && cb + j < dw) cm |= 0xFFu << (8 * j);
                     const int nv = min(R, dh - R * seg);
                     word = raw & cm & (((0xFF00u >> nv) & 0xFFu) * 0x01010101u);
                     base_off = (R * seg + 3) * TP + 4 * (w0 + gidx);
