@@ -186,6 +186,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="orbx", choices=["orbx", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="frames resident per step and per GPU")
+    ap.add_argument("--fast-ctas", type=int, default=0, help="resident FAST warps per SM in the overlapped schedule (0 = library default)")
     ap.add_argument("--host-chunk", type=int, default=0, help="frames per pipeline chunk of the host-buffer call (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-assoc", action="store_true", help="skip the landmark-association leg")
@@ -213,6 +214,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     B, K, CAP = args.batch, args.steps, 1280
     ex = orbx.ORBextractor(max_width=W, max_height=H, max_batch=B, device=local_rank, max_keypoints=CAP, host_chunk=args.host_chunk)
+    if args.fast_ctas:
+        ex.set_fast_ctas(args.fast_ctas)
     L, hnd = ex.L, ex.handle
     stream = torch.cuda.ExternalStream(ex.stream, device=dev)
 

@@ -116,19 +116,21 @@ __global__ void __launch_bounds__(BL_THREADS) k_blur7(const __grid_constant__ Le
     }
 }
 
-int launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride, cudaStream_t st)
+// tiles [tile_first, tile_first + ntiles) of the level-ordered tile table (ntiles < 0: to the end)
+int launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride, cudaStream_t st, int tile_first, int ntiles)
 {
-    if (h->geo.total_blur_tiles <= 0) return 0;
+    if (ntiles < 0) ntiles = h->geo.total_blur_tiles - tile_first;
+    if (ntiles <= 0) return 0;
     if (orbx_ensure_tmaps(h, nframes, l0, l0_step, l0_fstride) != 0) return -1;
     LevelMaps M;
     memcpy(M.m, h->tmap, sizeof(M.m));
     BlurParams P;
     P.blur = h->d_blur; P.blur_slab = h->blur_slab;
-    P.tiles = h->d_blur_tiles;
+    P.tiles = h->d_blur_tiles + tile_first;
     P.tile_rows = h->geo.max_hcell + 6;
     const size_t smem = 128 + (size_t)(P.tile_rows + BL_PADROWS) * ORBX_TMA_BOX_BYTES;
     if (smem > h->blur_smem) { cudaFuncSetAttribute(k_blur7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); h->blur_smem = smem; }
-    dim3 grid(h->geo.total_blur_tiles, nframes);
+    dim3 grid(ntiles, nframes);
     ProfScope ps(h, ORBX_K_BLUR, st);
     k_blur7<<<grid, BL_THREADS, smem, st>>>(M, P, h->d_geo);
     return 0;

@@ -35,19 +35,25 @@
 #include "orbx_tma.h"
 #include <algorithm>
 #include <cstring>
+#include <vector>
 
 // tile pitch TP = TMA box width, a template parameter: 80 bytes when every cell ROI (15 alignment + wCell + 6 + 4) fits, else 96
 // (wCell <= 69).  A 7-row sweep unit may start on the last detection row: the rows it reads past the tile fall into the score map
 // that follows the tile in shared memory (their flags are masked).
+#ifndef FS_WQ
 #define FS_WQ 512                // survivor queue (u16 tile offsets); a sweep step with more survivors than this is scored in place
+#endif
 
 struct FastParams {
     uint32_t *cand; size_t cand_slab;
     int32_t *ncand;
-    const uint32_t *cells;       // level:4 | cell row:14 | cell column:14
+    const uint4 *cells;          // two 16-byte words per cell (orbx_build_fast_cells)
     int ncells, nitems;          // items = ncells x frames
+    float inv_ncells;
     int ini_th, min_th;
+    int nlevels;
     int32_t *status;
+    int32_t *work;               // dynamic work counter (zeroed with the corner counts)
     int tile_rows;               // max (hCell + 6) over the levels
     int map_pitch;               // score-map pitch: >= max cell width + 2, multiple of 16
 };
@@ -101,6 +107,10 @@ __device__ __forceinline__ FastRow fast_row(const uint32_t *q)
 
 // Pre-test of R <= 8 detection rows x 4 pixels (8 flag bits per pixel column).  q = the item's word in tile row r0 (= ring row dy = -3 of the first
 // detection row).  Result: bit (7-k) of byte j set iff pixel (row r0 + k, byte j) may be a corner at threshold T.
+#ifndef FAST_PAIRS
+#define FAST_PAIRS 4
+#endif
+#if FAST_PAIRS == 4
 template <int TP> __device__ __noinline__ uint32_t fast_sweep7(const uint32_t *q, uint32_t HM, uint32_t KK, int R)
 {
     FastRow w[7];
@@ -125,6 +135,33 @@ template <int TP> __device__ __noinline__ uint32_t fast_sweep7(const uint32_t *q
     }
     return fl;
 }
+#else
+// two-pair variant: only the compass pairs (0,8) and (4,12) — half the sweep arithmetic for ~15 % more survivors
+template <int TP> __device__ __noinline__ uint32_t fast_sweep7(const uint32_t *q, uint32_t HM, uint32_t KK, int R)
+{
+    uint32_t wc[7], wp[7], wm[7];                                                // C, columns x+3.., columns x-3.. of the window rows
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const uint32_t *r = q + k * (TP / 4);
+        wc[k] = r[0];
+        if (k >= 3) { wp[k] = __byte_perm(wc[k], r[1], 0x6543); wm[k] = __byte_perm(r[-1], wc[k], 0x4321); }
+    }
+    uint32_t fl = 0u;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (k >= R) break;
+        const uint32_t *r = q + (k + 6) * (TP / 4);
+        wc[(k + 6) % 7] = r[0];
+        if (k + 6 < R + 3) { wp[(k + 6) % 7] = __byte_perm(r[0], r[1], 0x6543); wm[(k + 6) % 7] = __byte_perm(r[-1], r[0], 0x4321); }
+        const uint32_t C0 = wc[(k + 3) % 7];
+        const uint32_t t0 = (__vabsdiffu4(wc[(k + 6) % 7], C0) | __vabsdiffu4(wc[k % 7], C0)) & HM;
+        const uint32_t t1 = (__vabsdiffu4(wp[(k + 3) % 7], C0) | __vabsdiffu4(wm[(k + 3) % 7], C0)) & HM;
+        const uint32_t acc = (t0 | (t0 + KK)) & (t1 | (t1 + KK));
+        fl |= (acc >> k) & (0x80808080u >> k);
+    }
+    return fl;
+}
+#endif
 
 // loose pre-test threshold T = 2^sh - 1 <= th:  |d| > T  <=>  (|d| & HM) != 0;  t + KK sets bit 7 of every byte with t >= 2^sh
 __device__ __forceinline__ void fast_masks(int th, uint32_t &HM, uint32_t &KK)
@@ -134,28 +171,55 @@ __device__ __forceinline__ void fast_masks(int th, uint32_t &HM, uint32_t &KK)
     KK = (0x80u - (1u << sh)) * 0x01010101u;
 }
 
-// geometry of one work item, derived from its cell descriptor
-struct FastItem { int f, level, ci, cj, wcell, hcell, iniX, iniY, ax, dw, dh; };
-__device__ __forceinline__ FastItem fast_item(const FastParams &P, const FrameGeom *__restrict__ G, int item)
+// the (frame-independent) description of one cell, built on the host with the geometry (orbx_build_fast_cells): two 16-byte loads
+// replace ~250 instructions of per-cell address arithmetic
+//   c0.x = tile word column (TMA coordinate 0) | first tile row << 16      c0.y = level | ax << 8 | dw << 16 | dh << 24
+//   c0.z = R | nseg << 8 | nG << 16 | w0 << 24                             c0.w = kx | ky << 16
+//   c1.x = 1 / nG (float bits)   c1.y = offset of the level's corner list   c1.z = its capacity   c1.w = bytes the TMA box delivers
+struct FastCellRegs { uint4 c0, c1; };
+// item -> (frame, cell): float estimate + exact fix-up (no integer division on the per-cell path)
+__device__ __forceinline__ void fast_split(const FastParams &P, int item, int &f, int &c)
 {
-    FastItem t;
-    t.f = item / P.ncells;
-    const uint32_t cd = __ldg(P.cells + (item - t.f * P.ncells));
-    t.level = (int)(cd & 15u); t.ci = (int)((cd >> 4) & 0x3FFFu); t.cj = (int)(cd >> 18);
-    const LevelGeom &g = G->lv[t.level];
-    t.wcell = g.wcell; t.hcell = g.hcell;
-    // cell ROI in image coordinates — ORBextractor.cpp:805-822
-    t.iniX = ORBX_BORDER + t.cj * t.wcell; t.iniY = ORBX_BORDER + t.ci * t.hcell;
-    const int maxX = min(t.iniX + t.wcell + 6, g.w - ORBX_BORDER), maxY = min(t.iniY + t.hcell + 6, g.h - ORBX_BORDER);
-    t.dw = maxX - t.iniX - 6; t.dh = maxY - t.iniY - 6;      // detection area, ROI-relative origin (3,3)
-    t.ax = t.iniX & 15;                                      // tile byte of ROI column 0 (TMA boxes start on 16-byte columns)
-    return t;
+    f = __float2int_rz(((float)item + 0.5f) * P.inv_ncells);
+    c = item - f * P.ncells;
+    if (c < 0) { f--; c += P.ncells; }
+    else if (c >= P.ncells) { f++; c -= P.ncells; }
+}
+
+// the warp's result list -> the (frame, level) corner list at the slot range a counter atomic reserved
+#ifndef FS_RES
+#define FS_RES 64
+#endif
+__device__ __forceinline__ void fast_write_out(const uint32_t *res, int n, int base, uint32_t *gdst, int cap, int32_t *status, int lane)
+{
+    for (int i = lane; i < n; i += 32) {
+        if (base + i < cap) gdst[base + i] = res[i];
+        else atomicOr(status, ORBX_DS_CAND_OVERFLOW);
+    }
+}
+// synchronous variant (a cell with more results than the list holds)
+__device__ __noinline__ void fast_publish(const uint32_t *res, int n, int32_t *gcnt, uint32_t *gdst, int cap, int32_t *status, int lane)
+{
+    __syncwarp();
+    int base = 0;
+    if (lane == 0) base = atomicAdd(gcnt, n);
+    fast_write_out(res, n, __shfl_sync(0xffffffffu, base, 0), gdst, cap, status, lane);
+    __syncwarp();
+}
+
+template <int TP> __device__ __forceinline__ void fast_score_to_map(const uint8_t *s_img, uint8_t *s_sc, int SP, int off, int ax, int th)
+{
+    const int s = fast_score_packed<TP>(s_img + off);
+    const int tr = off / TP, tc = off - tr * TP - ax;                  // ROI coordinates = detection coordinates + 3
+    s_sc[(tr - 2) * SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
 }
 
 template <int TP> __global__ void __launch_bounds__(32) k_fast_cells(const __grid_constant__ LevelMaps M, FastParams P, const FrameGeom *__restrict__ G)
 {
     extern __shared__ __align__(128) uint8_t s_raw[];
     __shared__ __align__(8) uint64_t s_full;
+    __shared__ int s_q[2];                                // survivor queue: fill, first slot that did not fit
+    __shared__ uint32_t s_res[2 * FS_RES];                // result lists of the current and the previous cell
     uint8_t *s_dyn = s_raw + ((128u - (smem_u32(s_raw) & 127u)) & 127u);
     // layout: [128-byte pad | tile | score map | queue]: the word left of tile column 0 (read, never used) falls into the pad
     uint8_t *s_img = s_dyn + 128;                                                        // tile_rows x TP, 128-byte aligned (TMA destination)
@@ -164,8 +228,8 @@ template <int TP> __global__ void __launch_bounds__(32) k_fast_cells(const __gri
     const int SP = P.map_pitch;
     const int map_bytes = (((P.tile_rows - 4) * SP) + 127) & ~127;
     uint16_t *wq = reinterpret_cast<uint16_t *>(s_sc + map_bytes);
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(s_img);
     const int lane = threadIdx.x;
-    const int nl = G->nlevels;
 
     if (lane == 0) {
         mbar_init(&s_full, 1);
@@ -174,143 +238,175 @@ template <int TP> __global__ void __launch_bounds__(32) k_fast_cells(const __gri
     }
     __syncwarp();
 
-    int it_n = 0;
-    for (int item = blockIdx.x; item < P.nitems; item += gridDim.x, it_n++) {
-        const FastItem T = fast_item(P, G, item);
-        const LevelGeom &g = G->lv[T.level];
-        const int ax = T.ax, dw = T.dw, dh = T.dh;
-        if (lane == 0) {
-            // every lane finished reading the previous tile (the __syncwarp that ends the loop body)
-            mbar_expect_tx(&s_full, (uint32_t)((T.hcell + 6) * TP));
-            tma_load_3d(s_img, &M.m[T.level], (T.iniX & ~15) >> 2, T.iniY, T.f, &s_full);
-            if (item + (int)gridDim.x < P.nitems) {                                     // next cell's window -> L2
-                const FastItem N = fast_item(P, G, item + gridDim.x);
-                tma_prefetch_3d(&M.m[N.level], (N.iniX & ~15) >> 2, N.iniY, N.f);
-            }
+    // Work distribution: cell cost varies by an order of magnitude (empty cells are swept twice, textured ones score hundreds of
+    // survivors), so after its first cell a warp draws the next ones from a global counter.  Software pipeline over the warp's
+    // cells: the draw for the cell after next flies during the sweep, the next window is prefetched into L2 at the top and
+    // loaded by TMA as soon as the tile is free, and a finished cell's results are written to the corner list one cell later,
+    // when the counter atomic that reserved their slots has long returned.
+    if ((int)blockIdx.x >= P.nitems) return;
+    int it_n = 0, nres = 0, buf = 0;
+    int pn = 0, pbase = 0, pcap = 0;                                  // the previous cell's list: length, reserved base (lane 0), list capacity
+    uint32_t *pdst = nullptr;
+    int f, ci, nf = 0, nc = 0;                                        // (frame, cell) of the current and of the next item
+    fast_split(P, blockIdx.x, f, ci);
+    FastCellRegs C;
+    C.c0 = __ldg(P.cells + 2 * ci); C.c1 = __ldg(P.cells + 2 * ci + 1);
+    int nxt = 0;
+    if (lane == 0) {
+        mbar_expect_tx(&s_full, C.c1.w);
+        tma_load_3d(s_img, &M.m[C.c0.y & 15u], (int)(C.c0.x & 0xFFFFu), (int)(C.c0.x >> 16), f, &s_full);
+        nxt = atomicAdd(P.work, 1) + (int)gridDim.x;
+    }
+    nxt = __shfl_sync(0xffffffffu, nxt, 0);
+    fast_split(P, nxt, nf, nc);
+    for (;; it_n++) {
+        const bool has_next = nxt < P.nitems;
+        int drawn = 0;
+        if (has_next && lane == 0) {
+            drawn = atomicAdd(P.work, 1) + (int)gridDim.x;                              // consumed at the bottom of the loop
+            const uint4 n0 = __ldg(P.cells + 2 * nc);                                   // (read again below: L1-resident, and no registers stay live)
+            tma_prefetch_3d(&M.m[n0.y & 15u], (int)(n0.x & 0xFFFFu), (int)(n0.x >> 16), nf);
         }
+        const int level = (int)(C.c0.y & 15u), ax = (int)((C.c0.y >> 8) & 0xFFu), dw = (int)((C.c0.y >> 16) & 0xFFu), dh = (int)(C.c0.y >> 24);
+        const int R = (int)(C.c0.z & 0xFFu), nseg = (int)((C.c0.z >> 8) & 0xFFu), nG = (int)((C.c0.z >> 16) & 0xFFu), w0 = (int)(C.c0.z >> 24);
+        const float inv = __uint_as_float(C.c1.x);
+        uint32_t *res = s_res + buf * FS_RES;
+        uint32_t *gdst = P.cand + (size_t)f * P.cand_slab + C.c1.y;
+        int32_t *gcnt = &P.ncand[f * P.nlevels + level];
         // zero the score map (1-px ring included) while the tile lands
         for (int i = lane; i < ((dh + 2) * SP) / 16; i += 32) reinterpret_cast<uint4 *>(s_sc)[i] = make_uint4(0, 0, 0, 0);
         mbar_wait(&s_full, (uint32_t)(it_n & 1));
         __syncwarp();
 
-        const int w0 = (ax + 3) >> 2;                                  // tile word holding detection column 0
-        const int nG = ((ax + 3 + dw - 1) >> 2) - w0 + 1;              // words holding detection columns (<= 19)
-        // rows per sweep unit: the R in 4..8 that minimises (warp iterations) x (cost of a unit = 6 window rows + R tested rows)
-        int R = 8, nseg = (dh + 7) / 8;
-        {
-            int best = ((nG * nseg + 31) >> 5) * (42 + 30 * 8);
-            for (int r = 7; r >= 4; r--) {
-                const int ns = (dh + r - 1) / r, cost = ((nG * ns + 31) >> 5) * (42 + 30 * r);
-                if (cost < best) { best = cost; R = r; nseg = ns; }
-            }
-        }
         const int units = nG * nseg;
-        const float inv = 1.0f / (float)nG;
-        const uint32_t *words = reinterpret_cast<const uint32_t *>(s_img);
-        uint32_t *gdst = P.cand + (size_t)T.f * P.cand_slab + g.cand_off;
-        int32_t *gcnt = &P.ncand[T.f * nl + T.level];
         for (int pass = 0; pass < 2; pass++) {
             const int th = pass == 0 ? P.ini_th : P.min_th;
             uint32_t HM, KK;
             fast_masks(th, HM, KK);
-            int qn = 0;
-            bool ovf = false;
-            // ---- packed sweep + compaction into the warp's queue ----
+            if (lane == 0) { s_q[0] = 0; s_q[1] = 0x7fffffff; }
+            __syncwarp();
+            // ---- packed sweep; survivors take queue slots with one shared-memory atomic per lane ----
             for (int u0 = 0; u0 < units; u0 += 32) {
                 const int u = u0 + lane;
-                uint32_t word = 0u;
-                int base_off = 0;
                 if (u < units) {
-                    const int seg = __float2int_rd(((float)u + 0.5f) * inv), gidx = u - seg * nG;
-                    const uint32_t raw = fast_sweep7<TP>(words + (R * seg) * (TP / 4) + w0 + gidx, HM, KK, R);
-                    const int cb = 4 * (w0 + gidx) - (ax + 3);                // detection column of byte 0
-                    uint32_t cm = 0u;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) if (cb + j >= 0 && cb + j < dw) cm |= 0xFFu << (8 * j);
-                    const int nv = min(R, dh - R * seg);
-                    word = raw & cm & (((0xFF00u >> nv) & 0xFFu) * 0x01010101u);
-                    base_off = (R * seg + 3) * TP + 4 * (w0 + gidx);
-                }
-                const int cnt = __popc(word);
-                int incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                if (qn + total > FS_WQ) {                                     // queue full: score what is queued, NMS will scan the cell
-                    __syncwarp();
-                    for (int i = lane; i < qn; i += 32) {
-                        const int off = wq[i];
-                        const int s = fast_score_packed<TP>(s_img + off);
-                        const int tr = off / TP, tc = off - tr * TP - ax;
-                        s_sc[(tr - 2) * SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
-                    }
-                    __syncwarp();
-                    qn = 0; ovf = true;
-                    if (total > FS_WQ) {                                      // this step alone does not fit: score its survivors in place
-                        while (word) {
-                            const int bit = __ffs((int)word) - 1;
-                            word &= word - 1;
-                            const int off = base_off + (7 - (bit & 7)) * TP + (bit >> 3);
-                            const int s = fast_score_packed<TP>(s_img + off);
-                            const int tr = off / TP, tc = off - tr * TP - ax;
-                            s_sc[(tr - 2) * SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
+                    const int seg = __float2int_rd(((float)u + 0.5f) * inv), wcol = w0 + u - seg * nG, row0 = R * seg;
+                    const uint32_t raw = fast_sweep7<TP>(words + row0 * (TP / 4) + wcol, HM, KK, R);
+                    const int cb = 4 * wcol - (ax + 3);                       // detection column of byte 0 (-3 .. dw-1)
+                    const uint32_t cm = (0xFFFFFFFFu << (8 * max(0, -cb))) & (0xFFFFFFFFu >> (32 - 8 * min(4, dw - cb)));
+                    const int nv = min(R, dh - row0);
+                    uint32_t word = raw & cm & (((0xFF00u >> nv) & 0xFFu) * 0x01010101u);
+                    if (word) {
+                        const int cnt = __popc(word), base_off = (row0 + 3) * TP + 4 * wcol;
+                        int slot = atomicAdd(&s_q[0], cnt);
+                        if (slot + cnt <= FS_WQ) {
+                            do {
+                                const int bit = __ffs((int)word) - 1;
+                                word &= word - 1;
+                                wq[slot++] = (uint16_t)(base_off + (7 - (bit & 7)) * TP + (bit >> 3));
+                            } while (word);
+                        } else {                                              // queue full: score in place, NMS will scan the whole cell
+                            atomicMin(&s_q[1], slot);
+                            do {
+                                const int bit = __ffs((int)word) - 1;
+                                word &= word - 1;
+                                fast_score_to_map<TP>(s_img, s_sc, SP, base_off + (7 - (bit & 7)) * TP + (bit >> 3), ax, th);
+                            } while (word);
                         }
-                        continue;
                     }
                 }
-                int slot = qn + incl - cnt;
-                while (word) {
-                    const int bit = __ffs((int)word) - 1;
-                    word &= word - 1;
-                    wq[slot++] = (uint16_t)(base_off + (7 - (bit & 7)) * TP + (bit >> 3));
-                }
-                qn += total;
             }
             __syncwarp();
-            // ---- exact score of the queued survivors (ROI coords = detection coords + 3) ----
-            for (int i = lane; i < qn; i += 32) {
-                const int off = wq[i];
-                const int s = fast_score_packed<TP>(s_img + off);
-                const int tr = off / TP, tc = off - tr * TP - ax;
-                s_sc[(tr - 2) * SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
-            }
+            const bool ovf = s_q[1] <= FS_WQ;
+            const int qn = ovf ? s_q[1] : s_q[0];
+            // ---- exact score of the queued survivors ----
+            for (int i = lane; i < qn; i += 32) fast_score_to_map<TP>(s_img, s_sc, SP, wq[i], ax, th);
             __syncwarp();
             // ---- strict 3x3 NMS inside the cell: queue entries, or every pixel of the cell if the queue overflowed ----
             const int nitems = ovf ? dw * dh : qn;
-            const float invw = 1.0f / (float)dw;
+            const float invw = ovf ? 1.0f / (float)dw : 0.0f;
             int found = 0;
             for (int i0 = 0; i0 < nitems; i0 += 32) {
                 const int i = i0 + lane;
-                bool ok = false;
-                int r = 0, c = 0, s = 0;
-                if (i < nitems) {
+                const bool act = i < nitems;
+                int r = 0, c = 0;
+                if (act) {
                     if (ovf) { r = __float2int_rd(((float)i + 0.5f) * invw); c = i - r * dw; }
                     else { const int off = wq[i]; const int tr = off / TP; r = tr - 3; c = off - tr * TP - ax - 3; }
-                    const uint8_t *q = &s_sc[(r + 1) * SP + (c + 1)];
-                    s = q[0];
-                    // the zero ring around the map stands for "outside the cell's detection area"
-                    if (s != 0) ok = s > q[-SP] && s > q[SP] && s > q[-1] && s > q[-SP - 1] && s > q[SP - 1] && s > q[1] && s > q[-SP + 1] && s > q[SP + 1];
                 }
+                // all nine loads in flight at once; the zero ring around the map stands for "outside the cell's detection area"
+                const uint8_t *q = &s_sc[(r + 1) * SP + (c + 1)];
+                const int s = q[0];
+                const int n0 = q[-SP - 1], n1 = q[-SP], n2 = q[-SP + 1], n3 = q[-1], n4 = q[1], n5 = q[SP - 1], n6 = q[SP], n7 = q[SP + 1];
+                const int m = max(max(max(n0, n1), max(n2, n3)), max(max(n4, n5), max(n6, n7)));
+                const bool ok = act && s > m;                             // strict: s > m >= 0, so s != 0
                 const unsigned bal = __ballot_sync(0xffffffffu, ok);
                 if (bal) {
                     const int nk = __popc(bal);
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(gcnt, nk);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (ok) {
-                        // box-relative coordinates: kp.pt + (j*wCell, i*hCell) — ORBextractor.cpp:865-866
-                        const int go = base + __popc(bal & ((1u << lane) - 1u));
-                        if (go < g.cand_cap) gdst[go] = orbx_pack(T.cj * T.wcell + c + 3, T.ci * T.hcell + r + 3, s);
-                        else atomicOr(P.status, ORBX_DS_CAND_OVERFLOW);
-                    }
+                    if (nres + nk > FS_RES) { fast_publish(res, nres, gcnt, gdst, (int)C.c1.z, P.status, lane); nres = 0; }
+                    // box-relative coordinates: kp.pt + (j*wCell, i*hCell) — ORBextractor.cpp:865-866
+                    if (ok) res[nres + __popc(bal & ((1u << lane) - 1u))] = orbx_pack((int)(C.c0.w & 0xFFFFu) + c, (int)(C.c0.w >> 16) + r, s);
+                    nres += nk;
                     found += nk;
                 }
             }
+            __syncwarp();
             // the reference retries a cell at minThFAST iff iniThFAST produced nothing (:843-846)
             if (found > 0 || pass == 1) break;
-            __syncwarp();
         }
-        __syncwarp();                                                   // every lane is done with the tile, the map and the queue
+        // every lane is done with the tile, the map and the queue
+        if (has_next && lane == 0) {
+            const uint4 n0 = __ldg(P.cells + 2 * nc), n1 = __ldg(P.cells + 2 * nc + 1);
+            mbar_expect_tx(&s_full, n1.w);
+            tma_load_3d(s_img, &M.m[n0.y & 15u], (int)(n0.x & 0xFFFFu), (int)(n0.x >> 16), nf, &s_full);
+        }
+        // write out the previous cell's list (its counter atomic was issued one cell ago), then open this cell's
+        if (pn) fast_write_out(s_res + (buf ^ 1) * FS_RES, pn, __shfl_sync(0xffffffffu, pbase, 0), pdst, pcap, P.status, lane);
+        pn = nres;
+        if (nres) {
+            if (lane == 0) pbase = atomicAdd(gcnt, nres);
+            pdst = gdst; pcap = (int)C.c1.z; buf ^= 1; nres = 0;
+        }
+        if (!has_next) break;
+        f = nf; ci = nc;
+        C.c0 = __ldg(P.cells + 2 * ci); C.c1 = __ldg(P.cells + 2 * ci + 1);
+        nxt = __shfl_sync(0xffffffffu, drawn, 0);
+        fast_split(P, nxt, nf, nc);
+    }
+    if (pn) fast_write_out(s_res + (buf ^ 1) * FS_RES, pn, __shfl_sync(0xffffffffu, pbase, 0), pdst, pcap, P.status, lane);
+}
+
+// ---- host: the cell records ----
+static int fast_tile_pitch(const FrameGeom &G);
+void orbx_build_fast_cells(const FrameGeom &G, const std::vector<uint32_t> &ctab, std::vector<uint4> &out)
+{
+    const int TP = fast_tile_pitch(G);
+    out.resize(2 * ctab.size());
+    for (size_t i = 0; i < ctab.size(); i++) {
+        const uint32_t cd = ctab[i];
+        const int level = (int)(cd & 15u), ci = (int)((cd >> 4) & 0x3FFFu), cj = (int)(cd >> 18);
+        const LevelGeom &g = G.lv[level];
+        // cell ROI in image coordinates — ORBextractor.cpp:805-822
+        const int iniX = ORBX_BORDER + cj * g.wcell, iniY = ORBX_BORDER + ci * g.hcell;
+        const int maxX = std::min(iniX + g.wcell + 6, g.w - ORBX_BORDER), maxY = std::min(iniY + g.hcell + 6, g.h - ORBX_BORDER);
+        const int dw = maxX - iniX - 6, dh = maxY - iniY - 6;      // detection area, ROI-relative origin (3,3)
+        const int ax = iniX & 15;                                  // tile byte of ROI column 0 (TMA boxes start on 16-byte columns)
+        const int w0 = (ax + 3) >> 2;                              // tile word holding detection column 0
+        const int nG = ((ax + 3 + dw - 1) >> 2) - w0 + 1;          // words holding detection columns (<= 19)
+        // rows per sweep unit: the R in 4..8 that minimises (warp iterations) x (cost of a unit = 6 window rows + R tested rows)
+        int R = 8, nseg = (dh + 7) / 8, best = ((nG * nseg + 31) >> 5) * (42 + 30 * 8);
+        for (int r = 7; r >= 4; r--) {
+            const int ns = (dh + r - 1) / r, cost = ((nG * ns + 31) >> 5) * (42 + 30 * r);
+            if (cost < best) { best = cost; R = r; nseg = ns; }
+        }
+        const float inv = 1.0f / (float)nG;
+        uint32_t invb; memcpy(&invb, &inv, 4);
+        uint4 c0, c1;
+        c0.x = (uint32_t)((iniX & ~15) >> 2) | ((uint32_t)iniY << 16);
+        c0.y = (uint32_t)level | ((uint32_t)ax << 8) | ((uint32_t)dw << 16) | ((uint32_t)dh << 24);
+        c0.z = (uint32_t)R | ((uint32_t)nseg << 8) | ((uint32_t)nG << 16) | ((uint32_t)w0 << 24);
+        c0.w = (uint32_t)(cj * g.wcell + 3) | ((uint32_t)(ci * g.hcell + 3) << 16);
+        c1.x = invb; c1.y = (uint32_t)g.cand_off; c1.z = (uint32_t)g.cand_cap; c1.w = (uint32_t)((g.hcell + 6) * TP);
+        out[2 * i] = c0; out[2 * i + 1] = c1;
     }
 }
 
@@ -378,9 +474,10 @@ int launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, 
     FastParams P;
     P.cand = h->d_cand; P.cand_slab = G.cand_entries;
     P.ncand = h->d_ncand;
-    P.cells = h->d_cells; P.ncells = G.total_cells_valid; P.nitems = G.total_cells_valid * nframes;
+    P.cells = reinterpret_cast<const uint4 *>(h->d_cells); P.nlevels = G.nlevels; P.ncells = G.total_cells_valid; P.nitems = G.total_cells_valid * nframes; P.inv_ncells = 1.0f / (float)G.total_cells_valid;
     P.ini_th = h->prm.ini_th_fast; P.min_th = h->prm.min_th_fast;
     P.status = h->d_status;
+    P.work = h->d_ncand + (size_t)h->prm.max_batch * ORBX_MAX_LEVELS;
     P.tile_rows = G.max_hcell + 6;
     P.map_pitch = (G.max_wcell + 2 + 15) & ~15;
     const int TP = fast_tile_pitch(G);
@@ -393,7 +490,8 @@ int launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, 
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem);
         h->fast_grid_cap = std::max(1, occ) * h->sm_count; h->fast_smem = smem; h->fast_tp = TP;
     }
-    const int grid = std::min(P.nitems, h->fast_grid_cap);
+    int grid = std::min(P.nitems, h->fast_grid_cap);
+    if (!h->opt_serial && h->opt_fast_ctas > 0) grid = std::min(grid, h->opt_fast_ctas * h->sm_count);
     ProfScope ps(h, ORBX_K_FAST);
     kern<<<grid, 32, smem, h->stream>>>(M, P, h->d_geo);
     return 0;

@@ -191,7 +191,11 @@ static orbx_status set_geometry(orbx_handle *h, int w, int hgt)
     if (!xt.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_xtab, xt.data(), xt.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
     if (!yt.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_ytab, yt.data(), yt.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
     if (!strips.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_strips, strips.data(), strips.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    if (!ctab.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_cells, ctab.data(), ctab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (!ctab.empty()) {
+        std::vector<uint4> recs;
+        orbx_build_fast_cells(G, ctab, recs);
+        ORBX_CUDA(h, cudaMemcpy(h->d_cells, recs.data(), recs.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    }
     if (!btiles.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_blur_tiles, btiles.data(), btiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     G.total_strips = (int)strips.size();
     h->geo = G; h->pyr_slab = G.pyr_bytes; h->blur_slab = G.blur_bytes; h->tmap_valid = false;
@@ -217,6 +221,7 @@ extern "C" void orbx_destroy(orbx_handle *h)
     if (h->out_stream) cudaStreamDestroy(h->out_stream);
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_fork0) cudaEventDestroy(h->ev_fork0);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (int i = 0; i < 2; i++) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]); if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]); }
     delete h;
@@ -245,11 +250,14 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     cudaDeviceProp prop;
     CREATE_CUDA(cudaGetDeviceProperties(&prop, p.device));
     h->sm_count = prop.multiProcessorCount;
-    CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);          // (least, greatest): the dependent chain outranks the filler stream
+    CREATE_CUDA(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));
     CREATE_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CREATE_CUDA(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
-    CREATE_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, prio_lo));
     CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_fork0, cudaEventDisableTiming));
     CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) {
         CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
@@ -281,7 +289,7 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     h->strip_cap = G.total_cells + 64 * p.nlevels;
     CREATE_CUDA(cudaMalloc(&h->d_strips, sizeof(uint32_t) * h->strip_cap));
     h->cell_cap = G.total_cells + G.total_cells / 4 + 64 * p.nlevels;
-    CREATE_CUDA(cudaMalloc(&h->d_cells, sizeof(uint32_t) * h->cell_cap));
+    CREATE_CUDA(cudaMalloc(&h->d_cells, 2 * sizeof(uint4) * h->cell_cap));
     h->blur_tile_cap = G.total_blur_tiles + G.total_blur_tiles / 4 + 64 * p.nlevels;
     CREATE_CUDA(cudaMalloc(&h->d_blur_tiles, sizeof(uint32_t) * h->blur_tile_cap));
     CREATE_CUDA(cudaMalloc(&h->d_xtab, sizeof(ResizeTab) * h->tab_cap));
@@ -295,7 +303,7 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     CREATE_CUDA(cudaMalloc(&h->d_qtmp, h->cand_cap * sizeof(uint32_t)));
     CREATE_CUDA(cudaMalloc(&h->d_owner, h->cand_cap * sizeof(uint16_t)));
     CREATE_CUDA(cudaMalloc(&h->d_owner2, h->cand_cap * sizeof(uint16_t)));
-    CREATE_CUDA(cudaMalloc(&h->d_ncand, B * ORBX_MAX_LEVELS * sizeof(int32_t)));
+    CREATE_CUDA(cudaMalloc(&h->d_ncand, (B * ORBX_MAX_LEVELS + 4) * sizeof(int32_t)));   // + the FAST work counter
     CREATE_CUDA(cudaMalloc(&h->d_nsel, B * ORBX_MAX_LEVELS * sizeof(int32_t)));
     CREATE_CUDA(cudaMalloc(&h->d_sel, h->sel_cap * sizeof(uint32_t)));
     CREATE_CUDA(cudaMalloc(&h->d_kps_all, B * h->max_kp * sizeof(orbx_keypoint)));
@@ -346,6 +354,7 @@ extern "C" orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t v
 {
     if (!h) return ORBX_E_INVALID;
     if (option == ORBX_OPT_SERIAL) { h->opt_serial = value ? 1 : 0; return ORBX_OK; }
+    if (option == ORBX_OPT_FAST_CTAS) { h->opt_fast_ctas = value > 0 ? value : 0; return ORBX_OK; }
     h->err = "unknown option"; return ORBX_E_INVALID;
 }
 extern "C" void *orbx_stream(orbx_handle *h) { return h ? (void *)h->stream : nullptr; }
@@ -372,17 +381,26 @@ static orbx_status run_pipeline(orbx_handle *h, int nframes, const uint8_t *l0, 
                                 orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts)
 {
     const int nl = h->geo.nlevels;
-    ORBX_CUDA(h, cudaMemsetAsync(h->d_ncand, 0, (size_t)nframes * nl * sizeof(int32_t), h->stream));
-    if (launch_pyramid(h, nframes, l0, l0_step, l0_fstride) != 0) { h->err = "cuTensorMapEncodeTiled failed (frame base/step must be 16-byte aligned)"; return ORBX_E_CUDA; }   // ComputePyramid
-    // the blur needs only the pyramid, the quadtree only the FAST candidates: the (throughput-bound) blur runs on the aux
-    // stream beside FAST and the (latency-bound, low-occupancy) quadtree
+    ORBX_CUDA(h, cudaMemsetAsync(h->d_ncand, 0, ((size_t)h->prm.max_batch * ORBX_MAX_LEVELS + 4) * sizeof(int32_t), h->stream));   // corner counts + FAST work counter
+    // Schedule.  The main stream carries the dependent chain pyramid -> FAST -> quadtree -> describe; the blur (needed only by
+    // describe) runs on the low-priority aux stream as filler: level 0 depends on the input alone and starts beside the
+    // pyramid's seven shrinking launches, the other levels start once the pyramid exists and fill what FAST and the
+    // (latency-bound, low-occupancy) quadtree leave free.
+    const int l0_tiles = h->geo.lv[0].blur_tx * h->geo.lv[0].blur_ty;
     cudaStream_t bst = h->opt_serial ? h->stream : h->aux_stream;
+    if (!h->opt_serial) {
+        ORBX_CUDA(h, cudaEventRecord(h->ev_fork0, h->stream));
+        ORBX_CUDA(h, cudaStreamWaitEvent(h->aux_stream, h->ev_fork0, 0));
+        if (launch_blur(h, nframes, l0, l0_step, l0_fstride, bst, 0, l0_tiles) != 0) { h->err = "cuTensorMapEncodeTiled failed (frame base/step must be 16-byte aligned)"; return ORBX_E_CUDA; }
+    }
+    if (launch_pyramid(h, nframes, l0, l0_step, l0_fstride) != 0) { h->err = "cuTensorMapEncodeTiled failed (frame base/step must be 16-byte aligned)"; return ORBX_E_CUDA; }   // ComputePyramid
     if (!h->opt_serial) {
         ORBX_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
         ORBX_CUDA(h, cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
     }
     if (launch_fast(h, nframes, l0, l0_step, l0_fstride) != 0) { h->err = "cuTensorMapEncodeTiled failed (frame base/step must be 16-byte aligned)"; return ORBX_E_CUDA; }   // cell FAST
-    if (launch_blur(h, nframes, l0, l0_step, l0_fstride, bst) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return ORBX_E_CUDA; }   // GaussianBlur per level
+    if (h->opt_serial) { if (launch_blur(h, nframes, l0, l0_step, l0_fstride, bst) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return ORBX_E_CUDA; } }   // GaussianBlur per level
+    else if (launch_blur(h, nframes, l0, l0_step, l0_fstride, bst, l0_tiles, -1) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return ORBX_E_CUDA; }
     if (!h->opt_serial) ORBX_CUDA(h, cudaEventRecord(h->ev_join, h->aux_stream));
     launch_quadtree(h, nframes);                                                                 // DistributeOctTree
     if (!h->opt_serial) ORBX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));

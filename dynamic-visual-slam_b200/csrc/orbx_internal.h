@@ -69,8 +69,9 @@ struct orbx_handle {
     orbx_params prm;
     int device;
     cudaStream_t stream, copy_stream, out_stream, aux_stream;   // aux: blur runs beside FAST + quadtree
-    cudaEvent_t ev_fork, ev_join;
+    cudaEvent_t ev_fork, ev_fork0, ev_join;
     int opt_serial;
+    int opt_fast_ctas;           // FAST warps per SM in the overlapped schedule (0 = as many as fit)
     cudaEvent_t ev_a, ev_b;
     cudaEvent_t ev_in[2], ev_comp[2], ev_out[2];   // host-batch pipeline: input slot filled / kernels done / outputs copied
     int chunk;                                      // frames per pipeline chunk of the synchronous host-buffer batch calls
@@ -93,7 +94,7 @@ struct orbx_handle {
     CUtensorMap tmap[ORBX_MAX_LEVELS]; bool tmap_valid;      // box rows = hCell + 6 (FAST strips, blur tiles)
     CUtensorMap tmap_rz[ORBX_MAX_LEVELS];                    // box rows = ORBX_RZ_BOX_ROWS (resize source windows)
     CUtensorMap tmap_cell[ORBX_MAX_LEVELS];                  // box = 96 bytes x (hCell + 6) rows (FAST cell windows)
-    uint32_t *d_cells; int cell_cap;                         // FAST cell descriptors (k_fast.cu)
+    void *d_cells; int cell_cap;                             // FAST cell records, 32 bytes each (k_fast.cu: orbx_build_fast_cells)
     const uint8_t *tmap_l0; size_t tmap_l0_step, tmap_l0_fstride; int tmap_l0_frames;
     int pyr_grid_cap;                                     // resident CTAs of the cooperative pyramid kernel (0 = not probed, -1 = unavailable)
     size_t blur_smem, quad_smem; bool rz_configured;      // per-handle (= per-device) dynamic shared memory opt-ins
@@ -162,11 +163,12 @@ struct orbx_db {
 // ---- kernel launchers (one per .cu) ----
 int  launch_pyramid(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
 int  launch_resize_level(orbx_handle *h, int level, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
+void orbx_build_fast_cells(const FrameGeom &G, const std::vector<uint32_t> &ctab, std::vector<uint4> &out);   // k_fast.cu: 32-byte FAST cell records
 int  orbx_ensure_tmaps(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
 int  launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);   // -1: TMA descriptor encode failed
 void launch_quadtree(orbx_handle *h, int nframes);
 void launch_quadtree_geo(orbx_handle *h, const FrameGeom *d_geo, int nlevels, int nframes, int node_cap, size_t cand_slab, int sel_slab);
-int  launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride, cudaStream_t st);
+int  launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride, cudaStream_t st, int tile_first = 0, int ntiles = -1);
 void launch_describe_to(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride,
                         orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts);
 void upload_umax(const int *umax);

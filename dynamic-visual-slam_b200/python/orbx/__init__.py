@@ -224,6 +224,10 @@ class ORBextractor:
         """ORBX_OPT_SERIAL: one stream, kernels in order (isolated per-kernel timings) instead of the overlapped schedule."""
         self._check(self.L.orbx_set_option(self._h, 1, 1 if on else 0))
 
+    def set_fast_ctas(self, n):
+        """ORBX_OPT_FAST_CTAS: resident FAST warps per SM in the overlapped schedule (0 = as many as fit)."""
+        self._check(self.L.orbx_set_option(self._h, 2, int(n)))
+
     @property
     def stream(self):
         return self.L.orbx_stream(self._h)

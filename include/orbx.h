@@ -271,8 +271,11 @@ orbx_status orbx_synth_descriptors_device(orbx_handle *h, uint32_t seed, uint64_
 
 /* ---- options ----
  * ORBX_OPT_SERIAL: 1 = launch every kernel of a step on the handle's one stream, in order (per-kernel event timings are
- * then isolated, as the roofline accounting wants); 0 (default) = the blur runs on a second stream beside FAST + quadtree. */
+ * then isolated, as the roofline accounting wants); 0 (default) = the blur runs on a second stream beside FAST + quadtree.
+ * ORBX_OPT_FAST_CTAS: resident FAST warps per SM in the overlapped schedule (0 = default); fewer leave room for the blur
+ * running beside FAST. */
 #define ORBX_OPT_SERIAL 1
+#define ORBX_OPT_FAST_CTAS 2
 orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t value);
 
 /* ---- utilities ---- */
