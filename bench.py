@@ -56,6 +56,18 @@ def ncu_traffic(kernel, frames, launches_per_step):
         return None, None
 
 
+def ncu_warp_inst(kernel, frames):
+    """Executed warp instructions per step of `kernel` (all its launches) from the newest committed ncu capture, scaled to this
+    run's batch; None when the capture does not hold it."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    try:
+        t = json.load(open(files[-1])).get(kernel) if files else None
+        return t["warp_inst_per_frame_per_step"] * frames if t and t.get("warp_inst_per_frame_per_step") else None
+    except Exception:
+        return None
+
+
 def bind_to_gpu_numa(local_rank):
     """Multi-rank runs: pin this process to the CPUs nvidia-smi reports as local to its GPU, so that the pinned staging buffers are
     first-touched on that NUMA node and the H2D/D2H DMA does not cross sockets.  Best effort; returns the CPU list or None."""
@@ -296,6 +308,18 @@ def main():
                     "algorithmic_bytes_per_launch": ALG_BYTES[dom] * B / max(1.0, kernels[dom]["launches_per_step"]),
                     "dominant_overall": max(kernels, key=lambda n: kernels[n]["ms_per_step"])}
 
+    # The dense stages are exact 8/16-bit integer pipelines and turn out ISSUE-bound, not HBM-bound: executed warp instructions
+    # (committed ncu capture, scaled per frame) over the live kernel time, against 4 schedulers x SMs x the SM clock sampled below.
+    def issue_view(clk_mhz, sms):
+        out = {}
+        for name in dense:
+            wi = ncu_warp_inst(name, B)
+            if wi and clk_mhz:
+                peak = 4.0 * sms * clk_mhz * 1e6
+                ach = wi / (kernels[name]["ms_per_step"] * 1e-3)
+                out[name] = {"warp_inst_per_step": wi, "achieved_ginst_s": ach / 1e9, "peak_ginst_s": peak / 1e9, "frac": ach / peak}
+        return out or None
+
     # matching is integer-issue-bound: 8 POPC per descriptor pair against the measured POPC issue peak (orbx_bench_popc)
     match_roofline = None
     if "k_match_partial" in kernels:
@@ -308,7 +332,9 @@ def main():
         clocks = sampler.stop()
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
-                              "ms_per_step": ms / K, "kernels": kernels, "roofline": roofline, "match_roofline": match_roofline, "gpu_launches": int(gpu_launches), "clocks": clocks}))
+                              "ms_per_step": ms / K, "kernels": kernels, "roofline": roofline, "match_roofline": match_roofline,
+                              "issue": issue_view((clocks or {}).get("sm_mhz"), torch.cuda.get_device_properties(dev).multi_processor_count),
+                              "gpu_launches": int(gpu_launches), "clocks": clocks}))
         return
     # ---- e2e: the host-buffer C-ABI calls, pinned host memory, H2D + D2H inside the timed region ----
     # The caller keeps two batches in flight (orbx_track_batch_submit / orbx_batch_wait): every step's frames are DMA'd from
@@ -462,8 +488,9 @@ def main():
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "width": W, "height": H,
                        "nfeatures": 1000, "nlevels": 8, "l2_policy": "inputs larger than L2 (%.0f MB per step per GPU)" % (B * W * H * 3 / 1e6),
                        "sharding": "frame-parallel, no data-path collective", "cpu_affinity": numa,
-                       "schedule": "blur on a second stream beside FAST + quadtree; `kernels`/`roofline` timed in a second pass of the same K steps with every kernel on one stream (ORBX_OPT_SERIAL)"},
-            "roofline": roofline, "match_roofline": match_roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "e2e": e2e, "latency": latency,
+                       "schedule": "pyramid -> FAST -> quadtree -> describe on the main stream, blur on a low-priority second stream (level 0 beside the pyramid, the rest beside FAST + quadtree); `kernels`/`roofline` timed in a second pass of the same K steps with every kernel on one stream (ORBX_OPT_SERIAL)"},
+            "roofline": roofline, "match_roofline": match_roofline,
+            "issue": issue_view((clocks or {}).get("sm_mhz"), torch.cuda.get_device_properties(dev).multi_processor_count), "kernels": kernels, "cpu_baseline": cpu_baseline, "e2e": e2e, "latency": latency,
             "association": assoc, "gpu_launches": int(gpu_launches), "clocks": clocks,
             "keypoints_per_frame": float(nkp.mean()), "matches_per_frame": float(nm.mean()),
         }

@@ -52,10 +52,13 @@ traffic = {}
 for r in rr[2:]:
     name = kname(r[idx["Kernel Name"]])
     b = sum(float(r[idx[m]]) * scale.get(units[idx[m]], 1.0) for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-    t = traffic.setdefault(name, {"launches": 0, "dram_bytes": 0.0})
+    t = traffic.setdefault(name, {"launches": 0, "dram_bytes": 0.0, "warp_inst": 0.0})
     t["launches"] += 1; t["dram_bytes"] += b
+    if "smsp__inst_executed.sum" in idx:
+        t["warp_inst"] += float(r[idx["smsp__inst_executed.sum"]])
 for name, t in traffic.items():
     t["dram_bytes_per_frame_per_step"] = t["dram_bytes"] / FRAMES      # summed over the launches of one step
+    t["warp_inst_per_frame_per_step"] = t["warp_inst"] / FRAMES        # executed warp instructions (bench.py: issue-rate view)
     t["capture_frames"] = FRAMES
 json.dump(traffic, open(os.path.join(root, tag + "_traffic.json"), "w"), indent=1)
 with open(os.path.join(root, tag + "_summary.md"), "w") as f:
