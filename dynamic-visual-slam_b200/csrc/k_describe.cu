@@ -133,19 +133,34 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescParams P, cons
     if (level == 0) { img = P.l0 + (size_t)f * P.l0_fstride; step = P.l0_step; }
     else { img = P.pyr + (size_t)f * P.pyr_slab + g.off; step = (size_t)g.pitch; }
 
+    const uint8_t *bctr = P.blur + (size_t)f * P.blur_slab + g.boff + (size_t)cy * g.bpitch + cx;
+    const int bstep = g.bpitch;
+    // the rotated pattern stays inside the 37 x 37 window around the keypoint (EDGE_THRESHOLD = 19): pull its sectors towards L2
+    // now, the angle that decides which of its pixels are read is still ~1 us away
+    for (int r = lane; r < 37; r += 32) {
+        const uint8_t *row = bctr + (r - 18) * bstep;
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(row - 18));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(row));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(row + 18));
+    }
+
     // ---- IC_Angle: lane = column u+15, loop rows v ----
     int m10 = 0, m01 = 0;
     if (lane < 31) {
         const int u = lane - ORBX_HALF_PATCH;
         const int au = u < 0 ? -u : u;
         const uint8_t *ctr = img + (size_t)cy * step + cx + u;
+        // all 31 row loads are issued before the first use (the stage is load-latency-bound: 4 in flight measured 81 % long-scoreboard stalls)
+        int px[2 * ORBX_HALF_PATCH + 1];
+#pragma unroll
         for (int v = -ORBX_HALF_PATCH; v <= ORBX_HALF_PATCH; v++) {
             const int av = v < 0 ? -v : v;
-            if (au <= c_umax[av]) {
-                const int val = __ldg(ctr + (ptrdiff_t)v * (ptrdiff_t)step);
-                m10 += u * val; m01 += v * val;
-            }
+            px[v + ORBX_HALF_PATCH] = au <= c_umax[av] ? (int)__ldg(ctr + (ptrdiff_t)v * (ptrdiff_t)step) : 0;
         }
+        int colsum = 0;
+#pragma unroll
+        for (int v = -ORBX_HALF_PATCH; v <= ORBX_HALF_PATCH; v++) { colsum += px[v + ORBX_HALF_PATCH]; m01 += v * px[v + ORBX_HALF_PATCH]; }
+        m10 = u * colsum;
     }
     m10 = __reduce_add_sync(0xffffffffu, m10);
     m01 = __reduce_add_sync(0xffffffffu, m01);
@@ -155,8 +170,6 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescParams P, cons
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
     const float ang = __fmul_rn(angle, factorPI);
     const float a = glibc_cosf(ang), b = glibc_sinf(ang);
-    const uint8_t *bctr = P.blur + (size_t)f * P.blur_slab + g.boff + (size_t)cy * g.bpitch + cx;
-    const int bstep = g.bpitch;
     signed char pat[32];
     {
         const int4 *pp = reinterpret_cast<const int4 *>(c_pattern + lane * 32);
