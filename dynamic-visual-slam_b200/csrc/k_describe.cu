@@ -135,14 +135,6 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescParams P, cons
 
     const uint8_t *bctr = P.blur + (size_t)f * P.blur_slab + g.boff + (size_t)cy * g.bpitch + cx;
     const int bstep = g.bpitch;
-    // the rotated pattern stays inside the 37 x 37 window around the keypoint (EDGE_THRESHOLD = 19): pull its sectors towards L2
-    // now, the angle that decides which of its pixels are read is still ~1 us away
-    for (int r = lane; r < 37; r += 32) {
-        const uint8_t *row = bctr + (r - 18) * bstep;
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(row - 18));
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(row));
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(row + 18));
-    }
 
     // ---- IC_Angle: lane = column u+15, loop rows v ----
     int m10 = 0, m01 = 0;
