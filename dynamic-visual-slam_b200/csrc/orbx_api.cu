@@ -339,6 +339,7 @@ static orbx_status check_device_status(orbx_handle *h)
     const int s = h->h_status[0];
     if (s == 0) return ORBX_OK;
     ORBX_CUDA(h, cudaMemsetAsync(h->d_status, 0, sizeof(int32_t), h->stream));
+    if (s & ORBX_DS_BAD_INDEX) { h->err = "a match query index lies outside the keypoint array"; return ORBX_E_INVALID; }
     h->err = std::string("device capacity exceeded:") + ((s & ORBX_DS_CAND_OVERFLOW) ? " candidate list (lower cand_divisor)" : "") +
              ((s & ORBX_DS_NODE_OVERFLOW) ? " quadtree nodes" : "") + ((s & ORBX_DS_KP_OVERFLOW) ? " keypoint output (raise cap / max_keypoints)" : "");
     return ORBX_E_CAPACITY;
@@ -1135,6 +1136,66 @@ extern "C" orbx_status orbx_pack_keyframe(orbx_handle *h, const orbx_keypoint *k
     *n_out = m;
     if (m > cap) { h->err = "keyframe record capacity too small"; return ORBX_E_CAPACITY; }
     if (m > 0) ORBX_CUDA(h, cudaMemcpy(out, d_rec, (size_t)m * sizeof(orbx_kfrecord), cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+// ---- feature culling for the backend (frontend.cpp:1168-1218) ----
+#define ORBX_CULL_MAX 8192
+extern "C" orbx_status orbx_cull_keyframe_device(orbx_handle *h, const orbx_keypoint *d_kps, const uint8_t *d_desc, int32_t n,
+                                                 const int32_t *d_match_query, int32_t n_matches, int32_t max_new, float min_response,
+                                                 orbx_keypoint *d_out_kps, uint8_t *d_out_desc, int32_t *d_out_index, int32_t cap, int32_t *d_n_out)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    if (n < 0 || n_matches < 0 || max_new < 0 || (n > 0 && (!d_kps || !d_desc)) || (n_matches > 0 && !d_match_query) || !d_out_kps || !d_out_desc ||
+        !d_n_out || cap < 0 || ((uintptr_t)d_desc & 3) || ((uintptr_t)d_out_desc & 3)) { h->err = "bad culling arguments"; return ORBX_E_INVALID; }
+    if (n > ORBX_CULL_MAX) { h->err = "more than 8192 keypoints in one culling call"; return ORBX_E_CAPACITY; }
+    if (n == 0 && n_matches > 0) { h->err = "matches given for an empty keypoint set"; return ORBX_E_INVALID; }
+    if (n == 0) { ORBX_CUDA(h, cudaMemsetAsync(d_n_out, 0, sizeof(int32_t), h->stream)); return ORBX_OK; }
+    if (launch_cull(h, d_kps, d_desc, n, d_match_query, n_matches, max_new, min_response, d_out_kps, d_out_desc, d_out_index, cap, d_n_out) != 0) {
+        h->err = "shared-memory opt-in for the culling kernel failed"; return ORBX_E_CUDA;
+    }
+    ORBX_CUDA(h, cudaGetLastError());
+    return ORBX_OK;
+}
+extern "C" orbx_status orbx_cull_keyframe(orbx_handle *h, const orbx_keypoint *kps, const uint8_t *desc, int32_t n,
+                                          const int32_t *match_query, int32_t n_matches, int32_t max_new, float min_response,
+                                          orbx_keypoint *out_kps, uint8_t *out_desc, int32_t *out_index, int32_t cap, int32_t *n_out)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    if (n_out) *n_out = 0;
+    if (n < 0 || n_matches < 0 || max_new < 0 || (n > 0 && (!kps || !desc)) || (n_matches > 0 && !match_query) || !out_kps || !out_desc || !n_out || cap < 0) {
+        h->err = "bad culling arguments"; return ORBX_E_INVALID;
+    }
+    if (n > ORBX_CULL_MAX) { h->err = "more than 8192 keypoints in one culling call"; return ORBX_E_CAPACITY; }
+    for (int i = 0; i < n_matches; i++)
+        if (match_query[i] < 0 || match_query[i] >= n) { h->err = "a match query index lies outside the keypoint array"; return ORBX_E_INVALID; }
+    if (n == 0) return ORBX_OK;
+    if (h->pending[0].active || h->pending[1].active) { h->err = "an asynchronous batch is outstanding: call orbx_batch_wait first"; return ORBX_E_INVALID; }
+    orbx_status st;
+    const int ocap = n_matches + std::min(max_new, n);
+    const size_t in_k = align_up((size_t)n * sizeof(orbx_keypoint), 16), in_d = (size_t)n * ORBX_DESC_BYTES, in_q = align_up((size_t)std::max(n_matches, 1) * 4, 16);
+    const size_t out_k = align_up((size_t)std::max(ocap, 1) * sizeof(orbx_keypoint), 16), out_d = (size_t)std::max(ocap, 1) * ORBX_DESC_BYTES, out_i = align_up((size_t)std::max(ocap, 1) * 4, 16);
+    if ((st = grow(h, &h->d_mq, &h->mq_cap, in_k + in_d + in_q)) != ORBX_OK) return st;
+    if ((st = grow(h, &h->d_mt, &h->mt_cap, out_k + out_d + out_i + 16)) != ORBX_OK) return st;
+    orbx_keypoint *dk = (orbx_keypoint *)h->d_mq; uint8_t *dd = h->d_mq + in_k; int32_t *dq = (int32_t *)(h->d_mq + in_k + in_d);
+    orbx_keypoint *ok = (orbx_keypoint *)h->d_mt; uint8_t *od = h->d_mt + out_k; int32_t *oi = (int32_t *)(h->d_mt + out_k + out_d); int32_t *on = (int32_t *)(h->d_mt + out_k + out_d + out_i);
+    ORBX_CUDA(h, cudaMemcpyAsync(dk, kps, (size_t)n * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(h, cudaMemcpyAsync(dd, desc, (size_t)n * ORBX_DESC_BYTES, cudaMemcpyHostToDevice, h->stream));
+    if (n_matches > 0) ORBX_CUDA(h, cudaMemcpyAsync(dq, match_query, (size_t)n_matches * 4, cudaMemcpyHostToDevice, h->stream));
+    if (launch_cull(h, dk, dd, n, dq, n_matches, max_new, min_response, ok, od, oi, ocap, on) != 0) { h->err = "shared-memory opt-in for the culling kernel failed"; return ORBX_E_CUDA; }
+    int32_t m = 0;
+    ORBX_CUDA(h, cudaMemcpyAsync(&m, on, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    *n_out = m;
+    if (m > cap) { h->err = "culled feature capacity too small"; return ORBX_E_CAPACITY; }
+    if (m > 0) {
+        ORBX_CUDA(h, cudaMemcpyAsync(out_kps, ok, (size_t)m * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, h->stream));
+        ORBX_CUDA(h, cudaMemcpyAsync(out_desc, od, (size_t)m * ORBX_DESC_BYTES, cudaMemcpyDeviceToHost, h->stream));
+        if (out_index) ORBX_CUDA(h, cudaMemcpyAsync(out_index, oi, (size_t)m * 4, cudaMemcpyDeviceToHost, h->stream));
+        ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
     return ORBX_OK;
 }
 

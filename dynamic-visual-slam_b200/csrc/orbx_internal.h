@@ -97,7 +97,7 @@ struct orbx_handle {
     void *d_cells; int cell_cap;                             // FAST cell records, 32 bytes each (k_fast.cu: orbx_build_fast_cells)
     const uint8_t *tmap_l0; size_t tmap_l0_step, tmap_l0_fstride; int tmap_l0_frames;
     int pyr_grid_cap;                                     // resident CTAs of the cooperative pyramid kernel (0 = not probed, -1 = unavailable)
-    size_t blur_smem, quad_smem; bool rz_configured;      // per-handle (= per-device) dynamic shared memory opt-ins
+    size_t blur_smem, quad_smem, cull_smem; bool rz_configured;      // per-handle (= per-device) dynamic shared memory opt-ins
     int fast_grid_cap; size_t fast_smem; int fast_tp;   // resident CTAs / dynamic smem / tile pitch of the persistent FAST kernel
     // arenas, sized for max_width x max_height x max_batch
     uint8_t *d_pyr, *d_blur;     size_t pyr_slab, blur_slab;          // current per-frame strides
@@ -159,6 +159,7 @@ struct orbx_db {
 #define ORBX_DS_CAND_OVERFLOW 1
 #define ORBX_DS_NODE_OVERFLOW 2
 #define ORBX_DS_KP_OVERFLOW   4
+#define ORBX_DS_BAD_INDEX     8      // a caller-supplied index list pointed outside its array (k_cull)
 
 // ---- kernel launchers (one per .cu) ----
 int  launch_pyramid(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
@@ -168,6 +169,8 @@ int  orbx_ensure_tmaps(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0
 int  launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);   // -1: TMA descriptor encode failed
 void launch_quadtree(orbx_handle *h, int nframes);
 void launch_quadtree_geo(orbx_handle *h, const FrameGeom *d_geo, int nlevels, int nframes, int node_cap, size_t cand_slab, int sel_slab);
+int  launch_cull(orbx_handle *h, const orbx_keypoint *d_kps, const uint8_t *d_desc, int n, const int32_t *d_mq, int nm, int max_new, float min_response,
+                 orbx_keypoint *d_out_kps, uint8_t *d_out_desc, int32_t *d_out_index, int cap, int32_t *d_n_out);   // k_cull.cu; -1: shared memory opt-in failed
 int  launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride, cudaStream_t st, int tile_first = 0, int ntiles = -1);
 void launch_describe_to(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride,
                         orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts);

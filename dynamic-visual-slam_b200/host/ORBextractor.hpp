@@ -144,6 +144,35 @@ public:
         return n;                                                                  // monoIndex, :1166
     }
 
+    // The "FEATURE CULLING FOR BACKEND" block of Frontend::syncCallback (frontend.cpp:1168-1218): backend set = the query keypoint of
+    // every geometrically consistent match, then the best unmatched features by response (at most max_new, response >= min_response),
+    // equal responses in the order the reference's std::sort leaves them.
+    void cullForBackend(const std::vector<KeyPoint> &filtered_keypoints, const Mat &filtered_descriptors, const std::vector<DMatch> &matches,
+                        std::vector<KeyPoint> &backend_keypoints, Mat &backend_descriptors, int max_new = 200, float min_response = 50.0f)
+    {
+        const int n = (int)filtered_keypoints.size();
+        if (n > 0 && (filtered_descriptors.rows != n || filtered_descriptors.cols != 32 || filtered_descriptors.type() != type_8uc1()))
+            raise("cullForBackend: descriptors must be n x 32 CV_8UC1");
+        std::vector<int32_t> q(matches.size());
+        for (size_t i = 0; i < matches.size(); i++) q[i] = matches[i].queryIdx;
+        std::vector<uint8_t> din((size_t)std::max(n, 1) * ORBX_DESC_BYTES);
+        for (int r = 0; r < n; r++) std::memcpy(din.data() + (size_t)r * ORBX_DESC_BYTES, filtered_descriptors.ptr<uint8_t>(r), ORBX_DESC_BYTES);
+        const int cap = (int)q.size() + std::min(max_new, n);
+        std::vector<orbx_keypoint> ok((size_t)std::max(cap, 1));
+        std::vector<uint8_t> od((size_t)std::max(cap, 1) * ORBX_DESC_BYTES);
+        int32_t m = 0;
+        const orbx_status st = orbx_cull_keyframe(h_, (const orbx_keypoint *)filtered_keypoints.data(), din.data(), n, q.data(), (int32_t)q.size(),
+                                                  max_new, min_response, ok.data(), od.data(), nullptr, cap, &m);
+        if (st != ORBX_OK) raise(std::string("orbx_cull_keyframe: ") + orbx_last_error(h_));
+        backend_keypoints.resize((size_t)m);
+        if (m > 0) std::memcpy((void *)backend_keypoints.data(), ok.data(), (size_t)m * sizeof(orbx_keypoint));
+        if (m == 0) backend_descriptors = Mat();
+        else {
+            backend_descriptors.create(m, 32, type_8uc1());
+            for (int r = 0; r < m; r++) std::memcpy(backend_descriptors.ptr<uint8_t>(r), od.data() + (size_t)r * ORBX_DESC_BYTES, ORBX_DESC_BYTES);
+        }
+    }
+
     int GetLevels() { return orbx_get_levels(h_); }
     float GetScaleFactor() { return orbx_get_scale_factor(h_); }
     std::vector<float> GetScaleFactors() { return vec(orbx_get_scale_factors); }

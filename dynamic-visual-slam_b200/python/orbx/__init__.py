@@ -68,6 +68,8 @@ def load():
         "orbx_version": (ct.c_char_p, []),
         "orbx_sync": (i32, [vp]),
         "orbx_set_option": (i32, [vp, i32, i32]),
+        "orbx_cull_keyframe": (i32, [vp, vp, vp, i32, vp, i32, i32, f32, vp, vp, vp, i32, vp]),
+        "orbx_cull_keyframe_device": (i32, [vp, vp, vp, i32, vp, i32, i32, f32, vp, vp, vp, i32, vp]),
         "orbx_stream": (vp, [vp]),
         "orbx_get_levels": (i32, [vp]),
         "orbx_get_scale_factor": (f32, [vp]),
@@ -332,6 +334,19 @@ class ORBextractor:
         self._check(self.L.orbx_pack_keyframe(self._h, _p(kps), _p(desc), len(kps), _p(depth), depth.shape[1], depth.shape[0], depth.strides[0],
                                               _p(K), _p(out), len(out), ct.byref(n)))
         return out[:n.value].copy()
+
+    def cull_keyframe(self, kps, desc, match_query, max_new=200, min_response=50.0, cap=None):
+        """Feature culling for the backend (reference frontend.cpp:1168-1218): (kps, desc, index) — matched keypoints in match order, then
+        the best unmatched ones by response in the reference's std::sort order."""
+        kps = np.ascontiguousarray(kps, KP_DTYPE)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        q = np.ascontiguousarray(match_query, np.int32)
+        cap = len(q) + min(int(max_new), len(kps)) if cap is None else int(cap)
+        ok, od, oi = np.zeros(max(cap, 1), KP_DTYPE), np.zeros((max(cap, 1), 32), np.uint8), np.zeros(max(cap, 1), np.int32)
+        n = ct.c_int32()
+        self._check(self.L.orbx_cull_keyframe(self._h, _p(kps), _p(desc), len(kps), _p(q), len(q), int(max_new), ct.c_float(min_response),
+                                              _p(ok), _p(od), _p(oi), cap, ct.byref(n)))
+        return ok[:n.value].copy(), od[:n.value].copy(), oi[:n.value].copy()
 
     def extract_batch(self, frames, depth=None, cap=2048):
         frames = np.ascontiguousarray(frames, dtype=np.uint8)

@@ -236,6 +236,21 @@ orbx_status orbx_db_associate_device(orbx_db *db, const uint8_t *d_query, const 
                                      float max_desc_dist, double max_reproj_err, orbx_assoc *d_out);
 orbx_status orbx_merge_assoc_device(orbx_handle *h, const orbx_assoc *d_parts, int32_t nshards, int32_t nq, orbx_assoc *d_out);
 
+/* ---- feature culling for the backend: Frontend::syncCallback, frontend.cpp:1168-1218, SURVEY §8(f) rank 3 ----
+ * The set the frontend hands to isKeyframe / publishKeyframe: the keypoint of every (geometrically consistent) match, in match order,
+ * then the unmatched keypoints sorted by response — std::sort with `a.first > b.first`, so equal responses stay where libstdc++'s
+ * introsort leaves them — while fewer than max_new (reference: 200) were added and response >= min_response (reference: 50).
+ * match_query = DMatch::queryIdx of the matches that survived the caller's RANSAC mask (the F-matrix RANSAC stays on the CPU).
+ * out_index (optional) receives the index of every output element in the input arrays.  n <= 8192.  The keyframe-criterion match of
+ * isKeyframe (frontend.cpp:601-662) is orbx_match(k=1, max_dist=50) against the previous keyframe's culled descriptors.
+ * Device variant: asynchronous on the handle's stream; a query index outside [0, n) surfaces as ORBX_E_INVALID at the next sync.   */
+orbx_status orbx_cull_keyframe(orbx_handle *h, const orbx_keypoint *kps, const uint8_t *desc, int32_t n,
+                               const int32_t *match_query, int32_t n_matches, int32_t max_new /*200*/, float min_response /*50*/,
+                               orbx_keypoint *out_kps, uint8_t *out_desc, int32_t *out_index, int32_t cap, int32_t *n_out);
+orbx_status orbx_cull_keyframe_device(orbx_handle *h, const orbx_keypoint *d_kps, const uint8_t *d_desc, int32_t n,
+                                      const int32_t *d_match_query, int32_t n_matches, int32_t max_new, float min_response,
+                                      orbx_keypoint *d_out_kps, uint8_t *d_out_desc, int32_t *d_out_index, int32_t cap, int32_t *d_n_out);
+
 /* ---- keyframe packing: the landmark / observation loop of Frontend::publishKeyframe (frontend.cpp:731-776), SURVEY §8(f) rank 2 ----
  * For every keypoint with a depth in (0.3, 3.0) m: back-projection with the float intrinsics, world transform R*p + t in double,
  * one 80-byte record; order preserved; landmark_id = index of the keypoint in the input list, as in the reference.

@@ -288,6 +288,19 @@ def synth_descriptors(seed, first_row, nrows):
     return out
 
 
+def cull_keyframe(response, match_query, max_new=200, min_response=50.0):
+    """Frontend feature culling (reference frontend.cpp:1168-1218): indices into the filtered keypoints, matched first."""
+    r = np.ascontiguousarray(response, np.float32)
+    q = np.ascontiguousarray(match_query, np.int32)
+    out = np.zeros(len(q) + max(0, max_new) + 1, np.int32)
+    f = lib().orc_cull_keyframe
+    f.restype = ct.c_int
+    m = f(_p(r), len(r), _p(q), len(q), int(max_new), ct.c_float(min_response), _p(out))
+    if m < 0:
+        raise ValueError("match query index out of range")
+    return out[:m].copy()
+
+
 def introsort_pairs(cnt, ulx):
     n = len(cnt)
     c = np.array(cnt, np.int32)

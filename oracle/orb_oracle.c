@@ -386,6 +386,43 @@ void orc_introsort_pairs(int32_t *cnt, int32_t *ulx, int32_t *payload, int n)
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* Frontend feature culling for the backend — reference frontend.cpp:1168-1218.
+ * out = the query index of every match, in match order (:1181-1190), then the unmatched keypoints (index order, :1193-1198) sorted with
+ * std::sort and the comparator a.first > b.first on (response, index) pairs (:1201-1202) — equal responses stay where libstdc++'s
+ * introsort leaves them — taken while fewer than max_new were added and response >= min_response (:1209-1210).                     */
+static uint32_t cull_key(float response)
+{
+    union { float f; uint32_t u; } v;
+    v.f = response + 0.0f;                                  /* -0 -> +0: the float comparator does not tell them apart */
+    const uint32_t asc = v.u ^ ((v.u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+    return ~asc;                                            /* ascending key = descending response */
+}
+int orc_cull_keyframe(const float *response, int n, const int32_t *match_query, int n_matches, int max_new, float min_response, int32_t *out_index)
+{
+    unsigned char *matched = (unsigned char *)calloc((size_t)(n > 0 ? n : 1), 1);
+    int m = 0;
+    for (int i = 0; i < n_matches; i++) {
+        const int q = match_query[i];
+        if (q < 0 || q >= n) { free(matched); return -1; }
+        matched[q] = 1;
+        out_index[m++] = q;
+    }
+    srt_t *a = (srt_t *)malloc(sizeof(srt_t) * (size_t)(n > 0 ? n : 1));
+    int nu = 0;
+    for (int i = 0; i < n; i++)
+        if (!matched[i]) { a[nu].cnt = (int32_t)(cull_key(response[i]) ^ 0x80000000u); a[nu].ulx = 0; a[nu].payload = i; nu++; }
+    srt_sort(a, a + nu);
+    int added = 0;
+    for (int i = 0; i < nu; i++) {
+        if (added >= max_new || response[a[i].payload] < min_response) break;
+        out_index[m++] = a[i].payload;
+        added++;
+    }
+    free(a); free(matched);
+    return m;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* ExtractorNode / DivideNode / DistributeOctTree — ORBextractor.hpp:31-42, .cpp:480-536, 555-779.
  * Literal std::list emulation (doubly linked), push_front / erase exactly as the reference.    */
 typedef struct qnode {

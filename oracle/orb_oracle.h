@@ -105,6 +105,10 @@ typedef struct { uint64_t landmark_id; double position[3]; double pixel_x, pixel
 int orc_pack_keyframe(const orc_keypoint *kps, const uint8_t *desc, int n, const uint16_t *depth, int dw, int dh, size_t dstep_elems,
                       float fx, float fy, float cx, float cy, const double *R, const double *t, orc_kfrecord *out);
 
+/* Frontend feature culling for the backend (frontend.cpp:1168-1218): match query indices in match order, then the best unmatched
+ * keypoints by response (std::sort tie order of libstdc++); returns the number of indices written (<= n_matches + max_new), -1 on a bad index */
+int orc_cull_keyframe(const float *response, int n, const int32_t *match_query, int n_matches, int max_new, float min_response, int32_t *out_index);
+
 /* cv::ORB's HarrisResponses for one point (HARRIS_SCORE, ORBextractor.hpp:48) */
 float orc_harris_response(const uint8_t *img, size_t step, int x0, int y0, int blockSize, float k);
 

@@ -25,3 +25,13 @@ extern "C" void real_std_sort(int* cnt, int* ulx, int* payload, int n)
     for (int i = 0; i < n; i++) { c[i] = v[i].first; u[i] = v[i].second->ULx; p[i] = v[i].second->payload; }
     for (int i = 0; i < n; i++) { cnt[i] = c[i]; ulx[i] = u[i]; payload[i] = p[i]; }
 }
+
+// the frontend's sort of unmatched features (reference frontend.cpp:1193-1202): vector<pair<float, int>>, comparator a.first > b.first
+extern "C" void real_std_sort_response_desc(float* response, int* index, int n)
+{
+    std::vector<std::pair<float, int>> v;
+    v.reserve(n);
+    for (int i = 0; i < n; i++) v.push_back({response[i], index[i]});
+    std::sort(v.begin(), v.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+    for (int i = 0; i < n; i++) { response[i] = v[i].first; index[i] = v[i].second; }
+}

@@ -49,6 +49,14 @@ int main(int argc, char **argv)
         fwrite(good.data(), sizeof(orbx::DMatch), good.size(), f);
         std::vector<float> sf = extractor.GetScaleFactors();
         fwrite(sf.data(), sizeof(float), sf.size(), f);
+        // feature culling for the backend (frontend.cpp:1168-1218) on frame 1 with the distance-filtered matches standing in for the RANSAC inliers
+        std::vector<orbx::KeyPoint> bk;
+        orbx::Mat bd;
+        extractor.cullForBackend(k1, desc1, good, bk, bd);
+        const int32_t nb = (int32_t)bk.size();
+        fwrite(&nb, sizeof(nb), 1, f);
+        fwrite(bk.data(), sizeof(orbx::KeyPoint), bk.size(), f);
+        for (int r = 0; r < bd.rows; r++) fwrite(bd.ptr<uint8_t>(r), 1, 32, f);
         fclose(f);
         printf("adapter ok: %d %d %d keypoints, %zu matches, %zu good\n", n0, n1, n1f, matches.size(), good.size());
         return 0;

@@ -52,7 +52,10 @@ def test_adapter_matches_oracle(adapter_exe, oracle, tmp_path):
     dd1 = np.frombuffer(raw, np.uint8, 32 * n1, off).reshape(n1, 32); off += 32 * n1
     m = np.frombuffer(raw, oracle.DM_DTYPE, nm, off); off += 16 * nm
     good = np.frombuffer(raw, oracle.DM_DTYPE, ng, off); off += 16 * ng
-    sf = np.frombuffer(raw, np.float32, 8, off)
+    sf = np.frombuffer(raw, np.float32, 8, off); off += 32
+    nb = int(np.frombuffer(raw, np.int32, 1, off)[0]); off += 4
+    bk = np.frombuffer(raw, oracle.KP_DTYPE, nb, off); off += 28 * nb
+    bd = np.frombuffer(raw, np.uint8, 32 * nb, off).reshape(nb, 32)
     orc = oracle.COracle()
     r0, r1 = orc.extract(g0), orc.extract(g1)
     assert empty_rc == -1 and levels == 8 and npyr == 8
@@ -64,3 +67,6 @@ def test_adapter_matches_oracle(adapter_exe, oracle, tmp_path):
     assert np.array_equal(m.view(np.uint8), mo.view(np.uint8))
     assert np.array_equal(good.view(np.uint8), mo[mo["distance"] < 50.0].view(np.uint8))
     assert np.array_equal(sf, orc.scale)
+    gq = mo[mo["distance"] < 50.0]["queryIdx"]
+    idx = oracle.cull_keyframe(r1["kps"]["response"], gq)
+    assert nb == len(idx) > len(gq) and np.array_equal(bk.view(np.uint8), r1["kps"][idx].view(np.uint8)) and np.array_equal(bd, r1["desc"][idx])

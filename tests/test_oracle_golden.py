@@ -146,6 +146,42 @@ def test_introsort_emulation_matches_libstdcxx(oracle):
             assert oracle.introsort_pairs(cnt, ulx) == list(want), n
 
 
+def _cull_literal(response, match_query, max_new, min_response):
+    """Reference frontend.cpp:1168-1218 stated literally: std::set of matched query indices, matched keypoints in match order, unmatched
+    (response, index) pairs in index order sorted by the REAL std::sort with `a.first > b.first`, taken while added < max_new and
+    response >= min_response."""
+    import ctypes as ct
+    shim = ct.CDLL(os.path.join(os.path.dirname(GOLD), "..", "oracle", "libstdsort_shim.so"))
+    matched = set(int(q) for q in match_query)
+    out = [int(q) for q in match_query]
+    un = [(np.float32(response[i]), i) for i in range(len(response)) if i not in matched]
+    n = len(un)
+    r = (ct.c_float * max(n, 1))(*[float(a) for a, _ in un])
+    ix = (ct.c_int * max(n, 1))(*[b for _, b in un])
+    shim.real_std_sort_response_desc(r, ix, n)
+    added = 0
+    for k in range(n):
+        if added >= max_new or r[k] < min_response:
+            break
+        out.append(int(ix[k])); added += 1
+    return out
+
+
+def test_cull_rule_matches_libstdcxx(oracle):
+    """Feature culling for the backend (reference frontend.cpp:1168-1218): the C oracle against the literal statement above on
+    tie-heavy responses (FAST scores are small integers, so the std::sort tie order decides WHICH features survive the 200 cut)."""
+    rng = np.random.default_rng(23)
+    for n, nm, lo, hi in [(0, 0, 7, 60), (1, 0, 7, 60), (1, 1, 7, 60), (17, 3, 40, 70), (300, 100, 45, 56), (1000, 593, 7, 120),
+                          (1000, 0, 50, 52), (1000, 1000, 7, 120), (800, 10, 7, 49), (4096, 77, 48, 53)]:
+        resp = rng.integers(lo, hi, n).astype(np.float32)
+        q = rng.permutation(n)[:nm].astype(np.int32)
+        for max_new, min_resp in ((200, 50.0), (5, 0.0), (0, 50.0), (10000, 51.5)):
+            got = oracle.cull_keyframe(resp, q, max_new, min_resp).tolist()
+            assert got == _cull_literal(resp, q, max_new, min_resp), (n, nm, max_new, min_resp)
+    with pytest.raises(ValueError):
+        oracle.cull_keyframe(np.ones(4, np.float32), np.array([4], np.int32))
+
+
 def test_extract_edge_cases(oracle):
     orc = oracle.COracle()
     # featureless frame: no keypoints, not an error
