@@ -24,6 +24,9 @@ import time
 
 import numpy as np
 
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # NCCL prints its version banner to stdout: keep stdout to the one JSON line
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "dynamic-visual-slam_b200", "python"))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
