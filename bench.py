@@ -201,6 +201,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="orbx", choices=["orbx", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="frames resident per step and per GPU")
+    ap.add_argument("--separate-blur", action="store_true", help="blur every level with its own kernel (ORBX_OPT_FUSED_BLUR = 0) instead of inside the descriptor kernel")
     ap.add_argument("--fast-ctas", type=int, default=0, help="resident FAST warps per SM in the overlapped schedule (0 = library default)")
     ap.add_argument("--host-chunk", type=int, default=0, help="frames per pipeline chunk of the host-buffer call (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -231,6 +232,8 @@ def main():
     ex = orbx.ORBextractor(max_width=W, max_height=H, max_batch=B, device=local_rank, max_keypoints=CAP, host_chunk=args.host_chunk)
     if args.fast_ctas:
         ex.set_fast_ctas(args.fast_ctas)
+    if args.separate_blur:
+        ex.set_fused_blur(False)
     L, hnd = ex.L, ex.handle
     stream = torch.cuda.ExternalStream(ex.stream, device=dev)
 

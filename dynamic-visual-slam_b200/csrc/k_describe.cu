@@ -191,6 +191,177 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescParams P, cons
     }
 }
 
+// ---- fused variant: the 7x7 Gaussian of ORBextractor.cpp:1132-1133 evaluated ONLY where a descriptor reads it ----
+// The reference blurs every level (2.85 Mpx per 1280x720 frame) and then reads 512 blurred pixels around each of ~1000 keypoints.
+// The rotated pattern stays within 18 px of the keypoint (max |cvRound(rotated coordinate)| over all angles), so the 43 x 43 window
+// of the UN-blurred level around it holds every input of those 512 values; the same window holds the radius-15 disc of IC_Angle.
+// Per keypoint (one warp): the window is staged in shared memory with 16-byte loads (rows outside the level are fetched from their
+// BORDER_REFLECT_101 mirror, the at most two outside columns per side are mirrored in place — keypoints lie in [19, w-19), App. A.6);
+// row pass of the whole window (2 x IDP.4A per pixel, exact u16 row sums) into a second buffer; then each of the 512 samples is
+// one 7-tap column pass on that buffer: (sum + 32768) >> 16 — bit for bit the value cv::GaussianBlur leaves at that pixel.
+// Against blur + describe as two kernels this is ~3x fewer instructions and no blurred pyramid in HBM (no 2 x 2.85 MB per frame
+// written and re-read, no scattered DRAM gathers).  k_blur7 stays: orbx_get_blurred_level materialises levels with it on demand.
+#define DF_R 21
+#define DF_ROWS (2 * DF_R + 1)       // 43
+#define DF_PITCH 64                  // window tile pitch: 15 alignment bytes + 43 columns
+#define DF_RCOLS 40                  // row-pass columns: ten 4-pixel groups starting at the word that holds column x-18
+#define DF_CP 45                     // row sums are kept COLUMN-major (u16 [column][row], 45 entries per column): the seven taps of a
+                                     // sample's column pass are then four consecutive 32-bit words = 4 LDS + 4 IDP.2A per sample
+#define DF_WARP_BYTES (16 + DF_ROWS * DF_PITCH + 16 + ((DF_RCOLS * DF_CP * 2 + 16 + 15) & ~15))
+
+__device__ __forceinline__ void df_hpass4(uint32_t L, uint32_t C, uint32_t R, uint32_t &lo, uint32_t &hi)
+{
+    const uint32_t KLO = 0x38302212u;    // taps 18,34,48,56 on bytes x-3..x
+    const uint32_t KHI = 0x00122230u;    // taps 48,34,18 on bytes x+1..x+3
+    const uint32_t h0 = __dp4a(__funnelshift_r(L, C, 8), KLO, __dp4a(__funnelshift_r(C, R, 8), KHI, 0u));
+    const uint32_t h1 = __dp4a(__funnelshift_r(L, C, 16), KLO, __dp4a(__funnelshift_r(C, R, 16), KHI, 0u));
+    const uint32_t h2 = __dp4a(__funnelshift_r(L, C, 24), KLO, __dp4a(__funnelshift_r(C, R, 24), KHI, 0u));
+    const uint32_t h3 = __dp4a(C, KLO, __dp4a(R, KHI, 0u));
+    lo = h0 | (h1 << 16); hi = h2 | (h3 << 16);                                  // row sums <= 255 * 256 fit 16 bits
+}
+
+// blurred value from the column-major row sums: taps 18,34,48,56,48,34,18 on entries e .. e+6; the four words that hold them start at
+// entry e & ~1, so the tap weights sit one half-word later when e is odd
+__device__ __forceinline__ uint32_t df_sample(const uint32_t *rw, int e)
+{
+    const uint32_t *q = rw + (e >> 1);
+    const bool odd = e & 1;
+    uint32_t acc = 32768u;
+    acc = __dp2a_lo(q[0], odd ? 0x1200u : 0x2212u, acc);
+    acc = __dp2a_lo(q[1], odd ? 0x3022u : 0x3830u, acc);
+    acc = __dp2a_lo(q[2], odd ? 0x3038u : 0x2230u, acc);
+    acc = __dp2a_lo(q[3], odd ? 0x1222u : 0x0012u, acc);
+    return acc >> 16;
+}
+
+__global__ void __launch_bounds__(DESC_WARPS * 32) k_describe_fused(DescParams P, const FrameGeom *__restrict__ G)
+{
+    __shared__ __align__(16) uint8_t s_all[DESC_WARPS * DF_WARP_BYTES];
+    const int f = blockIdx.y;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nl = G->nlevels;
+    int gidx = blockIdx.x * DESC_WARPS + wid;
+    // locate (level, index in level): levels are concatenated in order (ORBextractor.cpp:1123)
+    int level = -1, k = gidx, total = 0;
+    for (int l = 0; l < nl; l++) {
+        const int c = P.nsel[f * nl + l];
+        if (level < 0) { if (k < c) level = l; else k -= c; }
+        total += c;
+    }
+    if (gidx == 0 && lane == 0) {
+        P.counts[f] = total <= P.cap ? total : 0;
+        if (total > P.cap) atomicOr(P.status, ORBX_DS_KP_OVERFLOW);
+    }
+    if (level < 0 || total > P.cap) return;
+    const LevelGeom &g = G->lv[level];
+    const uint32_t c = P.sel[(size_t)f * P.sel_slab + g.sel_off + k];
+    // pt += (minBorderX, minBorderY) — ORBextractor.cpp:886-887; integer-valued, cvRound is the identity
+    const int cx = orbx_px(c) + ORBX_BORDER, cy = orbx_py(c) + ORBX_BORDER;
+    const uint8_t *img; int step;
+    if (level == 0) { img = P.l0 + (size_t)f * P.l0_fstride; step = (int)P.l0_step; }
+    else { img = P.pyr + (size_t)f * P.pyr_slab + g.off; step = g.pitch; }
+    const int w = g.w, hgt = g.h;
+
+    uint8_t *tile = s_all + wid * DF_WARP_BYTES + 16;                              // 16 bytes of slack on either side of the tile
+    uint16_t *rows = reinterpret_cast<uint16_t *>(tile + DF_ROWS * DF_PITCH + 16);
+    // ---- stage the window: image columns from a 16-byte boundary, rows cy-21 .. cy+21 (mirrored outside the level) ----
+    const int xw = cx - DF_R;                                                      // window column 0
+    const int ax = xw & 15, xal = xw - ax;                                         // its byte in the tile; image column of tile byte 0 (may be -16)
+    {
+        uint4 v[6];                                                                // 172 chunks of 16 bytes: all six loads of a lane in flight together
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const int i = lane + 32 * k, r = i >> 2, ch = i & 3;
+            int y = cy - DF_R + r;
+            y = y < 0 ? -y : (y >= hgt ? 2 * hgt - 2 - y : y);
+            const int xs = xal + 16 * ch;
+            v[k] = make_uint4(0u, 0u, 0u, 0u);
+            if (i < DF_ROWS * 4 && xs >= 0 && xs + 16 <= step) v[k] = __ldg(reinterpret_cast<const uint4 *>(img + (size_t)y * step + xs));
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const int i = lane + 32 * k;
+            if (i < DF_ROWS * 4) *reinterpret_cast<uint4 *>(tile + (i >> 2) * DF_PITCH + 16 * (i & 3)) = v[k];
+        }
+    }
+    __syncwarp();
+    if (xw < 0 || xw + 2 * DF_R >= w) {                                            // columns outside the level: x -> -x resp. 2(w-1) - x
+        for (int r = lane; r < DF_ROWS; r += 32) {
+            uint8_t *row = tile + r * DF_PITCH - xal;                              // row[x] = pixel x of that (mirrored) image row
+            for (int x = xw; x < 0; x++) row[x] = row[-x];
+            for (int x = w; x <= xw + 2 * DF_R; x++) row[x] = row[2 * w - 2 - x];
+        }
+        __syncwarp();
+    }
+
+    // ---- IC_Angle on the staged window: lane = column u+15, all 31 rows ----
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int u = lane - ORBX_HALF_PATCH;
+        const int au = u < 0 ? -u : u;
+        const uint8_t *ctr = tile + DF_R * DF_PITCH + ax + DF_R + u;
+        int colsum = 0;
+#pragma unroll
+        for (int v = -ORBX_HALF_PATCH; v <= ORBX_HALF_PATCH; v++) {
+            const int av = v < 0 ? -v : v;
+            const int val = au <= c_umax[av] ? (int)ctr[v * DF_PITCH] : 0;
+            colsum += val; m01 += v * val;
+        }
+        m10 = u * colsum;
+    }
+    m10 = __reduce_add_sync(0xffffffffu, m10);
+    m01 = __reduce_add_sync(0xffffffffu, m01);
+    const float angle = cv_fast_atan2((float)m01, (float)m10);
+
+    // ---- row pass of the window: 43 rows x ten 4-pixel groups ----
+    const int b0 = (ax + 3) & ~3;                                                  // tile byte of row-pass column 0 (<= the byte of column x-18)
+    {
+        const uint32_t *tw = reinterpret_cast<const uint32_t *>(tile) + (b0 >> 2);
+        for (int u = lane; u < DF_ROWS * 10; u += 32) {
+            const int r = (u * 205) >> 11, gq = u - 10 * r;                        // u / 10 for u < 1029
+            const uint32_t *q = tw + r * (DF_PITCH / 4) + gq;
+            uint32_t lo, hi;
+            df_hpass4(q[-1], q[0], q[1], lo, hi);
+            uint16_t *o = rows + (4 * gq) * DF_CP + r;
+            o[0] = (uint16_t)lo; o[DF_CP] = (uint16_t)(lo >> 16); o[2 * DF_CP] = (uint16_t)hi; o[3 * DF_CP] = (uint16_t)(hi >> 16);
+        }
+    }
+    __syncwarp();
+
+    // ---- rBRIEF on blurred values computed at the sample points: lane i computes descriptor byte i ----
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    const float ang = __fmul_rn(angle, factorPI);
+    const float a = glibc_cosf(ang), b = glibc_sinf(ang);
+    signed char pat[32];
+    {
+        const int4 *pp = reinterpret_cast<const int4 *>(c_pattern + lane * 32);
+        *reinterpret_cast<int4 *>(pat) = __ldg(pp);
+        *reinterpret_cast<int4 *>(pat + 16) = __ldg(pp + 1);
+    }
+    const int e0 = (ax + DF_R - b0) * DF_CP + DF_R - 3;                            // entry of the first tap of the keypoint's own pixel
+    const uint32_t *rw = reinterpret_cast<const uint32_t *>(rows);
+    int val = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float x0 = (float)pat[4 * j], y0 = (float)pat[4 * j + 1], x1 = (float)pat[4 * j + 2], y1 = (float)pat[4 * j + 3];
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        val |= (df_sample(rw, e0 + c0 * DF_CP + r0) < df_sample(rw, e0 + c1 * DF_CP + r1)) << j;
+    }
+    uint8_t *drow = P.desc + ((size_t)f * P.cap + gidx) * ORBX_DESC_BYTES;
+    drow[lane] = (uint8_t)val;
+    if (lane == 0) {
+        orbx_keypoint kp;
+        kp.x = (float)cx; kp.y = (float)cy;
+        if (level != 0) { kp.x = __fmul_rn(kp.x, g.scale); kp.y = __fmul_rn(kp.y, g.scale); }   // :1147-1149
+        kp.size = g.size; kp.angle = angle; kp.response = (float)orbx_ps(c);
+        kp.octave = level; kp.class_id = -1;
+        P.kps[(size_t)f * P.cap + gidx] = kp;
+    }
+}
+
 void launch_describe_to(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride,
                         orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts)
 {
@@ -203,7 +374,8 @@ void launch_describe_to(orbx_handle *h, int nframes, const uint8_t *l0, size_t l
     const int maxk = h->geo.sel_entries < cap ? h->geo.sel_entries : cap;
     dim3 grid((maxk + DESC_WARPS - 1) / DESC_WARPS, nframes);
     ProfScope ps(h, ORBX_K_DESCRIBE);
-    k_describe<<<grid, DESC_WARPS * 32, 0, h->stream>>>(P, h->d_geo);
+    if (h->opt_fused_blur) k_describe_fused<<<grid, DESC_WARPS * 32, 0, h->stream>>>(P, h->d_geo);
+    else k_describe<<<grid, DESC_WARPS * 32, 0, h->stream>>>(P, h->d_geo);
 }
 
 // ---- Harris response of given points of one pyramid level (cv::ORB's HarrisResponses; HARRIS_SCORE of ORBextractor.hpp:48) ----

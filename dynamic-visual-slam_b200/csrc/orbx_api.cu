@@ -244,7 +244,7 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     if (p.device < 0 || p.device >= ndev) { g_create_err = "device ordinal out of range"; return ORBX_E_INVALID; }
     orbx_handle *h = new orbx_handle();
     h->prm = p; h->device = p.device; h->launches = 0; h->geo.width = -1; h->geo.height = -1;
-    h->prof_on = 0; h->prof_n = 0; h->prev_valid = 0;
+    h->prof_on = 0; h->prof_n = 0; h->prev_valid = 0; h->opt_fused_blur = 1; h->blur_valid = false;
     memset(h->prof_ms, 0, sizeof(h->prof_ms)); memset(h->prof_cnt, 0, sizeof(h->prof_cnt));
     CREATE_CUDA(cudaSetDevice(p.device));
     cudaDeviceProp prop;
@@ -356,6 +356,7 @@ extern "C" orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t v
     if (!h) return ORBX_E_INVALID;
     if (option == ORBX_OPT_SERIAL) { h->opt_serial = value ? 1 : 0; return ORBX_OK; }
     if (option == ORBX_OPT_FAST_CTAS) { h->opt_fast_ctas = value > 0 ? value : 0; return ORBX_OK; }
+    if (option == ORBX_OPT_FUSED_BLUR) { h->opt_fused_blur = value ? 1 : 0; return ORBX_OK; }
     h->err = "unknown option"; return ORBX_E_INVALID;
 }
 extern "C" void *orbx_stream(orbx_handle *h) { return h ? (void *)h->stream : nullptr; }
@@ -388,23 +389,26 @@ static orbx_status run_pipeline(orbx_handle *h, int nframes, const uint8_t *l0, 
     // pyramid's seven shrinking launches, the other levels start once the pyramid exists and fill what FAST and the
     // (latency-bound, low-occupancy) quadtree leave free.
     const int l0_tiles = h->geo.lv[0].blur_tx * h->geo.lv[0].blur_ty;
-    cudaStream_t bst = h->opt_serial ? h->stream : h->aux_stream;
-    if (!h->opt_serial) {
+    const bool side = !h->opt_serial && !h->opt_fused_blur;                       // a blur kernel on the aux stream
+    if (side) {
         ORBX_CUDA(h, cudaEventRecord(h->ev_fork0, h->stream));
         ORBX_CUDA(h, cudaStreamWaitEvent(h->aux_stream, h->ev_fork0, 0));
-        if (launch_blur(h, nframes, l0, l0_step, l0_fstride, bst, 0, l0_tiles) != 0) { h->err = "cuTensorMapEncodeTiled failed (frame base/step must be 16-byte aligned)"; return ORBX_E_CUDA; }
+        if (launch_blur(h, nframes, l0, l0_step, l0_fstride, h->aux_stream, 0, l0_tiles) != 0) { h->err = "cuTensorMapEncodeTiled failed (frame base/step must be 16-byte aligned)"; return ORBX_E_CUDA; }
     }
     if (launch_pyramid(h, nframes, l0, l0_step, l0_fstride) != 0) { h->err = "cuTensorMapEncodeTiled failed (frame base/step must be 16-byte aligned)"; return ORBX_E_CUDA; }   // ComputePyramid
-    if (!h->opt_serial) {
+    if (side) {
         ORBX_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
         ORBX_CUDA(h, cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
     }
     if (launch_fast(h, nframes, l0, l0_step, l0_fstride) != 0) { h->err = "cuTensorMapEncodeTiled failed (frame base/step must be 16-byte aligned)"; return ORBX_E_CUDA; }   // cell FAST
-    if (h->opt_serial) { if (launch_blur(h, nframes, l0, l0_step, l0_fstride, bst) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return ORBX_E_CUDA; } }   // GaussianBlur per level
-    else if (launch_blur(h, nframes, l0, l0_step, l0_fstride, bst, l0_tiles, -1) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return ORBX_E_CUDA; }
-    if (!h->opt_serial) ORBX_CUDA(h, cudaEventRecord(h->ev_join, h->aux_stream));
+    if (!h->opt_fused_blur) {                                                      // GaussianBlur per level as its own kernel
+        if (h->opt_serial) { if (launch_blur(h, nframes, l0, l0_step, l0_fstride, h->stream) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return ORBX_E_CUDA; } }
+        else if (launch_blur(h, nframes, l0, l0_step, l0_fstride, h->aux_stream, l0_tiles, -1) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return ORBX_E_CUDA; }
+    }
+    h->blur_valid = !h->opt_fused_blur;
+    if (side) ORBX_CUDA(h, cudaEventRecord(h->ev_join, h->aux_stream));
     launch_quadtree(h, nframes);                                                                 // DistributeOctTree
-    if (!h->opt_serial) ORBX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    if (side) ORBX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     const bool filtered = d_depth != nullptr || nboxes > 0;
     if (!filtered) launch_describe_to(h, nframes, l0, l0_step, l0_fstride, d_kps, d_desc, cap, d_counts);
     else {
@@ -802,6 +806,10 @@ extern "C" orbx_status orbx_get_blurred_level(orbx_handle *h, int32_t frame, int
     if (!h || !out || level < 0 || level >= h->geo.nlevels || frame < 0 || frame >= h->last_batch) return ORBX_E_INVALID;
     cudaSetDevice(h->device);
     const LevelGeom &g = h->geo.lv[level];
+    if (!h->blur_valid) {                                                          // fused mode: materialise the last batch's blurred levels now
+        if (launch_blur(h, h->last_batch, h->last_l0, h->last_l0_step, h->last_l0_fstride, h->stream) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return ORBX_E_CUDA; }
+        h->blur_valid = true;
+    }
     ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
     ORBX_CUDA(h, cudaMemcpy2D(out, out_step, h->d_blur + (size_t)frame * h->blur_slab + g.boff, g.bpitch, (size_t)g.w, (size_t)g.h, cudaMemcpyDeviceToHost));
     return ORBX_OK;

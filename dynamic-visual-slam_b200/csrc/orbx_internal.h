@@ -71,6 +71,8 @@ struct orbx_handle {
     cudaStream_t stream, copy_stream, out_stream, aux_stream;   // aux: blur runs beside FAST + quadtree
     cudaEvent_t ev_fork, ev_fork0, ev_join;
     int opt_serial;
+    int opt_fused_blur;          // 1 (default): the Gaussian is evaluated inside the descriptor kernel, no blurred pyramid is written
+    bool blur_valid;             // d_blur holds the blurred levels of the last batch
     int opt_fast_ctas;           // FAST warps per SM in the overlapped schedule (0 = as many as fit)
     cudaEvent_t ev_a, ev_b;
     cudaEvent_t ev_in[2], ev_comp[2], ev_out[2];   // host-batch pipeline: input slot filled / kernels done / outputs copied

@@ -288,9 +288,13 @@ orbx_status orbx_synth_descriptors_device(orbx_handle *h, uint32_t seed, uint64_
  * ORBX_OPT_SERIAL: 1 = launch every kernel of a step on the handle's one stream, in order (per-kernel event timings are
  * then isolated, as the roofline accounting wants); 0 (default) = the blur runs on a second stream beside FAST + quadtree.
  * ORBX_OPT_FAST_CTAS: resident FAST warps per SM in the overlapped schedule (0 = default); fewer leave room for the blur
- * running beside FAST. */
+ * running beside FAST.
+ * ORBX_OPT_FUSED_BLUR: 1 (default) = the 7x7 Gaussian is evaluated inside the descriptor kernel, only at the pixels the descriptors
+ * read (same bits); no blurred pyramid is written and orbx_get_blurred_level computes the level on demand.  0 = blur every level
+ * with its own kernel first, as the reference does. */
 #define ORBX_OPT_SERIAL 1
 #define ORBX_OPT_FAST_CTAS 2
+#define ORBX_OPT_FUSED_BLUR 3
 orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t value);
 
 /* ---- utilities ---- */
