@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescParams P, cons
 // written and re-read, no scattered DRAM gathers).  k_blur7 stays: orbx_get_blurred_level materialises levels with it on demand.
 #define DF_R 21
 #define DF_ROWS (2 * DF_R + 1)       // 43
-#define DF_PITCH 64                  // window tile pitch: 15 alignment bytes + 43 columns
+#define DF_PITCH 68                  // window tile pitch: 15 alignment bytes + 43 columns fit 64; 17 words so that a warp reading one word
+                                     // column of 32 consecutive rows (the row pass) touches 32 different banks
 #define DF_RCOLS 40                  // row-pass columns: ten 4-pixel groups starting at the word that holds column x-18
 #define DF_CP 45                     // row sums are kept COLUMN-major (u16 [column][row], 45 entries per column): the seven taps of a
                                      // sample's column pass are then four consecutive 32-bit words = 4 LDS + 4 IDP.2A per sample
@@ -281,7 +282,10 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe_fused(DescParams P
 #pragma unroll
         for (int k = 0; k < 6; k++) {
             const int i = lane + 32 * k;
-            if (i < DF_ROWS * 4) *reinterpret_cast<uint4 *>(tile + (i >> 2) * DF_PITCH + 16 * (i & 3)) = v[k];
+            if (i < DF_ROWS * 4) {
+                uint32_t *d = reinterpret_cast<uint32_t *>(tile + (i >> 2) * DF_PITCH + 16 * (i & 3));
+                d[0] = v[k].x; d[1] = v[k].y; d[2] = v[k].z; d[3] = v[k].w;
+            }
         }
     }
     __syncwarp();
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe_fused(DescParams P
     {
         const uint32_t *tw = reinterpret_cast<const uint32_t *>(tile) + (b0 >> 2);
         for (int u = lane; u < DF_ROWS * 10; u += 32) {
-            const int r = (u * 205) >> 11, gq = u - 10 * r;                        // u / 10 for u < 1029
+            const int gq = (u * 1525) >> 16, r = u - DF_ROWS * gq;                  // u / 43 for u < 2752: lanes run down the rows of one group
             const uint32_t *q = tw + r * (DF_PITCH / 4) + gq;
             uint32_t lo, hi;
             df_hpass4(q[-1], q[0], q[1], lo, hi);
