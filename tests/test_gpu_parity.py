@@ -55,6 +55,29 @@ def test_stages_bit_exact(ex, oracle, w, h, seed):
     assert np.array_equal(desc, ref["desc"]), "descriptors"
 
 
+def test_separate_blur_path_and_border_keypoints(ex, oracle):
+    """ORBX_OPT_FUSED_BLUR = 0 (blur every level with k_blur7, descriptors read the blurred pyramid) gives the same bits as the default
+    fused descriptor kernel; the frame is built so that corners sit right at the 19-px limit, where the fused kernel's 43 x 43 window
+    leaves the level and has to mirror rows and columns (BORDER_REFLECT_101)."""
+    w, h = 640, 480
+    rng = np.random.default_rng(12)
+    g = oracle.synth_gray(8, 0, w, h).copy()
+    band = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    g[:40], g[-40:], g[:, :40], g[:, -40:] = band[:40], band[-40:], band[:, :40], band[:, -40:]       # noise frame: corners everywhere near the edges
+    ref = oracle.COracle().extract(g, trace=True)
+    k = ref["kps"]
+    sc = oracle.COracle().scale
+    lx, ly = np.rint(k["x"] / sc[k["octave"]]), np.rint(k["y"] / sc[k["octave"]])                       # level coordinates
+    lw = np.array([ref["pyramid"][o].shape[1] for o in k["octave"]]); lh = np.array([ref["pyramid"][o].shape[0] for o in k["octave"]])
+    assert (lx <= 20).any() and (ly <= 20).any() and (lx >= lw - 21).any() and (ly >= lh - 21).any()       # windows leaving the level on all four sides
+    for fused in (True, False, True):
+        ex.set_fused_blur(fused)
+        kps, desc = ex(g)
+        assert np.array_equal(kps.view(np.uint8), k.view(np.uint8)) and np.array_equal(desc, ref["desc"]), "fused=%s" % fused
+        for l in (0, 3, 7):
+            assert np.array_equal(ex.blurred_level(l), ref["blurred"][l])
+
+
 def test_full_hd_and_other_parameters(built, oracle):
     """1920x1080 and non-default extractor parameters (nfeatures, scale factor, levels, thresholds) stay bit-exact."""
     import orbx
