@@ -35,6 +35,20 @@ struct ResizeParams {
     int src_level;
 };
 
+// vertical pass of four pixels: out = (((b0 * t0) >> 16) + ((b1 * t1) >> 16) + 2) >> 2, packed into one word.
+// The high halves of the eight products are gathered two per register (PRMT), so the additions, the rounding constant and the final
+// shift run on two pixels at once.  No clamp: a0 + a1 and b0 + b1 are 2048 +- 1, so t <= 32655 and every sum is at most 1021 + 2
+// (no carry between the halves, result <= 255).
+__device__ __forceinline__ uint32_t rz_vpack(int b0, int b1, const int (&t0)[4], const int (&t1)[4])
+{
+    uint32_t u[4], v[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { u[i] = (uint32_t)(b0 * t0[i]); v[i] = (uint32_t)(b1 * t1[i]); }
+    const uint32_t s01 = __byte_perm(u[0], u[1], 0x7632) + __byte_perm(v[0], v[1], 0x7632) + 0x00020002u;
+    const uint32_t s23 = __byte_perm(u[2], u[3], 0x7632) + __byte_perm(v[2], v[3], 0x7632) + 0x00020002u;
+    return __byte_perm(s01 >> 2, s23 >> 2, 0x6420);
+}
+
 __global__ void __launch_bounds__(RZ_THREADS) k_resize_linear(const __grid_constant__ LevelMaps M, ResizeParams P)
 {
     extern __shared__ __align__(128) uint8_t s_raw[];
@@ -96,13 +110,9 @@ __global__ void __launch_bounds__(RZ_THREADS) k_resize_linear(const __grid_const
             for (int i = 0; i < 4; i++) t1[i] = ((int)q[o[i]] * a0[i] + (int)q[o[i] + 1] * a1[i]) >> 4;
         }
         prev_off = e.y;
-        uint32_t v[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            tp[i] = t1[i];
-            v[i] = (uint32_t)min((((e.z * t0[i]) >> 16) + ((e.w * t1[i]) >> 16) + 2) >> 2, 255);
-        }
-        *reinterpret_cast<uint32_t *>(D) = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);   // pitch % 128 == 0: in-bounds
+        for (int i = 0; i < 4; i++) tp[i] = t1[i];
+        *reinterpret_cast<uint32_t *>(D) = rz_vpack(e.z, e.w, t0, t1);              // pitch % 128 == 0: the word is in-bounds
     }
 }
 
@@ -187,13 +197,9 @@ __global__ void __launch_bounds__(RZ_THREADS) k_pyramid_all(const __grid_constan
                         for (int i = 0; i < 4; i++) t1[i] = ((int)q[o[i]] * a0[i] + (int)q[o[i] + 1] * a1[i]) >> 4;
                     }
                     prev_off = e.y;
-                    uint32_t v[4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        tp[i] = t1[i];
-                        v[i] = (uint32_t)min((((e.z * t0[i]) >> 16) + ((e.w * t1[i]) >> 16) + 2) >> 2, 255);
-                    }
-                    *reinterpret_cast<uint32_t *>(D) = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+                    for (int i = 0; i < 4; i++) tp[i] = t1[i];
+                    *reinterpret_cast<uint32_t *>(D) = rz_vpack(e.z, e.w, t0, t1);
                 }
             }
             __syncthreads();                                                         // the window and the row table are reused by the next tile
