@@ -97,8 +97,10 @@ template <int NT> __global__ void __launch_bounds__(NT) k_quadtree(QtParams P, c
     __shared__ int s_M, s_nleaf, s_seq0, s_size, s_nsplit, s_state;
     __shared__ int s_sortcnt[2];
 
-    const int level = blockIdx.x;
-    const int f = blockIdx.y;
+    // level-major launch order: every frame's level 0 (most candidates, longest) first, the short top levels last — they fill the
+    // slots the first wave frees instead of trailing behind it
+    const int level = blockIdx.y;
+    const int f = blockIdx.x;
     const LevelGeom &g = G->lv[level];
     const int NC = P.node_cap;
     const int slot = f * G->nlevels + level;
@@ -345,7 +347,7 @@ void launch_quadtree_geo(orbx_handle *h, const FrameGeom *d_geo, int nlevels, in
         cudaFuncSetAttribute(k_quadtree<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         h->quad_smem = smem;
     }
-    dim3 grid(nlevels, nframes);
+    dim3 grid(nframes, nlevels);
     ProfScope ps(h, ORBX_K_QUADTREE);
     if (wide) k_quadtree<1024><<<grid, 1024, smem, h->stream>>>(P, d_geo);
     else k_quadtree<256><<<grid, 256, smem, h->stream>>>(P, d_geo);
