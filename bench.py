@@ -45,6 +45,9 @@ ALG_BYTES = {
 }
 
 
+POPC_PER_PAIR = 5.0              # csrc/orbx_hamming.h (ORBX_MATCH_CSA = 2)
+
+
 def ncu_traffic(kernel, frames, launches_per_step):
     """DRAM bytes per launch of `kernel` from the newest committed ncu --set full summary (profiles/*_traffic.json), scaled
     from the capture's batch to this run's; None when no capture is committed."""
@@ -326,14 +329,16 @@ def main():
                 out[name] = {"warp_inst_per_step": wi, "achieved_ginst_s": ach / 1e9, "peak_ginst_s": peak / 1e9, "frac": ach / peak}
         return out or None
 
-    # matching is integer-issue-bound: 8 POPC per descriptor pair against the measured POPC issue peak (orbx_bench_popc)
+    # matching is integer-issue-bound: POPC_PER_PAIR population counts per descriptor pair (three carry-save adders fold the eight XOR
+    # words into five, csrc/orbx_hamming.h) against the measured POPC issue peak (orbx_bench_popc)
     match_roofline = None
     if "k_match_partial" in kernels:
         pairs = float((nkp[1:].astype(np.float64) * nkp[:-1]).sum() + float(nkp[0]) * float(nkp[-1]))      # frame f vs f-1; frame 0 vs the carried last frame
         popc = ex.bench_popc()
         t_s = kernels["k_match_partial"]["ms_per_step"] * 1e-3
-        match_roofline = {"kernel": "k_match_partial", "bound": "integer issue (POPC)", "pairs_per_step": pairs, "achieved": 8.0 * pairs / t_s,
-                          "peak": popc, "unit": "POPC/s", "frac": 8.0 * pairs / t_s / popc if popc > 0 else None, "peak_source": "measured (orbx_bench_popc)"}
+        match_roofline = {"kernel": "k_match_partial", "bound": "integer issue (POPC)", "pairs_per_step": pairs, "popc_per_pair": POPC_PER_PAIR,
+                          "achieved": POPC_PER_PAIR * pairs / t_s, "peak": popc, "unit": "POPC/s",
+                          "frac": POPC_PER_PAIR * pairs / t_s / popc if popc > 0 else None, "peak_source": "measured (orbx_bench_popc)"}
     if args.kernels_only:
         clocks = sampler.stop()
         if rank == 0:
@@ -465,7 +470,7 @@ def main():
         assoc = {"queries": NQ, "db_rows": ROWS, "rows_per_gpu": rows_r, "ms_per_query_batch": ms_a,
                  "gpairs_per_s": NQ * ROWS / (ms_a * 1e-3) / 1e9, "exact_hits": int((res[:, 0] == 0).sum()),
                  "kernel_ms": kms, "popc_per_s_measured_peak": popc,
-                 "popc_frac": (8.0 * pairs / (kms * 1e-3)) / popc if popc > 0 and kms > 0 else None,
+                 "popc_frac": (POPC_PER_PAIR * pairs / (kms * 1e-3)) / popc if popc > 0 and kms > 0 else None,
                  "collective": "nccl all_gather_into_tensor of 32 KB/rank + merge kernel" if dist is not None else "none (1 GPU)"}
         db.close()
 

@@ -10,6 +10,7 @@
 // the splits — and, for a database sharded over GPUs, over the all-gathered per-shard results.
 // Exactly equal errors are resolved to the lowest landmark row (the reference iterates an unordered_map: unspecified there).
 #include "orbx_internal.h"
+#include "orbx_hamming.h"
 #include <float.h>
 
 #define AS_THREADS 128
@@ -61,8 +62,7 @@ __global__ void __launch_bounds__(AS_THREADS) k_assoc_partial(AssocParams P)
         if (qi >= P.nq) continue;
         for (int j = 0; j < cnt; j++) {
             const uint4 a = s_t[2 * j], b = s_t[2 * j + 1];
-            const int d = __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w) +
-                          __popc(q[4] ^ b.x) + __popc(q[5] ^ b.y) + __popc(q[6] ^ b.z) + __popc(q[7] ^ b.w);
+            const int d = hamming256(q, a, b);
             if ((float)d < P.max_dist) {
                 const double e = reproj_error(P.pos + (size_t)(base + j) * 3, P.pose, qx, qy);
                 if (e < P.max_err && e < best) { best = e; best_j = base + j; best_d = (float)d; }   // rows ascend: ties keep the lowest row

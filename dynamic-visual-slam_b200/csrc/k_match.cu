@@ -13,6 +13,7 @@
 // top-2 keys are merged (lexicographic min, 64-bit keys with global row numbers) by the epilogue
 // kernel, which also applies the threshold / ratio test and compacts in query order.
 #include "orbx_internal.h"
+#include "orbx_hamming.h"
 #include <float.h>
 
 #define MT_THREADS 128
@@ -28,12 +29,6 @@ struct MatchParams {
     int nq_max, nsplit, rows_per_split;
     uint32_t row_base;               // global index of train row 0 (database shards)
 };
-
-__device__ __forceinline__ int hamming256(const uint32_t q[8], const uint4 a, const uint4 b)
-{
-    return __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w) +
-           __popc(q[4] ^ b.x) + __popc(q[5] ^ b.y) + __popc(q[6] ^ b.z) + __popc(q[7] ^ b.w);
-}
 
 __global__ void __launch_bounds__(MT_THREADS) k_match_partial(MatchParams P)
 {
