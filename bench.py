@@ -499,7 +499,7 @@ def main():
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "width": W, "height": H,
                        "nfeatures": 1000, "nlevels": 8, "l2_policy": "inputs larger than L2 (%.0f MB per step per GPU)" % (B * W * H * 3 / 1e6),
                        "sharding": "frame-parallel, no data-path collective", "cpu_affinity": numa,
-                       "schedule": "pyramid -> FAST -> quadtree -> describe on the main stream, blur on a low-priority second stream (level 0 beside the pyramid, the rest beside FAST + quadtree); `kernels`/`roofline` timed in a second pass of the same K steps with every kernel on one stream (ORBX_OPT_SERIAL)"},
+                       "schedule": "one dependent chain pyramid -> FAST -> quadtree -> describe (7x7 Gaussian evaluated inside, at the sample points) -> filter -> match; `kernels`/`roofline` timed in a second pass of the same K steps with every kernel on one stream (ORBX_OPT_SERIAL)"},
             "roofline": roofline, "match_roofline": match_roofline,
             "issue": issue_view((clocks or {}).get("sm_mhz"), torch.cuda.get_device_properties(dev).multi_processor_count), "kernels": kernels, "cpu_baseline": cpu_baseline, "e2e": e2e, "latency": latency,
             "association": assoc, "gpu_launches": int(gpu_launches), "clocks": clocks,
