@@ -107,19 +107,19 @@ __device__ __forceinline__ FastRow fast_row(const uint32_t *q)
 
 // Pre-test of R <= 8 detection rows x 4 pixels (8 flag bits per pixel column).  q = the item's word in tile row r0 (= ring row dy = -3 of the first
 // detection row).  Result: bit (7-k) of byte j set iff pixel (row r0 + k, byte j) may be a corner at threshold T.
-#ifndef FAST_PAIRS
-#define FAST_PAIRS 4
+#ifndef FAST_RMAX
+#define FAST_RMAX 16                 // tallest sweep unit: a 37-row cell then takes 3 units per word column (30 units = ONE warp iteration at 94 %
+                                     // lane use) instead of 5 units of 8 rows (50 units = two iterations at 78 %)
 #endif
-#if FAST_PAIRS == 4
-template <int TP> __device__ __noinline__ uint32_t fast_sweep7(const uint32_t *q, uint32_t HM, uint32_t KK, int R)
+template <int TP> __device__ __noinline__ uint2 fast_sweep7(const uint32_t *q, uint32_t HM, uint32_t KK, int R)
 {
     FastRow w[7];
 #pragma unroll
     for (int k = 0; k < 6; k++) w[k] = fast_row(q + k * (TP / 4));
-    uint32_t fl = 0u;
+    uint32_t fl0 = 0u, fl1 = 0u;                                                 // rows 0..7 and rows 8..15 of the unit
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        if (k >= R) break;                                                       // units of R <= 8 rows (uniform); the window indices are mod 7
+    for (int k = 0; k < FAST_RMAX; k++) {
+        if (k >= R) break;                                                       // units of R <= FAST_RMAX rows (uniform); the window indices are mod 7
         w[(k + 6) % 7] = fast_row(q + (k + 6) * (TP / 4));                       // ring row dy = +3 of detection row k
         const uint32_t C0 = w[(k + 3) % 7].C;
         const uint32_t p08 = __vabsdiffu4(w[(k + 6) % 7].C, C0) | __vabsdiffu4(w[k % 7].C, C0);
@@ -131,37 +131,11 @@ template <int TP> __device__ __noinline__ uint32_t fast_sweep7(const uint32_t *q
         acc &= t1 | (t1 + KK);
         acc &= t2 | (t2 + KK);
         acc &= t3 | (t3 + KK);
-        fl |= (acc >> k) & (0x80808080u >> k);
+        if (k < 8) fl0 |= (acc >> k) & (0x80808080u >> k);
+        else fl1 |= (acc >> (k - 8)) & (0x80808080u >> (k - 8));
     }
-    return fl;
+    return make_uint2(fl0, fl1);
 }
-#else
-// two-pair variant: only the compass pairs (0,8) and (4,12) — half the sweep arithmetic for ~15 % more survivors
-template <int TP> __device__ __noinline__ uint32_t fast_sweep7(const uint32_t *q, uint32_t HM, uint32_t KK, int R)
-{
-    uint32_t wc[7], wp[7], wm[7];                                                // C, columns x+3.., columns x-3.. of the window rows
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-        const uint32_t *r = q + k * (TP / 4);
-        wc[k] = r[0];
-        if (k >= 3) { wp[k] = __byte_perm(wc[k], r[1], 0x6543); wm[k] = __byte_perm(r[-1], wc[k], 0x4321); }
-    }
-    uint32_t fl = 0u;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        if (k >= R) break;
-        const uint32_t *r = q + (k + 6) * (TP / 4);
-        wc[(k + 6) % 7] = r[0];
-        if (k + 6 < R + 3) { wp[(k + 6) % 7] = __byte_perm(r[0], r[1], 0x6543); wm[(k + 6) % 7] = __byte_perm(r[-1], r[0], 0x4321); }
-        const uint32_t C0 = wc[(k + 3) % 7];
-        const uint32_t t0 = (__vabsdiffu4(wc[(k + 6) % 7], C0) | __vabsdiffu4(wc[k % 7], C0)) & HM;
-        const uint32_t t1 = (__vabsdiffu4(wp[(k + 3) % 7], C0) | __vabsdiffu4(wm[(k + 3) % 7], C0)) & HM;
-        const uint32_t acc = (t0 | (t0 + KK)) & (t1 | (t1 + KK));
-        fl |= (acc >> k) & (0x80808080u >> k);
-    }
-    return fl;
-}
-#endif
 
 // loose pre-test threshold T = 2^sh - 1 <= th:  |d| > T  <=>  (|d| & HM) != 0;  t + KK sets bit 7 of every byte with t >= 2^sh
 __device__ __forceinline__ void fast_masks(int th, uint32_t &HM, uint32_t &KK)
@@ -290,27 +264,38 @@ template <int TP> __global__ void __launch_bounds__(32) k_fast_cells(const __gri
                 const int u = u0 + lane;
                 if (u < units) {
                     const int seg = __float2int_rd(((float)u + 0.5f) * inv), wcol = w0 + u - seg * nG, row0 = R * seg;
-                    const uint32_t raw = fast_sweep7<TP>(words + row0 * (TP / 4) + wcol, HM, KK, R);
+                    const uint2 raw = fast_sweep7<TP>(words + row0 * (TP / 4) + wcol, HM, KK, R);
                     const int cb = 4 * wcol - (ax + 3);                       // detection column of byte 0 (-3 .. dw-1)
                     const uint32_t cm = (0xFFFFFFFFu << (8 * max(0, -cb))) & (0xFFFFFFFFu >> (32 - 8 * min(4, dw - cb)));
-                    const int nv = min(R, dh - row0);
-                    uint32_t word = raw & cm & (((0xFF00u >> nv) & 0xFFu) * 0x01010101u);
-                    if (word) {
-                        const int cnt = __popc(word), base_off = (row0 + 3) * TP + 4 * wcol;
+                    const int nv = min(R, dh - row0);                         // valid rows of the unit: flag bit 7-k of a byte = row k (k < 8), row 8+k
+                    uint32_t w0f = raw.x & cm & (((0xFF00u >> min(nv, 8)) & 0xFFu) * 0x01010101u);
+                    uint32_t w1f = raw.y & cm & (((0xFF00u >> max(nv - 8, 0)) & 0xFFu) * 0x01010101u);
+                    if (w0f | w1f) {
+                        const int cnt = __popc(w0f) + __popc(w1f), base_off = (row0 + 3) * TP + 4 * wcol;
                         int slot = atomicAdd(&s_q[0], cnt);
                         if (slot + cnt <= FS_WQ) {
-                            do {
-                                const int bit = __ffs((int)word) - 1;
-                                word &= word - 1;
-                                wq[slot++] = (uint16_t)(base_off + (7 - (bit & 7)) * TP + (bit >> 3));
-                            } while (word);
+#pragma unroll
+                            for (int hw = 0; hw < 2; hw++) {
+                                uint32_t word = hw ? w1f : w0f;
+                                const int bo = base_off + 8 * hw * TP;
+                                while (word) {
+                                    const int bit = __ffs((int)word) - 1;
+                                    word &= word - 1;
+                                    wq[slot++] = (uint16_t)(bo + (7 - (bit & 7)) * TP + (bit >> 3));
+                                }
+                            }
                         } else {                                              // queue full: score in place, NMS will scan the whole cell
                             atomicMin(&s_q[1], slot);
-                            do {
-                                const int bit = __ffs((int)word) - 1;
-                                word &= word - 1;
-                                fast_score_to_map<TP>(s_img, s_sc, SP, base_off + (7 - (bit & 7)) * TP + (bit >> 3), ax, th);
-                            } while (word);
+#pragma unroll
+                            for (int hw = 0; hw < 2; hw++) {
+                                uint32_t word = hw ? w1f : w0f;
+                                const int bo = base_off + 8 * hw * TP;
+                                while (word) {
+                                    const int bit = __ffs((int)word) - 1;
+                                    word &= word - 1;
+                                    fast_score_to_map<TP>(s_img, s_sc, SP, bo + (7 - (bit & 7)) * TP + (bit >> 3), ax, th);
+                                }
+                            }
                         }
                     }
                 }
@@ -392,11 +377,12 @@ void orbx_build_fast_cells(const FrameGeom &G, const std::vector<uint32_t> &ctab
         const int ax = iniX & 15;                                  // tile byte of ROI column 0 (TMA boxes start on 16-byte columns)
         const int w0 = (ax + 3) >> 2;                              // tile word holding detection column 0
         const int nG = ((ax + 3 + dw - 1) >> 2) - w0 + 1;          // words holding detection columns (<= 19)
-        // rows per sweep unit: the R in 4..8 that minimises (warp iterations) x (cost of a unit = 6 window rows + R tested rows)
-        int R = 8, nseg = (dh + 7) / 8, best = ((nG * nseg + 31) >> 5) * (42 + 30 * 8);
-        for (int r = 7; r >= 4; r--) {
-            const int ns = (dh + r - 1) / r, cost = ((nG * ns + 31) >> 5) * (42 + 30 * r);
-            if (cost < best) { best = cost; R = r; nseg = ns; }
+        // rows per sweep unit: the R in 4..FAST_RMAX that minimises (warp iterations) x (cost of a unit = 6 window rows of 7 instructions
+        // + R tested rows of 23) + the per-iteration bookkeeping (~80)
+        int R = 0, nseg = 0, best = 0;
+        for (int r = FAST_RMAX; r >= 4; r--) {
+            const int ns = (dh + r - 1) / r, cost = ((nG * ns + 31) >> 5) * (42 + 23 * r + 80);
+            if (R == 0 || cost < best) { best = cost; R = r; nseg = ns; }
         }
         const float inv = 1.0f / (float)nG;
         uint32_t invb; memcpy(&invb, &inv, 4);
