@@ -236,10 +236,11 @@ template <int TP> __global__ void __launch_bounds__(32) k_fast_cells(const __gri
     for (;; it_n++) {
         const bool has_next = nxt < P.nitems;
         int drawn = 0;
+        uint32_t nx = 0u, ny = 0u;
         if (has_next && lane == 0) {
             drawn = atomicAdd(P.work, 1) + (int)gridDim.x;                              // consumed at the bottom of the loop
-            const uint4 n0 = __ldg(P.cells + 2 * nc);                                   // (read again below: L1-resident, and no registers stay live)
-            tma_prefetch_3d(&M.m[n0.y & 15u], (int)(n0.x & 0xFFFFu), (int)(n0.x >> 16), nf);
+            const uint4 n0 = __ldg(P.cells + 2 * nc);                                   // consumed after the tile wait below (read again later: L1-resident)
+            nx = n0.x; ny = n0.y;
         }
         const int level = (int)(C.c0.y & 15u), ax = (int)((C.c0.y >> 8) & 0xFFu), dw = (int)((C.c0.y >> 16) & 0xFFu), dh = (int)(C.c0.y >> 24);
         const int R = (int)(C.c0.z & 0xFFu), nseg = (int)((C.c0.z >> 8) & 0xFFu), nG = (int)((C.c0.z >> 16) & 0xFFu), w0 = (int)(C.c0.z >> 24);
@@ -250,6 +251,7 @@ template <int TP> __global__ void __launch_bounds__(32) k_fast_cells(const __gri
         // zero the score map (1-px ring included) while the tile lands
         for (int i = lane; i < ((dh + 2) * SP) / 16; i += 32) reinterpret_cast<uint4 *>(s_sc)[i] = make_uint4(0, 0, 0, 0);
         mbar_wait(&s_full, (uint32_t)(it_n & 1));
+        if (has_next && lane == 0) tma_prefetch_3d(&M.m[ny & 15u], (int)(nx & 0xFFFFu), (int)(nx >> 16), nf);   // next window -> L2
         __syncwarp();
 
         const int units = nG * nseg;

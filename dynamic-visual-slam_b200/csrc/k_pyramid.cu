@@ -61,11 +61,16 @@ __global__ void __launch_bounds__(RZ_THREADS) k_resize_linear(const __grid_const
     // source window of this tile: columns from a 16-byte boundary, rows from the first source row
     const int abase = __ldg(&P.xtab[x0].ofs) & ~15;
     const int sylo = max(0, min(__ldg(&P.ytab[y0].ofs), P.sh - 1));
+    // Programmatic dependent launch: the levels are a chain of launches of this kernel.  Every CTA releases the next level's launch at
+    // once (its CTAs take the slots this level's last wave frees and run their table prologue early); only the thread that issues the
+    // TMA load of the source window — the one access to the previous level — waits for the previous launch to be complete and visible.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) {
         mbar_init(&s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(&s_bar, (uint32_t)(ORBX_RZ_BOX_ROWS * ORBX_TMA_BOX_BYTES));
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         tma_load_3d(s_img, &M.m[P.src_level], abase >> 2, sylo, f, &s_bar);
     }
     for (int r = threadIdx.x; r <= y1 - y0; r += RZ_THREADS) {
@@ -266,6 +271,13 @@ int launch_resize_level(orbx_handle *h, int level, int nframes, const uint8_t *l
     if (!h->rz_configured) { cudaFuncSetAttribute(k_resize_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); h->rz_configured = true; }
     dim3 grid((gd.w + P.tw - 1) / P.tw, (gd.h + P.th - 1) / P.th, nframes);
     ProfScope ps(h, ORBX_K_RESIZE);
-    k_resize_linear<<<grid, RZ_THREADS, smem, h->stream>>>(M, P);
+    // levels >= 2 directly follow the launch that writes their source: allow them to start while it drains (see the kernel)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(RZ_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (level >= 2 && !h->prof_on) ? 1 : 0;
+    if (cudaLaunchKernelEx(&cfg, k_resize_linear, M, P) != cudaSuccess) { cudaGetLastError(); k_resize_linear<<<grid, RZ_THREADS, smem, h->stream>>>(M, P); }
     return 0;
 }
