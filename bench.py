@@ -315,7 +315,9 @@ def main():
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
                     "frac": kernels[dom]["frac_of_hbm"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": ALG_BYTES[dom] * B / max(1.0, kernels[dom]["launches_per_step"]),
-                    "dominant_overall": max(kernels, key=lambda n: kernels[n]["ms_per_step"])}
+                    "dominant_overall": max(kernels, key=lambda n: kernels[n]["ms_per_step"]),
+                    "note": "the kernel is an exact 8/16-bit integer pipeline bound by instruction issue, not by HBM: see `issue` (executed warp "
+                            "instructions / kernel time against 4 schedulers x SMs x SM clock); its DRAM traffic equals its algorithmic bytes"}
 
     # The dense stages are exact 8/16-bit integer pipelines and turn out ISSUE-bound, not HBM-bound: executed warp instructions
     # (committed ncu capture, scaled per frame) over the live kernel time, against 4 schedulers x SMs x the SM clock sampled below.
