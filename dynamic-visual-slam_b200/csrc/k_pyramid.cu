@@ -243,6 +243,8 @@ int launch_pyramid(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_ste
         PyrParams P;
         P.pyr = h->d_pyr; P.pyr_slab = h->pyr_slab; P.xtab = h->d_xtab; P.ytab = h->d_ytab;
         P.tw = G.rz_tw; P.th = G.rz_th; P.nframes = nframes;
+        // latency path: halve the tile height while level 1 would leave SMs without a tile (60 tiles of 192 x 64 for one 1280 x 720 frame)
+        while (P.th > 16 && ((G.lv[1].w + P.tw - 1) / P.tw) * ((G.lv[1].h + P.th - 1) / P.th) * nframes < h->sm_count) P.th = (P.th / 2 + 7) & ~7;
         const int tiles1 = ((G.lv[1].w + P.tw - 1) / P.tw) * ((G.lv[1].h + P.th - 1) / P.th) * nframes;
         const int grid = std::max(1, std::min(tiles1, h->pyr_grid_cap));
         const FrameGeom *dg = h->d_geo;
