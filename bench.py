@@ -205,6 +205,7 @@ def main():
     ap.add_argument("--impl", default="orbx", choices=["orbx", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="frames resident per step and per GPU")
     ap.add_argument("--separate-blur", action="store_true", help="blur every level with its own kernel (ORBX_OPT_FUSED_BLUR = 0) instead of inside the descriptor kernel")
+    ap.add_argument("--no-pdl", action="store_true", help="plain stream order instead of programmatic dependent launch (ORBX_OPT_PDL = 0)")
     ap.add_argument("--fast-ctas", type=int, default=0, help="resident FAST warps per SM in the overlapped schedule (0 = library default)")
     ap.add_argument("--host-chunk", type=int, default=0, help="frames per pipeline chunk of the host-buffer call (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -237,6 +238,8 @@ def main():
         ex.set_fast_ctas(args.fast_ctas)
     if args.separate_blur:
         ex.set_fused_blur(False)
+    if args.no_pdl:
+        ex.set_pdl(False)
     L, hnd = ex.L, ex.handle
     stream = torch.cuda.ExternalStream(ex.stream, device=dev)
 

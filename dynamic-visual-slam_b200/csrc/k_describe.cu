@@ -238,6 +238,7 @@ __device__ __forceinline__ uint32_t df_sample(const uint32_t *rw, int e)
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe_fused(DescParams P, const FrameGeom *__restrict__ G)
 {
     __shared__ __align__(16) uint8_t s_all[DESC_WARPS * DF_WARP_BYTES];
+    ORBX_PDL_ENTRY();
     const int f = blockIdx.y;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int nl = G->nlevels;
@@ -378,7 +379,7 @@ void launch_describe_to(orbx_handle *h, int nframes, const uint8_t *l0, size_t l
     const int maxk = h->geo.sel_entries < cap ? h->geo.sel_entries : cap;
     dim3 grid((maxk + DESC_WARPS - 1) / DESC_WARPS, nframes);
     ProfScope ps(h, ORBX_K_DESCRIBE);
-    if (h->opt_fused_blur) k_describe_fused<<<grid, DESC_WARPS * 32, 0, h->stream>>>(P, h->d_geo);
+    if (h->opt_fused_blur) orbx_launch_pdl(h, k_describe_fused, grid, dim3(DESC_WARPS * 32), 0, h->stream, P, (const FrameGeom *)h->d_geo);
     else k_describe<<<grid, DESC_WARPS * 32, 0, h->stream>>>(P, h->d_geo);
 }
 

@@ -194,6 +194,7 @@ template <int TP> __global__ void __launch_bounds__(32) k_fast_cells(const __gri
     __shared__ __align__(8) uint64_t s_full;
     __shared__ int s_q[2];                                // survivor queue: fill, first slot that did not fit
     __shared__ uint32_t s_res[2 * FS_RES];                // result lists of the current and the previous cell
+    ORBX_PDL_ENTRY();
     uint8_t *s_dyn = s_raw + ((128u - (smem_u32(s_raw) & 127u)) & 127u);
     // layout: [128-byte pad | tile | score map | queue]: the word left of tile column 0 (read, never used) falls into the pad
     uint8_t *s_img = s_dyn + 128;                                                        // tile_rows x TP, 128-byte aligned (TMA destination)
@@ -481,6 +482,6 @@ int launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, 
     int grid = std::min(P.nitems, h->fast_grid_cap);
     if (!h->opt_serial && h->opt_fast_ctas > 0) grid = std::min(grid, h->opt_fast_ctas * h->sm_count);
     ProfScope ps(h, ORBX_K_FAST);
-    kern<<<grid, 32, smem, h->stream>>>(M, P, h->d_geo);
+    orbx_launch_pdl(h, kern, dim3(grid), dim3(32), smem, h->stream, M, P, (const FrameGeom *)h->d_geo);
     return 0;
 }

@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(1024) k_filter(FilterParams P)
 {
     __shared__ int s_warp[33];                              // one CTA per frame, any block size that is a multiple of 32
     __shared__ int s_base;
+    ORBX_PDL_ENTRY();
     const int f = blockIdx.x;
     const int n = P.nin[f];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -94,7 +95,7 @@ void launch_filter(orbx_handle *h, int nframes, const uint16_t *d_depth, size_t 
     P.boxes = d_boxes; P.nboxes = nboxes; P.drop_mask = drop_mask;
     P.kout = d_kps; P.dout = d_desc; P.nout = d_counts; P.cap_out = cap; P.status = h->d_status;
     ProfScope ps(h, ORBX_K_FILTER);
-    k_filter<<<nframes, 1024, 0, h->stream>>>(P);
+    orbx_launch_pdl(h, k_filter, dim3(nframes), dim3(1024), 0, h->stream, P);
 }
 
 // ---- keyframe packing: the landmark / observation loop of Frontend::publishKeyframe (reference frontend.cpp:731-776) ----

@@ -33,6 +33,7 @@ struct MatchParams {
 __global__ void __launch_bounds__(MT_THREADS) k_match_partial(MatchParams P)
 {
     __shared__ uint4 s_t[MT_TILE * 2];
+    ORBX_PDL_ENTRY();
     const int prob = blockIdx.z;
     const int qs = P.qsel ? P.qsel[prob] : prob, ts = P.tsel ? P.tsel[prob] : prob;
     const int nq = P.nq_arr ? P.nq_arr[qs] : P.nq_imm;
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(1024) k_match_epilogue(MatchEpiParams P)
 {
     __shared__ int s_warp[33];                              // one CTA per problem, any block size that is a multiple of 32
     __shared__ int s_base;
+    ORBX_PDL_ENTRY();
     const int prob = blockIdx.x;
     const int qs = P.qsel ? P.qsel[prob] : prob, ts = P.tsel ? P.tsel[prob] : prob;
     const int nq = P.nq_arr ? P.nq_arr[qs] : P.nq_imm;
@@ -209,7 +211,7 @@ int launch_match_core(orbx_handle *h, const uint8_t *d_q, const int32_t *d_nq, i
         // every slot the epilogue reads (qi < nq, all splits) is written by the partial kernel; splits that
         // start beyond a problem's own nt write the "empty" key
         ProfScope ps(h, ORBX_K_MATCH);
-        k_match_partial<<<grid, MT_THREADS, 0, h->stream>>>(P);
+        orbx_launch_pdl(h, k_match_partial, grid, dim3(MT_THREADS), 0, h->stream, P);
     }
     MatchEpiParams E;
     E.part = (const unsigned long long *)h->d_mpart; E.nq_max = nq_max; E.nsplit = nsplit;
@@ -218,7 +220,7 @@ int launch_match_core(orbx_handle *h, const uint8_t *d_q, const int32_t *d_nq, i
     E.k = k; E.max_dist = max_dist; E.ratio_num = ratio_num;
     E.out = d_out; E.out_stride = out_stride; E.n_out = d_n_out; E.top2 = d_top2;
     ProfScope ps(h, ORBX_K_MATCH_EPI);
-    k_match_epilogue<<<nproblems, 1024, 0, h->stream>>>(E);
+    orbx_launch_pdl(h, k_match_epilogue, dim3(nproblems), dim3(1024), 0, h->stream, E);
     return 0;
 }
 

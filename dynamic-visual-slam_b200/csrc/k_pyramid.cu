@@ -279,7 +279,7 @@ int launch_resize_level(orbx_handle *h, int level, int nframes, const uint8_t *l
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = (level >= 2 && !h->prof_on) ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = (level >= 2 && !h->prof_on && h->opt_pdl) ? 1 : 0;
     if (cudaLaunchKernelEx(&cfg, k_resize_linear, M, P) != cudaSuccess) { cudaGetLastError(); k_resize_linear<<<grid, RZ_THREADS, smem, h->stream>>>(M, P); }
     return 0;
 }

@@ -99,6 +99,7 @@ template <int NT> __global__ void __launch_bounds__(NT) k_quadtree(QtParams P, c
 
     // level-major launch order: every frame's level 0 (most candidates, longest) first, the short top levels last — they fill the
     // slots the first wave frees instead of trailing behind it
+    ORBX_PDL_ENTRY();
     const int level = blockIdx.y;
     const int f = blockIdx.x;
     const LevelGeom &g = G->lv[level];
@@ -349,8 +350,8 @@ void launch_quadtree_geo(orbx_handle *h, const FrameGeom *d_geo, int nlevels, in
     }
     dim3 grid(nframes, nlevels);
     ProfScope ps(h, ORBX_K_QUADTREE);
-    if (wide) k_quadtree<1024><<<grid, 1024, smem, h->stream>>>(P, d_geo);
-    else k_quadtree<256><<<grid, 256, smem, h->stream>>>(P, d_geo);
+    if (wide) orbx_launch_pdl(h, k_quadtree<1024>, grid, dim3(1024), smem, h->stream, P, d_geo);
+    else orbx_launch_pdl(h, k_quadtree<256>, grid, dim3(256), smem, h->stream, P, d_geo);
 }
 
 void launch_quadtree(orbx_handle *h, int nframes)

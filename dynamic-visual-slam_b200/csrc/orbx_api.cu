@@ -244,7 +244,7 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     if (p.device < 0 || p.device >= ndev) { g_create_err = "device ordinal out of range"; return ORBX_E_INVALID; }
     orbx_handle *h = new orbx_handle();
     h->prm = p; h->device = p.device; h->launches = 0; h->geo.width = -1; h->geo.height = -1;
-    h->prof_on = 0; h->prof_n = 0; h->prev_valid = 0; h->opt_fused_blur = 1; h->blur_valid = false;
+    h->prof_on = 0; h->prof_n = 0; h->prev_valid = 0; h->opt_fused_blur = 1; h->blur_valid = false; h->opt_pdl = 1;
     memset(h->prof_ms, 0, sizeof(h->prof_ms)); memset(h->prof_cnt, 0, sizeof(h->prof_cnt));
     CREATE_CUDA(cudaSetDevice(p.device));
     cudaDeviceProp prop;
@@ -357,6 +357,7 @@ extern "C" orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t v
     if (option == ORBX_OPT_SERIAL) { h->opt_serial = value ? 1 : 0; return ORBX_OK; }
     if (option == ORBX_OPT_FAST_CTAS) { h->opt_fast_ctas = value > 0 ? value : 0; return ORBX_OK; }
     if (option == ORBX_OPT_FUSED_BLUR) { h->opt_fused_blur = value ? 1 : 0; return ORBX_OK; }
+    if (option == ORBX_OPT_PDL) { h->opt_pdl = value ? 1 : 0; return ORBX_OK; }
     h->err = "unknown option"; return ORBX_E_INVALID;
 }
 extern "C" void *orbx_stream(orbx_handle *h) { return h ? (void *)h->stream : nullptr; }
@@ -388,6 +389,7 @@ static orbx_status run_pipeline(orbx_handle *h, int nframes, const uint8_t *l0, 
     // describe) runs on the low-priority aux stream as filler: level 0 depends on the input alone and starts beside the
     // pyramid's seven shrinking launches, the other levels start once the pyramid exists and fill what FAST and the
     // (latency-bound, low-occupancy) quadtree leave free.
+    h->pdl_chain = nframes <= 8;
     const int l0_tiles = h->geo.lv[0].blur_tx * h->geo.lv[0].blur_ty;
     const bool side = !h->opt_serial && !h->opt_fused_blur;                       // a blur kernel on the aux stream
     if (side) {

@@ -230,6 +230,10 @@ class ORBextractor:
         """ORBX_OPT_FUSED_BLUR: evaluate the Gaussian inside the descriptor kernel (default) instead of blurring every level first."""
         self._check(self.L.orbx_set_option(self._h, 3, 1 if on else 0))
 
+    def set_pdl(self, on=True):
+        """ORBX_OPT_PDL: programmatic dependent launch of the step's kernel chain (default on)."""
+        self._check(self.L.orbx_set_option(self._h, 4, 1 if on else 0))
+
     def set_fast_ctas(self, n):
         """ORBX_OPT_FAST_CTAS: resident FAST warps per SM in the overlapped schedule (0 = as many as fit)."""
         self._check(self.L.orbx_set_option(self._h, 2, int(n)))

@@ -291,10 +291,14 @@ orbx_status orbx_synth_descriptors_device(orbx_handle *h, uint32_t seed, uint64_
  * running beside FAST.
  * ORBX_OPT_FUSED_BLUR: 1 (default) = the 7x7 Gaussian is evaluated inside the descriptor kernel, only at the pixels the descriptors
  * read (same bits); no blurred pyramid is written and orbx_get_blurred_level computes the level on demand.  0 = blur every level
- * with its own kernel first, as the reference does. */
+ * with its own kernel first, as the reference does.
+ * ORBX_OPT_PDL: 1 (default) = programmatic stream serialization (the next kernel's CTAs become resident while the previous one drains)
+ * for the pyramid's chain of launches and, for batches of up to 8 frames (the latency path), for every kernel of the step;
+ * 0 = plain stream order. */
 #define ORBX_OPT_SERIAL 1
 #define ORBX_OPT_FAST_CTAS 2
 #define ORBX_OPT_FUSED_BLUR 3
+#define ORBX_OPT_PDL 4
 orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t value);
 
 /* ---- utilities ---- */
