@@ -595,9 +595,12 @@ struct BatchArgs {
     orbx_keypoint *kps; uint8_t *desc; int cap; int32_t *counts; orbx_dmatch *matches; int32_t *mcounts; float max_dist;
 };
 
-static orbx_status enqueue_chunk(orbx_handle *h, const BatchArgs &A, int f0, int nb)
+// `inl`: a call that is one small chunk (the single-frame latency path) keeps its copies on the kernels' stream — two cross-stream
+// event hops less on the critical path; batches pipeline H2D / kernels / D2H over three streams
+static orbx_status enqueue_chunk(orbx_handle *h, const BatchArgs &A, int f0, int nb, bool inl = false)
 {
     const int slot = (int)(h->seq & 1);
+    cudaStream_t cs = inl ? h->stream : h->copy_stream, os = inl ? h->stream : h->out_stream;
     const int width = A.width, height = A.height;
     const size_t pitch = align_up((size_t)width, 128), dpitch = align_up((size_t)width * 2, 128);
     const size_t fstride = pitch * height, dfstride = dpitch * height;
@@ -608,7 +611,7 @@ static orbx_status enqueue_chunk(orbx_handle *h, const BatchArgs &A, int f0, int
     orbx_dmatch *d_m = nullptr; int32_t *d_mc = nullptr;
     if (A.track) {
         if (h->mout_cap < 2 * slot_kp * sizeof(orbx_dmatch) + 2 * (size_t)SC * sizeof(int32_t)) {
-            cudaStreamSynchronize(h->out_stream);                   // an older chunk may still be copying out of the old buffer
+            cudaStreamSynchronize(h->out_stream); cudaStreamSynchronize(h->stream);   // an older chunk may still be copying out of the old buffer
             if ((st = grow(h, (uint8_t **)&h->d_mout, &h->mout_cap, 2 * slot_kp * sizeof(orbx_dmatch) + 2 * (size_t)SC * sizeof(int32_t))) != ORBX_OK) return st;
         }
         d_m = h->d_mout + (size_t)slot * slot_kp;
@@ -619,18 +622,18 @@ static orbx_status enqueue_chunk(orbx_handle *h, const BatchArgs &A, int f0, int
     uint8_t *d_g = h->d_in + (size_t)slot * SC * fstride;
     uint8_t *d_d = (uint8_t *)h->d_depth_in + (size_t)slot * SC * dfstride;
     // ---- H2D (copy stream): the input slot is free once the kernels of the chunk that used it last are done ----
-    ORBX_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_comp[slot], 0));
-    if (tight) ORBX_CUDA(h, cudaMemcpyAsync(d_g, A.gray + (size_t)f0 * height * A.step, (size_t)nb * fstride, cudaMemcpyHostToDevice, h->copy_stream));
+    ORBX_CUDA(h, cudaStreamWaitEvent(cs, h->ev_comp[slot], 0));
+    if (tight) ORBX_CUDA(h, cudaMemcpyAsync(d_g, A.gray + (size_t)f0 * height * A.step, (size_t)nb * fstride, cudaMemcpyHostToDevice, cs));
     else for (int f = 0; f < nb; f++)
         ORBX_CUDA(h, cudaMemcpy2DAsync(d_g + (size_t)f * fstride, pitch, A.gray + (size_t)(f0 + f) * height * A.step, A.step,
-                                       (size_t)width, (size_t)height, cudaMemcpyHostToDevice, h->copy_stream));
+                                       (size_t)width, (size_t)height, cudaMemcpyHostToDevice, cs));
     if (A.depth && !depth_zc) {
-        if (A.dstep == dpitch) ORBX_CUDA(h, cudaMemcpyAsync(d_d, (const uint8_t *)A.depth + (size_t)f0 * height * A.dstep, (size_t)nb * dfstride, cudaMemcpyHostToDevice, h->copy_stream));
+        if (A.dstep == dpitch) ORBX_CUDA(h, cudaMemcpyAsync(d_d, (const uint8_t *)A.depth + (size_t)f0 * height * A.dstep, (size_t)nb * dfstride, cudaMemcpyHostToDevice, cs));
         else for (int f = 0; f < nb; f++)
             ORBX_CUDA(h, cudaMemcpy2DAsync(d_d + (size_t)f * dfstride, dpitch, (const uint8_t *)A.depth + (size_t)(f0 + f) * height * A.dstep, A.dstep,
-                                           (size_t)width * 2, (size_t)height, cudaMemcpyHostToDevice, h->copy_stream));
+                                           (size_t)width * 2, (size_t)height, cudaMemcpyHostToDevice, cs));
     }
-    ORBX_CUDA(h, cudaEventRecord(h->ev_in[slot], h->copy_stream));
+    ORBX_CUDA(h, cudaEventRecord(h->ev_in[slot], cs));
     // ---- kernels (main stream): the output slot is free once the D2H of the chunk that used it last is done ----
     ORBX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_in[slot], 0));
     ORBX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_out[slot], 0));
@@ -645,19 +648,19 @@ static orbx_status enqueue_chunk(orbx_handle *h, const BatchArgs &A, int f0, int
     if (st != ORBX_OK) return st;
     ORBX_CUDA(h, cudaEventRecord(h->ev_comp[slot], h->stream));
     // ---- D2H (out stream) ----
-    ORBX_CUDA(h, cudaStreamWaitEvent(h->out_stream, h->ev_comp[slot], 0));
-    ORBX_CUDA(h, cudaMemcpyAsync(A.counts + f0, o_c, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, h->out_stream));
+    ORBX_CUDA(h, cudaStreamWaitEvent(os, h->ev_comp[slot], 0));
+    ORBX_CUDA(h, cudaMemcpyAsync(A.counts + f0, o_c, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, os));
     ORBX_CUDA(h, cudaMemcpy2DAsync(A.kps + (size_t)f0 * A.cap, (size_t)A.cap * sizeof(orbx_keypoint), o_k, (size_t)h->max_kp * sizeof(orbx_keypoint),
-                                   (size_t)kcap * sizeof(orbx_keypoint), (size_t)nb, cudaMemcpyDeviceToHost, h->out_stream));
+                                   (size_t)kcap * sizeof(orbx_keypoint), (size_t)nb, cudaMemcpyDeviceToHost, os));
     ORBX_CUDA(h, cudaMemcpy2DAsync(A.desc + (size_t)f0 * A.cap * ORBX_DESC_BYTES, (size_t)A.cap * ORBX_DESC_BYTES, o_d, (size_t)h->max_kp * ORBX_DESC_BYTES,
-                                   (size_t)kcap * ORBX_DESC_BYTES, (size_t)nb, cudaMemcpyDeviceToHost, h->out_stream));
+                                   (size_t)kcap * ORBX_DESC_BYTES, (size_t)nb, cudaMemcpyDeviceToHost, os));
     if (A.track) {
-        ORBX_CUDA(h, cudaMemcpyAsync(A.mcounts + f0, d_mc, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, h->out_stream));
+        ORBX_CUDA(h, cudaMemcpyAsync(A.mcounts + f0, d_mc, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, os));
         ORBX_CUDA(h, cudaMemcpy2DAsync(A.matches + (size_t)f0 * A.cap, (size_t)A.cap * sizeof(orbx_dmatch), d_m, (size_t)h->max_kp * sizeof(orbx_dmatch),
-                                       (size_t)kcap * sizeof(orbx_dmatch), (size_t)nb, cudaMemcpyDeviceToHost, h->out_stream));
+                                       (size_t)kcap * sizeof(orbx_dmatch), (size_t)nb, cudaMemcpyDeviceToHost, os));
     }
-    ORBX_CUDA(h, cudaMemcpyAsync(h->h_status + 1 + slot, h->d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, h->out_stream));
-    ORBX_CUDA(h, cudaEventRecord(h->ev_out[slot], h->out_stream));
+    ORBX_CUDA(h, cudaMemcpyAsync(h->h_status + 1 + slot, h->d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, os));
+    ORBX_CUDA(h, cudaEventRecord(h->ev_out[slot], os));
     h->seq++;
     return ORBX_OK;
 }
@@ -691,11 +694,12 @@ static orbx_status host_batch(orbx_handle *h, const BatchArgs &A, int nframes)
     orbx_status st = set_geometry(h, A.width, A.height);
     if (st != ORBX_OK) return st;
     const int C = h->chunk;
+    const bool inl = nframes <= C && nframes <= 4;
     for (int f0 = 0; f0 < nframes; f0 += C) {
         const int nb = std::min(C, nframes - f0);
-        if ((st = enqueue_chunk(h, A, f0, nb)) != ORBX_OK) { drain_all(h); return st; }
+        if ((st = enqueue_chunk(h, A, f0, nb, inl)) != ORBX_OK) { drain_all(h); return st; }
     }
-    ORBX_CUDA(h, cudaStreamSynchronize(h->out_stream));
+    ORBX_CUDA(h, cudaStreamSynchronize(inl ? h->stream : h->out_stream));
     if ((st = finish_slot(h, 0, A.counts, nframes, A.cap)) != ORBX_OK) return st;
     return finish_slot(h, 1, A.counts, 0, A.cap);
 }
