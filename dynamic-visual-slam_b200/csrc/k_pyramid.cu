@@ -49,6 +49,35 @@ __device__ __forceinline__ uint32_t rz_vpack(int b0, int b1, const int (&t0)[4],
     return __byte_perm(s01 >> 2, s23 >> 2, 0x6420);
 }
 
+// horizontal pass of four adjacent output columns on one source row: (S[o] * a0 + S[o + 1] * a1) >> 4 each.
+// The four byte pairs lie within 8 bytes of the first one (scale <= 2): three aligned words, two funnel shifts that bring byte o[0] to
+// the front, then per column one PRMT (its pair into the low half) and one IDP.2A against the packed coefficients — 3 LDS + 10 ALU
+// instead of 8 byte loads + 8 IMAD.  Steeper scales take the byte-wise path.
+struct RzCols { int o[4], a0[4], a1[4]; int wofs, sh; uint32_t sel[4], cf[4]; };
+__device__ __forceinline__ void rz_cols_finish(RzCols &c)
+{
+    c.wofs = c.o[0] & ~3; c.sh = 8 * (c.o[0] & 3);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int d = min(c.o[i] - c.o[0], 6);
+        c.sel[i] = (uint32_t)d | ((uint32_t)(d + 1) << 4);
+        c.cf[i] = (uint32_t)(c.a0[i] & 0xFFFF) | ((uint32_t)c.a1[i] << 16);
+    }
+}
+__device__ __forceinline__ void rz_hrow(const uint8_t *q, const RzCols &c, bool bytewise, int (&t)[4])
+{
+    if (bytewise) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) t[i] = ((int)q[c.o[i]] * c.a0[i] + (int)q[c.o[i] + 1] * c.a1[i]) >> 4;
+        return;
+    }
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(q + c.wofs);
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    const uint32_t A = __funnelshift_r(w0, w1, c.sh), B = __funnelshift_r(w1, w2, c.sh);
+#pragma unroll
+    for (int i = 0; i < 4; i++) t[i] = (int)(__dp2a_lo(c.cf[i], __byte_perm(A, B, c.sel[i]), 0u) >> 4);
+}
+
 __global__ void __launch_bounds__(RZ_THREADS) k_resize_linear(const __grid_constant__ LevelMaps M, ResizeParams P)
 {
     extern __shared__ __align__(128) uint8_t s_raw[];
@@ -82,12 +111,14 @@ __global__ void __launch_bounds__(RZ_THREADS) k_resize_linear(const __grid_const
     const int x4 = x0 + 4 * grp;
     // horizontal table entries of the 4 columns: byte offsets inside the staged window (the right neighbour of the last
     // source column has coefficient 0, App. A.1) and the two coefficients
-    int o[4], a0[4], a1[4];
+    RzCols C;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const ResizeTab tx = P.xtab[min(x4 + i, P.dw - 1)];
-        o[i] = tx.ofs - abase; a0[i] = tx.a0; a1[i] = tx.a1;
+        C.o[i] = tx.ofs - abase; C.a0[i] = tx.a0; C.a1[i] = tx.a1;
     }
+    rz_cols_finish(C);
+    const bool bytewise = P.sw > 2 * P.dw;
     __syncthreads();                                                                 // barrier initialised, row table staged
     mbar_wait(&s_bar, 0);
     if (x4 > x1) return;
@@ -102,17 +133,13 @@ __global__ void __launch_bounds__(RZ_THREADS) k_resize_linear(const __grid_const
 #pragma unroll
             for (int i = 0; i < 4; i++) t0[i] = tp[i];
         } else {
-            const uint8_t *q = s_img + e.x;
-#pragma unroll
-            for (int i = 0; i < 4; i++) t0[i] = ((int)q[o[i]] * a0[i] + (int)q[o[i] + 1] * a1[i]) >> 4;
+            rz_hrow(s_img + e.x, C, bytewise, t0);
         }
         if (e.y == e.x) {
 #pragma unroll
             for (int i = 0; i < 4; i++) t1[i] = t0[i];
         } else {
-            const uint8_t *q = s_img + e.y;
-#pragma unroll
-            for (int i = 0; i < 4; i++) t1[i] = ((int)q[o[i]] * a0[i] + (int)q[o[i] + 1] * a1[i]) >> 4;
+            rz_hrow(s_img + e.y, C, bytewise, t1);
         }
         prev_off = e.y;
 #pragma unroll
@@ -168,12 +195,14 @@ __global__ void __launch_bounds__(RZ_THREADS) k_pyramid_all(const __grid_constan
                 s_rt[r] = make_int4((sy0 - sylo) * ORBX_TMA_BOX_BYTES, (sy1 - sylo) * ORBX_TMA_BOX_BYTES, ty.a0, ty.a1);
             }
             const int x4 = x0 + 4 * grp;
-            int o[4], a0[4], a1[4];
+            RzCols C;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const ResizeTab tx = xtab[min(x4 + i, dw - 1)];
-                o[i] = tx.ofs - abase; a0[i] = tx.a0; a1[i] = tx.a1;
+                C.o[i] = tx.ofs - abase; C.a0[i] = tx.a0; C.a1[i] = tx.a1;
             }
+            rz_cols_finish(C);
+            const bool bytewise = gs.w > 2 * dw;
             __syncthreads();                                                         // row table staged
             mbar_wait(&s_bar, loads & 1u);
             loads++;
@@ -189,17 +218,13 @@ __global__ void __launch_bounds__(RZ_THREADS) k_pyramid_all(const __grid_constan
 #pragma unroll
                         for (int i = 0; i < 4; i++) t0[i] = tp[i];
                     } else {
-                        const uint8_t *q = s_img + e.x;
-#pragma unroll
-                        for (int i = 0; i < 4; i++) t0[i] = ((int)q[o[i]] * a0[i] + (int)q[o[i] + 1] * a1[i]) >> 4;
+                        rz_hrow(s_img + e.x, C, bytewise, t0);
                     }
                     if (e.y == e.x) {
 #pragma unroll
                         for (int i = 0; i < 4; i++) t1[i] = t0[i];
                     } else {
-                        const uint8_t *q = s_img + e.y;
-#pragma unroll
-                        for (int i = 0; i < 4; i++) t1[i] = ((int)q[o[i]] * a0[i] + (int)q[o[i] + 1] * a1[i]) >> 4;
+                        rz_hrow(s_img + e.y, C, bytewise, t1);
                     }
                     prev_off = e.y;
 #pragma unroll
@@ -224,7 +249,7 @@ int launch_pyramid(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_ste
     const FrameGeom &G = h->geo;
     if (G.nlevels < 2) return 0;
     if (orbx_ensure_tmaps(h, nframes, l0, l0_step, l0_fstride) != 0) return -1;
-    const size_t smem = 128 + (size_t)ORBX_RZ_BOX_ROWS * ORBX_TMA_BOX_BYTES;
+    const size_t smem = 128 + (size_t)ORBX_RZ_BOX_ROWS * ORBX_TMA_BOX_BYTES + 16;      // + the third word rz_hrow may read past the last row
     if (h->pyr_grid_cap == 0) {
         int coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
@@ -269,7 +294,7 @@ int launch_resize_level(orbx_handle *h, int level, int nframes, const uint8_t *l
     P.sw = gs.w; P.sh = gs.h; P.dw = gd.w; P.dh = gd.h;
     P.xtab = h->d_xtab + gd.xtab_off; P.ytab = h->d_ytab + gd.ytab_off;
     P.tw = h->geo.rz_tw; P.th = h->geo.rz_th; P.src_level = level - 1;
-    const size_t smem = 128 + (size_t)ORBX_RZ_BOX_ROWS * ORBX_TMA_BOX_BYTES;
+    const size_t smem = 128 + (size_t)ORBX_RZ_BOX_ROWS * ORBX_TMA_BOX_BYTES + 16;      // + the third word rz_hrow may read past the last row
     if (!h->rz_configured) { cudaFuncSetAttribute(k_resize_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); h->rz_configured = true; }
     dim3 grid((gd.w + P.tw - 1) / P.tw, (gd.h + P.th - 1) / P.th, nframes);
     ProfScope ps(h, ORBX_K_RESIZE);
