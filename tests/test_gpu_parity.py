@@ -82,7 +82,9 @@ def test_full_hd_and_other_parameters(built, oracle):
     """1920x1080 and non-default extractor parameters (nfeatures, scale factor, levels, thresholds) stay bit-exact."""
     import orbx
     for (w, h, kw) in [(1920, 1080, dict()), (960, 540, dict(nfeatures=2000, scaleFactor=1.3, nlevels=6, iniThFAST=30, minThFAST=10)),
-                       (800, 600, dict(nfeatures=500, scaleFactor=1.1, nlevels=10, iniThFAST=12, minThFAST=5))]:
+                       (800, 600, dict(nfeatures=500, scaleFactor=1.1, nlevels=10, iniThFAST=12, minThFAST=5)),
+                       # scale 1.9: the widest byte span the word-based horizontal pass of the resize takes; 2.5: its byte-wise path
+                       (1280, 720, dict(nfeatures=800, scaleFactor=1.9, nlevels=4)), (1280, 720, dict(nfeatures=800, scaleFactor=2.5, nlevels=3))]:
         e = orbx.ORBextractor(max_width=w, max_height=h, **kw)
         try:
             g = oracle.synth_gray(31, 1, w, h)
