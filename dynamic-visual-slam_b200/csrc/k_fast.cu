@@ -8,25 +8,31 @@
 //
 // Design.  The reference's unit of work is the CELL (FAST, NMS and the threshold retry all run on one cell ROI), and here a
 // cell is owned by ONE WARP from start to finish: there is no block barrier anywhere in the kernel.
-//   * persistent one-warp CTAs loop over the (frame, level, cell) items of the whole batch (host-built cell table);
+//   * persistent one-warp CTAs; after its first cell a warp DRAWS its next (frame, level, cell) items from a global counter — cell
+//     cost varies by an order of magnitude, a static split left a third of the warps idle at the end;
+//   * a cell is described by a host-built 32-byte record (orbx_build_fast_cells): tile coordinates, detection area, sweep-unit
+//     shape, output list — two LDG.128 instead of ~250 instructions of address arithmetic per cell;
 //   * the cell's ROI (+3 px ring margin, 16-byte aligned start) arrives in the warp's shared memory by TMA
-//     (cp.async.bulk.tensor.3d, one descriptor per pyramid level, frames as the third tensor dimension); the next
-//     cell's window is prefetched into L2 (cp.async.bulk.prefetch.tensor) while the current one is processed;
-//   1. packed sweep: a sweep unit is one aligned 32-bit word of the tile (4 adjacent pixels) x 7 rows, walked with a
-//      7-row register window (3 LDS.32 + 4 PRMT per row of 4 pixels); lanes take the cell's units round-robin.  Per row it
+//     (cp.async.bulk.tensor.3d, one descriptor per pyramid level, frames as the third tensor dimension); software pipeline: the
+//     draw for the cell after next is in flight during the sweep, the next cell's window is prefetched into L2
+//     (cp.async.bulk.prefetch.tensor) and loaded as soon as the tile is free, and a cell's corners go to the global list one
+//     cell later, when the counter atomic that reserved their slots has long returned;
+//   1. packed sweep: a sweep unit is one aligned 32-bit word of the tile (4 adjacent pixels) x R rows, R <= 16 picked per cell
+//      shape on the host so that the cell is as few full warp iterations as possible (a 37-row cell: 30 units of 13 rows = ONE
+//      iteration); a unit is walked with a 7-row register window (3 LDS.32 + 4 PRMT per row of 4 pixels).  Per row it
 //      evaluates a polarity-agnostic pre-test on the four opposite ring pairs (0,8) (4,12) (2,10) (6,14):
 //      |I(ring) - I(p)| for 4 pixels is ONE VABSDIFF4.U8; "some member of the pair differs by more than T"
 //      with T = 2^k - 1 <= th is an OR, a mask and one add per pair (SWAR, no per-byte compares).  Every
 //      9-arc contains a member of each opposite pair, so the test is an exact NECESSARY condition for
-//      S > th; it is loose by design (T <= th, sign ignored) and passes ~5 % of the pixels.  Survivors are
-//      compacted into the warp's queue with shuffle prefix sums;
+//      S > th; it is loose by design (T <= th, sign ignored) and passes ~5 % of the pixels.  A lane's survivors (two flag
+//      words, rows 0-7 and 8-15) take slots of the warp's queue with one shared-memory atomic;
 //   2. exact score of the queued survivors, dense over the lanes: the 16-arc min/max network runs on packed
 //      u16x2 lanes (VIMNMX3.U16x2): low half = ring value, high half = 255 - ring value, so one instruction
 //      serves the darker and the brighter polarity;
-//   3. strict 3x3 NMS over the queue entries (scores outside the cell count as 0, as in the reference's per-ROI FAST);
+//   3. strict, branch-free 3x3 NMS over the queue entries against a zero-ringed score map (scores outside the cell count as 0,
+//      as in the reference's per-ROI FAST);
 //   4. a cell with no keypoint at iniThFAST is swept again at minThFAST (the reference's retry) by the same warp.
-// Keypoints are appended to the (frame, level) candidate list with one warp-aggregated global atomic per NMS step;
-// list order is arbitrary (the quadtree kernel is order-independent).
+// List order is arbitrary (the quadtree kernel is order-independent).
 //
 // Toolchain note: an earlier formulation on signed differences (d = I(p) - I(ring), score via
 // max(mn9, -mx9)) produced wrong results on sm_100a with nvcc 12.9 (the negation feeding a fused
@@ -38,7 +44,7 @@
 #include <vector>
 
 // tile pitch TP = TMA box width, a template parameter: 80 bytes when every cell ROI (15 alignment + wCell + 6 + 4) fits, else 96
-// (wCell <= 69).  A 7-row sweep unit may start on the last detection row: the rows it reads past the tile fall into the score map
+// (wCell <= 69).  The last sweep unit of a word column may reach up to 14 rows past the tile: those reads fall into the score map
 // that follows the tile in shared memory (their flags are masked).
 #ifndef FS_WQ
 #define FS_WQ 512                // survivor queue (u16 tile offsets); a sweep step with more survivors than this is scored in place
