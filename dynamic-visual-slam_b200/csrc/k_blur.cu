@@ -2,6 +2,8 @@
 // Replaces `GaussianBlur(workingMat, workingMat, Size(7,7), 2, 2, BORDER_REFLECT_101)` on the cloned
 // level (reference ORBextractor.cpp:1132-1133).  Arithmetic: SURVEY.md App. A.3 — taps
 // [18,34,48,56,48,34,18]/256, row pass in u16, column pass in u32, one rounding (c + 32768) >> 16.
+// Not on the default path any more: the descriptor kernel evaluates the same filter at the pixels it reads (k_describe.cu).  This
+// kernel materialises whole blurred levels for orbx_get_blurred_level and for ORBX_OPT_FUSED_BLUR = 0.
 //
 // HBM-bound stage, all levels of all frames in ONE launch.  A CTA produces a 256 x hCell output tile: its input
 // window (3-px halo, 288 bytes x (hCell + 6) rows) arrives by ONE TMA load (the per-level tensor maps shared with

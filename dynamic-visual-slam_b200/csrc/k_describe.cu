@@ -1,7 +1,9 @@
 // k_describe.cu — intensity-centroid orientation + rBRIEF-256 + keypoint assembly, one warp per keypoint.
 // Replaces IC_Angle / computeOrientation (reference ORBextractor.cpp:76-103, 471-478), computeOrbDescriptor /
 // computeDescriptors (:106-146, 1077-1084), the tail of ComputeKeyPointsOctTree (:874-890) and the
-// per-level assembly loop of operator() (:1123-1164).
+// per-level assembly loop of operator() (:1123-1164).  Two variants: k_describe_fused (default) also evaluates the 7x7 Gaussian of
+// :1132-1133 itself, only at the pixels the descriptor reads, from a staged window of the un-blurred level; k_describe reads a
+// blurred pyramid written by k_blur7 (ORBX_OPT_FUSED_BLUR = 0).  Same bits either way.
 //
 // Floating point on this stage must round exactly like the reference's x86-64 build:
 //   * cv::fastAtan2: fp32 polynomial, every operation rounded on its own (no FMA)   — SURVEY App. A.4
