@@ -30,7 +30,8 @@ struct MatchParams {
     uint32_t row_base;               // global index of train row 0 (database shards)
 };
 
-__global__ void __launch_bounds__(MT_THREADS) k_match_partial(MatchParams P)
+// TOP2 = false (k = 1 without a ratio test or raw top-2 output): only the best row is tracked, one VIMNMX per pair instead of three
+template <bool TOP2> __global__ void __launch_bounds__(MT_THREADS) k_match_partial(MatchParams P)
 {
     __shared__ uint4 s_t[MT_TILE * 2];
     ORBX_PDL_ENTRY();
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(MT_THREADS) k_match_partial(MatchParams P)
         for (int j = 0; j < cnt; j++, key++) {
             const int d = hamming256(q, s_t[2 * j], s_t[2 * j + 1]);
             const uint32_t kk = ((uint32_t)d << MT_KEY_SHIFT) + key;
-            m1 = min(m1, max(m0, kk));
+            if (TOP2) m1 = min(m1, max(m0, kk));
             m0 = min(m0, kk);
         }
     }
@@ -211,7 +212,8 @@ int launch_match_core(orbx_handle *h, const uint8_t *d_q, const int32_t *d_nq, i
         // every slot the epilogue reads (qi < nq, all splits) is written by the partial kernel; splits that
         // start beyond a problem's own nt write the "empty" key
         ProfScope ps(h, ORBX_K_MATCH);
-        orbx_launch_pdl(h, k_match_partial, grid, dim3(MT_THREADS), 0, h->stream, P);
+        if (k == 2 || d_top2) orbx_launch_pdl(h, k_match_partial<true>, grid, dim3(MT_THREADS), 0, h->stream, P);
+        else orbx_launch_pdl(h, k_match_partial<false>, grid, dim3(MT_THREADS), 0, h->stream, P);
     }
     MatchEpiParams E;
     E.part = (const unsigned long long *)h->d_mpart; E.nq_max = nq_max; E.nsplit = nsplit;
