@@ -152,6 +152,43 @@ def test_depth_filter(ex, oracle):
     assert np.array_equal(fd, od)
 
 
+def test_semantic_box_filter(ex, oracle):
+    """BASELINE configs[4] / reference backend.cpp:1011-1029, 746-751: keypoints whose pixel falls in a detection box of a dropped class
+    are removed (first containing box decides, edges inclusive, fp64 compares); combined with the depth filter, order preserved."""
+    w, h = 1280, 720
+    g = oracle.synth_gray(9, 3, w, h)
+    d = oracle.synth_depth(9, 3, w, h)
+    kps, desc = ex(g)
+    boxes = np.zeros(5, oracle.BOX_DTYPE)
+    boxes["cx"], boxes["cy"] = [300.0, 640.0, 700.0, 1000.5, 100.0], [200.0, 360.0, 400.0, 600.25, 650.0]
+    boxes["w"], boxes["h"] = [220.0, 400.0, 500.0, 301.0, 150.0], [180.0, 300.0, 380.0, 200.5, 120.0]
+    boxes["class_id"] = [0, 2, 0, 5, 63]                                  # box 2 overlaps box 1: the first containing box wins
+    # a keypoint exactly on an edge of box 0 must count as inside
+    kx, ky = float(kps["x"][0]), float(kps["y"][0])
+    boxes["cx"][0], boxes["w"][0] = kx - 110.0, 220.0                      # right edge == kx
+    boxes["cy"][0], boxes["h"][0] = ky, 180.0
+
+    def want(mask, depth):
+        k, dsc = (kps, desc) if depth is None else oracle.filter_depth(kps, desc, depth)[:2]
+        keep = []
+        for i in range(len(k)):
+            c = oracle.categorize(float(k["x"][i]), float(k["y"][i]), boxes)
+            keep.append(not (0 <= c < 64 and (mask >> c) & 1))
+        keep = np.array(keep, bool)
+        return k[keep], dsc[keep]
+
+    assert oracle.categorize(kx, ky, boxes) == 0
+    for mask in (1 << 0, 1 << 2, (1 << 0) | (1 << 5) | (1 << 63), 0):
+        for depth in (None, d):
+            gk, gd = ex(g, depth=depth, boxes=boxes, drop_class_mask=mask)
+            wk, wd = want(mask, depth)
+            assert np.array_equal(gk.view(np.uint8), wk.view(np.uint8)) and np.array_equal(gd, wd), (mask, depth is not None)
+            if mask:
+                assert 0 < len(gk) < len(kps)
+    gk, gd = ex(g, boxes=boxes[:0], drop_class_mask=1)                     # no boxes: nothing is labeled, nothing dropped
+    assert np.array_equal(gk.view(np.uint8), kps.view(np.uint8))
+
+
 def test_bgr_ingest(ex, oracle):
     """cvtColor(BGR2GRAY) on the device + extraction == the reference's host-side conversion followed by extraction."""
     import torch
