@@ -301,6 +301,23 @@ def cull_keyframe(response, match_query, max_new=200, min_response=50.0):
     return out[:m].copy()
 
 
+def trig_checksum(first_bits, last_bits, nthreads=0):
+    """Wrapping sums of the bit patterns of cosf / sinf(angle * factorPI) over the float bit patterns [first, last] of the angle (libm)."""
+    a, b = ct.c_uint64(), ct.c_uint64()
+    lib().orc_trig_checksum(ct.c_uint32(first_bits), ct.c_uint32(last_bits), ct.byref(a), ct.byref(b), int(nthreads))
+    return a.value, b.value
+
+
+def cosf(x):
+    return float(lib().orc_cosf(ct.c_float(x)))
+
+
+def sinf(x):
+    lib().orc_sinf.restype = ct.c_float
+    lib().orc_sinf.argtypes = [ct.c_float]
+    return float(lib().orc_sinf(ct.c_float(x)))
+
+
 def introsort_pairs(cnt, ulx):
     n = len(cnt)
     c = np.array(cnt, np.int32)

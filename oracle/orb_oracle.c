@@ -28,6 +28,26 @@ static inline int cv_round_d(double v) { return (int)lrint(v); }
 float orc_cosf(float x) { return cosf(x); }
 float orc_sinf(float x) { return sinf(x); }
 
+/* The trig of computeOrbDescriptor (ORBextractor.cpp:112-113: `angle = kpt.angle * factorPI; a = cos(angle), b = sin(angle)` in float)
+ * over a whole range of float bit patterns of kpt.angle: wrapping sums of the result bit patterns, with this machine's libm.  The CUDA
+ * restatement of glibc's cosf / sinf is pinned against it over every fp32 angle in [0, 360] degrees (tests/test_gpu_parity.py). */
+void orc_trig_checksum(uint32_t first, uint32_t last, uint64_t *sum_cos, uint64_t *sum_sin, int nthreads)
+{
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    const long long total = (long long)last - (long long)first + 1;
+    uint64_t sc = 0, ss = 0;
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for reduction(+ : sc, ss) num_threads(nthreads) schedule(static)
+    for (long long i = 0; i < total; i++) {
+        union { uint32_t u; float f; } d, c, n;
+        d.u = first + (uint32_t)i;
+        const float rad = d.f * factorPI;
+        c.f = cosf(rad); n.f = sinf(rad);
+        sc += c.u; ss += n.u;
+    }
+    *sum_cos = sc; *sum_sin = ss;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* ORBextractor::ORBextractor — ORBextractor.cpp:409-469                                      */
 int orc_extractor_init(orc_extractor *ex, int nfeatures, float scaleFactor, int nlevels,

@@ -125,6 +125,8 @@ void orc_introsort_pairs(int32_t *cnt, int32_t *ulx, int32_t *payload, int n);
 
 float orc_cosf(float x);
 float orc_sinf(float x);
+/* wrapping sums of the bit patterns of cosf / sinf(angle * factorPI) over the float bit patterns [first, last] of `angle` (libm) */
+void orc_trig_checksum(uint32_t first, uint32_t last, uint64_t *sum_cos, uint64_t *sum_sin, int nthreads);
 
 #ifdef __cplusplus
 }

@@ -152,6 +152,25 @@ def test_depth_filter(ex, oracle):
     assert np.array_equal(fd, od)
 
 
+def test_device_trig_and_atan2_pinned(ex, oracle):
+    """The only floating-point steps of the path must round like the reference's x86-64 build: the CUDA restatement of glibc's
+    cosf / sinf against this machine's libm over EVERY fp32 angle in [0, 360] degrees (1.1e9 values, by checksum of the result bit
+    patterns, and element-wise on a sample), and cv::fastAtan2 against the oracle (itself pinned to cv2 and the golden vectors)."""
+    first, last = 0x00000000, int(np.float32(360.0).view(np.uint32))
+    assert ex.test_trig_checksum(first, last) == oracle.trig_checksum(first, last)
+    rng = np.random.default_rng(6)
+    x = np.concatenate([rng.uniform(0, 6.2832, 20000), [0.0, 1e-30, 1e-5, np.pi / 4, np.pi / 2, np.pi, 2 * np.pi, 6.283185]]).astype(np.float32)
+    c, s_ = ex.test_trig(x)
+    wc = np.array([oracle.cosf(float(v)) for v in x], np.float32)
+    ws = np.array([oracle.sinf(float(v)) for v in x], np.float32)
+    assert np.array_equal(c.view(np.uint32), wc.view(np.uint32)) and np.array_equal(s_.view(np.uint32), ws.view(np.uint32))
+    ys = np.concatenate([rng.integers(-2900000, 2900000, 20000), [0, 0, 1, -1, 5, -5, 0, 7]]).astype(np.float32)
+    xs = np.concatenate([rng.integers(-2900000, 2900000, 20000), [0, 1, 0, 0, 5, 5, -3, -7]]).astype(np.float32)
+    got = ex.test_atan2(ys, xs)
+    want = np.array([oracle.fast_atan2(float(a), float(b)) for a, b in zip(ys, xs)], np.float32)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
 def test_semantic_box_filter(ex, oracle):
     """BASELINE configs[4] / reference backend.cpp:1011-1029, 746-751: keypoints whose pixel falls in a detection box of a dropped class
     are removed (first containing box decides, edges inclusive, fp64 compares); combined with the depth filter, order preserved."""
