@@ -115,12 +115,19 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescParams P, cons
     const int lane = threadIdx.x & 31;
     const int nl = G->nlevels;
     int gidx = blockIdx.x * DESC_WARPS + (threadIdx.x >> 5);
-    // locate (level, index in level): levels are concatenated in order (ORBextractor.cpp:1123)
-    int level = -1, k = gidx, total = 0;
-    for (int l = 0; l < nl; l++) {
-        const int c = P.nsel[f * nl + l];
-        if (level < 0) { if (k < c) level = l; else k -= c; }
-        total += c;
+    // locate (level, index in level): levels are concatenated in order (ORBextractor.cpp:1123).  Lane l holds level l's count; an
+    // inclusive warp scan gives the level boundaries, a ballot the level that contains keypoint gidx.
+    int level, k, total;
+    {
+        const int c = lane < nl ? P.nsel[f * nl + lane] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < ORBX_MAX_LEVELS; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        total = __shfl_sync(0xffffffffu, incl, nl - 1);
+        level = __popc(__ballot_sync(0xffffffffu, lane < nl && incl <= gidx));
+        const int before = __shfl_sync(0xffffffffu, incl, max(level - 1, 0));
+        k = gidx - (level > 0 ? before : 0);
+        if (level >= nl) level = -1;
     }
     if (gidx == 0 && lane == 0) {
         P.counts[f] = total <= P.cap ? total : 0;
@@ -245,12 +252,19 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe_fused(DescParams P
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int nl = G->nlevels;
     int gidx = blockIdx.x * DESC_WARPS + wid;
-    // locate (level, index in level): levels are concatenated in order (ORBextractor.cpp:1123)
-    int level = -1, k = gidx, total = 0;
-    for (int l = 0; l < nl; l++) {
-        const int c = P.nsel[f * nl + l];
-        if (level < 0) { if (k < c) level = l; else k -= c; }
-        total += c;
+    // locate (level, index in level): levels are concatenated in order (ORBextractor.cpp:1123).  Lane l holds level l's count; an
+    // inclusive warp scan gives the level boundaries, a ballot the level that contains keypoint gidx.
+    int level, k, total;
+    {
+        const int c = lane < nl ? P.nsel[f * nl + lane] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < ORBX_MAX_LEVELS; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        total = __shfl_sync(0xffffffffu, incl, nl - 1);
+        level = __popc(__ballot_sync(0xffffffffu, lane < nl && incl <= gidx));
+        const int before = __shfl_sync(0xffffffffu, incl, max(level - 1, 0));
+        k = gidx - (level > 0 ? before : 0);
+        if (level >= nl) level = -1;
     }
     if (gidx == 0 && lane == 0) {
         P.counts[f] = total <= P.cap ? total : 0;
