@@ -24,8 +24,8 @@ import time
 
 import numpy as np
 
-if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # NCCL prints its version banner to stdout: keep stdout to the one JSON line
-    os.environ["NCCL_DEBUG"] = "WARN"
+# NCCL prints its version banner (and any debug output) to stdout: send it to stderr, stdout carries the one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "dynamic-visual-slam_b200", "python"))
