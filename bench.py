@@ -24,8 +24,16 @@ import time
 
 import numpy as np
 
-# NCCL prints its version banner (and any debug output) to stdout: send it to stderr, stdout carries the one JSON line
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries the ONE JSON line and nothing else: libraries that chat on file descriptor 1 (NCCL prints its version banner there) are
+# pointed at stderr for the whole run, the line itself goes to a duplicate of the original stdout
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "dynamic-visual-slam_b200", "python"))
@@ -187,7 +195,7 @@ def run_reference(args, rank):
         t += dt
     fps = S * args.steps / t
     sample = "%d frames/step of the synthetic 1280x720 RGB-D stream, extract+filterDepth+match" % S
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -347,7 +355,7 @@ def main():
     if args.kernels_only:
         clocks = sampler.stop()
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+            emit(({"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
                               "ms_per_step": ms / K, "kernels": kernels, "roofline": roofline, "match_roofline": match_roofline,
                               "issue": issue_view((clocks or {}).get("sm_mhz"), torch.cuda.get_device_properties(dev).multi_processor_count),
                               "gpu_launches": int(gpu_launches), "clocks": clocks}))
@@ -510,7 +518,7 @@ def main():
             "association": assoc, "gpu_launches": int(gpu_launches), "clocks": clocks,
             "keypoints_per_frame": float(nkp.mean()), "matches_per_frame": float(nm.mean()),
         }
-        print(json.dumps(out))
+        emit(out)
     for p in hp.values():
         L.orbx_free_pinned(p)
     if dist is not None:
