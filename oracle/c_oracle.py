@@ -69,6 +69,10 @@ def _p(a):
     return a.ctypes.data_as(ct.c_void_p)
 
 
+class GeometryError(ValueError):
+    pass
+
+
 class COracle:
     def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7):
         self.ex = Extractor()
@@ -94,6 +98,10 @@ class COracle:
         lib().orc_level_size(ct.byref(self.ex), w, h, level, ct.byref(lw), ct.byref(lh))
         return lw.value, lh.value
 
+    def geometry_status(self, w, h):
+        """0 = supported; 1/2/3 = the reference throws or faults on this frame size (orc_geometry_status)"""
+        return int(lib().orc_geometry_status(ct.byref(self.ex), int(w), int(h)))
+
     def extract(self, gray, cap=20000, trace=False):
         gray = np.ascontiguousarray(gray, dtype=np.uint8)
         h, w = gray.shape
@@ -111,6 +119,8 @@ class COracle:
             tr.pyramid, tr.blurred, tr.cands, tr.cand_cap = _p(bufs["pyr"]), _p(bufs["blur"]), _p(bufs["cands"]), cand_cap
         n = lib().orc_extract(ct.byref(self.ex), _p(gray), w, h, ct.c_size_t(gray.strides[0]), _p(kps), _p(desc), cap,
                               ct.byref(tr) if tr is not None else None)
+        if n == -3:
+            raise GeometryError("frame size %dx%d is outside the reference's defined domain (status %d)" % (w, h, self.geometry_status(w, h)))
         if n < 0:
             raise RuntimeError("orc_extract failed: %d" % n)
         out = dict(kps=kps[:n].copy(), desc=desc[:n].copy())

@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """gen_golden.py — writes the golden vectors under tests/golden/ (TEST INFRASTRUCTURE).
 
-Runs in the build container only: it drives python cv2 (4.13.0) — the same OpenCV primitives the
+Runs in the build container only: it needs /root/reference (compiled unmodified into oracle/_ref, see oracle/Makefile) and
+python cv2; every extraction vector is asserted identical between the two before it is written.  It drives python cv2 (4.13.0) — the same OpenCV primitives the
 reference calls (cv::resize INTER_LINEAR, cv::FAST, cv::GaussianBlur, cv::fastAtan2,
 cv::BFMatcher(NORM_HAMMING)) — through oracle/cv_oracle.py, the literal restatement of the reference's
 ORB_SLAM3::ORBextractor (reference dynamic_visual_slam/src/ORBextractor.cpp).  The GPU box has neither
@@ -24,6 +25,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import c_oracle as co          # noqa: E402  (only for the synthetic input generator)
 import cv_oracle as cvo        # noqa: E402
+import ref_oracle as ro        # noqa: E402  (the reference's own ORBextractor.cpp, compiled unmodified: oracle/_ref)
 import cv2                     # noqa: E402
 
 OUT = os.path.join(HERE, "..", "tests", "golden")
@@ -54,6 +56,10 @@ def extract_case(name, img, **meta):
     ex = cvo.ORBextractorCV()
     tr = {}
     tab, desc = ex(img, trace=tr)
+    # every vector written below is ALSO what the compiled reference (oracle/_ref) returns for this input: the two independent
+    # routes — real cv2 primitives under a Python restatement, and the reference's own C++ over restated primitives — must agree
+    r = ro.RefExtractor().extract(img)
+    assert np.array_equal(r["kps"].view(np.uint8), kp_struct(tab).view(np.uint8)) and np.array_equal(r["desc"], desc), name
     cands = [np.array(sorted(c), np.int32).reshape(-1, 3) for c in tr["cands"]]
     np.savez_compressed(
         os.path.join(OUT, name + ".npz"),
@@ -79,6 +85,13 @@ def main():
     _, d1 = extract_case("extract_synth_320x240_s1_f1", co.synth_gray(1, 1, 320, 240), seed=1, frame=1)
     extract_case("extract_synth_417x301_s4_f0", co.synth_gray(4, 0, 417, 301), seed=4, frame=0)
     extract_case("extract_circles_640x480", circles_image(), image=circles_image())   # compresses to a few KB
+    # ---- the benchmark stream (bench.py SEED, 1280x720): per-frame checksums of the compiled reference's output ----
+    seed, frames = 20261018, list(range(32)) + [127, 128, 255, 1023, 4095]
+    ref = ro.RefExtractor()
+    res = [ref.extract(co.synth_gray(seed, f, 1280, 720)) for f in frames]
+    np.savez_compressed(os.path.join(OUT, "ref_stream_1280x720.npz"), seed=seed, frames=np.array(frames, np.int32),
+                        count=np.array([len(r["kps"]) for r in res], np.int32),
+                        kps_crc=np.array([crc(r["kps"]) for r in res], np.uint32), desc_crc=np.array([crc(r["desc"]) for r in res], np.uint32))
     # ---- primitives ----
     rng = np.random.default_rng(12345)
     noise = rng.integers(0, 256, (97, 131), dtype=np.uint8)

@@ -99,6 +99,29 @@ void orc_level_size(const orc_extractor *ex, int w, int h, int level, int *lw, i
     *lh = cv_round_f((float)h * s);
 }
 
+/* Where the reference itself is defined.  For small or very elongated images ORBextractor.cpp leaves defined behaviour:
+ *   1  a level rounds to zero columns or rows: cv::resize throws on the empty dsize (:1174, :1182);
+ *   2  a level has exactly 32 rows (maxBorderY - minBorderY == 0) or borders of opposite sign with |W/H| >= 0.5: the root count
+ *      nIni (:559) is infinite or negative and vpIniNodes.resize(nIni) throws std::length_error (:566) — observed with the compiled
+ *      reference (oracle/_ref; tests/test_oracle_vs_ref.py);
+ *   3  a level holds FAST cells but W/H < 0.5 rounds to nIni = 0 roots: vpIniNodes[...] indexes an empty vector (:586).
+ * 0 = supported: every division of the reference is finite where its result is used.  The CUDA library applies the same rule
+ * (ORBX_E_UNSUPPORTED) so that the two fail on exactly the same inputs. */
+int orc_geometry_status(const orc_extractor *ex, int w, int h)
+{
+    for (int l = 0; l < ex->nlevels; l++) {
+        int lw, lh;
+        orc_level_size(ex, w, h, l, &lw, &lh);
+        if (lw <= 0 || lh <= 0) return 1;
+        const int Wb = lw - 2 * (EDGE_THRESHOLD - 3), Hb = lh - 2 * (EDGE_THRESHOLD - 3);
+        if (Hb == 0) return 2;
+        const int nIni = (int)roundf((float)Wb / (float)Hb);
+        if (nIni < 0) return 2;
+        if (nIni == 0 && Wb >= 35 && Hb >= 35) return 3;
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* cv::resize(..., INTER_LINEAR) on CV_8UC1 — called at ORBextractor.cpp:1182.  SURVEY App. A.1 */
 void orc_resize_tables(int ssize, int dsize, int32_t *ofs, int16_t *coef, int horizontal)
@@ -718,6 +741,7 @@ int orc_extract(const orc_extractor *ex, const uint8_t *gray, int w, int h, size
                 orc_keypoint *kps, uint8_t *desc, int cap, orc_trace *tr)
 {
     if (!gray || w <= 0 || h <= 0) return -1;                                  /* :1090-1091 */
+    if (orc_geometry_status(ex, w, h) != 0) return -3;                         /* the reference throws or faults here */
     const int nl = ex->nlevels;
     int lw[ORC_MAX_LEVELS] = {0}, lh[ORC_MAX_LEVELS] = {0};
     uint8_t *pyr[ORC_MAX_LEVELS];

@@ -55,6 +55,8 @@ typedef struct {
 int  orc_extractor_init(orc_extractor *ex, int nfeatures, float scaleFactor, int nlevels,
                         int iniThFAST, int minThFAST);
 void orc_level_size(const orc_extractor *ex, int w, int h, int level, int *lw, int *lh);
+/* 0 = the reference's arithmetic is defined for this frame size; 1/2/3 = it throws or faults (see orb_oracle.c) */
+int  orc_geometry_status(const orc_extractor *ex, int w, int h);
 
 void orc_resize_linear(const uint8_t *src, int sw, int sh, size_t sstep,
                        uint8_t *dst, int dw, int dh, size_t dstep);
@@ -72,7 +74,7 @@ float orc_ic_angle(const uint8_t *img, size_t step, int cx, int cy, const int *u
 void orc_gaussian_blur7(const uint8_t *src, int w, int h, size_t sstep, uint8_t *dst, size_t dstep);
 void orc_descriptor(const uint8_t *blur, size_t step, int cx, int cy, float angle_deg, uint8_t *desc32);
 
-/* ORBextractor::operator() ; returns keypoint count, -1 on empty image, -2 capacity */
+/* ORBextractor::operator() ; returns keypoint count, -1 on empty image, -2 capacity, -3 frame size outside the reference's defined domain */
 int  orc_extract(const orc_extractor *ex, const uint8_t *gray, int w, int h, size_t step,
                  orc_keypoint *kps, uint8_t *desc, int cap, orc_trace *trace);
 /* frame-parallel (OpenMP) batch, used by the CPU baseline: frames tightly packed */
