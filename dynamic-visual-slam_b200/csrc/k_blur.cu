@@ -131,7 +131,7 @@ int launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, 
     P.tiles = h->d_blur_tiles + tile_first;
     P.tile_rows = h->geo.max_hcell + 6;
     const size_t smem = 128 + (size_t)(P.tile_rows + BL_PADROWS) * ORBX_TMA_BOX_BYTES;
-    if (smem > h->blur_smem) { cudaFuncSetAttribute(k_blur7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); h->blur_smem = smem; }
+    if (!orbx_optin_smem(h, (const void *)k_blur7, smem)) return -1;
     dim3 grid(ntiles, nframes);
     ProfScope ps(h, ORBX_K_BLUR, st);
     k_blur7<<<grid, BL_THREADS, smem, st>>>(M, P, h->d_geo);

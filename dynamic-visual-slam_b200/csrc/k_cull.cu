@@ -112,10 +112,7 @@ int launch_cull(orbx_handle *h, const orbx_keypoint *d_kps, const uint8_t *d_des
     P.out_kps = d_out_kps; P.out_desc = d_out_desc; P.out_index = d_out_index; P.cap = cap; P.n_out = d_n_out; P.status = h->d_status;
     P.range_cap = n / 16 + 4;
     const size_t smem = cull_smem_bytes(n, P.range_cap);
-    if (smem > h->cull_smem) {
-        if (cudaFuncSetAttribute(k_cull, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        h->cull_smem = smem;
-    }
+    if (!orbx_optin_smem(h, (const void *)k_cull, smem)) return -1;
     ProfScope ps(h, ORBX_K_OTHER);
     k_cull<<<1, CULL_THREADS, smem, h->stream>>>(P);
     return 0;

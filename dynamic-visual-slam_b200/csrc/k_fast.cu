@@ -480,7 +480,7 @@ int launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, 
     const size_t smem = 128 + 128 + (size_t)(((P.tile_rows * TP) + 127) & ~127) + map_bytes + FS_WQ * 2;
     auto kern = TP == 80 ? k_fast_cells<80> : k_fast_cells<96>;
     if (smem != h->fast_smem || TP != h->fast_tp) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (!orbx_optin_smem(h, (const void *)kern, smem)) return -1;
         int occ = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem);
         h->fast_grid_cap = std::max(1, occ) * h->sm_count; h->fast_smem = smem; h->fast_tp = TP;

@@ -13,7 +13,7 @@ struct FilterParams {
     const orbx_keypoint *kin; const uint8_t *din; const int32_t *nin; int cap_in;
     const uint16_t *depth; size_t dstep, dfstride; int dw, dh;     // steps in BYTES
     float dmin, dmax;
-    const orbx_box *boxes; int nboxes; unsigned long long drop_mask;
+    const orbx_box *boxes; const int32_t *box_offsets; int box_base; int nboxes; unsigned long long drop_mask;   // box_offsets (nullable): frame f owns boxes [off[f], off[f+1])
     orbx_keypoint *kout; uint8_t *dout; int32_t *nout; int cap_out;
     int32_t *status;
 };
@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(1024) k_filter(FilterParams P)
             }
             if (keep && P.nboxes > 0) {
                 const double px = (double)kp.x, py = (double)kp.y;
-                for (int b = 0; b < P.nboxes; b++) {
+                const int b0 = P.box_offsets ? P.box_offsets[f] - P.box_base : 0, b1 = P.box_offsets ? P.box_offsets[f + 1] - P.box_base : P.nboxes;
+                for (int b = b0; b < b1; b++) {
                     const orbx_box bx = P.boxes[b];
                     if (px >= bx.cx - bx.w / 2 && px <= bx.cx + bx.w / 2 && py >= bx.cy - bx.h / 2 && py <= bx.cy + bx.h / 2) {
                         if (bx.class_id >= 0 && bx.class_id < 64 && ((P.drop_mask >> bx.class_id) & 1ull)) keep = false;
@@ -85,14 +86,14 @@ __global__ void __launch_bounds__(1024) k_filter(FilterParams P)
 }
 
 void launch_filter(orbx_handle *h, int nframes, const uint16_t *d_depth, size_t dstep, size_t dfstride,
-                   const orbx_box *d_boxes, int nboxes, uint64_t drop_mask,
+                   const orbx_box *d_boxes, const int32_t *d_box_offsets, int box_base, int nboxes, uint64_t drop_mask,
                    orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts)
 {
     FilterParams P;
     P.kin = h->d_kps_all; P.din = h->d_desc_all; P.nin = h->d_count_all; P.cap_in = h->max_kp;
     P.depth = d_depth; P.dstep = dstep; P.dfstride = dfstride; P.dw = h->geo.width; P.dh = h->geo.height;
     P.dmin = h->prm.depth_min; P.dmax = h->prm.depth_max;
-    P.boxes = d_boxes; P.nboxes = nboxes; P.drop_mask = drop_mask;
+    P.boxes = d_boxes; P.box_offsets = d_box_offsets; P.box_base = box_base; P.nboxes = nboxes; P.drop_mask = drop_mask;
     P.kout = d_kps; P.dout = d_desc; P.nout = d_counts; P.cap_out = cap; P.status = h->d_status;
     ProfScope ps(h, ORBX_K_FILTER);
     orbx_launch_pdl(h, k_filter, dim3(nframes), dim3(1024), 0, h->stream, P);

@@ -255,9 +255,8 @@ int launch_pyramid(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_ste
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
         h->pyr_grid_cap = -1;
         if (coop) {
-            cudaFuncSetAttribute(k_pyramid_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             int occ = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pyramid_all, RZ_THREADS, smem) == cudaSuccess && occ > 0) h->pyr_grid_cap = occ * h->sm_count;
+            if (orbx_optin_smem(h, (const void *)k_pyramid_all, smem) && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pyramid_all, RZ_THREADS, smem) == cudaSuccess && occ > 0) h->pyr_grid_cap = occ * h->sm_count;
         }
     }
     // measured on B200: the fused launch saves ~35 us of CPU enqueue time and a few us of GPU time per frame at batch 1, but its six
@@ -295,7 +294,7 @@ int launch_resize_level(orbx_handle *h, int level, int nframes, const uint8_t *l
     P.xtab = h->d_xtab + gd.xtab_off; P.ytab = h->d_ytab + gd.ytab_off;
     P.tw = h->geo.rz_tw; P.th = h->geo.rz_th; P.src_level = level - 1;
     const size_t smem = 128 + (size_t)ORBX_RZ_BOX_ROWS * ORBX_TMA_BOX_BYTES + 16;      // + the third word rz_hrow may read past the last row
-    if (!h->rz_configured) { cudaFuncSetAttribute(k_resize_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); h->rz_configured = true; }
+    if (!orbx_optin_smem(h, (const void *)k_resize_linear, smem)) return -1;
     dim3 grid((gd.w + P.tw - 1) / P.tw, (gd.h + P.th - 1) / P.th, nframes);
     ProfScope ps(h, ORBX_K_RESIZE);
     // levels >= 2 directly follow the launch that writes their source: allow them to start while it drains (see the kernel)

@@ -326,6 +326,8 @@ template <int NT> __global__ void __launch_bounds__(NT) k_quadtree(QtParams P, c
     if (threadIdx.x == 0) P.nsel[slot] = L;
 }
 
+static size_t quadtree_smem(int NC);
+size_t orbx_quadtree_smem(int node_cap) { return quadtree_smem(node_cap); }
 static size_t quadtree_smem(int NC)
 {
     size_t per = 3 * (3 * sizeof(unsigned) + 4 * sizeof(short))   // cur, nxt, leaf
@@ -334,7 +336,7 @@ static size_t quadtree_smem(int NC)
     return per * (size_t)NC + 64;
 }
 
-void launch_quadtree_geo(orbx_handle *h, const FrameGeom *d_geo, int nlevels, int nframes, int node_cap, size_t cand_slab, int sel_slab)
+int launch_quadtree_geo(orbx_handle *h, const FrameGeom *d_geo, int nlevels, int nframes, int node_cap, size_t cand_slab, int sel_slab)
 {
     QtParams P;
     P.candA = h->d_cand; P.candB = h->d_cand2; P.ownA = h->d_owner; P.ownB = h->d_owner2; P.tmp = h->d_qtmp;
@@ -343,18 +345,15 @@ void launch_quadtree_geo(orbx_handle *h, const FrameGeom *d_geo, int nlevels, in
     P.node_cap = node_cap;
     const size_t smem = quadtree_smem(node_cap);
     const bool wide = nlevels * nframes <= h->sm_count;                // at most one CTA per SM: latency-bound, use 1024-thread blocks
-    if (smem > 48 * 1024 && smem > h->quad_smem) {
-        cudaFuncSetAttribute(k_quadtree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_quadtree<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        h->quad_smem = smem;
-    }
+    if (!orbx_optin_smem(h, (const void *)k_quadtree<256>, smem) || !orbx_optin_smem(h, (const void *)k_quadtree<1024>, smem)) return -1;
     dim3 grid(nframes, nlevels);
     ProfScope ps(h, ORBX_K_QUADTREE);
     if (wide) orbx_launch_pdl(h, k_quadtree<1024>, grid, dim3(1024), smem, h->stream, P, d_geo);
     else orbx_launch_pdl(h, k_quadtree<256>, grid, dim3(256), smem, h->stream, P, d_geo);
+    return 0;
 }
 
-void launch_quadtree(orbx_handle *h, int nframes)
+int launch_quadtree(orbx_handle *h, int nframes)
 {
-    launch_quadtree_geo(h, h->d_geo, h->geo.nlevels, nframes, h->geo.node_cap_max, h->geo.cand_entries, h->geo.sel_entries);
+    return launch_quadtree_geo(h, h->d_geo, h->geo.nlevels, nframes, h->geo.node_cap_max, h->geo.cand_entries, h->geo.sel_entries);
 }

@@ -15,6 +15,24 @@ static const void *mapped_device_view(const void *host);
 static inline int cv_round_f(float v) { return (int)lrintf(v); }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+bool orbx_optin_smem(orbx_handle *h, const void *func, size_t smem)
+{
+    if (smem <= 48 * 1024) return true;
+    if (smem > h->smem_optin_max) return false;
+    static std::mutex mu;
+    static std::vector<std::pair<std::pair<const void *, int>, size_t>> granted;      // (function, device) -> largest size set
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto &g : granted) if (g.first.first == func && g.first.second == h->device) {
+        if (smem <= g.second) return true;
+        if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return false; }
+        g.second = smem;
+        return true;
+    }
+    if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return false; }
+    granted.push_back({{func, h->device}, smem});
+    return true;
+}
+
 extern "C" const char *orbx_version(void) { return "orbx 0.1 (sm_100a)"; }
 
 extern "C" void orbx_default_params(orbx_params *p)
@@ -92,6 +110,11 @@ static bool build_geometry(const orbx_handle *h, int w, int hgt, FrameGeom &G, s
         if (l > 0) { g.off = off; off += align_up((size_t)g.pitch * g.h, 256); }
         g.bpitch = g.pitch; g.boff = boff; boff += align_up((size_t)g.bpitch * g.h, 256);
         const int W = g.w - 2 * ORBX_BORDER, H = g.h - 2 * ORBX_BORDER;    // maxBorder - minBorder, :786-795
+        // Where the reference itself leaves defined behaviour (pinned against the compiled reference, tests/test_oracle_vs_ref.py,
+        // same rule as oracle orc_geometry_status): a level with exactly 32 rows or with borders of opposite sign makes the root
+        // count nIni (:559) infinite or negative and vpIniNodes.resize(nIni) throws (:566); nIni == 0 with a cell grid indexes an
+        // empty vector (:586, checked below).  Such frame sizes are refused, never approximated.
+        if (H == 0 || (int)roundf((float)W / (float)H) < 0) return false;
         g.scale = h->scale[l];
         g.size = (float)(int)(ORBX_PATCH * h->scale[l]);                  // :880
         g.N = h->nfeat[l];
@@ -180,7 +203,14 @@ static orbx_status set_geometry(orbx_handle *h, int w, int hgt)
     if (w > h->prm.max_width || hgt > h->prm.max_height) { h->err = "frame larger than max_width x max_height"; return ORBX_E_INVALID; }
     if (w > 4096 + 2 * ORBX_BORDER || hgt > 4096 + 2 * ORBX_BORDER) { h->err = "frame larger than 4128 px"; return ORBX_E_UNSUPPORTED; }
     FrameGeom G; std::vector<ResizeTab> xt, yt; std::vector<uint32_t> strips, btiles, ctab;
-    if (!build_geometry(h, w, hgt, G, &xt, &yt, &strips, &btiles, &ctab)) { h->err = "unsupported frame geometry (aspect ratio gives 0 or > 64 quadtree roots, or a level vanishes)"; return ORBX_E_UNSUPPORTED; }
+    if (!build_geometry(h, w, hgt, G, &xt, &yt, &strips, &btiles, &ctab)) { h->err = "unsupported frame geometry: the reference throws or faults here (a pyramid level vanishes, has exactly 32 rows, or its aspect ratio gives a negative or zero quadtree root count, ORBextractor.cpp:559-586), or it has more than 64 roots"; return ORBX_E_UNSUPPORTED; }
+    // the quadtree keeps its node table in shared memory with 16-bit node ids (k_quadtree.cu): refuse here, with a clear message,
+    // what would otherwise surface as a launch failure on the first extraction
+    if (G.node_cap_max >= 65535 || orbx_quadtree_smem(G.node_cap_max) > h->smem_optin_max) {
+        h->err = "nfeatures per level too large for the quadtree's shared-memory node table (" + std::to_string(orbx_quadtree_smem(G.node_cap_max)) +
+                 " bytes needed, " + std::to_string(h->smem_optin_max) + " available per block)";
+        return ORBX_E_UNSUPPORTED;
+    }
     const size_t B = (size_t)h->prm.max_batch;
     if (G.pyr_bytes * B > h->pyr_cap || G.blur_bytes * B > h->blur_cap || G.cand_entries * B > h->cand_cap ||
         (size_t)G.sel_entries * B > h->sel_cap || (int)xt.size() > h->tab_cap || (int)yt.size() > h->tab_cap ||
@@ -210,7 +240,7 @@ extern "C" void orbx_destroy(orbx_handle *h)
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     void *dev[] = { h->d_bgr, h->d_cells, h->d_blur_tiles, h->d_strips, h->d_prev_desc, h->d_prev_count, h->d_geo, h->d_xtab, h->d_ytab, h->d_pyr, h->d_blur, h->d_in, h->d_depth_in, h->d_cand, h->d_cand2, h->d_qtmp,
                     h->d_owner, h->d_owner2, h->d_ncand, h->d_sel, h->d_nsel, h->d_kps_all, h->d_desc_all, h->d_count_all,
-                    h->d_kps_out, h->d_desc_out, h->d_count_out, h->d_boxes, h->d_status, h->d_mpart, h->d_mq, h->d_mt, h->d_mout, h->d_mcount };
+                    h->d_kps_out, h->d_desc_out, h->d_count_out, h->d_boxes, h->d_box_off, h->d_status_base, h->d_mpart, h->d_mq, h->d_mt, h->d_mout, h->d_mcount };
     for (void *p : dev) if (p) cudaFree(p);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_status) cudaFreeHost(h->h_status);
@@ -250,6 +280,7 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     cudaDeviceProp prop;
     CREATE_CUDA(cudaGetDeviceProperties(&prop, p.device));
     h->sm_count = prop.multiProcessorCount;
+    h->smem_optin_max = prop.sharedMemPerBlockOptin;
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);          // (least, greatest): the dependent chain outranks the filler stream
     CREATE_CUDA(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));
@@ -315,11 +346,13 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     CREATE_CUDA(cudaMalloc(&h->d_prev_desc, (size_t)h->max_kp * ORBX_DESC_BYTES));
     CREATE_CUDA(cudaMalloc(&h->d_prev_count, sizeof(int32_t)));
     CREATE_CUDA(cudaMemset(h->d_prev_count, 0, sizeof(int32_t)));
-    h->boxes_cap = 256;
-    CREATE_CUDA(cudaMalloc(&h->d_boxes, h->boxes_cap * sizeof(orbx_box)));
-    CREATE_CUDA(cudaMalloc(&h->d_status, sizeof(int32_t)));
+    h->boxes_cap = std::max<size_t>(256, 16 * B);
+    CREATE_CUDA(cudaMalloc(&h->d_boxes, 2 * (size_t)h->boxes_cap * sizeof(orbx_box)));
+    CREATE_CUDA(cudaMalloc(&h->d_box_off, 2 * (B + 1) * sizeof(int32_t)));
+    CREATE_CUDA(cudaMalloc(&h->d_status_base, 4 * sizeof(int32_t)));
+    h->d_status = h->d_status_base;
     CREATE_CUDA(cudaMalloc(&h->d_mcount, sizeof(int32_t) * 4));
-    CREATE_CUDA(cudaMemset(h->d_status, 0, sizeof(int32_t)));
+    CREATE_CUDA(cudaMemset(h->d_status_base, 0, 4 * sizeof(int32_t)));
     CREATE_CUDA(cudaMemset(h->d_nsel, 0, B * ORBX_MAX_LEVELS * sizeof(int32_t)));
     h->h_out_bytes = B * ((size_t)h->max_kp * (sizeof(orbx_keypoint) + ORBX_DESC_BYTES) + 64);
     CREATE_CUDA(cudaMallocHost(&h->h_out, h->h_out_bytes));
@@ -378,12 +411,24 @@ extern "C" orbx_status orbx_level_size(const orbx_handle *h, int32_t w, int32_t 
 }
 
 // ---- the extraction pipeline: ORBextractor::operator() (ORBextractor.cpp:1086-1167) on nframes frames ----
+// YOLO boxes on the device: one list for the whole call (off == nullptr) or per-frame ranges [off[f], off[f+1]) of `boxes`
+// (`base` is subtracted from the offsets: a pipeline chunk stages only its own boxes)
+struct DevBoxes { const orbx_box *boxes; const int32_t *off; int base; int n; uint64_t drop_mask; };
+static const DevBoxes kNoBoxes = { nullptr, nullptr, 0, 0, 0 };
+
 static orbx_status run_pipeline(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride,
-                                const uint16_t *d_depth, size_t dstep, size_t dfstride,
-                                const orbx_box *d_boxes, int nboxes, uint64_t drop_mask,
+                                const uint16_t *d_depth, size_t dstep, size_t dfstride, const DevBoxes &BX,
                                 orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts)
 {
+    const orbx_box *d_boxes = BX.boxes; const int nboxes = BX.n; const uint64_t drop_mask = BX.drop_mask;
     const int nl = h->geo.nlevels;
+    if (h->geo.total_cells_valid == 0) {
+        // no level holds a FAST cell (every level is narrower than 67 px): the reference's cell loops do not execute and it returns no
+        // keypoints (ORBextractor.cpp:799-806); nothing is launched, the pyramid is not built
+        ORBX_CUDA(h, cudaMemsetAsync(d_counts, 0, (size_t)nframes * sizeof(int32_t), h->stream));
+        h->last_batch = 0;
+        return ORBX_OK;
+    }
     ORBX_CUDA(h, cudaMemsetAsync(h->d_ncand, 0, ((size_t)h->prm.max_batch * ORBX_MAX_LEVELS + 4) * sizeof(int32_t), h->stream));   // corner counts + FAST work counter
     // Schedule.  The main stream carries the dependent chain pyramid -> FAST -> quadtree -> describe; the blur (needed only by
     // describe) runs on the low-priority aux stream as filler: level 0 depends on the input alone and starts beside the
@@ -409,13 +454,13 @@ static orbx_status run_pipeline(orbx_handle *h, int nframes, const uint8_t *l0, 
     }
     h->blur_valid = !h->opt_fused_blur;
     if (side) ORBX_CUDA(h, cudaEventRecord(h->ev_join, h->aux_stream));
-    launch_quadtree(h, nframes);                                                                 // DistributeOctTree
+    if (launch_quadtree(h, nframes) != 0) { h->err = "quadtree node table exceeds the shared-memory opt-in limit"; return ORBX_E_UNSUPPORTED; }   // DistributeOctTree
     if (side) ORBX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     const bool filtered = d_depth != nullptr || nboxes > 0;
     if (!filtered) launch_describe_to(h, nframes, l0, l0_step, l0_fstride, d_kps, d_desc, cap, d_counts);
     else {
         launch_describe_to(h, nframes, l0, l0_step, l0_fstride, h->d_kps_all, h->d_desc_all, h->max_kp, h->d_count_all);
-        launch_filter(h, nframes, d_depth, dstep, dfstride, d_boxes, nboxes, drop_mask, d_kps, d_desc, cap, d_counts);
+        launch_filter(h, nframes, d_depth, dstep, dfstride, d_boxes, BX.off, BX.base, nboxes, drop_mask, d_kps, d_desc, cap, d_counts);
     }
     h->last_batch = nframes; h->last_l0 = l0; h->last_l0_step = l0_step; h->last_l0_fstride = l0_fstride;
     ORBX_CUDA(h, cudaGetLastError());
@@ -427,6 +472,16 @@ extern "C" orbx_status orbx_extract_batch_device(orbx_handle *h, const uint8_t *
                                                  const uint16_t *d_depth, size_t dstep, size_t dframe_stride,
                                                  orbx_keypoint *d_kps, uint8_t *d_desc, int32_t cap, int32_t *d_counts)
 {
+    return orbx_extract_batch_boxes_device(h, d_gray, nframes, width, height, step, frame_stride, d_depth, dstep, dframe_stride,
+                                           nullptr, nullptr, 0, 0, d_kps, d_desc, cap, d_counts);
+}
+
+extern "C" orbx_status orbx_extract_batch_boxes_device(orbx_handle *h, const uint8_t *d_gray, int32_t nframes,
+                                                       int32_t width, int32_t height, size_t step, size_t frame_stride,
+                                                       const uint16_t *d_depth, size_t dstep, size_t dframe_stride,
+                                                       const orbx_box *d_boxes, const int32_t *d_box_offsets, int32_t nboxes_total, uint64_t drop_mask,
+                                                       orbx_keypoint *d_kps, uint8_t *d_desc, int32_t cap, int32_t *d_counts)
+{
     if (!h) return ORBX_E_INVALID;
     cudaSetDevice(h->device);
     if (!d_gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }
@@ -435,7 +490,10 @@ extern "C" orbx_status orbx_extract_batch_device(orbx_handle *h, const uint8_t *
     if (d_depth && ((dstep & 1) || dstep < (size_t)width * 2)) { h->err = "bad depth step"; return ORBX_E_INVALID; }
     orbx_status st = set_geometry(h, width, height);
     if (st != ORBX_OK) return st;
-    return run_pipeline(h, nframes, d_gray, step, frame_stride, d_depth, dstep, dframe_stride, nullptr, 0, 0, d_kps, d_desc, cap, d_counts);
+    if (nboxes_total < 0 || (nboxes_total > 0 && (!d_boxes || !d_box_offsets))) { h->err = "per-frame boxes need the box array and nframes + 1 offsets"; return ORBX_E_INVALID; }
+    if (nboxes_total > 0 && cap > h->max_kp) { h->err = "cap_per_frame larger than the handle's max_keypoints"; return ORBX_E_INVALID; }
+    const DevBoxes BX = { d_boxes, d_box_offsets, 0, nboxes_total, drop_mask };
+    return run_pipeline(h, nframes, d_gray, step, frame_stride, d_depth, dstep, dframe_stride, BX, d_kps, d_desc, cap, d_counts);
 }
 
 static orbx_status extract_one(orbx_handle *h, bool is_bgr, const uint8_t *gray, int32_t width, int32_t height, size_t step,
@@ -447,6 +505,7 @@ static orbx_status extract_one(orbx_handle *h, bool is_bgr, const uint8_t *gray,
     if (n_out) *n_out = 0;
     if (!gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }        // ORBextractor.cpp:1090-1091
     if (!kps || !desc || !n_out || cap < 0 || step < (size_t)width * (is_bgr ? 3 : 1) || nboxes < 0 || (nboxes > 0 && !boxes)) { h->err = "bad arguments"; return ORBX_E_INVALID; }
+    if (depth && (dstep < (size_t)width * 2 || (dstep & 1) || ((uintptr_t)depth & 1))) { h->err = "bad depth buffer: rows of at least 2*width bytes, even step, 2-byte aligned"; return ORBX_E_INVALID; }
     if (h->pending[0].active || h->pending[1].active) { h->err = "an asynchronous batch is outstanding: call orbx_batch_wait first"; return ORBX_E_INVALID; }
     orbx_status st = set_geometry(h, width, height);
     if (st != ORBX_OK) return st;
@@ -464,12 +523,13 @@ static orbx_status extract_one(orbx_handle *h, bool is_bgr, const uint8_t *gray,
         if (nboxes > h->boxes_cap) {
             cudaStreamSynchronize(h->stream);
             cudaFree(h->d_boxes); h->d_boxes = nullptr; h->boxes_cap = 0;
-            ORBX_CUDA(h, cudaMalloc(&h->d_boxes, (size_t)nboxes * sizeof(orbx_box)));
+            ORBX_CUDA(h, cudaMalloc(&h->d_boxes, 2 * (size_t)nboxes * sizeof(orbx_box)));
             h->boxes_cap = nboxes;
         }
         ORBX_CUDA(h, cudaMemcpyAsync(h->d_boxes, boxes, (size_t)nboxes * sizeof(orbx_box), cudaMemcpyHostToDevice, h->stream));
     }
-    st = run_pipeline(h, 1, h->d_in, pitch, 0, depth_zc ? depth_zc : (depth ? h->d_depth_in : nullptr), depth_zc ? dstep : dpitch, 0, h->d_boxes, nboxes, drop_mask,
+    const DevBoxes BX = { h->d_boxes, nullptr, 0, nboxes, drop_mask };
+    st = run_pipeline(h, 1, h->d_in, pitch, 0, depth_zc ? depth_zc : (depth ? h->d_depth_in : nullptr), depth_zc ? dstep : dpitch, 0, BX,
                       h->d_kps_out, h->d_desc_out, h->max_kp, h->d_count_out);
     if (st != ORBX_OK) return st;
     // one packed D2H: [count | keypoints | descriptors] for min(cap, max_kp) entries
@@ -531,12 +591,12 @@ extern "C" void orbx_track_reset(orbx_handle *h)
 }
 
 static orbx_status track_device(orbx_handle *h, const uint8_t *d_gray, int nframes, int width, int height, size_t step, size_t fstride,
-                                const uint16_t *d_depth, size_t dstep, size_t dfstride,
+                                const uint16_t *d_depth, size_t dstep, size_t dfstride, const DevBoxes &BX,
                                 orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts,
                                 orbx_dmatch *d_matches, int32_t *d_mcounts, float max_dist)
 {
     if (cap > h->max_kp) { h->err = "cap_per_frame larger than the handle's max_keypoints"; return ORBX_E_INVALID; }
-    orbx_status st = run_pipeline(h, nframes, d_gray, step, fstride, d_depth, dstep, dfstride, nullptr, 0, 0, d_kps, d_desc, cap, d_counts);
+    orbx_status st = run_pipeline(h, nframes, d_gray, step, fstride, d_depth, dstep, dfstride, BX, d_kps, d_desc, cap, d_counts);
     if (st != ORBX_OK) return st;
     // frame 0 against the carried state (prev count is 0 on the first frame => no matches, count 0)
     if (launch_match_core(h, d_desc, d_counts, cap, 0, h->d_prev_desc, h->d_prev_count, h->max_kp, 0, nullptr, nullptr, 1, 0,
@@ -560,6 +620,17 @@ extern "C" orbx_status orbx_track_batch_device(orbx_handle *h, const uint8_t *d_
                                                orbx_keypoint *d_kps, uint8_t *d_desc, int32_t cap, int32_t *d_counts,
                                                orbx_dmatch *d_matches, int32_t *d_mcounts, float max_dist)
 {
+    return orbx_track_batch_boxes_device(h, d_gray, nframes, width, height, step, frame_stride, d_depth, dstep, dframe_stride,
+                                         nullptr, nullptr, 0, 0, d_kps, d_desc, cap, d_counts, d_matches, d_mcounts, max_dist);
+}
+
+extern "C" orbx_status orbx_track_batch_boxes_device(orbx_handle *h, const uint8_t *d_gray, int32_t nframes,
+                                                     int32_t width, int32_t height, size_t step, size_t frame_stride,
+                                                     const uint16_t *d_depth, size_t dstep, size_t dframe_stride,
+                                                     const orbx_box *d_boxes, const int32_t *d_box_offsets, int32_t nboxes_total, uint64_t drop_mask,
+                                                     orbx_keypoint *d_kps, uint8_t *d_desc, int32_t cap, int32_t *d_counts,
+                                                     orbx_dmatch *d_matches, int32_t *d_mcounts, float max_dist)
+{
     if (!h) return ORBX_E_INVALID;
     cudaSetDevice(h->device);
     if (!d_gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }
@@ -568,7 +639,9 @@ extern "C" orbx_status orbx_track_batch_device(orbx_handle *h, const uint8_t *d_
     if (d_depth && ((dstep & 1) || dstep < (size_t)width * 2)) { h->err = "bad depth step"; return ORBX_E_INVALID; }
     orbx_status st = set_geometry(h, width, height);
     if (st != ORBX_OK) return st;
-    return track_device(h, d_gray, nframes, width, height, step, frame_stride, d_depth, dstep, dframe_stride, d_kps, d_desc, cap, d_counts, d_matches, d_mcounts, max_dist);
+    if (nboxes_total < 0 || (nboxes_total > 0 && (!d_boxes || !d_box_offsets))) { h->err = "per-frame boxes need the box array and nframes + 1 offsets"; return ORBX_E_INVALID; }
+    const DevBoxes BX = { d_boxes, d_box_offsets, 0, nboxes_total, drop_mask };
+    return track_device(h, d_gray, nframes, width, height, step, frame_stride, d_depth, dstep, dframe_stride, BX, d_kps, d_desc, cap, d_counts, d_matches, d_mcounts, max_dist);
 }
 
 // Device view of a host buffer the GPU can read in place (pinned / registered, mapped under UVA); nullptr for pageable memory.
@@ -593,6 +666,7 @@ static const void *mapped_device_view(const void *host)
 struct BatchArgs {
     bool track; const uint8_t *gray; int width, height; size_t step; const uint16_t *depth; size_t dstep;
     orbx_keypoint *kps; uint8_t *desc; int cap; int32_t *counts; orbx_dmatch *matches; int32_t *mcounts; float max_dist;
+    const orbx_box *boxes; const int32_t *box_off; uint64_t drop_mask;        // per-frame YOLO boxes (host), nullable
 };
 
 // `inl`: a call that is one small chunk (the single-frame latency path) keeps its copies on the kernels' stream — two cross-stream
@@ -633,6 +707,24 @@ static orbx_status enqueue_chunk(orbx_handle *h, const BatchArgs &A, int f0, int
             ORBX_CUDA(h, cudaMemcpy2DAsync(d_d + (size_t)f * dfstride, dpitch, (const uint8_t *)A.depth + (size_t)(f0 + f) * height * A.dstep, A.dstep,
                                            (size_t)width * 2, (size_t)height, cudaMemcpyHostToDevice, cs));
     }
+    // this chunk's YOLO boxes: the caller's offsets for frames f0..f0+nb as they are, its boxes [off[f0], off[f0+nb]) at the front of the slot
+    DevBoxes BX = kNoBoxes;
+    if (A.boxes && A.box_off) {
+        const int b0 = A.box_off[f0], nbx = A.box_off[f0 + nb] - b0;
+        if (nbx > 0) {
+            if (nbx > h->boxes_cap) {                                  // rare: grow both slots (drains the pipeline)
+                cudaStreamSynchronize(h->copy_stream); cudaStreamSynchronize(h->stream);
+                cudaFree(h->d_boxes); h->d_boxes = nullptr; h->boxes_cap = 0;
+                ORBX_CUDA(h, cudaMalloc(&h->d_boxes, 2 * (size_t)(nbx + 256) * sizeof(orbx_box)));
+                h->boxes_cap = nbx + 256;
+            }
+            orbx_box *d_b = h->d_boxes + (size_t)slot * h->boxes_cap;
+            int32_t *d_o = h->d_box_off + (size_t)slot * (SC + 1);
+            ORBX_CUDA(h, cudaMemcpyAsync(d_b, A.boxes + b0, (size_t)nbx * sizeof(orbx_box), cudaMemcpyHostToDevice, cs));
+            ORBX_CUDA(h, cudaMemcpyAsync(d_o, A.box_off + f0, (size_t)(nb + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+            BX.boxes = d_b; BX.off = d_o; BX.base = b0; BX.n = nbx; BX.drop_mask = A.drop_mask;
+        }
+    }
     ORBX_CUDA(h, cudaEventRecord(h->ev_in[slot], cs));
     // ---- kernels (main stream): the output slot is free once the D2H of the chunk that used it last is done ----
     ORBX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_in[slot], 0));
@@ -643,8 +735,13 @@ static orbx_status enqueue_chunk(orbx_handle *h, const BatchArgs &A, int f0, int
     const uint16_t *dd = nullptr; size_t dds = 0, ddf = 0;
     if (depth_zc) { dd = (const uint16_t *)(depth_zc + (size_t)f0 * height * A.dstep); dds = A.dstep; ddf = (size_t)height * A.dstep; }
     else if (A.depth) { dd = (const uint16_t *)d_d; dds = dpitch; ddf = dfstride; }
-    if (A.track) st = track_device(h, d_g, nb, width, height, pitch, fstride, dd, dds, ddf, o_k, o_d, h->max_kp, o_c, d_m, d_mc, A.max_dist);
-    else st = run_pipeline(h, nb, d_g, pitch, fstride, dd, dds, ddf, nullptr, 0, 0, o_k, o_d, h->max_kp, o_c);
+    // this chunk's kernels report device-side capacity flags into the slot's own word, so a flag raised by one chunk is never
+    // attributed to the other chunk in flight or to a later call
+    h->d_status = h->d_status_base + 1 + slot;           // (zeroed at the start of the call: host_batch / submit_batch)
+    if (A.track) st = track_device(h, d_g, nb, width, height, pitch, fstride, dd, dds, ddf, BX, o_k, o_d, h->max_kp, o_c, d_m, d_mc, A.max_dist);
+    else st = run_pipeline(h, nb, d_g, pitch, fstride, dd, dds, ddf, BX, o_k, o_d, h->max_kp, o_c);
+    int32_t *slot_status = h->d_status;
+    h->d_status = h->d_status_base;
     if (st != ORBX_OK) return st;
     ORBX_CUDA(h, cudaEventRecord(h->ev_comp[slot], h->stream));
     // ---- D2H (out stream) ----
@@ -659,7 +756,7 @@ static orbx_status enqueue_chunk(orbx_handle *h, const BatchArgs &A, int f0, int
         ORBX_CUDA(h, cudaMemcpy2DAsync(A.matches + (size_t)f0 * A.cap, (size_t)A.cap * sizeof(orbx_dmatch), d_m, (size_t)h->max_kp * sizeof(orbx_dmatch),
                                        (size_t)kcap * sizeof(orbx_dmatch), (size_t)nb, cudaMemcpyDeviceToHost, os));
     }
-    ORBX_CUDA(h, cudaMemcpyAsync(h->h_status + 1 + slot, h->d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, os));
+    ORBX_CUDA(h, cudaMemcpyAsync(h->h_status + 1 + slot, slot_status, sizeof(int32_t), cudaMemcpyDeviceToHost, os));
     ORBX_CUDA(h, cudaEventRecord(h->ev_out[slot], os));
     h->seq++;
     return ORBX_OK;
@@ -672,7 +769,6 @@ static orbx_status finish_slot(orbx_handle *h, int slot, const int32_t *counts, 
     const int s = h->h_status[1 + slot];
     if (s != 0) {
         h->h_status[1 + slot] = 0;
-        cudaMemsetAsync(h->d_status, 0, sizeof(int32_t), h->stream);
         h->err = std::string("device capacity exceeded:") + ((s & ORBX_DS_CAND_OVERFLOW) ? " candidate list (lower cand_divisor)" : "") +
                  ((s & ORBX_DS_NODE_OVERFLOW) ? " quadtree nodes" : "") + ((s & ORBX_DS_KP_OVERFLOW) ? " keypoint output (raise cap / max_keypoints)" : "");
         return ORBX_E_CAPACITY;
@@ -695,13 +791,15 @@ static orbx_status host_batch(orbx_handle *h, const BatchArgs &A, int nframes)
     if (st != ORBX_OK) return st;
     const int C = h->chunk;
     const bool inl = nframes <= C && nframes <= 4;
+    ORBX_CUDA(h, cudaMemsetAsync(h->d_status_base + 1, 0, 2 * sizeof(int32_t), h->stream));   // flags stay sticky across the chunks of THIS call only
     for (int f0 = 0; f0 < nframes; f0 += C) {
         const int nb = std::min(C, nframes - f0);
         if ((st = enqueue_chunk(h, A, f0, nb, inl)) != ORBX_OK) { drain_all(h); return st; }
     }
     ORBX_CUDA(h, cudaStreamSynchronize(inl ? h->stream : h->out_stream));
-    if ((st = finish_slot(h, 0, A.counts, nframes, A.cap)) != ORBX_OK) return st;
-    return finish_slot(h, 1, A.counts, 0, A.cap);
+    // both slots are always inspected (and their flags consumed), so nothing raised by this call survives into the next one
+    const orbx_status s0 = finish_slot(h, 0, A.counts, nframes, A.cap), s1 = finish_slot(h, 1, A.counts, 0, A.cap);
+    return s0 != ORBX_OK ? s0 : s1;
 }
 
 static orbx_status submit_batch(orbx_handle *h, const BatchArgs &A, int nframes, int32_t *ticket)
@@ -713,6 +811,7 @@ static orbx_status submit_batch(orbx_handle *h, const BatchArgs &A, int nframes,
     orbx_status st = set_geometry(h, A.width, A.height);      // (a geometry change synchronises the streams itself)
     if (st != ORBX_OK) return st;
     const uint64_t t = h->seq;
+    ORBX_CUDA(h, cudaMemsetAsync(h->d_status_base + 1 + slot, 0, sizeof(int32_t), h->stream));
     if ((st = enqueue_chunk(h, A, 0, nframes)) != ORBX_OK) { drain_all(h); return st; }
     h->pending[slot].active = true; h->pending[slot].ticket = t; h->pending[slot].counts = A.counts; h->pending[slot].nframes = nframes; h->pending[slot].cap = A.cap;
     *ticket = (int32_t)(t & 0x7FFFFFFF);
@@ -739,59 +838,82 @@ extern "C" orbx_status orbx_batch_wait(orbx_handle *h, int32_t ticket)
 static bool batch_args_ok(orbx_handle *h, const BatchArgs &A, int nframes)
 {
     if (!A.gray || A.width <= 0 || A.height <= 0) { h->err = "empty image"; return false; }
-    if (nframes < 0 || !A.kps || !A.desc || !A.counts || A.cap < 1 || A.step < (size_t)A.width || (A.depth && A.dstep < (size_t)A.width * 2) ||
+    if (nframes < 0 || !A.kps || !A.desc || !A.counts || A.cap < 1 || A.step < (size_t)A.width ||
         (A.track && (!A.matches || !A.mcounts))) { h->err = "bad arguments"; return false; }
+    if (A.depth && (A.dstep < (size_t)A.width * 2 || (A.dstep & 1) || ((uintptr_t)A.depth & 1))) { h->err = "bad depth buffer: rows of at least 2*width bytes, even step, 2-byte aligned"; return false; }
+    if ((A.boxes != nullptr) != (A.box_off != nullptr)) { h->err = "per-frame boxes need both the box array and nframes + 1 offsets"; return false; }
+    if (A.box_off) {
+        if (A.box_off[0] < 0) { h->err = "box offsets must start at >= 0"; return false; }
+        for (int f = 0; f < nframes; f++) if (A.box_off[f + 1] < A.box_off[f]) { h->err = "box offsets must not decrease"; return false; }
+    }
     return true;
+}
+
+// the five host-buffer batch entry points share one body: validate, then run synchronously (chunk pipeline) or enqueue one batch
+static orbx_status host_entry(orbx_handle *h, const BatchArgs &A, int nframes, int32_t *ticket, bool async)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    if (!A.gray || A.width <= 0 || A.height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }
+    if (!batch_args_ok(h, A, nframes)) return ORBX_E_INVALID;
+    return async ? submit_batch(h, A, nframes, ticket) : host_batch(h, A, nframes);
 }
 
 extern "C" orbx_status orbx_extract_batch(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
                                           size_t step, const uint16_t *depth, size_t dstep,
                                           orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *counts)
 {
-    if (!h) return ORBX_E_INVALID;
-    cudaSetDevice(h->device);
-    const BatchArgs A = { false, gray, width, height, step, depth, dstep, kps, desc, cap, counts, nullptr, nullptr, 0.f };
-    if (!gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }
-    if (!batch_args_ok(h, A, nframes)) return ORBX_E_INVALID;
-    return host_batch(h, A, nframes);
+    const BatchArgs A = { false, gray, width, height, step, depth, dstep, kps, desc, cap, counts, nullptr, nullptr, 0.f, nullptr, nullptr, 0 };
+    return host_entry(h, A, nframes, nullptr, false);
 }
-
+extern "C" orbx_status orbx_extract_batch_boxes(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
+                                                size_t step, const uint16_t *depth, size_t dstep,
+                                                const orbx_box *boxes, const int32_t *box_offsets, uint64_t drop_mask,
+                                                orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *counts)
+{
+    const BatchArgs A = { false, gray, width, height, step, depth, dstep, kps, desc, cap, counts, nullptr, nullptr, 0.f, boxes, box_offsets, drop_mask };
+    return host_entry(h, A, nframes, nullptr, false);
+}
 extern "C" orbx_status orbx_track_batch(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
                                         size_t step, const uint16_t *depth, size_t dstep,
                                         orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *counts,
                                         orbx_dmatch *matches, int32_t *mcounts, float max_dist)
 {
-    if (!h) return ORBX_E_INVALID;
-    cudaSetDevice(h->device);
-    const BatchArgs A = { true, gray, width, height, step, depth, dstep, kps, desc, cap, counts, matches, mcounts, max_dist };
-    if (!gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }
-    if (!batch_args_ok(h, A, nframes)) return ORBX_E_INVALID;
-    return host_batch(h, A, nframes);
+    const BatchArgs A = { true, gray, width, height, step, depth, dstep, kps, desc, cap, counts, matches, mcounts, max_dist, nullptr, nullptr, 0 };
+    return host_entry(h, A, nframes, nullptr, false);
 }
-
+extern "C" orbx_status orbx_track_batch_boxes(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
+                                              size_t step, const uint16_t *depth, size_t dstep,
+                                              const orbx_box *boxes, const int32_t *box_offsets, uint64_t drop_mask,
+                                              orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *counts,
+                                              orbx_dmatch *matches, int32_t *mcounts, float max_dist)
+{
+    const BatchArgs A = { true, gray, width, height, step, depth, dstep, kps, desc, cap, counts, matches, mcounts, max_dist, boxes, box_offsets, drop_mask };
+    return host_entry(h, A, nframes, nullptr, false);
+}
 extern "C" orbx_status orbx_extract_batch_submit(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
                                                  size_t step, const uint16_t *depth, size_t dstep,
                                                  orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *counts, int32_t *ticket)
 {
-    if (!h) return ORBX_E_INVALID;
-    cudaSetDevice(h->device);
-    const BatchArgs A = { false, gray, width, height, step, depth, dstep, kps, desc, cap, counts, nullptr, nullptr, 0.f };
-    if (!gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }
-    if (!batch_args_ok(h, A, nframes)) return ORBX_E_INVALID;
-    return submit_batch(h, A, nframes, ticket);
+    const BatchArgs A = { false, gray, width, height, step, depth, dstep, kps, desc, cap, counts, nullptr, nullptr, 0.f, nullptr, nullptr, 0 };
+    return host_entry(h, A, nframes, ticket, true);
 }
-
 extern "C" orbx_status orbx_track_batch_submit(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
                                                size_t step, const uint16_t *depth, size_t dstep,
                                                orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *counts,
                                                orbx_dmatch *matches, int32_t *mcounts, float max_dist, int32_t *ticket)
 {
-    if (!h) return ORBX_E_INVALID;
-    cudaSetDevice(h->device);
-    const BatchArgs A = { true, gray, width, height, step, depth, dstep, kps, desc, cap, counts, matches, mcounts, max_dist };
-    if (!gray || width <= 0 || height <= 0) { h->err = "empty image"; return ORBX_E_EMPTY; }
-    if (!batch_args_ok(h, A, nframes)) return ORBX_E_INVALID;
-    return submit_batch(h, A, nframes, ticket);
+    const BatchArgs A = { true, gray, width, height, step, depth, dstep, kps, desc, cap, counts, matches, mcounts, max_dist, nullptr, nullptr, 0 };
+    return host_entry(h, A, nframes, ticket, true);
+}
+extern "C" orbx_status orbx_track_batch_boxes_submit(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
+                                                     size_t step, const uint16_t *depth, size_t dstep,
+                                                     const orbx_box *boxes, const int32_t *box_offsets, uint64_t drop_mask,
+                                                     orbx_keypoint *kps, uint8_t *desc, int32_t cap, int32_t *counts,
+                                                     orbx_dmatch *matches, int32_t *mcounts, float max_dist, int32_t *ticket)
+{
+    const BatchArgs A = { true, gray, width, height, step, depth, dstep, kps, desc, cap, counts, matches, mcounts, max_dist, boxes, box_offsets, drop_mask };
+    return host_entry(h, A, nframes, ticket, true);
 }
 
 // ---- stage access (mvImagePyramid is public in the reference, ORBextractor.hpp:84) ----
@@ -1331,7 +1453,7 @@ extern "C" orbx_status orbx_test_quadtree(orbx_handle *h, const int32_t *xys, in
     cudaMemcpyAsync(d_g, &G, sizeof(G), cudaMemcpyHostToDevice, h->stream);
     cudaMemcpyAsync(h->d_cand, packed.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream);
     cudaMemcpyAsync(h->d_ncand, &n, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream);
-    launch_quadtree_geo(h, d_g, 1, 1, g.sel_cap, h->cand_cap, (int)h->sel_cap);
+    if (launch_quadtree_geo(h, d_g, 1, 1, g.sel_cap, h->cand_cap, (int)h->sel_cap) != 0) { cudaFree(d_g); h->err = "quadtree node table exceeds the shared-memory opt-in limit"; return ORBX_E_UNSUPPORTED; }
     int32_t m = 0;
     cudaMemcpyAsync(&m, h->d_nsel, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
     cudaError_t e = cudaStreamSynchronize(h->stream);

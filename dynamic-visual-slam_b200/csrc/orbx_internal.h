@@ -102,7 +102,7 @@ struct orbx_handle {
     void *d_cells; int cell_cap;                             // FAST cell records, 32 bytes each (k_fast.cu: orbx_build_fast_cells)
     const uint8_t *tmap_l0; size_t tmap_l0_step, tmap_l0_fstride; int tmap_l0_frames;
     int pyr_grid_cap;                                     // resident CTAs of the cooperative pyramid kernel (0 = not probed, -1 = unavailable)
-    size_t blur_smem, quad_smem, cull_smem; bool rz_configured;      // per-handle (= per-device) dynamic shared memory opt-ins
+    size_t smem_optin_max;                                // cudaDevAttrMaxSharedMemoryPerBlockOptin of the handle's device
     int fast_grid_cap; size_t fast_smem; int fast_tp;   // resident CTAs / dynamic smem / tile pitch of the persistent FAST kernel
     // arenas, sized for max_width x max_height x max_batch
     uint8_t *d_pyr, *d_blur;     size_t pyr_slab, blur_slab;          // current per-frame strides
@@ -118,8 +118,10 @@ struct orbx_handle {
     orbx_keypoint *d_kps_all; uint8_t *d_desc_all;   // unfiltered per-frame outputs [batch][max_kp]
     int32_t *d_count_all;        // [batch]
     orbx_keypoint *d_kps_out; uint8_t *d_desc_out; int32_t *d_count_out;   // host-API outputs [batch][max_kp]
-    orbx_box *d_boxes; int boxes_cap;
-    int32_t *d_status;           // device-side error flags
+    orbx_box *d_boxes; int boxes_cap;        // staged box lists: two slots of boxes_cap boxes (host-batch pipeline), slot 0 for single-frame calls
+    int32_t *d_box_off;                      // staged per-frame offsets: two slots of max_batch + 1
+    int32_t *d_status;           // device-side error flags: the word the kernels launched now report into
+    int32_t *d_status_base;      // [0] synchronous and device calls, [1 + slot] the chunk in staging slot `slot` of the host-batch pipeline
     // pinned staging for the host API
     uint8_t *h_out; size_t h_out_bytes;
     int32_t *h_status;
@@ -182,6 +184,12 @@ static inline void orbx_launch_pdl(orbx_handle *h, void (*kern)(KArgs...), dim3 
     }
 }
 
+// Dynamic shared memory above 48 KB needs an opt-in that CUDA keeps per FUNCTION and per DEVICE, not per handle: the largest size asked
+// for so far is remembered process-wide and only ever raised, so that a second handle on the same GPU can never lower what an earlier
+// one relies on.  false: `smem` exceeds the device's opt-in limit or the driver refused.
+bool orbx_optin_smem(orbx_handle *h, const void *func, size_t smem);
+size_t orbx_quadtree_smem(int node_cap);              // k_quadtree.cu: dynamic shared memory of one quadtree CTA
+
 // device status bits
 #define ORBX_DS_CAND_OVERFLOW 1
 #define ORBX_DS_NODE_OVERFLOW 2
@@ -194,8 +202,8 @@ int  launch_resize_level(orbx_handle *h, int level, int nframes, const uint8_t *
 void orbx_build_fast_cells(const FrameGeom &G, const std::vector<uint32_t> &ctab, std::vector<uint4> &out);   // k_fast.cu: 32-byte FAST cell records
 int  orbx_ensure_tmaps(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
 int  launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);   // -1: TMA descriptor encode failed
-void launch_quadtree(orbx_handle *h, int nframes);
-void launch_quadtree_geo(orbx_handle *h, const FrameGeom *d_geo, int nlevels, int nframes, int node_cap, size_t cand_slab, int sel_slab);
+int  launch_quadtree(orbx_handle *h, int nframes);     // -1: the node table does not fit the shared-memory opt-in limit
+int  launch_quadtree_geo(orbx_handle *h, const FrameGeom *d_geo, int nlevels, int nframes, int node_cap, size_t cand_slab, int sel_slab);
 int  launch_cull(orbx_handle *h, const orbx_keypoint *d_kps, const uint8_t *d_desc, int n, const int32_t *d_mq, int nm, int max_new, float min_response,
                  orbx_keypoint *d_out_kps, uint8_t *d_out_desc, int32_t *d_out_index, int cap, int32_t *d_n_out);   // k_cull.cu; -1: shared memory opt-in failed
 int  launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride, cudaStream_t st, int tile_first = 0, int ntiles = -1);
@@ -203,7 +211,7 @@ void launch_describe_to(orbx_handle *h, int nframes, const uint8_t *l0, size_t l
                         orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts);
 void upload_umax(const int *umax);
 void launch_filter(orbx_handle *h, int nframes, const uint16_t *d_depth, size_t dstep, size_t dfstride,
-                   const orbx_box *d_boxes, int nboxes, uint64_t drop_mask,
+                   const orbx_box *d_boxes, const int32_t *d_box_offsets, int box_base, int nboxes, uint64_t drop_mask,
                    orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts);
 int  launch_match_core(orbx_handle *h, const uint8_t *d_q, const int32_t *d_nq, int nq_max, size_t q_stride,
                        const uint8_t *d_t, const int32_t *d_nt, int nt_max, size_t t_stride,

@@ -105,15 +105,36 @@ public:
     ORBextractor(const ORBextractor &) = delete;
     ORBextractor &operator=(const ORBextractor &) = delete;
 
-    // Mask is ignored, as in the reference (ORBextractor.hpp:55-57); vLappingArea = {0,0} => mono only (:1152-1161).
-    int operator()(const Mat &image, const Mat & /*mask*/, std::vector<KeyPoint> &keypoints, Mat &descriptors,
-                   std::vector<int> & /*vLappingArea*/)
+    // Mask is ignored, as in the reference (ORBextractor.hpp:55-57).  vLappingArea reproduces the reference's mono / stereo split
+    // (ORBextractor.cpp:1139-1166): keypoints with vLappingArea[0] <= pt.x <= vLappingArea[1] (scaled coordinates) are written from the
+    // BACK of the arrays in the order they are met, all others from the front; the return value is the number at the front (monoIndex).
+    // The frontend passes {0, 0} (frontend.cpp:290), for which everything with pt.x != 0 is "mono" and the result is the plain list.
+#ifdef ORBX_WITH_OPENCV
+    int operator()(cv::InputArray _image, cv::InputArray /*_mask*/, std::vector<KeyPoint> &keypoints, cv::OutputArray _descriptors,
+                   std::vector<int> &vLappingArea)
     {
-        return extractFiltered(image, Mat(), keypoints, descriptors);
+        if (_image.empty()) return -1;                                             // ORBextractor.cpp:1090-1091
+        Mat image = _image.getMat(), desc;
+        const int n = extractFiltered(image, Mat(), keypoints, desc);
+        const int mono = applyLappingArea(keypoints, desc, vLappingArea);
+        if (n == 0) _descriptors.release();                                        // :1108
+        else desc.copyTo(_descriptors);                                            // _descriptors.create(n, 32, CV_8U), :1112
+        return mono;
     }
+#else
+    int operator()(const Mat &image, const Mat & /*mask*/, std::vector<KeyPoint> &keypoints, Mat &descriptors,
+                   std::vector<int> &vLappingArea)
+    {
+        const int n = extractFiltered(image, Mat(), keypoints, descriptors);
+        return n < 0 ? n : applyLappingArea(keypoints, descriptors, vLappingArea);
+    }
+#endif
 
-    // operator() followed by Frontend::filterDepth (frontend.cpp:503-527) when `depth` (CV_16UC1, millimetres) is given.
-    int extractFiltered(const Mat &image, const Mat &depth, std::vector<KeyPoint> &keypoints, Mat &descriptors)
+    // operator() followed by Frontend::filterDepth (frontend.cpp:503-527) when `depth` (CV_16UC1, millimetres) is given, and by
+    // Backend::categorizeObservation + the filtered_objects_ test (backend.cpp:1011-1029, 746-751) when YOLO boxes are given: a keypoint
+    // whose FIRST containing box has a class with its bit set in drop_class_mask is dropped.  Both run after selection, as in the reference.
+    int extractFiltered(const Mat &image, const Mat &depth, std::vector<KeyPoint> &keypoints, Mat &descriptors,
+                        const std::vector<orbx_box> &boxes = std::vector<orbx_box>(), uint64_t drop_class_mask = 0)
     {
         if (image.empty()) return -1;                                              // ORBextractor.cpp:1090-1091
         if (image.type() != type_8uc1()) raise("ORBextractor: image must be CV_8UC1");   // reference: assert, :1094
@@ -122,14 +143,13 @@ public:
         kbuf_.resize(cap_);
         dbuf_.resize((size_t)cap_ * ORBX_DESC_BYTES);
         int32_t n = 0;
-        orbx_status st = orbx_extract_filtered(h_, image.data, image.cols, image.rows, (size_t)image.step,
-                                               depth.empty() ? nullptr : (const uint16_t *)depth.data, depth.empty() ? 0 : (size_t)depth.step,
-                                               nullptr, 0, 0, kbuf_.data(), dbuf_.data(), cap_, &n);
-        if (st == ORBX_E_CAPACITY && n > cap_) {                                   // grow once and retry
-            cap_ = n + 64; kbuf_.resize(cap_); dbuf_.resize((size_t)cap_ * ORBX_DESC_BYTES);
+        orbx_status st = ORBX_OK;
+        for (int attempt = 0; attempt < 2; attempt++) {                            // grow once and retry on ORBX_E_CAPACITY
             st = orbx_extract_filtered(h_, image.data, image.cols, image.rows, (size_t)image.step,
                                        depth.empty() ? nullptr : (const uint16_t *)depth.data, depth.empty() ? 0 : (size_t)depth.step,
-                                       nullptr, 0, 0, kbuf_.data(), dbuf_.data(), cap_, &n);
+                                       boxes.empty() ? nullptr : boxes.data(), (int32_t)boxes.size(), drop_class_mask, kbuf_.data(), dbuf_.data(), cap_, &n);
+            if (st != ORBX_E_CAPACITY || n <= cap_) break;
+            cap_ = n + 64; kbuf_.resize(cap_); dbuf_.resize((size_t)cap_ * ORBX_DESC_BYTES);
         }
         if (st != ORBX_OK) raise(std::string("orbx_extract: ") + orbx_last_error(h_));
         keypoints.resize((size_t)n);
@@ -141,7 +161,7 @@ public:
         }
         last_w_ = image.cols; last_h_ = image.rows;
         pyramid_valid_ = false;
-        return n;                                                                  // monoIndex, :1166
+        return n;                                                                  // monoIndex for vLappingArea = {0, 0}, :1166
     }
 
     // The "FEATURE CULLING FOR BACKEND" block of Frontend::syncCallback (frontend.cpp:1168-1218): backend set = the query keypoint of
@@ -202,6 +222,28 @@ public:
     orbx_handle *handle() { return h_; }
 
 private:
+    // the reference's two-ended fill (ORBextractor.cpp:1152-1161), applied to the finished list; returns monoIndex
+    int applyLappingArea(std::vector<KeyPoint> &keypoints, Mat &descriptors, const std::vector<int> &lap)
+    {
+        const int n = (int)keypoints.size();
+        if (lap.size() < 2) raise("ORBextractor: vLappingArea needs two entries");     // the reference indexes [0] and [1] unchecked
+        std::vector<int> src((size_t)n);
+        int mono = 0, stereo = n - 1;
+        for (int i = 0; i < n; i++) {
+            const float x = keypoints[(size_t)i].pt.x;
+            if (x >= lap[0] && x <= lap[1]) src[(size_t)stereo--] = i; else src[(size_t)mono++] = i;
+        }
+        if (mono == n) return mono;                                                // nothing in the lapping area: order unchanged
+        std::vector<KeyPoint> k((size_t)n);
+        std::vector<uint8_t> d((size_t)n * ORBX_DESC_BYTES);
+        for (int j = 0; j < n; j++) {
+            k[(size_t)j] = keypoints[(size_t)src[(size_t)j]];
+            std::memcpy(d.data() + (size_t)j * ORBX_DESC_BYTES, descriptors.ptr<uint8_t>(src[(size_t)j]), ORBX_DESC_BYTES);
+        }
+        keypoints.swap(k);
+        for (int j = 0; j < n; j++) std::memcpy(descriptors.ptr<uint8_t>(j), d.data() + (size_t)j * ORBX_DESC_BYTES, ORBX_DESC_BYTES);
+        return mono;
+    }
     std::vector<float> vec(void (*fn)(const orbx_handle *, float *))
     {
         std::vector<float> v((size_t)nlevels_);
@@ -258,6 +300,66 @@ private:
         return v;
     }
     orbx_handle *h_;
+};
+
+// Backend side: the landmark loop of Backend::associateObservation (backend.cpp:1064-1120) against descriptors resident in HBM.
+// One instance per category map (the reference keeps category -> id -> LandmarkInfo, backend.cpp:306-323); rows are appended in the
+// order landmarks are created, `first_index` is the global index of row 0 when the map is sharded over several GPUs.
+class LandmarkDB {
+public:
+    LandmarkDB(ORBextractor &ex, int64_t capacity_rows, uint32_t first_index = 0) : h_(ex.handle())
+    {
+        if (orbx_db_create(h_, capacity_rows, first_index, &db_) != ORBX_OK) raise(std::string("orbx_db_create: ") + orbx_last_error(h_));
+    }
+    ~LandmarkDB() { orbx_db_destroy(db_); }
+    LandmarkDB(const LandmarkDB &) = delete;
+    LandmarkDB &operator=(const LandmarkDB &) = delete;
+
+    // append landmark descriptors (N x 32 CV_8U) with their positions (the reference's cv::Point3f, xyz floats)
+    void append(const Mat &descriptors, const float *xyz)
+    {
+        if (descriptors.empty()) return;
+        if (descriptors.cols != 32 || descriptors.type() != type_8uc1()) raise("LandmarkDB: descriptors must be N x 32 CV_8U");
+        std::vector<uint8_t> rows((size_t)descriptors.rows * 32);
+        for (int r = 0; r < descriptors.rows; r++) std::memcpy(rows.data() + (size_t)r * 32, descriptors.ptr<uint8_t>(r), 32);
+        const int64_t first = orbx_db_rows(db_);
+        if (orbx_db_append(db_, rows.data(), descriptors.rows) != ORBX_OK) raise(std::string("orbx_db_append: ") + orbx_last_error(h_));
+        if (xyz && orbx_db_set_positions(db_, first, descriptors.rows, xyz) != ORBX_OK) raise(std::string("orbx_db_set_positions: ") + orbx_last_error(h_));
+    }
+    void setPositions(int64_t first_row, int64_t nrows, const float *xyz)
+    {
+        if (orbx_db_set_positions(db_, first_row, nrows, xyz) != ORBX_OK) raise(std::string("orbx_db_set_positions: ") + orbx_last_error(h_));
+    }
+    int64_t rows() const { return orbx_db_rows(db_); }
+
+    // associateObservation for a batch of observations of this category: per observation the landmark (global row, -1 = none) with the
+    // smallest reprojection error among the rows at Hamming distance < max_desc_dist, if that error is < max_reproj_err
+    // (reference literals 50.0 and 5.0, backend.cpp:225-226).  pixels: nq x 2 floats (obs.pixel).
+    void associate(const Mat &descriptors, const float *pixels, const orbx_pose &pose, std::vector<orbx_assoc> &out,
+                   float max_desc_dist = 50.0f, double max_reproj_err = 5.0)
+    {
+        out.assign((size_t)(descriptors.empty() ? 0 : descriptors.rows), orbx_assoc());
+        if (descriptors.empty()) return;
+        if (descriptors.cols != 32 || descriptors.type() != type_8uc1()) raise("LandmarkDB: descriptors must be N x 32 CV_8U");
+        std::vector<uint8_t> q((size_t)descriptors.rows * 32);
+        for (int r = 0; r < descriptors.rows; r++) std::memcpy(q.data() + (size_t)r * 32, descriptors.ptr<uint8_t>(r), 32);
+        if (orbx_db_associate(db_, q.data(), pixels, descriptors.rows, &pose, max_desc_dist, max_reproj_err, out.data()) != ORBX_OK)
+            raise(std::string("orbx_db_associate: ") + orbx_last_error(h_));
+    }
+    // descriptor stage alone: the two nearest rows per query (BFMatcher tie-break), e.g. for an all-gather + orbx_merge_top2 over shards
+    void queryTop2(const Mat &descriptors, std::vector<orbx_top2> &out)
+    {
+        out.assign((size_t)(descriptors.empty() ? 0 : descriptors.rows), orbx_top2());
+        if (descriptors.empty()) return;
+        std::vector<uint8_t> q((size_t)descriptors.rows * 32);
+        for (int r = 0; r < descriptors.rows; r++) std::memcpy(q.data() + (size_t)r * 32, descriptors.ptr<uint8_t>(r), 32);
+        if (orbx_db_query_top2(db_, q.data(), descriptors.rows, out.data()) != ORBX_OK) raise(std::string("orbx_db_query_top2: ") + orbx_last_error(h_));
+    }
+    orbx_db *db() { return db_; }
+
+private:
+    orbx_handle *h_;
+    orbx_db *db_ = nullptr;
 };
 
 }  // namespace orbx

@@ -130,6 +130,11 @@ def load():
         "orbx_extract_batch_submit": (i32, [vp, vp, i32, i32, i32, sz, vp, sz, vp, vp, i32, vp, vp]),
         "orbx_track_batch_submit": (i32, [vp, vp, i32, i32, i32, sz, vp, sz, vp, vp, i32, vp, vp, vp, f32, vp]),
         "orbx_batch_wait": (i32, [vp, i32]),
+        "orbx_extract_batch_boxes_device": (i32, [vp, vp, i32, i32, i32, sz, sz, vp, sz, sz, vp, vp, i32, u64, vp, vp, i32, vp]),
+        "orbx_extract_batch_boxes": (i32, [vp, vp, i32, i32, i32, sz, vp, sz, vp, vp, u64, vp, vp, i32, vp]),
+        "orbx_track_batch_boxes_device": (i32, [vp, vp, i32, i32, i32, sz, sz, vp, sz, sz, vp, vp, i32, u64, vp, vp, i32, vp, vp, vp, f32]),
+        "orbx_track_batch_boxes": (i32, [vp, vp, i32, i32, i32, sz, vp, sz, vp, vp, u64, vp, vp, i32, vp, vp, vp, f32]),
+        "orbx_track_batch_boxes_submit": (i32, [vp, vp, i32, i32, i32, sz, vp, sz, vp, vp, u64, vp, vp, i32, vp, vp, vp, f32, vp]),
         "orbx_profile_enable": (None, [vp, i32]),
         "orbx_profile_kernels": (i32, []),
         "orbx_profile_name": (ct.c_char_p, [i32]),
@@ -356,7 +361,17 @@ class ORBextractor:
                                               _p(ok), _p(od), _p(oi), cap, ct.byref(n)))
         return ok[:n.value].copy(), od[:n.value].copy(), oi[:n.value].copy()
 
-    def extract_batch(self, frames, depth=None, cap=2048):
+    @staticmethod
+    def pack_frame_boxes(frame_boxes):
+        """list (one entry per frame) of BOX_DTYPE arrays -> (boxes, offsets[nframes + 1]) for the *_boxes batch calls"""
+        off = np.zeros(len(frame_boxes) + 1, np.int32)
+        off[1:] = np.cumsum([len(b) for b in frame_boxes])
+        parts = [np.ascontiguousarray(b, BOX_DTYPE) for b in frame_boxes if len(b)]
+        boxes = np.concatenate(parts) if parts else np.zeros(0, BOX_DTYPE)
+        return np.ascontiguousarray(boxes), off
+
+    def extract_batch(self, frames, depth=None, cap=2048, frame_boxes=None, drop_class_mask=0):
+        """frame_boxes: per-frame YOLO box lists (BASELINE configs[4]); keypoints inside a box of a masked class are dropped after selection"""
         frames = np.ascontiguousarray(frames, dtype=np.uint8)
         nf, h, w = frames.shape
         self._last_w, self._last_h = w, h
@@ -367,8 +382,13 @@ class ORBextractor:
         if depth is not None:
             depth = np.ascontiguousarray(depth, dtype=np.uint16)
             dptr, dstep = _p(depth), depth.strides[1]
-        self._check(self.L.orbx_extract_batch(self._h, _p(frames), nf, w, h, frames.strides[1], dptr, dstep,
-                                              _p(kps), _p(desc), cap, _p(counts)))
+        if frame_boxes is None:
+            self._check(self.L.orbx_extract_batch(self._h, _p(frames), nf, w, h, frames.strides[1], dptr, dstep,
+                                                  _p(kps), _p(desc), cap, _p(counts)))
+        else:
+            boxes, off = self.pack_frame_boxes(frame_boxes)
+            self._check(self.L.orbx_extract_batch_boxes(self._h, _p(frames), nf, w, h, frames.strides[1], dptr, dstep,
+                                                        _p(boxes), _p(off), ct.c_uint64(drop_class_mask), _p(kps), _p(desc), cap, _p(counts)))
         return kps, desc, counts
 
     def extract_batch_device(self, d_gray, nframes, w, h, step, frame_stride, d_kps, d_desc, cap, d_counts,
@@ -381,8 +401,8 @@ class ORBextractor:
     def track_reset(self):
         self.L.orbx_track_reset(self._h)
 
-    def track_batch(self, frames, depth=None, cap=2048, max_dist=50.0):
-        """frames [n,h,w] u8 (+ depth [n,h,w] u16): per-frame filtered keypoints/descriptors and matches vs the previous frame."""
+    def track_batch(self, frames, depth=None, cap=2048, max_dist=50.0, frame_boxes=None, drop_class_mask=0):
+        """frames [n,h,w] u8 (+ depth [n,h,w] u16, + per-frame YOLO boxes): per-frame filtered keypoints/descriptors and matches vs the previous frame."""
         frames = np.ascontiguousarray(frames, dtype=np.uint8)
         nf, h, w = frames.shape
         self._last_w, self._last_h = w, h
@@ -395,8 +415,14 @@ class ORBextractor:
         if depth is not None:
             depth = np.ascontiguousarray(depth, dtype=np.uint16)
             dptr, dstep = _p(depth), depth.strides[1]
-        self._check(self.L.orbx_track_batch(self._h, _p(frames), nf, w, h, frames.strides[1], dptr, dstep,
-                                            _p(kps), _p(desc), cap, _p(counts), _p(matches), _p(mcounts), ct.c_float(max_dist)))
+        if frame_boxes is None:
+            self._check(self.L.orbx_track_batch(self._h, _p(frames), nf, w, h, frames.strides[1], dptr, dstep,
+                                                _p(kps), _p(desc), cap, _p(counts), _p(matches), _p(mcounts), ct.c_float(max_dist)))
+        else:
+            boxes, off = self.pack_frame_boxes(frame_boxes)
+            self._check(self.L.orbx_track_batch_boxes(self._h, _p(frames), nf, w, h, frames.strides[1], dptr, dstep,
+                                                      _p(boxes), _p(off), ct.c_uint64(drop_class_mask),
+                                                      _p(kps), _p(desc), cap, _p(counts), _p(matches), _p(mcounts), ct.c_float(max_dist)))
         return kps, desc, counts, matches, mcounts
 
     def track_batch_submit(self, frames, depth, out, max_dist=50.0):

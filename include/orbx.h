@@ -138,15 +138,30 @@ orbx_status orbx_extract_batch(orbx_handle *h, const uint8_t *gray, int32_t nfra
 
 /* frame-parallel batch, DEVICE buffers, asynchronous.  nframes <= max_batch.  Frame f starts at
  * d_gray + f*frame_stride (bytes); rows are `step` bytes, step % 16 == 0 and 16-byte aligned base.
- * d_depth nullable (frame stride dframe_stride BYTES, row step dstep BYTES).  Per-frame boxes are
- * not supported in the batch call (use the single-frame call).  d_kps / d_desc hold cap_per_frame
- * entries per frame; d_counts[nframes].  Errors detected on the device (capacity) are reported by
- * the next orbx_sync.                                                                            */
+ * d_depth nullable (frame stride dframe_stride BYTES, row step dstep BYTES).  d_kps / d_desc hold
+ * cap_per_frame entries per frame; d_counts[nframes].  Errors detected on the device (capacity) are
+ * reported by the next orbx_sync.  Per-frame YOLO boxes: the *_boxes variants below.              */
 orbx_status orbx_extract_batch_device(orbx_handle *h, const uint8_t *d_gray, int32_t nframes,
                                       int32_t width, int32_t height, size_t step, size_t frame_stride,
                                       const uint16_t *d_depth, size_t dstep, size_t dframe_stride,
                                       orbx_keypoint *d_kps, uint8_t *d_desc, int32_t cap_per_frame,
                                       int32_t *d_counts);
+
+/* ---- per-frame YOLO box lists in the batch calls (BASELINE configs[4]: semantic-masked extraction) ----
+ * Backend::categorizeObservation + the filtered_objects_ test (backend.cpp:1011-1029, 746-751) for every frame of a batch: frame f owns
+ * boxes[box_offsets[f] .. box_offsets[f+1]) (nframes + 1 non-decreasing offsets; nboxes_total = box_offsets[nframes] for the device
+ * variants); a keypoint whose FIRST containing box (inclusive bounds, fp64 compares) has a class_id c with bit c of drop_class_mask set
+ * is dropped — after selection, so the retained set equals extract-then-filter.  boxes == NULL: no box filter.
+ * Otherwise identical to the calls without `_boxes`.                                                                              */
+orbx_status orbx_extract_batch_boxes_device(orbx_handle *h, const uint8_t *d_gray, int32_t nframes,
+                                            int32_t width, int32_t height, size_t step, size_t frame_stride,
+                                            const uint16_t *d_depth, size_t dstep, size_t dframe_stride,
+                                            const orbx_box *d_boxes, const int32_t *d_box_offsets, int32_t nboxes_total, uint64_t drop_class_mask,
+                                            orbx_keypoint *d_kps, uint8_t *d_desc, int32_t cap_per_frame, int32_t *d_counts);
+orbx_status orbx_extract_batch_boxes(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
+                                     size_t step, const uint16_t *depth, size_t dstep,
+                                     const orbx_box *boxes, const int32_t *box_offsets, uint64_t drop_class_mask,
+                                     orbx_keypoint *kps, uint8_t *desc, int32_t cap_per_frame, int32_t *counts);
 
 /* ---- stream step: the hot part of Frontend::syncCallback (frontend.cpp:1094-1132, first frame :1277-1317) ----
  * For every frame of the batch: extraction, depth filter (d_depth / depth nullable), then
@@ -164,6 +179,18 @@ orbx_status orbx_track_batch(orbx_handle *h, const uint8_t *gray, int32_t nframe
                              size_t step, const uint16_t *depth, size_t dstep,
                              orbx_keypoint *kps, uint8_t *desc, int32_t cap_per_frame, int32_t *counts,
                              orbx_dmatch *matches, int32_t *match_counts, float max_dist);
+/* the same with per-frame YOLO boxes (see orbx_extract_batch_boxes_device): descriptors of dropped keypoints never reach the matcher */
+orbx_status orbx_track_batch_boxes_device(orbx_handle *h, const uint8_t *d_gray, int32_t nframes,
+                                          int32_t width, int32_t height, size_t step, size_t frame_stride,
+                                          const uint16_t *d_depth, size_t dstep, size_t dframe_stride,
+                                          const orbx_box *d_boxes, const int32_t *d_box_offsets, int32_t nboxes_total, uint64_t drop_class_mask,
+                                          orbx_keypoint *d_kps, uint8_t *d_desc, int32_t cap_per_frame, int32_t *d_counts,
+                                          orbx_dmatch *d_matches, int32_t *d_match_counts, float max_dist);
+orbx_status orbx_track_batch_boxes(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
+                                   size_t step, const uint16_t *depth, size_t dstep,
+                                   const orbx_box *boxes, const int32_t *box_offsets, uint64_t drop_class_mask,
+                                   orbx_keypoint *kps, uint8_t *desc, int32_t cap_per_frame, int32_t *counts,
+                                   orbx_dmatch *matches, int32_t *match_counts, float max_dist);
 void        orbx_track_reset(orbx_handle *h);
 
 /* Asynchronous variants of the two host-buffer batch calls: enqueue ONE batch (1..max_batch frames) and return a ticket;
@@ -178,6 +205,11 @@ orbx_status orbx_track_batch_submit(orbx_handle *h, const uint8_t *gray, int32_t
                                     size_t step, const uint16_t *depth, size_t dstep,
                                     orbx_keypoint *kps, uint8_t *desc, int32_t cap_per_frame, int32_t *counts,
                                     orbx_dmatch *matches, int32_t *match_counts, float max_dist, int32_t *ticket);
+orbx_status orbx_track_batch_boxes_submit(orbx_handle *h, const uint8_t *gray, int32_t nframes, int32_t width, int32_t height,
+                                          size_t step, const uint16_t *depth, size_t dstep,
+                                          const orbx_box *boxes, const int32_t *box_offsets, uint64_t drop_class_mask,
+                                          orbx_keypoint *kps, uint8_t *desc, int32_t cap_per_frame, int32_t *counts,
+                                          orbx_dmatch *matches, int32_t *match_counts, float max_dist, int32_t *ticket);
 orbx_status orbx_batch_wait(orbx_handle *h, int32_t ticket);
 
 /* ---- matching: cv::BFMatcher(NORM_HAMMING) ----

@@ -292,6 +292,22 @@ def synth_depth(seed, frame, w, h):
     return out
 
 
+def synth_boxes(seed, frame, w, h):
+    out = np.zeros(4, BOX_DTYPE)
+    n = lib().orc_synth_boxes(ct.c_uint32(seed), int(frame), int(w), int(h), _p(out))
+    return out[:n].copy()
+
+
+def filter_boxes(kps, desc, boxes, drop_mask=1):
+    kps = np.ascontiguousarray(kps, dtype=KP_DTYPE)
+    desc = np.ascontiguousarray(desc, dtype=np.uint8).reshape(-1, 32)
+    boxes = np.ascontiguousarray(boxes, dtype=BOX_DTYPE)
+    okps = np.zeros(max(len(kps), 1), KP_DTYPE)
+    odesc = np.zeros((max(len(kps), 1), 32), np.uint8)
+    m = lib().orc_filter_boxes(_p(kps), _p(desc), len(kps), _p(boxes), len(boxes), ct.c_uint64(drop_mask), _p(okps), _p(odesc))
+    return okps[:m].copy(), odesc[:m].copy()
+
+
 def synth_descriptors(seed, first_row, nrows):
     out = np.zeros((nrows, 32), np.uint8)
     lib().orc_synth_descriptors(ct.c_uint32(seed), ct.c_uint64(first_row), nrows, _p(out))

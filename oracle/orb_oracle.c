@@ -967,6 +967,37 @@ void orc_synth_depth(uint32_t seed, int frame, int w, int h, uint16_t *out, size
             out[(size_t)y * step + x] = (uint16_t)d;
         }
 }
+/* YOLO-style dynamic-object boxes for BASELINE configs[4] (four per frame, ~15 % of the area, class "person"):
+ * centre on a quarter-pixel grid, size 15-25 % of the frame per axis; box 2 is of another class (1) so that the first-containing-
+ * box rule (backend.cpp:1015-1026) matters where it overlaps a "person" box (class 0).  Returns the number written (4). */
+int orc_synth_boxes(uint32_t seed, int frame, int w, int h, orc_box *out)
+{
+    for (int b = 0; b < 4; b++) {
+        uint32_t h0 = syn_hash((uint32_t)frame, (uint32_t)b, seed ^ 0xB0B0B0B0u), h1 = syn_hash((uint32_t)frame, (uint32_t)b, seed ^ 0x0B0B0B0Bu);
+        out[b].cx = (double)(h0 % (uint32_t)(4 * w)) / 4.0;
+        out[b].cy = (double)((h0 >> 13) % (uint32_t)(4 * h)) / 4.0;
+        out[b].w = (double)w * (double)(150 + h1 % 101) / 1000.0;
+        out[b].h = (double)h * (double)(150 + (h1 >> 11) % 101) / 1000.0;
+        out[b].class_id = b == 2 ? 1 : 0;
+        out[b].pad = 0;
+    }
+    return 4;
+}
+/* Backend::categorizeObservation + filtered_objects_ over a keypoint list (backend.cpp:1011-1029, 746-751): stable compaction of the
+ * keypoints whose first containing box is not of a class in drop_mask */
+int orc_filter_boxes(const orc_keypoint *kps, const uint8_t *desc, int n, const orc_box *boxes, int nboxes, uint64_t drop_mask,
+                     orc_keypoint *okps, uint8_t *odesc)
+{
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        const int c = orc_categorize(kps[i].x, kps[i].y, boxes, nboxes);
+        if (c >= 0 && c < 64 && ((drop_mask >> c) & 1ull)) continue;
+        okps[m] = kps[i];
+        memcpy(odesc + (size_t)m * 32, desc + (size_t)i * 32, 32);
+        m++;
+    }
+    return m;
+}
 /* landmark-database rows: counter-based, 32 B per row, uniform bytes */
 void orc_synth_descriptors(uint32_t seed, uint64_t first_row, int nrows, uint8_t *out)
 {

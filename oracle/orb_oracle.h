@@ -121,6 +121,9 @@ void orc_bgr2gray(const uint8_t *bgr, int w, int h, size_t sstep, uint8_t *gray,
 void orc_synth_gray(uint32_t seed, int frame, int w, int h, uint8_t *out, size_t step);
 void orc_synth_depth(uint32_t seed, int frame, int w, int h, uint16_t *out, size_t step_elems);
 void orc_synth_descriptors(uint32_t seed, uint64_t first_row, int nrows, uint8_t *out);
+int  orc_synth_boxes(uint32_t seed, int frame, int w, int h, orc_box *out /*4*/);
+int  orc_filter_boxes(const orc_keypoint *kps, const uint8_t *desc, int n, const orc_box *boxes, int nboxes, uint64_t drop_mask,
+                      orc_keypoint *okps, uint8_t *odesc);
 
 /* libstdc++ std::sort emulation on (count, ULx) keys, exported for its own test */
 void orc_introsort_pairs(int32_t *cnt, int32_t *ulx, int32_t *payload, int n);

@@ -104,6 +104,16 @@ public:
 };
 static_assert(sizeof(KeyPoint) == 28, "cv::KeyPoint layout");
 
+// cv::DMatch: 16-byte POD (used by the C++ adapter's OpenCV build mode, dynamic-visual-slam_b200/host/ORBextractor.hpp)
+struct DMatch {
+    DMatch() : queryIdx(-1), trainIdx(-1), imgIdx(-1), distance(3.402823466e+38f) {}
+    DMatch(int q, int t, float d) : queryIdx(q), trainIdx(t), imgIdx(-1), distance(d) {}
+    int queryIdx, trainIdx, imgIdx;
+    float distance;
+};
+static_assert(sizeof(DMatch) == 16, "cv::DMatch layout");
+namespace Error { enum { StsError = -2, StsBadArg = -5 }; }
+
 enum { BORDER_CONSTANT = 0, BORDER_REPLICATE = 1, BORDER_REFLECT = 2, BORDER_WRAP = 3, BORDER_REFLECT_101 = 4,
        BORDER_REFLECT101 = 4, BORDER_DEFAULT = 4, BORDER_ISOLATED = 16 };
 enum { INTER_NEAREST = 0, INTER_LINEAR = 1, INTER_CUBIC = 2, INTER_AREA = 3, INTER_LINEAR_EXACT = 5 };
@@ -235,3 +245,6 @@ typedef void (*ShimFastHook)(const ShimFastCall&, void* user);
 void shim_set_fast_hook(ShimFastHook hook, void* user);
 
 }  // namespace cv
+
+#define CV_Error(code, msg) throw cv::Exception(std::string(msg))
+#define CV_Assert(expr) do { if (!(expr)) throw cv::Exception(std::string("Assertion failed: ") + #expr); } while (0)

@@ -25,3 +25,14 @@ def oracle(built):
     import c_oracle
     c_oracle.lib()
     return c_oracle
+
+
+@pytest.fixture(scope="session")
+def refx(built):
+    """The REFERENCE's own ORBextractor.cpp, compiled unmodified (oracle/_ref, built in the container where /root/reference exists;
+    the prebuilt library travels to the GPU box).  None where it is unavailable — tests/test_gpu_parity.py::test_reference_binary_present
+    makes that loud on the GPU box."""
+    import ref_oracle
+    if not ref_oracle.available():
+        return None
+    return ref_oracle.RefExtractor()

@@ -25,8 +25,14 @@ def _kp_table(k):
                      k["class_id"].astype(np.float32)], 1)
 
 
+def test_reference_binary_present(refx):
+    """the compiled reference (oracle/_ref/libref_orbextractor.so) must have travelled to the GPU box: the parity tests below compare
+    the CUDA path with it directly, not only with the C restatement"""
+    assert refx is not None
+
+
 @pytest.mark.parametrize("w,h,seed", SIZES)
-def test_stages_bit_exact(ex, oracle, w, h, seed):
+def test_stages_bit_exact(ex, oracle, refx, w, h, seed):
     g = oracle.synth_gray(seed, 0, w, h)
     orc = oracle.COracle()
     ref = orc.extract(g, trace=True)
@@ -53,6 +59,11 @@ def test_stages_bit_exact(ex, oracle, w, h, seed):
     assert len(kps) == len(ref["kps"])
     assert np.array_equal(kps.view(np.uint8), ref["kps"].view(np.uint8)), "keypoints"
     assert np.array_equal(desc, ref["desc"]), "descriptors"
+    # the same against the reference's own compiled ORBextractor.cpp: operator() output and its public mvImagePyramid
+    r = refx.extract(g)
+    assert r["ret"] == len(kps) and np.array_equal(kps.view(np.uint8), r["kps"].view(np.uint8)) and np.array_equal(desc, r["desc"]), "vs compiled reference"
+    for l in range(8):
+        assert np.array_equal(ex.pyramid_level(l), refx.level(l)), "mvImagePyramid[%d] of the compiled reference" % l
 
 
 def test_separate_blur_path_and_border_keypoints(ex, oracle):
@@ -100,8 +111,8 @@ def test_full_hd_and_other_parameters(built, oracle):
             e.close()
 
 
-@pytest.mark.parametrize("w,h", [(257, 193), (511, 383), (513, 385), (1027, 771), (389, 263), (1281, 721), (833, 479), (1279, 719), (96, 80)])
-def test_awkward_sizes(built, oracle, w, h):
+@pytest.mark.parametrize("w,h", [(257, 193), (511, 383), (513, 385), (1027, 771), (389, 263), (1281, 721), (833, 479), (1279, 719), (100, 100), (160, 120)])
+def test_awkward_sizes(built, oracle, refx, w, h):
     """Sizes around the tile boundaries of the kernels (256-px blur tiles, 192-px resize tiles, 16-byte TMA columns)."""
     import orbx
     e = orbx.ORBextractor(max_width=w, max_height=h)
@@ -116,6 +127,35 @@ def test_awkward_sizes(built, oracle, w, h):
             r = ref["cands"][l]
             assert sorted(map(tuple, c.tolist())) == sorted(zip(r["x"].tolist(), r["y"].tolist(), r["score"].tolist())), ("FAST", l)
         assert np.array_equal(kps.view(np.uint8), ref["kps"].view(np.uint8)) and np.array_equal(desc, ref["desc"])
+        r = refx.extract(g)
+        assert np.array_equal(kps.view(np.uint8), r["kps"].view(np.uint8)) and np.array_equal(desc, r["desc"]), "vs compiled reference"
+    finally:
+        e.close()
+
+
+def test_frame_sizes_where_the_reference_throws_are_refused(built, oracle):
+    """Small or very elongated frames make the reference throw (std::length_error from vpIniNodes.resize, ORBextractor.cpp:559-566;
+    cv::resize on a vanished level) or index an empty vector (:586) — pinned with the compiled reference in
+    tests/test_oracle_vs_ref.py::test_defined_domain_equals_reference.  The library refuses exactly those sizes."""
+    import orbx
+    orc = oracle.COracle()
+    e = orbx.ORBextractor(max_width=320, max_height=320)
+    try:
+        seen = set()
+        for w in (1, 3, 20, 33, 64, 67, 96, 100, 115, 130, 160, 240, 300):
+            for h in (1, 20, 32, 40, 64, 80, 100, 115, 200, 240):
+                st = orc.geometry_status(w, h)
+                seen.add(st)
+                g = oracle.synth_gray(6, 0, w, h)
+                if st == 0:
+                    kps, desc = e(g)
+                    want = orc.extract(g)
+                    assert np.array_equal(kps.view(np.uint8), want["kps"].view(np.uint8)) and np.array_equal(desc, want["desc"]), (w, h)
+                else:
+                    with pytest.raises(orbx.OrbxError) as err:
+                        e(g)
+                    assert err.value.status == orbx.E_UNSUPPORTED, (w, h, st)
+        assert seen == {0, 1, 2, 3}
     finally:
         e.close()
 

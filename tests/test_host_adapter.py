@@ -70,3 +70,29 @@ def test_adapter_matches_oracle(adapter_exe, oracle, tmp_path):
     gq = mo[mo["distance"] < 50.0]["queryIdx"]
     idx = oracle.cull_keyframe(r1["kps"]["response"], gq)
     assert nb == len(idx) > len(gq) and np.array_equal(bk.view(np.uint8), r1["kps"][idx].view(np.uint8)) and np.array_equal(bd, r1["desc"][idx])
+
+
+def test_adapter_opencv_build_mode_compiles(built, tmp_path):
+    """-DORBX_WITH_OPENCV (the branch the ROS nodes compile: cv::InputArray / cv::OutputArray / cv::noArray() call shape) against the
+    OpenCV-shaped header shim (oracle/ref_shim) — the image has no OpenCV C++ headers, so this is the closest compile check available."""
+    src = tmp_path / "ocv_mode.cpp"
+    src.write_text('#define ORBX_WITH_OPENCV\n#include "dynamic-visual-slam_b200/host/ORBextractor.hpp"\n'
+                   'int main() { orbx::ORBextractor e(1000, 1.2f, 8, 20, 7); orbx::BFMatcher m(e); cv::Mat g, d; std::vector<cv::KeyPoint> k;\n'
+                   '  std::vector<int> lap = {0, 0}; int n = e(g, cv::noArray(), k, d, lap); std::vector<cv::DMatch> mm; m.match(d, d, mm);\n'
+                   '  orbx::LandmarkDB db(e, 16); return n + (int)db.rows(); }\n')
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I" + os.path.join(ROOT, "oracle", "ref_shim"), "-I" + ROOT, str(src)])
+
+
+@pytest.mark.gpu
+def test_same_callsite_on_reference_class_and_dropin(built, oracle, tmp_path):
+    """oracle/_ref/callsite_check: ONE templated call site (the frontend's operator() call, frontend.cpp:1094-1095) instantiated on the
+    reference's own compiled ORB_SLAM3::ORBextractor and on the drop-in adapter, results compared in-process, incl. the vLappingArea
+    mono / stereo split (ORBextractor.cpp:1152-1166), the empty-image return and the getters."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "callsite_check")
+    assert os.path.exists(exe), "oracle/_ref/callsite_check was not built in the container (make -C oracle _ref)"
+    for (w, h, seed) in [(640, 480, 5), (1280, 720, 3)]:
+        p = str(tmp_path / ("g%d.raw" % w))
+        oracle.synth_gray(seed, 0, w, h).tofile(p)
+        r = subprocess.run([exe, str(w), str(h), p], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert r.stdout.count("equal") >= 7 and "DIFFERENT" not in r.stdout
