@@ -117,6 +117,10 @@ __device__ __forceinline__ FastRow fast_row(const uint32_t *q)
 #define FAST_RMAX 16                 // tallest sweep unit: a 37-row cell then takes 3 units per word column (30 units = ONE warp iteration at 94 %
                                      // lane use) instead of 5 units of 8 rows (50 units = two iterations at 78 %)
 #endif
+#ifndef FAST_PAIRS
+#define FAST_PAIRS 4                 // opposite ring pairs tested in the sweep: 4 = (0,8) (4,12) (2,10) (6,14); 2 = (0,8) (4,12) only
+#endif
+#if FAST_PAIRS == 4
 template <int TP> __device__ __noinline__ uint2 fast_sweep7(const uint32_t *q, uint32_t HM, uint32_t KK, int R)
 {
     FastRow w[7];
@@ -142,6 +146,37 @@ template <int TP> __device__ __noinline__ uint2 fast_sweep7(const uint32_t *q, u
     }
     return make_uint2(fl0, fl1);
 }
+#else
+// Two-pair sweep: the vertical pair (0,8) and the horizontal pair (4,12) only.  On textured frames they alone reject 97.5 % of the pixels
+// (all four: 97.8 %), for half the arithmetic: a row needs its own word plus the two 3-byte-shifted views when it is the centre row,
+// and the vertical difference |I(y+3) - I(y)| of a row serves the centres y and y+3 (it is kept three rows).
+template <int TP> __device__ __noinline__ uint2 fast_sweep7(const uint32_t *q, uint32_t HM, uint32_t KK, int R)
+{
+    uint32_t c[7], dv[3];                                                        // c: rows k..k+6 (mod 7); dv[j % 3] = |C(j+3) - C(j)|
+#pragma unroll
+    for (int k = 0; k < 6; k++) c[k] = q[k * (TP / 4)];
+#pragma unroll
+    for (int j = 0; j < 3; j++) dv[j] = __vabsdiffu4(c[j + 3], c[j]);
+    uint32_t fl0 = 0u, fl1 = 0u;
+#pragma unroll
+    for (int k = 0; k < FAST_RMAX; k++) {
+        if (k >= R) break;
+        const uint32_t *row = q + (k + 3) * (TP / 4);                            // the centre row of detection row k
+        const uint32_t L = row[-1], Rw = row[1];
+        c[(k + 6) % 7] = q[(k + 6) * (TP / 4)];
+        const uint32_t C0 = c[(k + 3) % 7];
+        const uint32_t up = dv[k % 3];                                           // |C(k+3) - C(k)|: ring pixel 8 (dy = -3) of centre k+3
+        const uint32_t dn = __vabsdiffu4(c[(k + 6) % 7], C0);                    // ring pixel 0 (dy = +3)
+        dv[k % 3] = dn;                                                          // = |C(j+3) - C(j)| for j = k+3, needed again at k+3
+        const uint32_t t0 = (up | dn) & HM;
+        const uint32_t t1 = (__vabsdiffu4(__byte_perm(C0, Rw, 0x6543), C0) | __vabsdiffu4(__byte_perm(L, C0, 0x4321), C0)) & HM;
+        const uint32_t acc = (t0 | (t0 + KK)) & (t1 | (t1 + KK));
+        if (k < 8) fl0 |= (acc >> k) & (0x80808080u >> k);
+        else fl1 |= (acc >> (k - 8)) & (0x80808080u >> (k - 8));
+    }
+    return make_uint2(fl0, fl1);
+}
+#endif
 
 // loose pre-test threshold T = 2^sh - 1 <= th:  |d| > T  <=>  (|d| & HM) != 0;  t + KK sets bit 7 of every byte with t >= 2^sh
 __device__ __forceinline__ void fast_masks(int th, uint32_t &HM, uint32_t &KK)

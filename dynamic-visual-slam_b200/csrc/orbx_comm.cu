@@ -1,0 +1,154 @@
+// orbx_comm.cu — the ONE collective of the path, behind the C ABI: sharded landmark association (BASELINE configs[3]).
+//
+// Backend::associateObservation (reference backend.cpp:1064-1120) loops over every landmark of a category; with the map's descriptor
+// rows sharded over the GPUs of one box (contiguous global index ranges) a query batch is answered by
+//     per-shard kernel (k_match_partial / k_assoc_partial)  ->  ncclAllGather of nq x 16 B per rank  ->  k_merge_top2 / k_assoc_merge
+// all enqueued on the handle's stream: no host synchronisation between the query and the merged result, every rank ends with the full
+// answer.  NCCL is loaded at run time (dlopen "libnccl.so.2"; inside a torch process that is the library torch already loaded), so the
+// library has no link-time NCCL dependency and single-GPU users never touch it.  The communicator is the library's own: the caller only
+// moves the 128-byte unique id from rank 0 to the other ranks (torch.distributed broadcast in bench.py, anything in a C++ backend).
+#include "orbx_internal.h"
+#include <dlfcn.h>
+#include <mutex>
+
+namespace {
+typedef struct ncclComm *ncclComm_t;
+struct NcclId { char internal[128]; };                      // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128)
+enum { kNcclSuccess = 0, kNcclUint8 = 1 };
+struct NcclApi {
+    void *lib;
+    int (*GetUniqueId)(NcclId *);
+    int (*CommInitRank)(ncclComm_t *, int, NcclId, int);
+    int (*CommDestroy)(ncclComm_t);
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t);
+    const char *(*GetErrorString)(int);
+    int (*GetVersion)(int *);
+};
+NcclApi g_nccl = {};
+std::string g_nccl_err;
+
+bool load_nccl()
+{
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (g_nccl.lib) return true;
+    const char *names[] = { "libnccl.so.2", "libnccl.so" };
+    void *lib = nullptr;
+    for (const char *n : names) if ((lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL)) != nullptr) break;
+    if (!lib) { g_nccl_err = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "not found"); return false; }
+    NcclApi a = {};
+    a.lib = lib;
+    a.GetUniqueId = (int (*)(NcclId *))dlsym(lib, "ncclGetUniqueId");
+    a.CommInitRank = (int (*)(ncclComm_t *, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
+    a.CommDestroy = (int (*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
+    a.AllGather = (int (*)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclAllGather");
+    a.GetErrorString = (const char *(*)(int))dlsym(lib, "ncclGetErrorString");
+    a.GetVersion = (int (*)(int *))dlsym(lib, "ncclGetVersion");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather) { g_nccl_err = "libnccl.so.2 lacks a required symbol"; dlclose(lib); return false; }
+    g_nccl = a;
+    return true;
+}
+}  // namespace
+
+struct orbx_comm {
+    orbx_handle *h;
+    ncclComm_t comm;
+    int nranks, rank;
+    uint8_t *d_part, *d_all; size_t part_cap, all_cap;       // per-rank block and the gathered [rank][nq] blocks
+};
+
+#define ORBX_NCCL(h, call) do { int r_ = (call); if (r_ != kNcclSuccess) { \
+    (h)->err = std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "NCCL error"); return ORBX_E_CUDA; } } while (0)
+
+extern "C" orbx_status orbx_comm_get_unique_id(void *id128)
+{
+    if (!id128) return ORBX_E_INVALID;
+    if (!load_nccl()) return ORBX_E_UNSUPPORTED;
+    NcclId id;
+    if (g_nccl.GetUniqueId(&id) != kNcclSuccess) { g_nccl_err = "ncclGetUniqueId failed"; return ORBX_E_CUDA; }
+    memcpy(id128, &id, sizeof(id));
+    return ORBX_OK;
+}
+extern "C" const char *orbx_comm_last_error(void) { return g_nccl_err.c_str(); }
+
+extern "C" orbx_status orbx_comm_create(orbx_handle *h, int32_t nranks, int32_t rank, const void *id128, orbx_comm **out)
+{
+    if (!h || !out || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return ORBX_E_INVALID;
+    *out = nullptr;
+    cudaSetDevice(h->device);
+    if (!load_nccl()) { h->err = g_nccl_err; return ORBX_E_UNSUPPORTED; }
+    NcclId id;
+    memcpy(&id, id128, sizeof(id));
+    orbx_comm *c = new orbx_comm();
+    memset(c, 0, sizeof(*c));
+    c->h = h; c->nranks = nranks; c->rank = rank;
+    const int r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+    if (r != kNcclSuccess) { h->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); delete c; return ORBX_E_CUDA; }
+    *out = c;
+    return ORBX_OK;
+}
+extern "C" void orbx_comm_destroy(orbx_comm *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->h->device);
+    cudaStreamSynchronize(c->h->stream);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    if (c->d_part) cudaFree(c->d_part);
+    if (c->d_all) cudaFree(c->d_all);
+    delete c;
+}
+extern "C" int32_t orbx_comm_ranks(const orbx_comm *c) { return c ? c->nranks : 0; }
+extern "C" int32_t orbx_comm_rank(const orbx_comm *c) { return c ? c->rank : -1; }
+
+static orbx_status comm_scratch(orbx_comm *c, size_t part_bytes)
+{
+    orbx_handle *h = c->h;
+    if (part_bytes > c->part_cap) {
+        cudaStreamSynchronize(h->stream);
+        if (c->d_part) cudaFree(c->d_part);
+        if (c->d_all) cudaFree(c->d_all);
+        c->d_part = c->d_all = nullptr; c->part_cap = c->all_cap = 0;
+        ORBX_CUDA(h, cudaMalloc(&c->d_part, part_bytes));
+        ORBX_CUDA(h, cudaMalloc(&c->d_all, part_bytes * (size_t)c->nranks));
+        c->part_cap = part_bytes; c->all_cap = part_bytes * (size_t)c->nranks;
+    }
+    return ORBX_OK;
+}
+
+// per-shard top-2 -> all-gather -> merge, stream-ordered.  Every rank calls it with the same nq and its own shard; d_query is this rank's
+// copy of the (replicated) queries.  d_out[nq] receives the GLOBAL top-2 (lexicographic (distance, index) min over all shards = BFMatcher's
+// lowest-index tie-break).
+extern "C" orbx_status orbx_db_query_top2_sharded_device(orbx_db *db, orbx_comm *c, const uint8_t *d_query, int32_t nq, orbx_top2 *d_out)
+{
+    if (!db || !c || nq < 0 || !d_out || (nq > 0 && !d_query) || db->h != c->h) return ORBX_E_INVALID;
+    orbx_handle *h = db->h;
+    cudaSetDevice(h->device);
+    if (nq == 0) return ORBX_OK;
+    const size_t bytes = (size_t)nq * sizeof(orbx_top2);
+    orbx_status st = comm_scratch(c, bytes);
+    if (st != ORBX_OK) return st;
+    if ((st = orbx_db_query_top2_device(db, d_query, nq, (orbx_top2 *)c->d_part)) != ORBX_OK) return st;
+    ORBX_NCCL(h, g_nccl.AllGather(c->d_part, c->d_all, bytes, kNcclUint8, c->comm, h->stream));
+    launch_merge_top2(h, (const orbx_top2 *)c->d_all, c->nranks, nq, d_out);
+    ORBX_CUDA(h, cudaGetLastError());
+    return ORBX_OK;
+}
+
+// the whole of Backend::associateObservation over a sharded map: per-shard reprojection-gated best candidate -> all-gather -> merge
+// (smallest error, ties to the lowest global row)
+extern "C" orbx_status orbx_db_associate_sharded_device(orbx_db *db, orbx_comm *c, const uint8_t *d_query, const float *d_query_px, int32_t nq,
+                                                        const orbx_pose *pose, float max_desc_dist, double max_reproj_err, orbx_assoc *d_out)
+{
+    if (!db || !c || nq < 0 || !pose || !d_out || (nq > 0 && (!d_query || !d_query_px)) || db->h != c->h) return ORBX_E_INVALID;
+    orbx_handle *h = db->h;
+    cudaSetDevice(h->device);
+    if (nq == 0) return ORBX_OK;
+    const size_t bytes = (size_t)nq * sizeof(orbx_assoc);
+    orbx_status st = comm_scratch(c, bytes);
+    if (st != ORBX_OK) return st;
+    if ((st = orbx_db_associate_device(db, d_query, d_query_px, nq, pose, max_desc_dist, max_reproj_err, (orbx_assoc *)c->d_part)) != ORBX_OK) return st;
+    ORBX_NCCL(h, g_nccl.AllGather(c->d_part, c->d_all, bytes, kNcclUint8, c->comm, h->stream));
+    launch_assoc_merge(h, (const orbx_assoc *)c->d_all, c->nranks, nq, d_out);
+    ORBX_CUDA(h, cudaGetLastError());
+    return ORBX_OK;
+}

@@ -15,7 +15,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "liborbx.so"))
+# ORBX_LIB selects another build of the same library (kernel experiments: csrc/Makefile variant builds); never a fallback
+LIB_PATH = os.environ.get("ORBX_LIB") or os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "liborbx.so"))
 
 OK, E_INVALID, E_CUDA, E_CAPACITY, E_EMPTY, E_NOMEM, E_UNSUPPORTED = range(7)
 MAX_LEVELS = 16
@@ -130,6 +131,14 @@ def load():
         "orbx_extract_batch_submit": (i32, [vp, vp, i32, i32, i32, sz, vp, sz, vp, vp, i32, vp, vp]),
         "orbx_track_batch_submit": (i32, [vp, vp, i32, i32, i32, sz, vp, sz, vp, vp, i32, vp, vp, vp, f32, vp]),
         "orbx_batch_wait": (i32, [vp, i32]),
+        "orbx_comm_get_unique_id": (i32, [vp]),
+        "orbx_comm_last_error": (ct.c_char_p, []),
+        "orbx_comm_create": (i32, [vp, i32, i32, vp, vp]),
+        "orbx_comm_destroy": (None, [vp]),
+        "orbx_comm_ranks": (i32, [vp]),
+        "orbx_comm_rank": (i32, [vp]),
+        "orbx_db_query_top2_sharded_device": (i32, [vp, vp, vp, i32, vp]),
+        "orbx_db_associate_sharded_device": (i32, [vp, vp, vp, vp, i32, vp, f32, ct.c_double, vp]),
         "orbx_extract_batch_boxes_device": (i32, [vp, vp, i32, i32, i32, sz, sz, vp, sz, sz, vp, vp, i32, u64, vp, vp, i32, vp]),
         "orbx_extract_batch_boxes": (i32, [vp, vp, i32, i32, i32, sz, vp, sz, vp, vp, u64, vp, vp, i32, vp]),
         "orbx_track_batch_boxes_device": (i32, [vp, vp, i32, i32, i32, sz, sz, vp, sz, sz, vp, vp, i32, u64, vp, vp, i32, vp, vp, vp, f32]),
@@ -542,6 +551,43 @@ class BFMatcher:
         return self.ex.match(query, train, k=2).reshape(-1, 2)
 
 
+class Comm:
+    """The library's own NCCL communicator for the sharded landmark database (orbx_comm).  `dist` = an initialised torch.distributed
+    process group used ONLY to carry rank 0's 128-byte unique id to the other ranks (any transport would do)."""
+
+    def __init__(self, extractor, dist=None, nranks=None, rank=None, unique_id=None):
+        self.ex, self.L = extractor, extractor.L
+        if dist is not None:
+            import torch
+            nranks, rank = dist.get_world_size(), dist.get_rank()
+            buf = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                raw = (ct.c_uint8 * 128)()
+                st = self.L.orbx_comm_get_unique_id(raw)
+                if st != OK:
+                    raise OrbxError(st, (self.L.orbx_comm_last_error() or b"").decode())
+                buf = torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone()
+            if dist.get_backend() == "nccl":
+                buf = buf.cuda()
+            dist.broadcast(buf, 0)
+            unique_id = bytes(buf.cpu().numpy().tobytes())
+        self.nranks, self.rank = int(nranks), int(rank)
+        self._c = ct.c_void_p()
+        raw = (ct.c_uint8 * 128).from_buffer_copy(unique_id)
+        extractor._check(self.L.orbx_comm_create(extractor.handle, self.nranks, self.rank, raw, ct.byref(self._c)))
+
+    def close(self):
+        if self._c.value:
+            self.L.orbx_comm_destroy(self._c)
+            self._c = ct.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class LandmarkDB:
     """Row-sharded landmark descriptor database (Backend::associateObservation, backend.cpp:1064-1083)."""
 
@@ -581,6 +627,14 @@ class LandmarkDB:
 
     def query_top2_device(self, d_query, nq, d_out):
         self.ex._check(self.L.orbx_db_query_top2_device(self._db, d_query, nq, d_out))
+
+    def query_top2_sharded_device(self, comm, d_query, nq, d_out):
+        """collective: per-shard top-2 -> ncclAllGather -> merge on the handle's stream (orbx_db_query_top2_sharded_device)"""
+        self.ex._check(self.L.orbx_db_query_top2_sharded_device(self._db, comm._c, d_query, nq, d_out))
+
+    def associate_sharded_device(self, comm, d_query, d_query_px, nq, pose, d_out, max_desc_dist=50.0, max_reproj_err=5.0):
+        self.ex._check(self.L.orbx_db_associate_sharded_device(self._db, comm._c, d_query, d_query_px, nq, _p(pose), ct.c_float(max_desc_dist),
+                                                               ct.c_double(max_reproj_err), d_out))
 
     def set_positions(self, xyz, first_row=0):
         xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)

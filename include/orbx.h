@@ -268,6 +268,26 @@ orbx_status orbx_db_associate_device(orbx_db *db, const uint8_t *d_query, const 
                                      float max_desc_dist, double max_reproj_err, orbx_assoc *d_out);
 orbx_status orbx_merge_assoc_device(orbx_handle *h, const orbx_assoc *d_parts, int32_t nshards, int32_t nq, orbx_assoc *d_out);
 
+/* ---- sharded landmark database over the GPUs of one box: the ONE collective of the path (BASELINE configs[3]) ----
+ * One process (or thread) per GPU, each with its own handle and its shard (orbx_db_create with first_index = global index of its row 0).
+ * orbx_comm wraps an NCCL communicator owned by the library (NCCL is loaded with dlopen at first use; ORBX_E_UNSUPPORTED if absent):
+ * rank 0 calls orbx_comm_get_unique_id and the caller carries the 128 bytes to the other ranks by any means, then EVERY rank calls
+ * orbx_comm_create (collective).  The *_sharded_device calls are collective too (same nq on every rank, the queries replicated) and
+ * enqueue per-shard kernel -> ncclAllGather (nq x 16 B per rank) -> merge kernel on the handle's stream: no host synchronisation
+ * between query and merged result; every rank ends with the global answer (lexicographic (distance, index) resp. (error, index)
+ * minimum over the shards = what one unsharded database returns, BFMatcher's lowest-index tie-break included).                    */
+typedef struct orbx_comm orbx_comm;
+#define ORBX_COMM_ID_BYTES 128
+orbx_status orbx_comm_get_unique_id(void *id128);
+const char *orbx_comm_last_error(void);
+orbx_status orbx_comm_create(orbx_handle *h, int32_t nranks, int32_t rank, const void *id128, orbx_comm **out);
+void        orbx_comm_destroy(orbx_comm *c);
+int32_t     orbx_comm_ranks(const orbx_comm *c);
+int32_t     orbx_comm_rank(const orbx_comm *c);
+orbx_status orbx_db_query_top2_sharded_device(orbx_db *db, orbx_comm *c, const uint8_t *d_query, int32_t nq, orbx_top2 *d_out);
+orbx_status orbx_db_associate_sharded_device(orbx_db *db, orbx_comm *c, const uint8_t *d_query, const float *d_query_px, int32_t nq,
+                                             const orbx_pose *pose, float max_desc_dist, double max_reproj_err, orbx_assoc *d_out);
+
 /* ---- feature culling for the backend: Frontend::syncCallback, frontend.cpp:1168-1218, SURVEY §8(f) rank 3 ----
  * The set the frontend hands to isKeyframe / publishKeyframe: the keypoint of every (geometrically consistent) match, in match order,
  * then the unmatched keypoints sorted by response — std::sort with `a.first > b.first`, so equal responses stay where libstdc++'s
