@@ -261,6 +261,7 @@ def main():
     ap.add_argument("--separate-blur", action="store_true", help="blur every level with its own kernel (ORBX_OPT_FUSED_BLUR = 0) instead of inside the descriptor kernel")
     ap.add_argument("--no-pdl", action="store_true", help="plain stream order instead of programmatic dependent launch (ORBX_OPT_PDL = 0)")
     ap.add_argument("--fast-ctas", type=int, default=0, help="resident FAST warps per SM in the overlapped schedule (0 = library default)")
+    ap.add_argument("--overlap", action="store_true", help="two staggered half-batches on two streams (ORBX_OPT_OVERLAP = 1; measured slower than one chain)")
     ap.add_argument("--host-chunk", type=int, default=0, help="frames per pipeline chunk of the host-buffer call (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-assoc", action="store_true", help="skip the landmark-association leg")
@@ -297,6 +298,8 @@ def main():
         ex.set_fused_blur(False)
     if args.no_pdl:
         ex.set_pdl(False)
+    if args.overlap:
+        ex.set_overlap(True)
     L, hnd = ex.L, ex.handle
     stream = torch.cuda.ExternalStream(ex.stream, device=dev)
 

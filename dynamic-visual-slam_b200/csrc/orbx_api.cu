@@ -228,7 +228,7 @@ static orbx_status set_geometry(orbx_handle *h, int w, int hgt)
     }
     if (!btiles.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_blur_tiles, btiles.data(), btiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     G.total_strips = (int)strips.size();
-    h->geo = G; h->pyr_slab = G.pyr_bytes; h->blur_slab = G.blur_bytes; h->tmap_valid = false;
+    h->geo = G; h->pyr_slab = G.pyr_bytes; h->blur_slab = G.blur_bytes; h->tmap_valid = false; h->alt.tmap_valid = false;
     return ORBX_OK;
 }
 
@@ -253,6 +253,15 @@ extern "C" void orbx_destroy(orbx_handle *h)
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_fork0) cudaEventDestroy(h->ev_fork0);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_lane_fork) cudaEventDestroy(h->ev_lane_fork);
+    if (h->ev_lane_join) cudaEventDestroy(h->ev_lane_join);
+    if (h->ev_prev_ready) cudaEventDestroy(h->ev_prev_ready);
+    if (h->alt.allocated) {
+        void *lane[] = { h->alt.d_pyr, h->alt.d_cand, h->alt.d_cand2, h->alt.d_qtmp, h->alt.d_owner, h->alt.d_owner2, h->alt.d_ncand, h->alt.d_nsel, h->alt.d_sel,
+                         h->alt.d_kps_all, h->alt.d_desc_all, h->alt.d_count_all, h->alt.d_mpart };
+        for (void *p : lane) if (p) cudaFree(p);
+        if (h->alt.stream) cudaStreamDestroy(h->alt.stream);
+    }
     for (int i = 0; i < 2; i++) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]); if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]); }
     delete h;
 }
@@ -274,7 +283,8 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     if (p.device < 0 || p.device >= ndev) { g_create_err = "device ordinal out of range"; return ORBX_E_INVALID; }
     orbx_handle *h = new orbx_handle();
     h->prm = p; h->device = p.device; h->launches = 0; h->geo.width = -1; h->geo.height = -1;
-    h->prof_on = 0; h->prof_n = 0; h->prev_valid = 0; h->opt_fused_blur = 1; h->blur_valid = false; h->opt_pdl = 1;
+    h->prof_on = 0; h->prof_n = 0; h->prev_valid = 0; h->opt_fused_blur = 1; h->blur_valid = false; h->opt_pdl = 1; h->opt_overlap = 0; h->in_overlap = false; h->ev_after_pyramid = nullptr;
+    memset(&h->alt, 0, sizeof(h->alt));
     memset(h->prof_ms, 0, sizeof(h->prof_ms)); memset(h->prof_cnt, 0, sizeof(h->prof_cnt));
     CREATE_CUDA(cudaSetDevice(p.device));
     cudaDeviceProp prop;
@@ -290,6 +300,9 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_fork0, cudaEventDisableTiming));
     CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_lane_fork, cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_lane_join, cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_prev_ready, cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) {
         CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
         CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
@@ -391,6 +404,7 @@ extern "C" orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t v
     if (option == ORBX_OPT_FAST_CTAS) { h->opt_fast_ctas = value > 0 ? value : 0; return ORBX_OK; }
     if (option == ORBX_OPT_FUSED_BLUR) { h->opt_fused_blur = value ? 1 : 0; return ORBX_OK; }
     if (option == ORBX_OPT_PDL) { h->opt_pdl = value ? 1 : 0; return ORBX_OK; }
+    if (option == ORBX_OPT_OVERLAP) { h->opt_overlap = value ? 1 : 0; return ORBX_OK; }
     h->err = "unknown option"; return ORBX_E_INVALID;
 }
 extern "C" void *orbx_stream(orbx_handle *h) { return h ? (void *)h->stream : nullptr; }
@@ -415,6 +429,10 @@ extern "C" orbx_status orbx_level_size(const orbx_handle *h, int32_t w, int32_t 
 // (`base` is subtracted from the offsets: a pipeline chunk stages only its own boxes)
 struct DevBoxes { const orbx_box *boxes; const int32_t *off; int base; int n; uint64_t drop_mask; };
 static const DevBoxes kNoBoxes = { nullptr, nullptr, 0, 0, 0 };
+static orbx_status pipeline_device(orbx_handle *h, bool track, const uint8_t *d_gray, int nframes, int width, int height, size_t step, size_t fstride,
+                                   const uint16_t *d_depth, size_t dstep, size_t dfstride, const DevBoxes &BX,
+                                   orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts,
+                                   orbx_dmatch *d_matches, int32_t *d_mcounts, float max_dist);
 
 static orbx_status run_pipeline(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride,
                                 const uint16_t *d_depth, size_t dstep, size_t dfstride, const DevBoxes &BX,
@@ -443,6 +461,7 @@ static orbx_status run_pipeline(orbx_handle *h, int nframes, const uint8_t *l0, 
         if (launch_blur(h, nframes, l0, l0_step, l0_fstride, h->aux_stream, 0, l0_tiles) != 0) { h->err = "cuTensorMapEncodeTiled failed (frame base/step must be 16-byte aligned)"; return ORBX_E_CUDA; }
     }
     if (launch_pyramid(h, nframes, l0, l0_step, l0_fstride) != 0) { h->err = "cuTensorMapEncodeTiled failed (frame base/step must be 16-byte aligned)"; return ORBX_E_CUDA; }   // ComputePyramid
+    if (h->ev_after_pyramid) ORBX_CUDA(h, cudaEventRecord(h->ev_after_pyramid, h->stream));
     if (side) {
         ORBX_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
         ORBX_CUDA(h, cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
@@ -493,7 +512,7 @@ extern "C" orbx_status orbx_extract_batch_boxes_device(orbx_handle *h, const uin
     if (nboxes_total < 0 || (nboxes_total > 0 && (!d_boxes || !d_box_offsets))) { h->err = "per-frame boxes need the box array and nframes + 1 offsets"; return ORBX_E_INVALID; }
     if (nboxes_total > 0 && cap > h->max_kp) { h->err = "cap_per_frame larger than the handle's max_keypoints"; return ORBX_E_INVALID; }
     const DevBoxes BX = { d_boxes, d_box_offsets, 0, nboxes_total, drop_mask };
-    return run_pipeline(h, nframes, d_gray, step, frame_stride, d_depth, dstep, dframe_stride, BX, d_kps, d_desc, cap, d_counts);
+    return pipeline_device(h, false, d_gray, nframes, width, height, step, frame_stride, d_depth, dstep, dframe_stride, BX, d_kps, d_desc, cap, d_counts, nullptr, nullptr, 0.f);
 }
 
 static orbx_status extract_one(orbx_handle *h, bool is_bgr, const uint8_t *gray, int32_t width, int32_t height, size_t step,
@@ -590,7 +609,9 @@ extern "C" void orbx_track_reset(orbx_handle *h)
     h->prev_valid = 0;
 }
 
-static orbx_status track_device(orbx_handle *h, const uint8_t *d_gray, int nframes, int width, int height, size_t step, size_t fstride,
+static orbx_status track_matches(orbx_handle *h, int nframes, orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts,
+                                 orbx_dmatch *d_matches, int32_t *d_mcounts, float max_dist);
+static orbx_status track_chain(orbx_handle *h, const uint8_t *d_gray, int nframes, int width, int height, size_t step, size_t fstride,
                                 const uint16_t *d_depth, size_t dstep, size_t dfstride, const DevBoxes &BX,
                                 orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts,
                                 orbx_dmatch *d_matches, int32_t *d_mcounts, float max_dist)
@@ -598,6 +619,14 @@ static orbx_status track_device(orbx_handle *h, const uint8_t *d_gray, int nfram
     if (cap > h->max_kp) { h->err = "cap_per_frame larger than the handle's max_keypoints"; return ORBX_E_INVALID; }
     orbx_status st = run_pipeline(h, nframes, d_gray, step, fstride, d_depth, dstep, dfstride, BX, d_kps, d_desc, cap, d_counts);
     if (st != ORBX_OK) return st;
+    return track_matches(h, nframes, d_kps, d_desc, cap, d_counts, d_matches, d_mcounts, max_dist);
+}
+
+// matcher_.match(filtered, prev) + `distance < max_dist` for every frame of a batch, then prev = last frame (frontend.cpp:1123-1132, 1258-1259)
+static orbx_status track_matches(orbx_handle *h, int nframes, orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts,
+                                 orbx_dmatch *d_matches, int32_t *d_mcounts, float max_dist)
+{
+    (void)d_kps;
     // frame 0 against the carried state (prev count is 0 on the first frame => no matches, count 0)
     if (launch_match_core(h, d_desc, d_counts, cap, 0, h->d_prev_desc, h->d_prev_count, h->max_kp, 0, nullptr, nullptr, 1, 0,
                           1, max_dist, 0, d_matches, (size_t)cap, d_mcounts, nullptr) != 0) { h->err = "out of device memory (match scratch)"; return ORBX_E_NOMEM; }
@@ -610,6 +639,98 @@ static orbx_status track_device(orbx_handle *h, const uint8_t *d_gray, int nfram
     ORBX_CUDA(h, cudaMemcpyAsync(h->d_prev_desc, d_desc + (size_t)(nframes - 1) * cap * ORBX_DESC_BYTES, (size_t)cap * ORBX_DESC_BYTES, cudaMemcpyDeviceToDevice, h->stream));
     ORBX_CUDA(h, cudaMemcpyAsync(h->d_prev_count, d_counts + (nframes - 1), sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
     h->prev_valid = 1;
+    ORBX_CUDA(h, cudaGetLastError());
+    return ORBX_OK;
+}
+
+
+// ---- ORBX_OPT_OVERLAP: two half-batches on two lanes (see OrbxLane) ----
+static orbx_status ensure_alt_lane(orbx_handle *h)
+{
+    OrbxLane &A = h->alt;
+    if (A.allocated) return ORBX_OK;
+    const size_t B = (size_t)h->prm.max_batch;
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    ORBX_CUDA(h, cudaStreamCreateWithPriority(&A.stream, cudaStreamNonBlocking, prio_hi));
+    A.allocated = true;                                           // from here on orbx_destroy releases whatever exists
+    ORBX_CUDA(h, cudaMalloc(&A.d_pyr, h->pyr_cap));
+    ORBX_CUDA(h, cudaMalloc(&A.d_cand, h->cand_cap * sizeof(uint32_t)));
+    ORBX_CUDA(h, cudaMalloc(&A.d_cand2, h->cand_cap * sizeof(uint32_t)));
+    ORBX_CUDA(h, cudaMalloc(&A.d_qtmp, h->cand_cap * sizeof(uint32_t)));
+    ORBX_CUDA(h, cudaMalloc(&A.d_owner, h->cand_cap * sizeof(uint16_t)));
+    ORBX_CUDA(h, cudaMalloc(&A.d_owner2, h->cand_cap * sizeof(uint16_t)));
+    ORBX_CUDA(h, cudaMalloc(&A.d_ncand, (B * ORBX_MAX_LEVELS + 4) * sizeof(int32_t)));
+    ORBX_CUDA(h, cudaMalloc(&A.d_nsel, B * ORBX_MAX_LEVELS * sizeof(int32_t)));
+    ORBX_CUDA(h, cudaMemset(A.d_nsel, 0, B * ORBX_MAX_LEVELS * sizeof(int32_t)));
+    ORBX_CUDA(h, cudaMalloc(&A.d_sel, h->sel_cap * sizeof(uint32_t)));
+    ORBX_CUDA(h, cudaMalloc(&A.d_kps_all, B * h->max_kp * sizeof(orbx_keypoint)));
+    ORBX_CUDA(h, cudaMalloc(&A.d_desc_all, B * h->max_kp * ORBX_DESC_BYTES));
+    ORBX_CUDA(h, cudaMalloc(&A.d_count_all, B * sizeof(int32_t)));
+    A.d_mpart = nullptr; A.mpart_cap = 0; A.tmap_valid = false; A.tmap_l0 = nullptr;
+    return ORBX_OK;
+}
+
+// exchange the handle's active scratch (and stream) with the other lane's
+static void swap_lane(orbx_handle *h)
+{
+    OrbxLane &A = h->alt;
+    std::swap(h->stream, A.stream);
+    std::swap(h->d_pyr, A.d_pyr); std::swap(h->d_cand, A.d_cand); std::swap(h->d_cand2, A.d_cand2); std::swap(h->d_qtmp, A.d_qtmp);
+    std::swap(h->d_owner, A.d_owner); std::swap(h->d_owner2, A.d_owner2); std::swap(h->d_ncand, A.d_ncand); std::swap(h->d_nsel, A.d_nsel);
+    std::swap(h->d_sel, A.d_sel); std::swap(h->d_kps_all, A.d_kps_all); std::swap(h->d_desc_all, A.d_desc_all); std::swap(h->d_count_all, A.d_count_all);
+    std::swap(h->d_mpart, A.d_mpart); std::swap(h->mpart_cap, A.mpart_cap);
+    for (int l = 0; l < ORBX_MAX_LEVELS; l++) { std::swap(h->tmap[l], A.tmap[l]); std::swap(h->tmap_rz[l], A.tmap_rz[l]); std::swap(h->tmap_cell[l], A.tmap_cell[l]); }
+    std::swap(h->tmap_valid, A.tmap_valid); std::swap(h->tmap_l0, A.tmap_l0); std::swap(h->tmap_l0_step, A.tmap_l0_step);
+    std::swap(h->tmap_l0_fstride, A.tmap_l0_fstride); std::swap(h->tmap_l0_frames, A.tmap_l0_frames);
+}
+
+static bool overlap_applies(const orbx_handle *h, int nframes)
+{
+    return h->opt_overlap && nframes >= 32 && !h->opt_serial && !h->prof_on && h->opt_fused_blur;
+}
+
+// extraction (track == false) or the stream step (track == true) over nframes device frames: one chain, or two staggered half-batches
+static orbx_status pipeline_device(orbx_handle *h, bool track, const uint8_t *d_gray, int nframes, int width, int height, size_t step, size_t fstride,
+                                   const uint16_t *d_depth, size_t dstep, size_t dfstride, const DevBoxes &BX,
+                                   orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts,
+                                   orbx_dmatch *d_matches, int32_t *d_mcounts, float max_dist)
+{
+    if (!overlap_applies(h, nframes)) {
+        if (track) return track_chain(h, d_gray, nframes, width, height, step, fstride, d_depth, dstep, dfstride, BX, d_kps, d_desc, cap, d_counts, d_matches, d_mcounts, max_dist);
+        return run_pipeline(h, nframes, d_gray, step, fstride, d_depth, dstep, dfstride, BX, d_kps, d_desc, cap, d_counts);
+    }
+    orbx_status st = ensure_alt_lane(h);
+    if (st != ORBX_OK) return st;
+    const int nA = nframes / 2, nB = nframes - nA;
+    h->in_overlap = true;
+    // ---- first half on the handle's own lane; the second half may start once this half's pyramid is built ----
+    h->ev_after_pyramid = h->ev_lane_fork;
+    if (track) st = track_chain(h, d_gray, nA, width, height, step, fstride, d_depth, dstep, dfstride, BX, d_kps, d_desc, cap, d_counts, d_matches, d_mcounts, max_dist);
+    else st = run_pipeline(h, nA, d_gray, step, fstride, d_depth, dstep, dfstride, BX, d_kps, d_desc, cap, d_counts);
+    h->ev_after_pyramid = nullptr;
+    if (st != ORBX_OK) { h->in_overlap = false; return st; }
+    if (track) cudaEventRecord(h->ev_prev_ready, h->stream);                  // the first half's last frame is now the carried "previous frame"
+    const int keep_batch = h->last_batch; const uint8_t *keep_l0 = h->last_l0; const size_t keep_step = h->last_l0_step, keep_fs = h->last_l0_fstride;
+    // ---- second half on the other lane ----
+    swap_lane(h);
+    cudaStreamWaitEvent(h->stream, h->ev_lane_fork, 0);
+    DevBoxes BB = BX;
+    if (BB.off) BB.off += nA;
+    const uint8_t *gB = d_gray + (size_t)nA * fstride;
+    const uint16_t *dB = d_depth ? (const uint16_t *)((const uint8_t *)d_depth + (size_t)nA * dfstride) : nullptr;
+    orbx_keypoint *kB = d_kps + (size_t)nA * cap; uint8_t *eB = d_desc + (size_t)nA * cap * ORBX_DESC_BYTES; int32_t *cB = d_counts + nA;
+    if (track) {
+        // the extraction of this half needs nothing from the first one; its frame 0 is matched against the first half's last frame
+        st = run_pipeline(h, nB, gB, step, fstride, dB, dstep, dfstride, BB, kB, eB, cap, cB);
+        if (st == ORBX_OK) { cudaStreamWaitEvent(h->stream, h->ev_prev_ready, 0); st = track_matches(h, nB, kB, eB, cap, cB, d_matches + (size_t)nA * cap, d_mcounts + nA, max_dist); }
+    } else st = run_pipeline(h, nB, gB, step, fstride, dB, dstep, dfstride, BB, kB, eB, cap, cB);
+    cudaEventRecord(h->ev_lane_join, h->stream);
+    swap_lane(h);
+    cudaStreamWaitEvent(h->stream, h->ev_lane_join, 0);                        // the handle's stream is complete when both halves are
+    h->last_batch = keep_batch; h->last_l0 = keep_l0; h->last_l0_step = keep_step; h->last_l0_fstride = keep_fs;   // stage access: the first half
+    h->in_overlap = false;
+    if (st != ORBX_OK) return st;
     ORBX_CUDA(h, cudaGetLastError());
     return ORBX_OK;
 }
@@ -641,7 +762,8 @@ extern "C" orbx_status orbx_track_batch_boxes_device(orbx_handle *h, const uint8
     if (st != ORBX_OK) return st;
     if (nboxes_total < 0 || (nboxes_total > 0 && (!d_boxes || !d_box_offsets))) { h->err = "per-frame boxes need the box array and nframes + 1 offsets"; return ORBX_E_INVALID; }
     const DevBoxes BX = { d_boxes, d_box_offsets, 0, nboxes_total, drop_mask };
-    return track_device(h, d_gray, nframes, width, height, step, frame_stride, d_depth, dstep, dframe_stride, BX, d_kps, d_desc, cap, d_counts, d_matches, d_mcounts, max_dist);
+    if (cap > h->max_kp) { h->err = "cap_per_frame larger than the handle's max_keypoints"; return ORBX_E_INVALID; }
+    return pipeline_device(h, true, d_gray, nframes, width, height, step, frame_stride, d_depth, dstep, dframe_stride, BX, d_kps, d_desc, cap, d_counts, d_matches, d_mcounts, max_dist);
 }
 
 // Device view of a host buffer the GPU can read in place (pinned / registered, mapped under UVA); nullptr for pageable memory.
@@ -738,8 +860,7 @@ static orbx_status enqueue_chunk(orbx_handle *h, const BatchArgs &A, int f0, int
     // this chunk's kernels report device-side capacity flags into the slot's own word, so a flag raised by one chunk is never
     // attributed to the other chunk in flight or to a later call
     h->d_status = h->d_status_base + 1 + slot;           // (zeroed at the start of the call: host_batch / submit_batch)
-    if (A.track) st = track_device(h, d_g, nb, width, height, pitch, fstride, dd, dds, ddf, BX, o_k, o_d, h->max_kp, o_c, d_m, d_mc, A.max_dist);
-    else st = run_pipeline(h, nb, d_g, pitch, fstride, dd, dds, ddf, BX, o_k, o_d, h->max_kp, o_c);
+    st = pipeline_device(h, A.track, d_g, nb, width, height, pitch, fstride, dd, dds, ddf, BX, o_k, o_d, h->max_kp, o_c, d_m, d_mc, A.max_dist);
     int32_t *slot_status = h->d_status;
     h->d_status = h->d_status_base;
     if (st != ORBX_OK) return st;

@@ -65,6 +65,19 @@ enum { ORBX_K_RESIZE = 0, ORBX_K_FAST, ORBX_K_QUADTREE, ORBX_K_BLUR, ORBX_K_DESC
 
 struct ResizeTab { int32_t ofs; int16_t a0, a1; };   // 8 bytes
 
+// ORBX_OPT_OVERLAP: a second set of everything one pipeline run writes besides the caller's buffers.  A large batch is cut in two halves
+// that run on two streams, the second one stage behind the first, so that kernels bound on different units (FAST: ALU issue, descriptor
+// kernel: shared-memory wavefronts, matcher: POPC / ALU, quadtree: latency) share the SMs instead of running back to back.  The kernels
+// and their launchers are untouched: the handle's active fields are swapped with this set around the second half.
+struct OrbxLane {
+    bool allocated;
+    cudaStream_t stream;
+    uint8_t *d_pyr; uint32_t *d_cand, *d_cand2, *d_qtmp; uint16_t *d_owner, *d_owner2; int32_t *d_ncand, *d_nsel; uint32_t *d_sel;
+    orbx_keypoint *d_kps_all; uint8_t *d_desc_all; int32_t *d_count_all; uint32_t *d_mpart; size_t mpart_cap;
+    CUtensorMap tmap[ORBX_MAX_LEVELS], tmap_rz[ORBX_MAX_LEVELS], tmap_cell[ORBX_MAX_LEVELS]; bool tmap_valid;
+    const uint8_t *tmap_l0; size_t tmap_l0_step, tmap_l0_fstride; int tmap_l0_frames;
+};
+
 struct orbx_handle {
     orbx_params prm;
     int device;
@@ -77,6 +90,11 @@ struct orbx_handle {
     int opt_fused_blur;          // 1 (default): the Gaussian is evaluated inside the descriptor kernel, no blurred pyramid is written
     bool blur_valid;             // d_blur holds the blurred levels of the last batch
     int opt_fast_ctas;           // FAST warps per SM in the overlapped schedule (0 = as many as fit)
+    int opt_overlap;             // 1 (default): batches of >= 32 frames run as two half-batches on two streams (OrbxLane)
+    OrbxLane alt;                // the second lane's scratch (allocated on first use)
+    bool in_overlap;             // a half-batch run is being enqueued (FAST caps its resident warps so the other lane's kernels fit beside it)
+    cudaEvent_t ev_lane_fork, ev_lane_join, ev_prev_ready;
+    cudaEvent_t ev_after_pyramid;            // when set, run_pipeline records it right after the pyramid launches
     cudaEvent_t ev_a, ev_b;
     cudaEvent_t ev_in[2], ev_comp[2], ev_out[2];   // host-batch pipeline: input slot filled / kernels done / outputs copied
     int chunk;                                      // frames per pipeline chunk of the synchronous host-buffer batch calls

@@ -248,6 +248,10 @@ class ORBextractor:
         """ORBX_OPT_PDL: programmatic dependent launch of the step's kernel chain (default on)."""
         self._check(self.L.orbx_set_option(self._h, 4, 1 if on else 0))
 
+    def set_overlap(self, on=True):
+        """ORBX_OPT_OVERLAP: batches of >= 32 frames as two staggered half-batches on two streams (default off: measured slower)."""
+        self._check(self.L.orbx_set_option(self._h, 5, 1 if on else 0))
+
     def set_fast_ctas(self, n):
         """ORBX_OPT_FAST_CTAS: resident FAST warps per SM in the overlapped schedule (0 = as many as fit)."""
         self._check(self.L.orbx_set_option(self._h, 2, int(n)))

@@ -351,6 +351,12 @@ orbx_status orbx_synth_descriptors_device(orbx_handle *h, uint32_t seed, uint64_
 #define ORBX_OPT_FAST_CTAS 2
 #define ORBX_OPT_FUSED_BLUR 3
 #define ORBX_OPT_PDL 4
+/* ORBX_OPT_OVERLAP: 1 = device-buffer batch calls of >= 32 frames are cut into two half-batches that run on two streams, the second one
+ * stage behind the first (its pyramid beside the first half's FAST, its FAST beside the first half's quadtree / descriptor / match
+ * kernels ...), joined again on the handle's stream before the call returns; same results, same stream semantics.  0 (default) = one
+ * chain.  MEASURED SLOWER on B200 (128 x 1280x720: 1.190 ms one chain, 1.206-1.31 ms overlapped, profiles/r02d_overlap.log): every
+ * kernel of the step is instruction-issue bound, so co-resident kernels only split the issue slots and the half-batches add tails. */
+#define ORBX_OPT_OVERLAP 5
 orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t value);
 
 /* ---- utilities ---- */

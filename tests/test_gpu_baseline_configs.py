@@ -88,6 +88,33 @@ def test_bench_path_batch128_every_frame(built, oracle, refx):
         ex.close()
 
 
+def test_overlap_option_same_results(built, oracle):
+    """ORBX_OPT_OVERLAP = 1 (two staggered half-batches on two streams; off by default because it measured slower): identical outputs,
+    incl. the match of the second half's first frame against the first half's last and the carried frame across calls"""
+    import orbx
+    B = 40
+    ex = orbx.ORBextractor(max_width=W, max_height=H, max_batch=B, max_keypoints=CAP)
+    try:
+        ex.set_overlap(True)
+        _, ref = _cpu_stream(oracle, 0, 2 * B)
+        for step in range(2):
+            gray, depth = _device_stream(ex, step * B, B)
+            o = _outputs(B)
+            ex._check(ex.L.orbx_track_batch_device(ex.handle, gray.data_ptr(), B, W, H, W, W * H, depth.data_ptr(), 2 * W, 2 * W * H,
+                                                   o["kps"].data_ptr(), o["desc"].data_ptr(), CAP, o["cnt"].data_ptr(),
+                                                   o["m"].data_ptr(), o["mc"].data_ptr(), ct.c_float(50.0)))
+            ex.sync()
+            kk, dd = o["kps"].cpu().numpy().view(orbx.KP_DTYPE).reshape(B, CAP), o["desc"].cpu().numpy()
+            cc, mm, mc = o["cnt"].cpu().numpy(), o["m"].cpu().numpy().view(orbx.DM_DTYPE).reshape(B, CAP), o["mc"].cpu().numpy()
+            for f in range(B):
+                r = ref[step * B + f]
+                assert cc[f] == len(r["kps"]) and np.array_equal(kk[f, :cc[f]].view(np.uint8), r["kps"].view(np.uint8)) and np.array_equal(dd[f, :cc[f]], r["desc"]), (step, f)
+                if step or f:
+                    assert mc[f] == len(r["good"]) and np.array_equal(mm[f, :mc[f]].view(np.uint8), r["good"].view(np.uint8)), (step, f)
+    finally:
+        ex.close()
+
+
 def test_extract_batch128_vs_compiled_reference_and_golden_checksums(built, oracle, refx):
     """configs[2]'s unit of work (frame-parallel extraction, no depth) at batch 128: the reference's own compiled ORBextractor.cpp on a
     sample of frames, and the committed checksums of its output on frames 0..31 and 127"""
