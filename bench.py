@@ -676,6 +676,22 @@ def leg_config0(ex, orbx, cp, rank):
         k0, d0, k1, d1, good = out
     finally:
         e.close()
+    # the same pair through profile C (cv::ORB on the GPU: INTER_LINEAR_EXACT pyramid, whole-level FAST, Harris + retainBest, float blur)
+    ec = orbx.ORBextractor(max_width=w, max_height=h, device=ex.params.device, profile="cvorb")
+    try:
+        def pair_c():
+            a0, b0 = ec(g0)
+            a1, b1 = ec(g1)
+            return a0, b0, a1, b1, ec.match(b1, b0, k=2, ratio=0.75)
+        for _ in range(5):
+            outc = pair_c()
+        tc = []
+        for _ in range(40):
+            t0 = time.perf_counter()
+            outc = pair_c()
+            tc.append((time.perf_counter() - t0) * 1e3)
+    finally:
+        ec.close()
     # parity of this leg: extraction against the CPU path, kNN + ratio against the restatement
     r0 = cp.extract(g0[None], 1)
     r1 = cp.extract(g1[None], 1)
@@ -687,6 +703,9 @@ def leg_config0(ex, orbx, cp, rank):
     res = {"workload": "configs[0]: 640x480 synthetic frame pair, 1000 features, kNN k=2 + ratio 0.75", "gpu_pair_ms_p50": float(np.percentile(ts, 50)),
            "gpu_api": "2 x orbx_extract + orbx_match(k=2, ratio=0.75), host buffers, blocking calls", "keypoints": [int(len(k0)), int(len(k1))],
            "ratio_matches": int(len(good)), "parity_mismatch": not same, "cores": os.cpu_count()}
+    res["gpu_cvorb_pair_ms_p50"] = float(np.percentile(tc, 50))
+    res["gpu_cvorb_keypoints"] = [int(len(outc[0])), int(len(outc[2]))]
+    res["gpu_cvorb_ratio_matches"] = int(len(outc[4]))
     t_cpu = []
     for _ in range(5):
         t0 = time.perf_counter()
@@ -711,6 +730,11 @@ def leg_config0(ex, orbx, cp, rank):
                 t_cv.append((time.perf_counter() - t0) * 1e3)
             res["cv2_orb_knn_pair_ms_" + label] = float(np.median(t_cv[2:]))
             res["cv2_threads_" + label] = int(cv2.getNumThreads())
+            if nt == 1:                                        # profile C on the GPU against cv::ORB itself: same keypoint sets, same ratio matches
+                sa = {(p.octave, float(np.float32(p.pt[0])), float(np.float32(p.pt[1]))) for p in ka}
+                ga = {(int(q["octave"]), float(q["x"]), float(q["y"])) for q in outc[0]}
+                want = sorted((m[0].queryIdx, m[0].trainIdx) for m in bf.knnMatch(outc[3], outc[1], k=2) if len(m) == 2 and 4 * m[0].distance < 3 * m[1].distance)
+                res["gpu_cvorb_vs_cv2"] = {"keypoint_set_equal": sa == ga, "ratio_matches_equal": want == sorted(zip(outc[4]["queryIdx"].tolist(), outc[4]["trainIdx"].tolist()))}
         res["cv2_version"] = cv2.__version__
     except Exception as exc:                                   # cv2 is optional on the GPU box
         res["cv2"] = "unavailable: %s" % type(exc).__name__

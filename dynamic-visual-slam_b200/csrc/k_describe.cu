@@ -11,6 +11,7 @@
 //     fp32) restated below; pinned against glibc over every float32 angle in [0,360] degrees
 //   * x*b + y*a: fp32 multiply, fp32 add, cvRound = round-half-even                  — SURVEY App. A.5
 #include "orbx_internal.h"
+#include <cstring>
 
 // read with 128-bit __ldg per lane (lane i owns pairs 8i..8i+7): a __constant__ table would serialise the
 // 32 distinct addresses of a warp
@@ -397,6 +398,105 @@ void launch_describe_to(orbx_handle *h, int nframes, const uint8_t *l0, size_t l
     ProfScope ps(h, ORBX_K_DESCRIBE);
     if (h->opt_fused_blur) orbx_launch_pdl(h, k_describe_fused, grid, dim3(DESC_WARPS * 32), 0, h->stream, P, (const FrameGeom *)h->d_geo);
     else k_describe<<<grid, DESC_WARPS * 32, 0, h->stream>>>(P, h->d_geo);
+}
+
+// ---- profile C (cv::ORB): IC_Angle on the level, rBRIEF on the float-blurred level, keypoint assembly (orbx_cvorb.cu) ----
+// per-level lists [level][list_cap] of (x | y << 16) + Harris response, already in output order; one warp per keypoint
+struct DescCParams {
+    const uint8_t *img[ORBX_MAX_LEVELS]; int step[ORBX_MAX_LEVELS];
+    const uint8_t *blur[ORBX_MAX_LEVELS]; int bstep[ORBX_MAX_LEVELS];
+    float scale[ORBX_MAX_LEVELS];
+    const uint32_t *fxy; const float *fresp; const int32_t *fcount; int list_cap, nlevels;
+    orbx_keypoint *kps; uint8_t *desc; int cap; int32_t *count; int32_t *status;
+};
+__global__ void __launch_bounds__(DESC_WARPS * 32) k_describe_c(DescCParams P)
+{
+    ORBX_PDL_ENTRY();
+    const int lane = threadIdx.x & 31;
+    const int nl = P.nlevels;
+    const int gidx = blockIdx.x * DESC_WARPS + (threadIdx.x >> 5);
+    int level, k, total;
+    {
+        const int c = lane < nl ? P.fcount[lane] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < ORBX_MAX_LEVELS; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        total = __shfl_sync(0xffffffffu, incl, nl - 1);
+        level = __popc(__ballot_sync(0xffffffffu, lane < nl && incl <= gidx));
+        const int before = __shfl_sync(0xffffffffu, incl, max(level - 1, 0));
+        k = gidx - (level > 0 ? before : 0);
+        if (level >= nl) level = -1;
+    }
+    if (gidx == 0 && lane == 0) {
+        P.count[0] = total <= P.cap ? total : 0;
+        if (total > P.cap) atomicOr(P.status, ORBX_DS_KP_OVERFLOW);
+    }
+    if (level < 0 || total > P.cap) return;
+    const uint32_t c = P.fxy[(size_t)level * P.list_cap + k];
+    const int cx = (int)(c & 0xFFFFu), cy = (int)(c >> 16);
+    const uint8_t *img = P.img[level]; const size_t step = (size_t)P.step[level];
+    const uint8_t *bctr = P.blur[level] + (size_t)cy * P.bstep[level] + cx;
+    const int bstep = P.bstep[level];
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int u = lane - ORBX_HALF_PATCH;
+        const int au = u < 0 ? -u : u;
+        const uint8_t *ctr = img + (size_t)cy * step + cx + u;
+        int px[2 * ORBX_HALF_PATCH + 1];
+#pragma unroll
+        for (int v = -ORBX_HALF_PATCH; v <= ORBX_HALF_PATCH; v++) {
+            const int av = v < 0 ? -v : v;
+            px[v + ORBX_HALF_PATCH] = au <= c_umax[av] ? (int)__ldg(ctr + (ptrdiff_t)v * (ptrdiff_t)step) : 0;
+        }
+        int colsum = 0;
+#pragma unroll
+        for (int v = -ORBX_HALF_PATCH; v <= ORBX_HALF_PATCH; v++) { colsum += px[v + ORBX_HALF_PATCH]; m01 += v * px[v + ORBX_HALF_PATCH]; }
+        m10 = u * colsum;
+    }
+    m10 = __reduce_add_sync(0xffffffffu, m10);
+    m01 = __reduce_add_sync(0xffffffffu, m01);
+    const float angle = cv_fast_atan2((float)m01, (float)m10);
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    const float ang = __fmul_rn(angle, factorPI);
+    const float a = glibc_cosf(ang), b = glibc_sinf(ang);
+    signed char pat[32];
+    {
+        const int4 *pp = reinterpret_cast<const int4 *>(c_pattern + lane * 32);
+        *reinterpret_cast<int4 *>(pat) = __ldg(pp);
+        *reinterpret_cast<int4 *>(pat + 16) = __ldg(pp + 1);
+    }
+    int val = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float x0 = (float)pat[4 * j], y0 = (float)pat[4 * j + 1], x1 = (float)pat[4 * j + 2], y1 = (float)pat[4 * j + 3];
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int t0 = __ldg(bctr + r0 * bstep + c0), t1 = __ldg(bctr + r1 * bstep + c1);
+        val |= (t0 < t1) << j;
+    }
+    P.desc[(size_t)gidx * ORBX_DESC_BYTES + lane] = (uint8_t)val;
+    if (lane == 0) {
+        orbx_keypoint kp;
+        const float s = P.scale[level];
+        kp.x = __fmul_rn((float)cx, s); kp.y = __fmul_rn((float)cy, s);            // keypoints[i].pt *= scale (orb.cpp)
+        kp.size = __fmul_rn((float)ORBX_PATCH, s); kp.angle = angle; kp.response = P.fresp[(size_t)level * P.list_cap + k];
+        kp.octave = level; kp.class_id = -1;
+        P.kps[gidx] = kp;
+    }
+}
+void launch_describe_c(orbx_handle *h, int nlevels, const uint8_t *const *img, const int *step, const uint8_t *const *blur, const int *bstep,
+                       const float *scale, const uint32_t *d_fxy, const float *d_fresp, const int32_t *d_fcount, int list_cap, int max_total,
+                       orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_count)
+{
+    DescCParams P;
+    memset(&P, 0, sizeof(P));
+    for (int l = 0; l < nlevels; l++) { P.img[l] = img[l]; P.step[l] = step[l]; P.blur[l] = blur[l]; P.bstep[l] = bstep[l]; P.scale[l] = scale[l]; }
+    P.fxy = d_fxy; P.fresp = d_fresp; P.fcount = d_fcount; P.list_cap = list_cap; P.nlevels = nlevels;
+    P.kps = d_kps; P.desc = d_desc; P.cap = cap; P.count = d_count; P.status = h->d_status;
+    ProfScope ps(h, ORBX_K_DESCRIBE);
+    k_describe_c<<<(max_total + DESC_WARPS - 1) / DESC_WARPS, DESC_WARPS * 32, 0, h->stream>>>(P);
 }
 
 // ---- Harris response of given points of one pyramid level (cv::ORB's HarrisResponses; HARRIS_SCORE of ORBextractor.hpp:48) ----

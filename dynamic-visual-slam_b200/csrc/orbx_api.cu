@@ -237,6 +237,7 @@ extern "C" void orbx_destroy(orbx_handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    orbx_cvorb_destroy(h);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     void *dev[] = { h->d_bgr, h->d_cells, h->d_blur_tiles, h->d_strips, h->d_prev_desc, h->d_prev_count, h->d_geo, h->d_xtab, h->d_ytab, h->d_pyr, h->d_blur, h->d_in, h->d_depth_in, h->d_cand, h->d_cand2, h->d_qtmp,
                     h->d_owner, h->d_owner2, h->d_ncand, h->d_sel, h->d_nsel, h->d_kps_all, h->d_desc_all, h->d_count_all,
@@ -277,6 +278,7 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     if (p.nlevels < 1 || p.nlevels > ORBX_MAX_LEVELS || p.nfeatures < 1 || !(p.scale_factor > 1.0f) ||
         p.max_width < 1 || p.max_height < 1 || p.max_batch < 1 || p.ini_th_fast < 0 || p.min_th_fast < 0 ||
         p.ini_th_fast > 255 || p.min_th_fast > 255) { g_create_err = "invalid orbx_params"; return ORBX_E_INVALID; }
+    if (p.profile != ORBX_PROFILE_SLAM && p.profile != ORBX_PROFILE_CVORB) { g_create_err = "unknown orbx_params.profile"; return ORBX_E_INVALID; }
     if (p.scale_factor == 2.0f) { g_create_err = "scale_factor 2.0 takes cv::resize's INTER_AREA fast path, not implemented"; return ORBX_E_UNSUPPORTED; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { g_create_err = "no CUDA device: this path has no CPU fallback"; return ORBX_E_CUDA; }
@@ -318,7 +320,7 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     }
     const size_t B = (size_t)p.max_batch;
     // host-buffer calls are pipelined in chunks of `chunk` frames over two input and two output slots
-    h->chunk = p.reserved_[0] > 0 ? std::min(p.reserved_[0], p.max_batch) : std::max(1, std::min(32, p.max_batch / 4));
+    h->chunk = p.host_chunk > 0 ? std::min(p.host_chunk, p.max_batch) : std::max(1, std::min(32, p.max_batch / 4));
     h->seq = 0; h->pending[0].active = h->pending[1].active = false;
     const size_t S = 2 * B;                                       // the staging arenas hold two slots of max_batch frames
     // arenas are sized for the max geometry with 12% headroom so that smaller frames with unlucky padding still fit
@@ -373,6 +375,14 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     memset(h->h_status, 0, 64);
     orbx_status st = set_geometry(h, p.max_width, p.max_height);
     if (st != ORBX_OK) { g_create_err = h->err; orbx_destroy(h); return st; }
+    if (p.profile == ORBX_PROFILE_CVORB) {
+        if ((st = orbx_cvorb_create(h)) != ORBX_OK) { g_create_err = h->err; orbx_destroy(h); return st; }
+        // cv::ORB's per-level scale is pow(scaleFactor, level) in one step, not the extractor's running product (orb.cpp getScale)
+        for (int l = 0; l < p.nlevels; l++) {
+            h->scale[l] = (float)pow((double)p.scale_factor, (double)l);
+            h->inv_scale[l] = 1.0f / h->scale[l]; h->sigma2[l] = h->scale[l] * h->scale[l]; h->inv_sigma2[l] = 1.0f / h->sigma2[l];
+        }
+    }
     *out = h;
     return ORBX_OK;
 }
@@ -387,7 +397,7 @@ static orbx_status check_device_status(orbx_handle *h)
     ORBX_CUDA(h, cudaMemsetAsync(h->d_status, 0, sizeof(int32_t), h->stream));
     if (s & ORBX_DS_BAD_INDEX) { h->err = "a match query index lies outside the keypoint array"; return ORBX_E_INVALID; }
     h->err = std::string("device capacity exceeded:") + ((s & ORBX_DS_CAND_OVERFLOW) ? " candidate list (lower cand_divisor)" : "") +
-             ((s & ORBX_DS_NODE_OVERFLOW) ? " quadtree nodes" : "") + ((s & ORBX_DS_KP_OVERFLOW) ? " keypoint output (raise cap / max_keypoints)" : "");
+             ((s & ORBX_DS_NODE_OVERFLOW) ? " quadtree nodes / retained-corner list" : "") + ((s & ORBX_DS_KP_OVERFLOW) ? " keypoint output (raise cap / max_keypoints)" : "");
     return ORBX_E_CAPACITY;
 }
 
@@ -420,6 +430,7 @@ extern "C" void orbx_get_features_per_level(const orbx_handle *h, int32_t *o) { 
 extern "C" orbx_status orbx_level_size(const orbx_handle *h, int32_t w, int32_t hgt, int32_t level, int32_t *lw, int32_t *lh)
 {
     if (!h || level < 0 || level >= h->prm.nlevels || !lw || !lh) return ORBX_E_INVALID;
+    if (h->cv) { int a, b; orbx_cvorb_level_size(h, w, hgt, level, &a, &b); *lw = a; *lh = b; return ORBX_OK; }
     *lw = cv_round_f((float)w * h->inv_scale[level]); *lh = cv_round_f((float)hgt * h->inv_scale[level]);
     return ORBX_OK;
 }
@@ -439,6 +450,21 @@ static orbx_status run_pipeline(orbx_handle *h, int nframes, const uint8_t *l0, 
                                 orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts)
 {
     const orbx_box *d_boxes = BX.boxes; const int nboxes = BX.n; const uint64_t drop_mask = BX.drop_mask;
+    if (h->cv) {                                                  // profile C (cv::ORB): one frame at a time through orbx_cvorb.cu
+        const bool filt = d_depth != nullptr || nboxes > 0;
+        for (int f = 0; f < nframes; f++) {
+            const orbx_status st = filt
+                ? orbx_cvorb_run(h, l0 + (size_t)f * l0_fstride, h->geo.width, h->geo.height, l0_step, h->d_kps_all + (size_t)f * h->max_kp,
+                                 h->d_desc_all + (size_t)f * h->max_kp * ORBX_DESC_BYTES, h->max_kp, h->d_count_all + f)
+                : orbx_cvorb_run(h, l0 + (size_t)f * l0_fstride, h->geo.width, h->geo.height, l0_step, d_kps + (size_t)f * cap,
+                                 d_desc + (size_t)f * cap * ORBX_DESC_BYTES, cap, d_counts + f);
+            if (st != ORBX_OK) return st;
+        }
+        if (filt) launch_filter(h, nframes, d_depth, dstep, dfstride, d_boxes, BX.off, BX.base, nboxes, drop_mask, d_kps, d_desc, cap, d_counts);
+        h->last_batch = nframes; h->last_l0 = l0; h->last_l0_step = l0_step; h->last_l0_fstride = l0_fstride;
+        ORBX_CUDA(h, cudaGetLastError());
+        return ORBX_OK;
+    }
     const int nl = h->geo.nlevels;
     if (h->geo.total_cells_valid == 0) {
         // no level holds a FAST cell (every level is narrower than 67 px): the reference's cell loops do not execute and it returns no
@@ -1042,6 +1068,10 @@ extern "C" orbx_status orbx_get_pyramid_level(orbx_handle *h, int32_t frame, int
 {
     if (!h || !out || level < 0 || level >= h->geo.nlevels || frame < 0 || frame >= h->last_batch) return ORBX_E_INVALID;
     cudaSetDevice(h->device);
+    if (h->cv) {                                                   // profile C keeps the levels of the LAST frame it processed
+        if (frame != h->last_batch - 1) { h->err = "profile C: stage access is for the last frame of the batch"; return ORBX_E_INVALID; }
+        return orbx_cvorb_get_level(h, level, 0, out, out_step, h->last_l0 + (size_t)frame * h->last_l0_fstride, h->last_l0_step);
+    }
     const LevelGeom &g = h->geo.lv[level];
     const uint8_t *src; size_t step;
     if (level == 0) { src = h->last_l0 + (size_t)frame * h->last_l0_fstride; step = h->last_l0_step; }
@@ -1054,6 +1084,10 @@ extern "C" orbx_status orbx_get_blurred_level(orbx_handle *h, int32_t frame, int
 {
     if (!h || !out || level < 0 || level >= h->geo.nlevels || frame < 0 || frame >= h->last_batch) return ORBX_E_INVALID;
     cudaSetDevice(h->device);
+    if (h->cv) {
+        if (frame != h->last_batch - 1) { h->err = "profile C: stage access is for the last frame of the batch"; return ORBX_E_INVALID; }
+        return orbx_cvorb_get_level(h, level, 1, out, out_step, nullptr, 0);
+    }
     const LevelGeom &g = h->geo.lv[level];
     if (!h->blur_valid) {                                                          // fused mode: materialise the last batch's blurred levels now
         if (launch_blur(h, h->last_batch, h->last_l0, h->last_l0_step, h->last_l0_fstride, h->stream) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return ORBX_E_CUDA; }
@@ -1066,6 +1100,7 @@ extern "C" orbx_status orbx_get_blurred_level(orbx_handle *h, int32_t frame, int
 extern "C" orbx_status orbx_get_candidates(orbx_handle *h, int32_t frame, int32_t level, int32_t *out_xys, int32_t cap, int32_t *n_out)
 {
     if (!h || !out_xys || !n_out || level < 0 || level >= h->geo.nlevels || frame < 0 || frame >= h->last_batch) return ORBX_E_INVALID;
+    if (h->cv) { h->err = "candidate lists are a profile-S stage"; return ORBX_E_UNSUPPORTED; }
     cudaSetDevice(h->device);
     ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
     const LevelGeom &g = h->geo.lv[level];
@@ -1101,6 +1136,7 @@ extern "C" orbx_status orbx_harris_responses(orbx_handle *h, int32_t frame, int3
 extern "C" orbx_status orbx_get_level_counts(orbx_handle *h, int32_t frame, int32_t *out)
 {
     if (!h || !out || frame < 0 || frame >= h->last_batch) return ORBX_E_INVALID;
+    if (h->cv) { h->err = "per-level counts: read the octave field of the keypoints (profile C)"; return ORBX_E_UNSUPPORTED; }
     cudaSetDevice(h->device);
     ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
     ORBX_CUDA(h, cudaMemcpy(out, h->d_nsel + frame * h->geo.nlevels, sizeof(int32_t) * h->geo.nlevels, cudaMemcpyDeviceToHost));

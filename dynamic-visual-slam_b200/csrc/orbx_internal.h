@@ -78,8 +78,10 @@ struct OrbxLane {
     const uint8_t *tmap_l0; size_t tmap_l0_step, tmap_l0_fstride; int tmap_l0_frames;
 };
 
+struct orbx_cvorb;                     // profile C (cv::ORB) state, orbx_cvorb.cu
 struct orbx_handle {
     orbx_params prm;
+    orbx_cvorb *cv;              // non-null iff prm.profile == ORBX_PROFILE_CVORB
     int device;
     cudaStream_t stream, copy_stream, out_stream, aux_stream;   // aux: blur runs beside FAST + quadtree
     cudaEvent_t ev_fork, ev_fork0, ev_join;
@@ -213,6 +215,14 @@ size_t orbx_quadtree_smem(int node_cap);              // k_quadtree.cu: dynamic 
 #define ORBX_DS_NODE_OVERFLOW 2
 #define ORBX_DS_KP_OVERFLOW   4
 #define ORBX_DS_BAD_INDEX     8      // a caller-supplied index list pointed outside its array (k_cull)
+
+// ---- profile C (cv::ORB), orbx_cvorb.cu ----
+orbx_status orbx_cvorb_create(orbx_handle *h);
+void orbx_cvorb_destroy(orbx_handle *h);
+orbx_status orbx_cvorb_run(orbx_handle *h, const uint8_t *d_gray, int width, int height, size_t step,
+                           orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_count);
+orbx_status orbx_cvorb_get_level(orbx_handle *h, int level, int blurred, uint8_t *out, size_t out_step, const uint8_t *l0, size_t l0_step);
+void orbx_cvorb_level_size(const orbx_handle *h, int w, int hgt, int level, int *lw, int *lh);
 
 // ---- kernel launchers (one per .cu) ----
 int  launch_pyramid(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);

@@ -89,11 +89,14 @@ public:
     enum { HARRIS_SCORE = 0, FAST_SCORE = 1 };
 
     // max_width / max_height size the device arenas once (README default stream: 1280x720); device = CUDA ordinal.
+    // profile: ORBX_PROFILE_SLAM = this class in the reference (the frontend's extractor); ORBX_PROFILE_CVORB = cv::ORB::create(nfeatures,
+    // scaleFactor, nlevels, 31, 0, 2, HARRIS_SCORE, 31, iniThFAST), the extractor of the reference's gtest (test/test_dbow2_integration.cpp:19)
     ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST,
-                 int max_width = 1280, int max_height = 720, int device = 0)
+                 int max_width = 1280, int max_height = 720, int device = 0, int profile = ORBX_PROFILE_SLAM)
     {
         orbx_params p;
         orbx_default_params(&p);
+        p.profile = profile;
         p.nfeatures = nfeatures; p.scale_factor = scaleFactor; p.nlevels = nlevels;
         p.ini_th_fast = iniThFAST; p.min_th_fast = minThFAST;
         p.max_width = max_width; p.max_height = max_height; p.device = device;

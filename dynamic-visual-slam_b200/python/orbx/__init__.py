@@ -40,7 +40,7 @@ class Params(ct.Structure):
                 ("depth_min", ct.c_float), ("depth_max", ct.c_float),
                 ("max_width", ct.c_int32), ("max_height", ct.c_int32), ("max_batch", ct.c_int32),
                 ("max_keypoints", ct.c_int32), ("cand_divisor", ct.c_int32), ("device", ct.c_int32),
-                ("reserved_", ct.c_int32 * 3)]
+                ("host_chunk", ct.c_int32), ("profile", ct.c_int32), ("reserved_", ct.c_int32)]
 
 
 class OrbxError(RuntimeError):
@@ -195,7 +195,7 @@ class ORBextractor:
 
     def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7,
                  max_width=1280, max_height=720, max_batch=1, device=0, depth_min=0.3, depth_max=3.0,
-                 max_keypoints=0, cand_divisor=0, host_chunk=0):
+                 max_keypoints=0, cand_divisor=0, host_chunk=0, profile=0):
         L = load()
         p = Params()
         L.orbx_default_params(ct.byref(p))
@@ -203,7 +203,8 @@ class ORBextractor:
         p.ini_th_fast, p.min_th_fast = iniThFAST, minThFAST
         p.max_width, p.max_height, p.max_batch, p.device = max_width, max_height, max_batch, device
         p.depth_min, p.depth_max, p.max_keypoints, p.cand_divisor = depth_min, depth_max, max_keypoints, cand_divisor
-        p.reserved_[0] = host_chunk
+        p.host_chunk = host_chunk
+        p.profile = {"slam": 0, "cvorb": 1}.get(profile, profile)
         self._h = ct.c_void_p()
         st = L.orbx_create(ct.byref(p), ct.byref(self._h))
         if st != OK:

@@ -78,8 +78,22 @@ typedef struct {
     int32_t max_keypoints;    /* per-frame output capacity; 0 = nfeatures + 4*nlevels + 64 */
     int32_t cand_divisor;     /* candidate-list capacity per level = max(4096, pixels/cand_divisor); 0 = 16 */
     int32_t device;           /* CUDA device ordinal */
-    int32_t reserved_[3];     /* [0]: frames per pipeline chunk of the host-buffer batch calls, 0 = auto (max_batch/4, 1..32) */
+    int32_t host_chunk;       /* frames per pipeline chunk of the host-buffer batch calls, 0 = auto (max_batch/4, 1..32) */
+    int32_t profile;          /* ORBX_PROFILE_SLAM (0, default) | ORBX_PROFILE_CVORB (1), see below */
+    int32_t reserved_;
 } orbx_params;
+
+/* Extraction profiles: the two ORB extractors the reference uses.
+ *   ORBX_PROFILE_SLAM   the frontend's ORB_SLAM3::ORBextractor (ORBextractor.cpp; frontend.cpp:1094): INTER_LINEAR pyramid, per-cell FAST with the
+ *                       20 -> 7 retry, quadtree distribution, FAST score as the response, fixed-point blur.  Bit-exact.
+ *   ORBX_PROFILE_CVORB  cv::ORB (test/test_dbow2_integration.cpp:19,38; BASELINE configs[0]; north_star stage 3): INTER_LINEAR_EXACT pyramid,
+ *                       whole-level FAST(ini_th_fast) + retainBest(2N), Harris response (block 7, k 0.04) + retainBest(N), float-path blur.
+ *                       min_th_fast is unused.  Inside a level the keypoints come sorted by (response descending, y, x) — OpenCV leaves
+ *                       std::nth_element's order — so parity with cv::ORB is on sets; descriptors follow the AVX2/FMA build of OpenCV 4.13
+ *                       (>= 99.9 % of rows identical against other builds, as north_star states).  One frame at a time: the batch entry
+ *                       points loop over the frames; stage access and the stream (track) calls work as for the other profile.        */
+#define ORBX_PROFILE_SLAM 0
+#define ORBX_PROFILE_CVORB 1
 
 typedef struct orbx_handle orbx_handle;
 typedef struct orbx_db orbx_db;

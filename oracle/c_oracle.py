@@ -184,6 +184,34 @@ def gaussian_blur7(img):
     return out
 
 
+def resize_linear_exact(src, dw, dh):
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().orc_resize_linear_exact(_p(src), src.shape[1], src.shape[0], ct.c_size_t(src.strides[0]), _p(dst), dw, dh, ct.c_size_t(dw))
+    return dst
+
+
+def gaussian_blur7_f32(img):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    out = np.zeros_like(img)
+    lib().orc_gaussian_blur7_f32(_p(img), img.shape[1], img.shape[0], ct.c_size_t(img.strides[0]), _p(out), ct.c_size_t(out.strides[0]))
+    return out
+
+
+def ic_angle(img, cx, cy, umax):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    f = lib().orc_ic_angle
+    f.restype = ct.c_float
+    return float(f(_p(img), ct.c_size_t(img.strides[0]), int(cx), int(cy), (ct.c_int * 16)(*umax)))
+
+
+def descriptor(blur, cx, cy, angle_deg):
+    blur = np.ascontiguousarray(blur, dtype=np.uint8)
+    d = np.zeros(32, np.uint8)
+    lib().orc_descriptor(_p(blur), ct.c_size_t(blur.strides[0]), int(cx), int(cy), ct.c_float(angle_deg), _p(d))
+    return d
+
+
 def fast_atan2(y, x):
     return float(lib().orc_fast_atan2(ct.c_float(y), ct.c_float(x)))
 

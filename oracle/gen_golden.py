@@ -92,6 +92,21 @@ def main():
     np.savez_compressed(os.path.join(OUT, "ref_stream_1280x720.npz"), seed=seed, frames=np.array(frames, np.int32),
                         count=np.array([len(r["kps"]) for r in res], np.int32),
                         kps_crc=np.array([crc(r["kps"]) for r in res], np.uint32), desc_crc=np.array([crc(r["desc"]) for r in res], np.uint32))
+    # ---- profile C: cv::ORB itself (cv2.ORB_create) on the reference's three-circle test image (100 features, as the gtest) and on
+    #      synthetic frames (1000 features, BASELINE configs[0]); rows sorted by (octave, response descending, y, x) ----
+    import cvorb_oracle as cvc
+    for name, img, nf in (("cvorb_circles_640x480_n100", circles_image(), 100), ("cvorb_synth_640x480_f0", co.synth_gray(20261018, 0, 640, 480), 1000),
+                          ("cvorb_synth_640x480_f1", co.synth_gray(20261018, 1, 640, 480), 1000)):
+        kp, d = cv2.ORB_create(nf).detectAndCompute(img, None)
+        t = np.zeros(len(kp), co.KP_DTYPE)
+        for i, k in enumerate(kp):
+            t[i] = (k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave, k.class_id)
+        order = np.lexsort((t["x"], t["y"], -t["response"].astype(np.float64), t["octave"]))
+        ok, od = cvc.CvOrb(nfeatures=nf).extract(img)
+        assert np.array_equal(t[order].view(np.uint8), ok.view(np.uint8)) and np.array_equal(d[order], od), name      # the restatement IS cv2's output
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), image_crc=crc(img), nfeatures=nf, kps=t[order], desc=d[order],
+                            **({"image": img} if "circles" in name else {"seed": 20261018, "frame": int(name[-1]), "width": 640, "height": 480}))
+        print(name, len(kp), "keypoints")
     # ---- primitives ----
     rng = np.random.default_rng(12345)
     noise = rng.integers(0, 256, (97, 131), dtype=np.uint8)

@@ -711,6 +711,76 @@ void orc_gaussian_blur7(const uint8_t *src, int w, int h, size_t sstep, uint8_t 
     free(rows);
 }
 
+/* ---- profile C (cv::ORB, the reference's gtest test/test_dbow2_integration.cpp:19,38 and BASELINE configs[0]) primitives ---- */
+/* cv::resize(..., INTER_LINEAR_EXACT) on CV_8UC1: ufixedpoint16 coefficients (8 fractional bits) from the double-precision source
+ * coordinate, horizontal pass exact in 16 bits, vertical pass in 32 bits with ONE rounding (+32768 >> 16).  Pinned bit for bit against
+ * cv2.resize(INTER_LINEAR_EXACT) in tests/test_cvorb_oracle.py. */
+void orc_resize_exact_tables(int ssize, int dsize, int32_t *ofs, int16_t *coef /*2 per i, c0 + c1 = 256*/)
+{
+    const double scale = 1.0 / ((double)dsize / (double)ssize);
+    for (int x = 0; x < dsize; x++) {
+        const double fval = scale * ((double)x + 0.5) - 0.5;
+        int ival = (int)floor(fval);
+        int c0, c1;
+        if (ival >= 0 && ssize > 1) {
+            if (ival < ssize - 1) { c1 = (int)lrint((fval - (double)ival) * 256.0); c0 = 256 - c1; }
+            else { ival = ssize - 2; c0 = 0; c1 = 256; }
+        } else { ival = 0; c0 = 256; c1 = 0; }
+        ofs[x] = ival; coef[2 * x] = (int16_t)c0; coef[2 * x + 1] = (int16_t)c1;
+    }
+}
+void orc_resize_linear_exact(const uint8_t *src, int sw, int sh, size_t sstep, uint8_t *dst, int dw, int dh, size_t dstep)
+{
+    int32_t *xofs = (int32_t *)malloc(sizeof(int32_t) * dw), *yofs = (int32_t *)malloc(sizeof(int32_t) * dh);
+    int16_t *xa = (int16_t *)malloc(sizeof(int16_t) * 2 * dw), *ya = (int16_t *)malloc(sizeof(int16_t) * 2 * dh);
+    orc_resize_exact_tables(sw, dw, xofs, xa);
+    orc_resize_exact_tables(sh, dh, yofs, ya);
+    for (int y = 0; y < dh; y++) {
+        const uint8_t *S0 = src + (size_t)yofs[y] * sstep, *S1 = src + (size_t)(yofs[y] + 1 < sh ? yofs[y] + 1 : sh - 1) * sstep;
+        uint8_t *D = dst + (size_t)y * dstep;
+        for (int x = 0; x < dw; x++) {
+            const int x0 = xofs[x], x1 = x0 + 1 < sw ? x0 + 1 : sw - 1;
+            const uint32_t h0 = (uint32_t)S0[x0] * xa[2 * x] + (uint32_t)S0[x1] * xa[2 * x + 1];
+            const uint32_t h1 = (uint32_t)S1[x0] * xa[2 * x] + (uint32_t)S1[x1] * xa[2 * x + 1];
+            const uint32_t v = (h0 * (uint32_t)ya[2 * y] + h1 * (uint32_t)ya[2 * y + 1] + 32768u) >> 16;
+            D[x] = (uint8_t)(v > 255u ? 255u : v);
+        }
+    }
+    free(xofs); free(yofs); free(xa); free(ya);
+}
+/* cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) on a SUB-MATRIX (cv::ORB blurs its pyramid layers in place inside one big buffer):
+ * OpenCV then runs sepFilter2D with the CV_32F kernel getGaussianKernel(7, 2).  fp32 arithmetic of the AVX2/FMA build of cv2 4.13.0
+ * (found by matching cv2.ORB descriptors, 5000 of 5000 rows): row pass = k0*p0, then fused multiply-adds left to right; column pass =
+ * k3*r3, then fused multiply-adds of the symmetric pairs (r[3+i] + r[3-i]) * k[3+i]; one rounding to u8 (round half to even).
+ * A scalar OpenCV build differs in 1-3 px per 120k, hence north_star's ">= 99.9 % of descriptor rows" bar for profile C. */
+static const uint32_t k_gauss7_f32_bits[7] = { 1032826801u, 1040595070u, 1044597305u, 1046301408u, 1044597305u, 1040595070u, 1032826801u };
+void orc_gaussian_blur7_f32(const uint8_t *src, int w, int h, size_t sstep, uint8_t *dst, size_t dstep)
+{
+    float k[7];
+    memcpy(k, k_gauss7_f32_bits, sizeof(k));
+    float *rows = (float *)malloc(sizeof(float) * (size_t)w * h);
+    for (int y = 0; y < h; y++) {
+        const uint8_t *S = src + (size_t)y * sstep;
+        for (int x = 0; x < w; x++) {
+            float s = k[0] * (float)S[reflect101(x - 3, w)];
+            for (int i = 1; i < 7; i++) s = fmaf((float)S[reflect101(x + i - 3, w)], k[i], s);
+            rows[(size_t)y * w + x] = s;
+        }
+    }
+    for (int y = 0; y < h; y++) {
+        const float *r[7];
+        for (int j = 0; j < 7; j++) r[j] = rows + (size_t)reflect101(y + j - 3, h) * w;
+        uint8_t *D = dst + (size_t)y * dstep;
+        for (int x = 0; x < w; x++) {
+            float s = k[3] * r[3][x];
+            for (int i = 1; i <= 3; i++) s = fmaf(r[3 + i][x] + r[3 - i][x], k[3 + i], s);
+            long v = lrintf(s);
+            D[x] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+        }
+    }
+    free(rows);
+}
+
 /* computeOrbDescriptor — ORBextractor.cpp:106-146 */
 void orc_descriptor(const uint8_t *blur, size_t step_, int cx, int cy, float angle_deg, uint8_t *desc)
 {

@@ -72,6 +72,10 @@ int  orc_distribute_octtree(const orc_cand *cands, int n, int minX, int maxX, in
 float orc_fast_atan2(float y, float x);
 float orc_ic_angle(const uint8_t *img, size_t step, int cx, int cy, const int *umax);
 void orc_gaussian_blur7(const uint8_t *src, int w, int h, size_t sstep, uint8_t *dst, size_t dstep);
+/* profile C (cv::ORB) primitives: cv::resize INTER_LINEAR_EXACT and the float-path GaussianBlur of a sub-matrix */
+void orc_resize_exact_tables(int ssize, int dsize, int32_t *ofs, int16_t *coef /*2 per i*/);
+void orc_resize_linear_exact(const uint8_t *src, int sw, int sh, size_t sstep, uint8_t *dst, int dw, int dh, size_t dstep);
+void orc_gaussian_blur7_f32(const uint8_t *src, int w, int h, size_t sstep, uint8_t *dst, size_t dstep);
 void orc_descriptor(const uint8_t *blur, size_t step, int cx, int cy, float angle_deg, uint8_t *desc32);
 
 /* ORBextractor::operator() ; returns keypoint count, -1 on empty image, -2 capacity, -3 frame size outside the reference's defined domain */
