@@ -150,6 +150,91 @@ __global__ void __launch_bounds__(RZ_THREADS) k_resize_linear(const __grid_const
 
 int launch_resize_level(orbx_handle *h, int level, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
 
+// ---- batch variant: warp = 32 column groups x 16 consecutive output rows, every branch warp-uniform, no register shuffling ----
+// Same arithmetic and the same helpers as k_resize_linear; what changes is who does what.  There a 192-thread CTA maps 48 column groups
+// x 4 row bands onto 6 warps, so two warps straddle two bands and diverge on every "can the previous row's horizontal pass be reused?"
+// branch, and the reuse itself costs register moves; the profile showed 86 warp instructions per (warp, output row) against ~45 of
+// arithmetic.  Here a CTA is 4 warps over a 128 x 64 output tile: a warp owns 128 columns x 16 rows, its reuse decisions are the same for
+// all lanes, and the row loop is unrolled by two with the roles of the two row registers swapped, so "this row's lower source row is the
+// next row's upper one" (5 rows out of 6 at scale 1.2) needs no copy at all.  Row codes are prepared once per tile in shared memory:
+// code 0 = upper source row is the previous output row's lower one; anything else = interpolate both rows (always correct).
+#define RZ2_TW 128
+#define RZ2_TH 64
+#define RZ2_WARPS 4
+#define RZ2_ROWS (RZ2_TH / RZ2_WARPS)
+template <bool bytewise> __global__ void __launch_bounds__(RZ2_WARPS * 32) k_resize_linear2(const __grid_constant__ LevelMaps M, ResizeParams P)
+{
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int4 s_rt[RZ2_TH];                                                 // per output row: smem offsets of its two source rows | code << 24, b0, b1
+    uint8_t *s_img = s_raw + ((128u - (smem_u32(s_raw) & 127u)) & 127u);
+    const int f = blockIdx.z;
+    const int x0 = blockIdx.x * RZ2_TW, y0 = blockIdx.y * RZ2_TH;
+    const int x1 = min(x0 + RZ2_TW, P.dw) - 1, y1 = min(y0 + RZ2_TH, P.dh) - 1;
+    const int abase = __ldg(&P.xtab[x0].ofs) & ~15;
+    const int sylo = max(0, min(__ldg(&P.ytab[y0].ofs), P.sh - 1));
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&s_bar, (uint32_t)(ORBX_RZ_BOX_ROWS * ORBX_TMA_BOX_BYTES));
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        tma_load_3d(s_img, &M.m[P.src_level], abase >> 2, sylo, f, &s_bar);
+    }
+    for (int r = threadIdx.x; r <= y1 - y0; r += RZ2_WARPS * 32) {
+        const ResizeTab ty = P.ytab[y0 + r];
+        const int sy0 = max(0, min(ty.ofs, P.sh - 1)), sy1 = max(0, min(ty.ofs + 1, P.sh - 1));
+        int code = 1;
+        if (r % RZ2_ROWS != 0) {                                                    // not the first row of a warp's band: compare with the previous output row
+            const ResizeTab tp = P.ytab[y0 + r - 1];
+            const int py1 = max(0, min(tp.ofs + 1, P.sh - 1));
+            if (sy0 == py1 && sy1 != sy0) code = 0;
+        }
+        s_rt[r] = make_int4((sy0 - sylo) * ORBX_TMA_BOX_BYTES, ((sy1 - sylo) * ORBX_TMA_BOX_BYTES) | (code << 24), ty.a0, ty.a1);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int x4 = x0 + 4 * lane;
+    RzCols C;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const ResizeTab tx = P.xtab[min(x4 + i, P.dw - 1)];
+        C.o[i] = tx.ofs - abase; C.a0[i] = tx.a0; C.a1[i] = tx.a1;
+    }
+    rz_cols_finish(C);
+    __syncthreads();
+    mbar_wait(&s_bar, 0);
+    if (x4 > x1) return;
+    const int nrows = y1 - y0 + 1;
+    const int rb = wid * RZ2_ROWS, re = min(nrows, rb + RZ2_ROWS);
+    if (rb >= re) return;
+    uint8_t *D = P.dst + (size_t)f * P.dst_fstride + (size_t)(y0 + rb) * P.dst_step + x4;
+    int X[4], Y[4];                                                                  // horizontal passes of two source rows; which one is "upper" alternates
+    int r = rb;
+    for (; r + 1 < re; r += 2) {
+        {   // even step: the previous row's lower source row (if any) sits in X; this row leaves its lower one in Y
+            const int4 e = s_rt[r];
+            if (e.y >> 24) rz_hrow(s_img + e.x, C, bytewise, X);
+            rz_hrow(s_img + (e.y & 0xFFFFFF), C, bytewise, Y);
+            *reinterpret_cast<uint32_t *>(D) = rz_vpack(e.z, e.w, X, Y);
+            D += P.dst_step;
+        }
+        {   // odd step: roles swapped
+            const int4 e = s_rt[r + 1];
+            if (e.y >> 24) rz_hrow(s_img + e.x, C, bytewise, Y);
+            rz_hrow(s_img + (e.y & 0xFFFFFF), C, bytewise, X);
+            *reinterpret_cast<uint32_t *>(D) = rz_vpack(e.z, e.w, Y, X);
+            D += P.dst_step;
+        }
+    }
+    if (r < re) {
+        const int4 e = s_rt[r];
+        if (e.y >> 24) rz_hrow(s_img + e.x, C, bytewise, X);
+        rz_hrow(s_img + (e.y & 0xFFFFFF), C, bytewise, Y);
+        *reinterpret_cast<uint32_t *>(D) = rz_vpack(e.z, e.w, X, Y);
+    }
+}
+
 // ---- all levels in one cooperative launch ----
 struct PyrParams {
     uint8_t *pyr; size_t pyr_slab;
@@ -304,6 +389,15 @@ int launch_resize_level(orbx_handle *h, int level, int nframes, const uint8_t *l
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = (level >= 2 && !h->prof_on && h->opt_pdl) ? 1 : 0;
+#ifndef ORBX_RESIZE_V1
+    if (h->geo.rz_tw >= RZ2_TW && h->geo.rz_th >= RZ2_TH) {                     // the 128 x 64 tile's source window fits the TMA box at every level
+        auto kern = P.sw > 2 * P.dw ? k_resize_linear2<true> : k_resize_linear2<false>;      // scales above 2 take the byte-wise horizontal pass
+        if (!orbx_optin_smem(h, (const void *)kern, smem)) return -1;
+        cfg.gridDim = dim3((gd.w + RZ2_TW - 1) / RZ2_TW, (gd.h + RZ2_TH - 1) / RZ2_TH, nframes); cfg.blockDim = dim3(RZ2_WARPS * 32);
+        if (cudaLaunchKernelEx(&cfg, kern, M, P) != cudaSuccess) { cudaGetLastError(); kern<<<cfg.gridDim, RZ2_WARPS * 32, smem, h->stream>>>(M, P); }
+        return 0;
+    }
+#endif
     if (cudaLaunchKernelEx(&cfg, k_resize_linear, M, P) != cudaSuccess) { cudaGetLastError(); k_resize_linear<<<grid, RZ_THREADS, smem, h->stream>>>(M, P); }
     return 0;
 }
