@@ -482,12 +482,14 @@ int orbx_ensure_tmaps(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_
         for (int l = 1; l < G.nlevels; l++)
             if (!encode_level(&h->tmap[l], h->d_pyr + G.lv[l].off, (size_t)G.lv[l].pitch, G.lv[l].h, h->pyr_slab, h->prm.max_batch, G.lv[l].hcell + 6) ||
                 !encode_level(&h->tmap_rz[l], h->d_pyr + G.lv[l].off, (size_t)G.lv[l].pitch, G.lv[l].h, h->pyr_slab, h->prm.max_batch, ORBX_RZ_BOX_ROWS) ||
+                !encode_level(&h->tmap_rz2[l], h->d_pyr + G.lv[l].off, (size_t)G.lv[l].pitch, G.lv[l].h, h->pyr_slab, h->prm.max_batch, ORBX_RZ_BOX_ROWS, ORBX_RZ2_BOX_WORDS) ||
                 !encode_level(&h->tmap_cell[l], h->d_pyr + G.lv[l].off, (size_t)G.lv[l].pitch, G.lv[l].h, h->pyr_slab, h->prm.max_batch, G.lv[l].hcell + 6, fast_tile_pitch(G) / 4)) return -1;
         h->tmap_valid = true; h->tmap_l0 = nullptr;
     }
     if (h->tmap_l0 != l0 || h->tmap_l0_step != l0_step || h->tmap_l0_fstride != l0_fstride || h->tmap_l0_frames < nframes) {
         if (!encode_level(&h->tmap[0], l0, l0_step, G.lv[0].h, l0_fstride, nframes, G.lv[0].hcell + 6) ||
             !encode_level(&h->tmap_rz[0], l0, l0_step, G.lv[0].h, l0_fstride, nframes, ORBX_RZ_BOX_ROWS) ||
+            !encode_level(&h->tmap_rz2[0], l0, l0_step, G.lv[0].h, l0_fstride, nframes, ORBX_RZ_BOX_ROWS, ORBX_RZ2_BOX_WORDS) ||
             !encode_level(&h->tmap_cell[0], l0, l0_step, G.lv[0].h, l0_fstride, nframes, G.lv[0].hcell + 6, fast_tile_pitch(G) / 4)) return -1;
         h->tmap_l0 = l0; h->tmap_l0_step = l0_step; h->tmap_l0_fstride = l0_fstride; h->tmap_l0_frames = nframes;
     }

@@ -178,7 +178,7 @@ template <bool bytewise> __global__ void __launch_bounds__(RZ2_WARPS * 32) k_res
         mbar_init(&s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&s_bar, (uint32_t)(ORBX_RZ_BOX_ROWS * ORBX_TMA_BOX_BYTES));
+        mbar_expect_tx(&s_bar, (uint32_t)(ORBX_RZ_BOX_ROWS * ORBX_RZ2_BOX_BYTES));
         asm volatile("griddepcontrol.wait;" ::: "memory");
         tma_load_3d(s_img, &M.m[P.src_level], abase >> 2, sylo, f, &s_bar);
     }
@@ -191,7 +191,7 @@ template <bool bytewise> __global__ void __launch_bounds__(RZ2_WARPS * 32) k_res
             const int py1 = max(0, min(tp.ofs + 1, P.sh - 1));
             if (sy0 == py1 && sy1 != sy0) code = 0;
         }
-        s_rt[r] = make_int4((sy0 - sylo) * ORBX_TMA_BOX_BYTES, ((sy1 - sylo) * ORBX_TMA_BOX_BYTES) | (code << 24), ty.a0, ty.a1);
+        s_rt[r] = make_int4((sy0 - sylo) * ORBX_RZ2_BOX_BYTES, ((sy1 - sylo) * ORBX_RZ2_BOX_BYTES) | (code << 24), ty.a0, ty.a1);
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int x4 = x0 + 4 * lane;
@@ -390,11 +390,13 @@ int launch_resize_level(orbx_handle *h, int level, int nframes, const uint8_t *l
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = (level >= 2 && !h->prof_on && h->opt_pdl) ? 1 : 0;
 #ifndef ORBX_RESIZE_V1
-    if (h->geo.rz_tw >= RZ2_TW && h->geo.rz_th >= RZ2_TH) {                     // the 128 x 64 tile's source window fits the TMA box at every level
+    if (h->geo.rz2_ok) {                                                       // the 128 x 64 tile's source window fits the 192-byte box at every level
+        memcpy(M.m, h->tmap_rz2, sizeof(M.m));
+        const size_t smem2 = 128 + (size_t)ORBX_RZ_BOX_ROWS * ORBX_RZ2_BOX_BYTES + 16;
         auto kern = P.sw > 2 * P.dw ? k_resize_linear2<true> : k_resize_linear2<false>;      // scales above 2 take the byte-wise horizontal pass
-        if (!orbx_optin_smem(h, (const void *)kern, smem)) return -1;
-        cfg.gridDim = dim3((gd.w + RZ2_TW - 1) / RZ2_TW, (gd.h + RZ2_TH - 1) / RZ2_TH, nframes); cfg.blockDim = dim3(RZ2_WARPS * 32);
-        if (cudaLaunchKernelEx(&cfg, kern, M, P) != cudaSuccess) { cudaGetLastError(); kern<<<cfg.gridDim, RZ2_WARPS * 32, smem, h->stream>>>(M, P); }
+        if (!orbx_optin_smem(h, (const void *)kern, smem2)) return -1;
+        cfg.gridDim = dim3((gd.w + RZ2_TW - 1) / RZ2_TW, (gd.h + RZ2_TH - 1) / RZ2_TH, nframes); cfg.blockDim = dim3(RZ2_WARPS * 32); cfg.dynamicSmemBytes = smem2;
+        if (cudaLaunchKernelEx(&cfg, kern, M, P) != cudaSuccess) { cudaGetLastError(); kern<<<cfg.gridDim, RZ2_WARPS * 32, smem2, h->stream>>>(M, P); }
         return 0;
     }
 #endif

@@ -192,6 +192,18 @@ static bool build_geometry(const orbx_handle *h, int w, int hgt, FrameGeom &G, s
         if (!fits) { if (rtw > 16) rtw -= 16; if (rth > 8) rth -= 8; if (rtw <= 16 && rth <= 8) return false; }
     }
     G.rz_tw = rtw; G.rz_th = rth;
+    // batch kernel (k_resize_linear2): 128 x 64 output tiles, source window in a 192-byte x 80-row box
+    G.rz2_ok = (xt && yt) ? 1 : 0;
+    if (xt && yt) for (int l = 1; l < p.nlevels && G.rz2_ok; l++) {
+        const LevelGeom &g = G.lv[l];
+        const ResizeTab *tx = xt->data() + g.xtab_off, *ty = yt->data() + g.ytab_off;
+        for (int x0 = 0; x0 < g.w && G.rz2_ok; x0 += 128) if (tx[std::min(x0 + 128, g.w) - 1].ofs + 1 - (tx[x0].ofs & ~15) >= 192 - 8) G.rz2_ok = 0;   // - 8: the third word rz_hrow reads
+        for (int y0 = 0; y0 < g.h && G.rz2_ok; y0 += 64) {
+            const int y1 = std::min(y0 + 64, g.h) - 1;
+            const int lo = std::max(0, std::min(ty[y0].ofs, G.lv[l - 1].h - 1)), hi = std::max(0, std::min(ty[y1].ofs + 1, G.lv[l - 1].h - 1));
+            if (hi - lo + 1 > 80) G.rz2_ok = 0;
+        }
+    }
     G.total_cells = cells; G.total_blur_tiles = tiles; G.total_strips = std::max(strips, 1); G.max_hcell = max_hcell; G.max_wcell = max_wcell; G.total_cells_valid = cells_valid;
     G.pyr_bytes = std::max<size_t>(off, 256); G.blur_bytes = boff; G.cand_entries = coff; G.sel_entries = soff; G.node_cap_max = ncmax;
     return true;
@@ -706,7 +718,7 @@ static void swap_lane(orbx_handle *h)
     std::swap(h->d_owner, A.d_owner); std::swap(h->d_owner2, A.d_owner2); std::swap(h->d_ncand, A.d_ncand); std::swap(h->d_nsel, A.d_nsel);
     std::swap(h->d_sel, A.d_sel); std::swap(h->d_kps_all, A.d_kps_all); std::swap(h->d_desc_all, A.d_desc_all); std::swap(h->d_count_all, A.d_count_all);
     std::swap(h->d_mpart, A.d_mpart); std::swap(h->mpart_cap, A.mpart_cap);
-    for (int l = 0; l < ORBX_MAX_LEVELS; l++) { std::swap(h->tmap[l], A.tmap[l]); std::swap(h->tmap_rz[l], A.tmap_rz[l]); std::swap(h->tmap_cell[l], A.tmap_cell[l]); }
+    for (int l = 0; l < ORBX_MAX_LEVELS; l++) { std::swap(h->tmap[l], A.tmap[l]); std::swap(h->tmap_rz[l], A.tmap_rz[l]); std::swap(h->tmap_rz2[l], A.tmap_rz2[l]); std::swap(h->tmap_cell[l], A.tmap_cell[l]); }
     std::swap(h->tmap_valid, A.tmap_valid); std::swap(h->tmap_l0, A.tmap_l0); std::swap(h->tmap_l0_step, A.tmap_l0_step);
     std::swap(h->tmap_l0_fstride, A.tmap_l0_fstride); std::swap(h->tmap_l0_frames, A.tmap_l0_frames);
 }
@@ -1489,6 +1501,35 @@ extern "C" orbx_status orbx_cull_keyframe(orbx_handle *h, const orbx_keypoint *k
         if (out_index) ORBX_CUDA(h, cudaMemcpyAsync(out_index, oi, (size_t)m * 4, cudaMemcpyDeviceToHost, h->stream));
         ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
     }
+    return ORBX_OK;
+}
+
+// ---- geometric validation: hypothesis scoring (frontend.cpp:1134-1154) ----
+extern "C" orbx_status orbx_fmat_score(orbx_handle *h, const float *pts1, const float *pts2, int32_t n, const double *F, int32_t nh, double threshold,
+                                       int32_t *inlier_counts, int32_t *best, uint8_t *best_mask)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    if (n < 0 || nh < 1 || !F || !best || (n > 0 && (!pts1 || !pts2)) || !(threshold >= 0)) { h->err = "bad fundamental-matrix scoring arguments"; return ORBX_E_INVALID; }
+    if (h->pending[0].active || h->pending[1].active) { h->err = "an asynchronous batch is outstanding: call orbx_batch_wait first"; return ORBX_E_INVALID; }
+    orbx_status st;
+    const size_t bp = align_up((size_t)std::max(n, 1) * 8, 16), bf = align_up((size_t)nh * 72, 16), bc = align_up((size_t)nh * 4, 16), bm = align_up((size_t)nh * std::max(n, 1), 16);
+    if ((st = grow(h, &h->d_mq, &h->mq_cap, 2 * bp + bf + bc + 16 + align_up((size_t)std::max(n, 1), 16))) != ORBX_OK) return st;
+    if ((st = grow(h, &h->d_mt, &h->mt_cap, bm)) != ORBX_OK) return st;
+    float *d_p1 = (float *)h->d_mq, *d_p2 = (float *)(h->d_mq + bp);
+    double *d_F = (double *)(h->d_mq + 2 * bp);
+    int32_t *d_c = (int32_t *)(h->d_mq + 2 * bp + bf), *d_b = (int32_t *)(h->d_mq + 2 * bp + bf + bc);
+    uint8_t *d_bm = h->d_mq + 2 * bp + bf + bc + 16;
+    if (n > 0) {
+        ORBX_CUDA(h, cudaMemcpyAsync(d_p1, pts1, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+        ORBX_CUDA(h, cudaMemcpyAsync(d_p2, pts2, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    ORBX_CUDA(h, cudaMemcpyAsync(d_F, F, (size_t)nh * 72, cudaMemcpyHostToDevice, h->stream));
+    launch_fmat_score(h, d_p1, d_p2, n, d_F, nh, (float)(threshold * threshold), d_c, h->d_mt, d_b, d_bm);
+    ORBX_CUDA(h, cudaMemcpyAsync(best, d_b, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (inlier_counts) ORBX_CUDA(h, cudaMemcpyAsync(inlier_counts, d_c, (size_t)nh * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (best_mask && n > 0) ORBX_CUDA(h, cudaMemcpyAsync(best_mask, d_bm, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
     return ORBX_OK;
 }
 

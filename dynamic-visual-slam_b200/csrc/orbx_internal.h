@@ -52,6 +52,7 @@ struct FrameGeom {
     int width, height;
     int total_cells, total_blur_tiles, total_strips, max_hcell, max_wcell, total_cells_valid;
     int rz_tw, rz_th;        // output tile of the resize kernel: its source window fits the 288-byte x 80-row TMA box at every level
+    int rz2_ok;              // the 128 x 64 tile of the batch kernel fits a 192-byte x 80-row box at every level (scale factors up to ~1.35)
     size_t pyr_bytes;        // per-frame pyramid slab size (levels 1..)
     size_t blur_bytes;       // per-frame blurred slab size (levels 0..)
     size_t cand_entries;     // per-frame candidate slab entries
@@ -74,7 +75,7 @@ struct OrbxLane {
     cudaStream_t stream;
     uint8_t *d_pyr; uint32_t *d_cand, *d_cand2, *d_qtmp; uint16_t *d_owner, *d_owner2; int32_t *d_ncand, *d_nsel; uint32_t *d_sel;
     orbx_keypoint *d_kps_all; uint8_t *d_desc_all; int32_t *d_count_all; uint32_t *d_mpart; size_t mpart_cap;
-    CUtensorMap tmap[ORBX_MAX_LEVELS], tmap_rz[ORBX_MAX_LEVELS], tmap_cell[ORBX_MAX_LEVELS]; bool tmap_valid;
+    CUtensorMap tmap[ORBX_MAX_LEVELS], tmap_rz[ORBX_MAX_LEVELS], tmap_rz2[ORBX_MAX_LEVELS], tmap_cell[ORBX_MAX_LEVELS]; bool tmap_valid;
     const uint8_t *tmap_l0; size_t tmap_l0_step, tmap_l0_fstride; int tmap_l0_frames;
 };
 
@@ -118,6 +119,7 @@ struct orbx_handle {
     // TMA tensor maps of the pyramid levels (k_fast.cu): levels >= 1 depend on the geometry only, level 0 on the caller's frames
     CUtensorMap tmap[ORBX_MAX_LEVELS]; bool tmap_valid;      // box rows = hCell + 6 (FAST strips, blur tiles)
     CUtensorMap tmap_rz[ORBX_MAX_LEVELS];                    // box rows = ORBX_RZ_BOX_ROWS (resize source windows)
+    CUtensorMap tmap_rz2[ORBX_MAX_LEVELS];                   // the same with a 192-byte box: source windows of the 128-column batch tiles
     CUtensorMap tmap_cell[ORBX_MAX_LEVELS];                  // box = 96 bytes x (hCell + 6) rows (FAST cell windows)
     void *d_cells; int cell_cap;                             // FAST cell records, 32 bytes each (k_fast.cu: orbx_build_fast_cells)
     const uint8_t *tmap_l0; size_t tmap_l0_step, tmap_l0_fstride; int tmap_l0_frames;
@@ -265,3 +267,5 @@ void launch_test_trig(orbx_handle *h, const float *d_in, int n, float *d_c, floa
 void launch_test_atan2(orbx_handle *h, const float *d_y, const float *d_x, int n, float *d_o);
 void launch_trig_checksum(orbx_handle *h, uint32_t first, uint32_t last, unsigned long long *d_sums);
 double run_popc_bench(orbx_handle *h);
+void launch_fmat_score(orbx_handle *h, const float *d_p1, const float *d_p2, int n, const double *d_F, int nh, float t2,
+                       int32_t *d_counts, uint8_t *d_masks, int32_t *d_best, uint8_t *d_best_mask);

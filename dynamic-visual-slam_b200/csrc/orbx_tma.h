@@ -10,6 +10,8 @@
 #define ORBX_TMA_BOX_WORDS 72            // 288 bytes
 #define ORBX_TMA_BOX_BYTES (ORBX_TMA_BOX_WORDS * 4)
 #define ORBX_RZ_BOX_ROWS 80               // source rows staged per resize tile (k_pyramid.cu)
+#define ORBX_RZ2_BOX_WORDS 48             // 192 bytes: source window of a 128-column output tile (k_resize_linear2)
+#define ORBX_RZ2_BOX_BYTES (ORBX_RZ2_BOX_WORDS * 4)
 
 struct LevelMaps { CUtensorMap m[ORBX_MAX_LEVELS]; };
 

@@ -131,6 +131,7 @@ def load():
         "orbx_extract_batch_submit": (i32, [vp, vp, i32, i32, i32, sz, vp, sz, vp, vp, i32, vp, vp]),
         "orbx_track_batch_submit": (i32, [vp, vp, i32, i32, i32, sz, vp, sz, vp, vp, i32, vp, vp, vp, f32, vp]),
         "orbx_batch_wait": (i32, [vp, i32]),
+        "orbx_fmat_score": (i32, [vp, vp, vp, i32, vp, i32, ct.c_double, vp, vp, vp]),
         "orbx_comm_get_unique_id": (i32, [vp]),
         "orbx_comm_last_error": (ct.c_char_p, []),
         "orbx_comm_create": (i32, [vp, i32, i32, vp, vp]),
@@ -404,6 +405,18 @@ class ORBextractor:
             self._check(self.L.orbx_extract_batch_boxes(self._h, _p(frames), nf, w, h, frames.strides[1], dptr, dstep,
                                                         _p(boxes), _p(off), ct.c_uint64(drop_class_mask), _p(kps), _p(desc), cap, _p(counts)))
         return kps, desc, counts
+
+    def fmat_score(self, pts1, pts2, F, threshold=2.0):
+        """Inlier counts of fundamental-matrix hypotheses F [nh, 3, 3] under OpenCV's RANSAC error (frontend.cpp:1134-1154);
+        returns (counts[nh], best index, mask[n] of the best)."""
+        pts1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+        pts2 = np.ascontiguousarray(pts2, np.float32).reshape(-1, 2)
+        F = np.ascontiguousarray(F, np.float64).reshape(-1, 9)
+        counts = np.zeros(len(F), np.int32)
+        mask = np.zeros(max(len(pts1), 1), np.uint8)
+        best = ct.c_int32()
+        self._check(self.L.orbx_fmat_score(self._h, _p(pts1), _p(pts2), len(pts1), _p(F), len(F), ct.c_double(threshold), _p(counts), ct.byref(best), _p(mask)))
+        return counts, best.value, mask[:len(pts1)].copy()
 
     def extract_batch_device(self, d_gray, nframes, w, h, step, frame_stride, d_kps, d_desc, cap, d_counts,
                              d_depth=None, dstep=0, dframe_stride=0):

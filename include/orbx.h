@@ -317,6 +317,16 @@ orbx_status orbx_cull_keyframe_device(orbx_handle *h, const orbx_keypoint *d_kps
                                       const int32_t *d_match_query, int32_t n_matches, int32_t max_new, float min_response,
                                       orbx_keypoint *d_out_kps, uint8_t *d_out_desc, int32_t *d_out_index, int32_t cap, int32_t *d_n_out);
 
+/* ---- geometric validation, hypothesis scoring: SURVEY §8(f) rank 4 ----
+ * The K x N evaluation inside cv::findFundamentalMat(prev_pts, curr_pts, mask, cv::FM_RANSAC, 2.0, 0.99) (frontend.cpp:1134-1154, :625-645):
+ * for each of nh fundamental-matrix hypotheses F (row-major 3x3 doubles; x2' F x1 = 0 with pts1 = prev_pts, pts2 = curr_pts) the symmetric
+ * epipolar error OpenCV's RANSAC uses (double precision, its operation order), inlier <=> (float)err <= (float)(threshold^2).
+ * inlier_counts[nh]; *best = hypothesis with the most inliers (ties: lowest index); best_mask[n] = its inlier mask, bit-identical to the
+ * mask OpenCV computes for that F.  Sampling and the minimal solves stay with the caller (PnP / F-matrix RANSAC are the reference's,
+ * north_star).  inlier_counts, best_mask may be NULL.                                                                          */
+orbx_status orbx_fmat_score(orbx_handle *h, const float *pts1, const float *pts2, int32_t n, const double *F, int32_t nh, double threshold,
+                            int32_t *inlier_counts, int32_t *best, uint8_t *best_mask);
+
 /* ---- keyframe packing: the landmark / observation loop of Frontend::publishKeyframe (frontend.cpp:731-776), SURVEY §8(f) rank 2 ----
  * For every keypoint with a depth in (0.3, 3.0) m: back-projection with the float intrinsics, world transform R*p + t in double,
  * one 80-byte record; order preserved; landmark_id = index of the keypoint in the input list, as in the reference.

@@ -212,6 +212,15 @@ def descriptor(blur, cx, cy, angle_deg):
     return d
 
 
+def fmat_inliers(p1, p2, F, thresh=2.0):
+    p1 = np.ascontiguousarray(p1, np.float32).reshape(-1, 2)
+    p2 = np.ascontiguousarray(p2, np.float32).reshape(-1, 2)
+    F = np.ascontiguousarray(F, np.float64).reshape(9)
+    mask = np.zeros(max(len(p1), 1), np.uint8)
+    n = lib().orc_fmat_inliers(_p(p1), _p(p2), len(p1), _p(F), ct.c_double(thresh), _p(mask))
+    return n, mask[:len(p1)].copy()
+
+
 def fast_atan2(y, x):
     return float(lib().orc_fast_atan2(ct.c_float(y), ct.c_float(x)))
 

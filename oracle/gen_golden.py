@@ -107,6 +107,22 @@ def main():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), image_crc=crc(img), nfeatures=nf, kps=t[order], desc=d[order],
                             **({"image": img} if "circles" in name else {"seed": 20261018, "frame": int(name[-1]), "width": 640, "height": 480}))
         print(name, len(kp), "keypoints")
+    # ---- geometric validation: cv::findFundamentalMat(FM_RANSAC, 2.0, 0.99) on the matches of a synthetic frame pair (frontend.cpp:1134-1154):
+    #      the returned model and ITS inlier mask; the scoring restatement / kernel must reproduce that mask for that model ----
+    orc = co.COracle()
+    ra, rb = orc.extract(co.synth_gray(20261018, 0, 640, 480)), orc.extract(co.synth_gray(20261018, 1, 640, 480))
+    mm = co.match(rb["desc"], ra["desc"])
+    mm = mm[mm["distance"] < 50.0]
+    p_prev = np.stack([ra["kps"]["x"][mm["trainIdx"]], ra["kps"]["y"][mm["trainIdx"]]], 1).astype(np.float32)
+    p_curr = np.stack([rb["kps"]["x"][mm["queryIdx"]], rb["kps"]["y"][mm["queryIdx"]]], 1).astype(np.float32)
+    rngf = np.random.default_rng(99)
+    bad = rngf.choice(len(p_curr), len(p_curr) // 5, replace=False)                  # 20 % gross outliers
+    p_curr[bad] += rngf.uniform(-40, 40, (len(bad), 2)).astype(np.float32)
+    Fm, msk = cv2.findFundamentalMat(p_prev, p_curr, cv2.FM_RANSAC, 2.0, 0.99)
+    n_in, m2 = co.fmat_inliers(p_prev, p_curr, Fm[:3], 2.0)
+    assert np.array_equal(m2, msk.ravel()), "scoring restatement differs from cv2's mask for cv2's own model"
+    np.savez_compressed(os.path.join(OUT, "fmat_ransac.npz"), pts_prev=p_prev, pts_curr=p_curr, F=Fm[:3].astype(np.float64), mask=msk.ravel().astype(np.uint8))
+    print("fmat_ransac", len(p_prev), "pairs,", int(msk.sum()), "inliers")
     # ---- primitives ----
     rng = np.random.default_rng(12345)
     noise = rng.integers(0, 256, (97, 131), dtype=np.uint8)

@@ -711,6 +711,28 @@ void orc_gaussian_blur7(const uint8_t *src, int w, int h, size_t sstep, uint8_t 
     free(rows);
 }
 
+/* cv::findFundamentalMat(..., FM_RANSAC, thresh, conf) scores a model with FMEstimatorCallback::computeError (calib3d/src/fundam.cpp):
+ * symmetric epipolar distance in double, stored as float; inlier <=> err <= (float)(thresh*thresh) — reference call sites
+ * frontend.cpp:1134-1154, :625-645.  F row-major 3x3, pts1 = the first point set (x2' F x1 = 0).  Returns the inlier count. */
+int orc_fmat_inliers(const float *p1, const float *p2, int n, const double *F, double thresh, uint8_t *mask)
+{
+    const float t = (float)(thresh * thresh);
+    int cnt = 0;
+    for (int i = 0; i < n; i++) {
+        const double x1 = p1[2 * i], y1 = p1[2 * i + 1], x2 = p2[2 * i], y2 = p2[2 * i + 1];
+        double a = F[0] * x1 + F[1] * y1 + F[2], b = F[3] * x1 + F[4] * y1 + F[5], c = F[6] * x1 + F[7] * y1 + F[8];
+        const double s2 = 1. / (a * a + b * b), d2 = x2 * a + y2 * b + c;
+        a = F[0] * x2 + F[3] * y2 + F[6]; b = F[1] * x2 + F[4] * y2 + F[7]; c = F[2] * x2 + F[5] * y2 + F[8];
+        const double s1 = 1. / (a * a + b * b), d1 = x1 * a + y1 * b + c;
+        const double e1 = d1 * d1 * s1, e2 = d2 * d2 * s2;
+        const float err = (float)(e1 > e2 ? e1 : e2);
+        const int in = err <= t;
+        if (mask) mask[i] = (uint8_t)in;
+        cnt += in;
+    }
+    return cnt;
+}
+
 /* ---- profile C (cv::ORB, the reference's gtest test/test_dbow2_integration.cpp:19,38 and BASELINE configs[0]) primitives ---- */
 /* cv::resize(..., INTER_LINEAR_EXACT) on CV_8UC1: ufixedpoint16 coefficients (8 fractional bits) from the double-precision source
  * coordinate, horizontal pass exact in 16 bits, vertical pass in 32 bits with ONE rounding (+32768 >> 16).  Pinned bit for bit against
