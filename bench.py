@@ -546,18 +546,27 @@ def main():
         def assoc_step():
             db.query_top2_sharded_device(comm, q.data_ptr(), NQ, merged.data_ptr())      # per-shard kernel -> ncclAllGather -> merge, one stream, no host sync
 
-        for _ in range(3):
-            assoc_step()
-        barrier()
-        ex.profile_enable(True)
-        e0.record(stream)
-        for _ in range(K):
-            assoc_step()
-        e1.record(stream)
-        barrier()
-        profa = ex.profile_read()
-        ex.profile_enable(False)
-        ms_a = max_over_ranks(e0.elapsed_time(e1) / K)
+        def time_assoc():
+            for _ in range(3):
+                assoc_step()
+            barrier()
+            ex.profile_enable(True)
+            e0.record(stream)
+            for _ in range(K):
+                assoc_step()
+            e1.record(stream)
+            barrier()
+            pr = ex.profile_read()
+            ex.profile_enable(False)
+            return max_over_ranks(e0.elapsed_time(e1) / K), pr
+
+        peer = comm.peer_memory
+        comm.set_transport(nccl=True)
+        ms_nccl, _ = time_assoc()
+        merged_nccl = merged.clone()
+        comm.set_transport(nccl=False)
+        ms_a, profa = time_assoc()                  # default transport: peer-memory mailboxes where the ranks could map each other, else NCCL again
+        same_transports = bool((merged_nccl == merged).all().item())
         res = merged.cpu().numpy().view(np.uint32)
         # the merged answer against ONE unsharded database on this GPU (every rank checks its own copy of the merged result)
         full = orbx.LandmarkDB(ex, ROWS, first_index=0)
@@ -585,8 +594,10 @@ def main():
                  "mismatches_vs_unsharded": mism, "cpu_check": cpu_check,
                  "kernel_ms": kms, "popc_per_s_measured_peak": popc,
                  "popc_frac": (POPC_PER_PAIR * NQ * rows_r / (kms * 1e-3)) / popc if popc > 0 and kms > 0 else None,
-                 "collective": "orbx_db_query_top2_sharded_device: per-shard kernel -> ncclAllGather (32 KB/rank) -> merge kernel on the handle's stream, "
-                               "no host synchronisation; timed with CUDA events on that stream" + ("" if world > 1 else " (1 rank: the all-gather is a device copy)")}
+                 "transport": "peer memory (NVLink stores into every peer's mailbox + sequence flags, one kernel)" if peer else "nccl",
+                 "ms_per_query_batch_nccl": ms_nccl, "transports_agree": same_transports,
+                 "collective": "orbx_db_query_top2_sharded_device: per-shard kernel -> exchange of 32 KB/rank -> merge kernel, all on the handle's stream, "
+                               "no host synchronisation; timed with CUDA events on that stream; exchange = peer-memory mailboxes (default) or ncclAllGather"}
         comm.close(); db.close(); full.close()
         del drows, frows
 

@@ -77,13 +77,13 @@ __global__ void __launch_bounds__(AS_THREADS) k_assoc_partial(AssocParams P)
 }
 
 // lexicographic (error, landmark row) minimum over `nparts` partial results laid out [part][nq]
-__global__ void k_assoc_merge(const orbx_assoc *parts, int nparts, int nq, orbx_assoc *out)
+__global__ void k_assoc_merge(const orbx_assoc *parts, size_t stride, int nparts, int nq, orbx_assoc *out)
 {
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
     orbx_assoc best; best.reproj_error = DBL_MAX; best.landmark = -1; best.distance = 0.f;
     for (int s = 0; s < nparts; s++) {
-        const orbx_assoc p = parts[(size_t)s * nq + qi];
+        const orbx_assoc p = parts[(size_t)s * stride + qi];
         if (p.landmark < 0) continue;
         if (best.landmark < 0 || p.reproj_error < best.reproj_error || (p.reproj_error == best.reproj_error && p.landmark < best.landmark)) best = p;
     }
@@ -119,13 +119,17 @@ int launch_assoc(orbx_handle *h, const uint8_t *d_q, const float *d_qpx, int nq,
         k_assoc_partial<<<grid, AS_THREADS, 0, h->stream>>>(P);
     }
     ProfScope ps(h, ORBX_K_OTHER);
-    k_assoc_merge<<<(nq + 127) / 128, 128, 0, h->stream>>>((const orbx_assoc *)h->d_mpart, (int)split, nq, d_out);
+    k_assoc_merge<<<(nq + 127) / 128, 128, 0, h->stream>>>((const orbx_assoc *)h->d_mpart, (size_t)nq, (int)split, nq, d_out);
     return 0;
 }
 
-void launch_assoc_merge(orbx_handle *h, const orbx_assoc *d_parts, int nparts, int nq, orbx_assoc *d_out)
+void launch_assoc_merge_strided(orbx_handle *h, const orbx_assoc *d_parts, size_t stride, int nparts, int nq, orbx_assoc *d_out)
 {
     if (nq <= 0) return;
     ProfScope ps(h, ORBX_K_OTHER);
-    k_assoc_merge<<<(nq + 127) / 128, 128, 0, h->stream>>>(d_parts, nparts, nq, d_out);
+    k_assoc_merge<<<(nq + 127) / 128, 128, 0, h->stream>>>(d_parts, stride, nparts, nq, d_out);
+}
+void launch_assoc_merge(orbx_handle *h, const orbx_assoc *d_parts, int nparts, int nq, orbx_assoc *d_out)
+{
+    launch_assoc_merge_strided(h, d_parts, (size_t)nq, nparts, nq, d_out);
 }

@@ -108,7 +108,9 @@ __global__ void __launch_bounds__(1024) k_match_epilogue(MatchEpiParams P)
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
     const int nw = blockDim.x >> 5;
-    for (int base = 0; base < nq; base += blockDim.x) {
+    // the modes without compaction (top-2 records, knnMatch pairs) are independent per query: gridDim.y CTAs share a problem's queries
+    // (a 2048-query database lookup merged by ONE CTA took 0.1 ms — a third of the 8-GPU query); the compacting modes keep one CTA
+    for (int base = blockIdx.y * blockDim.x; base < nq; base += blockDim.x * gridDim.y) {
         const int qi = base + threadIdx.x;
         unsigned long long a = ~0ull, b = ~0ull;
         if (qi < nq && nt > 0) {
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(1024) k_match_epilogue(MatchEpiParams P)
         if (threadIdx.x == 0) s_base += s_warp[32];
         __syncthreads();
     }
-    if (threadIdx.x == 0 && P.n_out) {
+    if (threadIdx.x == 0 && blockIdx.y == 0 && P.n_out) {
         if (P.top2) P.n_out[prob] = nq;
         else if (P.k == 2 && P.ratio_num <= 0) P.n_out[prob] = 2 * nq;
         else P.n_out[prob] = s_base;
@@ -222,18 +224,20 @@ int launch_match_core(orbx_handle *h, const uint8_t *d_q, const int32_t *d_nq, i
     E.k = k; E.max_dist = max_dist; E.ratio_num = ratio_num;
     E.out = d_out; E.out_stride = out_stride; E.n_out = d_n_out; E.top2 = d_top2;
     ProfScope ps(h, ORBX_K_MATCH_EPI);
-    orbx_launch_pdl(h, k_match_epilogue, dim3(nproblems), dim3(1024), 0, h->stream, E);
+    const bool independent = d_top2 != nullptr || (k == 2 && ratio_num <= 0);
+    if (independent) orbx_launch_pdl(h, k_match_epilogue, dim3(nproblems, (nq_max + 127) / 128), dim3(128), 0, h->stream, E);
+    else orbx_launch_pdl(h, k_match_epilogue, dim3(nproblems), dim3(1024), 0, h->stream, E);
     return 0;
 }
 
 // ---- merge of per-shard top-2 after the all-gather ----
-__global__ void k_merge_top2(const orbx_top2 *parts, int nshards, int nq, orbx_top2 *out)
+__global__ void k_merge_top2(const orbx_top2 *parts, size_t stride, int nshards, int nq, orbx_top2 *out)
 {
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
     unsigned long long a = ~0ull, b = ~0ull;
     for (int s = 0; s < nshards; s++) {
-        const orbx_top2 p = parts[(size_t)s * nq + qi];
+        const orbx_top2 p = parts[(size_t)s * stride + qi];
         if (p.dist0 != 0xFFFFFFFFu) top2_insert(a, b, ((unsigned long long)p.dist0 << 32) | p.idx0);
         if (p.dist1 != 0xFFFFFFFFu) top2_insert(a, b, ((unsigned long long)p.dist1 << 32) | p.idx1);
     }
@@ -242,11 +246,16 @@ __global__ void k_merge_top2(const orbx_top2 *parts, int nshards, int nq, orbx_t
     r.dist1 = b == ~0ull ? 0xFFFFFFFFu : (uint32_t)(b >> 32); r.idx1 = (uint32_t)b;
     out[qi] = r;
 }
-void launch_merge_top2(orbx_handle *h, const orbx_top2 *d_parts, int nshards, int nq, orbx_top2 *d_out)
+// parts laid out [shard][stride entries]: stride = nq after an all-gather, the mailbox slot size after the peer-memory exchange
+void launch_merge_top2_strided(orbx_handle *h, const orbx_top2 *d_parts, size_t stride, int nshards, int nq, orbx_top2 *d_out)
 {
     if (nq <= 0) return;
-    k_merge_top2<<<(nq + 127) / 128, 128, 0, h->stream>>>(d_parts, nshards, nq, d_out);
+    k_merge_top2<<<(nq + 127) / 128, 128, 0, h->stream>>>(d_parts, stride, nshards, nq, d_out);
     h->launches++;
+}
+void launch_merge_top2(orbx_handle *h, const orbx_top2 *d_parts, int nshards, int nq, orbx_top2 *d_out)
+{
+    launch_merge_top2_strided(h, d_parts, (size_t)nq, nshards, nq, d_out);
 }
 
 // ---- radius query: every (query, row) with distance < max_dist (backend.cpp:1074-1076) ----

@@ -10,6 +10,7 @@
 #include "orbx_internal.h"
 #include <dlfcn.h>
 #include <mutex>
+#include <vector>
 
 namespace {
 typedef struct ncclComm *ncclComm_t;
@@ -50,12 +51,49 @@ bool load_nccl()
 }
 }  // namespace
 
+// Peer-memory exchange (the fused alternative to ncclAllGather for this 32 KB message): every rank owns a MAILBOX
+//     data  [2 parities][nranks][ORBX_P2P_SLOT bytes]      flags [2 parities][nranks] (u32 sequence numbers)
+// mapped into every peer through CUDA IPC.  One kernel per step (k_p2p_push_wait): the rank's per-shard block is stored straight into
+// slot [seq & 1][rank] of EVERY peer's mailbox over NVLink (16-byte stores), a system-scope fence, then the sequence number is published in
+// each peer's flag; the same kernel then waits (acquire loads) until its own mailbox holds all nranks blocks of this sequence, and the
+// merge kernel follows on the stream.  No proxy thread, no host hand-shake, ~10 us instead of NCCL's ~100 us for this size.
+// Two parities suffice: a rank can enter step s only after every peer has published step s-1, i.e. after that peer finished merging s-2.
+#define ORBX_P2P_SLOT (64 * 1024)
+#define ORBX_P2P_MAX_RANKS 16
+struct P2pPeers { uint8_t *data[ORBX_P2P_MAX_RANKS]; uint32_t *flags[ORBX_P2P_MAX_RANKS]; };
+
 struct orbx_comm {
     orbx_handle *h;
     ncclComm_t comm;
     int nranks, rank;
     uint8_t *d_part, *d_all; size_t part_cap, all_cap;       // per-rank block and the gathered [rank][nq] blocks
+    // peer-memory transport
+    int transport;                                            // 0 = peer memory when available (default), 1 = NCCL
+    bool p2p_ok; uint8_t *mbox; P2pPeers peers; void *opened[ORBX_P2P_MAX_RANKS]; uint32_t seq;
 };
+
+__global__ void __launch_bounds__(1024) k_p2p_push_wait(P2pPeers P, const uint4 *__restrict__ src, int n16, int nranks, int rank, uint32_t seq,
+                                                        const uint32_t *my_flags /* this rank's own mailbox flags, parity selected */)
+{
+    const int par = (int)(seq & 1u);
+    const size_t slot = ((size_t)par * nranks + rank) * ORBX_P2P_SLOT;
+    for (int p = 0; p < nranks; p++) {
+        uint4 *dst = reinterpret_cast<uint4 *>(P.data[p] + slot);
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < nranks) {
+        volatile uint32_t *f = P.flags[threadIdx.x] + par * ORBX_P2P_MAX_RANKS + rank;
+        *f = seq;                                                                    // publish: block of `rank` for sequence `seq` is in peer threadIdx.x's mailbox
+    }
+    if ((int)threadIdx.x < nranks) {
+        const volatile uint32_t *f = my_flags + par * ORBX_P2P_MAX_RANKS + threadIdx.x;
+        while (*f != seq) { }                                                        // every peer's block of this sequence has landed here
+    }
+    __threadfence_system();
+    __syncthreads();
+}
 
 #define ORBX_NCCL(h, call) do { int r_ = (call); if (r_ != kNcclSuccess) { \
     (h)->err = std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "NCCL error"); return ORBX_E_CUDA; } } while (0)
@@ -84,7 +122,72 @@ extern "C" orbx_status orbx_comm_create(orbx_handle *h, int32_t nranks, int32_t 
     c->h = h; c->nranks = nranks; c->rank = rank;
     const int r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
     if (r != kNcclSuccess) { h->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); delete c; return ORBX_E_CUDA; }
+    // peer-memory mailboxes: allocate, exchange the CUDA IPC handles with the (just created) communicator, map every peer's mailbox.
+    // Any failure (no peer access, IPC unavailable) leaves the NCCL transport in charge.
+    c->p2p_ok = false; c->seq = 0; c->transport = 0;
+    if (nranks <= ORBX_P2P_MAX_RANKS) {
+        const size_t data_bytes = (size_t)2 * nranks * ORBX_P2P_SLOT, flag_bytes = 2 * ORBX_P2P_MAX_RANKS * sizeof(uint32_t);
+        cudaIpcMemHandle_t mine, *d_handles = nullptr;
+        std::vector<cudaIpcMemHandle_t> all((size_t)nranks);
+        bool ok = cudaMalloc(&c->mbox, data_bytes + flag_bytes) == cudaSuccess && cudaMemset(c->mbox, 0, data_bytes + flag_bytes) == cudaSuccess &&
+                  cudaIpcGetMemHandle(&mine, c->mbox) == cudaSuccess && cudaMalloc(&d_handles, sizeof(cudaIpcMemHandle_t) * (size_t)(nranks + 1)) == cudaSuccess;
+        int all_ok = 0;
+        if (d_handles) {
+            // the all-gather also runs when this rank failed so that the collective stays matched; slot nranks is the send buffer
+            cudaMemcpy(d_handles + nranks, &mine, sizeof(mine), cudaMemcpyHostToDevice);
+            const bool gathered = g_nccl.AllGather(d_handles + nranks, d_handles, sizeof(cudaIpcMemHandle_t), kNcclUint8, c->comm, h->stream) == kNcclSuccess;
+            ok = ok && gathered && cudaStreamSynchronize(h->stream) == cudaSuccess &&
+                 cudaMemcpy(all.data(), d_handles, sizeof(cudaIpcMemHandle_t) * (size_t)nranks, cudaMemcpyDeviceToHost) == cudaSuccess;
+        }
+        if (ok) {
+            for (int p = 0; p < nranks && ok; p++) {
+                void *ptr = c->mbox;
+                if (p != rank) { ok = cudaIpcOpenMemHandle(&ptr, all[(size_t)p], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess; if (ok) c->opened[p] = ptr; }
+                c->peers.data[p] = (uint8_t *)ptr; c->peers.flags[p] = (uint32_t *)((uint8_t *)ptr + data_bytes);
+            }
+        }
+        cudaGetLastError();
+        // everyone must agree, or a rank on the NCCL path would wait for a peer that writes mailboxes: all-gather the verdicts
+        if (d_handles) {
+            int32_t v = ok ? 1 : 0;
+            std::vector<int32_t> vs((size_t)nranks, 0);
+            cudaMemcpy((uint8_t *)d_handles + sizeof(cudaIpcMemHandle_t) * (size_t)nranks, &v, sizeof(v), cudaMemcpyHostToDevice);
+            if (g_nccl.AllGather((uint8_t *)d_handles + sizeof(cudaIpcMemHandle_t) * (size_t)nranks, d_handles, sizeof(int32_t), kNcclUint8, c->comm, h->stream) == kNcclSuccess &&
+                cudaStreamSynchronize(h->stream) == cudaSuccess && cudaMemcpy(vs.data(), d_handles, sizeof(int32_t) * (size_t)nranks, cudaMemcpyDeviceToHost) == cudaSuccess) {
+                all_ok = 1;
+                for (int p = 0; p < nranks; p++) all_ok &= vs[(size_t)p];
+            }
+            cudaFree(d_handles);
+        }
+        c->p2p_ok = all_ok != 0;
+        cudaGetLastError();
+    }
     *out = c;
+    return ORBX_OK;
+}
+extern "C" orbx_status orbx_comm_set_transport(orbx_comm *c, int32_t transport)
+{
+    if (!c || transport < 0 || transport > 1) return ORBX_E_INVALID;
+    c->transport = transport;
+    return ORBX_OK;
+}
+extern "C" int32_t orbx_comm_peer_memory(const orbx_comm *c) { return c && c->p2p_ok ? 1 : 0; }
+
+// exchange `bytes` of every rank's d_part: afterwards `*gathered` points at [rank][bytes-per-rank stride] blocks on this rank
+static orbx_status comm_exchange(orbx_comm *c, size_t bytes, const uint8_t **gathered, size_t *stride)
+{
+    orbx_handle *h = c->h;
+    if (c->p2p_ok && c->transport == 0 && bytes <= ORBX_P2P_SLOT && (bytes & 15) == 0) {
+        c->seq++;
+        const int par = (int)(c->seq & 1u);
+        const size_t data_bytes = (size_t)2 * c->nranks * ORBX_P2P_SLOT;
+        { ProfScope ps(h, ORBX_K_OTHER);
+          k_p2p_push_wait<<<1, 1024, 0, h->stream>>>(c->peers, (const uint4 *)c->d_part, (int)(bytes / 16), c->nranks, c->rank, c->seq, (const uint32_t *)(c->mbox + data_bytes)); }
+        *gathered = c->mbox + (size_t)par * c->nranks * ORBX_P2P_SLOT; *stride = ORBX_P2P_SLOT;
+        return ORBX_OK;
+    }
+    ORBX_NCCL(h, g_nccl.AllGather(c->d_part, c->d_all, bytes, kNcclUint8, c->comm, h->stream));
+    *gathered = c->d_all; *stride = bytes;
     return ORBX_OK;
 }
 extern "C" void orbx_comm_destroy(orbx_comm *c)
@@ -92,6 +195,8 @@ extern "C" void orbx_comm_destroy(orbx_comm *c)
     if (!c) return;
     cudaSetDevice(c->h->device);
     cudaStreamSynchronize(c->h->stream);
+    for (int p = 0; p < c->nranks && p < ORBX_P2P_MAX_RANKS; p++) if (c->opened[p]) cudaIpcCloseMemHandle(c->opened[p]);
+    if (c->mbox) cudaFree(c->mbox);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     if (c->d_part) cudaFree(c->d_part);
     if (c->d_all) cudaFree(c->d_all);
@@ -128,8 +233,9 @@ extern "C" orbx_status orbx_db_query_top2_sharded_device(orbx_db *db, orbx_comm 
     orbx_status st = comm_scratch(c, bytes);
     if (st != ORBX_OK) return st;
     if ((st = orbx_db_query_top2_device(db, d_query, nq, (orbx_top2 *)c->d_part)) != ORBX_OK) return st;
-    ORBX_NCCL(h, g_nccl.AllGather(c->d_part, c->d_all, bytes, kNcclUint8, c->comm, h->stream));
-    launch_merge_top2(h, (const orbx_top2 *)c->d_all, c->nranks, nq, d_out);
+    const uint8_t *g; size_t stride;
+    if ((st = comm_exchange(c, bytes, &g, &stride)) != ORBX_OK) return st;
+    launch_merge_top2_strided(h, (const orbx_top2 *)g, stride / sizeof(orbx_top2), c->nranks, nq, d_out);
     ORBX_CUDA(h, cudaGetLastError());
     return ORBX_OK;
 }
@@ -147,8 +253,9 @@ extern "C" orbx_status orbx_db_associate_sharded_device(orbx_db *db, orbx_comm *
     orbx_status st = comm_scratch(c, bytes);
     if (st != ORBX_OK) return st;
     if ((st = orbx_db_associate_device(db, d_query, d_query_px, nq, pose, max_desc_dist, max_reproj_err, (orbx_assoc *)c->d_part)) != ORBX_OK) return st;
-    ORBX_NCCL(h, g_nccl.AllGather(c->d_part, c->d_all, bytes, kNcclUint8, c->comm, h->stream));
-    launch_assoc_merge(h, (const orbx_assoc *)c->d_all, c->nranks, nq, d_out);
+    const uint8_t *g; size_t stride;
+    if ((st = comm_exchange(c, bytes, &g, &stride)) != ORBX_OK) return st;
+    launch_assoc_merge_strided(h, (const orbx_assoc *)g, stride / sizeof(orbx_assoc), c->nranks, nq, d_out);
     ORBX_CUDA(h, cudaGetLastError());
     return ORBX_OK;
 }

@@ -253,6 +253,7 @@ void launch_match_radius(orbx_handle *h, const uint8_t *d_q, int nq, const uint8
 int  launch_assoc(orbx_handle *h, const uint8_t *d_q, const float *d_qpx, int nq, const uint8_t *d_t, const float *d_pos, int nt, uint32_t row_base,
                   const orbx_pose *pose, float max_dist, double max_err, orbx_assoc *d_out);
 void launch_assoc_merge(orbx_handle *h, const orbx_assoc *d_parts, int nparts, int nq, orbx_assoc *d_out);
+void launch_assoc_merge_strided(orbx_handle *h, const orbx_assoc *d_parts, size_t stride, int nparts, int nq, orbx_assoc *d_out);
 void launch_pack_keyframe(orbx_handle *h, int nframes, const orbx_keypoint *d_kps, const uint8_t *d_desc, const int32_t *d_counts, int cap_in,
                           const uint16_t *d_depth, size_t dstep, size_t dfstride, int dw, int dh, const orbx_kfparams *K,
                           orbx_kfrecord *d_out, int32_t *d_nout, int cap_out);
@@ -260,6 +261,7 @@ void launch_harris(orbx_handle *h, const uint8_t *img, size_t step, int w, int h
 void launch_bgr2gray(orbx_handle *h, const uint8_t *d_bgr, size_t sstep, size_t sfstride, uint8_t *d_gray, size_t dstep, size_t dfstride,
                      int w, int hgt, int nframes, cudaStream_t st);
 void launch_merge_top2(orbx_handle *h, const orbx_top2 *d_parts, int nshards, int nq, orbx_top2 *d_out);
+void launch_merge_top2_strided(orbx_handle *h, const orbx_top2 *d_parts, size_t stride, int nshards, int nq, orbx_top2 *d_out);
 void launch_synth_gray(orbx_handle *h, uint32_t seed, int first, int n, int w, int hh, uint8_t *d, size_t step, size_t fstride);
 void launch_synth_depth(orbx_handle *h, uint32_t seed, int first, int n, int w, int hh, uint16_t *d, size_t step, size_t fstride);
 void launch_synth_desc(orbx_handle *h, uint32_t seed, uint64_t first_row, int64_t nrows, uint8_t *d);

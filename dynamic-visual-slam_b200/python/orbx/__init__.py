@@ -137,6 +137,8 @@ def load():
         "orbx_comm_create": (i32, [vp, i32, i32, vp, vp]),
         "orbx_comm_destroy": (None, [vp]),
         "orbx_comm_ranks": (i32, [vp]),
+        "orbx_comm_set_transport": (i32, [vp, i32]),
+        "orbx_comm_peer_memory": (i32, [vp]),
         "orbx_comm_rank": (i32, [vp]),
         "orbx_db_query_top2_sharded_device": (i32, [vp, vp, vp, i32, vp]),
         "orbx_db_associate_sharded_device": (i32, [vp, vp, vp, vp, i32, vp, f32, ct.c_double, vp]),
@@ -593,6 +595,14 @@ class Comm:
         self._c = ct.c_void_p()
         raw = (ct.c_uint8 * 128).from_buffer_copy(unique_id)
         extractor._check(self.L.orbx_comm_create(extractor.handle, self.nranks, self.rank, raw, ct.byref(self._c)))
+
+    @property
+    def peer_memory(self):
+        """True when the mailboxes of all ranks are mapped into each other (CUDA IPC over NVLink)"""
+        return bool(self.L.orbx_comm_peer_memory(self._c))
+
+    def set_transport(self, nccl):
+        self.ex._check(self.L.orbx_comm_set_transport(self._c, 1 if nccl else 0))
 
     def close(self):
         if self._c.value:

@@ -298,6 +298,11 @@ orbx_status orbx_comm_create(orbx_handle *h, int32_t nranks, int32_t rank, const
 void        orbx_comm_destroy(orbx_comm *c);
 int32_t     orbx_comm_ranks(const orbx_comm *c);
 int32_t     orbx_comm_rank(const orbx_comm *c);
+/* Transport of the exchange step.  0 (default): peer memory — every rank stores its block straight into a mailbox in each peer's HBM
+ * over NVLink (CUDA IPC mappings set up by orbx_comm_create) and waits on sequence flags inside one small kernel; used when all ranks
+ * could map each other (orbx_comm_peer_memory() == 1) and the block fits the 64 KB slot, else NCCL.  1: always ncclAllGather.  */
+orbx_status orbx_comm_set_transport(orbx_comm *c, int32_t transport);
+int32_t     orbx_comm_peer_memory(const orbx_comm *c);
 orbx_status orbx_db_query_top2_sharded_device(orbx_db *db, orbx_comm *c, const uint8_t *d_query, int32_t nq, orbx_top2 *d_out);
 orbx_status orbx_db_associate_sharded_device(orbx_db *db, orbx_comm *c, const uint8_t *d_query, const float *d_query_px, int32_t nq,
                                              const orbx_pose *pose, float max_desc_dist, double max_reproj_err, orbx_assoc *d_out);
