@@ -262,6 +262,7 @@ def main():
     ap.add_argument("--no-pdl", action="store_true", help="plain stream order instead of programmatic dependent launch (ORBX_OPT_PDL = 0)")
     ap.add_argument("--fast-ctas", type=int, default=0, help="resident FAST warps per SM in the overlapped schedule (0 = library default)")
     ap.add_argument("--overlap", action="store_true", help="two staggered half-batches on two streams (ORBX_OPT_OVERLAP = 1; measured slower than one chain)")
+    ap.add_argument("--popc-match", action="store_true", help="the LOP3/POPC matcher instead of the int8 tensor-core GEMM (ORBX_OPT_MATCH_MMA = 0)")
     ap.add_argument("--host-chunk", type=int, default=0, help="frames per pipeline chunk of the host-buffer call (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-assoc", action="store_true", help="skip the landmark-association leg")
@@ -300,6 +301,8 @@ def main():
         ex.set_pdl(False)
     if args.overlap:
         ex.set_overlap(True)
+    if args.popc_match:
+        ex.set_match_mma(False)
     L, hnd = ex.L, ex.handle
     stream = torch.cuda.ExternalStream(ex.stream, device=dev)
 
@@ -415,10 +418,14 @@ def main():
         pairs = float((nkp[1:].astype(np.float64) * nkp[:-1]).sum() + float(nkp[0]) * float(nkp[-1]))      # frame f vs f-1; frame 0 vs the carried last frame
         popc = ex.bench_popc()
         t_s = kernels["k_match_partial"]["ms_per_step"] * 1e-3
-        match_roofline = {"kernel": "k_match_partial", "bound": "integer issue (ALU pipe; POPC count shown for reference)", "pairs_per_step": pairs,
-                          "popc_per_pair": POPC_PER_PAIR, "achieved": POPC_PER_PAIR * pairs / t_s, "peak": popc, "unit": "POPC/s",
-                          "frac": POPC_PER_PAIR * pairs / t_s / popc if popc > 0 else None, "peak_source": "measured (orbx_bench_popc)",
-                          "gpairs_per_s": pairs / t_s / 1e9}
+        match_roofline = {"kernel": "k_match_mma" if not args.popc_match else "k_match_partial",
+                          "engine": "int8 tensor-core GEMM (mma.sync m16n8k32.u8 on descriptors unpacked to 0/1 bytes, d = |q| + |t| - 2 q.t)" if not args.popc_match
+                                    else "LOP3/POPC (5 POPC per pair after carry-save adders)",
+                          "bound": "tensor pipe (legacy mma.sync int8: ncu 58 % busy at 1.28 T pairs/s)" if not args.popc_match else "integer issue (ALU pipe)",
+                          "pairs_per_step": pairs, "gpairs_per_s": pairs / t_s / 1e9,
+                          "popc_equivalent": {"popc_per_pair": POPC_PER_PAIR, "achieved": POPC_PER_PAIR * pairs / t_s, "peak": popc, "unit": "POPC/s",
+                                              "frac": POPC_PER_PAIR * pairs / t_s / popc if popc > 0 else None, "peak_source": "measured (orbx_bench_popc)",
+                                              "note": "what the POPC kernel would need to sustain for the same pairs/s"}}
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     if args.kernels_only:
         clocks = sampler.stop()
@@ -592,8 +599,8 @@ def main():
                  "query_set": "%d database rows i*512 with 0..40 bit flips + %d random rows" % (n_true, NQ - n_true),
                  "nn_below_50": int((res[:, 0] < 50).sum()), "nn_from_other_shards": int((res[:, 1] >= rows_r).sum()) if world > 1 else 0,
                  "mismatches_vs_unsharded": mism, "cpu_check": cpu_check,
-                 "kernel_ms": kms, "popc_per_s_measured_peak": popc,
-                 "popc_frac": (POPC_PER_PAIR * NQ * rows_r / (kms * 1e-3)) / popc if popc > 0 and kms > 0 else None,
+                 "kernel_ms": kms, "kernel_gpairs_per_s": NQ * rows_r / (kms * 1e-3) / 1e9 if kms > 0 else None,
+                 "engine": "k_match_mma (int8 tensor-core GEMM)" if not args.popc_match else "k_match_partial (POPC)", "popc_per_s_measured_peak": popc,
                  "transport": "peer memory (NVLink stores into every peer's mailbox + sequence flags, one kernel)" if peer else "nccl",
                  "ms_per_query_batch_nccl": ms_nccl, "transports_agree": same_transports,
                  "collective": "orbx_db_query_top2_sharded_device: per-shard kernel -> exchange of 32 KB/rank -> merge kernel, all on the handle's stream, "

@@ -76,6 +76,136 @@ template <bool TOP2> __global__ void __launch_bounds__(MT_THREADS) k_match_parti
     }
 }
 
+// ---- tensor-core variant: Hamming distance as an exact integer GEMM ----
+// popc(q ^ t) = popc(q) + popc(t) - 2 popc(q & t), and popc(q & t) is the dot product of the two descriptors read as 256 0/1 integers.
+// sm_100a has no native binary MMA (ptxas emulates mma.sync ... b1.xor.popc with ~150 instructions around eight IMMA.16832.U8.U8), but the int8
+// path itself is usable: this kernel runs the 2048 x 1M association at 1.28 T pairs/s against 0.81 T pairs/s of k_match_partial (1.6x) and the
+// frame matcher at 0.090 ms against 0.129 ms per 128-frame step, bit-identical.  (tools/imma_probe.cu over-estimated the pipe: operands that never
+// change let it report 4.98 T pairs/s; the real kernel shows the tensor pipe 58 % busy at 0.28 IMMA/clk/SM.)  Any fixed permutation of the 256 bit positions gives the same dot product, so the operands are unpacked the cheapest way:
+// (w >> s) & 0x01010101 turns bits {s, s+8, s+16, s+24} of a descriptor word into one register of four 0/1 bytes.  k-step ks of the MMA takes
+// word ks; thread t of a quad supplies shift t for k = 4t..4t+3 and shift t+4 for k = 16+4t..16+4t+3, on the query (A) and the train (B) side alike.
+//   * a warp owns 16 queries: A fragments (8 k-steps x 4 registers) stay in registers for the whole kernel;
+//   * the CTA (8 warps = 128 queries, the same tiling as k_match_partial) stages 64 train rows at a time: each thread unpacks one (row group,
+//     lane) slice once, in fragment order, into shared memory (double buffered, one barrier per chunk), together with the packed key base
+//     (popc(t) << 22 | local row);  every warp then reads its B registers with four LDS.128 per 8-row tile;
+//   * per 16 x 8 tile: 8 IMMA, then per pair ONE integer multiply-add forms the packed key (distance << 22 | row) = base + (popc(q) << 22) - dot << 23
+//     and the usual min/max keeps the best (two) per query; rows past the end carry distance 511 and never win.
+// Output = k_match_partial's partial top-2 layout: the epilogue and every caller are unchanged, results are bit-identical.
+#define MM_CHUNK 64
+#define MM_DEAD (511u << MT_KEY_SHIFT)
+__device__ __forceinline__ void imma_16832(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <bool TOP2> __global__ void __launch_bounds__(256) k_match_mma(MatchParams P)
+{
+    __shared__ uint4 s_b[2][MM_CHUNK / 8][4][32];                 // [buffer][8-row group][16-byte piece][lane]: 32 KB, conflict-free LDS.128 / STS.128
+    __shared__ uint32_t s_tk[2][MM_CHUNK];
+    ORBX_PDL_ENTRY();
+    const int prob = blockIdx.z;
+    const int qs = P.qsel ? P.qsel[prob] : prob, ts = P.tsel ? P.tsel[prob] : prob;
+    const int nq = P.nq_arr ? P.nq_arr[qs] : P.nq_imm;
+    const int nt = P.nt_arr ? P.nt_arr[ts] : P.nt_imm;
+    if (blockIdx.x * MT_THREADS >= nq) return;
+    const int rps = P.nt_arr ? ((((nt + P.nsplit - 1) / P.nsplit) + 7) & ~7) : P.rows_per_split;
+    const int r0 = blockIdx.y * rps;
+    const int r1 = min(nt, r0 + rps);
+    const uint8_t *qbase = P.q + (size_t)qs * P.q_stride;
+    const uint4 *tbase = reinterpret_cast<const uint4 *>(P.t + (size_t)ts * P.t_stride);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int qa = blockIdx.x * MT_THREADS + warp * 16 + g, qb = qa + 8;            // the two query rows whose results this quad holds
+    const uint32_t M1 = 0x01010101u;
+    uint32_t a[8][4], pqa, pqb;
+    {
+        const uint4 *pa = reinterpret_cast<const uint4 *>(qbase + (size_t)(qa < nq ? qa : 0) * ORBX_DESC_BYTES);
+        const uint4 *pb = reinterpret_cast<const uint4 *>(qbase + (size_t)(qb < nq ? qb : 0) * ORBX_DESC_BYTES);
+        const uint4 x0 = __ldg(pa), x1 = __ldg(pa + 1), y0 = __ldg(pb), y1 = __ldg(pb + 1);
+        const uint32_t wa[8] = { x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w }, wb[8] = { y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w };
+        int ca = 0, cb = 0;
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) {
+            a[ks][0] = (wa[ks] >> t) & M1; a[ks][1] = (wb[ks] >> t) & M1; a[ks][2] = (wa[ks] >> (t + 4)) & M1; a[ks][3] = (wb[ks] >> (t + 4)) & M1;
+            ca += __popc(wa[ks]); cb += __popc(wb[ks]);
+        }
+        pqa = (uint32_t)ca << MT_KEY_SHIFT; pqb = (uint32_t)cb << MT_KEY_SHIFT;
+    }
+    uint32_t m0a = MT_INF, m1a = MT_INF, m0b = MT_INF, m1b = MT_INF;
+    const int nrows = max(0, r1 - r0), nchunks = (nrows + MM_CHUNK - 1) / MM_CHUNK;
+    // staging of chunk c into buffer c & 1: this thread owns the slice of (group G, lane L) = threadIdx.x.  The two global loads are issued
+    // BEFORE the tiles of the current chunk are computed and unpacked AFTER them, so their latency hides behind the MMAs.
+    const int G_ = threadIdx.x >> 5, L_ = threadIdx.x & 31;
+    auto fetch = [&](int c, uint4 &x0, uint4 &x1) {
+        const int lrow = c * MM_CHUNK + G_ * 8 + (L_ >> 2);
+        x0 = make_uint4(0u, 0u, 0u, 0u); x1 = x0;
+        if (lrow < nrows) { const uint4 *p = tbase + (size_t)(r0 + lrow) * 2; x0 = __ldg(p); x1 = __ldg(p + 1); }
+    };
+    auto stage = [&](int c, const uint4 x0, const uint4 x1) {
+        const int G = G_, L = L_, lrow = c * MM_CHUNK + G * 8 + (L >> 2), tt = L & 3;
+        const bool valid = lrow < nrows;
+        const uint32_t w[8] = { x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w };
+        uint32_t r[16];
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) { r[2 * ks] = (w[ks] >> tt) & M1; r[2 * ks + 1] = (w[ks] >> (tt + 4)) & M1; }
+        s_b[c & 1][G][0][L] = make_uint4(r[0], r[1], r[2], r[3]); s_b[c & 1][G][1][L] = make_uint4(r[4], r[5], r[6], r[7]);
+        s_b[c & 1][G][2][L] = make_uint4(r[8], r[9], r[10], r[11]); s_b[c & 1][G][3][L] = make_uint4(r[12], r[13], r[14], r[15]);
+        if (tt == 0) {
+            int pc = 0;
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++) pc += __popc(w[ks]);
+            s_tk[c & 1][G * 8 + (L >> 2)] = valid ? (((uint32_t)pc << MT_KEY_SHIFT) | (uint32_t)lrow) : (MM_DEAD | (uint32_t)(lrow & ((1 << MT_KEY_SHIFT) - 1)));
+        }
+    };
+    uint4 nx0, nx1;
+    if (nchunks > 0) { fetch(0, nx0, nx1); stage(0, nx0, nx1); }
+    __syncthreads();
+    for (int c = 0; c < nchunks; c++) {
+        if (c + 1 < nchunks) fetch(c + 1, nx0, nx1);            // in flight during this chunk's tiles
+        const int groups = min(MM_CHUNK / 8, (nrows - c * MM_CHUNK + 7) >> 3);
+        for (int G = 0; G < groups; G++) {
+            const uint4 b0 = s_b[c & 1][G][0][lane], b1 = s_b[c & 1][G][1][lane], b2 = s_b[c & 1][G][2][lane], b3 = s_b[c & 1][G][3][lane];
+            // one chain of eight MMAs: two chains of four measured no faster (1.76 vs 1.68 ms on 2048 x 1M) — ncu shows the tensor pipe itself
+            // 58 % busy at 0.28 IMMA/clk/SM: legacy mma.sync int8 peaks near 0.48 IMMA/clk/SM (~1.1 POP/s) on B200, a quarter of tcgen05's rate
+            int acc[4] = { 0, 0, 0, 0 };
+            imma_16832(acc, a[0], b0.x, b0.y); imma_16832(acc, a[1], b0.z, b0.w);
+            imma_16832(acc, a[2], b1.x, b1.y); imma_16832(acc, a[3], b1.z, b1.w);
+            imma_16832(acc, a[4], b2.x, b2.y); imma_16832(acc, a[5], b2.z, b2.w);
+            imma_16832(acc, a[6], b3.x, b3.y); imma_16832(acc, a[7], b3.z, b3.w);
+            const uint2 tk = *reinterpret_cast<const uint2 *>(&s_tk[c & 1][G * 8 + 2 * t]);      // columns 2t and 2t + 1 of this tile
+            const uint32_t two23 = 1u << (MT_KEY_SHIFT + 1);
+            const uint32_t k00 = pqa + tk.x - (uint32_t)acc[0] * two23, k01 = pqa + tk.y - (uint32_t)acc[1] * two23;
+            const uint32_t k10 = pqb + tk.x - (uint32_t)acc[2] * two23, k11 = pqb + tk.y - (uint32_t)acc[3] * two23;
+            if (TOP2) { m1a = min(m1a, max(m0a, k00)); m0a = min(m0a, k00); m1a = min(m1a, max(m0a, k01)); m0a = min(m0a, k01);
+                        m1b = min(m1b, max(m0b, k10)); m0b = min(m0b, k10); m1b = min(m1b, max(m0b, k11)); m0b = min(m0b, k11); }
+            else { m0a = min(m0a, min(k00, k01)); m0b = min(m0b, min(k10, k11)); }
+        }
+        if (c + 1 < nchunks) stage(c + 1, nx0, nx1);            // the other buffer: everyone left it at the barrier that ended chunk c - 1
+        __syncthreads();
+    }
+    // the four lanes of a quad hold different columns of the same two query rows: merge their (best, second best)
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+        const uint32_t x0 = __shfl_xor_sync(0xffffffffu, m0a, o), x1 = __shfl_xor_sync(0xffffffffu, m1a, o);
+        const uint32_t y0 = __shfl_xor_sync(0xffffffffu, m0b, o), y1 = __shfl_xor_sync(0xffffffffu, m1b, o);
+        m1a = min(max(m0a, x0), min(m1a, x1)); m0a = min(m0a, x0);
+        m1b = min(max(m0b, y0), min(m1b, y1)); m0b = min(m0b, y0);
+    }
+    if (t == 0) {
+        const unsigned long long gb = (unsigned long long)P.row_base + (unsigned long long)r0;
+        const uint32_t lowmask = (1u << MT_KEY_SHIFT) - 1;
+        if (qa < nq) {
+            unsigned long long *o = P.part + (((size_t)prob * P.nsplit + blockIdx.y) * P.nq_max + qa) * 2;
+            o[0] = m0a >= MM_DEAD ? ~0ull : (((unsigned long long)(m0a >> MT_KEY_SHIFT) << 32) | (gb + (m0a & lowmask)));
+            o[1] = (!TOP2 || m1a >= MM_DEAD) ? ~0ull : (((unsigned long long)(m1a >> MT_KEY_SHIFT) << 32) | (gb + (m1a & lowmask)));
+        }
+        if (qb < nq) {
+            unsigned long long *o = P.part + (((size_t)prob * P.nsplit + blockIdx.y) * P.nq_max + qb) * 2;
+            o[0] = m0b >= MM_DEAD ? ~0ull : (((unsigned long long)(m0b >> MT_KEY_SHIFT) << 32) | (gb + (m0b & lowmask)));
+            o[1] = (!TOP2 || m1b >= MM_DEAD) ? ~0ull : (((unsigned long long)(m1b >> MT_KEY_SHIFT) << 32) | (gb + (m1b & lowmask)));
+        }
+    }
+}
+
 struct MatchEpiParams {
     const unsigned long long *part; int nq_max, nsplit;
     const int32_t *nq_arr; int nq_imm; const int32_t *nt_arr; int nt_imm;
@@ -214,7 +344,10 @@ int launch_match_core(orbx_handle *h, const uint8_t *d_q, const int32_t *d_nq, i
         // every slot the epilogue reads (qi < nq, all splits) is written by the partial kernel; splits that
         // start beyond a problem's own nt write the "empty" key
         ProfScope ps(h, ORBX_K_MATCH);
-        if (k == 2 || d_top2) orbx_launch_pdl(h, k_match_partial<true>, grid, dim3(MT_THREADS), 0, h->stream, P);
+        if (h->opt_match_mma) {                                    // Hamming as an int8 tensor-core GEMM (k_match_mma): 8 warps x 16 queries per CTA
+            if (k == 2 || d_top2) orbx_launch_pdl(h, k_match_mma<true>, grid, dim3(256), 0, h->stream, P);
+            else orbx_launch_pdl(h, k_match_mma<false>, grid, dim3(256), 0, h->stream, P);
+        } else if (k == 2 || d_top2) orbx_launch_pdl(h, k_match_partial<true>, grid, dim3(MT_THREADS), 0, h->stream, P);
         else orbx_launch_pdl(h, k_match_partial<false>, grid, dim3(MT_THREADS), 0, h->stream, P);
     }
     MatchEpiParams E;

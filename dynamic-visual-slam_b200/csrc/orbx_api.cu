@@ -297,7 +297,7 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     if (p.device < 0 || p.device >= ndev) { g_create_err = "device ordinal out of range"; return ORBX_E_INVALID; }
     orbx_handle *h = new orbx_handle();
     h->prm = p; h->device = p.device; h->launches = 0; h->geo.width = -1; h->geo.height = -1;
-    h->prof_on = 0; h->prof_n = 0; h->prev_valid = 0; h->opt_fused_blur = 1; h->blur_valid = false; h->opt_pdl = 1; h->opt_overlap = 0; h->in_overlap = false; h->ev_after_pyramid = nullptr;
+    h->prof_on = 0; h->prof_n = 0; h->prev_valid = 0; h->opt_fused_blur = 1; h->blur_valid = false; h->opt_pdl = 1; h->opt_overlap = 0; h->opt_match_mma = 1; h->in_overlap = false; h->ev_after_pyramid = nullptr;
     memset(&h->alt, 0, sizeof(h->alt));
     memset(h->prof_ms, 0, sizeof(h->prof_ms)); memset(h->prof_cnt, 0, sizeof(h->prof_cnt));
     CREATE_CUDA(cudaSetDevice(p.device));
@@ -427,6 +427,7 @@ extern "C" orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t v
     if (option == ORBX_OPT_FUSED_BLUR) { h->opt_fused_blur = value ? 1 : 0; return ORBX_OK; }
     if (option == ORBX_OPT_PDL) { h->opt_pdl = value ? 1 : 0; return ORBX_OK; }
     if (option == ORBX_OPT_OVERLAP) { h->opt_overlap = value ? 1 : 0; return ORBX_OK; }
+    if (option == ORBX_OPT_MATCH_MMA) { h->opt_match_mma = value ? 1 : 0; return ORBX_OK; }
     h->err = "unknown option"; return ORBX_E_INVALID;
 }
 extern "C" void *orbx_stream(orbx_handle *h) { return h ? (void *)h->stream : nullptr; }

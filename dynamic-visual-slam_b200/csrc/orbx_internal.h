@@ -93,6 +93,7 @@ struct orbx_handle {
     int opt_fused_blur;          // 1 (default): the Gaussian is evaluated inside the descriptor kernel, no blurred pyramid is written
     bool blur_valid;             // d_blur holds the blurred levels of the last batch
     int opt_fast_ctas;           // FAST warps per SM in the overlapped schedule (0 = as many as fit)
+    int opt_match_mma;           // 1 (default): Hamming matching as an int8 tensor-core GEMM (k_match_mma); 0: the POPC kernel (k_match_partial)
     int opt_overlap;             // 1 (default): batches of >= 32 frames run as two half-batches on two streams (OrbxLane)
     OrbxLane alt;                // the second lane's scratch (allocated on first use)
     bool in_overlap;             // a half-batch run is being enqueued (FAST caps its resident warps so the other lane's kernels fit beside it)

@@ -256,6 +256,10 @@ class ORBextractor:
         """ORBX_OPT_OVERLAP: batches of >= 32 frames as two staggered half-batches on two streams (default off: measured slower)."""
         self._check(self.L.orbx_set_option(self._h, 5, 1 if on else 0))
 
+    def set_match_mma(self, on=True):
+        """ORBX_OPT_MATCH_MMA: Hamming matching as an int8 tensor-core GEMM (default on) or the POPC kernel."""
+        self._check(self.L.orbx_set_option(self._h, 6, 1 if on else 0))
+
     def set_fast_ctas(self, n):
         """ORBX_OPT_FAST_CTAS: resident FAST warps per SM in the overlapped schedule (0 = as many as fit)."""
         self._check(self.L.orbx_set_option(self._h, 2, int(n)))

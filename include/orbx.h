@@ -386,6 +386,10 @@ orbx_status orbx_synth_descriptors_device(orbx_handle *h, uint32_t seed, uint64_
  * chain.  MEASURED SLOWER on B200 (128 x 1280x720: 1.190 ms one chain, 1.206-1.31 ms overlapped, profiles/r02d_overlap.log): every
  * kernel of the step is instruction-issue bound, so co-resident kernels only split the issue slots and the half-batches add tails. */
 #define ORBX_OPT_OVERLAP 5
+/* ORBX_OPT_MATCH_MMA: 1 (default) = the brute-force matcher and the landmark-database top-2 query compute Hamming distances as an exact int8
+ * tensor-core GEMM (popc(q ^ t) = popc(q) + popc(t) - 2 q.t on descriptors unpacked to 0/1 bytes, mma.sync m16n8k32.u8); 0 = the LOP3 / POPC
+ * kernel.  Same results bit for bit. */
+#define ORBX_OPT_MATCH_MMA 6
 orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t value);
 
 /* ---- utilities ---- */
