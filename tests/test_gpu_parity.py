@@ -180,6 +180,32 @@ def test_match_bit_exact(ex, oracle):
     assert np.array_equal(good.view(np.uint8), ko[keep, 0].view(np.uint8))
 
 
+def test_both_match_engines_ragged_sizes(built, oracle):
+    """ORBX_OPT_MATCH_MMA: the int8 tensor-core GEMM matcher (default) and the LOP3/POPC matcher against BFMatcher's restatement on ragged
+    problem sizes (fewer rows than one 8-row MMA tile, sizes straddling the 16-query / 64-row staging units, duplicates -> lowest-index ties)"""
+    import orbx
+    rng = np.random.default_rng(11)
+    e = orbx.ORBextractor(max_width=320, max_height=240)
+    try:
+        for nq, nt in [(1, 1), (1, 7), (3, 9), (16, 8), (17, 63), (33, 65), (129, 130), (500, 1000), (1000, 777), (64, 4096)]:
+            q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+            t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+            if nt > 4:
+                t[nt - 1] = t[1]; q[0] = t[1]                       # exact duplicate at both ends of the train set: tie at distance 0
+                t[nt // 2] = t[1]
+            want1, want2 = oracle.match(q, t), oracle.knn2(q, t)
+            for mma in (True, False):
+                e.set_match_mma(mma)
+                m = e.match(q, t, k=1)
+                assert np.array_equal(m.view(np.uint8), want1.view(np.uint8)), (nq, nt, mma)
+                k2 = e.match(q, t, k=2).reshape(-1, 2)
+                assert np.array_equal(k2["trainIdx"], want2["trainIdx"]) and np.array_equal(k2["distance"], want2["distance"]), (nq, nt, mma)
+                good = e.match(q, t, k=1, max_dist=110.0)
+                assert np.array_equal(good.view(np.uint8), want1[want1["distance"] < 110.0].view(np.uint8)), (nq, nt, mma)
+    finally:
+        e.close()
+
+
 def test_depth_filter(ex, oracle):
     w, h = 1280, 720
     g = oracle.synth_gray(9, 2, w, h)
