@@ -346,7 +346,7 @@ int launch_match_core(orbx_handle *h, const uint8_t *d_q, const int32_t *d_nq, i
         ProfScope ps(h, ORBX_K_MATCH);
         // Hamming as an int8 tensor-core GEMM (k_match_mma, 8 warps x 16 queries per CTA) once there is enough work to amortise its staging: a single
         // frame pair (the latency path, ~1 M pairs) stays on the POPC kernel, which measured 10 us less there
-        if (h->opt_match_mma && (double)nproblems * nq_max * nt_max >= 8e6) {
+        if (h->opt_match_mma == 2 || (h->opt_match_mma && (double)nproblems * nq_max * nt_max >= 8e6)) {
             if (k == 2 || d_top2) orbx_launch_pdl(h, k_match_mma<true>, grid, dim3(256), 0, h->stream, P);
             else orbx_launch_pdl(h, k_match_mma<false>, grid, dim3(256), 0, h->stream, P);
         } else if (k == 2 || d_top2) orbx_launch_pdl(h, k_match_partial<true>, grid, dim3(MT_THREADS), 0, h->stream, P);

@@ -427,7 +427,7 @@ extern "C" orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t v
     if (option == ORBX_OPT_FUSED_BLUR) { h->opt_fused_blur = value ? 1 : 0; return ORBX_OK; }
     if (option == ORBX_OPT_PDL) { h->opt_pdl = value ? 1 : 0; return ORBX_OK; }
     if (option == ORBX_OPT_OVERLAP) { h->opt_overlap = value ? 1 : 0; return ORBX_OK; }
-    if (option == ORBX_OPT_MATCH_MMA) { h->opt_match_mma = value ? 1 : 0; return ORBX_OK; }
+    if (option == ORBX_OPT_MATCH_MMA) { h->opt_match_mma = value < 0 ? 0 : (value > 2 ? 2 : value); return ORBX_OK; }
     h->err = "unknown option"; return ORBX_E_INVALID;
 }
 extern "C" void *orbx_stream(orbx_handle *h) { return h ? (void *)h->stream : nullptr; }

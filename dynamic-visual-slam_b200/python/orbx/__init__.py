@@ -257,8 +257,8 @@ class ORBextractor:
         self._check(self.L.orbx_set_option(self._h, 5, 1 if on else 0))
 
     def set_match_mma(self, on=True):
-        """ORBX_OPT_MATCH_MMA: Hamming matching as an int8 tensor-core GEMM (default on) or the POPC kernel."""
-        self._check(self.L.orbx_set_option(self._h, 6, 1 if on else 0))
+        """ORBX_OPT_MATCH_MMA: 1 = int8 tensor-core GEMM for calls of >= 8 M pairs (default), 2 = always, 0 / False = always the POPC kernel."""
+        self._check(self.L.orbx_set_option(self._h, 6, int(on)))
 
     def set_fast_ctas(self, n):
         """ORBX_OPT_FAST_CTAS: resident FAST warps per SM in the overlapped schedule (0 = as many as fit)."""

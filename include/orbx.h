@@ -387,7 +387,8 @@ orbx_status orbx_synth_descriptors_device(orbx_handle *h, uint32_t seed, uint64_
  * kernel of the step is instruction-issue bound, so co-resident kernels only split the issue slots and the half-batches add tails. */
 #define ORBX_OPT_OVERLAP 5
 /* ORBX_OPT_MATCH_MMA: 1 (default) = the brute-force matcher and the landmark-database top-2 query compute Hamming distances as an exact int8
- * tensor-core GEMM (popc(q ^ t) = popc(q) + popc(t) - 2 q.t on descriptors unpacked to 0/1 bytes, mma.sync m16n8k32.u8); 0 = the LOP3 / POPC
+ * tensor-core GEMM (popc(q ^ t) = popc(q) + popc(t) - 2 q.t on descriptors unpacked to 0/1 bytes, mma.sync m16n8k32.u8) when a call holds at
+ * least 8 M descriptor pairs (a single frame pair stays on the POPC kernel: less fixed latency); 2 = always the GEMM; 0 = always the LOP3 / POPC
  * kernel.  Same results bit for bit. */
 #define ORBX_OPT_MATCH_MMA 6
 orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t value);
