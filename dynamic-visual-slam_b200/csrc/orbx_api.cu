@@ -1534,6 +1534,34 @@ extern "C" orbx_status orbx_fmat_score(orbx_handle *h, const float *pts1, const 
     return ORBX_OK;
 }
 
+extern "C" orbx_status orbx_fmat_ransac(orbx_handle *h, const float *pts1, const float *pts2, int32_t n, int32_t nh, double threshold, uint32_t seed,
+                                        double *F_out, uint8_t *best_mask, int32_t *n_inliers)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    if (n < 8 || nh < 1 || !pts1 || !pts2 || !F_out || !best_mask || !(threshold >= 0)) { h->err = "bad fundamental-matrix RANSAC arguments (n >= 8, nh >= 1)"; return ORBX_E_INVALID; }
+    if (h->pending[0].active || h->pending[1].active) { h->err = "an asynchronous batch is outstanding: call orbx_batch_wait first"; return ORBX_E_INVALID; }
+    orbx_status st;
+    const size_t bp = align_up((size_t)n * 8, 16), bf = align_up((size_t)nh * 72, 16), bc = align_up((size_t)nh * 4, 16), bm = align_up((size_t)nh * n, 16);
+    if ((st = grow(h, &h->d_mq, &h->mq_cap, 2 * bp + bf + bc + 16 + align_up((size_t)n, 16))) != ORBX_OK) return st;
+    if ((st = grow(h, &h->d_mt, &h->mt_cap, bm)) != ORBX_OK) return st;
+    float *d_p1 = (float *)h->d_mq, *d_p2 = (float *)(h->d_mq + bp);
+    double *d_F = (double *)(h->d_mq + 2 * bp);
+    int32_t *d_c = (int32_t *)(h->d_mq + 2 * bp + bf), *d_b = (int32_t *)(h->d_mq + 2 * bp + bf + bc);
+    uint8_t *d_bm = h->d_mq + 2 * bp + bf + bc + 16;
+    ORBX_CUDA(h, cudaMemcpyAsync(d_p1, pts1, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(h, cudaMemcpyAsync(d_p2, pts2, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    launch_fmat_hypotheses(h, d_p1, d_p2, n, nh, seed, d_F);
+    launch_fmat_score(h, d_p1, d_p2, n, d_F, nh, (float)(threshold * threshold), d_c, h->d_mt, d_b, d_bm);
+    int32_t best = 0;
+    ORBX_CUDA(h, cudaMemcpyAsync(&best, d_b, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(h, cudaMemcpyAsync(best_mask, d_bm, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    ORBX_CUDA(h, cudaMemcpy(F_out, d_F + (size_t)best * 9, 72, cudaMemcpyDeviceToHost));
+    if (n_inliers) ORBX_CUDA(h, cudaMemcpy(n_inliers, d_c + best, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
 // ---- synthetic inputs ----
 extern "C" orbx_status orbx_synth_gray_device(orbx_handle *h, uint32_t seed, int32_t first, int32_t n, int32_t w, int32_t hgt, uint8_t *d, size_t step, size_t fstride)
 {

@@ -270,5 +270,6 @@ void launch_test_trig(orbx_handle *h, const float *d_in, int n, float *d_c, floa
 void launch_test_atan2(orbx_handle *h, const float *d_y, const float *d_x, int n, float *d_o);
 void launch_trig_checksum(orbx_handle *h, uint32_t first, uint32_t last, unsigned long long *d_sums);
 double run_popc_bench(orbx_handle *h);
+void launch_fmat_hypotheses(orbx_handle *h, const float *d_p1, const float *d_p2, int n, int nh, uint32_t seed, double *d_F);
 void launch_fmat_score(orbx_handle *h, const float *d_p1, const float *d_p2, int n, const double *d_F, int nh, float t2,
                        int32_t *d_counts, uint8_t *d_masks, int32_t *d_best, uint8_t *d_best_mask);

@@ -132,6 +132,7 @@ def load():
         "orbx_track_batch_submit": (i32, [vp, vp, i32, i32, i32, sz, vp, sz, vp, vp, i32, vp, vp, vp, f32, vp]),
         "orbx_batch_wait": (i32, [vp, i32]),
         "orbx_fmat_score": (i32, [vp, vp, vp, i32, vp, i32, ct.c_double, vp, vp, vp]),
+        "orbx_fmat_ransac": (i32, [vp, vp, vp, i32, i32, ct.c_double, u32, vp, vp, vp]),
         "orbx_comm_get_unique_id": (i32, [vp]),
         "orbx_comm_last_error": (ct.c_char_p, []),
         "orbx_comm_create": (i32, [vp, i32, i32, vp, vp]),
@@ -423,6 +424,16 @@ class ORBextractor:
         best = ct.c_int32()
         self._check(self.L.orbx_fmat_score(self._h, _p(pts1), _p(pts2), len(pts1), _p(F), len(F), ct.c_double(threshold), _p(counts), ct.byref(best), _p(mask)))
         return counts, best.value, mask[:len(pts1)].copy()
+
+    def fmat_ransac(self, pts1, pts2, iters=1000, threshold=2.0, seed=1):
+        """Device RANSAC for the fundamental matrix (8-point hypotheses + OpenCV's scoring): returns (F [3,3], mask [n], inliers)."""
+        pts1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+        pts2 = np.ascontiguousarray(pts2, np.float32).reshape(-1, 2)
+        F = np.zeros(9, np.float64)
+        mask = np.zeros(len(pts1), np.uint8)
+        n = ct.c_int32()
+        self._check(self.L.orbx_fmat_ransac(self._h, _p(pts1), _p(pts2), len(pts1), int(iters), ct.c_double(threshold), ct.c_uint32(seed), _p(F), _p(mask), ct.byref(n)))
+        return F.reshape(3, 3), mask, n.value
 
     def extract_batch_device(self, d_gray, nframes, w, h, step, frame_stride, d_kps, d_desc, cap, d_counts,
                              d_depth=None, dstep=0, dframe_stride=0):

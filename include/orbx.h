@@ -332,6 +332,14 @@ orbx_status orbx_cull_keyframe_device(orbx_handle *h, const orbx_keypoint *d_kps
 orbx_status orbx_fmat_score(orbx_handle *h, const float *pts1, const float *pts2, int32_t n, const double *F, int32_t nh, double threshold,
                             int32_t *inlier_counts, int32_t *best, uint8_t *best_mask);
 
+/* The whole geometric validation on the device: nh minimal samples (8 distinct correspondences each, counter-based generator from `seed`)
+ * -> normalised 8-point fundamental matrices (fp64, rank 2 enforced, F(2,2) = 1) -> OpenCV's scoring as above -> the model with the most inliers.
+ * NOT a restatement of cv::findFundamentalMat (its 7-point samples come from OpenCV's own RNG and cannot be reproduced); what holds by
+ * construction is the contract of its result: best_mask is exactly the inlier set OpenCV's error function gives for F_out at `threshold`.
+ * n >= 8, nh >= 1.  F_out: row-major 3x3.  n_inliers may be NULL.                                                                */
+orbx_status orbx_fmat_ransac(orbx_handle *h, const float *pts1, const float *pts2, int32_t n, int32_t nh, double threshold, uint32_t seed,
+                             double *F_out, uint8_t *best_mask, int32_t *n_inliers);
+
 /* ---- keyframe packing: the landmark / observation loop of Frontend::publishKeyframe (frontend.cpp:731-776), SURVEY §8(f) rank 2 ----
  * For every keypoint with a depth in (0.3, 3.0) m: back-projection with the float intrinsics, world transform R*p + t in double,
  * one 80-byte record; order preserved; landmark_id = index of the keypoint in the input list, as in the reference.

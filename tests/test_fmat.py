@@ -63,3 +63,45 @@ def test_gpu_scoring_bit_exact(built, oracle):
         assert c0.tolist() == [0] and len(m0) == 0
     finally:
         ex.close()
+
+
+@pytest.mark.gpu
+def test_gpu_ransac_model_and_its_inlier_set(built, oracle):
+    """orbx_fmat_ransac: 8-point hypotheses generated and scored on the device.  The sample sequence is its own (OpenCV's RNG cannot be
+    reproduced), so the checks are (1) the contract of the result — the returned mask is exactly the inlier set OpenCV's error function
+    gives for the returned model — and (2) quality: on a synthetic two-view scene with 15 % gross outliers it finds (nearly) all true inliers,
+    and as many as cv2.findFundamentalMat where cv2 is importable."""
+    import orbx
+    rng = np.random.default_rng(5)
+    ex = orbx.ORBextractor(max_width=640, max_height=480)
+    try:
+        for trial in range(3):
+            X = rng.uniform(-2, 2, (400, 3)) + [0, 0, 6]
+            K = np.array([[600.0, 0, 320], [0, 600, 240], [0, 0, 1]])
+            a = rng.normal(0, 0.05, 3)
+            th = np.linalg.norm(a); k = a / th
+            Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+            R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+            t = rng.normal(0, 0.3, 3)
+            pa = (K @ X.T).T
+            pb = (K @ (R @ X.T + t[:, None])).T
+            p1 = (pa[:, :2] / pa[:, 2:]).astype(np.float32) + rng.normal(0, 0.3, (400, 2)).astype(np.float32)
+            p2 = (pb[:, :2] / pb[:, 2:]).astype(np.float32) + rng.normal(0, 0.3, (400, 2)).astype(np.float32)
+            p2[:60] += rng.uniform(-50, 50, (60, 2)).astype(np.float32)
+            F, mask, n_in = ex.fmat_ransac(p1, p2, iters=1000, threshold=2.0, seed=7 + trial)
+            n_or, m_or = oracle.fmat_inliers(p1, p2, F, 2.0)
+            assert n_in == n_or and np.array_equal(mask, m_or), "the mask must be OpenCV's inlier set of the returned model"
+            assert abs(F[2, 2] - 1.0) < 1e-12 and abs(np.linalg.det(F)) < 1e-9 * max(1.0, np.abs(F).max() ** 3)        # scaled like OpenCV's, rank 2
+            assert mask[60:].sum() >= 0.9 * 340 and mask[:60].sum() <= 12, (trial, int(mask[60:].sum()), int(mask[:60].sum()))
+            try:
+                import cv2
+                _, mcv = cv2.findFundamentalMat(p1, p2, cv2.FM_RANSAC, 2.0, 0.99)
+                assert n_in >= 0.95 * int(mcv.sum()), (trial, n_in, int(mcv.sum()))
+            except ImportError:
+                pass
+        F2, mask2, n2 = ex.fmat_ransac(p1, p2, iters=1000, threshold=2.0, seed=9)
+        assert np.array_equal(F, F2) and np.array_equal(mask, mask2)                                                    # deterministic in the seed
+        with pytest.raises(orbx.OrbxError):
+            ex.fmat_ransac(p1[:7], p2[:7])
+    finally:
+        ex.close()

@@ -169,3 +169,40 @@ def test_db_device_pointer_variants(built, oracle):
     finally:
         db.close()
         ex.close()
+
+
+def test_two_handles_share_a_gpu_and_argument_validation(built, oracle):
+    """(a) dynamic shared-memory opt-ins are per function and device — a second handle with smaller needs must not lower what
+    the first one relies on; (b) an nfeatures whose quadtree node table cannot fit shared memory is refused at create with a message;
+    (c) a bad depth step is ORBX_E_INVALID, not a device fault."""
+    import orbx
+    rng = np.random.default_rng(3)
+    a = orbx.ORBextractor(max_width=W, max_height=H)
+    b = orbx.ORBextractor(max_width=W, max_height=H)
+    try:
+        n_big, n_small = 8000, 64
+        kb = np.zeros(n_big, orbx.KP_DTYPE); kb["response"] = rng.integers(0, 200, n_big).astype(np.float32)
+        db = rng.integers(0, 256, (n_big, 32), dtype=np.uint8)
+        want_big = oracle.cull_keyframe(kb["response"], np.arange(0, n_big, 7, dtype=np.int32))
+        _, _, ia = a.cull_keyframe(kb, db, np.arange(0, n_big, 7, dtype=np.int32))          # handle A: large opt-in
+        assert np.array_equal(ia, want_big)
+        _, _, ib = b.cull_keyframe(kb[:n_small], db[:n_small], np.zeros(0, np.int32))       # handle B: small launch of the same kernel
+        assert np.array_equal(ib, oracle.cull_keyframe(kb["response"][:n_small], np.zeros(0, np.int32)))
+        _, _, ia2 = a.cull_keyframe(kb, db, np.arange(0, n_big, 7, dtype=np.int32))         # handle A again: must still launch
+        assert np.array_equal(ia2, want_big)
+        g = oracle.synth_gray(3, 0, W, H)
+        depth = oracle.synth_depth(3, 0, W, H)
+        kps = np.zeros(4096, orbx.KP_DTYPE); desc = np.zeros((4096, 32), np.uint8); n = ct.c_int32()
+        st = a.L.orbx_extract_filtered(a.handle, g.ctypes.data_as(ct.c_void_p), W, H, W, depth.ctypes.data_as(ct.c_void_p), 2 * W - 1, None, 0, ct.c_uint64(0),
+                                       kps.ctypes.data_as(ct.c_void_p), desc.ctypes.data_as(ct.c_void_p), 4096, ct.byref(n))
+        assert st == orbx.E_INVALID                                                          # odd depth step
+        st = a.L.orbx_extract_filtered(a.handle, g.ctypes.data_as(ct.c_void_p), W, H, W, depth.ctypes.data_as(ct.c_void_p), W, None, 0, ct.c_uint64(0),
+                                       kps.ctypes.data_as(ct.c_void_p), desc.ctypes.data_as(ct.c_void_p), 4096, ct.byref(n))
+        assert st == orbx.E_INVALID                                                          # depth rows shorter than 2 * width
+        k_ok, _ = a(g, depth=depth)                                                          # the handle stays usable
+        assert len(k_ok) > 100
+    finally:
+        a.close(); b.close()
+    with pytest.raises(orbx.OrbxError) as err:
+        orbx.ORBextractor(nfeatures=60000, max_width=W, max_height=H)
+    assert err.value.status == orbx.E_UNSUPPORTED and "shared-memory" in str(err.value)

@@ -1,6 +1,7 @@
 #!/bin/bash
-# Runs on the GPU box (under gpurun): un-profiled bench, ncu launch list of one step, ncu --set full of the step's kernels, and (tag2) the
-# kernels outside the step chain.   usage: tools/profile_round.sh <tag>
+# Runs on the GPU box (under gpurun): un-profiled bench, ncu launch list of one step, ncu --set full of the step's kernels.
+# The kernels outside the step chain: tools/profile_extra.sh (its own gpurun call: gpurun_out/ is limited to 64 MiB per call).
+# usage: tools/profile_round.sh <tag>
 set -u
 TAG=${1:-r02}
 O=gpurun_out
@@ -11,7 +12,3 @@ $CMD > $O/${TAG}_plain.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -s 46 -c 15 --csv --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu_list.log 2>&1
 ncu --set full --clock-control none --import-source on -s 46 -c 15 -o $O/${TAG}_full -f $CMD > $O/${TAG}_ncu_full.log 2>&1
 tail -2 $O/${TAG}_ncu_full.log
-python tools/profile_extra.py > $O/${TAG}_extra_plain.log 2>&1 || exit 1
-ncu --set full --clock-control none --import-source on -k "regex:k_match_mma|k_match_partial|k_assoc_partial|k_blur7|k_cull|k_cfast|k_cretain|k_cblur|k_fmat_score|k_resize_exact|k_describe_c|k_describe$" \
-    -o $O/${TAG}_extra -f python tools/profile_extra.py > $O/${TAG}_ncu_extra.log 2>&1
-tail -2 $O/${TAG}_ncu_extra.log
