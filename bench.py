@@ -54,6 +54,7 @@ LEVEL_PX = [1280 * 720, 1067 * 600, 889 * 500, 741 * 417, 617 * 347, 514 * 289, 
 ALG_BYTES = {
     "k_resize_linear": sum(LEVEL_PX[:7]) + sum(LEVEL_PX[1:]),      # read L0..L6 once, write L1..L7 once (7 launches)
     "k_fast_cells": sum(LEVEL_PX),                                  # read every level once
+    "k_fast_dense": sum(LEVEL_PX),                                  # the same levels, whole-level tiles (its score map is scratch, not algorithmic traffic)
     "k_blur7": 2 * sum(LEVEL_PX),                                   # read + write every level once
 }
 POPC_PER_PAIR = 5.0              # csrc/orbx_hamming.h (ORBX_MATCH_CSA = 2)
@@ -262,6 +263,7 @@ def main():
     ap.add_argument("--no-pdl", action="store_true", help="plain stream order instead of programmatic dependent launch (ORBX_OPT_PDL = 0)")
     ap.add_argument("--fast-ctas", type=int, default=0, help="resident FAST warps per SM in the overlapped schedule (0 = library default)")
     ap.add_argument("--overlap", action="store_true", help="two staggered half-batches on two streams (ORBX_OPT_OVERLAP = 1; measured slower than one chain)")
+    ap.add_argument("--fast-dense", action="store_true", help="the dense FAST formulation (ORBX_OPT_FAST_DENSE = 1) instead of the warp-per-cell kernel")
     ap.add_argument("--popc-match", action="store_true", help="the LOP3/POPC matcher instead of the int8 tensor-core GEMM (ORBX_OPT_MATCH_MMA = 0)")
     ap.add_argument("--host-chunk", type=int, default=0, help="frames per pipeline chunk of the host-buffer call (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -303,6 +305,8 @@ def main():
         ex.set_overlap(True)
     if args.popc_match:
         ex.set_match_mma(False)
+    if args.fast_dense:
+        ex.set_fast_dense(1)
     L, hnd = ex.L, ex.handle
     stream = torch.cuda.ExternalStream(ex.stream, device=dev)
 

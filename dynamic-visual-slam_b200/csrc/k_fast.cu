@@ -62,129 +62,11 @@ struct FastParams {
     int32_t *work;               // dynamic work counter (zeroed with the corner counts)
     int tile_rows;               // max (hCell + 6) over the levels
     int map_pitch;               // score-map pitch: >= max cell width + 2, multiple of 16
+    const int32_t *items;        // retry mode (k_fast_dense.cu): the (frame, cell) items to run and their device-side count; null = all of them
+    const int32_t *nitems_dev;
 };
 
-#define RO(dx, dy) ((dy) * TP + (dx))
-
-// S on the raw ring values: S = max( I(p) - min_k max9_k(ring), max_k min9_k(ring) - I(p) ).
-// Packed lanes: lo16 = r, hi16 = 255 - r  =>  a lane-wise min yields (min r, 255 - max r).
-// min9_k = min3( min3(r_k..r_k+2), min3(r_k+3..r_k+5), min3(r_k+6..r_k+8) ): 40 three-input min/max in all.
-__device__ __forceinline__ uint32_t vmin3u2(uint32_t a, uint32_t b, uint32_t c) { return __vminu2(__vminu2(a, b), c); }
-__device__ __forceinline__ uint32_t vmax3u2(uint32_t a, uint32_t b, uint32_t c) { return __vmaxu2(__vmaxu2(a, b), c); }
-template <int TP> __device__ __forceinline__ int fast_score_packed(const uint8_t *p)
-{
-    const int v = p[0];
-    uint32_t r[16];
-#define PK(x) ((uint32_t)(x) * 0xFFFF0001u + 0x00FF0000u)
-    r[0] = PK(p[RO(0, 3)]);   r[1] = PK(p[RO(1, 3)]);    r[2] = PK(p[RO(2, 2)]);    r[3] = PK(p[RO(3, 1)]);
-    r[4] = PK(p[RO(3, 0)]);   r[5] = PK(p[RO(3, -1)]);   r[6] = PK(p[RO(2, -2)]);   r[7] = PK(p[RO(1, -3)]);
-    r[8] = PK(p[RO(0, -3)]);  r[9] = PK(p[RO(-1, -3)]);  r[10] = PK(p[RO(-2, -2)]); r[11] = PK(p[RO(-3, -1)]);
-    r[12] = PK(p[RO(-3, 0)]); r[13] = PK(p[RO(-3, 1)]);  r[14] = PK(p[RO(-2, 2)]);  r[15] = PK(p[RO(-1, 3)]);
-#undef PK
-    uint32_t m3[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) m3[k] = vmin3u2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
-    uint32_t m9[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) m9[k] = vmin3u2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
-    uint32_t b4[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) b4[k] = __vmaxu2(vmax3u2(m9[4 * k], m9[4 * k + 1], m9[4 * k + 2]), m9[4 * k + 3]);
-    const uint32_t best = __vmaxu2(__vmaxu2(b4[0], b4[1]), __vmaxu2(b4[2], b4[3]));   // per lane: max_k min9_k
-    const int hi_of_min = (int)(best & 0xFFFFu);                  // max_k min9_k(r)
-    const int lo_of_max = 255 - (int)(best >> 16);                // min_k max9_k(r)
-    const int s_dark = v - lo_of_max, s_bright = hi_of_min - v;
-    return s_dark > s_bright ? s_dark : s_bright;
-}
-
-// one tile row entering the sweep window: the thread's own word C plus the four shifted views of it
-struct FastRow { uint32_t C, P2, M2, P3, M3; };
-__device__ __forceinline__ FastRow fast_row(const uint32_t *q)
-{
-    const uint32_t L = q[-1], C = q[0], R = q[1];
-    FastRow w;
-    w.C = C;
-    w.P2 = __byte_perm(C, R, 0x5432);      // columns x+2 .. x+5
-    w.M2 = __byte_perm(L, C, 0x5432);      // columns x-2 .. x+1
-    w.P3 = __byte_perm(C, R, 0x6543);      // columns x+3 .. x+6
-    w.M3 = __byte_perm(L, C, 0x4321);      // columns x-3 .. x
-    return w;
-}
-
-// Pre-test of R <= 8 detection rows x 4 pixels (8 flag bits per pixel column).  q = the item's word in tile row r0 (= ring row dy = -3 of the first
-// detection row).  Result: bit (7-k) of byte j set iff pixel (row r0 + k, byte j) may be a corner at threshold T.
-#ifndef FAST_RMAX
-#define FAST_RMAX 16                 // tallest sweep unit: a 37-row cell then takes 3 units per word column (30 units = ONE warp iteration at 94 %
-                                     // lane use) instead of 5 units of 8 rows (50 units = two iterations at 78 %)
-#endif
-#ifndef FAST_PAIRS
-#define FAST_PAIRS 2                 // opposite ring pairs tested in the sweep: 4 = (0,8) (4,12) (2,10) (6,14); 2 = (0,8) (4,12) only (measured: 0.474 -> 0.450 ms per 128 frames)
-#endif
-#if FAST_PAIRS == 4
-template <int TP> __device__ __noinline__ uint2 fast_sweep7(const uint32_t *q, uint32_t HM, uint32_t KK, int R)
-{
-    FastRow w[7];
-#pragma unroll
-    for (int k = 0; k < 6; k++) w[k] = fast_row(q + k * (TP / 4));
-    uint32_t fl0 = 0u, fl1 = 0u;                                                 // rows 0..7 and rows 8..15 of the unit
-#pragma unroll
-    for (int k = 0; k < FAST_RMAX; k++) {
-        if (k >= R) break;                                                       // units of R <= FAST_RMAX rows (uniform); the window indices are mod 7
-        w[(k + 6) % 7] = fast_row(q + (k + 6) * (TP / 4));                       // ring row dy = +3 of detection row k
-        const uint32_t C0 = w[(k + 3) % 7].C;
-        const uint32_t p08 = __vabsdiffu4(w[(k + 6) % 7].C, C0) | __vabsdiffu4(w[k % 7].C, C0);
-        const uint32_t p4c = __vabsdiffu4(w[(k + 3) % 7].P3, C0) | __vabsdiffu4(w[(k + 3) % 7].M3, C0);
-        const uint32_t p2a = __vabsdiffu4(w[(k + 5) % 7].P2, C0) | __vabsdiffu4(w[(k + 1) % 7].M2, C0);
-        const uint32_t p6e = __vabsdiffu4(w[(k + 1) % 7].P2, C0) | __vabsdiffu4(w[(k + 5) % 7].M2, C0);
-        const uint32_t t0 = p08 & HM, t1 = p4c & HM, t2 = p2a & HM, t3 = p6e & HM;
-        uint32_t acc = t0 | (t0 + KK);
-        acc &= t1 | (t1 + KK);
-        acc &= t2 | (t2 + KK);
-        acc &= t3 | (t3 + KK);
-        if (k < 8) fl0 |= (acc >> k) & (0x80808080u >> k);
-        else fl1 |= (acc >> (k - 8)) & (0x80808080u >> (k - 8));
-    }
-    return make_uint2(fl0, fl1);
-}
-#else
-// Two-pair sweep: the vertical pair (0,8) and the horizontal pair (4,12) only.  On textured frames they alone reject 97.5 % of the pixels
-// (all four: 97.8 %), for half the arithmetic: a row needs its own word plus the two 3-byte-shifted views when it is the centre row,
-// and the vertical difference |I(y+3) - I(y)| of a row serves the centres y and y+3 (it is kept three rows).
-template <int TP> __device__ __noinline__ uint2 fast_sweep7(const uint32_t *q, uint32_t HM, uint32_t KK, int R)
-{
-    uint32_t c[7], dv[3];                                                        // c: rows k..k+6 (mod 7); dv[j % 3] = |C(j+3) - C(j)|
-#pragma unroll
-    for (int k = 0; k < 6; k++) c[k] = q[k * (TP / 4)];
-#pragma unroll
-    for (int j = 0; j < 3; j++) dv[j] = __vabsdiffu4(c[j + 3], c[j]);
-    uint32_t fl0 = 0u, fl1 = 0u;
-#pragma unroll
-    for (int k = 0; k < FAST_RMAX; k++) {
-        if (k >= R) break;
-        const uint32_t *row = q + (k + 3) * (TP / 4);                            // the centre row of detection row k
-        const uint32_t L = row[-1], Rw = row[1];
-        c[(k + 6) % 7] = q[(k + 6) * (TP / 4)];
-        const uint32_t C0 = c[(k + 3) % 7];
-        const uint32_t up = dv[k % 3];                                           // |C(k+3) - C(k)|: ring pixel 8 (dy = -3) of centre k+3
-        const uint32_t dn = __vabsdiffu4(c[(k + 6) % 7], C0);                    // ring pixel 0 (dy = +3)
-        dv[k % 3] = dn;                                                          // = |C(j+3) - C(j)| for j = k+3, needed again at k+3
-        const uint32_t t0 = (up | dn) & HM;
-        const uint32_t t1 = (__vabsdiffu4(__byte_perm(C0, Rw, 0x6543), C0) | __vabsdiffu4(__byte_perm(L, C0, 0x4321), C0)) & HM;
-        const uint32_t acc = (t0 | (t0 + KK)) & (t1 | (t1 + KK));
-        if (k < 8) fl0 |= (acc >> k) & (0x80808080u >> k);
-        else fl1 |= (acc >> (k - 8)) & (0x80808080u >> (k - 8));
-    }
-    return make_uint2(fl0, fl1);
-}
-#endif
-
-// loose pre-test threshold T = 2^sh - 1 <= th:  |d| > T  <=>  (|d| & HM) != 0;  t + KK sets bit 7 of every byte with t >= 2^sh
-__device__ __forceinline__ void fast_masks(int th, uint32_t &HM, uint32_t &KK)
-{
-    const int sh = min(7, 31 - __clz(th + 1));
-    HM = ((0xFFu << sh) & 0xFFu) * 0x01010101u;
-    KK = (0x80u - (1u << sh)) * 0x01010101u;
-}
+#include "orbx_fast_dev.h"
 
 // the (frame-independent) description of one cell, built on the host with the geometry (orbx_build_fast_cells): two 16-byte loads
 // replace ~250 instructions of per-cell address arithmetic
@@ -193,33 +75,14 @@ __device__ __forceinline__ void fast_masks(int th, uint32_t &HM, uint32_t &KK)
 //   c1.x = 1 / nG (float bits)   c1.y = offset of the level's corner list   c1.z = its capacity   c1.w = bytes the TMA box delivers
 struct FastCellRegs { uint4 c0, c1; };
 // item -> (frame, cell): float estimate + exact fix-up (no integer division on the per-cell path)
-__device__ __forceinline__ void fast_split(const FastParams &P, int item, int &f, int &c)
+template <bool RETRY> __device__ __forceinline__ void fast_split(const FastParams &P, int idx, int nitems, int &f, int &c)
 {
+    int item = idx;
+    if (RETRY) item = idx < nitems ? P.items[idx] : 0;          // written by the previous kernel of the stream: plain loads
     f = __float2int_rz(((float)item + 0.5f) * P.inv_ncells);
     c = item - f * P.ncells;
     if (c < 0) { f--; c += P.ncells; }
     else if (c >= P.ncells) { f++; c -= P.ncells; }
-}
-
-// the warp's result list -> the (frame, level) corner list at the slot range a counter atomic reserved
-#ifndef FS_RES
-#define FS_RES 64
-#endif
-__device__ __forceinline__ void fast_write_out(const uint32_t *res, int n, int base, uint32_t *gdst, int cap, int32_t *status, int lane)
-{
-    for (int i = lane; i < n; i += 32) {
-        if (base + i < cap) gdst[base + i] = res[i];
-        else atomicOr(status, ORBX_DS_CAND_OVERFLOW);
-    }
-}
-// synchronous variant (a cell with more results than the list holds)
-__device__ __noinline__ void fast_publish(const uint32_t *res, int n, int32_t *gcnt, uint32_t *gdst, int cap, int32_t *status, int lane)
-{
-    __syncwarp();
-    int base = 0;
-    if (lane == 0) base = atomicAdd(gcnt, n);
-    fast_write_out(res, n, __shfl_sync(0xffffffffu, base, 0), gdst, cap, status, lane);
-    __syncwarp();
 }
 
 template <int TP> __device__ __forceinline__ void fast_score_to_map(const uint8_t *s_img, uint8_t *s_sc, int SP, int off, int ax, int th)
@@ -229,7 +92,7 @@ template <int TP> __device__ __forceinline__ void fast_score_to_map(const uint8_
     s_sc[(tr - 2) * SP + (tc - 2)] = (uint8_t)(s > th ? s - 1 : 0);
 }
 
-template <int TP> __global__ void __launch_bounds__(32) k_fast_cells(const __grid_constant__ LevelMaps M, FastParams P, const FrameGeom *__restrict__ G)
+template <int TP, bool RETRY> __global__ void __launch_bounds__(32) k_fast_cells(const __grid_constant__ LevelMaps M, FastParams P, const FrameGeom *__restrict__ G)
 {
     extern __shared__ __align__(128) uint8_t s_raw[];
     __shared__ __align__(8) uint64_t s_full;
@@ -259,12 +122,13 @@ template <int TP> __global__ void __launch_bounds__(32) k_fast_cells(const __gri
     // cells: the draw for the cell after next flies during the sweep, the next window is prefetched into L2 at the top and
     // loaded by TMA as soon as the tile is free, and a finished cell's results are written to the corner list one cell later,
     // when the counter atomic that reserved their slots has long returned.
-    if ((int)blockIdx.x >= P.nitems) return;
+    const int nwork = RETRY ? *P.nitems_dev : P.nitems;
+    if ((int)blockIdx.x >= nwork) return;
     int it_n = 0, nres = 0, buf = 0;
     int pn = 0, pbase = 0, pcap = 0;                                  // the previous cell's list: length, reserved base (lane 0), list capacity
     uint32_t *pdst = nullptr;
     int f, ci, nf = 0, nc = 0;                                        // (frame, cell) of the current and of the next item
-    fast_split(P, blockIdx.x, f, ci);
+    fast_split<RETRY>(P, blockIdx.x, nwork, f, ci);
     FastCellRegs C;
     C.c0 = __ldg(P.cells + 2 * ci); C.c1 = __ldg(P.cells + 2 * ci + 1);
     int nxt = 0;
@@ -274,9 +138,9 @@ template <int TP> __global__ void __launch_bounds__(32) k_fast_cells(const __gri
         nxt = atomicAdd(P.work, 1) + (int)gridDim.x;
     }
     nxt = __shfl_sync(0xffffffffu, nxt, 0);
-    fast_split(P, nxt, nf, nc);
+    fast_split<RETRY>(P, nxt, nwork, nf, nc);
     for (;; it_n++) {
-        const bool has_next = nxt < P.nitems;
+        const bool has_next = nxt < nwork;
         int drawn = 0;
         uint32_t nx = 0u, ny = 0u;
         if (has_next && lane == 0) {
@@ -297,7 +161,7 @@ template <int TP> __global__ void __launch_bounds__(32) k_fast_cells(const __gri
         __syncwarp();
 
         const int units = nG * nseg;
-        for (int pass = 0; pass < 2; pass++) {
+        for (int pass = RETRY ? 1 : 0; pass < 2; pass++) {
             const int th = pass == 0 ? P.ini_th : P.min_th;
             uint32_t HM, KK;
             fast_masks(th, HM, KK);
@@ -399,7 +263,7 @@ template <int TP> __global__ void __launch_bounds__(32) k_fast_cells(const __gri
         f = nf; ci = nc;
         C.c0 = __ldg(P.cells + 2 * ci); C.c1 = __ldg(P.cells + 2 * ci + 1);
         nxt = __shfl_sync(0xffffffffu, drawn, 0);
-        fast_split(P, nxt, nf, nc);
+        fast_split<RETRY>(P, nxt, nwork, nf, nc);
     }
     if (pn) fast_write_out(s_res + (buf ^ 1) * FS_RES, pn, __shfl_sync(0xffffffffu, pbase, 0), pdst, pcap, P.status, lane);
 }
@@ -457,7 +321,12 @@ static PFN_tmapEncodeTiled get_encode()
 }
 
 // level as a 3-D tensor of u32 elements: (row pitch / 4) x rows x frames; box = FS_TPW x (hCell + 6) x 1, zero fill outside
-static bool encode_level(CUtensorMap *m, const uint8_t *base, size_t pitch, int rows, size_t fstride, int frames, int box_rows, int box_words = ORBX_TMA_BOX_WORDS)
+static bool encode_level(CUtensorMap *m, const uint8_t *base, size_t pitch, int rows, size_t fstride, int frames, int box_rows, int box_words = ORBX_TMA_BOX_WORDS);
+bool orbx_encode_level(CUtensorMap *m, const uint8_t *base, size_t pitch, int rows, size_t fstride, int frames, int box_rows, int box_words)
+{
+    return encode_level(m, base, pitch, rows, fstride, frames, box_rows, box_words);
+}
+static bool encode_level(CUtensorMap *m, const uint8_t *base, size_t pitch, int rows, size_t fstride, int frames, int box_rows, int box_words)
 {
     PFN_tmapEncodeTiled enc = get_encode();
     if (!enc || ((uintptr_t)base & 15) || (pitch & 15) || pitch == 0) return false;
@@ -496,11 +365,12 @@ int orbx_ensure_tmaps(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_
     return 0;
 }
 
-int launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride)
+// the warp-per-cell kernel over every (frame, cell) item, or (retry mode, after the dense formulation of k_fast_dense.cu) over the listed
+// items at minThFAST only
+int launch_fast_cells(orbx_handle *h, int nframes, const int32_t *d_items, const int32_t *d_nitems)
 {
+    ProfScope ps(h, d_items ? ORBX_K_FAST_RETRY : ORBX_K_FAST);
     const FrameGeom &G = h->geo;
-    if (G.total_cells_valid <= 0) return 0;
-    if (orbx_ensure_tmaps(h, nframes, l0, l0_step, l0_fstride) != 0) return -1;
     LevelMaps M;
     memcpy(M.m, h->tmap_cell, sizeof(M.m));
     FastParams P;
@@ -510,21 +380,33 @@ int launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, 
     P.ini_th = h->prm.ini_th_fast; P.min_th = h->prm.min_th_fast;
     P.status = h->d_status;
     P.work = h->d_ncand + (size_t)h->prm.max_batch * ORBX_MAX_LEVELS;
+    P.items = d_items; P.nitems_dev = d_nitems;
     P.tile_rows = G.max_hcell + 6;
     P.map_pitch = (G.max_wcell + 2 + 15) & ~15;
     const int TP = fast_tile_pitch(G);
     const size_t map_bytes = (size_t)((((P.tile_rows - 4) * P.map_pitch) + 127) & ~127);
     const size_t smem = 128 + 128 + (size_t)(((P.tile_rows * TP) + 127) & ~127) + map_bytes + FS_WQ * 2;
-    auto kern = TP == 80 ? k_fast_cells<80> : k_fast_cells<96>;
+    auto kern = d_items ? (TP == 80 ? k_fast_cells<80, true> : k_fast_cells<96, true>) : (TP == 80 ? k_fast_cells<80, false> : k_fast_cells<96, false>);
+    if (!orbx_optin_smem(h, (const void *)kern, smem)) return -1;
     if (smem != h->fast_smem || TP != h->fast_tp) {
-        if (!orbx_optin_smem(h, (const void *)kern, smem)) return -1;
         int occ = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem);
         h->fast_grid_cap = std::max(1, occ) * h->sm_count; h->fast_smem = smem; h->fast_tp = TP;
     }
     int grid = std::min(P.nitems, h->fast_grid_cap);
     if (!h->opt_serial && h->opt_fast_ctas > 0) grid = std::min(grid, h->opt_fast_ctas * h->sm_count);
-    ProfScope ps(h, ORBX_K_FAST);
     orbx_launch_pdl(h, kern, dim3(grid), dim3(32), smem, h->stream, M, P, (const FrameGeom *)h->d_geo);
     return 0;
+}
+
+int launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride)
+{
+    const FrameGeom &G = h->geo;
+    if (G.total_cells_valid <= 0) return 0;
+    if (orbx_ensure_tmaps(h, nframes, l0, l0_step, l0_fstride) != 0) return -1;
+    // dense formulation for batches (ORBX_OPT_FAST_DENSE): one pass over whole levels + per-corner NMS, then this kernel on the few
+    // cells that need the minThFAST retry.  The half-batch lanes of ORBX_OPT_OVERLAP share one dense scratch: warp-per-cell there.
+    const bool dense = h->opt_fast_dense == 2 || (h->opt_fast_dense == 1 && nframes >= ORBX_FAST_DENSE_MIN_FRAMES);
+    if (dense && !h->in_overlap && h->dense_ok) return launch_fast_dense(h, nframes);
+    return launch_fast_cells(h, nframes, nullptr, nullptr);
 }

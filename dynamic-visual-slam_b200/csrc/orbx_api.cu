@@ -239,6 +239,16 @@ static orbx_status set_geometry(orbx_handle *h, int w, int hgt)
         ORBX_CUDA(h, cudaMemcpy(h->d_cells, recs.data(), recs.size() * sizeof(uint4), cudaMemcpyHostToDevice));
     }
     if (!btiles.empty()) ORBX_CUDA(h, cudaMemcpy(h->d_blur_tiles, btiles.data(), btiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    h->dgeo.ntiles = 0;                                    // 0 tiles = this geometry runs the warp-per-cell kernel
+    if (h->dense_ok) {
+        DenseGeom D; std::vector<uint4> dt;
+        orbx_build_fast_dense(G, h->prm.cand_divisor, D, &dt);
+        if (D.ntiles > 0 && D.ntiles <= h->dtile_cap && D.map_bytes * B <= h->smap_cap && D.cl_entries * B <= h->clist_cap) {
+            ORBX_CUDA(h, cudaMemcpy(h->d_dtiles, dt.data(), dt.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+            h->dgeo = D;
+        }
+    }
+    h->geo_serial++;
     G.total_strips = (int)strips.size();
     h->geo = G; h->pyr_slab = G.pyr_bytes; h->blur_slab = G.blur_bytes; h->tmap_valid = false; h->alt.tmap_valid = false;
     return ORBX_OK;
@@ -253,7 +263,8 @@ extern "C" void orbx_destroy(orbx_handle *h)
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     void *dev[] = { h->d_bgr, h->d_cells, h->d_blur_tiles, h->d_strips, h->d_prev_desc, h->d_prev_count, h->d_geo, h->d_xtab, h->d_ytab, h->d_pyr, h->d_blur, h->d_in, h->d_depth_in, h->d_cand, h->d_cand2, h->d_qtmp,
                     h->d_owner, h->d_owner2, h->d_ncand, h->d_sel, h->d_nsel, h->d_kps_all, h->d_desc_all, h->d_count_all,
-                    h->d_kps_out, h->d_desc_out, h->d_count_out, h->d_boxes, h->d_box_off, h->d_status_base, h->d_mpart, h->d_mq, h->d_mt, h->d_mout, h->d_mcount };
+                    h->d_kps_out, h->d_desc_out, h->d_count_out, h->d_boxes, h->d_box_off, h->d_status_base, h->d_mpart, h->d_mq, h->d_mt, h->d_mout, h->d_mcount,
+                    h->d_dtiles, h->d_smap, h->d_clist, h->d_dense_zero, h->d_retry };
     for (void *p : dev) if (p) cudaFree(p);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_status) cudaFreeHost(h->h_status);
@@ -348,6 +359,7 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     CREATE_CUDA(cudaMalloc(&h->d_strips, sizeof(uint32_t) * h->strip_cap));
     h->cell_cap = G.total_cells + G.total_cells / 4 + 64 * p.nlevels;
     CREATE_CUDA(cudaMalloc(&h->d_cells, 2 * sizeof(uint4) * h->cell_cap));
+    h->opt_fast_dense = 0; h->dense_ok = false;          // its arenas are allocated when ORBX_OPT_FAST_DENSE is first switched on (dense_alloc)
     h->blur_tile_cap = G.total_blur_tiles + G.total_blur_tiles / 4 + 64 * p.nlevels;
     CREATE_CUDA(cudaMalloc(&h->d_blur_tiles, sizeof(uint32_t) * h->blur_tile_cap));
     CREATE_CUDA(cudaMalloc(&h->d_xtab, sizeof(ResizeTab) * h->tab_cap));
@@ -419,6 +431,38 @@ extern "C" orbx_status orbx_sync(orbx_handle *h)
     cudaSetDevice(h->device);
     return check_device_status(h);
 }
+// dense FAST formulation (k_fast_dense.cu): score maps + corner lists for max_batch frames of the largest geometry, allocated when the
+// option is first switched on (0.8 GB at 128 frames of 1280 x 720)
+static orbx_status dense_alloc(orbx_handle *h)
+{
+    if (h->dense_ok) return ORBX_OK;
+    const orbx_params &p = h->prm;
+    if (p.profile != ORBX_PROFILE_SLAM) { h->err = "ORBX_OPT_FAST_DENSE is a profile-S option"; return ORBX_E_UNSUPPORTED; }
+    cudaSetDevice(h->device);
+    FrameGeom G;
+    if (!build_geometry(h, p.max_width, p.max_height, G, nullptr, nullptr)) { h->err = "max_width x max_height is not a supported geometry"; return ORBX_E_UNSUPPORTED; }
+    const size_t B = (size_t)p.max_batch;
+    DenseGeom D;
+    orbx_build_fast_dense(G, p.cand_divisor, D, nullptr);
+    h->dtile_cap = D.ntiles + D.ntiles / 4 + 64 * p.nlevels;
+    h->smap_cap = (D.map_bytes + D.map_bytes / 8 + 65536) * B;
+    h->clist_cap = (D.cl_entries + D.cl_entries / 8 + 4096 * p.nlevels) * B;
+    h->dense_zero_bytes = (4 + B * ORBX_MAX_LEVELS) * sizeof(int32_t) + B * (size_t)h->cell_cap;
+    if (cudaMalloc(&h->d_dtiles, sizeof(uint4) * h->dtile_cap) != cudaSuccess || cudaMalloc(&h->d_smap, h->smap_cap) != cudaSuccess ||
+        cudaMalloc(&h->d_clist, h->clist_cap * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&h->d_dense_zero, h->dense_zero_bytes) != cudaSuccess ||
+        cudaMalloc(&h->d_retry, B * (size_t)h->cell_cap * sizeof(int32_t)) != cudaSuccess) {
+        cudaGetLastError();
+        void *dn[] = { h->d_dtiles, h->d_smap, h->d_clist, h->d_dense_zero, h->d_retry };
+        for (void *q : dn) if (q) cudaFree(q);
+        h->d_dtiles = nullptr; h->d_smap = nullptr; h->d_clist = nullptr; h->d_dense_zero = nullptr; h->d_retry = nullptr;
+        h->err = "out of device memory for the dense FAST arenas";
+        return ORBX_E_CUDA;
+    }
+    h->dense_ok = true;
+    h->geo.width = -1; h->geo.height = -1;                 // the next call rebuilds the geometry, now with the tile table
+    return ORBX_OK;
+}
+
 extern "C" orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t value)
 {
     if (!h) return ORBX_E_INVALID;
@@ -427,6 +471,12 @@ extern "C" orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t v
     if (option == ORBX_OPT_FUSED_BLUR) { h->opt_fused_blur = value ? 1 : 0; return ORBX_OK; }
     if (option == ORBX_OPT_PDL) { h->opt_pdl = value ? 1 : 0; return ORBX_OK; }
     if (option == ORBX_OPT_OVERLAP) { h->opt_overlap = value ? 1 : 0; return ORBX_OK; }
+    if (option == ORBX_OPT_FAST_DENSE) {
+        const int v = value < 0 ? 0 : (value > 2 ? 2 : value);
+        if (v > 0) { const orbx_status st = dense_alloc(h); if (st != ORBX_OK) return st; }
+        h->opt_fast_dense = v;
+        return ORBX_OK;
+    }
     if (option == ORBX_OPT_MATCH_MMA) { h->opt_match_mma = value < 0 ? 0 : (value > 2 ? 2 : value); return ORBX_OK; }
     h->err = "unknown option"; return ORBX_E_INVALID;
 }
@@ -1110,6 +1160,47 @@ extern "C" orbx_status orbx_get_blurred_level(orbx_handle *h, int32_t frame, int
     ORBX_CUDA(h, cudaMemcpy2D(out, out_step, h->d_blur + (size_t)frame * h->blur_slab + g.boff, g.bpitch, (size_t)g.w, (size_t)g.h, cudaMemcpyDeviceToHost));
     return ORBX_OK;
 }
+// dense FAST formulation: the iniThFAST score map of a level (S - 1 where S > iniThFAST, else 0 — cv::FAST's score buffer over the whole
+// level), valid after a batch that ran k_fast_dense.  out: (h - 38) rows x (w - 38) columns, level pixel (19 + c, 19 + r) at out[r][c];
+// pixels outside the cell grid read 0.
+extern "C" orbx_status orbx_get_fast_scores(orbx_handle *h, int32_t frame, int32_t level, uint8_t *out, size_t out_step)
+{
+    if (!h || !out || level < 0 || level >= h->geo.nlevels || frame < 0 || frame >= h->last_batch) return ORBX_E_INVALID;
+    if (h->cv || !h->dense_ok || h->dgeo.ntiles <= 0) { h->err = "no dense FAST run on this handle"; return ORBX_E_UNSUPPORTED; }
+    cudaSetDevice(h->device);
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    const LevelGeom &g = h->geo.lv[level];
+    const DenseLevel &d = h->dgeo.lv[level];
+    const int ow = g.w - 2 * (ORBX_BORDER + 3), oh = g.h - 2 * (ORBX_BORDER + 3);
+    if (ow <= 0 || oh <= 0 || out_step < (size_t)ow) return ORBX_E_INVALID;
+    for (int r = 0; r < oh; r++) memset(out + (size_t)r * out_step, 0, (size_t)ow);
+    if (d.ntx <= 0) return ORBX_OK;
+    const int rows = std::min(oh, d.nty * 16), cols = std::min(ow, d.map_pitch - (ORBX_BORDER + 3 - 4));
+    ORBX_CUDA(h, cudaMemcpy2D(out, out_step, h->d_smap + (size_t)frame * h->dgeo.map_bytes + d.map_off + (ORBX_BORDER + 3 - 4), (size_t)d.map_pitch,
+                              (size_t)cols, (size_t)rows, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+// dense FAST formulation, stage access for tests: the corners k_fast_dense left to k_fast_nms (those on tile edges, and every corner of a
+// tile with more pre-test survivors than its queue holds) of frame slot `frame`, as (x, y, score) triples like orbx_get_candidates
+extern "C" orbx_status orbx_get_fast_edge_corners(orbx_handle *h, int32_t frame, int32_t level, int32_t *out_xys, int32_t cap, int32_t *n_out)
+{
+    if (!h || !out_xys || !n_out || level < 0 || level >= h->geo.nlevels || frame < 0 || frame >= h->last_batch) return ORBX_E_INVALID;
+    if (h->cv || !h->dense_ok || h->dgeo.ntiles <= 0) { h->err = "no dense FAST run on this handle"; return ORBX_E_UNSUPPORTED; }
+    cudaSetDevice(h->device);
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    const DenseLevel &d = h->dgeo.lv[level];
+    int32_t n = 0;
+    ORBX_CUDA(h, cudaMemcpy(&n, h->d_dense_zero + 4 + frame * h->geo.nlevels + level, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    *n_out = n;
+    if (n > d.cl_cap) { h->err = "corner list overflowed"; return ORBX_E_CAPACITY; }
+    if (n > cap) return ORBX_E_CAPACITY;
+    std::vector<uint32_t> tmp((size_t)std::max(n, 1));
+    ORBX_CUDA(h, cudaMemcpy(tmp.data(), h->d_clist + (size_t)frame * h->dgeo.cl_entries + d.cl_off, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) { out_xys[3 * i] = orbx_px(tmp[i]); out_xys[3 * i + 1] = orbx_py(tmp[i]); out_xys[3 * i + 2] = orbx_ps(tmp[i]); }
+    return ORBX_OK;
+}
+
 extern "C" orbx_status orbx_get_candidates(orbx_handle *h, int32_t frame, int32_t level, int32_t *out_xys, int32_t cap, int32_t *n_out)
 {
     if (!h || !out_xys || !n_out || level < 0 || level >= h->geo.nlevels || frame < 0 || frame >= h->last_batch) return ORBX_E_INVALID;
@@ -1698,7 +1789,7 @@ extern "C" orbx_status orbx_test_quadtree(orbx_handle *h, const int32_t *xys, in
 
 // ---- per-kernel event profiling ----
 static const char *k_prof_names[ORBX_K_COUNT] = { "k_resize_linear", "k_fast_cells", "k_quadtree", "k_blur7", "k_describe", "k_filter",
-                                                  "k_match_partial", "k_match_epilogue", "other" };
+                                                  "k_match_partial", "k_match_epilogue", "other", "k_fast_dense", "k_fast_nms", "k_fast_retry" };
 extern "C" int32_t orbx_profile_kernels(void) { return ORBX_K_COUNT; }
 extern "C" const char *orbx_profile_name(int32_t id) { return id >= 0 && id < ORBX_K_COUNT ? k_prof_names[id] : ""; }
 extern "C" void orbx_profile_enable(orbx_handle *h, int32_t on)

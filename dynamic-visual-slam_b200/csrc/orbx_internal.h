@@ -61,8 +61,18 @@ struct FrameGeom {
     LevelGeom lv[ORBX_MAX_LEVELS];
 };
 
+// dense FAST formulation (k_fast_dense.cu): score maps, corner lists and tiles of a frame geometry
+struct DenseLevel {
+    int map_off, map_pitch;      // score map of the level inside a frame's map slab (bytes); map column 0 = level column 4, map row 0 = level row 19
+    int cl_off, cl_cap;          // corner list (entries) inside a frame's corner slab
+    int ntx, nty;                // tiles of 128 x 16 detection pixels
+    int ncv, nrv, cellv_first;   // cells the reference runs: columns, rows, index of the level's first cell record
+};
+struct DenseGeom { DenseLevel lv[ORBX_MAX_LEVELS]; int ntiles; size_t map_bytes, cl_entries; };
+#define ORBX_FAST_DENSE_MIN_FRAMES 8
+
 enum { ORBX_K_RESIZE = 0, ORBX_K_FAST, ORBX_K_QUADTREE, ORBX_K_BLUR, ORBX_K_DESCRIBE, ORBX_K_FILTER,
-       ORBX_K_MATCH, ORBX_K_MATCH_EPI, ORBX_K_OTHER, ORBX_K_COUNT };
+       ORBX_K_MATCH, ORBX_K_MATCH_EPI, ORBX_K_OTHER, ORBX_K_FAST_DENSE, ORBX_K_FAST_NMS, ORBX_K_FAST_RETRY, ORBX_K_COUNT };
 
 struct ResizeTab { int32_t ofs; int16_t a0, a1; };   // 8 bytes
 
@@ -127,6 +137,17 @@ struct orbx_handle {
     int pyr_grid_cap;                                     // resident CTAs of the cooperative pyramid kernel (0 = not probed, -1 = unavailable)
     size_t smem_optin_max;                                // cudaDevAttrMaxSharedMemoryPerBlockOptin of the handle's device
     int fast_grid_cap; size_t fast_smem; int fast_tp;   // resident CTAs / dynamic smem / tile pitch of the persistent FAST kernel
+    // dense FAST formulation (k_fast_dense.cu), used for batches: ORBX_OPT_FAST_DENSE 0 = never, 1 (default) = batches of >= ORBX_FAST_DENSE_MIN_FRAMES, 2 = always
+    int opt_fast_dense; bool dense_ok; int dense_grid_cap; unsigned geo_serial;
+    DenseGeom dgeo;
+    void *d_dtiles; int dtile_cap;                        // tile records, 16 bytes each
+    uint8_t *d_smap; size_t smap_cap;                     // score maps [batch]
+    uint32_t *d_clist; size_t clist_cap;                  // corner lists [batch] (entries)
+    int32_t *d_dense_zero; size_t dense_zero_bytes;       // [work counter, retry count, 2 spare][corner counts][served-cell flags]: zeroed per launch
+    int32_t *d_retry;                                     // (frame, cell) items of the minThFAST retry launch
+    CUtensorMap tmap_dense[ORBX_MAX_LEVELS];              // box = 144 bytes x 22 rows
+    const uint8_t *tmap_dense_pyr; unsigned tmap_dense_serial;
+    const uint8_t *tmap_dense_l0; size_t tmap_dense_l0_step, tmap_dense_l0_fstride; int tmap_dense_l0_frames;
     // arenas, sized for max_width x max_height x max_batch
     uint8_t *d_pyr, *d_blur;     size_t pyr_slab, blur_slab;          // current per-frame strides
     size_t pyr_cap, blur_cap;                                          // arena bytes
@@ -233,6 +254,10 @@ int  launch_resize_level(orbx_handle *h, int level, int nframes, const uint8_t *
 void orbx_build_fast_cells(const FrameGeom &G, const std::vector<uint32_t> &ctab, std::vector<uint4> &out);   // k_fast.cu: 32-byte FAST cell records
 int  orbx_ensure_tmaps(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);
 int  launch_fast(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride);   // -1: TMA descriptor encode failed
+int  launch_fast_cells(orbx_handle *h, int nframes, const int32_t *d_items, const int32_t *d_nitems);   // k_fast.cu: every (frame, cell), or the listed ones at minThFAST
+int  launch_fast_dense(orbx_handle *h, int nframes);                                                    // k_fast_dense.cu
+void orbx_build_fast_dense(const FrameGeom &G, int cand_divisor, DenseGeom &D, std::vector<uint4> *tiles);
+bool orbx_encode_level(CUtensorMap *m, const uint8_t *base, size_t pitch, int rows, size_t fstride, int frames, int box_rows, int box_words);
 int  launch_quadtree(orbx_handle *h, int nframes);     // -1: the node table does not fit the shared-memory opt-in limit
 int  launch_quadtree_geo(orbx_handle *h, const FrameGeom *d_geo, int nlevels, int nframes, int node_cap, size_t cand_slab, int sel_slab);
 int  launch_cull(orbx_handle *h, const orbx_keypoint *d_kps, const uint8_t *d_desc, int n, const int32_t *d_mq, int nm, int max_new, float min_response,

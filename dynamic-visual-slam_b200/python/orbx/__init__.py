@@ -108,6 +108,8 @@ def load():
         "orbx_get_pyramid_level": (i32, [vp, i32, i32, vp, sz]),
         "orbx_get_blurred_level": (i32, [vp, i32, i32, vp, sz]),
         "orbx_get_candidates": (i32, [vp, i32, i32, vp, i32, vp]),
+        "orbx_get_fast_scores": (i32, [vp, i32, i32, vp, ct.c_size_t]),
+        "orbx_get_fast_edge_corners": (i32, [vp, i32, i32, vp, i32, vp]),
         "orbx_get_level_counts": (i32, [vp, i32, vp]),
         "orbx_harris_responses": (i32, [vp, i32, i32, vp, i32, i32, f32, vp]),
         "orbx_synth_gray_device": (i32, [vp, u32, i32, i32, i32, i32, vp, sz, sz]),
@@ -260,6 +262,10 @@ class ORBextractor:
     def set_match_mma(self, on=True):
         """ORBX_OPT_MATCH_MMA: 1 = int8 tensor-core GEMM for calls of >= 8 M pairs (default), 2 = always, 0 / False = always the POPC kernel."""
         self._check(self.L.orbx_set_option(self._h, 6, int(on)))
+
+    def set_fast_dense(self, mode=1):
+        """ORBX_OPT_FAST_DENSE: 0 = warp-per-cell FAST kernel (default), 1 = dense formulation for batches of >= 8 frames, 2 = for every call."""
+        self._check(self.L.orbx_set_option(self._h, 7, int(mode)))
 
     def set_fast_ctas(self, n):
         """ORBX_OPT_FAST_CTAS: resident FAST warps per SM in the overlapped schedule (0 = as many as fit)."""
@@ -507,6 +513,19 @@ class ORBextractor:
         out = np.zeros((h, w), np.uint8)
         self._check(self.L.orbx_get_blurred_level(self._h, frame, level, _p(out), out.strides[0]))
         return out
+
+    def fast_scores(self, level, frame=0):
+        """iniThFAST score map of a level after a dense FAST run: [h - 38, w - 38], level pixel (19 + c, 19 + r) at [r, c]."""
+        w, h = self.level_size(self._last_w, self._last_h, level)
+        out = np.zeros((max(h - 38, 1), max(w - 38, 1)), np.uint8)
+        self._check(self.L.orbx_get_fast_scores(self._h, frame, level, _p(out), out.strides[0]))
+        return out
+
+    def fast_edge_corners(self, level, frame=0, cap=1 << 20):
+        out = np.zeros((cap, 3), np.int32)
+        n = ct.c_int32()
+        self._check(self.L.orbx_get_fast_edge_corners(self._h, frame, level, _p(out), cap, ct.byref(n)))
+        return out[:n.value].copy()
 
     def candidates(self, level, frame=0, cap=1 << 18):
         out = np.zeros((cap, 3), np.int32)

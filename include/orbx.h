@@ -354,6 +354,13 @@ orbx_status orbx_pack_keyframe(orbx_handle *h, const orbx_keypoint *kps, const u
 
 /* ---- stage access for parity tests (the reference exposes mvImagePyramid publicly, ORBextractor.hpp:84) ----
  * Valid after an extract call, for frame slot `frame` of the last batch.  Host outputs.          */
+/* ORBX_OPT_FAST_DENSE runs: the iniThFAST score map of a level of frame slot `frame` of the last batch — cv::FAST's score buffer (S - 1 where
+ * the pixel is a corner at iniThFAST, else 0) over the level's detection range: (h - 38) rows x (w - 38) columns, level pixel (19 + c, 19 + r)
+ * at out[r][c].  Columns / rows past the cell grid read 0 (ORBextractor.cpp:811-816 skips those cells).                              */
+orbx_status orbx_get_fast_scores(orbx_handle *h, int32_t frame, int32_t level, uint8_t *out, size_t out_step);
+/* ORBX_OPT_FAST_DENSE runs: the corners the tile kernel left to the cross-tile NMS kernel (tile-edge corners, and every corner of a tile whose
+ * pre-test survivors exceeded its queue), as (x, y, score) like orbx_get_candidates.  Test / diagnosis access.                      */
+orbx_status orbx_get_fast_edge_corners(orbx_handle *h, int32_t frame, int32_t level, int32_t *out_xys, int32_t cap, int32_t *n_out);
 orbx_status orbx_get_pyramid_level(orbx_handle *h, int32_t frame, int32_t level, uint8_t *out, size_t out_step);
 orbx_status orbx_get_blurred_level(orbx_handle *h, int32_t frame, int32_t level, uint8_t *out, size_t out_step);
 /* Harris corner response (cv::ORB's HarrisResponses, block 7, k 0.04: the HARRIS_SCORE the reference's ORBextractor.hpp:48 names but
@@ -399,6 +406,13 @@ orbx_status orbx_synth_descriptors_device(orbx_handle *h, uint32_t seed, uint64_
  * least 8 M descriptor pairs (a single frame pair stays on the POPC kernel: less fixed latency); 2 = always the GEMM; 0 = always the LOP3 / POPC
  * kernel.  Same results bit for bit. */
 #define ORBX_OPT_MATCH_MMA 6
+/* ORBX_OPT_FAST_DENSE: the second FAST formulation (k_fast_dense.cu): whole-level tiles of 128 x 16 pixels scored at iniThFAST into a score map
+ * and a corner list, a per-corner NMS kernel restricted to the corner's cell, and a retry launch of the warp-per-cell kernel for the cells
+ * iniThFAST left empty.  0 (default) = the warp-per-cell kernel for every call; 1 = dense for batches of >= 8 frames; 2 = dense for every
+ * call.  Same keypoint sets (tests/test_gpu_fast_dense.py).  Off by default: measured 0.50 ms against 0.45 ms per 128 frames of 1280 x 720
+ * — its NMS kernel re-reads the 420 MB of score maps from HBM.  Switching it on allocates its arenas
+ * (0.8 GB at 128 frames of 1280 x 720): ORBX_E_CUDA if they cannot be had.                                                          */
+#define ORBX_OPT_FAST_DENSE 7
 orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t value);
 
 /* ---- utilities ---- */

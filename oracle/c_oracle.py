@@ -112,7 +112,7 @@ class COracle:
         if trace:
             sizes = [self.level_size(w, h, l) for l in range(self.nlevels)]
             total = sum(a * b for a, b in sizes)
-            cand_cap = 1 << 17
+            cand_cap = max(1 << 17, w * h // 4 + 1024)
             bufs = dict(pyr=np.zeros(total, np.uint8), blur=np.zeros(total, np.uint8),
                         cands=np.zeros((self.nlevels, cand_cap), CAND_DTYPE))
             tr = Trace()

@@ -850,6 +850,7 @@ int orc_extract(const orc_extractor *ex, const uint8_t *gray, int w, int h, size
     if (tr && tr->pyramid) memcpy(tr->pyramid, buf, total);
 
     int ccap = ex->nfeatures * 10 > 65536 ? ex->nfeatures * 10 : 65536;
+    if (ccap < w * h / 4 + 1024) ccap = w * h / 4 + 1024;                     /* noise frames: ~10 % of the pixels are FAST keypoints */
     orc_cand *cands = (orc_cand *)malloc(sizeof(orc_cand) * ccap);
     orc_cand *sel = (orc_cand *)malloc(sizeof(orc_cand) * ccap);
     int n_out = 0, overflow = 0;
