@@ -609,6 +609,46 @@ def main():
                  "ms_per_query_batch_nccl": ms_nccl, "transports_agree": same_transports,
                  "collective": "orbx_db_query_top2_sharded_device: per-shard kernel -> exchange of 32 KB/rank -> merge kernel, all on the handle's stream, "
                                "no host synchronisation; timed with CUDA events on that stream; exchange = peer-memory mailboxes (default) or ncclAllGather"}
+        # ---- the whole associateObservation call (descriptor gate + reprojection gate, backend.cpp:1064-1120) against the sharded database ----
+        prng = np.random.default_rng(99)
+        pos_all = np.stack([prng.uniform(-2, 2, ROWS), prng.uniform(-1.2, 1.2, ROWS), prng.uniform(0.4, 6.0, ROWS)], 1).astype(np.float32)
+        Rm, tv, Kc = np.eye(3), np.zeros(3), (615.3, 615.9, 640.2, 360.4)
+        pose = orbx.LandmarkDB.pose(Rm, tv, *Kc)
+        db.set_positions(pos_all[first_r:first_r + rows_r])
+        full.set_positions(pos_all)
+        src = (np.arange(n_true) * 512) % ROWS
+        uv = np.stack([Kc[0] * pos_all[src, 0].astype(np.float64) / pos_all[src, 2] + Kc[2], Kc[1] * pos_all[src, 1].astype(np.float64) / pos_all[src, 2] + Kc[3]], 1)
+        qpx_h = np.zeros((NQ, 2), np.float32)
+        qpx_h[:n_true] = (uv + prng.normal(0, 2.5, (n_true, 2))).astype(np.float32)          # some beyond the 5-px gate
+        qpx_h[n_true:] = prng.uniform(0, 700, (NQ - n_true, 2)).astype(np.float32)
+        qpx = torch.from_numpy(qpx_h).to(dev)
+        g_out = torch.zeros((NQ, 16), dtype=torch.uint8, device=dev)
+
+        def gated_step():
+            db.associate_sharded_device(comm, q.data_ptr(), qpx.data_ptr(), NQ, pose, g_out.data_ptr())
+
+        for _ in range(3):
+            gated_step()
+        barrier()
+        e0.record(stream)
+        for _ in range(K):
+            gated_step()
+        e1.record(stream)
+        barrier()
+        ms_g = max_over_ranks(e0.elapsed_time(e1) / K)
+        got_g = g_out.cpu().numpy().view(orbx.ASSOC_DTYPE).reshape(-1)
+        one = full.associate(qh, qpx_h, pose)                                                  # ONE unsharded database on this GPU
+        mism_g = int(sum_over_ranks(float((got_g.view(np.uint8).reshape(NQ, 16) != one.view(np.uint8).reshape(NQ, 16)).any(axis=1).sum())))
+        gated_cpu = None
+        if rank == 0:
+            QC = 48
+            widx, werr, wdist = co_all.associate(qh[:QC], qpx_h[:QC], frows.cpu().numpy(), pos_all, Rm, tv, *Kc)
+            okg = (got_g["landmark"][:QC] == widx) & ((widx < 0) | ((got_g["reproj_error"][:QC].view(np.uint64) == werr.view(np.uint64)) & (got_g["distance"][:QC] == wdist)))
+            gated_cpu = {"queries": QC, "mismatches": int((~okg).sum()), "against": "associateObservation restatement (oracle) over the full 1M-row database"}
+        assoc["gated"] = {"call": "orbx_db_associate_sharded_device (Hamming < 50, then smallest reprojection error < 5 px): per-shard kernel -> exchange of 32 KB/rank -> merge",
+                          "ms_per_query_batch": ms_g, "gpairs_per_s": NQ * ROWS / (ms_g * 1e-3) / 1e9, "associated": int((got_g["landmark"] >= 0).sum()),
+                          "mismatches_vs_unsharded": mism_g, "cpu_check": gated_cpu,
+                          "engine": "k_assoc_mma (int8 tensor-core GEMM, reprojection in the epilogue)" if not args.popc_match else "k_assoc_partial (POPC)"}
         comm.close(); db.close(); full.close()
         del drows, frows
 

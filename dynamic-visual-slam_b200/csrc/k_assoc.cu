@@ -76,6 +76,128 @@ __global__ void __launch_bounds__(AS_THREADS) k_assoc_partial(AssocParams P)
     }
 }
 
+// ---- tensor-core variant: the Hamming gate as the exact int8 GEMM of k_match_mma (k_match.cu), the reprojection test in its epilogue ----
+// popc(q ^ t) = popc(q) + popc(t) - 2 q.t with the descriptors unpacked to 0/1 bytes; a warp owns 16 observations (A fragments in registers),
+// the CTA stages 64 landmark rows at a time in fragment order.  Per pair the epilogue forms the packed key (distance << 22 | local row) with one
+// multiply-add; a key below (50 << 22) is a candidate (a handful per observation among a million rows) and only then the fp64 reprojection
+// of k_assoc_partial runs.  A quad's four lanes see different landmark columns of the same two observations, rows ascending per lane: their
+// results merge by (error, row) like the splits do.  Same partial layout, same merge kernel, bit-identical results.
+#define AM_CHUNK 64
+#define AM_KEY_SHIFT 22
+#define AM_DEAD (511u << AM_KEY_SHIFT)
+__device__ __forceinline__ void assoc_imma_16832(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+struct AssocBest { double e; int row; float d; };
+__device__ __forceinline__ void assoc_try(AssocBest &b, uint32_t key, uint32_t thr, int r0, const AssocParams &P, float qx, float qy)
+{
+    if (key < thr) {
+        const int row = r0 + (int)(key & ((1u << AM_KEY_SHIFT) - 1));
+        const double e = reproj_error(P.pos + (size_t)row * 3, P.pose, qx, qy);
+        if (e < P.max_err && e < b.e) { b.e = e; b.row = row; b.d = (float)(key >> AM_KEY_SHIFT); }     // a lane's rows ascend: ties keep the lowest row
+    }
+}
+__global__ void __launch_bounds__(256) k_assoc_mma(AssocParams P)
+{
+    __shared__ uint4 s_b[2][AM_CHUNK / 8][4][32];                 // [buffer][8-row group][16-byte piece][lane]
+    __shared__ uint32_t s_tk[2][AM_CHUNK];
+    const int r0 = blockIdx.y * P.rows_per_split, r1 = min(P.nt, r0 + P.rows_per_split);
+    const uint4 *tbase = reinterpret_cast<const uint4 *>(P.t);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int qa = blockIdx.x * AS_THREADS + warp * 16 + g, qb = qa + 8;
+    const uint32_t M1 = 0x01010101u;
+    uint32_t a[8][4], pqa, pqb;
+    {
+        const uint4 *pa = reinterpret_cast<const uint4 *>(P.q + (size_t)(qa < P.nq ? qa : 0) * ORBX_DESC_BYTES);
+        const uint4 *pb = reinterpret_cast<const uint4 *>(P.q + (size_t)(qb < P.nq ? qb : 0) * ORBX_DESC_BYTES);
+        const uint4 x0 = __ldg(pa), x1 = __ldg(pa + 1), y0 = __ldg(pb), y1 = __ldg(pb + 1);
+        const uint32_t wa[8] = { x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w }, wb[8] = { y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w };
+        int ca = 0, cb = 0;
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) {
+            a[ks][0] = (wa[ks] >> t) & M1; a[ks][1] = (wb[ks] >> t) & M1; a[ks][2] = (wa[ks] >> (t + 4)) & M1; a[ks][3] = (wb[ks] >> (t + 4)) & M1;
+            ca += __popc(wa[ks]); cb += __popc(wb[ks]);
+        }
+        pqa = (uint32_t)ca << AM_KEY_SHIFT; pqb = (uint32_t)cb << AM_KEY_SHIFT;
+    }
+    const float qax = qa < P.nq ? __ldg(P.qpx + 2 * qa) : 0.f, qay = qa < P.nq ? __ldg(P.qpx + 2 * qa + 1) : 0.f;
+    const float qbx = qb < P.nq ? __ldg(P.qpx + 2 * qb) : 0.f, qby = qb < P.nq ? __ldg(P.qpx + 2 * qb + 1) : 0.f;
+    // (float)d < max_dist for an integer d  <=>  d < ceil(max_dist); distances are at most 256
+    const int dlim = max(0, min(257, (int)ceilf(P.max_dist)));
+    const uint32_t thr = (uint32_t)dlim << AM_KEY_SHIFT;
+    AssocBest ba = { DBL_MAX, -1, 0.f }, bb = { DBL_MAX, -1, 0.f };
+    const int nrows = max(0, r1 - r0), nchunks = (nrows + AM_CHUNK - 1) / AM_CHUNK;
+    const int G_ = threadIdx.x >> 5, L_ = threadIdx.x & 31;
+    auto fetch = [&](int c, uint4 &x0, uint4 &x1) {
+        const int lrow = c * AM_CHUNK + G_ * 8 + (L_ >> 2);
+        x0 = make_uint4(0u, 0u, 0u, 0u); x1 = x0;
+        if (lrow < nrows) { const uint4 *p = tbase + (size_t)(r0 + lrow) * 2; x0 = __ldg(p); x1 = __ldg(p + 1); }
+    };
+    auto stage = [&](int c, const uint4 x0, const uint4 x1) {
+        const int G = G_, L = L_, lrow = c * AM_CHUNK + G * 8 + (L >> 2), tt = L & 3;
+        const uint32_t w[8] = { x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w };
+        uint32_t r[16];
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) { r[2 * ks] = (w[ks] >> tt) & M1; r[2 * ks + 1] = (w[ks] >> (tt + 4)) & M1; }
+        s_b[c & 1][G][0][L] = make_uint4(r[0], r[1], r[2], r[3]); s_b[c & 1][G][1][L] = make_uint4(r[4], r[5], r[6], r[7]);
+        s_b[c & 1][G][2][L] = make_uint4(r[8], r[9], r[10], r[11]); s_b[c & 1][G][3][L] = make_uint4(r[12], r[13], r[14], r[15]);
+        if (tt == 0) {
+            int pc = 0;
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++) pc += __popc(w[ks]);
+            s_tk[c & 1][G * 8 + (L >> 2)] = lrow < nrows ? (((uint32_t)pc << AM_KEY_SHIFT) | (uint32_t)lrow) : (AM_DEAD | (uint32_t)(lrow & ((1 << AM_KEY_SHIFT) - 1)));
+        }
+    };
+    uint4 nx0, nx1;
+    if (nchunks > 0) { fetch(0, nx0, nx1); stage(0, nx0, nx1); }
+    __syncthreads();
+    for (int c = 0; c < nchunks; c++) {
+        if (c + 1 < nchunks) fetch(c + 1, nx0, nx1);            // in flight during this chunk's tiles
+        const int groups = min(AM_CHUNK / 8, (nrows - c * AM_CHUNK + 7) >> 3);
+        for (int G = 0; G < groups; G++) {
+            const uint4 b0 = s_b[c & 1][G][0][lane], b1 = s_b[c & 1][G][1][lane], b2 = s_b[c & 1][G][2][lane], b3 = s_b[c & 1][G][3][lane];
+            int acc[4] = { 0, 0, 0, 0 };
+            assoc_imma_16832(acc, a[0], b0.x, b0.y); assoc_imma_16832(acc, a[1], b0.z, b0.w);
+            assoc_imma_16832(acc, a[2], b1.x, b1.y); assoc_imma_16832(acc, a[3], b1.z, b1.w);
+            assoc_imma_16832(acc, a[4], b2.x, b2.y); assoc_imma_16832(acc, a[5], b2.z, b2.w);
+            assoc_imma_16832(acc, a[6], b3.x, b3.y); assoc_imma_16832(acc, a[7], b3.z, b3.w);
+            const uint2 tk = *reinterpret_cast<const uint2 *>(&s_tk[c & 1][G * 8 + 2 * t]);      // columns 2t and 2t + 1 of this tile
+            const uint32_t two23 = 1u << (AM_KEY_SHIFT + 1);
+            const uint32_t k00 = pqa + tk.x - (uint32_t)acc[0] * two23, k01 = pqa + tk.y - (uint32_t)acc[1] * two23;
+            const uint32_t k10 = pqb + tk.x - (uint32_t)acc[2] * two23, k11 = pqb + tk.y - (uint32_t)acc[3] * two23;
+            if (min(min(k00, k01), min(k10, k11)) < thr) {                                          // rare: a descriptor within the gate
+                assoc_try(ba, k00, thr, r0, P, qax, qay); assoc_try(ba, k01, thr, r0, P, qax, qay);
+                assoc_try(bb, k10, thr, r0, P, qbx, qby); assoc_try(bb, k11, thr, r0, P, qbx, qby);
+            }
+        }
+        if (c + 1 < nchunks) stage(c + 1, nx0, nx1);
+        __syncthreads();
+    }
+    // the four lanes of a quad hold different landmark columns of the same two observations: lexicographic (error, row) minimum
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+        const double ea = __shfl_xor_sync(0xffffffffu, ba.e, o), eb = __shfl_xor_sync(0xffffffffu, bb.e, o);
+        const int ra = __shfl_xor_sync(0xffffffffu, ba.row, o), rb = __shfl_xor_sync(0xffffffffu, bb.row, o);
+        const float da = __shfl_xor_sync(0xffffffffu, ba.d, o), db = __shfl_xor_sync(0xffffffffu, bb.d, o);
+        if (ra >= 0 && (ba.row < 0 || ea < ba.e || (ea == ba.e && ra < ba.row))) { ba.e = ea; ba.row = ra; ba.d = da; }
+        if (rb >= 0 && (bb.row < 0 || eb < bb.e || (eb == bb.e && rb < bb.row))) { bb.e = eb; bb.row = rb; bb.d = db; }
+    }
+    if (t == 0) {
+        if (qa < P.nq) {
+            orbx_assoc r;
+            r.reproj_error = ba.e; r.landmark = ba.row < 0 ? -1 : (int32_t)(P.row_base + (uint32_t)ba.row); r.distance = ba.d;
+            P.part[(size_t)blockIdx.y * P.nq + qa] = r;
+        }
+        if (qb < P.nq) {
+            orbx_assoc r;
+            r.reproj_error = bb.e; r.landmark = bb.row < 0 ? -1 : (int32_t)(P.row_base + (uint32_t)bb.row); r.distance = bb.d;
+            P.part[(size_t)blockIdx.y * P.nq + qb] = r;
+        }
+    }
+}
+
 // lexicographic (error, landmark row) minimum over `nparts` partial results laid out [part][nq]
 __global__ void k_assoc_merge(const orbx_assoc *parts, size_t stride, int nparts, int nq, orbx_assoc *out)
 {
@@ -116,7 +238,9 @@ int launch_assoc(orbx_handle *h, const uint8_t *d_q, const float *d_qpx, int nq,
     dim3 grid(qtiles, (unsigned)split);
     {
         ProfScope ps(h, ORBX_K_OTHER);
-        k_assoc_partial<<<grid, AS_THREADS, 0, h->stream>>>(P);
+        // the int8 tensor-core GEMM once there is enough work to amortise its staging (ORBX_OPT_MATCH_MMA, as for the matcher)
+        if (h->opt_match_mma == 2 || (h->opt_match_mma && (double)nq * (double)nt >= 8e6)) k_assoc_mma<<<grid, 256, 0, h->stream>>>(P);
+        else k_assoc_partial<<<grid, AS_THREADS, 0, h->stream>>>(P);
     }
     ProfScope ps(h, ORBX_K_OTHER);
     k_assoc_merge<<<(nq + 127) / 128, 128, 0, h->stream>>>((const orbx_assoc *)h->d_mpart, (size_t)nq, (int)split, nq, d_out);

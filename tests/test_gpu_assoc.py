@@ -43,10 +43,13 @@ def _assert_assoc(got, want):
     assert np.array_equal(got["distance"][sel], dist[sel])
 
 
-def test_associate_matches_reference_semantics(built, oracle):
+@pytest.mark.parametrize("engine", [0, 2])
+def test_associate_matches_reference_semantics(built, oracle, engine):
+    """engine: ORBX_OPT_MATCH_MMA 0 = k_assoc_partial (POPC), 2 = k_assoc_mma (int8 tensor-core GEMM + the same reprojection epilogue)"""
     import orbx
-    rows, pos, q, qpx, R, t, K = _scene(oracle, 20000, 700, 5)
+    rows, pos, q, qpx, R, t, K = _scene(oracle, 20000 + 37 * engine, 700 + engine, 5)      # row / query counts off the 64 / 16 tile sizes
     ex = orbx.ORBextractor(max_width=320, max_height=240)
+    ex.set_match_mma(engine)
     db = orbx.LandmarkDB(ex, 32768)
     try:
         db.append(rows)
@@ -60,12 +63,14 @@ def test_associate_matches_reference_semantics(built, oracle):
         db.close(); ex.close()
 
 
-def test_associate_sharded_merge(built, oracle):
+@pytest.mark.parametrize("engine", [0, 2])
+def test_associate_sharded_merge(built, oracle, engine):
     """Two shards (global row ranges) merged by orbx_merge_assoc_device == one unsharded database."""
     import torch
     import orbx
     rows, pos, q, qpx, R, t, K = _scene(oracle, 12001, 300, 9)
     ex = orbx.ORBextractor(max_width=320, max_height=240)
+    ex.set_match_mma(engine)
     cut = 7000
     dbs = [orbx.LandmarkDB(ex, 8192, first_index=0), orbx.LandmarkDB(ex, 8192, first_index=cut)]
     try:
