@@ -263,7 +263,7 @@ def main():
     ap.add_argument("--no-pdl", action="store_true", help="plain stream order instead of programmatic dependent launch (ORBX_OPT_PDL = 0)")
     ap.add_argument("--fast-ctas", type=int, default=0, help="resident FAST warps per SM in the overlapped schedule (0 = library default)")
     ap.add_argument("--overlap", action="store_true", help="two staggered half-batches on two streams (ORBX_OPT_OVERLAP = 1; measured slower than one chain)")
-    ap.add_argument("--fast-dense", action="store_true", help="the dense FAST formulation (ORBX_OPT_FAST_DENSE = 1) instead of the warp-per-cell kernel")
+    ap.add_argument("--fast-dense", type=int, default=0, help="ORBX_OPT_FAST_DENSE: 1 = the dense FAST formulation for batches, 3 = the same with the NMS inside the tile kernel")
     ap.add_argument("--popc-match", action="store_true", help="the LOP3/POPC matcher instead of the int8 tensor-core GEMM (ORBX_OPT_MATCH_MMA = 0)")
     ap.add_argument("--host-chunk", type=int, default=0, help="frames per pipeline chunk of the host-buffer call (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -306,7 +306,7 @@ def main():
     if args.popc_match:
         ex.set_match_mma(False)
     if args.fast_dense:
-        ex.set_fast_dense(1)
+        ex.set_fast_dense(args.fast_dense)
     L, hnd = ex.L, ex.handle
     stream = torch.cuda.ExternalStream(ex.stream, device=dev)
 

@@ -38,29 +38,152 @@
 #define FN_THREADS 256
 #define FN_BLOCKS_X 12
 
+#ifndef FD_NMS_ITEMS
+#define FD_NMS_ITEMS 128          // NMS work items per frame (each takes every 128th group of 128 corners of every level)
+#endif
+#ifndef FD_NMS_LAG
+#define FD_NMS_LAG 8              // the NMS items of frame f follow the tile items of frame f + 8 (the resident warps span ~2.3 frames of items and publish a tile one
+                                  // tile late): its tiles are done when they are drawn, its maps (10 frames x 3.3 MB in flight) still in L2
+#endif
+
 struct DenseLevelDev { int map_off, map_pitch, cl_off, cl_cap; };
 struct DenseParams {
     uint32_t *clist; size_t clist_slab;          // corner lists, entries per frame
     int32_t *ncorner;                            // [frame][level]
     uint8_t *smap; size_t smap_slab;             // score maps, bytes per frame
-    const uint4 *tiles; int ntiles, nitems; float inv_ntiles;
+    const uint4 *tiles; int ntiles, nframes, nitems;   // nitems: tile items and NMS items (dense_item)
+    float inv_per;                               // 1 / (ntiles + FD_NMS_ITEMS)
     int th, nlevels;
     int32_t *status, *work;
+    int32_t *done;                               // [frame]: tiles whose score map and corners are in global memory
     DenseLevelDev lv[ORBX_MAX_LEVELS];
 };
+
+// ---- strict 3x3 NMS inside the corner's cell (cv::FAST's NMS, which the reference runs per cell ROI) ----
+struct NmsLevel {
+    int map_off, map_pitch, cl_off, cl_cap;
+    int x1, y1, wcell, hcell, ncv, nrv, cellv_first, cand_cap;      // x1, y1: first column / row past the last cell's detection area
+    unsigned mw, mh;                                                  // ceil(2^32 / wcell), ceil(2^32 / hcell): exact quotients by __umulhi for coordinates < 2^16
+    unsigned cand_off;
+};
+struct NmsParams {
+    const uint32_t *clist; size_t clist_slab; const int32_t *ncorner;
+    const uint8_t *smap; size_t smap_slab;
+    uint32_t *cand; size_t cand_slab; int32_t *ncand;
+    uint8_t *found; int ncells, nlevels;
+    int32_t *status;
+    NmsLevel lv[ORBX_MAX_LEVELS];
+};
+
+// The calling warp takes the groups base0, base0 + stride, ... of the (frame, level) corner list; a lane takes FOUR consecutive entries
+// (one 16-byte load) and has their 32 neighbour loads in flight together: the work is a chain of dependent global round trips
+// (entry -> neighbours -> slot atomic -> store), four corners per trip instead of one.  n = entries in the list.
+__device__ __forceinline__ void nms_groups(const NmsParams &P, int f, int level, int n, int base0, int stride, int lane)
+{
+    const NmsLevel &L = P.lv[level];
+    const uint4 *list4 = reinterpret_cast<const uint4 *>(P.clist + (size_t)f * P.clist_slab + L.cl_off);   // list starts are multiples of 64 entries
+    const uint8_t *map = P.smap + (size_t)f * P.smap_slab + L.map_off;
+    uint32_t *cdst = P.cand + (size_t)f * P.cand_slab + L.cand_off;
+    int32_t *ccnt = &P.ncand[f * P.nlevels + level];
+    uint8_t *found = P.found + (size_t)f * P.ncells + L.cellv_first;
+    const int pitch = L.map_pitch, wcell = L.wcell, hcell = L.hcell;
+    for (int base = base0; 4 * base < n; base += stride) {
+        const int g = base + lane;                                                 // group of four entries
+        uint4 c4 = make_uint4(0, 0, 0, 0);
+        if (4 * g < n) c4 = list4[g];
+        const uint32_t cs[4] = { c4.x, c4.y, c4.z, c4.w };
+        int nbr[4][8], ctr[4], cell[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t c = cs[k];
+            const bool act = 4 * g + k < n;
+            const int xr = act ? orbx_px(c) - 3 : 0, yr = act ? orbx_py(c) - 3 : 0;                     // relative to the first detection column / row (level 19)
+            const int cj = (int)__umulhi((unsigned)xr, L.mw), ci = (int)__umulhi((unsigned)yr, L.mh);
+            // the cell's detection area — ORBextractor.cpp:805-822 minus cv::FAST's 3-px margin; the corner is inside it by construction
+            const int cx0 = cj * wcell, cx1 = min(cx0 + wcell, L.x1), cy0 = ci * hcell, cy1 = min(cy0 + hcell, L.y1);
+            const uint8_t *p = map + yr * pitch + (xr + (ORBX_BORDER + 3 - 4));
+            const bool xl = act && xr > cx0, xh = act && xr + 1 < cx1, yl = act && yr > cy0, yh = act && yr + 1 < cy1;
+            nbr[k][0] = yl ? p[-pitch] : 0;        nbr[k][1] = (yl && xl) ? p[-pitch - 1] : 0;  nbr[k][2] = (yl && xh) ? p[-pitch + 1] : 0;
+            nbr[k][3] = xl ? p[-1] : 0;            nbr[k][4] = xh ? p[1] : 0;
+            nbr[k][5] = yh ? p[pitch] : 0;         nbr[k][6] = (yh && xl) ? p[pitch - 1] : 0;   nbr[k][7] = (yh && xh) ? p[pitch + 1] : 0;
+            ctr[k] = act ? orbx_ps(c) : 0;                                       // S - 1 >= 1 for a listed corner
+            cell[k] = ci * L.ncv + cj;
+        }
+        unsigned keep = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int m = max(max(max(nbr[k][0], nbr[k][1]), max(nbr[k][2], nbr[k][3])), max(max(nbr[k][4], nbr[k][5]), max(nbr[k][6], nbr[k][7])));
+            if (ctr[k] > m) { keep |= 1u << k; found[cell[k]] = 1; }             // strict maximum; the cell is served: no minThFAST retry — ORBextractor.cpp:843-846
+        }
+        const int cnt = __popc(keep);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {
+            int pos = 0;
+            if (lane == 31) pos = atomicAdd(ccnt, total);
+            pos = __shfl_sync(0xffffffffu, pos, 31) + incl - cnt;
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (keep & (1u << k)) {
+                if (pos < L.cand_cap) cdst[pos] = cs[k];
+                else atomicOr(P.status, ORBX_DS_CAND_OVERFLOW);
+                pos++;
+            }
+        }
+    }
+}
+
+// stand-alone NMS pass (FUSE = false): grid (blocks, frames, levels)
+__global__ void __launch_bounds__(FN_THREADS) k_fast_nms(NmsParams P)
+{
+    ORBX_PDL_ENTRY();
+    const int f = blockIdx.y, level = blockIdx.z;
+    const int n = min(P.ncorner[f * P.nlevels + level], P.lv[level].cl_cap);     // plain loads: written by the previous kernel of the stream
+    if ((int)(blockIdx.x * FN_THREADS * 4) >= n) return;
+    nms_groups(P, f, level, n, blockIdx.x * FN_THREADS + (threadIdx.x & ~31), gridDim.x * FN_THREADS, threadIdx.x & 31);
+}
 
 // tile record (host-built, frame-independent):
 //   x = box word column | box row << 16          y = level | vx0 << 4 | vx1 << 12 | vh << 20   (valid detection bytes [vx0, vx1) of the 128, valid rows)
 //   z = byte offset of the tile in the frame's score-map slab          w = (x - 16 of detection byte 0) & 0xFFFF | (y - 16 of detection row 0) << 16
-__device__ __forceinline__ void dense_split(const DenseParams &P, int item, int &f, int &t)
+//
+// Work items of k_fast_dense.  FUSE = false (default): item = frame * ntiles + tile, the NMS is the next kernel.  FUSE = true (ORBX_OPT_FAST_DENSE = 3,
+// an experiment kept with its test): as a second kernel the NMS re-reads every score map of the batch from HBM (420 MB per 128 frames of
+// 1280 x 720, 0.13 ms), so here it runs inside the tile kernel while a frame's map is still in L2: the item sequence is F blocks of [ntiles tile
+// items of frame q | FD_NMS_ITEMS NMS items of frame q - FD_NMS_LAG], then the NMS items of the last FD_NMS_LAG frames.  A warp that draws an NMS
+// item waits until every tile of that frame has published its map and corners (done[f], a release / acquire counter); tile items never wait, a
+// warp publishes its own deferred corner list before it waits and holds no drawn tile item while it waits, so the waits neither deadlock nor
+// chain.  Measured: same results, but 0.565 ms against 0.32 + 0.13 ms for the two kernels — the NMS is a chain of dependent global round
+// trips (entry -> 32 neighbour bytes -> slot atomic -> store, ~8 us per 128 corners on a loaded SM) whatever memory answers them, and inside the
+// tile kernel each such chain occupies one of the SM's 24 one-warp CTAs instead of one of 40 cheap warps of k_fast_nms.
+enum { DI_TILE = 0, DI_NMS = 1, DI_SKIP = 2, DI_END = 3 };
+template <bool FUSE> __device__ __forceinline__ int dense_item(const DenseParams &P, int idx, int &f, int &t)
 {
-    f = __float2int_rz(((float)item + 0.5f) * P.inv_ntiles);
-    t = item - f * P.ntiles;
-    if (t < 0) { f--; t += P.ntiles; }
-    else if (t >= P.ntiles) { f++; t -= P.ntiles; }
+    f = 0; t = 0;
+    if (idx >= P.nitems) return DI_END;
+    if (!FUSE) {
+        f = __float2int_rz(((float)idx + 0.5f) * P.inv_per);                   // inv_per = 1 / ntiles here
+        t = idx - f * P.ntiles;
+        if (t < 0) { f--; t += P.ntiles; }
+        else if (t >= P.ntiles) { f++; t -= P.ntiles; }
+        return DI_TILE;
+    }
+    const int per = P.ntiles + FD_NMS_ITEMS, body = P.nframes * per;
+    if (idx >= body) {                                                          // tail: NMS of the last frames
+        const int rem = idx - body, f0 = max(P.nframes - FD_NMS_LAG, 0);
+        f = f0 + rem / FD_NMS_ITEMS; t = rem % FD_NMS_ITEMS;
+        return DI_NMS;
+    }
+    int q = __float2int_rz(((float)idx + 0.5f) * P.inv_per), r = idx - q * per;
+    if (r < 0) { q--; r += per; }
+    else if (r >= per) { q++; r -= per; }
+    if (r < P.ntiles) { f = q; t = r; return DI_TILE; }
+    f = q - FD_NMS_LAG; t = r - P.ntiles;
+    return f >= 0 ? DI_NMS : DI_SKIP;
 }
 
-__global__ void __launch_bounds__(32, FD_MINB) k_fast_dense(const __grid_constant__ LevelMaps M, DenseParams P)
+template <bool FUSE> __global__ void __launch_bounds__(32, FD_MINB) k_fast_dense(const __grid_constant__ LevelMaps M, const __grid_constant__ DenseParams P, const __grid_constant__ NmsParams Q)
 {
     extern __shared__ __align__(128) uint8_t s_raw[];
     __shared__ __align__(8) uint64_t s_full;
@@ -92,34 +215,81 @@ __global__ void __launch_bounds__(32, FD_MINB) k_fast_dense(const __grid_constan
     // the lane's share of the redistributed flags: bytes lane + 32 m of the 256 flag bytes = column (lane & 3) of the word columns
     // (lane >> 3) + 4 m, rows 8 * ((lane >> 2) & 1) ...: pre-test survivors come in blobs, a blob's bytes go to different lanes
     const int walk_base = (3 + 8 * ((lane >> 2) & 1)) * FD_TP + 4 + 4 * (lane >> 3) + (lane & 3);
-    int it_n = 0, nres = 0, buf = 0;
-    int pn = 0, pbase = 0, pcap = 0;
+    int ntma = 0, nres = 0, buf = 0;
+    // the previous tile: its corner list waits in shared memory for the counter atomic that reserved its slots
+    bool have_prev = false;
+    int pn = 0, pbase = 0, pcap = 0, pf = 0;
     uint32_t *pdst = nullptr;
-    int f, ti, nf = 0, nt = 0;
-    dense_split(P, blockIdx.x, f, ti);
+    auto flush_prev = [&]() {                                       // publish the previous tile's corners, then count the tile as done
+        if (!have_prev) return;
+        if (pn) fast_write_out(s_res + (buf ^ 1) * FD_RES, pn, __shfl_sync(0xffffffffu, pbase, 0), pdst, pcap, P.status, lane);
+        if (FUSE) {
+            __syncwarp();                                           // every lane's map and list stores are ordered before lane 0's fence,
+            if (lane == 0) { __threadfence(); atomicAdd(&P.done[pf], 1); }      // which is cumulative: one release per tile (32 fences cost 4x the tile)
+        }
+        have_prev = false; pn = 0;
+    };
+    auto draw = [&]() {                                             // synchronous draw of the next item index
+        int v = 0;
+        if (lane == 0) v = atomicAdd(P.work, 1) + (int)gridDim.x;
+        return __shfl_sync(0xffffffffu, v, 0);
+    };
+    auto do_nms = [&](int f, int j) {                               // NMS item j of frame f: every FD_NMS_ITEMS-th group of 128 corners of every level
+        if (lane == 0) {
+            int spins = 0;
+            while (*reinterpret_cast<volatile int32_t *>(&P.done[f]) < P.ntiles) {
+                __nanosleep(256);
+                if (++spins > (1 << 22)) { atomicOr(P.status, ORBX_DS_INTERNAL); break; }       // ~1 s; never seen — a wait without a bound would take the GPU with it
+            }
+        }
+        if (lane == 0) __threadfence();                             // acquire: the frame's maps and lists are visible to the warp after the barrier
+        __syncwarp();
+        int nl = 0;                                                 // lane l holds level l's corner count: one round trip for all levels
+        if (lane < P.nlevels) nl = min(*reinterpret_cast<volatile const int32_t *>(&Q.ncorner[f * Q.nlevels + lane]), Q.lv[lane].cl_cap);
+        for (int level = 0; level < P.nlevels; level++) {
+            const int n = __shfl_sync(0xffffffffu, nl, level);
+            nms_groups(Q, f, level, n, j * 32, FD_NMS_ITEMS * 32, lane);
+        }
+    };
+    // acquire(): handle the items that are not tiles until `cur` is a tile item (true) or the items are exhausted (false).  A warp that waits
+    // in an NMS item must not sit on a drawn tile item (frames would complete late and the waits would chain): `nxt` is drawn only when needed
+    // (-1 = not drawn), and never ahead of an NMS item.
+    int cur = blockIdx.x, nxt = -1, f = 0, ti = 0;
+    auto acquire = [&]() {
+        for (;;) {
+            const int type = dense_item<FUSE>(P, cur, f, ti);
+            if (type == DI_TILE) return true;
+            if (type == DI_END) return false;
+            if (type == DI_NMS) { flush_prev(); do_nms(f, ti); }
+            if (nxt < 0) nxt = draw();
+            cur = nxt; nxt = -1;
+        }
+    };
+    if (!acquire()) { flush_prev(); return; }
     uint4 T = __ldg(P.tiles + ti);
-    int nxt = 0;
     if (lane == 0) {
         mbar_expect_tx(&s_full, FD_BOX_ROWS * FD_TP);
         tma_load_3d(s_img, &M.m[T.y & 15u], (int)(T.x & 0xFFFFu), (int)(T.x >> 16), f, &s_full);
-        nxt = atomicAdd(P.work, 1) + (int)gridDim.x;
     }
-    nxt = __shfl_sync(0xffffffffu, nxt, 0);
-    dense_split(P, nxt, nf, nt);
-    for (;; it_n++) {
-        const bool has_next = nxt < P.nitems;
-        int drawn = 0;
+    for (;;) {
+        // the draw for the item after next flies during the sweep (unless the next item is an NMS item: see acquire); the next item, if it is a
+        // tile, is prefetched into L2
+        if (nxt < 0) nxt = draw();
+        int drawn = -1, nf = 0, nt = 0;
+        const int next_type = dense_item<FUSE>(P, nxt, nf, nt);
+        const bool next_tile = next_type == DI_TILE;
+        if (next_type != DI_NMS && lane == 0) drawn = atomicAdd(P.work, 1) + (int)gridDim.x;     // consumed at the bottom of the loop
         uint4 NT = make_uint4(0, 0, 0, 0);
-        if (has_next) NT = __ldg(P.tiles + nt);
-        if (has_next && lane == 0) drawn = atomicAdd(P.work, 1) + (int)gridDim.x;         // consumed at the bottom of the loop
+        if (next_tile) NT = __ldg(P.tiles + nt);
         const int level = (int)(T.y & 15u);
         const int xb = (int)(int16_t)(T.w & 0xFFFFu), yb = (int)(T.w >> 16);
         const DenseLevelDev LV = P.lv[level];
         uint32_t *res = s_res + buf * FD_RES;
         uint32_t *gdst = P.clist + (size_t)f * P.clist_slab + LV.cl_off;
         int32_t *gcnt = &P.ncorner[f * P.nlevels + level];
-        mbar_wait(&s_full, (uint32_t)(it_n & 1));
-        if (has_next && lane == 0) tma_prefetch_3d(&M.m[NT.y & 15u], (int)(NT.x & 0xFFFFu), (int)(NT.x >> 16), nf);   // next window -> L2
+        mbar_wait(&s_full, (uint32_t)(ntma & 1));
+        ntma++;
+        if (next_tile && lane == 0) tma_prefetch_3d(&M.m[NT.y & 15u], (int)(NT.x & 0xFFFFu), (int)(NT.x >> 16), nf);   // next window -> L2
         __syncwarp();
 
         // ---- packed sweep: lane = word column (4 pixels) x 16 rows ----
@@ -197,7 +367,7 @@ __global__ void __launch_bounds__(32, FD_MINB) k_fast_dense(const __grid_constan
             if (total <= FD_WQ) break;
         }
         // every lane is done with the tile: load the next one, then move the score tile out (and zero it for the next tile)
-        if (has_next && lane == 0) {
+        if (next_tile && lane == 0) {
             mbar_expect_tx(&s_full, FD_BOX_ROWS * FD_TP);
             tma_load_3d(s_img, &M.m[NT.y & 15u], (int)(NT.x & 0xFFFFu), (int)(NT.x >> 16), nf, &s_full);
         }
@@ -212,94 +382,20 @@ __global__ void __launch_bounds__(32, FD_MINB) k_fast_dense(const __grid_constan
             }
         }
         // write out the previous tile's corners (their counter atomic was issued one tile ago), then open this tile's
-        if (pn) fast_write_out(s_res + (buf ^ 1) * FD_RES, pn, __shfl_sync(0xffffffffu, pbase, 0), pdst, pcap, P.status, lane);
-        pn = nres;
+        flush_prev();
+        have_prev = true; pf = f; pn = nres;
         if (nres) { if (lane == 0) pbase = atomicAdd(gcnt, nres); pdst = gdst; pcap = LV.cl_cap; }
         buf ^= 1; nres = 0;
-        if (!has_next) break;
-        f = nf; ti = nt; T = NT;
-        nxt = __shfl_sync(0xffffffffu, drawn, 0);
-        dense_split(P, nxt, nf, nt);
-    }
-    if (pn) fast_write_out(s_res + (buf ^ 1) * FD_RES, pn, __shfl_sync(0xffffffffu, pbase, 0), pdst, pcap, P.status, lane);
-}
-
-// ---- step 2: strict 3x3 NMS inside the corner's cell (cv::FAST's NMS, which the reference runs per cell ROI), one thread per corner ----
-struct NmsLevel {
-    int map_off, map_pitch, cl_off, cl_cap;
-    int x1, y1, wcell, hcell, ncv, nrv, cellv_first, cand_cap;      // x1, y1: first column / row past the last cell's detection area
-    unsigned mw, mh;                                                  // ceil(2^32 / wcell), ceil(2^32 / hcell): exact quotients by __umulhi for coordinates < 2^16
-    unsigned cand_off;
-};
-struct NmsParams {
-    const uint32_t *clist; size_t clist_slab; const int32_t *ncorner;
-    const uint8_t *smap; size_t smap_slab;
-    uint32_t *cand; size_t cand_slab; int32_t *ncand;
-    uint8_t *found; int ncells, nlevels;
-    int32_t *status;
-    NmsLevel lv[ORBX_MAX_LEVELS];
-};
-
-// A thread takes FOUR consecutive list entries (one 16-byte load) and has their 32 neighbour loads in flight together: the kernel is a
-// chain of dependent global round trips (entry -> neighbours -> slot atomic -> store), four corners per trip instead of one.
-__global__ void __launch_bounds__(FN_THREADS) k_fast_nms(NmsParams P)
-{
-    ORBX_PDL_ENTRY();
-    const int f = blockIdx.y, level = blockIdx.z, lane = threadIdx.x & 31;
-    const NmsLevel &L = P.lv[level];
-    const int n = min(P.ncorner[f * P.nlevels + level], L.cl_cap);              // plain loads: written by the previous kernel of the stream
-    if ((int)(blockIdx.x * FN_THREADS * 4) >= n) return;
-    const uint4 *list4 = reinterpret_cast<const uint4 *>(P.clist + (size_t)f * P.clist_slab + L.cl_off);   // list starts are multiples of 64 entries
-    const uint8_t *map = P.smap + (size_t)f * P.smap_slab + L.map_off;
-    uint32_t *cdst = P.cand + (size_t)f * P.cand_slab + L.cand_off;
-    int32_t *ccnt = &P.ncand[f * P.nlevels + level];
-    uint8_t *found = P.found + (size_t)f * P.ncells + L.cellv_first;
-    const int pitch = L.map_pitch, wcell = L.wcell, hcell = L.hcell;
-    for (int base = blockIdx.x * FN_THREADS; 4 * base < n; base += gridDim.x * FN_THREADS) {
-        const int g = base + threadIdx.x;                                          // group of four entries
-        uint4 c4 = make_uint4(0, 0, 0, 0);
-        if (4 * g < n) c4 = list4[g];
-        const uint32_t cs[4] = { c4.x, c4.y, c4.z, c4.w };
-        int nbr[4][8], ctr[4], cell[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t c = cs[k];
-            const bool act = 4 * g + k < n;
-            const int xr = act ? orbx_px(c) - 3 : 0, yr = act ? orbx_py(c) - 3 : 0;                     // relative to the first detection column / row (level 19)
-            const int cj = (int)__umulhi((unsigned)xr, L.mw), ci = (int)__umulhi((unsigned)yr, L.mh);
-            // the cell's detection area — ORBextractor.cpp:805-822 minus cv::FAST's 3-px margin; the corner is inside it by construction
-            const int cx0 = cj * wcell, cx1 = min(cx0 + wcell, L.x1), cy0 = ci * hcell, cy1 = min(cy0 + hcell, L.y1);
-            const uint8_t *p = map + yr * pitch + (xr + (ORBX_BORDER + 3 - 4));
-            const bool xl = act && xr > cx0, xh = act && xr + 1 < cx1, yl = act && yr > cy0, yh = act && yr + 1 < cy1;
-            nbr[k][0] = yl ? p[-pitch] : 0;        nbr[k][1] = (yl && xl) ? p[-pitch - 1] : 0;  nbr[k][2] = (yl && xh) ? p[-pitch + 1] : 0;
-            nbr[k][3] = xl ? p[-1] : 0;            nbr[k][4] = xh ? p[1] : 0;
-            nbr[k][5] = yh ? p[pitch] : 0;         nbr[k][6] = (yh && xl) ? p[pitch - 1] : 0;   nbr[k][7] = (yh && xh) ? p[pitch + 1] : 0;
-            ctr[k] = act ? orbx_ps(c) : 0;                                       // S - 1 >= 1 for a listed corner
-            cell[k] = ci * L.ncv + cj;
-        }
-        unsigned keep = 0u;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int m = max(max(max(nbr[k][0], nbr[k][1]), max(nbr[k][2], nbr[k][3])), max(max(nbr[k][4], nbr[k][5]), max(nbr[k][6], nbr[k][7])));
-            if (ctr[k] > m) { keep |= 1u << k; found[cell[k]] = 1; }             // strict maximum; the cell is served: no minThFAST retry — ORBextractor.cpp:843-846
-        }
-        const int cnt = __popc(keep);
-        int incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total) {
-            int pos = 0;
-            if (lane == 31) pos = atomicAdd(ccnt, total);
-            pos = __shfl_sync(0xffffffffu, pos, 31) + incl - cnt;
-#pragma unroll
-            for (int k = 0; k < 4; k++) if (keep & (1u << k)) {
-                if (pos < L.cand_cap) cdst[pos] = cs[k];
-                else atomicOr(P.status, ORBX_DS_CAND_OVERFLOW);
-                pos++;
-            }
+        cur = nxt; nxt = __shfl_sync(0xffffffffu, drawn, 0);
+        if (next_tile) { f = nf; ti = nt; T = NT; continue; }
+        if (!acquire()) break;                                                   // NMS items (and the end) are handled there
+        T = __ldg(P.tiles + ti);
+        if (lane == 0) {
+            mbar_expect_tx(&s_full, FD_BOX_ROWS * FD_TP);
+            tma_load_3d(s_img, &M.m[T.y & 15u], (int)(T.x & 0xFFFFu), (int)(T.x >> 16), f, &s_full);
         }
     }
+    flush_prev();
 }
 
 // ---- step 3: the cells iniThFAST left empty -> item list of the retry launch ----
@@ -382,20 +478,27 @@ int launch_fast_dense(orbx_handle *h, int nframes)
     if (D.ntiles <= 0) return launch_fast_cells(h, nframes, nullptr, nullptr);
     if (ensure_dense_tmaps(h, nframes) != 0) return -1;
     const int ncells = G.total_cells_valid;
-    // one memset: [work counter, retry count, 2 spare][corner counts][served flags]
+    // one memset: [work counter, retry count, 2 spare][corner counts][tiles done per frame][served flags]
+    const size_t B = (size_t)h->prm.max_batch;
     int32_t *zero = h->d_dense_zero;
     int32_t *ncorner = zero + 4;
-    uint8_t *found = reinterpret_cast<uint8_t *>(ncorner + (size_t)h->prm.max_batch * ORBX_MAX_LEVELS);
-    cudaMemsetAsync(zero, 0, (4 + (size_t)h->prm.max_batch * ORBX_MAX_LEVELS) * sizeof(int32_t) + (size_t)nframes * ncells, h->stream);
+    int32_t *done = ncorner + B * ORBX_MAX_LEVELS;
+    uint8_t *found = reinterpret_cast<uint8_t *>(done + B);
+    cudaMemsetAsync(zero, 0, (4 + B * ORBX_MAX_LEVELS + B) * sizeof(int32_t) + (size_t)nframes * ncells, h->stream);
+    const bool fuse = h->opt_dense_fuse != 0;
 
     LevelMaps M;
     memcpy(M.m, h->tmap_dense, sizeof(M.m));
     DenseParams P;
     P.clist = h->d_clist; P.clist_slab = D.cl_entries; P.ncorner = ncorner;
     P.smap = h->d_smap; P.smap_slab = D.map_bytes;
-    P.tiles = reinterpret_cast<const uint4 *>(h->d_dtiles); P.ntiles = D.ntiles; P.nitems = D.ntiles * nframes; P.inv_ntiles = 1.0f / (float)D.ntiles;
+    P.tiles = reinterpret_cast<const uint4 *>(h->d_dtiles); P.ntiles = D.ntiles; P.nframes = nframes;
+    if (fuse) {                                                       // dense_item: F blocks of (tiles, NMS items of the frame FD_NMS_LAG back), then the last frames' NMS items
+        P.nitems = nframes * (D.ntiles + FD_NMS_ITEMS) + std::min(nframes, FD_NMS_LAG) * FD_NMS_ITEMS;
+        P.inv_per = 1.0f / (float)(D.ntiles + FD_NMS_ITEMS);
+    } else { P.nitems = D.ntiles * nframes; P.inv_per = 1.0f / (float)D.ntiles; }
     P.th = h->prm.ini_th_fast; P.nlevels = G.nlevels;
-    P.status = h->d_status; P.work = zero;
+    P.status = h->d_status; P.work = zero; P.done = done;
     NmsParams Q;
     Q.clist = h->d_clist; Q.clist_slab = D.cl_entries; Q.ncorner = ncorner;
     Q.smap = h->d_smap; Q.smap_slab = D.map_bytes;
@@ -416,21 +519,21 @@ int launch_fast_dense(orbx_handle *h, int nframes)
         q.mw = (unsigned)((0x100000000ull + (unsigned)g.wcell - 1) / (unsigned)g.wcell); q.mh = (unsigned)((0x100000000ull + (unsigned)g.hcell - 1) / (unsigned)g.hcell);
     }
     const size_t smem = 128 + 128 + FD_TILE_BYTES + FD_ROWS * 128 + FD_WQ * 2 + 2 * FD_RES * 4;
+    auto kern = fuse ? k_fast_dense<true> : k_fast_dense<false>;
     if (!h->dense_grid_cap) {
-        if (!orbx_optin_smem(h, (const void *)k_fast_dense, smem)) return -1;
+        if (!orbx_optin_smem(h, (const void *)kern, smem)) return -1;
         int occ = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fast_dense, 32, smem);
-        h->dense_grid_cap = std::max(1, occ) * h->sm_count;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fast_dense<true>, 32, smem);
+        h->dense_grid_cap = std::max(1, occ) * h->sm_count;             // the fused kernel's waits need every CTA of the grid resident
     }
     int grid = std::min(P.nitems, h->dense_grid_cap);
     if (!h->opt_serial && h->opt_fast_ctas > 0) grid = std::min(grid, h->opt_fast_ctas * h->sm_count);
-    { ProfScope ps(h, ORBX_K_FAST_DENSE); orbx_launch_pdl(h, k_fast_dense, dim3(grid), dim3(32), smem, h->stream, M, P); }
+    { ProfScope ps(h, ORBX_K_FAST_DENSE); orbx_launch_pdl(h, kern, dim3(grid), dim3(32), smem, h->stream, M, P, Q); }
     const int nit = nframes * ncells;
     {
         ProfScope ps(h, ORBX_K_FAST_NMS);
-        orbx_launch_pdl(h, k_fast_nms, dim3(FN_BLOCKS_X, nframes, G.nlevels), dim3(FN_THREADS), 0, h->stream, Q);
+        if (!fuse) { orbx_launch_pdl(h, k_fast_nms, dim3(FN_BLOCKS_X, nframes, G.nlevels), dim3(FN_THREADS), 0, h->stream, Q); h->launches++; }
         orbx_launch_pdl(h, k_fast_retry_list, dim3((nit + 255) / 256), dim3(256), 0, h->stream, (const uint8_t *)found, nit, h->d_retry, zero + 1);
-        h->launches++;
     }
     return launch_fast_cells(h, nframes, h->d_retry, zero + 1);
 }

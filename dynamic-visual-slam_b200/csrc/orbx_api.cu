@@ -359,7 +359,7 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     CREATE_CUDA(cudaMalloc(&h->d_strips, sizeof(uint32_t) * h->strip_cap));
     h->cell_cap = G.total_cells + G.total_cells / 4 + 64 * p.nlevels;
     CREATE_CUDA(cudaMalloc(&h->d_cells, 2 * sizeof(uint4) * h->cell_cap));
-    h->opt_fast_dense = 0; h->dense_ok = false;          // its arenas are allocated when ORBX_OPT_FAST_DENSE is first switched on (dense_alloc)
+    h->opt_fast_dense = 0; h->opt_dense_fuse = 0; h->dense_ok = false;          // its arenas are allocated when ORBX_OPT_FAST_DENSE is first switched on (dense_alloc)
     h->blur_tile_cap = G.total_blur_tiles + G.total_blur_tiles / 4 + 64 * p.nlevels;
     CREATE_CUDA(cudaMalloc(&h->d_blur_tiles, sizeof(uint32_t) * h->blur_tile_cap));
     CREATE_CUDA(cudaMalloc(&h->d_xtab, sizeof(ResizeTab) * h->tab_cap));
@@ -420,6 +420,7 @@ static orbx_status check_device_status(orbx_handle *h)
     if (s == 0) return ORBX_OK;
     ORBX_CUDA(h, cudaMemsetAsync(h->d_status, 0, sizeof(int32_t), h->stream));
     if (s & ORBX_DS_BAD_INDEX) { h->err = "a match query index lies outside the keypoint array"; return ORBX_E_INVALID; }
+    if (s & ORBX_DS_INTERNAL) { h->err = "internal: a frame of the dense FAST kernel did not complete within its wait bound; results of this call are incomplete"; return ORBX_E_CUDA; }
     h->err = std::string("device capacity exceeded:") + ((s & ORBX_DS_CAND_OVERFLOW) ? " candidate list (lower cand_divisor)" : "") +
              ((s & ORBX_DS_NODE_OVERFLOW) ? " quadtree nodes / retained-corner list" : "") + ((s & ORBX_DS_KP_OVERFLOW) ? " keypoint output (raise cap / max_keypoints)" : "");
     return ORBX_E_CAPACITY;
@@ -447,7 +448,7 @@ static orbx_status dense_alloc(orbx_handle *h)
     h->dtile_cap = D.ntiles + D.ntiles / 4 + 64 * p.nlevels;
     h->smap_cap = (D.map_bytes + D.map_bytes / 8 + 65536) * B;
     h->clist_cap = (D.cl_entries + D.cl_entries / 8 + 4096 * p.nlevels) * B;
-    h->dense_zero_bytes = (4 + B * ORBX_MAX_LEVELS) * sizeof(int32_t) + B * (size_t)h->cell_cap;
+    h->dense_zero_bytes = (4 + B * ORBX_MAX_LEVELS + B) * sizeof(int32_t) + B * (size_t)h->cell_cap;
     if (cudaMalloc(&h->d_dtiles, sizeof(uint4) * h->dtile_cap) != cudaSuccess || cudaMalloc(&h->d_smap, h->smap_cap) != cudaSuccess ||
         cudaMalloc(&h->d_clist, h->clist_cap * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&h->d_dense_zero, h->dense_zero_bytes) != cudaSuccess ||
         cudaMalloc(&h->d_retry, B * (size_t)h->cell_cap * sizeof(int32_t)) != cudaSuccess) {
@@ -472,9 +473,10 @@ extern "C" orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t v
     if (option == ORBX_OPT_PDL) { h->opt_pdl = value ? 1 : 0; return ORBX_OK; }
     if (option == ORBX_OPT_OVERLAP) { h->opt_overlap = value ? 1 : 0; return ORBX_OK; }
     if (option == ORBX_OPT_FAST_DENSE) {
-        const int v = value < 0 ? 0 : (value > 2 ? 2 : value);
+        const int v = value < 0 ? 0 : (value > 3 ? 3 : value);
         if (v > 0) { const orbx_status st = dense_alloc(h); if (st != ORBX_OK) return st; }
-        h->opt_fast_dense = v;
+        h->opt_fast_dense = v == 3 ? 2 : v;
+        h->opt_dense_fuse = v == 3 ? 1 : 0;                      // 3: every call, the NMS as work items of the tile kernel (measured slower: k_fast_dense.cu)
         return ORBX_OK;
     }
     if (option == ORBX_OPT_MATCH_MMA) { h->opt_match_mma = value < 0 ? 0 : (value > 2 ? 2 : value); return ORBX_OK; }
@@ -979,6 +981,7 @@ static orbx_status finish_slot(orbx_handle *h, int slot, const int32_t *counts, 
     const int s = h->h_status[1 + slot];
     if (s != 0) {
         h->h_status[1 + slot] = 0;
+        if (s & ORBX_DS_INTERNAL) { h->err = "internal: a frame of the dense FAST kernel did not complete within its wait bound; results of this call are incomplete"; return ORBX_E_CUDA; }
         h->err = std::string("device capacity exceeded:") + ((s & ORBX_DS_CAND_OVERFLOW) ? " candidate list (lower cand_divisor)" : "") +
                  ((s & ORBX_DS_NODE_OVERFLOW) ? " quadtree nodes" : "") + ((s & ORBX_DS_KP_OVERFLOW) ? " keypoint output (raise cap / max_keypoints)" : "");
         return ORBX_E_CAPACITY;

@@ -139,6 +139,7 @@ struct orbx_handle {
     int fast_grid_cap; size_t fast_smem; int fast_tp;   // resident CTAs / dynamic smem / tile pitch of the persistent FAST kernel
     // dense FAST formulation (k_fast_dense.cu), used for batches: ORBX_OPT_FAST_DENSE 0 = never, 1 (default) = batches of >= ORBX_FAST_DENSE_MIN_FRAMES, 2 = always
     int opt_fast_dense; bool dense_ok; int dense_grid_cap; unsigned geo_serial;
+    int opt_dense_fuse;          // 0 (default): the NMS runs as a second kernel; 1: as work items inside k_fast_dense while the frame's score map is in L2 (measured slower)
     DenseGeom dgeo;
     void *d_dtiles; int dtile_cap;                        // tile records, 16 bytes each
     uint8_t *d_smap; size_t smap_cap;                     // score maps [batch]
@@ -238,6 +239,7 @@ size_t orbx_quadtree_smem(int node_cap);              // k_quadtree.cu: dynamic 
 #define ORBX_DS_CAND_OVERFLOW 1
 #define ORBX_DS_NODE_OVERFLOW 2
 #define ORBX_DS_KP_OVERFLOW   4
+#define ORBX_DS_INTERNAL     16      // a device-side wait ran into its bound (k_fast_dense)
 #define ORBX_DS_BAD_INDEX     8      // a caller-supplied index list pointed outside its array (k_cull)
 
 // ---- profile C (cv::ORB), orbx_cvorb.cu ----

@@ -264,7 +264,8 @@ class ORBextractor:
         self._check(self.L.orbx_set_option(self._h, 6, int(on)))
 
     def set_fast_dense(self, mode=1):
-        """ORBX_OPT_FAST_DENSE: 0 = warp-per-cell FAST kernel (default), 1 = dense formulation for batches of >= 8 frames, 2 = for every call."""
+        """ORBX_OPT_FAST_DENSE: 0 = warp-per-cell FAST kernel (default), 1 = dense formulation for batches of >= 8 frames, 2 = for every call,
+        3 = for every call with the NMS inside the tile kernel."""
         self._check(self.L.orbx_set_option(self._h, 7, int(mode)))
 
     def set_fast_ctas(self, n):

@@ -409,7 +409,7 @@ orbx_status orbx_synth_descriptors_device(orbx_handle *h, uint32_t seed, uint64_
 /* ORBX_OPT_FAST_DENSE: the second FAST formulation (k_fast_dense.cu): whole-level tiles of 128 x 16 pixels scored at iniThFAST into a score map
  * and a corner list, a per-corner NMS kernel restricted to the corner's cell, and a retry launch of the warp-per-cell kernel for the cells
  * iniThFAST left empty.  0 (default) = the warp-per-cell kernel for every call; 1 = dense for batches of >= 8 frames; 2 = dense for every
- * call.  Same keypoint sets (tests/test_gpu_fast_dense.py).  Off by default: measured 0.50 ms against 0.45 ms per 128 frames of 1280 x 720
+ * call; 3 = dense for every call with the NMS as work items inside the tile kernel (an experiment, slower).  Same keypoint sets (tests/test_gpu_fast_dense.py).  Off by default: measured 0.50 ms against 0.45 ms per 128 frames of 1280 x 720
  * — its NMS kernel re-reads the 420 MB of score maps from HBM.  Switching it on allocates its arenas
  * (0.8 GB at 128 frames of 1280 x 720): ORBX_E_CUDA if they cannot be had.                                                          */
 #define ORBX_OPT_FAST_DENSE 7

@@ -59,13 +59,14 @@ def test_dense_and_cell_formulations_agree_with_each_other_and_the_oracle(built,
     ex = orbx.ORBextractor(max_width=w, max_height=h, max_batch=n, max_keypoints=4096, cand_divisor=2)   # the noise frame: ~10 % of its pixels are keypoints
     try:
         outs, cands = {}, {}
-        for mode in (0, 2):
+        for mode in (0, 2, 3):                                       # warp per cell; dense with the NMS as a second kernel; dense with the NMS inside the tile kernel
             ex.set_fast_dense(mode)
             outs[mode] = _extract_device(ex, frames, 4096)
             cands[mode] = _cand_sets(ex, n)
         for f in range(n):
             for l in range(8):
                 assert cands[0][f][l] == cands[2][f][l], ("FAST candidate sets differ between the formulations", f, l, len(cands[0][f][l]), len(cands[2][f][l]))
+                assert cands[0][f][l] == cands[3][f][l], ("FAST candidate sets differ (NMS inside the tile kernel)", f, l, len(cands[0][f][l]), len(cands[3][f][l]))
         k0, d0, c0 = outs[0]
         k2, d2, c2 = outs[2]
         assert np.array_equal(c0, c2)
@@ -91,7 +92,7 @@ def test_dense_with_other_thresholds_and_single_frame_calls(built, oracle):
         ex = orbx.ORBextractor(max_width=w, max_height=h, max_batch=8, iniThFAST=ini, minThFAST=mn, max_keypoints=4096, cand_divisor=2)   # thresholds near 0: most pixels are corners
         try:
             ref = oracle.COracle(iniThFAST=ini, minThFAST=mn).extract(g, trace=True)
-            for mode in (0, 2):
+            for mode in (0, 2, 3):
                 ex.set_fast_dense(mode)
                 kps, desc = ex(g, cap=4096)
                 for l in range(8):
