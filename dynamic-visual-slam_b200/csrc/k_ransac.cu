@@ -101,7 +101,7 @@ template <int N> __device__ void jacobi_eig(double *A, double *V)
         }
     }
 }
-__global__ void __launch_bounds__(64) k_fmat_hypotheses(const float *__restrict__ p1, const float *__restrict__ p2, int n, int nh, uint32_t seed, double *__restrict__ Fout)
+__global__ void __launch_bounds__(32) k_fmat_hypotheses(const float *__restrict__ p1, const float *__restrict__ p2, int n, int nh, uint32_t seed, double *__restrict__ Fout)
 {
     const int hi = blockIdx.x * blockDim.x + threadIdx.x;
     if (hi >= nh) return;
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(64) k_fmat_hypotheses(const float *__restrict_
 void launch_fmat_hypotheses(orbx_handle *h, const float *d_p1, const float *d_p2, int n, int nh, uint32_t seed, double *d_F)
 {
     ProfScope ps(h, ORBX_K_OTHER);
-    k_fmat_hypotheses<<<(nh + 63) / 64, 64, 0, h->stream>>>(d_p1, d_p2, n, nh, seed, d_F);
+    k_fmat_hypotheses<<<(nh + 31) / 32, 32, 0, h->stream>>>(d_p1, d_p2, n, nh, seed, d_F);
 }
 
 void launch_fmat_score(orbx_handle *h, const float *d_p1, const float *d_p2, int n, const double *d_F, int nh, float t2,

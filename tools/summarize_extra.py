@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Per-kernel ncu --set full metrics of the kernels outside the step chain (tools/profile_extra.sh) -> profiles/<tag>_extra_kernels.csv
-usage: summarize_extra.py <tag> <extra.ncu-rep>"""
+usage: summarize_extra.py <tag> <extra.ncu-rep> [output suffix, default _extra_kernels.csv]"""
 import csv, os, re, subprocess, sys
 tag, rep = sys.argv[1], sys.argv[2]
 root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles")
@@ -17,9 +17,9 @@ seen = {}
 for r in rr[2:]:
     n = re.sub(r"<.*$", "", re.sub(r"^void\s+", "", r[idx["Kernel Name"]].split("(")[0].strip()))
     seen[n] = seen.get(n, 0) + 1
-    if seen[n] > 2 and not n.startswith("k_resize_exact"):
+    if seen[n] > (4 if n.startswith("k_fast") else 2) and not n.startswith("k_resize_exact"):
         continue
     rows.append(["%s#%d" % (n, seen[n])] + [r[idx[w]] for w in want if w in idx])
-csv.writer(open(os.path.join(root, tag + "_extra_kernels.csv"), "w")).writerows(rows)
+csv.writer(open(os.path.join(root, tag + (sys.argv[3] if len(sys.argv) > 3 else "_extra_kernels.csv")), "w")).writerows(rows)
 for r in rows[1:]:
     print(r[0].ljust(22), " ".join(x[:10].rjust(11) for x in r[1:10]))
