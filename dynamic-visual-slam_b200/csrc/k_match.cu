@@ -16,19 +16,7 @@
 #include "orbx_hamming.h"
 #include <float.h>
 
-#define MT_THREADS 128
-#define MT_TILE 256                 // train rows staged per shared-memory tile (8 KB)
-#define MT_KEY_SHIFT 22
-#define MT_INF 0xFFFFFFFFu
-
-struct MatchParams {
-    const uint8_t *q; const int32_t *nq_arr; int nq_imm; size_t q_stride;     // stride between problems' query sets (bytes)
-    const uint8_t *t; const int32_t *nt_arr; int nt_imm; size_t t_stride;
-    const int32_t *qsel, *tsel;     // problem -> set index (nullable: identity)
-    unsigned long long *part;        // [problem][split][nq_max][2] 64-bit keys (dist<<32 | global row)
-    int nq_max, nsplit, rows_per_split;
-    uint32_t row_base;               // global index of train row 0 (database shards)
-};
+#include "orbx_match.h"
 
 // TOP2 = false (k = 1 without a ratio test or raw top-2 output): only the best row is tracked, one VIMNMX per pair instead of three
 template <bool TOP2> __global__ void __launch_bounds__(MT_THREADS) k_match_partial(MatchParams P)
@@ -313,6 +301,24 @@ static int pick_split(orbx_handle *h, int nq_max, int nt_max, int nproblems, int
     return (int)split;
 }
 
+// the tensor-memory kernel: 128-row tiles, two resident CTAs per SM, each should see many tiles
+static int pick_split_umma(const orbx_handle *h, int nq_max, int nt_max, int nproblems, int *rows_per_split)
+{
+    const int qtiles = (nq_max + MT_THREADS - 1) / MT_THREADS;
+    const long ctas_wanted = (long)h->sm_count * 4;
+    long split = (ctas_wanted + (long)qtiles * nproblems - 1) / ((long)qtiles * nproblems);
+    const long max_split = (nt_max + 127) / 128;
+    if (split > max_split) split = max_split;
+    if (split < 1) split = 1;
+    long rps = (nt_max + split - 1) / split;
+    rps = (rps + 127) / 128 * 128;
+    if (rps > (1 << MT_KEY_SHIFT)) rps = 1 << MT_KEY_SHIFT;
+    split = (nt_max + rps - 1) / rps;
+    if (split < 1) split = 1;
+    *rows_per_split = (int)rps;
+    return (int)split;
+}
+
 static int ensure_part(orbx_handle *h, size_t entries)
 {
     if (entries <= h->mpart_cap) return 0;
@@ -331,7 +337,11 @@ int launch_match_core(orbx_handle *h, const uint8_t *d_q, const int32_t *d_nq, i
 {
     if (nproblems <= 0 || nq_max <= 0) return 0;
     int rps = MT_TILE;
-    const int nsplit = nt_max > 0 ? pick_split(h, nq_max, nt_max, nproblems, &rps) : 1;
+    // engine (ORBX_OPT_MATCH_MMA): 0 = POPC, 1 = the tensor-memory kernel once there is enough work to amortise its staging (a single frame pair, the
+    // latency path of ~1 M pairs, stays on the POPC kernel), 2 = the mma.sync kernel, 3 = the tensor-memory kernel for every call
+    const bool big = (double)nproblems * nq_max * nt_max >= 8e6;
+    const int engine = h->opt_match_mma == 3 || (h->opt_match_mma == 1 && big) ? 3 : (h->opt_match_mma == 2 ? 2 : 0);
+    const int nsplit = nt_max <= 0 ? 1 : (engine == 3 ? pick_split_umma(h, nq_max, nt_max, nproblems, &rps) : pick_split(h, nq_max, nt_max, nproblems, &rps));
     if (ensure_part(h, (size_t)nproblems * nsplit * nq_max * 2) != 0) return -1;
     if (nt_max > 0) {
         MatchParams P;
@@ -344,9 +354,8 @@ int launch_match_core(orbx_handle *h, const uint8_t *d_q, const int32_t *d_nq, i
         // every slot the epilogue reads (qi < nq, all splits) is written by the partial kernel; splits that
         // start beyond a problem's own nt write the "empty" key
         ProfScope ps(h, ORBX_K_MATCH);
-        // Hamming as an int8 tensor-core GEMM (k_match_mma, 8 warps x 16 queries per CTA) once there is enough work to amortise its staging: a single
-        // frame pair (the latency path, ~1 M pairs) stays on the POPC kernel, which measured 10 us less there
-        if (h->opt_match_mma == 2 || (h->opt_match_mma && (double)nproblems * nq_max * nt_max >= 8e6)) {
+        if (engine == 3) launch_match_umma(h, P, grid, k == 2 || d_top2 != nullptr);
+        else if (engine == 2) {
             if (k == 2 || d_top2) orbx_launch_pdl(h, k_match_mma<true>, grid, dim3(256), 0, h->stream, P);
             else orbx_launch_pdl(h, k_match_mma<false>, grid, dim3(256), 0, h->stream, P);
         } else if (k == 2 || d_top2) orbx_launch_pdl(h, k_match_partial<true>, grid, dim3(MT_THREADS), 0, h->stream, P);

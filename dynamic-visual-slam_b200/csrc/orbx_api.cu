@@ -479,7 +479,7 @@ extern "C" orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t v
         h->opt_dense_fuse = v == 3 ? 1 : 0;                      // 3: every call, the NMS as work items of the tile kernel (measured slower: k_fast_dense.cu)
         return ORBX_OK;
     }
-    if (option == ORBX_OPT_MATCH_MMA) { h->opt_match_mma = value < 0 ? 0 : (value > 2 ? 2 : value); return ORBX_OK; }
+    if (option == ORBX_OPT_MATCH_MMA) { h->opt_match_mma = value < 0 ? 0 : (value > 3 ? 3 : value); return ORBX_OK; }
     h->err = "unknown option"; return ORBX_E_INVALID;
 }
 extern "C" void *orbx_stream(orbx_handle *h) { return h ? (void *)h->stream : nullptr; }

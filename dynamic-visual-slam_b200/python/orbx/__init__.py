@@ -260,7 +260,8 @@ class ORBextractor:
         self._check(self.L.orbx_set_option(self._h, 5, 1 if on else 0))
 
     def set_match_mma(self, on=True):
-        """ORBX_OPT_MATCH_MMA: 1 = int8 tensor-core GEMM for calls of >= 8 M pairs (default), 2 = always, 0 / False = always the POPC kernel."""
+        """ORBX_OPT_MATCH_MMA: 1 = tensor-memory (tcgen05) matcher for calls of >= 8 M pairs (default), 3 = for every call, 2 = the mma.sync int8 matcher,
+        0 / False = always the POPC kernel."""
         self._check(self.L.orbx_set_option(self._h, 6, int(on)))
 
     def set_fast_dense(self, mode=1):

@@ -181,20 +181,23 @@ def test_match_bit_exact(ex, oracle):
 
 
 def test_both_match_engines_ragged_sizes(built, oracle):
-    """ORBX_OPT_MATCH_MMA: the int8 tensor-core GEMM matcher (default) and the LOP3/POPC matcher against BFMatcher's restatement on ragged
-    problem sizes (fewer rows than one 8-row MMA tile, sizes straddling the 16-query / 64-row staging units, duplicates -> lowest-index ties)"""
+    """ORBX_OPT_MATCH_MMA: the tensor-memory matcher (tcgen05, 3), the mma.sync int8 GEMM matcher (2) and the LOP3/POPC matcher (0) against
+    BFMatcher's restatement on ragged problem sizes (fewer rows than one MMA tile, sizes straddling the 16 / 128-query and 64 / 128-row staging
+    units, several splits, duplicates -> lowest-index ties, all-ones / all-zeros descriptors: the extremes of the signed key arithmetic)"""
     import orbx
     rng = np.random.default_rng(11)
     e = orbx.ORBextractor(max_width=320, max_height=240)
     try:
-        for nq, nt in [(1, 1), (1, 7), (3, 9), (16, 8), (17, 63), (33, 65), (129, 130), (500, 1000), (1000, 777), (64, 4096)]:
+        for nq, nt in [(1, 1), (1, 7), (3, 9), (16, 8), (17, 63), (33, 65), (129, 130), (500, 1000), (1000, 777), (64, 4096), (257, 40000), (1500, 120000)]:          # the last: tens of 128-row tiles per CTA in the tensor-memory kernel
             q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
             t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
             if nt > 4:
                 t[nt - 1] = t[1]; q[0] = t[1]                       # exact duplicate at both ends of the train set: tie at distance 0
                 t[nt // 2] = t[1]
+            if nt > 8 and nq > 2:
+                t[3] = 255; t[4] = 0; q[1] = 255; q[2] = 0           # popcounts 256 and 0 on both sides
             want1, want2 = oracle.match(q, t), oracle.knn2(q, t)
-            for mma in (2, 0):                                       # 2 = force the tensor-core GEMM whatever the problem size
+            for mma in (3, 2, 0):                                    # 3 / 2 = force the tensor-core kernels whatever the problem size
                 e.set_match_mma(mma)
                 m = e.match(q, t, k=1)
                 assert np.array_equal(m.view(np.uint8), want1.view(np.uint8)), (nq, nt, mma)
