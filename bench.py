@@ -607,7 +607,7 @@ def main():
                  "nn_below_50": int((res[:, 0] < 50).sum()), "nn_from_other_shards": int((res[:, 1] >= rows_r).sum()) if world > 1 else 0,
                  "mismatches_vs_unsharded": mism, "cpu_check": cpu_check,
                  "kernel_ms": kms, "kernel_gpairs_per_s": NQ * rows_r / (kms * 1e-3) / 1e9 if kms > 0 else None,
-                 "engine": "k_match_mma (int8 tensor-core GEMM)" if not args.popc_match else "k_match_partial (POPC)", "popc_per_s_measured_peak": popc,
+                 "engine": "k_match_partial (POPC)" if args.popc_match else ("k_match_mma (mma.sync int8 GEMM)" if args.match_engine == 2 else "k_match_umma (tcgen05.mma kind::i8, accumulators in TMEM)"), "popc_per_s_measured_peak": popc,
                  "transport": "peer memory (NVLink stores into every peer's mailbox + sequence flags, one kernel)" if peer else "nccl",
                  "ms_per_query_batch_nccl": ms_nccl, "transports_agree": same_transports,
                  "collective": "orbx_db_query_top2_sharded_device: per-shard kernel -> exchange of 32 KB/rank -> merge kernel, all on the handle's stream, "
@@ -651,7 +651,7 @@ def main():
         assoc["gated"] = {"call": "orbx_db_associate_sharded_device (Hamming < 50, then smallest reprojection error < 5 px): per-shard kernel -> exchange of 32 KB/rank -> merge",
                           "ms_per_query_batch": ms_g, "gpairs_per_s": NQ * ROWS / (ms_g * 1e-3) / 1e9, "associated": int((got_g["landmark"] >= 0).sum()),
                           "mismatches_vs_unsharded": mism_g, "cpu_check": gated_cpu,
-                          "engine": "k_assoc_mma (int8 tensor-core GEMM, reprojection in the epilogue)" if not args.popc_match else "k_assoc_partial (POPC)"}
+                          "engine": "k_assoc_partial (POPC)" if args.popc_match else ("k_assoc_mma (mma.sync int8 GEMM, reprojection in the epilogue)" if args.match_engine == 2 else "k_assoc_umma (tcgen05 int8 GEMM, accumulators in TMEM, reprojection in the epilogue)")}
         comm.close(); db.close(); full.close()
         del drows, frows
 

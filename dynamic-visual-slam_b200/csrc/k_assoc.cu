@@ -11,6 +11,8 @@
 // Exactly equal errors are resolved to the lowest landmark row (the reference iterates an unordered_map: unspecified there).
 #include "orbx_internal.h"
 #include "orbx_hamming.h"
+#include "orbx_match.h"
+#include "orbx_umma.h"
 #include <float.h>
 
 #define AS_THREADS 128
@@ -198,6 +200,114 @@ __global__ void __launch_bounds__(256) k_assoc_mma(AssocParams P)
     }
 }
 
+// ---- tensor-memory variant (tcgen05): the tiles and the pipeline of k_match_umma (k_match_umma.cu), the gate + reprojection epilogue of k_assoc_mma ----
+// A thread reads back 64 landmark columns of its observation per tile; keys are signed and lack the observation's own popcount, so the gate is
+// key < (ceil(max_dist) << 22) - (popc(q) << 22).  Rows ascend per thread; the two threads that hold the two column halves of an observation and
+// the splits merge by (error, row).
+__global__ void __launch_bounds__(UM_THREADS) k_assoc_umma(AssocParams P, int32_t *status)
+{
+    extern __shared__ __align__(16) uint8_t um_raw[];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(16) int32_t s_tk[3][UM_TILE];
+    __shared__ double s_e[128];
+    __shared__ int s_r[128];
+    __shared__ float s_d[128];
+    const int r0 = blockIdx.y * P.rows_per_split, r1 = min(P.nt, r0 + P.rows_per_split);
+    const int nrows = max(0, r1 - r0), ntiles = (nrows + UM_TILE - 1) / UM_TILE;
+    const uint4 *tbase = reinterpret_cast<const uint4 *>(P.t);
+    uint8_t *sa = um_raw + ((1024u - (um_smem(um_raw) & 1023u)) & 1023u), *sb = sa + UM_A_BYTES;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int srow = tid >> 1, shalf = tid & 1;
+    if (tid == 0) {
+        um_bar_init(&s_bar[0]); um_bar_init(&s_bar[1]);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) um_tmem_alloc(&s_tmem, 256);
+    {
+        const int qrow = blockIdx.x * 128 + srow;
+        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+        if (qrow < P.nq) x = __ldg(reinterpret_cast<const uint4 *>(P.q + (size_t)qrow * ORBX_DESC_BYTES) + shalf);
+        um_unpack(sa, srow, shalf, x);
+    }
+    const int eq = 32 * (warp & 3) + lane, ehalf = warp >> 2;
+    const int qrow = blockIdx.x * 128 + eq;
+    int pq;
+    {
+        const uint4 *qp = reinterpret_cast<const uint4 *>(P.q + (size_t)(qrow < P.nq ? qrow : 0) * ORBX_DESC_BYTES);
+        const uint4 a = __ldg(qp), b = __ldg(qp + 1);
+        pq = (__popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w)) << MT_KEY_SHIFT;
+    }
+    const float qx = qrow < P.nq ? __ldg(P.qpx + 2 * qrow) : 0.f, qy = qrow < P.nq ? __ldg(P.qpx + 2 * qrow + 1) : 0.f;
+    // (float)d < max_dist for an integer d  <=>  d < ceil(max_dist); in the signed keys that lack popc(q): key < (dlim << 22) - (popc(q) << 22)
+    const int dlim = max(0, min(257, (int)ceilf(P.max_dist)));
+    const int thr = (dlim << MT_KEY_SHIFT) - pq;
+    AssocBest best = { DBL_MAX, -1, 0.f };
+    auto fetch = [&](int t) {
+        const int lrow = t * UM_TILE + srow;
+        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+        if (lrow < nrows) x = __ldg(tbase + (size_t)(r0 + lrow) * 2 + shalf);
+        return x;
+    };
+    auto stage = [&](int t, const uint4 x) {
+        um_unpack(sb + (t & 1) * UM_B_BYTES, srow, shalf, x);
+        int pc = __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+        pc += __shfl_xor_sync(0xffffffffu, pc, 1);
+        const int lrow = t * UM_TILE + srow;
+        if (shalf == 0) s_tk[t % 3][srow] = lrow < nrows ? ((pc << MT_KEY_SHIFT) | lrow) : (int32_t)(UM_DEAD | (uint32_t)(lrow & ((1 << MT_KEY_SHIFT) - 1)));
+    };
+    auto candidate = [&](int key) {                                 // a landmark inside the descriptor gate: the fp64 reprojection of k_assoc_partial
+        if (key < thr) {
+            const int row = r0 + (key & ((1 << MT_KEY_SHIFT) - 1));
+            const double e = reproj_error(P.pos + (size_t)row * 3, P.pose, qx, qy);
+            if (e < P.max_err && e < best.e) { best.e = e; best.row = row; best.d = (float)(((uint32_t)key + (uint32_t)pq) >> MT_KEY_SHIFT); }   // rows ascend: ties keep the lowest
+        }
+    };
+    if (ntiles > 0) stage(0, fetch(0));
+    um_publish();
+    const uint32_t tm = s_tmem;
+    bool failed = false;
+    for (int t = 0; t <= ntiles; t++) {
+        if (t < ntiles && tid == 0)
+            um_issue_tile(um_smem(sa), um_smem(sb + (t & 1) * UM_B_BYTES), tm + (uint32_t)((t & 1) * UM_TILE), &s_bar[t & 1]);
+        uint4 nx = make_uint4(0u, 0u, 0u, 0u);
+        if (t + 1 < ntiles) nx = fetch(t + 1);
+        if (t > 0) {
+            const int e = t - 1, buf = e & 1;
+            if (!um_wait(&s_bar[buf], (uint32_t)((e >> 1) & 1))) failed = true;
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                uint32_t v[32];
+                const int col0 = 64 * ehalf + 32 * c;
+                const uint32_t taddr = tm + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(buf * UM_TILE + col0);
+                UM_TMEM_LD32(v, taddr);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int4 *tk4 = reinterpret_cast<const int4 *>(&s_tk[e % 3][col0]);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int4 k4 = tk4[j];
+                    const int k0 = (int)((uint32_t)k4.x - (v[4 * j] << (MT_KEY_SHIFT + 1))), k1 = (int)((uint32_t)k4.y - (v[4 * j + 1] << (MT_KEY_SHIFT + 1)));
+                    const int k2 = (int)((uint32_t)k4.z - (v[4 * j + 2] << (MT_KEY_SHIFT + 1))), k3 = (int)((uint32_t)k4.w - (v[4 * j + 3] << (MT_KEY_SHIFT + 1)));
+                    if (min(min(k0, k1), min(k2, k3)) < thr) { candidate(k0); candidate(k1); candidate(k2); candidate(k3); }      // rare
+                }
+            }
+        }
+        if (t + 1 < ntiles) stage(t + 1, nx);
+        um_publish();
+    }
+    if (warp == 0) um_tmem_free(tm, 256);
+    if (failed && lane == 0) atomicOr(status, ORBX_DS_INTERNAL);
+    if (ehalf == 1) { s_e[eq] = best.e; s_r[eq] = best.row; s_d[eq] = best.d; }
+    __syncthreads();
+    if (ehalf == 0 && qrow < P.nq) {
+        const double e1 = s_e[eq]; const int rw1 = s_r[eq];
+        if (rw1 >= 0 && (best.row < 0 || e1 < best.e || (e1 == best.e && rw1 < best.row))) { best.e = e1; best.row = rw1; best.d = s_d[eq]; }
+        orbx_assoc r;
+        r.reproj_error = best.e; r.landmark = best.row < 0 ? -1 : (int32_t)(P.row_base + (uint32_t)best.row); r.distance = best.d;
+        P.part[(size_t)blockIdx.y * P.nq + qrow] = r;
+    }
+}
+
 // lexicographic (error, landmark row) minimum over `nparts` partial results laid out [part][nq]
 __global__ void k_assoc_merge(const orbx_assoc *parts, size_t stride, int nparts, int nq, orbx_assoc *out)
 {
@@ -216,14 +326,18 @@ int launch_assoc(orbx_handle *h, const uint8_t *d_q, const float *d_qpx, int nq,
                  const orbx_pose *pose, float max_dist, double max_err, orbx_assoc *d_out)
 {
     if (nq <= 0) return 0;
-    // split the landmark range so that the grid covers the machine a few times over
+    // engine (ORBX_OPT_MATCH_MMA, as for the matcher): 3 / 1 = the tensor-memory kernel (always / for calls of >= 8 M pairs), 2 = mma.sync, 0 = POPC
+    const bool big = (double)nq * (double)nt >= 8e6;
+    const int engine = h->opt_match_mma == 3 || (h->opt_match_mma == 1 && big) ? 3 : (h->opt_match_mma == 2 ? 2 : 0);
+    // split the landmark range so that the grid covers the machine a few times over (the tensor-memory kernel: two resident CTAs per SM, 128-row tiles)
     const int qtiles = (nq + AS_THREADS - 1) / AS_THREADS;
-    long split = ((long)h->sm_count * 16 + qtiles - 1) / qtiles;
-    const long max_split = std::max(1, (nt + AS_TILE - 1) / AS_TILE);
+    const int unit = engine == 3 ? UM_TILE : AS_TILE;
+    long split = ((long)h->sm_count * (engine == 3 ? 4 : 16) + qtiles - 1) / qtiles;
+    const long max_split = std::max(1, (nt + unit - 1) / unit);
     if (split > max_split) split = max_split;
     if (split < 1) split = 1;
     long rps = (std::max(nt, 1) + split - 1) / split;
-    rps = (rps + AS_TILE - 1) / AS_TILE * AS_TILE;
+    rps = (rps + unit - 1) / unit * unit;
     split = (std::max(nt, 1) + rps - 1) / rps;
     const size_t need = (size_t)split * nq * sizeof(orbx_assoc);
     if (need > h->mpart_cap * sizeof(unsigned long long)) {
@@ -238,8 +352,10 @@ int launch_assoc(orbx_handle *h, const uint8_t *d_q, const float *d_qpx, int nq,
     dim3 grid(qtiles, (unsigned)split);
     {
         ProfScope ps(h, ORBX_K_OTHER);
-        // the int8 tensor-core GEMM once there is enough work to amortise its staging (ORBX_OPT_MATCH_MMA, as for the matcher)
-        if (h->opt_match_mma == 2 || (h->opt_match_mma && (double)nq * (double)nt >= 8e6)) k_assoc_mma<<<grid, 256, 0, h->stream>>>(P);
+        if (engine == 3) {
+            orbx_optin_smem(h, (const void *)k_assoc_umma, UM_SMEM);
+            k_assoc_umma<<<grid, UM_THREADS, UM_SMEM, h->stream>>>(P, h->d_status);
+        } else if (engine == 2) k_assoc_mma<<<grid, 256, 0, h->stream>>>(P);
         else k_assoc_partial<<<grid, AS_THREADS, 0, h->stream>>>(P);
     }
     ProfScope ps(h, ORBX_K_OTHER);

@@ -1,0 +1,85 @@
+// orbx_umma.h — device pieces shared by the tensor-memory (tcgen05) kernels: k_match_umma.cu (top-2 matcher) and k_assoc.cu (association with
+// the reprojection gate).  Operand encodings checked by tools/umma_probe.cu.
+#pragma once
+#include "orbx_internal.h"
+
+#define UM_TILE 128
+#define UM_THREADS 256
+#define UM_A_BYTES (128 * 256)
+#define UM_B_BYTES (UM_TILE * 256)
+#define UM_SMEM (UM_A_BYTES + 2 * UM_B_BYTES + 1024)             // + alignment slack; 97 KB (+ 2 KB static): at most two CTAs per SM = 2 x 256 of the 512 TMEM columns
+#define UM_DEAD (511u << MT_KEY_SHIFT)
+
+__device__ __forceinline__ uint32_t um_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// shared-memory matrix descriptor, K-major, no swizzle: start address >> 4 | LBO (next 16-byte k chunk: 128 B) | SBO (next 8-row group: 256 B) | version 1
+__device__ __forceinline__ uint64_t um_desc(uint32_t saddr) { return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (8ull << 16) | (16ull << 32) | (1ull << 46); }
+// instruction descriptor: D = s32 (2 << 4), A = B = u8, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+#define UM_IDESC ((2u << 4) | ((uint32_t)(UM_TILE >> 3) << 17) | ((uint32_t)(128 >> 4) << 24))
+
+// unpack 16 bytes of a descriptor (words 4 half .. 4 half + 3 of row `row`) into the operand tile: word w = k-block, shifts 0-3 -> chunk 0, 4-7 -> chunk 1
+__device__ __forceinline__ void um_unpack(uint8_t *tile, int row, int half, const uint4 x)
+{
+    const uint32_t M1 = 0x01010101u;
+    const uint32_t w[4] = { x.x, x.y, x.z, x.w };
+    uint8_t *base = tile + (row >> 3) * 256 + (row & 7) * 16;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint8_t *p = base + (4 * half + i) * (128 * 32);
+        *reinterpret_cast<uint4 *>(p) = make_uint4(w[i] & M1, (w[i] >> 1) & M1, (w[i] >> 2) & M1, (w[i] >> 3) & M1);
+        *reinterpret_cast<uint4 *>(p + 128) = make_uint4((w[i] >> 4) & M1, (w[i] >> 5) & M1, (w[i] >> 6) & M1, (w[i] >> 7) & M1);
+    }
+}
+
+
+// one tcgen05.ld 32x32b.x32: the calling warp's 32 TMEM lanes (a thread = one lane = one query), 32 consecutive 32-bit columns from taddr
+#define UM_TMEM_LD32(v, taddr) \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];" \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), \
+                   "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), \
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) \
+                 : "r"(taddr))
+
+// tile t of a CTA: eight MMAs (K = 8 x 32 bytes) of A (128 rows at a0) x B (128 rows at b0) into TMEM columns tc .. tc + 127, then the commit that
+// makes `bar` complete a phase when they are done.  One thread calls this.
+__device__ __forceinline__ void um_issue_tile(uint32_t a0, uint32_t b0, uint32_t tc, uint64_t *bar)
+{
+#pragma unroll
+    for (int kb = 0; kb < 8; kb++) {
+        const uint64_t da = um_desc(a0 + kb * (128 * 32)), db = um_desc(b0 + kb * (UM_TILE * 32));
+        const uint32_t acc = kb > 0 ? 1u : 0u;
+        asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}"
+                     ::"r"(tc), "l"(da), "l"(db), "r"(UM_IDESC), "r"(acc), "r"(0u) : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(um_smem(bar)) : "memory");
+}
+// bounded wait for a phase of `bar` (a lost commit must not take the GPU with it): false = timed out
+__device__ __forceinline__ bool um_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    for (int spin = 0; spin < (1 << 24) && !ok; spin++)
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(um_smem(bar)), "r"(parity) : "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    return ok != 0;
+}
+// generic-proxy writes of the operands -> visible to the tensor core; orders the CTA's TMEM reads before the next MMAs
+__device__ __forceinline__ void um_publish()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void um_tmem_alloc(uint32_t *dst, int ncols)          // one warp; ncols a power of two >= 32
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(um_smem(dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void um_tmem_free(uint32_t taddr, int ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void um_bar_init(uint64_t *bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(um_smem(bar)) : "memory");
+}

@@ -43,9 +43,9 @@ def _assert_assoc(got, want):
     assert np.array_equal(got["distance"][sel], dist[sel])
 
 
-@pytest.mark.parametrize("engine", [0, 2])
+@pytest.mark.parametrize("engine", [0, 2, 3])
 def test_associate_matches_reference_semantics(built, oracle, engine):
-    """engine: ORBX_OPT_MATCH_MMA 0 = k_assoc_partial (POPC), 2 = k_assoc_mma (int8 tensor-core GEMM + the same reprojection epilogue)"""
+    """engine: ORBX_OPT_MATCH_MMA 0 = k_assoc_partial (POPC), 2 = k_assoc_mma (mma.sync int8 GEMM), 3 = k_assoc_umma (tcgen05), each with the same reprojection epilogue"""
     import orbx
     rows, pos, q, qpx, R, t, K = _scene(oracle, 20000 + 37 * engine, 700 + engine, 5)      # row / query counts off the 64 / 16 tile sizes
     ex = orbx.ORBextractor(max_width=320, max_height=240)
@@ -63,7 +63,7 @@ def test_associate_matches_reference_semantics(built, oracle, engine):
         db.close(); ex.close()
 
 
-@pytest.mark.parametrize("engine", [0, 2])
+@pytest.mark.parametrize("engine", [0, 2, 3])
 def test_associate_sharded_merge(built, oracle, engine):
     """Two shards (global row ranges) merged by orbx_merge_assoc_device == one unsharded database."""
     import torch
