@@ -425,10 +425,13 @@ def main():
         pairs = float((nkp[1:].astype(np.float64) * nkp[:-1]).sum() + float(nkp[0]) * float(nkp[-1]))      # frame f vs f-1; frame 0 vs the carried last frame
         popc = ex.bench_popc()
         t_s = kernels["k_match_partial"]["ms_per_step"] * 1e-3
-        match_roofline = {"kernel": "k_match_mma" if not args.popc_match else "k_match_partial",
-                          "engine": "int8 tensor-core GEMM (mma.sync m16n8k32.u8 on descriptors unpacked to 0/1 bytes, d = |q| + |t| - 2 q.t)" if not args.popc_match
-                                    else "LOP3/POPC (5 POPC per pair after carry-save adders)",
-                          "bound": "tensor pipe (legacy mma.sync int8: ncu 58 % busy at 1.28 T pairs/s)" if not args.popc_match else "integer issue (ALU pipe)",
+        eng = 0 if args.popc_match else (args.match_engine if args.match_engine >= 0 else 1)
+        match_roofline = {"kernel": {0: "k_match_partial", 2: "k_match_mma"}.get(eng, "k_match_umma"),
+                          "engine": {0: "LOP3/POPC (5 POPC per pair after carry-save adders)",
+                                     2: "int8 tensor-core GEMM (mma.sync m16n8k32.u8 on descriptors unpacked to 0/1 bytes, d = |q| + |t| - 2 q.t)"}.get(
+                                     eng, "int8 GEMM on tcgen05 (tcgen05.mma kind::i8, 128 x 128 x 256 tiles, accumulators in TMEM; d = |q| + |t| - 2 q.t on descriptors unpacked to 0/1 bytes)"),
+                          "bound": {0: "integer issue (ALU pipe)", 2: "tensor pipe (legacy mma.sync int8: ncu 58 % busy at 1.28 T pairs/s)"}.get(
+                                   eng, "its own per-tile lock-step (ncu: tensor pipe 29 % busy, 30 % of the samples at the CTA barrier); the tensor pipe would allow ~9 T pairs/s"),
                           "pairs_per_step": pairs, "gpairs_per_s": pairs / t_s / 1e9,
                           "popc_equivalent": {"popc_per_pair": POPC_PER_PAIR, "achieved": POPC_PER_PAIR * pairs / t_s, "peak": popc, "unit": "POPC/s",
                                               "frac": POPC_PER_PAIR * pairs / t_s / popc if popc > 0 else None, "peak_source": "measured (orbx_bench_popc)",

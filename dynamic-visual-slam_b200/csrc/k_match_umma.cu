@@ -15,14 +15,17 @@
 #include "orbx_match.h"
 #include "orbx_umma.h"
 
-template <bool TOP2> __global__ void __launch_bounds__(UM_THREADS) k_match_umma(MatchParams P, int32_t *status)
+#define UM_THREADS_X 512             // 16 warps: four per TMEM lane quarter, each reads back 32 of a tile's 128 columns (the read-back is latency bound:
+                                     // two CTAs x 8 warps left the SM half idle); the first 256 threads also stage the operands
+
+template <bool TOP2> __global__ void __launch_bounds__(UM_THREADS_X, 2) k_match_umma(MatchParams P, int32_t *status)
 {
     extern __shared__ __align__(16) uint8_t um_raw[];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) int32_t s_tk[3][UM_TILE];            // per train row of a tile: popc(t) << 22 | local row  (dead rows: 511 << 22); three tiles are
                                                                   // live at once: t - 1 (being read back), t (in the tensor core), t + 1 (being staged)
-    __shared__ uint32_t s_m[2][128];                              // merge of the two column halves at the end
+    __shared__ uint32_t s_m[3][2][128];                           // merge of the four column quarters at the end
     ORBX_PDL_ENTRY();
     const int prob = blockIdx.z;
     const int qs = P.qsel ? P.qsel[prob] : prob, ts = P.tsel ? P.tsel[prob] : prob;
@@ -36,7 +39,8 @@ template <bool TOP2> __global__ void __launch_bounds__(UM_THREADS) k_match_umma(
     const uint4 *tbase = reinterpret_cast<const uint4 *>(P.t + (size_t)ts * P.t_stride);
     uint8_t *sa = um_raw + ((1024u - (um_smem(um_raw) & 1023u)) & 1023u), *sb = sa + UM_A_BYTES;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int srow = tid >> 1, shalf = tid & 1;                   // staging role: 16 bytes of one row
+    const int srow = (tid & 255) >> 1, shalf = tid & 1;           // staging role (threads 0..255): 16 bytes of one row
+    const bool stager = tid < 256;
 
     if (tid == 0) {
         um_bar_init(&s_bar[0]); um_bar_init(&s_bar[1]);
@@ -48,10 +52,10 @@ template <bool TOP2> __global__ void __launch_bounds__(UM_THREADS) k_match_umma(
     {
         const int qrow = blockIdx.x * 128 + srow;
         uint4 x = make_uint4(0u, 0u, 0u, 0u);
-        if (qrow < nq) x = __ldg(reinterpret_cast<const uint4 *>(qbase + (size_t)qrow * ORBX_DESC_BYTES) + shalf);
-        um_unpack(sa, srow, shalf, x);
+        if (stager && qrow < nq) x = __ldg(reinterpret_cast<const uint4 *>(qbase + (size_t)qrow * ORBX_DESC_BYTES) + shalf);
+        if (stager) um_unpack(sa, srow, shalf, x);
     }
-    // the epilogue role: warp w reads TMEM lanes 32 (w & 3) .. + 31 (a thread = query 32 (w & 3) + lane), columns 64 (w >> 2) .. + 63 of a tile
+    // the epilogue role: warp w reads TMEM lanes 32 (w & 3) .. + 31 (a thread = query 32 (w & 3) + lane), columns 32 (w >> 2) .. + 31 of a tile
     const int eq = 32 * (warp & 3) + lane, ehalf = warp >> 2;
     {
         const int qrow = blockIdx.x * 128 + eq;
@@ -63,10 +67,11 @@ template <bool TOP2> __global__ void __launch_bounds__(UM_THREADS) k_match_umma(
     auto fetch = [&](int t) {
         const int lrow = t * UM_TILE + srow;
         uint4 x = make_uint4(0u, 0u, 0u, 0u);
-        if (lrow < nrows) x = __ldg(tbase + (size_t)(r0 + lrow) * 2 + shalf);
+        if (stager && lrow < nrows) x = __ldg(tbase + (size_t)(r0 + lrow) * 2 + shalf);
         return x;
     };
     auto stage = [&](int t, const uint4 x) {
+        if (!stager) return;
         um_unpack(sb + (t & 1) * UM_B_BYTES, srow, shalf, x);
         int pc = __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
         pc += __shfl_xor_sync(0xffffffffu, pc, 1);
@@ -87,25 +92,29 @@ template <bool TOP2> __global__ void __launch_bounds__(UM_THREADS) k_match_umma(
         if (t > 0) {                                              // epilogue of tile t - 1 (its MMAs were committed one iteration ago)
             const int e = t - 1, buf = e & 1;
             if (!um_wait(&s_bar[buf], (uint32_t)((e >> 1) & 1))) failed = true;
+            uint32_t v[32];
+            const uint32_t taddr = tm + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(buf * UM_TILE + 32 * ehalf);
+            UM_TMEM_LD32(v, taddr);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int4 *tk4 = reinterpret_cast<const int4 *>(&s_tk[e % 3][32 * ehalf]);
 #pragma unroll
-            for (int c = 0; c < 2; c++) {
-                uint32_t v[32];
-                const int col0 = 64 * ehalf + 32 * c;
-                const uint32_t taddr = tm + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(buf * UM_TILE + col0);
-                UM_TMEM_LD32(v, taddr);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int4 *tk4 = reinterpret_cast<const int4 *>(&s_tk[e % 3][col0]);
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int4 k4 = tk4[j];                                            // one broadcast load: the key bases of four train rows
-                    const int kk[4] = { k4.x, k4.y, k4.z, k4.w };
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const int key = (int)((uint32_t)kk[i] - (v[4 * j + i] << (MT_KEY_SHIFT + 1)));     // (popc(t) - 2 q.t) << 22 | row
-                        if (TOP2) m1 = min(m1, max(m0, key));
-                        m0 = min(m0, key);
+            for (int j = 0; j < 8; j++) {
+                const int4 k4 = tk4[j];                                                // one broadcast load: the key bases of four train rows
+                const uint32_t *vv = &v[4 * j];
+                // (popc(t) - 2 q.t) << 22 | row
+                const int ka = (int)((uint32_t)k4.x - (vv[0] << (MT_KEY_SHIFT + 1))), kb = (int)((uint32_t)k4.y - (vv[1] << (MT_KEY_SHIFT + 1)));
+                const int kc = (int)((uint32_t)k4.z - (vv[2] << (MT_KEY_SHIFT + 1))), kd = (int)((uint32_t)k4.w - (vv[3] << (MT_KEY_SHIFT + 1)));
+                if (TOP2) {
+                    // the second best only moves when a key undercuts it — ~2 ln(n) times per query over n rows: test the smallest of four keys
+                    // against it (two three-input minima and a compare per four pairs) and update (best, second best) on that rare path
+                    const int k4min = min(min(ka, kb), min(kc, kd));
+                    if (k4min < m1) {
+                        m1 = min(m1, max(m0, ka)); m0 = min(m0, ka);
+                        m1 = min(m1, max(m0, kb)); m0 = min(m0, kb);
+                        m1 = min(m1, max(m0, kc)); m0 = min(m0, kc);
+                        m1 = min(m1, max(m0, kd)); m0 = min(m0, kd);
                     }
-                }
+                } else m0 = min(min(m0, min(ka, kb)), min(kc, kd));
             }
         }
         if (t + 1 < ntiles) stage(t + 1, nx);                     // buffer (t + 1) & 1: tile t - 1's MMAs have read it (their commit was waited for)
@@ -114,11 +123,14 @@ template <bool TOP2> __global__ void __launch_bounds__(UM_THREADS) k_match_umma(
     if (warp == 0) um_tmem_free(tm, 256);
     if (failed && lane == 0) atomicOr(status, ORBX_DS_INTERNAL);
     // the two warps that hold the two column halves of a query: merge, then write like k_match_partial
-    if (ehalf == 1) { s_m[0][eq] = (uint32_t)m0; s_m[1][eq] = (uint32_t)m1; }
+    if (ehalf > 0) { s_m[ehalf - 1][0][eq] = (uint32_t)m0; s_m[ehalf - 1][1][eq] = (uint32_t)m1; }
     __syncthreads();
     if (ehalf == 0) {
-        const int x0 = (int)s_m[0][eq], x1 = (int)s_m[1][eq];
-        m1 = min(max(m0, x0), min(m1, x1)); m0 = min(m0, x0);
+#pragma unroll
+        for (int o = 0; o < 3; o++) {
+            const int x0 = (int)s_m[o][0][eq], x1 = (int)s_m[o][1][eq];
+            m1 = min(max(m0, x0), min(m1, x1)); m0 = min(m0, x0);
+        }
         const int qrow = blockIdx.x * 128 + eq;
         if (qrow < nq) {
             // back to unsigned keys with the query's popcount: distance << 22 | local row; a dead row carries >= 511 << 22
@@ -136,5 +148,5 @@ void launch_match_umma(orbx_handle *h, const MatchParams &P, dim3 grid, bool top
 {
     auto kern = top2 ? k_match_umma<true> : k_match_umma<false>;
     orbx_optin_smem(h, (const void *)kern, UM_SMEM);
-    orbx_launch_pdl(h, kern, grid, dim3(UM_THREADS), UM_SMEM, h->stream, P, h->d_status);
+    orbx_launch_pdl(h, kern, grid, dim3(UM_THREADS_X), UM_SMEM, h->stream, P, h->d_status);
 }

@@ -401,10 +401,12 @@ orbx_status orbx_synth_descriptors_device(orbx_handle *h, uint32_t seed, uint64_
  * chain.  MEASURED SLOWER on B200 (128 x 1280x720: 1.190 ms one chain, 1.206-1.31 ms overlapped, profiles/r02d_overlap.log): every
  * kernel of the step is instruction-issue bound, so co-resident kernels only split the issue slots and the half-batches add tails. */
 #define ORBX_OPT_OVERLAP 5
-/* ORBX_OPT_MATCH_MMA: 1 (default) = the brute-force matcher and the landmark-database top-2 query compute Hamming distances as an exact int8
- * tensor-core GEMM (popc(q ^ t) = popc(q) + popc(t) - 2 q.t on descriptors unpacked to 0/1 bytes, mma.sync m16n8k32.u8) when a call holds at
- * least 8 M descriptor pairs (a single frame pair stays on the POPC kernel: less fixed latency); 2 = always the GEMM; 0 = always the LOP3 / POPC
- * kernel.  Same results bit for bit. */
+/* ORBX_OPT_MATCH_MMA: the engine of the brute-force matcher, the landmark-database top-2 query and the association's descriptor gate.  All of
+ * them compute Hamming distances as an exact integer GEMM on descriptors unpacked to 0/1 bytes (popc(q ^ t) = popc(q) + popc(t) - 2 q.t) or with
+ * LOP3 / POPC; same results bit for bit.
+ *   1 (default) = the tensor-memory kernels (tcgen05.mma kind::i8, 128 x 128 x 256 tiles, accumulators in TMEM: k_match_umma, k_assoc_umma) when a
+ *                 call holds at least 8 M descriptor pairs; a single frame pair stays on the POPC kernel (less fixed latency)
+ *   3 = the tensor-memory kernels for every call        2 = the mma.sync m16n8k32.u8 kernels (k_match_mma, k_assoc_mma)        0 = LOP3 / POPC */
 #define ORBX_OPT_MATCH_MMA 6
 /* ORBX_OPT_FAST_DENSE: the second FAST formulation (k_fast_dense.cu): whole-level tiles of 128 x 16 pixels scored at iniThFAST into a score map
  * and a corner list, a per-corner NMS kernel restricted to the corner's cell, and a retry launch of the warp-per-cell kernel for the cells

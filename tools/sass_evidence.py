@@ -5,7 +5,7 @@ import collections, os, re, subprocess, sys
 root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 out = subprocess.run(["cuobjdump", "-sass", os.path.join(root, "dynamic-visual-slam_b200", "lib", "liborbx.so")], capture_output=True, text=True).stdout
-cols = ["UTMALDG", "UTMAPF", "SYNCS", "VABSDIFF4", "VIMNMX3", "IDP.4A", "IDP.2A", "PRMT", "POPC", "ATOMS", "REDUX"]
+cols = ["UTMALDG", "UTMAPF", "SYNCS", "UTCIMMA", "LDTM", "UTCBAR", "UTCATOMSWS", "IMMA", "VABSDIFF4", "VIMNMX3", "IDP.4A", "IDP.2A", "PRMT", "POPC", "ATOMS", "REDUX"]
 cur, counts = None, collections.OrderedDict()
 for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
@@ -20,7 +20,8 @@ for line in out.splitlines():
         counts[cur]["_total"] += 1
 with open(os.path.join(root, "profiles", tag + "_sass_evidence.md"), "w") as f:
     f.write("# SASS evidence (cuobjdump -sass of liborbx.so, sm_100a)\n\nStatic instruction counts per kernel: `UTMALDG` / `UTMAPF` = TMA tensor load / L2 prefetch "
-            "(cp.async.bulk.tensor / cp.async.bulk.prefetch.tensor), `SYNCS` = mbarrier operations, `VABSDIFF4` / `VIMNMX3` / `IDP` / `PRMT` / `POPC` = "
+            "(cp.async.bulk.tensor / cp.async.bulk.prefetch.tensor), `SYNCS` = mbarrier operations, `UTCIMMA` = tcgen05.mma kind::i8, `LDTM` = tcgen05.ld (TMEM -> registers), "
+            "`UTCBAR` = tcgen05.commit, `UTCATOMSWS` = TMEM allocation, `IMMA` = mma.sync int8, `VABSDIFF4` / `VIMNMX3` / `IDP` / `PRMT` / `POPC` = "
             "the packed-integer instructions the kernels are built on, `ATOMS` = shared-memory atomics, `REDUX` = warp reductions.\n\n")
     f.write("| kernel | SASS instr | " + " | ".join(cols) + " |\n|---|---|" + "---|" * len(cols) + "\n")
     for k, c in counts.items():
