@@ -79,7 +79,28 @@ __device__ __forceinline__ void um_tmem_free(uint32_t taddr, int ncols)
 {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void um_bar_init(uint64_t *bar)
+__device__ __forceinline__ void um_bar_init(uint64_t *bar, int count = 1)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(um_smem(bar)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(um_smem(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void um_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(um_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void um_commit(uint64_t *bar)            // arrives on `bar` when every tcgen05.mma issued so far by this thread is complete
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(um_smem(bar)) : "memory");
+}
+// wait of a pipeline role: bounded, and gives up as soon as any role of the CTA has given up (*abort), so that a lost arrival costs one bound, not
+// one per tile.  false = the pipeline is broken: leave the role loop.
+__device__ __forceinline__ bool um_wait_role(uint64_t *bar, uint32_t parity, volatile int *abort)
+{
+    uint32_t ok = 0;
+    for (int spin = 0; !ok; spin++) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(um_smem(bar)), "r"(parity) : "memory");
+        if (!ok && (spin & 1023) == 1023 && (*abort || spin > (1 << 24))) { *abort = 1; return false; }
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    return true;
 }
