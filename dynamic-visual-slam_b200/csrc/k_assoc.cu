@@ -200,106 +200,49 @@ __global__ void __launch_bounds__(256) k_assoc_mma(AssocParams P)
     }
 }
 
-// ---- tensor-memory variant (tcgen05): the tiles and the pipeline of k_match_umma (k_match_umma.cu), the gate + reprojection epilogue of k_assoc_mma ----
-// A thread reads back 64 landmark columns of its observation per tile; keys are signed and lack the observation's own popcount, so the gate is
-// key < (ceil(max_dist) << 22) - (popc(q) << 22).  Rows ascend per thread; the two threads that hold the two column halves of an observation and
-// the splits merge by (error, row).
-__global__ void __launch_bounds__(UM_THREADS) k_assoc_umma(AssocParams P, int32_t *status)
-{
-    extern __shared__ __align__(16) uint8_t um_raw[];
-    __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ uint32_t s_tmem;
-    __shared__ __align__(16) int32_t s_tk[3][UM_TILE];
-    __shared__ double s_e[128];
-    __shared__ int s_r[128];
-    __shared__ float s_d[128];
-    const int r0 = blockIdx.y * P.rows_per_split, r1 = min(P.nt, r0 + P.rows_per_split);
-    const int nrows = max(0, r1 - r0), ntiles = (nrows + UM_TILE - 1) / UM_TILE;
-    const uint4 *tbase = reinterpret_cast<const uint4 *>(P.t);
-    uint8_t *sa = um_raw + ((1024u - (um_smem(um_raw) & 1023u)) & 1023u), *sb = sa + UM_A_BYTES;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int srow = tid >> 1, shalf = tid & 1;
-    if (tid == 0) {
-        um_bar_init(&s_bar[0]); um_bar_init(&s_bar[1]);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) um_tmem_alloc(&s_tmem, 256);
+// ---- tensor-memory variant (tcgen05): the pipeline of k_match_umma (orbx_umma.h: um_pipeline) with the gate + reprojection as its read-back policy ----
+// Keys are signed and lack the observation's own popcount, so the gate is key < (ceil(max_dist) << 22) - (popc(q) << 22).  Rows ascend per
+// thread; the two threads that hold the two column halves of an observation, and the splits, merge by (error, row).
+struct AssocEpi {
+    const AssocParams &P; int r0; float qx, qy; int pq, thr;
+    AssocBest best;
+    __device__ __forceinline__ AssocEpi(const AssocParams &p, int r0_, float qx_, float qy_) : P(p), r0(r0_), qx(qx_), qy(qy_), pq(0), thr(0), best{ DBL_MAX, -1, 0.f } {}
+    __device__ __forceinline__ void begin(const uint4 a, const uint4 b)
     {
-        const int qrow = blockIdx.x * 128 + srow;
-        uint4 x = make_uint4(0u, 0u, 0u, 0u);
-        if (qrow < P.nq) x = __ldg(reinterpret_cast<const uint4 *>(P.q + (size_t)qrow * ORBX_DESC_BYTES) + shalf);
-        um_unpack(sa, srow, shalf, x);
-    }
-    const int eq = 32 * (warp & 3) + lane, ehalf = warp >> 2;
-    const int qrow = blockIdx.x * 128 + eq;
-    int pq;
-    {
-        const uint4 *qp = reinterpret_cast<const uint4 *>(P.q + (size_t)(qrow < P.nq ? qrow : 0) * ORBX_DESC_BYTES);
-        const uint4 a = __ldg(qp), b = __ldg(qp + 1);
         pq = (__popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w)) << MT_KEY_SHIFT;
+        // (float)d < max_dist for an integer d  <=>  d < ceil(max_dist); distances are at most 256
+        thr = (max(0, min(257, (int)ceilf(P.max_dist))) << MT_KEY_SHIFT) - pq;
     }
-    const float qx = qrow < P.nq ? __ldg(P.qpx + 2 * qrow) : 0.f, qy = qrow < P.nq ? __ldg(P.qpx + 2 * qrow + 1) : 0.f;
-    // (float)d < max_dist for an integer d  <=>  d < ceil(max_dist); in the signed keys that lack popc(q): key < (dlim << 22) - (popc(q) << 22)
-    const int dlim = max(0, min(257, (int)ceilf(P.max_dist)));
-    const int thr = (dlim << MT_KEY_SHIFT) - pq;
-    AssocBest best = { DBL_MAX, -1, 0.f };
-    auto fetch = [&](int t) {
-        const int lrow = t * UM_TILE + srow;
-        uint4 x = make_uint4(0u, 0u, 0u, 0u);
-        if (lrow < nrows) x = __ldg(tbase + (size_t)(r0 + lrow) * 2 + shalf);
-        return x;
-    };
-    auto stage = [&](int t, const uint4 x) {
-        um_unpack(sb + (t & 1) * UM_B_BYTES, srow, shalf, x);
-        int pc = __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
-        pc += __shfl_xor_sync(0xffffffffu, pc, 1);
-        const int lrow = t * UM_TILE + srow;
-        if (shalf == 0) s_tk[t % 3][srow] = lrow < nrows ? ((pc << MT_KEY_SHIFT) | lrow) : (int32_t)(UM_DEAD | (uint32_t)(lrow & ((1 << MT_KEY_SHIFT) - 1)));
-    };
-    auto candidate = [&](int key) {                                 // a landmark inside the descriptor gate: the fp64 reprojection of k_assoc_partial
+    __device__ __forceinline__ void candidate(int key)             // a landmark inside the descriptor gate: the fp64 reprojection of k_assoc_partial
+    {
         if (key < thr) {
             const int row = r0 + (key & ((1 << MT_KEY_SHIFT) - 1));
             const double e = reproj_error(P.pos + (size_t)row * 3, P.pose, qx, qy);
             if (e < P.max_err && e < best.e) { best.e = e; best.row = row; best.d = (float)(((uint32_t)key + (uint32_t)pq) >> MT_KEY_SHIFT); }   // rows ascend: ties keep the lowest
         }
-    };
-    if (ntiles > 0) stage(0, fetch(0));
-    um_publish();
-    const uint32_t tm = s_tmem;
-    bool failed = false;
-    for (int t = 0; t <= ntiles; t++) {
-        if (t < ntiles && tid == 0)
-            um_issue_tile(um_smem(sa), um_smem(sb + (t & 1) * UM_B_BYTES), tm + (uint32_t)((t & 1) * UM_TILE), &s_bar[t & 1]);
-        uint4 nx = make_uint4(0u, 0u, 0u, 0u);
-        if (t + 1 < ntiles) nx = fetch(t + 1);
-        if (t > 0) {
-            const int e = t - 1, buf = e & 1;
-            if (!um_wait(&s_bar[buf], (uint32_t)((e >> 1) & 1))) failed = true;
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                uint32_t v[32];
-                const int col0 = 64 * ehalf + 32 * c;
-                const uint32_t taddr = tm + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(buf * UM_TILE + col0);
-                UM_TMEM_LD32(v, taddr);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int4 *tk4 = reinterpret_cast<const int4 *>(&s_tk[e % 3][col0]);
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int4 k4 = tk4[j];
-                    const int k0 = (int)((uint32_t)k4.x - (v[4 * j] << (MT_KEY_SHIFT + 1))), k1 = (int)((uint32_t)k4.y - (v[4 * j + 1] << (MT_KEY_SHIFT + 1)));
-                    const int k2 = (int)((uint32_t)k4.z - (v[4 * j + 2] << (MT_KEY_SHIFT + 1))), k3 = (int)((uint32_t)k4.w - (v[4 * j + 3] << (MT_KEY_SHIFT + 1)));
-                    if (min(min(k0, k1), min(k2, k3)) < thr) { candidate(k0); candidate(k1); candidate(k2); candidate(k3); }      // rare
-                }
-            }
-        }
-        if (t + 1 < ntiles) stage(t + 1, nx);
-        um_publish();
     }
-    if (warp == 0) um_tmem_free(tm, 256);
-    if (failed && lane == 0) atomicOr(status, ORBX_DS_INTERNAL);
-    if (ehalf == 1) { s_e[eq] = best.e; s_r[eq] = best.row; s_d[eq] = best.d; }
+    // inline on purpose: as an out-of-line call (by reference or by value) the rare path measured 15 % slower — the call constrains the registers of the loop
+    __device__ __forceinline__ void keys4(int ka, int kb, int kc, int kd)
+    {
+        if (min(min(ka, kb), min(kc, kd)) < thr) { candidate(ka); candidate(kb); candidate(kc); candidate(kd); }      // rare
+    }
+};
+__global__ void __launch_bounds__(UM_THREADS, 2) k_assoc_umma(const __grid_constant__ AssocParams P, int32_t *status)
+{
+    extern __shared__ __align__(16) uint8_t um_raw[];
+    __shared__ double s_e[128];
+    __shared__ int s_r[128];
+    __shared__ float s_d[128];
+    const int r0 = blockIdx.y * P.rows_per_split, r1 = min(P.nt, r0 + P.rows_per_split);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, eq = 32 * (warp & 3) + lane, qrow = blockIdx.x * 128 + eq;
+    const bool reader = warp >= 8 && qrow < P.nq;
+    AssocEpi epi(P, r0, reader ? __ldg(P.qpx + 2 * qrow) : 0.f, reader ? __ldg(P.qpx + 2 * qrow + 1) : 0.f);
+    const bool ok = um_pipeline(um_raw, P.q, P.nq, blockIdx.x * 128, reinterpret_cast<const uint4 *>(P.t), r0, max(0, r1 - r0), epi);
+    if (!ok && threadIdx.x == 0) atomicOr(status, ORBX_DS_INTERNAL);
+    if (warp >= 12) { s_e[eq] = epi.best.e; s_r[eq] = epi.best.row; s_d[eq] = epi.best.d; }
     __syncthreads();
-    if (ehalf == 0 && qrow < P.nq) {
+    if (warp >= 8 && warp < 12 && qrow < P.nq) {
+        AssocBest best = epi.best;
         const double e1 = s_e[eq]; const int rw1 = s_r[eq];
         if (rw1 >= 0 && (best.row < 0 || e1 < best.e || (e1 == best.e && rw1 < best.row))) { best.e = e1; best.row = rw1; best.d = s_d[eq]; }
         orbx_assoc r;
