@@ -222,9 +222,13 @@ struct AssocEpi {
         }
     }
     // inline on purpose: as an out-of-line call (by reference or by value) the rare path measured 15 % slower — the call constrains the registers of the loop
-    __device__ __forceinline__ void keys4(int ka, int kb, int kc, int kd)
+    __device__ __forceinline__ void keys8(const int (&k)[8])
     {
-        if (min(min(ka, kb), min(kc, kd)) < thr) { candidate(ka); candidate(kb); candidate(kc); candidate(kd); }      // rare
+        const int kmin = min(min(min(k[0], k[1]), min(k[2], k[3])), min(min(k[4], k[5]), min(k[6], k[7])));
+        if (kmin < thr) {                                                                              // rare
+#pragma unroll
+            for (int i = 0; i < 8; i++) candidate(k[i]);
+        }
     }
 };
 __global__ void __launch_bounds__(UM_THREADS, 2) k_assoc_umma(const __grid_constant__ AssocParams P, int32_t *status)

@@ -22,19 +22,17 @@ template <bool TOP2> struct MatchEpi {
     {
         pq = (__popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w)) << MT_KEY_SHIFT;
     }
-    __device__ __forceinline__ void keys4(int ka, int kb, int kc, int kd)
+    __device__ __forceinline__ void keys8(const int (&k)[8])
     {
+        const int kmin = min(min(min(k[0], k[1]), min(k[2], k[3])), min(min(k[4], k[5]), min(k[6], k[7])));
         if (TOP2) {
-            // the second best only moves when a key undercuts it — ~2 ln(n) times per query over n rows: test the smallest of four keys against
-            // it (two three-input minima and a compare per four pairs) and update (best, second best) on that rare path
-            const int k4min = min(min(ka, kb), min(kc, kd));
-            if (k4min < m1) {
-                m1 = min(m1, max(m0, ka)); m0 = min(m0, ka);
-                m1 = min(m1, max(m0, kb)); m0 = min(m0, kb);
-                m1 = min(m1, max(m0, kc)); m0 = min(m0, kc);
-                m1 = min(m1, max(m0, kd)); m0 = min(m0, kd);
+            // the second best only moves when a key undercuts it — ~2 ln(n) times per query over n rows: test the smallest of eight keys against
+            // it (four three-input minima and a compare per eight pairs) and update (best, second best) on that rare path
+            if (kmin < m1) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) { m1 = min(m1, max(m0, k[i])); m0 = min(m0, k[i]); }
             }
-        } else m0 = min(min(m0, min(ka, kb)), min(kc, kd));
+        } else m0 = min(m0, kmin);
     }
 };
 

@@ -112,10 +112,10 @@ __device__ __forceinline__ bool um_wait_role(uint64_t *bar, uint32_t parity, vol
 //   producers --b_full[2]--> MMA issuer --acc_full[2]--> read-back warps        (tcgen05.commit arrives on acc_full and on b_empty)
 //   producers <--b_empty[2]-- MMA issuer <--acc_empty[2]-- read-back warps
 // Key bases (popc(t) << 22 | local row; 511 << 22 for rows past the end) live in a ring of eight tiles: an entry is read up to four tiles after it
-// was written.  The read-back hands every four keys to the policy EPI:
+// was written.  The read-back hands eight keys at a time to the policy EPI:
 //   keys are SIGNED and lack the query's own popcount (a per-thread constant):  key = (popc(t) - 2 q.t) << 22 | local row, in [-2^30, 2^31)
 //   EPI::begin(q words)          once per read-back thread (its query's descriptor)
-//   EPI::keys4(ka, kb, kc, kd)   four consecutive train rows, ascending
+//   EPI::keys8(k[8])             eight consecutive train rows, ascending
 // Every wait is bounded and gives up when any role has given up: returns false if the pipeline broke (results are then undefined; no hang).
 template <class EPI>
 __device__ __forceinline__ bool um_pipeline(uint8_t *um_raw, const uint8_t *qbase, int nq, int q0, const uint4 *tbase, int r0, int nrows, EPI &epi)
@@ -204,11 +204,15 @@ __device__ __forceinline__ bool um_pipeline(uint8_t *um_raw, const uint8_t *qbas
                 }
                 const int4 *tk4 = reinterpret_cast<const int4 *>(&s_tk[t & 7][col0]);
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int4 k4 = tk4[j];                                        // one broadcast load: the key bases of four train rows
-                    const uint32_t *vv = &v[4 * j];
-                    epi.keys4((int)((uint32_t)k4.x - (vv[0] << (MT_KEY_SHIFT + 1))), (int)((uint32_t)k4.y - (vv[1] << (MT_KEY_SHIFT + 1))),
-                              (int)((uint32_t)k4.z - (vv[2] << (MT_KEY_SHIFT + 1))), (int)((uint32_t)k4.w - (vv[3] << (MT_KEY_SHIFT + 1))));
+                for (int j = 0; j < 4; j++) {
+                    const int4 ka4 = tk4[2 * j], kb4 = tk4[2 * j + 1];             // two broadcast loads: the key bases of eight train rows
+                    const uint32_t *vv = &v[8 * j];
+                    int k[8];
+                    k[0] = (int)((uint32_t)ka4.x - (vv[0] << (MT_KEY_SHIFT + 1))); k[1] = (int)((uint32_t)ka4.y - (vv[1] << (MT_KEY_SHIFT + 1)));
+                    k[2] = (int)((uint32_t)ka4.z - (vv[2] << (MT_KEY_SHIFT + 1))); k[3] = (int)((uint32_t)ka4.w - (vv[3] << (MT_KEY_SHIFT + 1)));
+                    k[4] = (int)((uint32_t)kb4.x - (vv[4] << (MT_KEY_SHIFT + 1))); k[5] = (int)((uint32_t)kb4.y - (vv[5] << (MT_KEY_SHIFT + 1)));
+                    k[6] = (int)((uint32_t)kb4.z - (vv[6] << (MT_KEY_SHIFT + 1))); k[7] = (int)((uint32_t)kb4.w - (vv[7] << (MT_KEY_SHIFT + 1)));
+                    epi.keys8(k);
                 }
             }
         }
