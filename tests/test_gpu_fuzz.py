@@ -1,5 +1,6 @@
 """Randomised parity sweep (tools/fuzz_parity.py): random frame sizes, feature counts, scale factors, level counts, FAST thresholds and frame
-contents; the CUDA path with both FAST formulations against the C oracle and the reference's compiled ORBextractor.cpp.  The tool runs
+contents; the CUDA path with both FAST formulations against the C oracle and the reference's compiled ORBextractor.cpp, then the three matcher
+engines on random problem sizes.  The tool runs
 hundreds of cases on demand (620 cases over two seeds at the end of round 2: 0 mismatches); the test keeps a short sweep in the suite."""
 import os
 import subprocess

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Randomised parity sweep on the GPU box: random frame sizes / nfeatures / scale factors / thresholds / contents, the CUDA path (both FAST
-formulations) against the C oracle and, where built, the reference's compiled ORBextractor.cpp.  usage: fuzz_parity.py [cases] [seed]"""
+formulations) against the C oracle and, where built, the reference's compiled ORBextractor.cpp; then the three matcher engines (POPC, mma.sync,
+tcgen05) on random problem sizes against BFMatcher's restatement.  usage: fuzz_parity.py [cases] [seed]"""
 import sys, os, numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "dynamic-visual-slam_b200", "python")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -54,5 +55,27 @@ for case in range(ncases):
                 print("ORACLE != COMPILED REFERENCE case", case, dict(w=w, h=h, nf=nf, sf=sf, nl=nl, ini=ini, mn=mn, kind=kind), flush=True)
     finally:
         ex.close()
+# ---- matcher engines (POPC, mma.sync, tcgen05) on random problem sizes: k = 1, k = 2, threshold ----
+em = orbx.ORBextractor(max_width=320, max_height=240)
+for case in range(ncases):
+    nq, nt = int(rng.integers(1, 2500)), int(rng.integers(1, 6000))
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    if nt > 3:                                                       # near neighbours and exact duplicates (ties -> lowest index)
+        for i in range(0, nq, 3):
+            q[i] = t[int(rng.integers(0, nt))]; q[i, int(rng.integers(0, 32))] ^= np.uint8(1 << int(rng.integers(0, 8)))
+        t[nt - 1] = t[0]
+    want1, want2 = co.match(q, t), co.knn2(q, t)
+    for eng in (0, 2, 3):
+        em.set_match_mma(eng)
+        m = em.match(q, t, k=1)
+        k2 = em.match(q, t, k=2).reshape(-1, 2)
+        good = em.match(q, t, k=1, max_dist=60.0)
+        ok = (np.array_equal(m.view(np.uint8), want1.view(np.uint8)) and np.array_equal(k2["trainIdx"], want2["trainIdx"]) and np.array_equal(k2["distance"], want2["distance"])
+              and np.array_equal(good.view(np.uint8), want1[want1["distance"] < 60.0].view(np.uint8)))
+        if not ok:
+            bad += 1
+            print("MATCH MISMATCH case", case, dict(nq=nq, nt=nt, engine=eng), flush=True)
+em.close()
 print("fuzz: %d cases, %d mismatches, compiled reference %s" % (ncases, bad, "checked" if have_ref else "absent"))
 sys.exit(1 if bad else 0)
