@@ -1293,7 +1293,7 @@ extern "C" orbx_status orbx_match(orbx_handle *h, const uint8_t *q, int32_t nq, 
     if (st != ORBX_OK) return st;
     int32_t n = 0;
     ORBX_CUDA(h, cudaMemcpyAsync(&n, h->d_mcount, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    { const orbx_status ds = check_device_status(h); if (ds != ORBX_OK) return ds; }      // synchronises; a broken tensor-memory pipeline (never seen) must not return silently
     if (n > 0) ORBX_CUDA(h, cudaMemcpy(out, h->d_mout, (size_t)n * sizeof(orbx_dmatch), cudaMemcpyDeviceToHost));
     *n_out = n;
     return ORBX_OK;
@@ -1399,7 +1399,7 @@ extern "C" orbx_status orbx_db_query_top2(orbx_db *db, const uint8_t *q, int32_t
     if (st != ORBX_OK) return st;
     if ((st = orbx_db_query_top2_device(db, db->d_q, nq, db->d_out)) != ORBX_OK) return st;
     ORBX_CUDA(h, cudaMemcpyAsync(out, db->d_out, (size_t)nq * sizeof(orbx_top2), cudaMemcpyDeviceToHost, h->stream));
-    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    { const orbx_status ds = check_device_status(h); if (ds != ORBX_OK) return ds; }      // synchronises; a broken tensor-memory pipeline (never seen) must not return silently
     return ORBX_OK;
 }
 extern "C" orbx_status orbx_merge_top2_device(orbx_handle *h, const orbx_top2 *d_parts, int32_t nshards, int32_t nq, orbx_top2 *d_out)
@@ -1477,7 +1477,7 @@ extern "C" orbx_status orbx_db_associate(orbx_db *db, const uint8_t *q, const fl
     ORBX_CUDA(h, cudaMemcpyAsync(db->d_qpx, qpx, (size_t)nq * 2 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     if ((st = orbx_db_associate_device(db, db->d_q, db->d_qpx, nq, pose, max_dist, max_err, (orbx_assoc *)db->d_out)) != ORBX_OK) return st;
     ORBX_CUDA(h, cudaMemcpyAsync(out, db->d_out, (size_t)nq * sizeof(orbx_assoc), cudaMemcpyDeviceToHost, h->stream));
-    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    { const orbx_status ds = check_device_status(h); if (ds != ORBX_OK) return ds; }      // synchronises; a broken tensor-memory pipeline (never seen) must not return silently
     return ORBX_OK;
 }
 extern "C" orbx_status orbx_merge_assoc_device(orbx_handle *h, const orbx_assoc *d_parts, int32_t nshards, int32_t nq, orbx_assoc *d_out)
