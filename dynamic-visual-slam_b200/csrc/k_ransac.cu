@@ -69,6 +69,114 @@ __global__ void __launch_bounds__(256) k_fmat_best(const int32_t *counts, int nh
     if (best_mask) for (int i = threadIdx.x; i < n; i += blockDim.x) best_mask[i] = masks[(size_t)b * n + i];
 }
 
+// ---- pose hypotheses: the scoring loop of cv::solvePnPRansac (Frontend::estimateCameraPose, frontend.cpp:906-923) ----
+// PnPRansacCallback::computeError projects every 3D point with cv::projectPoints (double; the distortion terms vanish for the zero coefficients of
+// a rectified stream), stores the projections as float and takes the squared pixel distance in float; inlier <=> err <= (float)(4.0 * 4.0).
+// One CTA per hypothesis (R row-major 3x3 = cv::Rodrigues(rvec), t), every operation rounded on its own; k_fmat_best picks the winner.
+struct PnpParams {
+    const float *p3, *p2; int n;
+    const double *Rt; int nh;                 // [nh][12]: R (9), t (3)
+    double fx, fy, cx, cy; float t2;
+    int32_t *counts; uint8_t *masks;          // masks: [nh][n]
+};
+__global__ void __launch_bounds__(256) k_pnp_score(PnpParams P)
+{
+    __shared__ int s_cnt;
+    const int hi = blockIdx.x;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    double R[9], t[3];
+#pragma unroll
+    for (int i = 0; i < 9; i++) R[i] = P.Rt[(size_t)hi * 12 + i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) t[i] = P.Rt[(size_t)hi * 12 + 9 + i];
+    int local = 0;
+    for (int i = threadIdx.x; i < P.n; i += blockDim.x) {
+        const double X = (double)P.p3[3 * i], Y = (double)P.p3[3 * i + 1], Z = (double)P.p3[3 * i + 2];
+        double x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(R[0], X), __dmul_rn(R[1], Y)), __dmul_rn(R[2], Z)), t[0]);
+        double y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(R[3], X), __dmul_rn(R[4], Y)), __dmul_rn(R[5], Z)), t[1]);
+        double z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(R[6], X), __dmul_rn(R[7], Y)), __dmul_rn(R[8], Z)), t[2]);
+        z = z != 0.0 ? __ddiv_rn(1.0, z) : 1.0;
+        x = __dmul_rn(x, z); y = __dmul_rn(y, z);
+        const float u = (float)__dadd_rn(__dmul_rn(x, P.fx), P.cx), v = (float)__dadd_rn(__dmul_rn(y, P.fy), P.cy);
+        const float dx = __fsub_rn(P.p2[2 * i], u), dy = __fsub_rn(P.p2[2 * i + 1], v);
+        const float e = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        const bool in = e <= P.t2;
+        P.masks[(size_t)hi * P.n + i] = in ? 1 : 0;
+        local += in;
+    }
+    local = __reduce_add_sync(0xffffffffu, local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&s_cnt, local);
+    __syncthreads();
+    if (threadIdx.x == 0) P.counts[hi] = s_cnt;
+}
+void launch_pnp_score(orbx_handle *h, const float *d_p3, const float *d_p2, int n, const double *d_Rt, int nh, double fx, double fy, double cx, double cy,
+                      float t2, int32_t *d_counts, uint8_t *d_masks, int32_t *d_best, uint8_t *d_best_mask)
+{
+    PnpParams P;
+    P.p3 = d_p3; P.p2 = d_p2; P.n = n; P.Rt = d_Rt; P.nh = nh; P.fx = fx; P.fy = fy; P.cx = cx; P.cy = cy; P.t2 = t2; P.counts = d_counts; P.masks = d_masks;
+    { ProfScope ps(h, ORBX_K_OTHER); k_pnp_score<<<nh, 256, 0, h->stream>>>(P); }
+    { ProfScope ps(h, ORBX_K_OTHER); k_fmat_best<<<1, 256, 0, h->stream>>>(d_counts, nh, d_masks, n, d_best, d_best_mask); }
+}
+
+// ---- the 3D-2D correspondences in front of it (frontend.cpp:858-892): stable compaction of the matches whose previous-frame keypoint has a usable depth ----
+// One CTA; match order is kept (OpenCV's RANSAC samples by index).  std::round on floats = half away from zero; X = (u - cx) * d / fx in float.
+struct PnpPointsParams {
+    const orbx_keypoint *prev, *curr; const orbx_dmatch *m; int nm, nprev, ncurr;
+    const uint16_t *depth; int w, h; size_t dstep;
+    float fx, fy, cx, cy;
+    float *p3, *p2; int32_t *n_out; int32_t *status;
+};
+__global__ void __launch_bounds__(1024) k_pnp_points(PnpPointsParams P)
+{
+    __shared__ int s_w[32];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < P.nm; i0 += 1024) {
+        const int i = i0 + threadIdx.x;
+        bool keep = false;
+        float X = 0.f, Y = 0.f, d = 0.f, u2 = 0.f, v2 = 0.f;
+        if (i < P.nm) {
+            const orbx_dmatch mm = P.m[i];
+            if (mm.trainIdx < 0 || mm.trainIdx >= P.nprev || mm.queryIdx < 0 || mm.queryIdx >= P.ncurr) atomicOr(P.status, ORBX_DS_BAD_INDEX);
+            else {
+                const float px = P.prev[mm.trainIdx].x, py = P.prev[mm.trainIdx].y;
+                const int xp = (int)roundf(px), yp = (int)roundf(py);
+                if (xp >= 0 && yp >= 0 && xp < P.w && yp < P.h) {
+                    d = __fmul_rn((float)*reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(P.depth) + (size_t)yp * P.dstep + 2 * (size_t)xp), 0.001f);
+                    if (!(d <= 0.3f || d > 3.0f)) {
+                        keep = true;
+                        X = __fdiv_rn(__fmul_rn(__fsub_rn(px, P.cx), d), P.fx); Y = __fdiv_rn(__fmul_rn(__fsub_rn(py, P.cy), d), P.fy);
+                        u2 = P.curr[mm.queryIdx].x; v2 = P.curr[mm.queryIdx].y;
+                    }
+                }
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_w[wid] = __popc(bal);
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < wid; w++) before += s_w[w];
+        const int pos = s_base + before + __popc(bal & ((1u << lane) - 1u));
+        if (keep) { P.p3[3 * pos] = X; P.p3[3 * pos + 1] = Y; P.p3[3 * pos + 2] = d; P.p2[2 * pos] = u2; P.p2[2 * pos + 1] = v2; }
+        __syncthreads();
+        if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 32; w++) tot += s_w[w]; s_base += tot; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *P.n_out = s_base;
+}
+void launch_pnp_points(orbx_handle *h, const orbx_keypoint *d_prev, int nprev, const orbx_keypoint *d_curr, int ncurr, const orbx_dmatch *d_m, int nm,
+                       const uint16_t *d_depth, int w, int hgt, size_t dstep, float fx, float fy, float cx, float cy, float *d_p3, float *d_p2, int32_t *d_n)
+{
+    PnpPointsParams P;
+    P.prev = d_prev; P.curr = d_curr; P.m = d_m; P.nm = nm; P.nprev = nprev; P.ncurr = ncurr; P.depth = d_depth; P.w = w; P.h = hgt; P.dstep = dstep;
+    P.fx = fx; P.fy = fy; P.cx = cx; P.cy = cy; P.p3 = d_p3; P.p2 = d_p2; P.n_out = d_n; P.status = h->d_status;
+    ProfScope ps(h, ORBX_K_OTHER);
+    k_pnp_points<<<1, 1024, 0, h->stream>>>(P);
+}
+
 // ---- hypothesis generation on the device: one thread = one minimal sample -> one fundamental matrix (normalised 8-point) ----
 // OpenCV's FM_RANSAC draws 7-point samples from its own cv::RNG and solves a cubic; neither the sequence nor the solver's root choice can be
 // reproduced elsewhere, so this is NOT a restatement of it but the same estimator family: Hartley-normalised 8-point on 8 distinct

@@ -1628,6 +1628,74 @@ extern "C" orbx_status orbx_fmat_score(orbx_handle *h, const float *pts1, const 
     return ORBX_OK;
 }
 
+// cv::solvePnPRansac's scoring loop (frontend.cpp:906-923): nh poses (R row-major 3x3, t) against n 3D-2D correspondences
+extern "C" orbx_status orbx_pnp_score(orbx_handle *h, const float *pts3d, const float *pts2d, int32_t n, const double *Rt, int32_t nh,
+                                      double fx, double fy, double cx, double cy, double threshold, int32_t *inlier_counts, int32_t *best, uint8_t *best_mask)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    if (n < 0 || nh < 1 || !Rt || !best || (n > 0 && (!pts3d || !pts2d)) || !(threshold >= 0)) { h->err = "bad pose scoring arguments"; return ORBX_E_INVALID; }
+    if (h->pending[0].active || h->pending[1].active) { h->err = "an asynchronous batch is outstanding: call orbx_batch_wait first"; return ORBX_E_INVALID; }
+    orbx_status st;
+    const size_t b3 = align_up((size_t)std::max(n, 1) * 12, 16), b2 = align_up((size_t)std::max(n, 1) * 8, 16), bf = align_up((size_t)nh * 96, 16), bc = align_up((size_t)nh * 4, 16),
+                 bm = align_up((size_t)nh * std::max(n, 1), 16);
+    if ((st = grow(h, &h->d_mq, &h->mq_cap, b3 + b2 + bf + bc + 16 + align_up((size_t)std::max(n, 1), 16))) != ORBX_OK) return st;
+    if ((st = grow(h, &h->d_mt, &h->mt_cap, bm)) != ORBX_OK) return st;
+    float *d_p3 = (float *)h->d_mq, *d_p2 = (float *)(h->d_mq + b3);
+    double *d_Rt = (double *)(h->d_mq + b3 + b2);
+    int32_t *d_c = (int32_t *)(h->d_mq + b3 + b2 + bf), *d_b = (int32_t *)(h->d_mq + b3 + b2 + bf + bc);
+    uint8_t *d_bm = h->d_mq + b3 + b2 + bf + bc + 16;
+    if (n > 0) {
+        ORBX_CUDA(h, cudaMemcpyAsync(d_p3, pts3d, (size_t)n * 12, cudaMemcpyHostToDevice, h->stream));
+        ORBX_CUDA(h, cudaMemcpyAsync(d_p2, pts2d, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    ORBX_CUDA(h, cudaMemcpyAsync(d_Rt, Rt, (size_t)nh * 96, cudaMemcpyHostToDevice, h->stream));
+    launch_pnp_score(h, d_p3, d_p2, n, d_Rt, nh, fx, fy, cx, cy, (float)(threshold * threshold), d_c, h->d_mt, d_b, d_bm);
+    ORBX_CUDA(h, cudaMemcpyAsync(best, d_b, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (inlier_counts) ORBX_CUDA(h, cudaMemcpyAsync(inlier_counts, d_c, (size_t)nh * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (best_mask && n > 0) ORBX_CUDA(h, cudaMemcpyAsync(best_mask, d_bm, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    ORBX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+// the 3D-2D correspondences of Frontend::estimateCameraPose (frontend.cpp:858-892), in match order
+extern "C" orbx_status orbx_pnp_points(orbx_handle *h, const orbx_keypoint *prev_kps, int32_t n_prev, const orbx_keypoint *curr_kps, int32_t n_curr,
+                                       const orbx_dmatch *matches, int32_t nm, const uint16_t *prev_depth, int32_t width, int32_t height, size_t dstep,
+                                       float fx, float fy, float cx, float cy, float *pts3d, float *pts2d, int32_t *n_out)
+{
+    if (!h) return ORBX_E_INVALID;
+    cudaSetDevice(h->device);
+    if (nm < 0 || n_prev < 0 || n_curr < 0 || !n_out || (nm > 0 && (!matches || !prev_kps || !curr_kps || !prev_depth || !pts3d || !pts2d)) || width < 1 || height < 1 ||
+        dstep < (size_t)width * 2 || (dstep & 1)) { h->err = "bad correspondence arguments"; return ORBX_E_INVALID; }
+    if (h->pending[0].active || h->pending[1].active) { h->err = "an asynchronous batch is outstanding: call orbx_batch_wait first"; return ORBX_E_INVALID; }
+    *n_out = 0;
+    if (nm == 0) return ORBX_OK;
+    orbx_status st;
+    const size_t bk0 = align_up((size_t)std::max(n_prev, 1) * sizeof(orbx_keypoint), 16), bk1 = align_up((size_t)std::max(n_curr, 1) * sizeof(orbx_keypoint), 16),
+                 bmm = align_up((size_t)nm * sizeof(orbx_dmatch), 16), b3 = align_up((size_t)nm * 12, 16), b2 = align_up((size_t)nm * 8, 16);
+    if ((st = grow(h, &h->d_mq, &h->mq_cap, bk0 + bk1 + bmm + b3 + b2 + 16)) != ORBX_OK) return st;
+    if ((st = grow(h, (uint8_t **)&h->d_depth_in, &h->depth_cap, (size_t)height * dstep)) != ORBX_OK) return st;
+    orbx_keypoint *d_k0 = (orbx_keypoint *)h->d_mq, *d_k1 = (orbx_keypoint *)(h->d_mq + bk0);
+    orbx_dmatch *d_m = (orbx_dmatch *)(h->d_mq + bk0 + bk1);
+    float *d_p3 = (float *)(h->d_mq + bk0 + bk1 + bmm), *d_p2 = (float *)(h->d_mq + bk0 + bk1 + bmm + b3);
+    int32_t *d_n = (int32_t *)(h->d_mq + bk0 + bk1 + bmm + b3 + b2);
+    ORBX_CUDA(h, cudaMemcpyAsync(d_k0, prev_kps, (size_t)n_prev * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(h, cudaMemcpyAsync(d_k1, curr_kps, (size_t)n_curr * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(h, cudaMemcpyAsync(d_m, matches, (size_t)nm * sizeof(orbx_dmatch), cudaMemcpyHostToDevice, h->stream));
+    ORBX_CUDA(h, cudaMemcpyAsync(h->d_depth_in, prev_depth, (size_t)height * dstep, cudaMemcpyHostToDevice, h->stream));
+    launch_pnp_points(h, d_k0, n_prev, d_k1, n_curr, d_m, nm, h->d_depth_in, width, height, dstep, fx, fy, cx, cy, d_p3, d_p2, d_n);
+    int32_t n = 0;
+    ORBX_CUDA(h, cudaMemcpyAsync(&n, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    st = check_device_status(h);                                   // synchronises; a match index outside its keypoint array -> ORBX_E_INVALID
+    if (st != ORBX_OK) return st;
+    if (n > 0) {
+        ORBX_CUDA(h, cudaMemcpy(pts3d, d_p3, (size_t)n * 12, cudaMemcpyDeviceToHost));
+        ORBX_CUDA(h, cudaMemcpy(pts2d, d_p2, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    }
+    *n_out = n;
+    return ORBX_OK;
+}
+
 extern "C" orbx_status orbx_fmat_ransac(orbx_handle *h, const float *pts1, const float *pts2, int32_t n, int32_t nh, double threshold, uint32_t seed,
                                         double *F_out, uint8_t *best_mask, int32_t *n_inliers)
 {

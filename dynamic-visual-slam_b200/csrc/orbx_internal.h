@@ -298,5 +298,9 @@ void launch_test_atan2(orbx_handle *h, const float *d_y, const float *d_x, int n
 void launch_trig_checksum(orbx_handle *h, uint32_t first, uint32_t last, unsigned long long *d_sums);
 double run_popc_bench(orbx_handle *h);
 void launch_fmat_hypotheses(orbx_handle *h, const float *d_p1, const float *d_p2, int n, int nh, uint32_t seed, double *d_F);
+void launch_pnp_score(orbx_handle *h, const float *d_p3, const float *d_p2, int n, const double *d_Rt, int nh, double fx, double fy, double cx, double cy,
+                      float t2, int32_t *d_counts, uint8_t *d_masks, int32_t *d_best, uint8_t *d_best_mask);   // k_ransac.cu
+void launch_pnp_points(orbx_handle *h, const orbx_keypoint *d_prev, int nprev, const orbx_keypoint *d_curr, int ncurr, const orbx_dmatch *d_m, int nm,
+                       const uint16_t *d_depth, int w, int hgt, size_t dstep, float fx, float fy, float cx, float cy, float *d_p3, float *d_p2, int32_t *d_n);
 void launch_fmat_score(orbx_handle *h, const float *d_p1, const float *d_p2, int n, const double *d_F, int nh, float t2,
                        int32_t *d_counts, uint8_t *d_masks, int32_t *d_best, uint8_t *d_best_mask);

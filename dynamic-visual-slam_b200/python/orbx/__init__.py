@@ -134,6 +134,8 @@ def load():
         "orbx_track_batch_submit": (i32, [vp, vp, i32, i32, i32, sz, vp, sz, vp, vp, i32, vp, vp, vp, f32, vp]),
         "orbx_batch_wait": (i32, [vp, i32]),
         "orbx_fmat_score": (i32, [vp, vp, vp, i32, vp, i32, ct.c_double, vp, vp, vp]),
+        "orbx_pnp_points": (i32, [vp, vp, i32, vp, i32, vp, i32, vp, i32, i32, ct.c_size_t, ct.c_float, ct.c_float, ct.c_float, ct.c_float, vp, vp, vp]),
+        "orbx_pnp_score": (i32, [vp, vp, vp, i32, vp, i32, ct.c_double, ct.c_double, ct.c_double, ct.c_double, ct.c_double, vp, vp, vp]),
         "orbx_fmat_ransac": (i32, [vp, vp, vp, i32, i32, ct.c_double, u32, vp, vp, vp]),
         "orbx_comm_get_unique_id": (i32, [vp]),
         "orbx_comm_last_error": (ct.c_char_p, []),
@@ -420,6 +422,28 @@ class ORBextractor:
             self._check(self.L.orbx_extract_batch_boxes(self._h, _p(frames), nf, w, h, frames.strides[1], dptr, dstep,
                                                         _p(boxes), _p(off), ct.c_uint64(drop_class_mask), _p(kps), _p(desc), cap, _p(counts)))
         return kps, desc, counts
+
+    def pnp_points(self, prev_kps, curr_kps, matches, prev_depth, fx, fy, cx, cy):
+        """The 3D-2D correspondences of Frontend::estimateCameraPose (frontend.cpp:858-892): (points3d [n,3], points2d [n,2]) in match order."""
+        prev_kps = np.ascontiguousarray(prev_kps, KP_DTYPE); curr_kps = np.ascontiguousarray(curr_kps, KP_DTYPE)
+        matches = np.ascontiguousarray(matches, DM_DTYPE); depth = np.ascontiguousarray(prev_depth, np.uint16)
+        nm = len(matches)
+        p3 = np.zeros((max(nm, 1), 3), np.float32); p2 = np.zeros((max(nm, 1), 2), np.float32)
+        n = ct.c_int32()
+        self._check(self.L.orbx_pnp_points(self._h, _p(prev_kps), len(prev_kps), _p(curr_kps), len(curr_kps), _p(matches), nm, _p(depth), depth.shape[1], depth.shape[0],
+                                           depth.strides[0], ct.c_float(fx), ct.c_float(fy), ct.c_float(cx), ct.c_float(cy), _p(p3), _p(p2), ct.byref(n)))
+        return p3[:n.value].copy(), p2[:n.value].copy()
+
+    def pnp_score(self, pts3d, pts2d, R, t, fx, fy, cx, cy, threshold=4.0):
+        """Inlier counts of pose hypotheses (R [nh,3,3], t [nh,3]) under cv::solvePnPRansac's error (frontend.cpp:911-923);
+        returns (counts[nh], best index, mask[n] of the best)."""
+        pts3d = np.ascontiguousarray(pts3d, np.float32).reshape(-1, 3); pts2d = np.ascontiguousarray(pts2d, np.float32).reshape(-1, 2)
+        R = np.ascontiguousarray(R, np.float64).reshape(-1, 9); t = np.ascontiguousarray(t, np.float64).reshape(-1, 3)
+        Rt = np.ascontiguousarray(np.concatenate([R, t], 1))
+        counts = np.zeros(len(Rt), np.int32); mask = np.zeros(max(len(pts3d), 1), np.uint8); best = ct.c_int32()
+        self._check(self.L.orbx_pnp_score(self._h, _p(pts3d), _p(pts2d), len(pts3d), _p(Rt), len(Rt), ct.c_double(fx), ct.c_double(fy), ct.c_double(cx), ct.c_double(cy),
+                                          ct.c_double(threshold), _p(counts), ct.byref(best), _p(mask)))
+        return counts, best.value, mask[:len(pts3d)]
 
     def fmat_score(self, pts1, pts2, F, threshold=2.0):
         """Inlier counts of fundamental-matrix hypotheses F [nh, 3, 3] under OpenCV's RANSAC error (frontend.cpp:1134-1154);

@@ -340,6 +340,22 @@ orbx_status orbx_fmat_score(orbx_handle *h, const float *pts1, const float *pts2
 orbx_status orbx_fmat_ransac(orbx_handle *h, const float *pts1, const float *pts2, int32_t n, int32_t nh, double threshold, uint32_t seed,
                              double *F_out, uint8_t *best_mask, int32_t *n_inliers);
 
+/* ---- pose estimation, the data-parallel parts of Frontend::estimateCameraPose (frontend.cpp:843-960) ----
+ * orbx_pnp_points: the 3D-2D correspondence loop (:858-892).  For every match, in match order: the previous frame's keypoint (trainIdx) is
+ * back-projected with the depth at its rounded pixel (std::round), kept iff the pixel is inside the image and 0.3 < d <= 3.0 m;
+ * X = (u - cx) * d / fx in float (the reference's intrinsics are float members).  pts3d [nm * 3], pts2d [nm * 2] (current frame's keypoint, queryIdx).
+ * A match index outside its keypoint array: ORBX_E_INVALID.
+ * orbx_pnp_score: cv::solvePnPRansac's scoring loop (:911-923, PnPRansacCallback::computeError): nh pose hypotheses, each 12 doubles (R row-major =
+ * cv::Rodrigues(rvec), then t), against all correspondences — cv::projectPoints in double without distortion, projections stored as float, squared
+ * pixel distance in float, inlier <=> err <= (float)(threshold * threshold) (the reference passes 4.0).  inlier_counts [nh] (nullable), *best = the
+ * hypothesis with the most inliers (lowest index on ties), best_mask [n] (nullable).  The mask of a given pose equals OpenCV's bit for bit
+ * (tests/test_pnp.py pins the arithmetic against cv2.projectPoints).  Minimal-sample solves (P3P / EPnP) and the final refinement stay with the caller. */
+orbx_status orbx_pnp_points(orbx_handle *h, const orbx_keypoint *prev_kps, int32_t n_prev, const orbx_keypoint *curr_kps, int32_t n_curr,
+                            const orbx_dmatch *matches, int32_t nm, const uint16_t *prev_depth, int32_t width, int32_t height, size_t dstep,
+                            float fx, float fy, float cx, float cy, float *pts3d, float *pts2d, int32_t *n_out);
+orbx_status orbx_pnp_score(orbx_handle *h, const float *pts3d, const float *pts2d, int32_t n, const double *Rt, int32_t nh,
+                           double fx, double fy, double cx, double cy, double threshold, int32_t *inlier_counts, int32_t *best, uint8_t *best_mask);
+
 /* ---- keyframe packing: the landmark / observation loop of Frontend::publishKeyframe (frontend.cpp:731-776), SURVEY §8(f) rank 2 ----
  * For every keypoint with a depth in (0.3, 3.0) m: back-projection with the float intrinsics, world transform R*p + t in double,
  * one 80-byte record; order preserved; landmark_id = index of the keypoint in the input list, as in the reference.

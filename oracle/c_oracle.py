@@ -221,6 +221,25 @@ def fmat_inliers(p1, p2, F, thresh=2.0):
     return n, mask[:len(p1)].copy()
 
 
+def pnp_points(prev_kps, curr_kps, matches, depth, fx, fy, cx, cy):
+    """Frontend::estimateCameraPose's correspondence loop (frontend.cpp:858-892): (points3d [n,3] f32, points2d [n,2] f32) in match order"""
+    prev_kps = np.ascontiguousarray(prev_kps, KP_DTYPE); curr_kps = np.ascontiguousarray(curr_kps, KP_DTYPE)
+    matches = np.ascontiguousarray(matches, DM_DTYPE); depth = np.ascontiguousarray(depth, np.uint16)
+    p3 = np.zeros((max(len(matches), 1), 3), np.float32); p2 = np.zeros((max(len(matches), 1), 2), np.float32)
+    n = lib().orc_pnp_points(_p(prev_kps), _p(curr_kps), _p(matches), len(matches), _p(depth), depth.shape[1], depth.shape[0], ct.c_size_t(depth.strides[0]),
+                             ct.c_float(fx), ct.c_float(fy), ct.c_float(cx), ct.c_float(cy), _p(p3), _p(p2))
+    return p3[:n].copy(), p2[:n].copy()
+
+
+def pnp_inliers(p3, p2, R, t, fx, fy, cx, cy, thresh=4.0):
+    """inlier count and mask of a pose under cv::solvePnPRansac's error (projectPoints without distortion, squared pixel error <= thresh^2)"""
+    p3 = np.ascontiguousarray(p3, np.float32).reshape(-1, 3); p2 = np.ascontiguousarray(p2, np.float32).reshape(-1, 2)
+    R = np.ascontiguousarray(R, np.float64).reshape(9); t = np.ascontiguousarray(t, np.float64).reshape(3)
+    mask = np.zeros(len(p3), np.uint8)
+    n = lib().orc_pnp_inliers(_p(p3), _p(p2), len(p3), _p(R), _p(t), ct.c_double(fx), ct.c_double(fy), ct.c_double(cx), ct.c_double(cy), ct.c_double(thresh), _p(mask))
+    return int(n), mask
+
+
 def fast_atan2(y, x):
     return float(lib().orc_fast_atan2(ct.c_float(y), ct.c_float(x)))
 

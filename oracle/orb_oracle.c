@@ -733,6 +733,55 @@ int orc_fmat_inliers(const float *p1, const float *p2, int n, const double *F, d
     return cnt;
 }
 
+/* Frontend::estimateCameraPose, frontend.cpp:858-892: the 3D-2D correspondences handed to cv::solvePnPRansac.  For every match, in match order:
+ * the previous frame's keypoint (trainIdx) is back-projected with the depth at its rounded pixel (std::round on floats: half away from zero),
+ * kept iff the pixel lies inside the depth image and 0.3 < d <= 3.0 m; X = (u - cx) * d / fx in float (rgb_fx_ ... are float members, :278).
+ * kps as 28-byte records (x, y first), matches as (queryIdx, trainIdx, imgIdx, distance).  Returns the number of correspondences. */
+int orc_pnp_points(const orc_keypoint *prev_kps, const orc_keypoint *curr_kps, const orc_dmatch *m, int nm, const uint16_t *depth, int w, int h,
+                   size_t dstep, float fx, float fy, float cx, float cy, float *p3, float *p2)
+{
+    int n = 0;
+    for (int i = 0; i < nm; i++) {
+        const float px = prev_kps[m[i].trainIdx].x, py = prev_kps[m[i].trainIdx].y;
+        const int xp = (int)roundf(px), yp = (int)roundf(py);
+        if (xp < 0 || yp < 0 || xp >= w || yp >= h) continue;
+        const float d = (float)*(const uint16_t *)((const uint8_t *)depth + (size_t)yp * dstep + 2 * (size_t)xp) * 0.001f;
+        if (d <= 0.3f || d > 3.0f) continue;
+        p3[3 * n] = (px - cx) * d / fx; p3[3 * n + 1] = (py - cy) * d / fy; p3[3 * n + 2] = d;
+        p2[2 * n] = curr_kps[m[i].queryIdx].x; p2[2 * n + 1] = curr_kps[m[i].queryIdx].y;
+        n++;
+    }
+    return n;
+}
+
+/* cv::solvePnPRansac(points3d, points2d, K, dist, rvec, tvec, false, 100, 4.0, 0.99, inliers) (frontend.cpp:911-923) scores a pose with
+ * PnPRansacCallback::computeError (calib3d/src/solvepnp.cpp): cv::projectPoints in double (x = R0 X + R1 Y + R2 Z + t0 ...; x /= z via z = 1/z;
+ * u = x fx + cx — the distortion terms vanish for the zero coefficients of a rectified stream), projections stored as float, squared pixel
+ * distance accumulated in float; inlier <=> err <= (float)(thresh * thresh).  R row-major 3x3 (= cv::Rodrigues(rvec)), t 3.  Pinned against
+ * cv2.projectPoints in tests/test_pnp.py.  Returns the inlier count. */
+int orc_pnp_inliers(const float *p3, const float *p2, int n, const double *R, const double *t, double fx, double fy, double cx, double cy,
+                    double thresh, uint8_t *mask)
+{
+    const float t2 = (float)(thresh * thresh);
+    int cnt = 0;
+    for (int i = 0; i < n; i++) {
+        const double X = p3[3 * i], Y = p3[3 * i + 1], Z = p3[3 * i + 2];
+        double x = R[0] * X + R[1] * Y + R[2] * Z + t[0];
+        double y = R[3] * X + R[4] * Y + R[5] * Z + t[1];
+        double z = R[6] * X + R[7] * Y + R[8] * Z + t[2];
+        z = z ? 1. / z : 1;
+        x *= z; y *= z;
+        const float u = (float)(x * fx + cx), v = (float)(y * fy + cy);
+        const float dx = p2[2 * i] - u, dy = p2[2 * i + 1] - v;
+        float e = dx * dx;
+        e += dy * dy;
+        const int in = e <= t2;
+        if (mask) mask[i] = (uint8_t)in;
+        cnt += in;
+    }
+    return cnt;
+}
+
 /* ---- profile C (cv::ORB, the reference's gtest test/test_dbow2_integration.cpp:19,38 and BASELINE configs[0]) primitives ---- */
 /* cv::resize(..., INTER_LINEAR_EXACT) on CV_8UC1: ufixedpoint16 coefficients (8 fractional bits) from the double-precision source
  * coordinate, horizontal pass exact in 16 bits, vertical pass in 32 bits with ONE rounding (+32768 >> 16).  Pinned bit for bit against

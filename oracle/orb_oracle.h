@@ -74,6 +74,10 @@ float orc_ic_angle(const uint8_t *img, size_t step, int cx, int cy, const int *u
 void orc_gaussian_blur7(const uint8_t *src, int w, int h, size_t sstep, uint8_t *dst, size_t dstep);
 /* inlier mask / count of one fundamental-matrix hypothesis under OpenCV's RANSAC error (frontend.cpp:1134-1154) */
 int  orc_fmat_inliers(const float *p1, const float *p2, int n, const double *F, double thresh, uint8_t *mask);
+int  orc_pnp_points(const orc_keypoint *prev_kps, const orc_keypoint *curr_kps, const orc_dmatch *m, int nm, const uint16_t *depth, int w, int h,
+                    size_t dstep, float fx, float fy, float cx, float cy, float *p3, float *p2);
+int  orc_pnp_inliers(const float *p3, const float *p2, int n, const double *R, const double *t, double fx, double fy, double cx, double cy,
+                     double thresh, uint8_t *mask);
 /* profile C (cv::ORB) primitives: cv::resize INTER_LINEAR_EXACT and the float-path GaussianBlur of a sub-matrix */
 void orc_resize_exact_tables(int ssize, int dsize, int32_t *ofs, int16_t *coef /*2 per i*/);
 void orc_resize_linear_exact(const uint8_t *src, int sw, int sh, size_t sstep, uint8_t *dst, int dw, int dh, size_t dstep);
