@@ -20,7 +20,20 @@ __device__ __align__(16) const signed char c_pattern[1024] = {
 };
 __device__ __constant__ int c_umax[16];
 
-void upload_umax(const int *umax) { cudaMemcpyToSymbol(c_umax, umax, sizeof(int) * 16); }
+// per patch row v = lane - 15 of IC_Angle's disc: byte masks of the 31 columns u = -15 .. 15 (byte 4 i + j of the row = column 4 i + j - 15),
+// 0xFF where |u| <= umax[|v|] (ORBextractor.cpp:76-103); read with two 128-bit __ldg per lane by the fused kernel
+__device__ __align__(16) uint32_t g_ic_mask[32][8];
+
+void upload_umax(const int *umax)
+{
+    cudaMemcpyToSymbol(c_umax, umax, sizeof(int) * 16);
+    uint32_t m[32][8];
+    memset(m, 0, sizeof(m));
+    for (int v = -ORBX_HALF_PATCH; v <= ORBX_HALF_PATCH; v++)
+        for (int u = -ORBX_HALF_PATCH; u <= ORBX_HALF_PATCH; u++)
+            if ((u < 0 ? -u : u) <= umax[v < 0 ? -v : v]) m[v + ORBX_HALF_PATCH][(u + ORBX_HALF_PATCH) >> 2] |= 0xFFu << (8 * ((u + ORBX_HALF_PATCH) & 3));
+    cudaMemcpyToSymbol(g_ic_mask, m, sizeof(m));
+}
 
 // ---- glibc sinf/cosf (sysdeps/ieee754/flt-32/s_sincosf.h algorithm, |x| < 120) ----
 __device__ __forceinline__ float glibc_sincos_poly(double x, double x2, int neg, int n)
@@ -213,22 +226,23 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescParams P, cons
 // written and re-read, no scattered DRAM gathers).  k_blur7 stays: orbx_get_blurred_level materialises levels with it on demand.
 #define DF_R 21
 #define DF_ROWS (2 * DF_R + 1)       // 43
-#define DF_PITCH 68                  // window tile pitch: 15 alignment bytes + 43 columns fit 64; 17 words so that a warp reading one word
-                                     // column of 32 consecutive rows (the row pass) touches 32 different banks
+#define DF_PITCH 76                  // window tile pitch: 15 alignment bytes + 43 columns fit 64; 19 words: lanes on consecutive rows (IC_Angle) hit 32
+                                     // different banks, and so do lanes on consecutive ROW PAIRS (row pass: 38 words = 6 banks apart, times 16 pairs =
+                                     // the 16 even banks, the neighbour group on the odd ones; six pairs x five groups for the last rows)
 #define DF_RCOLS 40                  // row-pass columns: ten 4-pixel groups starting at the word that holds column x-18
-#define DF_CP 45                     // row sums are kept COLUMN-major (u16 [column][row], 45 entries per column): the seven taps of a
-                                     // sample's column pass are then four consecutive 32-bit words = 4 LDS + 4 IDP.2A per sample
+#define DF_CP 46                     // row sums are kept COLUMN-major (u16 [column][row], 46 entries per column: 43 rows, row 43 of the last row pair,
+                                     // and an even count so that a row pair is one aligned 32-bit store): the seven taps of a sample's column pass
+                                     // are then four consecutive 32-bit words = 4 LDS + 4 IDP.2A per sample
 #define DF_WARP_BYTES (16 + DF_ROWS * DF_PITCH + 16 + ((DF_RCOLS * DF_CP * 2 + 16 + 15) & ~15))
 
-__device__ __forceinline__ void df_hpass4(uint32_t L, uint32_t C, uint32_t R, uint32_t &lo, uint32_t &hi)
+// row sums of the four pixels of word C (L, R = the words on either side): taps 18,34,48,56,48,34,18 on bytes x-3 .. x+3.  The taps are laid out per
+// output byte against the three words as they are (ten IDP.4A, no funnel shifts): byte 0 needs L and C, bytes 1 and 2 all three, byte 3 C and R.
+__device__ __forceinline__ void df_hpass4(uint32_t L, uint32_t C, uint32_t R, uint32_t &h0, uint32_t &h1, uint32_t &h2, uint32_t &h3)
 {
-    const uint32_t KLO = 0x38302212u;    // taps 18,34,48,56 on bytes x-3..x
-    const uint32_t KHI = 0x00122230u;    // taps 48,34,18 on bytes x+1..x+3
-    const uint32_t h0 = __dp4a(__funnelshift_r(L, C, 8), KLO, __dp4a(__funnelshift_r(C, R, 8), KHI, 0u));
-    const uint32_t h1 = __dp4a(__funnelshift_r(L, C, 16), KLO, __dp4a(__funnelshift_r(C, R, 16), KHI, 0u));
-    const uint32_t h2 = __dp4a(__funnelshift_r(L, C, 24), KLO, __dp4a(__funnelshift_r(C, R, 24), KHI, 0u));
-    const uint32_t h3 = __dp4a(C, KLO, __dp4a(R, KHI, 0u));
-    lo = h0 | (h1 << 16); hi = h2 | (h3 << 16);                                  // row sums <= 255 * 256 fit 16 bits
+    h0 = __dp4a(L, 0x30221200u, __dp4a(C, 0x12223038u, 0u));
+    h1 = __dp4a(L, 0x22120000u, __dp4a(C, 0x22303830u, __dp4a(R, 0x00000012u, 0u)));
+    h2 = __dp4a(L, 0x12000000u, __dp4a(C, 0x30383022u, __dp4a(R, 0x00001222u, 0u)));
+    h3 = __dp4a(C, 0x38302212u, __dp4a(R, 0x00122230u, 0u));                    // row sums <= 255 * 256 fit 16 bits
 }
 
 // blurred value from the column-major row sums: taps 18,34,48,56,48,34,18 on entries e .. e+6; the four words that hold them start at
@@ -287,21 +301,24 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe_fused(DescParams P
     const int xw = cx - DF_R;                                                      // window column 0
     const int ax = xw & 15, xal = xw - ax;                                         // its byte in the tile; image column of tile byte 0 (may be -16)
     {
-        uint4 v[6];                                                                // 172 chunks of 16 bytes: all six loads of a lane in flight together
+        // 43 rows x four 16-byte chunks.  A lane = (chunk, row of a quad, which quad): the two quads of an iteration lie 16 rows apart (19 x 16 words =
+        // 16 banks: no conflict between their 4-word chunks; rows 4 apart would collide three chunks over); all six loads of a lane in flight together
+        uint4 v[6];
+        const int ch = lane & 3, sub = (lane >> 2) & 3, half = lane >> 4;
 #pragma unroll
         for (int k = 0; k < 6; k++) {
-            const int i = lane + 32 * k, r = i >> 2, ch = i & 3;
+            const int r = 4 * (k < 4 ? k + 4 * half : (k == 4 ? 8 + half : 10 + half)) + sub;
             int y = cy - DF_R + r;
             y = y < 0 ? -y : (y >= hgt ? 2 * hgt - 2 - y : y);
             const int xs = xal + 16 * ch;
             v[k] = make_uint4(0u, 0u, 0u, 0u);
-            if (i < DF_ROWS * 4 && xs >= 0 && xs + 16 <= step) v[k] = __ldg(reinterpret_cast<const uint4 *>(img + (size_t)y * step + xs));
+            if (r < DF_ROWS && xs >= 0 && xs + 16 <= step) v[k] = __ldg(reinterpret_cast<const uint4 *>(img + (size_t)y * step + xs));
         }
 #pragma unroll
         for (int k = 0; k < 6; k++) {
-            const int i = lane + 32 * k;
-            if (i < DF_ROWS * 4) {
-                uint32_t *d = reinterpret_cast<uint32_t *>(tile + (i >> 2) * DF_PITCH + 16 * (i & 3));
+            const int r = 4 * (k < 4 ? k + 4 * half : (k == 4 ? 8 + half : 10 + half)) + sub;
+            if (r < DF_ROWS) {
+                uint32_t *d = reinterpret_cast<uint32_t *>(tile + r * DF_PITCH + 16 * ch);
                 d[0] = v[k].x; d[1] = v[k].y; d[2] = v[k].z; d[3] = v[k].w;
             }
         }
@@ -316,36 +333,55 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe_fused(DescParams P
         __syncwarp();
     }
 
-    // ---- IC_Angle on the staged window: lane = column u+15, all 31 rows ----
+    // ---- IC_Angle on the staged window: lane = patch row v + 15; the row's 31 columns as eight words brought to the column grid by one
+    // warp-uniform funnel shift, masked to the disc, then two IDP.4A per word: S = sum of I, T = sum of (u + 15) I; m10 = sum over rows of T - 15 S ----
     int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int u = lane - ORBX_HALF_PATCH;
-        const int au = u < 0 ? -u : u;
-        const uint8_t *ctr = tile + DF_R * DF_PITCH + ax + DF_R + u;
-        int colsum = 0;
+    if (lane < 2 * ORBX_HALF_PATCH + 1) {
+        const int p0 = ax + DF_R - ORBX_HALF_PATCH;                                // tile byte of column u = -15
+        const uint32_t *rw32 = reinterpret_cast<const uint32_t *>(tile + (DF_R - ORBX_HALF_PATCH + lane) * DF_PITCH) + (p0 >> 2);
+        const int sh = 8 * (p0 & 3);
+        const uint4 ma = __ldg(reinterpret_cast<const uint4 *>(g_ic_mask[lane])), mb = __ldg(reinterpret_cast<const uint4 *>(g_ic_mask[lane]) + 1);
+        const uint32_t mk[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+        uint32_t wv[9];
 #pragma unroll
-        for (int v = -ORBX_HALF_PATCH; v <= ORBX_HALF_PATCH; v++) {
-            const int av = v < 0 ? -v : v;
-            const int val = au <= c_umax[av] ? (int)ctr[v * DF_PITCH] : 0;
-            colsum += val; m01 += v * val;
+        for (int i = 0; i < 9; i++) wv[i] = rw32[i];
+        uint32_t S = 0, T = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t a = __funnelshift_r(wv[i], wv[i + 1], sh) & mk[i];
+            S = __dp4a(a, 0x01010101u, S);
+            T = __dp4a(a, 0x03020100u + 0x04040404u * (uint32_t)i, T);
         }
-        m10 = u * colsum;
+        m10 = (int)T - ORBX_HALF_PATCH * (int)S;
+        m01 = (lane - ORBX_HALF_PATCH) * (int)S;
     }
     m10 = __reduce_add_sync(0xffffffffu, m10);
     m01 = __reduce_add_sync(0xffffffffu, m01);
     const float angle = cv_fast_atan2((float)m01, (float)m10);
 
-    // ---- row pass of the window: 43 rows x ten 4-pixel groups ----
+    // ---- row pass of the window: ten 4-pixel groups x 22 row pairs (rows 2 p, 2 p + 1; row 43 is padding).  A lane's unit is one group x one row
+    // pair: six words in, ten IDP.4A per row, and the two rows of a column leave as ONE 32-bit store into the column-major buffer.  Five iterations
+    // take row pairs 0..15 of two adjacent groups (lanes 0-15 / 16-31: rows two apart sit two banks apart at the 17-word pitch, the neighbour group
+    // fills the odd banks), two more take row pairs 16..21 of all ten groups ----
     const int b0 = (ax + 3) & ~3;                                                  // tile byte of row-pass column 0 (<= the byte of column x-18)
     {
         const uint32_t *tw = reinterpret_cast<const uint32_t *>(tile) + (b0 >> 2);
-        for (int u = lane; u < DF_ROWS * 10; u += 32) {
-            const int gq = (u * 1525) >> 16, r = u - DF_ROWS * gq;                  // u / 43 for u < 2752: lanes run down the rows of one group
-            const uint32_t *q = tw + r * (DF_PITCH / 4) + gq;
-            uint32_t lo, hi;
-            df_hpass4(q[-1], q[0], q[1], lo, hi);
-            uint16_t *o = rows + (4 * gq) * DF_CP + r;
-            o[0] = (uint16_t)lo; o[DF_CP] = (uint16_t)(lo >> 16); o[2 * DF_CP] = (uint16_t)hi; o[3 * DF_CP] = (uint16_t)(hi >> 16);
+        uint32_t *rw32 = reinterpret_cast<uint32_t *>(rows);
+#pragma unroll
+        for (int it = 0; it < 7; it++) {
+            int gq, rp;
+            bool act = true;
+            if (it < 5) { gq = 2 * it + (lane >> 4); rp = lane & 15; }
+            else { const int g5 = (lane * 43) >> 8; gq = 5 * (it - 5) + g5; rp = 16 + lane - 6 * g5; act = lane < 30; }   // lane / 6: five groups x six row pairs
+            if (act) {
+                const uint32_t *q = tw + (2 * rp) * (DF_PITCH / 4) + gq;
+                uint32_t a0, a1, a2, a3, c0, c1, c2, c3;
+                df_hpass4(q[-1], q[0], q[1], a0, a1, a2, a3);
+                df_hpass4(q[DF_PITCH / 4 - 1], q[DF_PITCH / 4], q[DF_PITCH / 4 + 1], c0, c1, c2, c3);
+                uint32_t *o = rw32 + (4 * gq) * (DF_CP / 2) + rp;
+                o[0] = __byte_perm(a0, c0, 0x5410); o[DF_CP / 2] = __byte_perm(a1, c1, 0x5410);                 // (row 2 p, row 2 p + 1) of one column
+                o[2 * (DF_CP / 2)] = __byte_perm(a2, c2, 0x5410); o[3 * (DF_CP / 2)] = __byte_perm(a3, c3, 0x5410);
+            }
         }
     }
     __syncwarp();
