@@ -263,6 +263,7 @@ def main():
     ap.add_argument("--no-pdl", action="store_true", help="plain stream order instead of programmatic dependent launch (ORBX_OPT_PDL = 0)")
     ap.add_argument("--fast-ctas", type=int, default=0, help="resident FAST warps per SM in the overlapped schedule (0 = library default)")
     ap.add_argument("--overlap", action="store_true", help="two staggered half-batches on two streams (ORBX_OPT_OVERLAP = 1; measured slower than one chain)")
+    ap.add_argument("--describe-all", action="store_true", help="the reference's order: describe every selected keypoint, then filter (ORBX_OPT_FILTER_FIRST = 0)")
     ap.add_argument("--fast-dense", type=int, default=0, help="ORBX_OPT_FAST_DENSE: 1 = the dense FAST formulation for batches, 3 = the same with the NMS inside the tile kernel")
     ap.add_argument("--match-engine", type=int, default=-1, help="ORBX_OPT_MATCH_MMA: 1 = default (tensor-memory kernel for large calls), 2 = the mma.sync kernel, 3 = tensor-memory kernel always, 0 = POPC")
     ap.add_argument("--popc-match", action="store_true", help="the LOP3/POPC matcher instead of the int8 tensor-core GEMM (ORBX_OPT_MATCH_MMA = 0)")
@@ -304,6 +305,8 @@ def main():
         ex.set_pdl(False)
     if args.overlap:
         ex.set_overlap(True)
+    if args.describe_all:
+        ex.set_filter_first(False)
     if args.popc_match:
         ex.set_match_mma(False)
     elif args.match_engine >= 0:

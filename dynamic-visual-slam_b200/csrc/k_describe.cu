@@ -119,6 +119,7 @@ struct DescParams {
     orbx_keypoint *kps; uint8_t *desc; int cap;     // per-frame capacity
     int32_t *counts;
     int32_t *status;
+    const int32_t *map; int map_slab;               // fused kernel, filter-first order (k_keep_list): output slot -> index in the selected list; counts[] is then an input
 };
 
 #define DESC_WARPS 4
@@ -266,7 +267,14 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe_fused(DescParams P
     const int f = blockIdx.y;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int nl = G->nlevels;
-    int gidx = blockIdx.x * DESC_WARPS + wid;
+    const int slot = blockIdx.x * DESC_WARPS + wid;                    // output row
+    int gidx = slot;                                                   // index in the frame's selected list (levels concatenated)
+    if (P.map) {
+        // filter-first order: k_keep_list has applied the depth / box filter to the selected POSITIONS and left the survivors' indices, in
+        // order, with their count — only those get an angle and a descriptor, straight into their final rows
+        if (slot >= P.counts[f]) return;
+        gidx = P.map[(size_t)f * P.map_slab + slot];
+    }
     // locate (level, index in level): levels are concatenated in order (ORBextractor.cpp:1123).  Lane l holds level l's count; an
     // inclusive warp scan gives the level boundaries, a ballot the level that contains keypoint gidx.
     int level, k, total;
@@ -281,11 +289,14 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe_fused(DescParams P
         k = gidx - (level > 0 ? before : 0);
         if (level >= nl) level = -1;
     }
-    if (gidx == 0 && lane == 0) {
-        P.counts[f] = total <= P.cap ? total : 0;
-        if (total > P.cap) atomicOr(P.status, ORBX_DS_KP_OVERFLOW);
+    if (!P.map) {
+        if (gidx == 0 && lane == 0) {
+            P.counts[f] = total <= P.cap ? total : 0;
+            if (total > P.cap) atomicOr(P.status, ORBX_DS_KP_OVERFLOW);
+        }
+        if (total > P.cap) return;
     }
-    if (level < 0 || total > P.cap) return;
+    if (level < 0) return;
     const LevelGeom &g = G->lv[level];
     const uint32_t c = P.sel[(size_t)f * P.sel_slab + g.sel_off + k];
     // pt += (minBorderX, minBorderY) — ORBextractor.cpp:886-887; integer-valued, cvRound is the identity
@@ -408,7 +419,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe_fused(DescParams P
         const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
         val |= (df_sample(rw, e0 + c0 * DF_CP + r0) < df_sample(rw, e0 + c1 * DF_CP + r1)) << j;
     }
-    uint8_t *drow = P.desc + ((size_t)f * P.cap + gidx) * ORBX_DESC_BYTES;
+    uint8_t *drow = P.desc + ((size_t)f * P.cap + slot) * ORBX_DESC_BYTES;
     drow[lane] = (uint8_t)val;
     if (lane == 0) {
         orbx_keypoint kp;
@@ -416,14 +427,15 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe_fused(DescParams P
         if (level != 0) { kp.x = __fmul_rn(kp.x, g.scale); kp.y = __fmul_rn(kp.y, g.scale); }   // :1147-1149
         kp.size = g.size; kp.angle = angle; kp.response = (float)orbx_ps(c);
         kp.octave = level; kp.class_id = -1;
-        P.kps[(size_t)f * P.cap + gidx] = kp;
+        P.kps[(size_t)f * P.cap + slot] = kp;
     }
 }
 
 void launch_describe_to(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride,
-                        orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts)
+                        orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts, const int32_t *d_map, int map_slab)
 {
     DescParams P;
+    P.map = h->opt_fused_blur ? d_map : nullptr; P.map_slab = map_slab;
     P.l0 = l0; P.l0_step = l0_step; P.l0_fstride = l0_fstride;
     P.pyr = h->d_pyr; P.pyr_slab = h->pyr_slab;
     P.blur = h->d_blur; P.blur_slab = h->blur_slab;

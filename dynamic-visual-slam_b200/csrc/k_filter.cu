@@ -8,12 +8,11 @@
 // Both run AFTER the quadtree, exactly where the reference applies them, so the
 // retained set is identical to extract-then-filter.  One CTA per frame; order preserved.
 #include "orbx_internal.h"
+#include "orbx_keep.h"
 
 struct FilterParams {
     const orbx_keypoint *kin; const uint8_t *din; const int32_t *nin; int cap_in;
-    const uint16_t *depth; size_t dstep, dfstride; int dw, dh;     // steps in BYTES
-    float dmin, dmax;
-    const orbx_box *boxes; const int32_t *box_offsets; int box_base; int nboxes; unsigned long long drop_mask;   // box_offsets (nullable): frame f owns boxes [off[f], off[f+1])
+    KeepParams K;                                                 // depth + box test (orbx_keep.h)
     orbx_keypoint *kout; uint8_t *dout; int32_t *nout; int cap_out;
     int32_t *status;
 };
@@ -39,27 +38,7 @@ __global__ void __launch_bounds__(1024) k_filter(FilterParams P)
         orbx_keypoint kp;
         if (i < n) {
             kp = kin[i];
-            keep = true;
-            if (P.depth) {
-                const int x = (int)roundf(kp.x), y = (int)roundf(kp.y);
-                if (x < 0 || y < 0 || x >= P.dw || y >= P.dh) keep = false;
-                else {
-                    const uint16_t raw = *(const uint16_t *)((const uint8_t *)P.depth + (size_t)f * P.dfstride + (size_t)y * P.dstep + (size_t)x * 2);
-                    const float d = __fmul_rn((float)raw, 0.001f);
-                    if (d < P.dmin || d > P.dmax) keep = false;
-                }
-            }
-            if (keep && P.nboxes > 0) {
-                const double px = (double)kp.x, py = (double)kp.y;
-                const int b0 = P.box_offsets ? P.box_offsets[f] - P.box_base : 0, b1 = P.box_offsets ? P.box_offsets[f + 1] - P.box_base : P.nboxes;
-                for (int b = b0; b < b1; b++) {
-                    const orbx_box bx = P.boxes[b];
-                    if (px >= bx.cx - bx.w / 2 && px <= bx.cx + bx.w / 2 && py >= bx.cy - bx.h / 2 && py <= bx.cy + bx.h / 2) {
-                        if (bx.class_id >= 0 && bx.class_id < 64 && ((P.drop_mask >> bx.class_id) & 1ull)) keep = false;
-                        break;                                  // first containing box decides
-                    }
-                }
-            }
+            keep = orbx_keep(P.K, f, kp.x, kp.y);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) s_warp[wid] = __popc(bal);
@@ -85,15 +64,95 @@ __global__ void __launch_bounds__(1024) k_filter(FilterParams P)
     }
 }
 
+static KeepParams keep_params(const orbx_handle *h, const uint16_t *d_depth, size_t dstep, size_t dfstride,
+                              const orbx_box *d_boxes, const int32_t *d_box_offsets, int box_base, int nboxes, uint64_t drop_mask)
+{
+    KeepParams K;
+    K.depth = d_depth; K.dstep = dstep; K.dfstride = dfstride; K.dw = h->geo.width; K.dh = h->geo.height;
+    K.dmin = h->prm.depth_min; K.dmax = h->prm.depth_max;
+    K.boxes = d_boxes; K.box_offsets = d_box_offsets; K.box_base = box_base; K.nboxes = nboxes; K.drop_mask = drop_mask;
+    return K;
+}
+
+// ---- filter-first order: the same test on the SELECTED positions, before any descriptor work ----
+// The filters look at a keypoint's position only: pt = (selected pixel + border) * the level's scale (ORBextractor.cpp:886-887, 1147-1149) is known
+// as soon as the quadtree has selected it.  One CTA per frame walks the frame's selected list in output order (levels concatenated, :1123),
+// forms pt exactly as the descriptor kernel does, applies orbx_keep and leaves the surviving list indices, in order, in map[f][0 .. nout[f]) —
+// k_describe_fused then works on those alone and writes their final rows.  Same capacity semantics as k_filter.
+struct KeepListParams {
+    const uint32_t *sel; int sel_slab; const int32_t *nsel;
+    KeepParams K;
+    int32_t *map; int map_slab; int32_t *nout; int cap_out;
+    int32_t *status;
+};
+
+__global__ void __launch_bounds__(1024) k_keep_list(KeepListParams P, const FrameGeom *__restrict__ G)
+{
+    __shared__ int s_warp[33];
+    __shared__ int s_base;
+    __shared__ int s_lend[ORBX_MAX_LEVELS + 1];                 // s_lend[l] = selected keypoints of levels < l
+    ORBX_PDL_ENTRY();
+    const int f = blockIdx.x;
+    const int nl = G->nlevels;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int l = 0; l < nl; l++) { s_lend[l] = run; run += P.nsel[f * nl + l]; }
+        s_lend[nl] = run; s_base = 0;
+    }
+    __syncthreads();
+    const int n = s_lend[nl];
+    const uint32_t *sel = P.sel + (size_t)f * P.sel_slab;
+    int32_t *map = P.map + (size_t)f * P.map_slab;
+    const int nw = blockDim.x >> 5;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        bool keep = false;
+        if (i < n) {
+            int level = 0;
+            while (level + 1 < nl && i >= s_lend[level + 1]) level++;
+            const LevelGeom &g = G->lv[level];
+            const uint32_t c = sel[g.sel_off + (i - s_lend[level])];
+            float kx = (float)(orbx_px(c) + ORBX_BORDER), ky = (float)(orbx_py(c) + ORBX_BORDER);
+            if (level != 0) { kx = __fmul_rn(kx, g.scale); ky = __fmul_rn(ky, g.scale); }
+            keep = orbx_keep(P.K, f, kx, ky);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        if (threadIdx.x == 0) { int run = 0; for (int w = 0; w < nw; w++) { const int c = s_warp[w]; s_warp[w] = run; run += c; } s_warp[32] = run; }
+        __syncthreads();
+        const int o = s_base + s_warp[wid] + __popc(bal & ((1u << lane) - 1u));
+        if (keep && o < P.cap_out && o < P.map_slab) map[o] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += s_warp[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (s_base > P.cap_out || s_base > P.map_slab) { atomicOr(P.status, ORBX_DS_KP_OVERFLOW); P.nout[f] = 0; }
+        else P.nout[f] = s_base;
+    }
+}
+
+void launch_keep_list(orbx_handle *h, int nframes, const uint16_t *d_depth, size_t dstep, size_t dfstride,
+                      const orbx_box *d_boxes, const int32_t *d_box_offsets, int box_base, int nboxes, uint64_t drop_mask,
+                      int32_t *d_map, int map_slab, int32_t *d_counts, int cap)
+{
+    KeepListParams P;
+    P.sel = h->d_sel; P.sel_slab = h->geo.sel_entries; P.nsel = h->d_nsel;
+    P.K = keep_params(h, d_depth, dstep, dfstride, d_boxes, d_box_offsets, box_base, nboxes, drop_mask);
+    P.map = d_map; P.map_slab = map_slab; P.nout = d_counts; P.cap_out = cap; P.status = h->d_status;
+    ProfScope ps(h, ORBX_K_FILTER);
+    orbx_launch_pdl(h, k_keep_list, dim3(nframes), dim3(1024), 0, h->stream, P, (const FrameGeom *)h->d_geo);
+}
+
 void launch_filter(orbx_handle *h, int nframes, const uint16_t *d_depth, size_t dstep, size_t dfstride,
                    const orbx_box *d_boxes, const int32_t *d_box_offsets, int box_base, int nboxes, uint64_t drop_mask,
                    orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts)
 {
     FilterParams P;
     P.kin = h->d_kps_all; P.din = h->d_desc_all; P.nin = h->d_count_all; P.cap_in = h->max_kp;
-    P.depth = d_depth; P.dstep = dstep; P.dfstride = dfstride; P.dw = h->geo.width; P.dh = h->geo.height;
-    P.dmin = h->prm.depth_min; P.dmax = h->prm.depth_max;
-    P.boxes = d_boxes; P.box_offsets = d_box_offsets; P.box_base = box_base; P.nboxes = nboxes; P.drop_mask = drop_mask;
+    P.K = keep_params(h, d_depth, dstep, dfstride, d_boxes, d_box_offsets, box_base, nboxes, drop_mask);
     P.kout = d_kps; P.dout = d_desc; P.nout = d_counts; P.cap_out = cap; P.status = h->d_status;
     ProfScope ps(h, ORBX_K_FILTER);
     orbx_launch_pdl(h, k_filter, dim3(nframes), dim3(1024), 0, h->stream, P);

@@ -308,7 +308,7 @@ extern "C" orbx_status orbx_create(const orbx_params *pp, orbx_handle **out)
     if (p.device < 0 || p.device >= ndev) { g_create_err = "device ordinal out of range"; return ORBX_E_INVALID; }
     orbx_handle *h = new orbx_handle();
     h->prm = p; h->device = p.device; h->launches = 0; h->geo.width = -1; h->geo.height = -1;
-    h->prof_on = 0; h->prof_n = 0; h->prev_valid = 0; h->opt_fused_blur = 1; h->blur_valid = false; h->opt_pdl = 1; h->opt_overlap = 0; h->opt_match_mma = 1; h->in_overlap = false; h->ev_after_pyramid = nullptr;
+    h->prof_on = 0; h->prof_n = 0; h->prev_valid = 0; h->opt_fused_blur = 1; h->opt_filter_first = 1; h->blur_valid = false; h->opt_pdl = 1; h->opt_overlap = 0; h->opt_match_mma = 1; h->in_overlap = false; h->ev_after_pyramid = nullptr;
     memset(&h->alt, 0, sizeof(h->alt));
     memset(h->prof_ms, 0, sizeof(h->prof_ms)); memset(h->prof_cnt, 0, sizeof(h->prof_cnt));
     CREATE_CUDA(cudaSetDevice(p.device));
@@ -470,6 +470,7 @@ extern "C" orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t v
     if (option == ORBX_OPT_SERIAL) { h->opt_serial = value ? 1 : 0; return ORBX_OK; }
     if (option == ORBX_OPT_FAST_CTAS) { h->opt_fast_ctas = value > 0 ? value : 0; return ORBX_OK; }
     if (option == ORBX_OPT_FUSED_BLUR) { h->opt_fused_blur = value ? 1 : 0; return ORBX_OK; }
+    if (option == ORBX_OPT_FILTER_FIRST) { h->opt_filter_first = value ? 1 : 0; return ORBX_OK; }
     if (option == ORBX_OPT_PDL) { h->opt_pdl = value ? 1 : 0; return ORBX_OK; }
     if (option == ORBX_OPT_OVERLAP) { h->opt_overlap = value ? 1 : 0; return ORBX_OK; }
     if (option == ORBX_OPT_FAST_DENSE) {
@@ -568,7 +569,16 @@ static orbx_status run_pipeline(orbx_handle *h, int nframes, const uint8_t *l0, 
     if (side) ORBX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     const bool filtered = d_depth != nullptr || nboxes > 0;
     if (!filtered) launch_describe_to(h, nframes, l0, l0_step, l0_fstride, d_kps, d_desc, cap, d_counts);
-    else {
+    else if (h->opt_fused_blur && h->opt_filter_first) {
+        // Filter first.  The depth / box filter (frontend.cpp:503-527, backend.cpp:1011-1029) looks at a keypoint's POSITION only, which is known
+        // once the quadtree has selected it; the reference computes the angle and the descriptor of every selected keypoint and then drops
+        // rows.  Here the filter runs on the selected positions and leaves an ordered index list (k_keep_list), and the descriptor kernel works
+        // on the survivors alone, writing their final rows: same output, a fifth less descriptor work on the RGB-D stream, no compaction copy.
+        // The index list lives in the (otherwise unused) unfiltered-keypoint arena, which every half-batch lane owns a copy of.
+        int32_t *d_map = reinterpret_cast<int32_t *>(h->d_kps_all);
+        launch_keep_list(h, nframes, d_depth, dstep, dfstride, d_boxes, BX.off, BX.base, nboxes, drop_mask, d_map, h->max_kp, d_counts, cap);
+        launch_describe_to(h, nframes, l0, l0_step, l0_fstride, d_kps, d_desc, cap, d_counts, d_map, h->max_kp);
+    } else {
         launch_describe_to(h, nframes, l0, l0_step, l0_fstride, h->d_kps_all, h->d_desc_all, h->max_kp, h->d_count_all);
         launch_filter(h, nframes, d_depth, dstep, dfstride, d_boxes, BX.off, BX.base, nboxes, drop_mask, d_kps, d_desc, cap, d_counts);
     }

@@ -100,6 +100,7 @@ struct orbx_handle {
     int opt_pdl;                 // 1 (default): programmatic stream serialization where it measured faster (below)
     bool pdl_chain;              // this call's kernels use it: small batches only — at 128 frames the early-resident CTAs of the next kernel cost
                                  // 1 % of throughput, at one frame they take 9 % off the latency; the resize chain always uses it (+0.5 %)
+    int opt_filter_first;        // 1 (default): depth / box filter on the selected positions BEFORE the descriptor kernel (k_keep_list), which then works on the survivors only
     int opt_fused_blur;          // 1 (default): the Gaussian is evaluated inside the descriptor kernel, no blurred pyramid is written
     bool blur_valid;             // d_blur holds the blurred levels of the last batch
     int opt_fast_ctas;           // FAST warps per SM in the overlapped schedule (0 = as many as fit)
@@ -265,8 +266,13 @@ int  launch_quadtree_geo(orbx_handle *h, const FrameGeom *d_geo, int nlevels, in
 int  launch_cull(orbx_handle *h, const orbx_keypoint *d_kps, const uint8_t *d_desc, int n, const int32_t *d_mq, int nm, int max_new, float min_response,
                  orbx_keypoint *d_out_kps, uint8_t *d_out_desc, int32_t *d_out_index, int cap, int32_t *d_n_out);   // k_cull.cu; -1: shared memory opt-in failed
 int  launch_blur(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride, cudaStream_t st, int tile_first = 0, int ntiles = -1);
+// d_map (nullable, fused kernel only): filter-first order — launch_keep_list has left, per frame, the indices (in the selected list) of the
+// keypoints the depth / box filter keeps and their count in d_counts; only those are described, straight into their final rows
 void launch_describe_to(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride,
-                        orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts);
+                        orbx_keypoint *d_kps, uint8_t *d_desc, int cap, int32_t *d_counts, const int32_t *d_map = nullptr, int map_slab = 0);
+void launch_keep_list(orbx_handle *h, int nframes, const uint16_t *d_depth, size_t dstep, size_t dfstride,
+                      const orbx_box *d_boxes, const int32_t *d_box_offsets, int box_base, int nboxes, uint64_t drop_mask,
+                      int32_t *d_map, int map_slab, int32_t *d_counts, int cap);                  // k_filter.cu
 void upload_umax(const int *umax);
 void launch_filter(orbx_handle *h, int nframes, const uint16_t *d_depth, size_t dstep, size_t dfstride,
                    const orbx_box *d_boxes, const int32_t *d_box_offsets, int box_base, int nboxes, uint64_t drop_mask,

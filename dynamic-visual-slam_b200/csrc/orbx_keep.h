@@ -1,0 +1,46 @@
+// orbx_keep.h — the post-selection keep test of a keypoint, shared by k_filter (the stable compaction) and k_describe_fused (which
+// skips the descriptor work of keypoints the compaction is going to drop).  ONE function, so both kernels take the same decision:
+//   * Frontend::isValidDepth / filterDepth (reference frontend.cpp:457-473, 503-527): keep iff x = round(pt.x), y = round(pt.y) (half away
+//     from zero) lies inside the depth image and d = depth_u16 * 0.001f satisfies depth_min <= d <= depth_max;
+//   * Backend::categorizeObservation + filtered_objects_ (backend.cpp:1011-1029, 746-751): the first box containing the pixel (inclusive
+//     bounds, fp64 compares) gives the class; drop iff that class is in the drop mask.
+#pragma once
+#include "orbx_internal.h"
+
+struct KeepParams {
+    const uint16_t *depth; size_t dstep, dfstride; int dw, dh;     // steps in BYTES; depth == nullptr: no depth test
+    float dmin, dmax;
+    const orbx_box *boxes; const int32_t *box_offsets; int box_base; int nboxes; unsigned long long drop_mask;   // box_offsets (nullable): frame f owns boxes [off[f], off[f+1])
+};
+
+// The test in two halves, so that a caller can put independent work between the depth load and its first use:
+// orbx_keep_fetch = the depth sample (-1: the rounded position is outside the depth image, 0 without a depth test), orbx_keep_decide = the verdict.
+__device__ __forceinline__ int orbx_keep_fetch(const KeepParams &P, int f, float kx, float ky)
+{
+    if (!P.depth) return 0;
+    const int x = (int)roundf(kx), y = (int)roundf(ky);
+    if (x < 0 || y < 0 || x >= P.dw || y >= P.dh) return -1;
+    return (int)*(const uint16_t *)((const uint8_t *)P.depth + (size_t)f * P.dfstride + (size_t)y * P.dstep + (size_t)x * 2);
+}
+__device__ __forceinline__ bool orbx_keep_decide(const KeepParams &P, int f, float kx, float ky, int raw)
+{
+    if (P.depth) {
+        if (raw < 0) return false;
+        const float d = __fmul_rn((float)raw, 0.001f);
+        if (d < P.dmin || d > P.dmax) return false;
+    }
+    if (P.nboxes > 0) {
+        const double px = (double)kx, py = (double)ky;
+        const int b0 = P.box_offsets ? P.box_offsets[f] - P.box_base : 0, b1 = P.box_offsets ? P.box_offsets[f + 1] - P.box_base : P.nboxes;
+        for (int b = b0; b < b1; b++) {
+            const orbx_box bx = P.boxes[b];
+            if (px >= bx.cx - bx.w / 2 && px <= bx.cx + bx.w / 2 && py >= bx.cy - bx.h / 2 && py <= bx.cy + bx.h / 2)   // first containing box decides
+                return !(bx.class_id >= 0 && bx.class_id < 64 && ((P.drop_mask >> bx.class_id) & 1ull));
+        }
+    }
+    return true;
+}
+__device__ __forceinline__ bool orbx_keep(const KeepParams &P, int f, float kx, float ky)
+{
+    return orbx_keep_decide(P, f, kx, ky, orbx_keep_fetch(P, f, kx, ky));
+}

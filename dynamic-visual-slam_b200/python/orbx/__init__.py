@@ -271,6 +271,11 @@ class ORBextractor:
         3 = for every call with the NMS inside the tile kernel."""
         self._check(self.L.orbx_set_option(self._h, 7, int(mode)))
 
+    def set_filter_first(self, on=True):
+        """ORBX_OPT_FILTER_FIRST: 1 (default) = the depth / box filter runs on the selected positions before the descriptor kernel, which then
+        describes the survivors only; 0 = the reference's order (describe everything, then drop rows).  Same output."""
+        self._check(self.L.orbx_set_option(self._h, 8, 1 if on else 0))
+
     def set_fast_ctas(self, n):
         """ORBX_OPT_FAST_CTAS: resident FAST warps per SM in the overlapped schedule (0 = as many as fit)."""
         self._check(self.L.orbx_set_option(self._h, 2, int(n)))

@@ -431,6 +431,13 @@ orbx_status orbx_synth_descriptors_device(orbx_handle *h, uint32_t seed, uint64_
  * — its NMS kernel re-reads the 420 MB of score maps from HBM.  Switching it on allocates its arenas
  * (0.8 GB at 128 frames of 1280 x 720): ORBX_E_CUDA if they cannot be had.                                                          */
 #define ORBX_OPT_FAST_DENSE 7
+/* ORBX_OPT_FILTER_FIRST: order of the depth / box filter and the descriptor kernel in the filtered calls.  The filters of the reference
+ * (frontend.cpp:503-527 after operator(), backend.cpp:1011-1029) look at a keypoint's position only, which is final once the quadtree has
+ * selected it.  1 (default) = the filter runs on the selected positions first and leaves an ordered index list (k_keep_list); the descriptor
+ * kernel computes angles and descriptors of the survivors only, straight into their final rows.  0 = the reference's order: describe every
+ * selected keypoint, then drop rows (k_filter).  Same output bit for bit (tests/test_gpu_baseline_configs.py runs both); on the RGB-D
+ * stream a fifth of the selected keypoints fail the depth test. */
+#define ORBX_OPT_FILTER_FIRST 8
 orbx_status orbx_set_option(orbx_handle *h, int32_t option, int32_t value);
 
 /* ---- utilities ---- */

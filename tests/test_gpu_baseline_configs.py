@@ -207,6 +207,67 @@ def test_configs4_boxes_at_batch_device_and_host(built, oracle):
         ex.close()
 
 
+def test_filter_order_option_same_results(built, oracle):
+    """ORBX_OPT_FILTER_FIRST: the default (depth / box filter on the selected positions, then descriptors of the survivors only) and the
+    reference's order (describe every selected keypoint, then drop rows) give the same bytes as the CPU sequence — depth alone, depth +
+    boxes, through the device and the host entry (pinned depth gathered in place), and agree on the capacity error"""
+    import orbx
+    import torch
+    B = 12
+    _, ref = _cpu_stream(oracle, 0, B, with_boxes=True)
+    _, ref_d = _cpu_stream(oracle, 0, B)
+    frame_boxes = [oracle.synth_boxes(SEED, f, W, H) for f in range(B)]
+    ex = orbx.ORBextractor(max_width=W, max_height=H, max_batch=B, max_keypoints=CAP, host_chunk=5)
+    try:
+        gray, depth = _device_stream(ex, 0, B)
+        boxes, off = ex.pack_frame_boxes(frame_boxes)
+        d_boxes = torch.from_numpy(boxes.view(np.uint8).reshape(-1)).to("cuda:0")
+        d_off = torch.from_numpy(off).to("cuda:0")
+        frames, depths = gray.cpu().numpy(), depth.cpu().numpy().view(np.uint16)
+        got = {}
+        for first in (1, 0):
+            ex.set_filter_first(bool(first))
+            ex.track_reset()
+            o = _outputs(B)
+            ex._check(ex.L.orbx_track_batch_boxes_device(ex.handle, gray.data_ptr(), B, W, H, W, W * H, depth.data_ptr(), 2 * W, 2 * W * H,
+                                                         d_boxes.data_ptr(), d_off.data_ptr(), len(boxes), ct.c_uint64(1),
+                                                         o["kps"].data_ptr(), o["desc"].data_ptr(), CAP, o["cnt"].data_ptr(),
+                                                         o["m"].data_ptr(), o["mc"].data_ptr(), ct.c_float(50.0)))
+            ex.sync()
+            kk, dd = o["kps"].cpu().numpy().view(orbx.KP_DTYPE).reshape(B, CAP), o["desc"].cpu().numpy()
+            cc, mm, mc = o["cnt"].cpu().numpy(), o["m"].cpu().numpy().view(orbx.DM_DTYPE).reshape(B, CAP), o["mc"].cpu().numpy()
+            for f in range(B):
+                r = ref[f]
+                assert cc[f] == len(r["kps"]) and np.array_equal(kk[f, :cc[f]].view(np.uint8), r["kps"].view(np.uint8)) and np.array_equal(dd[f, :cc[f]], r["desc"]), (first, f)
+                assert mc[f] == len(r["good"]) and np.array_equal(mm[f, :mc[f]].view(np.uint8), r["good"].view(np.uint8)), (first, f)
+            # host entry, depth alone (pinned depth is gathered in place: one PCIe read per selected keypoint in either order)
+            ex.track_reset()
+            kps, desc, counts, matches, mcounts = ex.track_batch(frames, depths, cap=CAP)
+            for f in range(B):
+                r = ref_d[f]
+                assert counts[f] == len(r["kps"]) and np.array_equal(kps[f, :counts[f]].view(np.uint8), r["kps"].view(np.uint8)) and np.array_equal(desc[f, :counts[f]], r["desc"]), (first, f)
+                assert mcounts[f] == len(r["good"]) and np.array_equal(matches[f, :mcounts[f]].view(np.uint8), r["good"].view(np.uint8)), (first, f)
+            # single-frame host call
+            k1, d1 = ex(frames[3], depth=depths[3])
+            assert np.array_equal(k1.view(np.uint8), ref_d[3]["kps"].view(np.uint8)) and np.array_equal(d1, ref_d[3]["desc"]), first
+            # an output capacity below the filtered count: the same error in either order
+            small = min(len(r["kps"]) for r in ref_d) - 1
+            with pytest.raises(orbx.OrbxError) as e:
+                ex.extract_batch(frames[:2], depth=depths[:2], cap=small)
+            got[first] = [str(e.value)]
+            # the device entry with an output capacity below the filtered count: the kernels raise the capacity flag, counts read 0
+            o = _outputs(2)
+            ex._check(ex.L.orbx_extract_batch_device(ex.handle, gray.data_ptr(), 2, W, H, W, W * H, depth.data_ptr(), 2 * W, 2 * W * H,
+                                                     o["kps"].data_ptr(), o["desc"].data_ptr(), small, o["cnt"].data_ptr()))
+            with pytest.raises(orbx.OrbxError) as e:
+                ex.sync()
+            got[first].append(str(e.value))
+            assert o["cnt"].cpu().numpy().tolist() == [0, 0]
+        assert got[0] == got[1], got
+    finally:
+        ex.close()
+
+
 def test_capacity_flag_of_one_call_does_not_leak_into_the_next(built, oracle):
     """a device capacity flag raised by a multi-chunk host batch must not surface in a later, valid call"""
     import orbx
