@@ -225,6 +225,9 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(DescParams P, cons
 // one 7-tap column pass on that buffer: (sum + 32768) >> 16 — bit for bit the value cv::GaussianBlur leaves at that pixel.
 // Against blur + describe as two kernels this is ~3x fewer instructions and no blurred pyramid in HBM (no 2 x 2.85 MB per frame
 // written and re-read, no scattered DRAM gathers).  k_blur7 stays: orbx_get_blurred_level materialises levels with it on demand.
+#ifndef DESC_STRIDE
+#define DESC_STRIDE 3                // batches: rows per warp of the fused kernel (grid-stride walk)
+#endif
 #define DF_R 21
 #define DF_ROWS (2 * DF_R + 1)       // 43
 #define DF_PITCH 76                  // window tile pitch: 15 alignment bytes + 43 columns fit 64; 19 words: lanes on consecutive rows (IC_Angle) hit 32
@@ -267,36 +270,33 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe_fused(DescParams P
     const int f = blockIdx.y;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int nl = G->nlevels;
-    const int slot = blockIdx.x * DESC_WARPS + wid;                    // output row
-    int gidx = slot;                                                   // index in the frame's selected list (levels concatenated)
-    if (P.map) {
-        // filter-first order: k_keep_list has applied the depth / box filter to the selected POSITIONS and left the survivors' indices, in
-        // order, with their count — only those get an angle and a descriptor, straight into their final rows
-        if (slot >= P.counts[f]) return;
-        gidx = P.map[(size_t)f * P.map_slab + slot];
-    }
-    // locate (level, index in level): levels are concatenated in order (ORBextractor.cpp:1123).  Lane l holds level l's count; an
-    // inclusive warp scan gives the level boundaries, a ballot the level that contains keypoint gidx.
-    int level, k, total;
-    {
-        const int c = lane < nl ? P.nsel[f * nl + lane] : 0;
-        int incl = c;
+    // level boundaries of the frame's selected list: levels are concatenated in order (ORBextractor.cpp:1123).  Lane l holds level l's count; an
+    // inclusive warp scan gives the boundaries, a ballot (per keypoint, below) the level that contains list index gidx.
+    int incl = lane < nl ? P.nsel[f * nl + lane] : 0;
 #pragma unroll
-        for (int o = 1; o < ORBX_MAX_LEVELS; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-        total = __shfl_sync(0xffffffffu, incl, nl - 1);
-        level = __popc(__ballot_sync(0xffffffffu, lane < nl && incl <= gidx));
-        const int before = __shfl_sync(0xffffffffu, incl, max(level - 1, 0));
-        k = gidx - (level > 0 ? before : 0);
-        if (level >= nl) level = -1;
-    }
-    if (!P.map) {
-        if (gidx == 0 && lane == 0) {
+    for (int o = 1; o < ORBX_MAX_LEVELS; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    const int total = __shfl_sync(0xffffffffu, incl, nl - 1);
+    int nrows = total;                                                 // output rows of this frame
+    if (P.map) nrows = P.counts[f];                                    // filter-first order: k_keep_list has applied the depth / box filter to the selected
+                                                                       // POSITIONS and left the survivors' list indices, in order, with their count — only
+                                                                       // those get an angle and a descriptor, straight into their final rows
+    else {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
             P.counts[f] = total <= P.cap ? total : 0;
             if (total > P.cap) atomicOr(P.status, ORBX_DS_KP_OVERFLOW);
         }
         if (total > P.cap) return;
     }
-    if (level < 0) return;
+    uint8_t *tile = s_all + wid * DF_WARP_BYTES + 16;                              // 16 bytes of slack on either side of the tile
+    uint16_t *rows = reinterpret_cast<uint16_t *>(tile + DF_ROWS * DF_PITCH + 16);
+    // a warp walks the frame's rows with the grid's stride (the launch holds about a third of the rows' worth of warps per frame: fewer, longer
+    // CTAs, and none that finds nothing to do)
+    for (int slot = blockIdx.x * DESC_WARPS + wid; slot < nrows; slot += gridDim.x * DESC_WARPS) {
+    const int gidx = P.map ? P.map[(size_t)f * P.map_slab + slot] : slot;        // index in the frame's selected list
+    const int level = __popc(__ballot_sync(0xffffffffu, lane < nl && incl <= gidx));
+    if (level >= nl) break;                                                        // (a list index past the list: cannot happen)
+    const int before = __shfl_sync(0xffffffffu, incl, max(level - 1, 0));
+    const int k = gidx - (level > 0 ? before : 0);
     const LevelGeom &g = G->lv[level];
     const uint32_t c = P.sel[(size_t)f * P.sel_slab + g.sel_off + k];
     // pt += (minBorderX, minBorderY) — ORBextractor.cpp:886-887; integer-valued, cvRound is the identity
@@ -306,8 +306,6 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe_fused(DescParams P
     else { img = P.pyr + (size_t)f * P.pyr_slab + g.off; step = g.pitch; }
     const int w = g.w, hgt = g.h;
 
-    uint8_t *tile = s_all + wid * DF_WARP_BYTES + 16;                              // 16 bytes of slack on either side of the tile
-    uint16_t *rows = reinterpret_cast<uint16_t *>(tile + DF_ROWS * DF_PITCH + 16);
     // ---- stage the window: image columns from a 16-byte boundary, rows cy-21 .. cy+21 (mirrored outside the level) ----
     const int xw = cx - DF_R;                                                      // window column 0
     const int ax = xw & 15, xal = xw - ax;                                         // its byte in the tile; image column of tile byte 0 (may be -16)
@@ -429,6 +427,8 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe_fused(DescParams P
         kp.octave = level; kp.class_id = -1;
         P.kps[(size_t)f * P.cap + slot] = kp;
     }
+    __syncwarp();                                                                  // the tile and the row sums are rewritten by the next keypoint
+    }
 }
 
 void launch_describe_to(orbx_handle *h, int nframes, const uint8_t *l0, size_t l0_step, size_t l0_fstride,
@@ -443,8 +443,10 @@ void launch_describe_to(orbx_handle *h, int nframes, const uint8_t *l0, size_t l
     P.kps = d_kps; P.desc = d_desc; P.cap = cap; P.counts = d_counts; P.status = h->d_status;
     const int maxk = h->geo.sel_entries < cap ? h->geo.sel_entries : cap;
     dim3 grid((maxk + DESC_WARPS - 1) / DESC_WARPS, nframes);
+    // fused kernel: warps stride over the frame's rows; a third of the CTAs for batches, one warp per row when few frames must fill the machine
+    dim3 gridf(nframes >= 16 ? (grid.x + DESC_STRIDE - 1) / DESC_STRIDE : grid.x, nframes);
     ProfScope ps(h, ORBX_K_DESCRIBE);
-    if (h->opt_fused_blur) orbx_launch_pdl(h, k_describe_fused, grid, dim3(DESC_WARPS * 32), 0, h->stream, P, (const FrameGeom *)h->d_geo);
+    if (h->opt_fused_blur) orbx_launch_pdl(h, k_describe_fused, gridf, dim3(DESC_WARPS * 32), 0, h->stream, P, (const FrameGeom *)h->d_geo);
     else k_describe<<<grid, DESC_WARPS * 32, 0, h->stream>>>(P, h->d_geo);
 }
 
