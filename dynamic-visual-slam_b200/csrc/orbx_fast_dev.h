@@ -89,7 +89,9 @@ template <int TP> __device__ __noinline__ uint2 fast_sweep7(const uint32_t *q, u
 // Two-pair sweep: the vertical pair (0,8) and the horizontal pair (4,12) only.  On textured frames they alone reject 97.5 % of the pixels
 // (all four: 97.8 %), for half the arithmetic: a row needs its own word plus the two 3-byte-shifted views when it is the centre row,
 // and the vertical difference |I(y+3) - I(y)| of a row serves the centres y and y+3 (it is kept three rows).
-template <int TP> __device__ __noinline__ uint2 fast_sweep7(const uint32_t *q, uint32_t HM, uint32_t KK, int R)
+// RR > 0: the unit height as a compile-time constant — the row loop is then straight-line code (no exit test per row), so the loads and the
+// SWAR chains of different rows interleave; RR = 0: any height up to FAST_RMAX, one exit test per row.
+template <int TP, int RR> __device__ __forceinline__ uint2 fast_sweep7_body(const uint32_t *q, uint32_t HM, uint32_t KK, int R)
 {
     uint32_t c[7], dv[3];                                                        // c: rows k..k+6 (mod 7); dv[j % 3] = |C(j+3) - C(j)|
 #pragma unroll
@@ -98,8 +100,8 @@ template <int TP> __device__ __noinline__ uint2 fast_sweep7(const uint32_t *q, u
     for (int j = 0; j < 3; j++) dv[j] = __vabsdiffu4(c[j + 3], c[j]);
     uint32_t fl0 = 0u, fl1 = 0u;
 #pragma unroll
-    for (int k = 0; k < FAST_RMAX; k++) {
-        if (k >= R) break;
+    for (int k = 0; k < (RR > 0 ? RR : FAST_RMAX); k++) {
+        if (RR == 0 && k >= R) break;
         const uint32_t *row = q + (k + 3) * (TP / 4);                            // the centre row of detection row k
         const uint32_t L = row[-1], Rw = row[1];
         c[(k + 6) % 7] = q[(k + 6) * (TP / 4)];
@@ -114,6 +116,19 @@ template <int TP> __device__ __noinline__ uint2 fast_sweep7(const uint32_t *q, u
         else fl1 |= (acc >> (k - 8)) & (0x80808080u >> (k - 8));
     }
     return make_uint2(fl0, fl1);
+}
+#ifndef FAST_FIXED_R
+#define FAST_FIXED_R 1               // 1: straight-line instances for the unit heights of ~36-row cells (12, 13); 0: the generic loop only
+#endif
+template <int TP, int RR> __device__ __noinline__ uint2 fast_sweep7_fixed(const uint32_t *q, uint32_t HM, uint32_t KK) { return fast_sweep7_body<TP, RR>(q, HM, KK, RR); }
+template <int TP> __device__ __noinline__ uint2 fast_sweep7_any(const uint32_t *q, uint32_t HM, uint32_t KK, int R) { return fast_sweep7_body<TP, 0>(q, HM, KK, R); }
+template <int TP> __device__ __forceinline__ uint2 fast_sweep7(const uint32_t *q, uint32_t HM, uint32_t KK, int R)
+{
+#if FAST_FIXED_R
+    if (R == 12) return fast_sweep7_fixed<TP, 12>(q, HM, KK);                   // R is uniform over the warp (a property of the cell)
+    if (R == 13) return fast_sweep7_fixed<TP, 13>(q, HM, KK);
+#endif
+    return fast_sweep7_any<TP>(q, HM, KK, R);
 }
 #endif
 
