@@ -5,6 +5,7 @@ W, H, CAP = 1280, 720, 1280
 dev = torch.device("cuda", 0)
 ex = orbx.ORBextractor(max_width=W, max_height=H, max_batch=1, max_keypoints=CAP)
 L, hnd = ex.L, ex.handle
+if 'describe-all' in sys.argv: ex.set_filter_first(False)          # ORBX_OPT_FILTER_FIRST = 0 (the reference's order)
 gray = torch.empty((1, H, W), dtype=torch.uint8, device=dev); depth = torch.empty((1, H, W), dtype=torch.int16, device=dev)
 ex._check(L.orbx_synth_gray_device(hnd, 7, 0, 1, W, H, gray.data_ptr(), W, W * H))
 ex._check(L.orbx_synth_depth_device(hnd, 7, 0, 1, W, H, depth.data_ptr(), 2 * W, 2 * W * H))
@@ -25,3 +26,12 @@ t0 = time.perf_counter()
 for _ in range(200): step()
 ex.sync()
 print("back-to-back per frame %.1f us" % ((time.perf_counter() - t0) / 200 * 1e6))
+
+# the blocking host call (pinned host buffers in, host arrays out): what bench.py reports as `latency`
+orc_frames = gray.cpu().numpy(); orc_depth = depth.cpu().numpy().view(np.uint16)
+ex.track_reset()
+for _ in range(20): ex.track_batch(orc_frames, orc_depth, cap=CAP)
+ts = []
+for _ in range(300):
+    t0 = time.perf_counter(); ex.track_batch(orc_frames, orc_depth, cap=CAP); ts.append((time.perf_counter() - t0) * 1e6)
+print("host call, batch 1: p50 %.1f us, p95 %.1f us" % (np.percentile(ts, 50), np.percentile(ts, 95)))
