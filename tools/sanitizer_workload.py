@@ -17,4 +17,12 @@ k2, d2 = e2(g, cap=8192)
 db = orbx.LandmarkDB(ex, 4096)
 rows = co.synth_descriptors(1, 0, 3000); db.append(rows); db.set_positions(np.random.default_rng(2).standard_normal((3000, 3)).astype(np.float32) + [0, 0, 3])
 a = db.associate(rows[:50], np.full((50, 2), 300, np.float32), orbx.LandmarkDB.pose(np.eye(3), np.zeros(3), 600, 600, 320, 240))
+# a batch large enough for the strided descriptor grid (>= 16 frames), filter first and the reference's order, depth + per-frame boxes
+e3 = orbx.ORBextractor(max_width=w, max_height=h, max_batch=16)
+f16 = np.stack([co.synth_gray(5, f, w, h) for f in range(16)]); d16 = np.stack([co.synth_depth(5, f, w, h) for f in range(16)])
+b16 = [co.synth_boxes(5, f, w, h) for f in range(16)]
+o1 = e3.track_batch(f16, d16, frame_boxes=b16, drop_class_mask=1)
+e3.set_filter_first(False); e3.track_reset()
+o0 = e3.track_batch(f16, d16, frame_boxes=b16, drop_class_mask=1)
+assert all(np.array_equal(a, b) for a, b in zip(o1, o0))
 print("sanitizer workload ok", len(k), len(k2), out[2].tolist(), int((a["landmark"] >= 0).sum()))
