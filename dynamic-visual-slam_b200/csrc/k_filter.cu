@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(1024) k_keep_list(KeepListParams P, const Fram
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        if (s_base > P.cap_out || s_base > P.map_slab) { atomicOr(P.status, ORBX_DS_KP_OVERFLOW); P.nout[f] = 0; }
+        // (n > map_slab: more selected keypoints than the handle's max_keypoints — the reference's order reports that from the descriptor kernel)
+        if (s_base > P.cap_out || n > P.map_slab) { atomicOr(P.status, ORBX_DS_KP_OVERFLOW); P.nout[f] = 0; }
         else P.nout[f] = s_base;
     }
 }

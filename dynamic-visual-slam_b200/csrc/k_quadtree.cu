@@ -19,6 +19,9 @@
 // block size NT is a template parameter: 256 threads when the batch fills the machine with CTAs (one per frame x level), 1024
 // for small batches, where the kernel is a chain of dependent global-memory passes and wider blocks shorten every pass
 #define QT_NONE 0xFFFFu
+#ifndef QT_BATCH_THREADS
+#define QT_BATCH_THREADS 256         // block size when the batch fills the machine with CTAs (measured: 128 / 512 in DESIGN.md)
+#endif
 
 struct QtParams {
     uint32_t *candA, *candB;     // per-frame slabs of packed candidates
@@ -349,7 +352,10 @@ int launch_quadtree_geo(orbx_handle *h, const FrameGeom *d_geo, int nlevels, int
     dim3 grid(nframes, nlevels);
     ProfScope ps(h, ORBX_K_QUADTREE);
     if (wide) orbx_launch_pdl(h, k_quadtree<1024>, grid, dim3(1024), smem, h->stream, P, d_geo);
-    else orbx_launch_pdl(h, k_quadtree<256>, grid, dim3(256), smem, h->stream, P, d_geo);
+    else {
+        if (!orbx_optin_smem(h, (const void *)k_quadtree<QT_BATCH_THREADS>, smem)) return -1;
+        orbx_launch_pdl(h, k_quadtree<QT_BATCH_THREADS>, grid, dim3(QT_BATCH_THREADS), smem, h->stream, P, d_geo);
+    }
     return 0;
 }
 
