@@ -115,3 +115,16 @@ def test_product_does_not_link_the_oracle(built):
                 assert set(re.findall(r'"([\w.]+\.so[\w.]*)"', code)) == {"libnccl.so.2", "libnccl.so"}, f
             else:
                 assert "dlopen" not in code, f
+
+
+def test_option_numbers_of_the_binding_match_the_header():
+    """every ORBX_OPT_* of include/orbx.h has its own number, and the ctypes mirror's set_* helpers pass exactly those numbers"""
+    hdr = open(os.path.join(ROOT, "include", "orbx.h")).read()
+    opts = {name: int(num) for name, num in re.findall(r"#define\s+ORBX_OPT_(\w+)\s+(\d+)", hdr)}
+    assert len(set(opts.values())) == len(opts) >= 8 and opts["FILTER_FIRST"] == 8
+    src = open(os.path.join(ROOT, "dynamic-visual-slam_b200", "python", "orbx", "__init__.py")).read()
+    used = {}
+    for meth, doc_opt, num in re.findall(r"def (set_\w+)\(self[^\n]*\n\s+\"\"\"ORBX_OPT_(\w+):.*?orbx_set_option\(self\._h, (\d+),", src, flags=re.S):
+        used[doc_opt] = int(num)
+    assert used and all(opts[k] == v for k, v in used.items()), (opts, used)
+    assert set(used) == set(opts), (sorted(set(opts) - set(used)), "options without a helper in the binding")
