@@ -24,5 +24,9 @@ b16 = [co.synth_boxes(5, f, w, h) for f in range(16)]
 o1 = e3.track_batch(f16, d16, frame_boxes=b16, drop_class_mask=1)
 e3.set_filter_first(False); e3.track_reset()
 o0 = e3.track_batch(f16, d16, frame_boxes=b16, drop_class_mask=1)
-assert all(np.array_equal(a, b) for a, b in zip(o1, o0))
+assert np.array_equal(o1[2], o0[2]) and np.array_equal(o1[4], o0[4]), "counts differ between the two filter orders"
+for f in range(16):                                   # rows past a frame's count are not defined: compare the valid ones
+    n, nm = int(o1[2][f]), int(o1[4][f])
+    assert np.array_equal(o1[0][f, :n].view(np.uint8), o0[0][f, :n].view(np.uint8)) and np.array_equal(o1[1][f, :n], o0[1][f, :n]), ("keypoints / descriptors", f)
+    assert np.array_equal(o1[3][f, :nm].view(np.uint8), o0[3][f, :nm].view(np.uint8)), ("matches", f)
 print("sanitizer workload ok", len(k), len(k2), out[2].tolist(), int((a["landmark"] >= 0).sum()))
