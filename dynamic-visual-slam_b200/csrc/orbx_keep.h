@@ -1,5 +1,5 @@
-// orbx_keep.h — the post-selection keep test of a keypoint, shared by k_filter (the stable compaction) and k_describe_fused (which
-// skips the descriptor work of keypoints the compaction is going to drop).  ONE function, so both kernels take the same decision:
+// orbx_keep.h — the post-selection keep test of a keypoint, shared by k_filter (stable compaction of described rows, the reference's order) and
+// k_keep_list (the same test on the selected positions, before any descriptor work).  ONE function, so both orders take the same decision:
 //   * Frontend::isValidDepth / filterDepth (reference frontend.cpp:457-473, 503-527): keep iff x = round(pt.x), y = round(pt.y) (half away
 //     from zero) lies inside the depth image and d = depth_u16 * 0.001f satisfies depth_min <= d <= depth_max;
 //   * Backend::categorizeObservation + filtered_objects_ (backend.cpp:1011-1029, 746-751): the first box containing the pixel (inclusive
@@ -13,19 +13,12 @@ struct KeepParams {
     const orbx_box *boxes; const int32_t *box_offsets; int box_base; int nboxes; unsigned long long drop_mask;   // box_offsets (nullable): frame f owns boxes [off[f], off[f+1])
 };
 
-// The test in two halves, so that a caller can put independent work between the depth load and its first use:
-// orbx_keep_fetch = the depth sample (-1: the rounded position is outside the depth image, 0 without a depth test), orbx_keep_decide = the verdict.
-__device__ __forceinline__ int orbx_keep_fetch(const KeepParams &P, int f, float kx, float ky)
-{
-    if (!P.depth) return 0;
-    const int x = (int)roundf(kx), y = (int)roundf(ky);
-    if (x < 0 || y < 0 || x >= P.dw || y >= P.dh) return -1;
-    return (int)*(const uint16_t *)((const uint8_t *)P.depth + (size_t)f * P.dfstride + (size_t)y * P.dstep + (size_t)x * 2);
-}
-__device__ __forceinline__ bool orbx_keep_decide(const KeepParams &P, int f, float kx, float ky, int raw)
+__device__ __forceinline__ bool orbx_keep(const KeepParams &P, int f, float kx, float ky)
 {
     if (P.depth) {
-        if (raw < 0) return false;
+        const int x = (int)roundf(kx), y = (int)roundf(ky);
+        if (x < 0 || y < 0 || x >= P.dw || y >= P.dh) return false;
+        const uint16_t raw = *(const uint16_t *)((const uint8_t *)P.depth + (size_t)f * P.dfstride + (size_t)y * P.dstep + (size_t)x * 2);
         const float d = __fmul_rn((float)raw, 0.001f);
         if (d < P.dmin || d > P.dmax) return false;
     }
@@ -39,8 +32,4 @@ __device__ __forceinline__ bool orbx_keep_decide(const KeepParams &P, int f, flo
         }
     }
     return true;
-}
-__device__ __forceinline__ bool orbx_keep(const KeepParams &P, int f, float kx, float ky)
-{
-    return orbx_keep_decide(P, f, kx, ky, orbx_keep_fetch(P, f, kx, ky));
 }
